@@ -1,0 +1,52 @@
+"""CPU parity oracle loader — TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
+reference legs may import this package.  kueue_b200/ never does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+def build(force: bool = False) -> str:
+    so = os.path.join(_HERE, "libkueue_oracle.so")
+    src = os.path.join(_HERE, "kueue_oracle.cpp")
+    hdr = os.path.join(_HERE, "..", "include", "kueue_b200.h")
+    stale = (not os.path.exists(so)) or any(os.path.getmtime(so) < os.path.getmtime(p) for p in (src, hdr))
+    if force or stale:
+        subprocess.check_call(["make", "-s", "-C", _HERE, "-B", "libkueue_oracle.so"])
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = C.CDLL(build())
+        _LIB.ko_tree_eval.restype = C.c_int32
+        _LIB.ko_run_cycle.restype = C.c_int32
+        _LIB.ko_get_targets.restype = C.c_int32
+    return _LIB
+
+
+def tree_eval(snap):
+    from kueue_b200 import abi
+    out = abi.TreeOut(snap)
+    s = snap.as_struct()
+    rc = lib().ko_tree_eval(C.byref(s), C.byref(out.struct))
+    assert rc == 0
+    return out
+
+
+def run_cycle(snap, tgt_capacity=None):
+    from kueue_b200 import abi
+    out = abi.CycleOut(snap, tgt_capacity)
+    s = snap.as_struct()
+    rc = lib().ko_run_cycle(C.byref(s), C.byref(out.struct))
+    assert rc == 0, rc
+    out.n_targets = out.struct.n_targets
+    return out
