@@ -33,11 +33,16 @@ def lib():
     return _LIB
 
 
-def tree_eval(snap):
+def tree_eval(snap, wl_req=None):
+    import numpy as np
     from kueue_b200 import abi
     out = abi.TreeOut(snap)
     s = snap.as_struct()
-    rc = lib().ko_tree_eval(C.byref(s), C.byref(out.struct))
+    if wl_req is not None:
+        wl_req = np.ascontiguousarray(wl_req, np.int64)
+        rc = lib().ko_tree_eval_req(C.byref(s), wl_req.ctypes.data_as(C.POINTER(C.c_int64)), C.byref(out.struct))
+    else:
+        rc = lib().ko_tree_eval(C.byref(s), C.byref(out.struct))
     assert rc == 0
     return out
 

@@ -260,14 +260,36 @@ class Oracle {
     return {height[rootOf(cq)], false};
   }
 
+  // Is fr a key of node n's SubtreeQuota map?  CQs: defined by their ResourceGroups
+  // (resource.go:52-75); cohorts: own quota (approximated as any non-default cell) or
+  // any child's (accumulateFromChild resource_node.go:210-213).  Only the wlReq test
+  // path of dominantResourceShare can observe this.
+  bool frDefined(int n, int fr) {
+    if (n < Q) {
+      int f = fr / R, r = fr % R;
+      for (int g = s.cq_rg_start[n]; g < s.cq_rg_start[n + 1]; g++) {
+        if (!(s.rg_res_mask[g] & (1u << r))) continue;
+        for (int k = s.rg_flavor_start[g]; k < s.rg_flavor_start[g + 1]; k++) if (s.rg_flavors[k] == f) return true;
+      }
+      return false;
+    }
+    size_t i = (size_t)n * FR + fr;
+    if (s.nominal[i] != 0 || s.borrow_limit[i] != KB_NO_LIMIT || s.lend_limit[i] != KB_NO_LIMIT) return true;
+    for (int ch : childCohorts[n]) if (frDefined(ch, fr)) return true;
+    for (int ch : childCqs[n]) if (frDefined(ch, fr)) return true;
+    return false;
+  }
+
   // ---- fair_sharing.go ----------------------------------------------------
-  DRS dominantResourceShare(int n) {  // :126-156 with wlReq == nil
+  DRS dominantResourceShare(int n, const i64 *wlReq = nullptr) {  // :126-156
     DRS drs; drs.fairWeight = s.fair_weight[n];
     if (!hasParent(n)) return drs;
     i64 borrowing[KB_MAX_RESOURCES]; bool any = false;
     for (int r = 0; r < R; r++) borrowing[r] = 0;
     for (int fr = 0; fr < FR; fr++) {
-      i64 amountBorrowed = U(n, fr) - Sub(n, fr);
+      // wlReq only counts on FlavorResources that are keys of the node's SubtreeQuota
+      // map (`for fr, quota := range SubtreeQuota`, :133); the scheduler always passes nil.
+      i64 amountBorrowed = ((wlReq && frDefined(n, fr)) ? wlReq[fr] : 0) + U(n, fr) - Sub(n, fr);
       if (amountBorrowed > 0) { borrowing[fr % R] += amountBorrowed; any = true; }
     }
     if (!any) return drs;
@@ -1040,7 +1062,9 @@ class Oracle {
 extern "C" {
 
 // K1 parity surface: SubtreeQuota / Usage / Available / PotentialAvailable / DRS.
-int32_t ko_tree_eval(const kb_snapshot *s, kb_tree_out *out) {
+// wl_req: optional [F*R] request added to every node's usage when computing DRS
+// (the wlReq argument of dominantResourceShare, fair_sharing.go:126).
+int32_t ko_tree_eval_req(const kb_snapshot *s, const int64_t *wl_req, kb_tree_out *out) {
   Oracle o(*s);
   size_t n = (size_t)o.N * o.FR;
   if (out->subtree_quota) memcpy(out->subtree_quota, o.subtree.data(), n * sizeof(i64));
@@ -1051,13 +1075,15 @@ int32_t ko_tree_eval(const kb_snapshot *s, kb_tree_out *out) {
       if (out->potential_available) out->potential_available[(size_t)q * o.FR + fr] = o.potentialAvailable(q, fr);
     }
   for (int nd = 0; nd < o.N; nd++) {
-    DRS d = o.dominantResourceShare(nd);
+    DRS d = o.dominantResourceShare(nd, wl_req);
     if (out->drs_rounded) out->drs_rounded[nd] = Oracle::roundedWeightedShare(d);
     if (out->drs_resource) out->drs_resource[nd] = d.dominantResource;
     if (out->drs_borrowing) out->drs_borrowing[nd] = d.borrowing;
   }
   return 0;
 }
+
+int32_t ko_tree_eval(const kb_snapshot *s, kb_tree_out *out) { return ko_tree_eval_req(s, nullptr, out); }
 
 int32_t ko_run_cycle(const kb_snapshot *s, kb_cycle_out *out) {
   Oracle o(*s);
