@@ -1,0 +1,248 @@
+#!/usr/bin/env python3
+"""bench.py — admission decisions/sec of the batched scheduling-cycle evaluator.
+
+    python bench.py --gpus N --steps K --warmup W [--config 2] [--impl reference]
+
+One "step" = one pass of the hot path (tree pass -> nominate -> group -> ordered
+admit) over one synthetic snapshot of BASELINE.json's configuration, every pending
+workload evaluated as an entry of the cycle (the north star's batched evaluator).
+`value` = decisions/sec with the snapshot already resident in HBM (device time from
+CUDA events on the library's launching stream, L2 flushed between steps); `e2e` =
+the same metric through the reference-facing C-ABI call kb_run_cycle with host
+buffers (host -> device copies, kernels, device -> host copies all inside the timed
+region).  N > 1: each rank evaluates its own snapshot shard (root cohorts are
+independent, so there is no data-path collective) — weak scaling.
+
+--impl reference times the CPU restatement of the reference's cycle (oracle/, the
+Go toolchain is absent so the Go scheduler itself cannot run here) on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "admission decisions/sec per scheduling cycle"
+UNIT = "decisions/s"
+WORKLOADS = {
+    1: "cfg1: 100 pending x 10 CQ x 2 flavors x 3 resources",
+    2: "cfg2: 100k pending x 1k ClusterQueues x 8 flavors x 4 resources, StrictFIFO, no borrowing",
+    3: "cfg3: 1M pending x 10k ClusterQueues, BestEffortFIFO + flat cohorts + DRF fair sharing",
+    4: "cfg4: 1M pending x 10k ClusterQueues, depth-4 hierarchical cohorts (classical order)",
+}
+
+
+def algorithmic_bytes(snap) -> dict:
+    """B = W_eval*(P*R*8 + 24) + W_eval*out_B + (Q+C)*FR*32 + (Q+C)*16."""
+    W = snap.n_heads
+    P = snap.n_podset / max(1, snap.n_wl)
+    R, FR, N = snap.n_resource, snap.n_fr, snap.n_nodes
+    nrg = snap.n_rg / max(1, snap.n_cq)
+    wl_in = W * (P * R * 8 + 24)
+    wl_out = W * (8 + P * nrg)
+    nodes = N * FR * 32 + N * 16
+    return {"nominate": wl_in + wl_out + nodes, "tree": nodes + N * FR * 16, "total": wl_in + wl_out + nodes}
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self._stop_evt = threading.Event()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                self.samples.append((float(out[0]), float(out[1])))
+                for n, v in zip(names, out[2:]):
+                    if v.strip().lower() == "active":
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=6)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(s[0] for s in self.samples)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.samples[0][1], "reasons": sorted(self.reasons)}
+
+
+def cpu_baseline(snap, budget_s: float = 12.0):
+    """Oracle (kind 'port') on one host core over repeated passes of the same snapshot."""
+    import oracle
+    oracle.run_cycle(snap)  # warm
+    n, t0 = 0, time.perf_counter()
+    while True:
+        oracle.run_cycle(snap)
+        n += 1
+        dt = time.perf_counter() - t0
+        if dt > budget_s or n >= 200:
+            break
+    return {"value": n * snap.n_heads / dt, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": f"{n} full passes of the same snapshot ({snap.n_heads} decisions each) in {dt:.1f} s, 1 thread "
+                      f"(the reference cycle is single-goroutine, scheduler.go:468)"}
+
+
+def run_reference(args, rank, world):
+    from kueue_b200 import synth
+    if rank != 0:
+        return
+    import oracle
+    snap = synth.make_snapshot(args.config)
+    for _ in range(args.warmup):
+        oracle.run_cycle(snap)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        oracle.run_cycle(snap)
+    dt = time.perf_counter() - t0
+    val = args.steps * snap.n_heads / dt
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "int64", "data": "synthetic",
+            "config": {"workload": WORKLOADS[args.config], "heads": "all pending workloads"},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "kind": "port",
+                             "sample": f"{args.steps} full passes ({snap.n_heads} decisions each); C++ restatement of "
+                                       "pkg/scheduler (Go toolchain absent), 1 thread like the reference's cycle"},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", type=int, default=2)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        return run_reference(args, rank, world)
+
+    import torch
+    import torch.distributed as dist
+    from kueue_b200 import abi, native, synth
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    # each rank owns its own shard of the cluster: independent root cohorts => no collective on the data path
+    snap = synth.make_snapshot(args.config, seed=args.config * 1000 + rank)
+    ev = native.Evaluator(local_rank)
+    out = abi.CycleOut(snap)
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- resident-input throughput (value) ----
+    ev.upload(snap)
+    ev.set_profile(True)
+    for _ in range(max(3, args.warmup)):
+        flush.zero_(); torch.cuda.synchronize()
+        ev.cycle_resident()
+    sampler = ClockSampler(local_rank); sampler.start()
+    barrier()
+    t_wall0 = time.perf_counter()
+    dev_ms = 0.0
+    kms = np.zeros(8)
+    launches = 0
+    for _ in range(args.steps):
+        flush.zero_(); torch.cuda.synchronize()  # L2 flush between timed iterations
+        ev.cycle_resident()
+        st = ev.stats()
+        dev_ms += st.last_cycle_gpu_ms
+        kms += np.array(list(st.kernel_ms))
+        launches += st.kernel_launches
+    barrier()
+    wall_ms = (time.perf_counter() - t_wall0) * 1e3
+    clocks = sampler.stop()
+    ev.set_profile(False)
+
+    # ---- end-to-end through the C-ABI with host buffers (e2e) ----
+    for _ in range(2):
+        ev.run_cycle(snap, out)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ev.run_cycle(snap, out)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    st = ev.stats()
+    h2d, d2h = int(st.h2d_bytes), int(st.d2h_bytes)
+
+    t = torch.tensor([dev_ms, e2e_s, float(snap.n_heads)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        dev_ms, e2e_s, total_dec = tmax[0].item(), tmax[1].item(), tsum[2].item()
+    else:
+        total_dec = float(snap.n_heads)
+    if rank == 0:
+        ms_per_step = dev_ms / args.steps
+        value = total_dec / (ms_per_step / 1e3)
+        e2e = total_dec * args.steps / e2e_s
+        ab = algorithmic_bytes(snap)
+        top = int(np.argmax(kms))
+        top_ms = kms[top] / args.steps
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        kname = abi.KERNEL_NAMES[top]
+        kbytes = ab["nominate"] if kname == "k_nominate" else (ab["tree"] if kname in ("k_tree", "k_lone") else ab["total"])
+        achieved = kbytes / (top_ms / 1e3) / 1e9 if top_ms > 0 else 0.0
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int64", "data": "synthetic",
+            "config": {"workload": WORKLOADS[args.config], "heads": "all pending workloads (batched evaluator)",
+                       "decisions_per_step_per_gpu": snap.n_heads, "l2": "512 MiB flush buffer written between timed steps",
+                       "timing": "CUDA events on the library stream around the cycle's kernels, summed over steps, max over ranks",
+                       "wall_ms_per_step_incl_flush": wall_ms / args.steps},
+            "clocks": clocks,
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": launches,
+            "kernel_ms_per_step": {abi.KERNEL_NAMES[i]: kms[i] / args.steps for i in range(8) if kms[i] > 0},
+            "roofline": {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak if peak else None, "traffic": None,
+                         "algorithmic_bytes_per_launch": kbytes, "kernel_ms": top_ms,
+                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)"},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(snap)
+        print(json.dumps(line))
+    ev.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

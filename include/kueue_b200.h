@@ -37,6 +37,7 @@ extern "C" {
 #define KB_MAX_RESOURCES 16   /* n_resource <= 16  */
 #define KB_MAX_FLAVORS   64   /* n_flavor   <= 64 (eligibility bitmask is u64) */
 #define KB_MAX_DEPTH     16   /* CQ -> root path length <= 16 */
+#define KB_N_KERNELS     8
 
 typedef enum kb_status {
   KB_OK = 0,
@@ -189,13 +190,13 @@ typedef struct kb_cycle_out {
   int32_t *borrow;       /* [n_heads] Assignment.Borrowing (flavorassigner.go:128)      */
   int32_t *commit_rank;  /* [n_heads] position in the iterator order among the entries of
                             the same ROOT cohort (scheduler.go:778-817 / tournament)     */
-  /* per podset of the head workloads: row = entry_ps_start[entry] + podset,
-   * entry_ps_start is the exclusive prefix sum of the heads' podset counts. */
-  int8_t  *ps_flavor;    /* [head podsets][R] assigned global flavor idx or -1
+  /* per podset, indexed like the INPUT podset tables: row = wl_ps_start[wl] + podset
+   * for wl = heads[entry].  Rows of workloads that are not heads are left untouched. */
+  int8_t  *ps_flavor;    /* [n_podset][R] assigned global flavor idx or -1
                             (PodSetAssignment.Flavors, flavorassigner.go:262-273)        */
-  int8_t  *ps_res_mode;  /* [head podsets][R] FlavorAssignment.Mode or -1               */
-  int8_t  *ps_tried_idx; /* [head podsets][R] FlavorAssignment.TriedFlavorIdx (-1 none) */
-  int32_t *ps_count;     /* [head podsets] admitted Count (partial admission)           */
+  int8_t  *ps_res_mode;  /* [n_podset][R] FlavorAssignment.Mode or -1                   */
+  int8_t  *ps_tried_idx; /* [n_podset][R] FlavorAssignment.TriedFlavorIdx (-1 none)     */
+  int32_t *ps_count;     /* [n_podset] admitted Count (partial admission)               */
   /* preemption targets, CSR by entry (preemption.go:111-115) */
   int32_t *tgt_start;    /* [n_heads+1]                                                 */
   int32_t *tgt_adm;      /* [tgt_capacity] index into admitted tables                   */
@@ -223,7 +224,14 @@ typedef struct kb_stats {
   int64_t h2d_bytes, d2h_bytes;  /* of the last call                                     */
   int32_t kernel_launches;       /* kernels of this library launched by the last call    */
   int32_t sm_count;
+  /* per-kernel device time of the last kb_cycle_resident when kb_set_profile(h, 1):
+   * CUDA events recorded on the launching stream around each kernel. */
+  float   kernel_ms[KB_N_KERNELS];
 } kb_stats;
+
+/* indices into kb_stats.kernel_ms */
+enum { KB_K_TREE = 0, KB_K_LONE = 1, KB_K_NOMINATE = 2, KB_K_SCAN = 3, KB_K_SCATTER = 4,
+       KB_K_ADMIT = 5, KB_K_FAIR = 6, KB_K_PREEMPT = 7 };
 
 typedef struct kb_handle kb_handle;
 
@@ -258,6 +266,7 @@ int32_t kb_cycle_resident(kb_handle *h);
 int32_t kb_download(kb_handle *h, kb_cycle_out *out);
 
 int32_t kb_get_stats(const kb_handle *h, kb_stats *out);
+int32_t kb_set_profile(kb_handle *h, int32_t on);  /* per-kernel event timing on/off */
 
 #ifdef __cplusplus
 }

@@ -94,7 +94,11 @@ class kb_stats(C.Structure):
     _fields_ = [
         ("last_cycle_gpu_ms", C.c_double), ("last_h2d_ms", C.c_double), ("last_d2h_ms", C.c_double),
         ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64), ("kernel_launches", C.c_int32), ("sm_count", C.c_int32),
+        ("kernel_ms", C.c_float * 8),
     ]
+
+
+KERNEL_NAMES = ["k_tree", "k_lone", "k_nominate", "k_scan_roots", "k_scatter", "k_admit", "k_fair", "k_preempt"]
 
 
 class kb_config(C.Structure):
@@ -241,7 +245,7 @@ class CycleOut:
 
     def __init__(self, snap: FlatSnapshot, tgt_capacity: int | None = None, with_usage: bool = True):
         H, R = snap.n_heads, snap.n_resource
-        HP = snap.head_podsets()
+        HP = snap.n_podset
         cap = tgt_capacity if tgt_capacity is not None else max(16, 4 * snap.n_adm + 16)
         self.decision = np.zeros(H, np.uint8)
         self.mode = np.zeros(H, np.uint8)
@@ -255,8 +259,6 @@ class CycleOut:
         self.tgt_adm = np.zeros(cap, np.int32)
         self.tgt_reason = np.zeros(cap, np.uint8)
         self.node_usage = np.zeros((snap.n_nodes, snap.n_fr), np.int64) if with_usage else None
-        st = snap.arrays["wl_ps_start"]; h = snap.arrays["heads"]
-        self.entry_ps_start = np.concatenate([[0], np.cumsum(st[h + 1] - st[h])]).astype(np.int64) if H else np.zeros(1, np.int64)
         s = kb_cycle_out()
         s.decision = _ptr(self.decision, C.c_uint8); s.mode = _ptr(self.mode, C.c_uint8)
         s.borrow = _ptr(self.borrow, C.c_int32); s.commit_rank = _ptr(self.commit_rank, C.c_int32)

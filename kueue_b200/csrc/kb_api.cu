@@ -1,0 +1,422 @@
+// kb_api.cu — C-ABI of libkueue_b200 (include/kueue_b200.h): handle, snapshot upload
+// (host -> HBM, plus the static topology tables the kernels need), cycle launch,
+// result download.  One handle = one CUDA device + one stream; calls are blocking and
+// not re-entrant per handle (SURVEY.md §8b threading row).
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "kb_kernels.cuh"
+
+#define KB_VERSION 100
+
+namespace {
+
+struct Arena {  // grow-only device arena, 256 B aligned sub-allocations
+  char *base = nullptr;
+  size_t cap = 0, used = 0;
+  void reset() { used = 0; }
+  bool reserve(size_t bytes) {
+    if (bytes <= cap) return true;
+    if (base) cudaFree(base);
+    base = nullptr; cap = 0;
+    size_t want = bytes + bytes / 4 + (1 << 20);
+    if (cudaMalloc(&base, want) != cudaSuccess) return false;
+    cap = want;
+    return true;
+  }
+  template <typename T> T *take(size_t n) {
+    size_t b = (n * sizeof(T) + 255) & ~(size_t)255;
+    if (b == 0) b = 256;
+    T *p = (T *)(base + used);
+    used += b;
+    return p;
+  }
+};
+inline size_t pad256(size_t b) { b = (b + 255) & ~(size_t)255; return b ? b : 256; }
+
+}  // namespace
+
+struct kb_handle {
+  int device = 0;
+  int sm_count = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
+  Arena arena;
+  DevSnap D{};
+  bool uploaded = false;
+  bool profile = false;
+  cudaEvent_t kev[KB_N_KERNELS + 1] = {};
+  int kev_id[KB_N_KERNELS + 1] = {};
+  int kev_n = 0;
+  std::string err;
+  kb_stats stats{};
+  // tree_eval scratch
+  i64 *d_drs_rounded = nullptr; int32_t *d_drs_res = nullptr; uint8_t *d_drs_borrowing = nullptr;
+  // host-side derived topology
+  std::vector<int32_t> root_slot, depth, height, tree_start, tree_nodes, tree_level, lone, cq_adm_start, cq_adm;
+};
+
+static thread_local std::string g_err;
+
+static int32_t fail(kb_handle *h, int32_t code, const std::string &msg) {
+  if (h) h->err = msg; else g_err = msg;
+  return code;
+}
+#define CUDA_TRY(h, expr)                                                                           \
+  do {                                                                                              \
+    cudaError_t _e = (expr);                                                                        \
+    if (_e != cudaSuccess) return fail(h, KB_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+  } while (0)
+
+extern "C" {
+
+int32_t kb_version(void) { return KB_VERSION; }
+
+const char *kb_last_error(const kb_handle *h) { return h ? h->err.c_str() : g_err.c_str(); }
+
+int32_t kb_alloc_pinned(void **ptr, uint64_t bytes) {
+  if (!ptr) return KB_ERR_INVALID;
+  cudaError_t e = cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocDefault);
+  if (e != cudaSuccess) { g_err = cudaGetErrorString(e); return KB_ERR_CUDA; }
+  return KB_OK;
+}
+int32_t kb_free_pinned(void *ptr) {
+  if (!ptr) return KB_OK;
+  return cudaFreeHost(ptr) == cudaSuccess ? KB_OK : KB_ERR_CUDA;
+}
+
+int32_t kb_create(const kb_config *cfg, kb_handle **out) {
+  if (!out) return KB_ERR_INVALID;
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(nullptr, KB_ERR_NO_DEVICE, "no CUDA device");
+  int dev = cfg ? cfg->device : 0;
+  if (dev < 0 || dev >= ndev) return fail(nullptr, KB_ERR_INVALID, "bad device ordinal");
+  kb_handle *h = new kb_handle();
+  h->device = dev;
+  if (cudaSetDevice(dev) != cudaSuccess) { delete h; return fail(nullptr, KB_ERR_CUDA, "cudaSetDevice failed"); }
+  cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, dev);
+  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return fail(nullptr, KB_ERR_CUDA, "stream"); }
+  cudaEventCreate(&h->ev0); cudaEventCreate(&h->ev1); cudaEventCreate(&h->ev2); cudaEventCreate(&h->ev3);
+  for (int i = 0; i <= KB_N_KERNELS; i++) cudaEventCreate(&h->kev[i]);
+  h->stats.sm_count = h->sm_count;
+  *out = h;
+  return KB_OK;
+}
+
+void kb_destroy(kb_handle *h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  if (h->arena.base) cudaFree(h->arena.base);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->ev2) cudaEventDestroy(h->ev2);
+  if (h->ev3) cudaEventDestroy(h->ev3);
+  for (int i = 0; i <= KB_N_KERNELS; i++) if (h->kev[i]) cudaEventDestroy(h->kev[i]);
+  delete h;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------
+// validation + static topology
+// ---------------------------------------------------------------------------
+static int32_t build_topology(kb_handle *h, const kb_snapshot *s) {
+  int Q = s->n_cq, C = s->n_cohort, N = Q + C;
+  if (Q < 0 || C < 0 || s->n_flavor < 1 || s->n_flavor > KB_MAX_FLAVORS || s->n_resource < 1 ||
+      s->n_resource > KB_MAX_RESOURCES || s->n_wl < 0 || s->n_podset < 0 || s->n_adm < 0 || s->n_heads < 0)
+    return fail(h, KB_ERR_INVALID, "bad dimensions");
+  if (s->n_flavor > 127) return fail(h, KB_ERR_INVALID, "flavor index must fit int8");
+  for (int n = 0; n < N; n++) {
+    int p = s->parent[n];
+    if (p != -1 && (p < Q || p >= N)) return fail(h, KB_ERR_INVALID, "parent must be a cohort node or -1");
+  }
+  h->depth.assign(N, -1);
+  h->root_slot.assign(N, -1);
+  std::vector<int32_t> root(N, -1);
+  for (int n = 0; n < N; n++) {  // depth + root with cycle detection (hierarchy/cycle.go:31-44)
+    int steps = 0, t = n;
+    while (s->parent[t] >= 0) {
+      t = s->parent[t];
+      if (++steps > KB_MAX_DEPTH) return fail(h, KB_ERR_INVALID, "cohort tree deeper than KB_MAX_DEPTH or cyclic");
+    }
+    h->depth[n] = steps;
+    root[n] = t;
+  }
+  // roots: every parentless node; slots in ascending node order
+  int nroots = 0;
+  std::vector<int32_t> slot_of_root(N, -1);
+  for (int n = 0; n < N; n++) if (s->parent[n] < 0) slot_of_root[n] = nroots++;
+  for (int n = 0; n < N; n++) h->root_slot[n] = slot_of_root[root[n]];
+  // children counts -> height (getNodeHeight hierarchical_preemption.go:202-208)
+  std::vector<int32_t> nchild(N, 0);
+  for (int n = 0; n < N; n++) if (s->parent[n] >= 0) nchild[s->parent[n]]++;
+  h->height.assign(N, 0);
+  for (int n = Q; n < N; n++) h->height[n] = std::min(nchild[n], 1);
+  {  // process cohorts by depth descending so children are final before parents
+    std::vector<int32_t> order;
+    for (int n = Q; n < N; n++) order.push_back(n);
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return h->depth[a] > h->depth[b]; });
+    for (int n : order) {
+      int p = s->parent[n];
+      if (p >= 0) h->height[p] = std::max(h->height[p], h->height[n] + 1);
+    }
+  }
+  // cohort-rooted trees: nodes grouped by root, ordered by depth ascending
+  std::vector<int32_t> tree_of_root(N, -1);
+  int ntrees = 0;
+  for (int n = Q; n < N; n++) if (s->parent[n] < 0) tree_of_root[n] = ntrees++;
+  std::vector<int32_t> cnt(ntrees + 1, 0);
+  h->lone.clear();
+  for (int n = 0; n < N; n++) {
+    int t = tree_of_root[root[n]];
+    if (t >= 0) cnt[t + 1]++;
+    else h->lone.push_back(n);  // parentless CQ
+  }
+  for (int t = 0; t < ntrees; t++) cnt[t + 1] += cnt[t];
+  h->tree_start.assign(cnt.begin(), cnt.end());
+  h->tree_nodes.assign(cnt[ntrees], 0);
+  h->tree_level.assign((size_t)ntrees * KB_LEVELS, 0);
+  {
+    // counting sort by (tree, depth)
+    std::vector<int32_t> lvlcnt((size_t)ntrees * KB_LEVELS, 0);
+    for (int n = 0; n < N; n++) { int t = tree_of_root[root[n]]; if (t >= 0) lvlcnt[(size_t)t * KB_LEVELS + h->depth[n] + 1]++; }
+    for (int t = 0; t < ntrees; t++)
+      for (int l = 0; l + 1 < KB_LEVELS; l++) lvlcnt[(size_t)t * KB_LEVELS + l + 1] += lvlcnt[(size_t)t * KB_LEVELS + l];
+    h->tree_level = lvlcnt;
+    std::vector<int32_t> cur = lvlcnt;
+    for (int n = 0; n < N; n++) {
+      int t = tree_of_root[root[n]];
+      if (t < 0) continue;
+      int pos = cur[(size_t)t * KB_LEVELS + h->depth[n]]++;
+      h->tree_nodes[h->tree_start[t] + pos] = n;
+    }
+  }
+  // admitted workloads grouped by CQ (ClusterQueueSnapshot.Workloads)
+  h->cq_adm_start.assign(Q + 1, 0);
+  for (int a = 0; a < s->n_adm; a++) {
+    int c = s->adm_cq[a];
+    if (c < 0 || c >= Q) return fail(h, KB_ERR_INVALID, "adm_cq out of range");
+    h->cq_adm_start[c + 1]++;
+  }
+  for (int q = 0; q < Q; q++) h->cq_adm_start[q + 1] += h->cq_adm_start[q];
+  h->cq_adm.assign(std::max(1, s->n_adm), 0);
+  {
+    std::vector<int32_t> cur(h->cq_adm_start.begin(), h->cq_adm_start.end() - 1);
+    for (int a = 0; a < s->n_adm; a++) h->cq_adm[cur[s->adm_cq[a]]++] = a;
+  }
+  // light bounds checks on the hot tables
+  for (int i = 0; i < s->n_heads; i++) if (s->heads[i] < 0 || s->heads[i] >= s->n_wl) return fail(h, KB_ERR_INVALID, "heads out of range");
+  for (int w = 0; w < s->n_wl; w++) {
+    if (s->wl_cq[w] < 0 || s->wl_cq[w] >= Q) return fail(h, KB_ERR_INVALID, "wl_cq out of range");
+    if (s->wl_ps_start[w + 1] < s->wl_ps_start[w]) return fail(h, KB_ERR_INVALID, "wl_ps_start not monotone");
+  }
+  if (s->n_wl && s->wl_ps_start[s->n_wl] != s->n_podset) return fail(h, KB_ERR_INVALID, "wl_ps_start[n_wl] != n_podset");
+  h->D.nTrees = ntrees;
+  h->D.nLone = (int)h->lone.size();
+  h->D.nRoots = nroots;
+  return KB_OK;
+}
+
+template <typename T>
+static cudaError_t up(kb_handle *h, const T *&dst, const T *src, size_t n, int64_t *bytes) {
+  T *d = h->arena.take<T>(n);
+  dst = d;
+  if (n == 0) return cudaSuccess;
+  *bytes += (int64_t)(n * sizeof(T));
+  return cudaMemcpyAsync(d, src, n * sizeof(T), cudaMemcpyHostToDevice, h->stream);
+}
+
+extern "C" int32_t kb_upload(kb_handle *h, const kb_snapshot *s) {
+  if (!h || !s) return KB_ERR_INVALID;
+  cudaSetDevice(h->device);
+  h->uploaded = false;
+  int32_t rc = build_topology(h, s);
+  if (rc != KB_OK) return rc;
+  DevSnap &D = h->D;
+  int Q = s->n_cq, C = s->n_cohort, N = Q + C, F = s->n_flavor, R = s->n_resource, FR = F * R;
+  D.Q = Q; D.C = C; D.N = N; D.F = F; D.R = R; D.FR = FR; D.W = s->n_wl; D.P = s->n_podset; D.A = s->n_adm;
+  D.AU = s->n_adm_use; D.H = s->n_heads; D.NRG = s->n_rg; D.pods_res = s->pods_resource; D.flags = s->flags; D.now_ns = s->now_ns;
+  size_t NF = (size_t)N * FR, P = (size_t)s->n_podset, W = (size_t)s->n_wl, A = (size_t)s->n_adm, H = (size_t)s->n_heads;
+  int ntrees = D.nTrees, nroots = D.nRoots;
+  // exact arena size
+  size_t tot = 0;
+  auto need = [&](size_t n, size_t sz) { tot += pad256(n * sz); };
+  need(N, 4); need(N, 8); need(NF, 8); need(NF, 8); need(NF, 8); need((size_t)Q * FR, 8);
+  for (int k = 0; k < 4; k++) need(Q, 1);
+  need(Q, 4); for (int k = 0; k < 4; k++) need(Q, 1); need(Q, 8);
+  need(Q + 1, 4); need(s->n_rg, 4); need(s->n_rg + 1, 4); need(s->n_rg ? s->rg_flavor_start[s->n_rg] : 0, 4);
+  need(W, 4); need(W, 4); need(W, 8); need(W, 8); need(W, 8); need(W + 1, 4);
+  need(P * R, 8); need(P, 4); need(P, 4); need(P, 4); need(P, 8); need(P * R, 1);
+  need(A, 4); need(A, 4); need(A, 8); need(A, 8); need(A, 8); need(A, 1); need(A + 1, 4); need(s->n_adm_use, 4); need(s->n_adm_use, 8);
+  need(H, 4);
+  need(N, 4); need(N, 4); need(N, 4); need(ntrees + 1, 4); need(h->tree_nodes.size(), 4); need(h->tree_level.size(), 4);
+  need(h->lone.size(), 4); need(Q + 1, 4); need(h->cq_adm.size(), 4);
+  need(NF, 8); need(NF, 8); need(NF, 8); need(NF, 8);
+  need(nroots, 4); need(nroots + 1, 4); need(nroots, 4); need(H, 4);
+  need(H, 1); need(H, 1); need(H, 4); need(H, 4); need(P * R, 1); need(P * R, 1); need(P * R, 1); need(P, 4);
+  need(1, 4); need(N, 8); need(N, 4); need(N, 1);
+  if (!h->arena.reserve(tot + 4096)) return fail(h, KB_ERR_CUDA, "cudaMalloc failed");
+  h->arena.reset();
+  int64_t bytes = 0;
+  CUDA_TRY(h, cudaEventRecord(h->ev0, h->stream));
+#define UP(field, src, n) CUDA_TRY(h, up(h, D.field, src, (size_t)(n), &bytes))
+  UP(parent, s->parent, N); UP(fair_weight, s->fair_weight, N);
+  UP(nominal, (const i64 *)s->nominal, NF); UP(blimit, (const i64 *)s->borrow_limit, NF); UP(llimit, (const i64 *)s->lend_limit, NF);
+  UP(cq_usage, (const i64 *)s->cq_usage, (size_t)Q * FR);
+  UP(cq_within_cq, s->cq_within_cq, Q); UP(cq_reclaim_within, s->cq_reclaim_within, Q); UP(cq_borrow_within, s->cq_borrow_within, Q);
+  UP(cq_has_bwc_threshold, s->cq_has_bwc_threshold, Q); UP(cq_bwc_threshold, s->cq_bwc_threshold, Q);
+  UP(cq_when_can_borrow, s->cq_when_can_borrow, Q); UP(cq_when_can_preempt, s->cq_when_can_preempt, Q);
+  UP(cq_preference, s->cq_preference, Q); UP(cq_strategy, s->cq_strategy, Q); UP(cq_generation, (const i64 *)s->cq_generation, Q);
+  UP(cq_rg_start, s->cq_rg_start, Q + 1); UP(rg_res_mask, s->rg_res_mask, s->n_rg); UP(rg_flavor_start, s->rg_flavor_start, s->n_rg + 1);
+  UP(rg_flavors, s->rg_flavors, s->n_rg ? s->rg_flavor_start[s->n_rg] : 0);
+  UP(wl_cq, s->wl_cq, W); UP(wl_priority, s->wl_priority, W); UP(wl_ts, (const i64 *)s->wl_ts, W); UP(wl_uid, (const i64 *)s->wl_uid, W);
+  UP(wl_last_gen, (const i64 *)s->wl_last_gen, W); UP(wl_ps_start, s->wl_ps_start, W + 1);
+  UP(ps_req, (const i64 *)s->ps_req, P * R); UP(ps_req_mask, s->ps_req_mask, P); UP(ps_count, s->ps_count, P);
+  UP(ps_min_count, s->ps_min_count, P); UP(ps_flavor_ok, (const u64 *)s->ps_flavor_ok, P); UP(ps_last_tried, s->ps_last_tried, P * R);
+  UP(adm_cq, s->adm_cq, A); UP(adm_priority, s->adm_priority, A); UP(adm_ts, (const i64 *)s->adm_ts, A);
+  UP(adm_qr_ts, (const i64 *)s->adm_qr_ts, A); UP(adm_uid, (const i64 *)s->adm_uid, A); UP(adm_evicted, s->adm_evicted, A);
+  UP(adm_use_start, s->adm_use_start, A + 1); UP(adm_use_fr, s->adm_use_fr, s->n_adm_use); UP(adm_use_qty, (const i64 *)s->adm_use_qty, s->n_adm_use);
+  UP(heads, s->heads, H);
+  UP(root_slot, h->root_slot.data(), N); UP(depth, h->depth.data(), N); UP(height, h->height.data(), N);
+  UP(tree_start, h->tree_start.data(), ntrees + 1); UP(tree_nodes, h->tree_nodes.data(), h->tree_nodes.size());
+  UP(tree_level, h->tree_level.data(), h->tree_level.size()); UP(lone_cqs, h->lone.data(), h->lone.size());
+  UP(cq_adm_start, h->cq_adm_start.data(), Q + 1); UP(cq_adm, h->cq_adm.data(), h->cq_adm.size());
+#undef UP
+  D.subtree = h->arena.take<i64>(NF); D.usage = h->arena.take<i64>(NF);
+  D.avail = h->arena.take<i64>(NF); D.potential = h->arena.take<i64>(NF);
+  D.root_count = h->arena.take<int32_t>(nroots); D.root_offset = h->arena.take<int32_t>(nroots + 1);
+  D.root_cursor = h->arena.take<int32_t>(nroots); D.root_entries = h->arena.take<int32_t>(H);
+  D.decision = h->arena.take<uint8_t>(H); D.mode = h->arena.take<uint8_t>(H);
+  D.borrow = h->arena.take<int32_t>(H); D.rank = h->arena.take<int32_t>(H);
+  D.ps_flavor = h->arena.take<int8_t>(P * R); D.ps_res_mode = h->arena.take<int8_t>(P * R); D.ps_tried = h->arena.take<int8_t>(P * R);
+  D.ps_count_out = h->arena.take<int32_t>(P);
+  D.status = h->arena.take<uint32_t>(1);
+  h->d_drs_rounded = h->arena.take<i64>(N); h->d_drs_res = h->arena.take<int32_t>(N); h->d_drs_borrowing = h->arena.take<uint8_t>(N);
+  // rows of workloads that are not heads stay at -1
+  CUDA_TRY(h, cudaMemsetAsync(D.ps_flavor, 0xff, P * R, h->stream));
+  CUDA_TRY(h, cudaMemsetAsync(D.ps_res_mode, 0xff, P * R, h->stream));
+  CUDA_TRY(h, cudaMemsetAsync(D.ps_tried, 0xff, P * R, h->stream));
+  CUDA_TRY(h, cudaEventRecord(h->ev1, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));  // host vectors / caller buffers may be released after return
+  float ms = 0; cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+  h->stats.last_h2d_ms = ms; h->stats.h2d_bytes = bytes;
+  h->uploaded = true;
+  return KB_OK;
+}
+
+// per-kernel timing: an event before each kernel (and one after the last) when profiling
+static inline void kmark(kb_handle *h, int id) {
+  if (!h->profile || h->kev_n > KB_N_KERNELS) return;
+  h->kev_id[h->kev_n] = id;
+  cudaEventRecord(h->kev[h->kev_n++], h->stream);
+}
+static int32_t launch_tree(kb_handle *h, int *launches) {
+  DevSnap &D = h->D;
+  if (D.nTrees) { kmark(h, KB_K_TREE); k_tree<<<D.nTrees, 256, 0, h->stream>>>(D); (*launches)++; }
+  if (D.nLone) { kmark(h, KB_K_LONE); int n = D.nLone * D.FR; k_lone<<<(n + 255) / 256, 256, 0, h->stream>>>(D); (*launches)++; }
+  return KB_OK;
+}
+
+extern "C" int32_t kb_cycle_resident(kb_handle *h) {
+  if (!h || !h->uploaded) return fail(h, KB_ERR_INVALID, "kb_upload first");
+  cudaSetDevice(h->device);
+  DevSnap &D = h->D;
+  int launches = 0;
+  CUDA_TRY(h, cudaEventRecord(h->ev2, h->stream));
+  CUDA_TRY(h, cudaMemsetAsync(D.status, 0, 4, h->stream));
+  CUDA_TRY(h, cudaMemsetAsync(D.root_count, 0, sizeof(int32_t) * (size_t)std::max(1, D.nRoots), h->stream));
+  h->kev_n = 0;
+  if ((D.flags & KB_F_FAIR_SHARING) && D.H) return fail(h, KB_ERR_UNSUPPORTED, "fair sharing iterator not built yet");
+  launch_tree(h, &launches);
+  if (D.H) {
+    kmark(h, KB_K_NOMINATE); k_nominate<<<(D.H + 127) / 128, 128, 0, h->stream>>>(D); launches++;
+    kmark(h, KB_K_SCAN); k_scan_roots<<<1, 1024, 0, h->stream>>>(D); launches++;
+    kmark(h, KB_K_SCATTER); k_scatter<<<(D.H + 255) / 256, 256, 0, h->stream>>>(D); launches++;
+    kmark(h, KB_K_ADMIT); k_admit<<<D.nRoots, 128, 0, h->stream>>>(D); launches++;
+  }
+  kmark(h, -1);
+  CUDA_TRY(h, cudaEventRecord(h->ev3, h->stream));
+  CUDA_TRY(h, cudaGetLastError());
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  float ms = 0; cudaEventElapsedTime(&ms, h->ev2, h->ev3);
+  h->stats.last_cycle_gpu_ms = ms;
+  h->stats.kernel_launches = launches;
+  for (int i = 0; i < KB_N_KERNELS; i++) h->stats.kernel_ms[i] = 0.f;
+  for (int i = 0; i + 1 < h->kev_n; i++) {
+    float kms = 0; cudaEventElapsedTime(&kms, h->kev[i], h->kev[i + 1]);
+    if (h->kev_id[i] >= 0) h->stats.kernel_ms[h->kev_id[i]] += kms;
+  }
+  uint32_t st = 0;
+  CUDA_TRY(h, cudaMemcpy(&st, D.status, 4, cudaMemcpyDeviceToHost));
+  if (st & KBS_UNSUPPORTED_PREEMPTION) return fail(h, KB_ERR_UNSUPPORTED, "snapshot needs the preemption search (not in this build)");
+  if (st & KBS_TARGET_OVERFLOW) return fail(h, KB_ERR_CAPACITY, "per-entry usage cell capacity exceeded");
+  return KB_OK;
+}
+
+extern "C" int32_t kb_download(kb_handle *h, kb_cycle_out *out) {
+  if (!h || !h->uploaded || !out) return fail(h, KB_ERR_INVALID, "nothing to download");
+  cudaSetDevice(h->device);
+  DevSnap &D = h->D;
+  size_t H = D.H, PR = (size_t)D.P * D.R;
+  int64_t bytes = 0;
+  CUDA_TRY(h, cudaEventRecord(h->ev0, h->stream));
+#define DOWN(dst, src, n, T) if (out->dst && (n)) { CUDA_TRY(h, cudaMemcpyAsync(out->dst, D.src, (n) * sizeof(T), cudaMemcpyDeviceToHost, h->stream)); bytes += (n) * sizeof(T); }
+  DOWN(decision, decision, H, uint8_t); DOWN(mode, mode, H, uint8_t); DOWN(borrow, borrow, H, int32_t); DOWN(commit_rank, rank, H, int32_t);
+  DOWN(ps_flavor, ps_flavor, PR, int8_t); DOWN(ps_res_mode, ps_res_mode, PR, int8_t); DOWN(ps_tried_idx, ps_tried, PR, int8_t);
+  DOWN(ps_count, ps_count_out, (size_t)D.P, int32_t);
+  DOWN(node_usage, usage, (size_t)D.N * D.FR, i64);
+#undef DOWN
+  CUDA_TRY(h, cudaEventRecord(h->ev1, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  if (out->tgt_start) memset(out->tgt_start, 0, sizeof(int32_t) * (H + 1));
+  out->n_targets = 0;
+  float ms = 0; cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+  h->stats.last_d2h_ms = ms; h->stats.d2h_bytes = bytes;
+  return KB_OK;
+}
+
+extern "C" int32_t kb_run_cycle(kb_handle *h, const kb_snapshot *s, kb_cycle_out *out) {
+  int32_t rc = kb_upload(h, s);
+  if (rc != KB_OK) return rc;
+  rc = kb_cycle_resident(h);
+  if (rc != KB_OK) return rc;
+  return kb_download(h, out);
+}
+
+extern "C" int32_t kb_tree_eval(kb_handle *h, const kb_snapshot *s, kb_tree_out *out) {
+  int32_t rc = kb_upload(h, s);
+  if (rc != KB_OK) return rc;
+  DevSnap &D = h->D;
+  int launches = 0;
+  launch_tree(h, &launches);
+  k_drs<<<(D.N + 127) / 128, 128, 0, h->stream>>>(D, h->d_drs_rounded, h->d_drs_res, h->d_drs_borrowing);
+  CUDA_TRY(h, cudaGetLastError());
+  size_t NF = (size_t)D.N * D.FR, QF = (size_t)D.Q * D.FR;
+  if (out->subtree_quota) CUDA_TRY(h, cudaMemcpyAsync(out->subtree_quota, D.subtree, NF * 8, cudaMemcpyDeviceToHost, h->stream));
+  if (out->usage) CUDA_TRY(h, cudaMemcpyAsync(out->usage, D.usage, NF * 8, cudaMemcpyDeviceToHost, h->stream));
+  if (out->available) CUDA_TRY(h, cudaMemcpyAsync(out->available, D.avail, QF * 8, cudaMemcpyDeviceToHost, h->stream));
+  if (out->potential_available) CUDA_TRY(h, cudaMemcpyAsync(out->potential_available, D.potential, QF * 8, cudaMemcpyDeviceToHost, h->stream));
+  if (out->drs_rounded) CUDA_TRY(h, cudaMemcpyAsync(out->drs_rounded, h->d_drs_rounded, (size_t)D.N * 8, cudaMemcpyDeviceToHost, h->stream));
+  if (out->drs_resource) CUDA_TRY(h, cudaMemcpyAsync(out->drs_resource, h->d_drs_res, (size_t)D.N * 4, cudaMemcpyDeviceToHost, h->stream));
+  if (out->drs_borrowing) CUDA_TRY(h, cudaMemcpyAsync(out->drs_borrowing, h->d_drs_borrowing, (size_t)D.N, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  if (out->available) for (size_t i = 0; i < QF; i++) if (out->available[i] < 0) out->available[i] = 0;  // Available() clamps at the CQ (clusterqueue_snapshot.go:154-156)
+  return KB_OK;
+}
+
+extern "C" int32_t kb_set_profile(kb_handle *h, int32_t on) {
+  if (!h) return KB_ERR_INVALID;
+  h->profile = on != 0;
+  return KB_OK;
+}
+
+extern "C" int32_t kb_get_stats(const kb_handle *h, kb_stats *out) {
+  if (!h || !out) return KB_ERR_INVALID;
+  *out = h->stats;
+  return KB_OK;
+}

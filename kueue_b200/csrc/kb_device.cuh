@@ -1,0 +1,109 @@
+// kb_device.cuh — device-side view of one flattened snapshot and the quota-tree
+// arithmetic shared by the kernels.  sm_100a only.
+//
+// Reference semantics restated per function (paths relative to /root/reference):
+// resourceNode arithmetic = pkg/cache/scheduler/resource_node.go, borrow height =
+// pkg/scheduler/preemption/classical/hierarchical_preemption.go:202-227.
+#pragma once
+
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "../../include/kueue_b200.h"
+
+typedef long long i64;
+typedef unsigned long long u64;
+
+#define KB_LEVELS (KB_MAX_DEPTH + 2)
+
+// Status word bits written by kernels (checked by the host after a cycle).
+enum { KBS_UNSUPPORTED_PREEMPTION = 1u << 0, KBS_TARGET_OVERFLOW = 1u << 1, KBS_PATH_TOO_DEEP = 1u << 2 };
+
+struct DevSnap {
+  // dimensions
+  int Q, C, N, F, R, FR, W, P, A, AU, H, NRG, pods_res;
+  uint32_t flags;
+  i64 now_ns;
+  // ---- inputs (device copies of kb_snapshot tables) ----
+  const int32_t *parent;
+  const double *fair_weight;
+  const i64 *nominal, *blimit, *llimit, *cq_usage;
+  const uint8_t *cq_within_cq, *cq_reclaim_within, *cq_borrow_within, *cq_has_bwc_threshold;
+  const int32_t *cq_bwc_threshold;
+  const uint8_t *cq_when_can_borrow, *cq_when_can_preempt, *cq_preference, *cq_strategy;
+  const i64 *cq_generation;
+  const int32_t *cq_rg_start;
+  const uint32_t *rg_res_mask;
+  const int32_t *rg_flavor_start, *rg_flavors;
+  const int32_t *wl_cq, *wl_priority;
+  const i64 *wl_ts, *wl_uid, *wl_last_gen;
+  const int32_t *wl_ps_start;
+  const i64 *ps_req;
+  const uint32_t *ps_req_mask;
+  const int32_t *ps_count, *ps_min_count;
+  const u64 *ps_flavor_ok;
+  const int8_t *ps_last_tried;
+  const int32_t *adm_cq, *adm_priority;
+  const i64 *adm_ts, *adm_qr_ts, *adm_uid;
+  const uint8_t *adm_evicted;
+  const int32_t *adm_use_start, *adm_use_fr;
+  const i64 *adm_use_qty;
+  const int32_t *heads;
+  // ---- derived, static per topology (host-built at upload) ----
+  const int32_t *root_slot;   // [N] dense index of the node's root among all roots
+  const int32_t *depth;       // [N] distance to the root
+  const int32_t *height;      // [N] getNodeHeight (cohorts), 0 for CQs
+  const int32_t *tree_start;  // [nTrees+1] into tree_nodes (cohort-rooted trees)
+  const int32_t *tree_nodes;  // per tree: nodes ordered by depth ascending (root first)
+  const int32_t *tree_level;  // [nTrees][KB_LEVELS] start (relative) of each depth level
+  const int32_t *lone_cqs;    // CQs without a cohort
+  const int32_t *cq_adm_start;// [Q+1] admitted workloads grouped by CQ
+  const int32_t *cq_adm;      // [A]
+  int nTrees, nLone, nRoots;
+  // ---- derived per cycle ----
+  i64 *subtree;    // [N][FR] resourceNode.SubtreeQuota
+  i64 *usage;      // [N][FR] resourceNode.Usage (mutated by the admit kernel)
+  i64 *avail;      // [N][FR] available() at cycle start (may be negative)
+  i64 *potential;  // [N][FR] potentialAvailable()
+  // entry grouping by root
+  int32_t *root_count;   // [nRoots]
+  int32_t *root_offset;  // [nRoots+1]
+  int32_t *root_cursor;  // [nRoots]
+  int32_t *root_entries; // [H]
+  // ---- outputs (device) ----
+  uint8_t *decision, *mode;
+  int32_t *borrow, *rank;
+  int8_t *ps_flavor, *ps_res_mode, *ps_tried;
+  int32_t *ps_count_out;
+  uint32_t *status;  // [1] KBS_* bits
+};
+
+__device__ __forceinline__ i64 imax(i64 a, i64 b) { return a > b ? a : b; }
+__device__ __forceinline__ i64 imin(i64 a, i64 b) { return a < b ? a : b; }
+
+// localQuota resource_node.go:66-71
+__device__ __forceinline__ i64 local_quota(i64 subtree, i64 lend_limit) {
+  return lend_limit != KB_NO_LIMIT ? imax(0, subtree - lend_limit) : 0;
+}
+
+// FindHeightOfLowestSubtreeThatFits hierarchical_preemption.go:214-227, on the
+// cycle-start usage.  Returns the borrow height; *may_reclaim = second result.
+__device__ inline int find_height(const DevSnap &D, const i64 *usage, int cq, int fr, i64 val, bool *may_reclaim) {
+  int FR = D.FR;
+  int p = D.parent[cq];
+  size_t c = (size_t)cq * FR + fr;
+  i64 ucq = usage[c];
+  if (!(ucq + val > D.nominal[c]) || p < 0) { *may_reclaim = p >= 0; return 0; }
+  i64 remaining = val - imax(0, local_quota(D.subtree[c], D.llimit[c]) - ucq);
+  int t = p, last = p;
+  while (t >= 0) {
+    size_t i = (size_t)t * FR + fr;
+    i64 u = usage[i], sub = D.subtree[i];
+    if (!(u + remaining > sub)) { *may_reclaim = D.parent[t] >= 0; return D.height[t]; }
+    remaining -= imax(0, local_quota(sub, D.llimit[i]) - u);
+    last = t;
+    t = D.parent[t];
+  }
+  *may_reclaim = false;
+  return D.height[last];
+}

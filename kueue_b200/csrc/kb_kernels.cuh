@@ -1,0 +1,551 @@
+// kb_kernels.cuh — sm_100a kernels of the scheduling cycle.
+//
+//   K1  k_tree / k_lone   resource-node tree: SubtreeQuota, cohort Usage (bottom-up,
+//                         resource_node.go:183-217), available / potentialAvailable
+//                         (top-down, :104-133) for every (node, flavor-resource) cell.
+//   K1d k_drs             dominantResourceShare per node (fair_sharing.go:126-174).
+//   K2  k_nominate        flavorassigner.Assign for every entry of the cycle
+//                         (flavorassigner.go:540-1047), one thread per workload,
+//                         coalesced reads of the podset request rows.
+//   K3  k_scan / k_scatter group entries by root cohort.
+//   K5  k_admit           per-root ordered admit loop (scheduler.go:269-401,778-817):
+//                         block-local bitonic sort of the root's entries, then one warp
+//                         commits them in order with one lane per flavor-resource cell.
+//
+// All of it is integer compare/add work bounded by HBM/L2 bandwidth and latency:
+// no tensor cores.
+#pragma once
+
+#include "kb_device.cuh"
+
+// ---------------------------------------------------------------------------
+// K1: tree pass, one CTA per cohort-rooted tree.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_tree(DevSnap D) {
+  int t = blockIdx.x;
+  int FR = D.FR;
+  const int32_t *nodes = D.tree_nodes + D.tree_start[t];
+  int nn = D.tree_start[t + 1] - D.tree_start[t];
+  const int32_t *lvl = D.tree_level + (size_t)t * KB_LEVELS;
+  int nlev = 0;
+  while (nlev + 1 < KB_LEVELS && lvl[nlev + 1] > lvl[nlev]) nlev++;  // levels [0, nlev)
+  // init: SubtreeQuota = Nominal; Usage = CQ usage | 0 (updateCohortResourceNode :184-190)
+  for (int i = threadIdx.x; i < nn * FR; i += blockDim.x) {
+    int n = nodes[i / FR], fr = i % FR;
+    size_t c = (size_t)n * FR + fr;
+    D.subtree[c] = D.nominal[c];
+    D.usage[c] = n < D.Q ? D.cq_usage[c] : 0;
+  }
+  __syncthreads();
+  // bottom-up accumulateFromChild :210-217
+  for (int L = nlev - 1; L >= 1; L--) {
+    int a = lvl[L], b = lvl[L + 1];
+    for (int i = threadIdx.x; i < (b - a) * FR; i += blockDim.x) {
+      int n = nodes[a + i / FR], fr = i % FR;
+      size_t c = (size_t)n * FR + fr;
+      size_t pc = (size_t)D.parent[n] * FR + fr;
+      i64 sub = D.subtree[c];
+      i64 lq = local_quota(sub, D.llimit[c]);
+      atomicAdd((u64 *)&D.subtree[pc], (u64)(sub - lq));
+      i64 spill = imax(0, D.usage[c] - lq);
+      if (spill) atomicAdd((u64 *)&D.usage[pc], (u64)spill);
+    }
+    __syncthreads();
+  }
+  // top-down available / potentialAvailable :104-133
+  for (int L = 0; L < nlev; L++) {
+    int a = lvl[L], b = lvl[L + 1];
+    for (int i = threadIdx.x; i < (b - a) * FR; i += blockDim.x) {
+      int n = nodes[a + i / FR], fr = i % FR;
+      size_t c = (size_t)n * FR + fr;
+      i64 sub = D.subtree[c], u = D.usage[c];
+      if (L == 0) {
+        D.avail[c] = sub - u;
+        D.potential[c] = sub;
+      } else {
+        size_t pc = (size_t)D.parent[n] * FR + fr;
+        i64 lq = local_quota(sub, D.llimit[c]);
+        i64 bl = D.blimit[c];
+        i64 pa = D.avail[pc];
+        i64 pot = lq + D.potential[pc];
+        if (bl != KB_NO_LIMIT) {
+          i64 stored = sub - lq, used = imax(0, u - lq);
+          pa = imin(stored - used + bl, pa);
+          pot = imin(sub + bl, pot);
+        }
+        D.avail[c] = imax(0, lq - u) + pa;
+        D.potential[c] = pot;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ClusterQueues without a cohort: the node is its own root.
+__global__ void k_lone(DevSnap D) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= D.nLone * D.FR) return;
+  int n = D.lone_cqs[i / D.FR], fr = i % D.FR;
+  size_t c = (size_t)n * D.FR + fr;
+  i64 nom = D.nominal[c], u = D.cq_usage[c];
+  D.subtree[c] = nom;
+  D.usage[c] = u;
+  D.avail[c] = nom - u;
+  D.potential[c] = nom;
+}
+
+// ---------------------------------------------------------------------------
+// K1d: DominantResourceShare of every node (fair_sharing.go:126-156, wlReq = nil).
+// ---------------------------------------------------------------------------
+struct DevDRS {
+  double weight, ratio;
+  int res;
+  bool borrowing;
+};
+__device__ __forceinline__ bool drs_zero_weight_borrows(const DevDRS &d) { return d.weight == 0 && d.ratio != 0; }
+__device__ __forceinline__ double drs_precise(const DevDRS &d) {  // :75-83
+  if (d.ratio == 0) return 0.0;
+  if (d.weight == 0) return __longlong_as_double(0x7ff0000000000000LL);
+  return d.ratio / d.weight;
+}
+__device__ __forceinline__ int cmp_d(double a, double b) { return a < b ? -1 : (a > b ? 1 : 0); }
+__device__ inline int drs_compare(const DevDRS &a, const DevDRS &b) {  // CompareDRS :89-100
+  bool za = drs_zero_weight_borrows(a), zb = drs_zero_weight_borrows(b);
+  if (za && zb) return cmp_d(a.ratio, b.ratio);
+  if (za) return 1;
+  if (zb) return -1;
+  return cmp_d(drs_precise(a), drs_precise(b));
+}
+// DRS of node n when its usage row is `u[fr] + extra[fr]` (extra may be null).
+template <typename UsageFn>
+__device__ inline DevDRS drs_node(const DevSnap &D, int n, UsageFn usage_of) {
+  DevDRS d{D.fair_weight[n], 0.0, -1, false};
+  int p = D.parent[n];
+  if (p < 0) return d;
+  int R = D.R, F = D.F, FR = D.FR;
+  for (int r = 0; r < R; r++) {
+    i64 b = 0, lend = 0;
+    for (int f = 0; f < F; f++) {
+      int fr = f * R + r;
+      i64 over = usage_of(fr) - D.subtree[(size_t)n * FR + fr];
+      if (over > 0) b += over;
+      lend += D.potential[(size_t)p * FR + fr];  // calculateLendable :160-174
+    }
+    if (b > 0) {
+      d.borrowing = true;
+      if (lend > 0) {
+        double ratio = (double)b * 1000.0 / (double)lend;
+        if (ratio > d.ratio) { d.ratio = ratio; d.res = r; }  // ascending r => smaller name wins ties
+      }
+    }
+  }
+  return d;
+}
+__global__ void k_drs(DevSnap D, i64 *drs_rounded, int32_t *drs_res, uint8_t *drs_borrowing) {
+  int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= D.N) return;
+  const i64 *u = D.usage + (size_t)n * D.FR;
+  DevDRS d = drs_node(D, n, [&](int fr) { return u[fr]; });
+  i64 v;
+  if (drs_zero_weight_borrows(d)) v = INT64_MAX;  // roundedWeightedShare :110-118
+  else v = (i64)ceil(drs_precise(d));
+  drs_rounded[n] = v;
+  drs_res[n] = d.res;
+  drs_borrowing[n] = d.borrowing;
+}
+
+// ---------------------------------------------------------------------------
+// K2: nominate.  preemptionMode values flavorassigner.go:399-407
+// ---------------------------------------------------------------------------
+enum { PM_NOFIT = 0, PM_NOCAND = 1, PM_PREEMPT = 2, PM_RECLAIM = 3, PM_FIT = 4 };
+
+__device__ __forceinline__ bool gm_preferred(int apm, int ab, int bpm, int bb, int pref) {  // isPreferred :410-441
+  if (apm == PM_NOFIT) return false;
+  if (bpm == PM_NOFIT) return true;
+  if (pref == KB_PREF_PREEMPTION_OVER_BORROWING) {
+    if (ab != bb) return ab < bb;
+    return apm > bpm;
+  }
+  if (apm != bpm) return apm > bpm;
+  return ab < bb;
+}
+__device__ __forceinline__ int fa_mode(int pm) {  // flavorAssignmentMode :470-485
+  return pm == PM_NOFIT ? KB_MODE_NOFIT : (pm == PM_FIT ? KB_MODE_FIT : KB_MODE_PREEMPT);
+}
+__device__ __forceinline__ int rg_by_resource(const DevSnap &D, int cq, int r) {  // RGByResource clusterqueue_snapshot.go:67-74
+  for (int g = D.cq_rg_start[cq]; g < D.cq_rg_start[cq + 1]; g++)
+    if (D.rg_res_mask[g] & (1u << r)) return g;
+  return -1;
+}
+// Effective request of podset `row` for resource r with `count` pods admitted
+// (ScaledTo workload.go:258-275; pods resource flavorassigner.go:585-587).
+__device__ __forceinline__ i64 ps_request(const DevSnap &D, int row, int r, int count, bool covers_pods) {
+  if (covers_pods && r == D.pods_res) return count;
+  i64 q = D.ps_req[(size_t)row * D.R + r];
+  int full = D.ps_count[row];
+  if (full != 0 && full != count) q = q / full * count;
+  return q;
+}
+
+// SimulatePreemption (preemption_oracle.go:41-71).  This build evaluates the cases in
+// which no candidate can exist; anything else raises KBS_UNSUPPORTED_PREEMPTION so the
+// host fails loudly (the Go shim then runs the reference path for the cycle).
+__device__ inline int simulate_preemption(const DevSnap &D, int cq, int *borrow_after) {
+  bool own = D.cq_within_cq[cq] != KB_POLICY_NEVER && D.cq_adm_start[cq + 1] > D.cq_adm_start[cq];
+  bool cohort = D.parent[cq] >= 0 && D.cq_reclaim_within[cq] != KB_POLICY_NEVER && D.A > 0;
+  if (own || cohort) atomicOr(D.status, KBS_UNSUPPORTED_PREEMPTION);
+  *borrow_after = 0;
+  return PM_NOCAND;
+}
+
+// fitsResourceQuota :1017-1047
+__device__ inline int fits_resource_quota(const DevSnap &D, int cq, int fr, i64 assumed, i64 request, int *borrow) {
+  size_t c = (size_t)cq * D.FR + fr;
+  i64 avail = imax(0, D.avail[c]);
+  i64 val = assumed + request;
+  if (val > D.potential[c]) { *borrow = 0; return PM_NOFIT; }
+  bool may_reclaim;
+  int b = find_height(D, D.usage, cq, fr, val, &may_reclaim);
+  if (val <= avail) { *borrow = b; return PM_FIT; }
+  bool can_pwb = D.cq_borrow_within[cq] != KB_POLICY_NEVER ||
+                 ((D.flags & KB_F_FAIR_SHARING) && D.cq_reclaim_within[cq] != KB_POLICY_NEVER);  // :1049-1052
+  if (val <= D.nominal[c] || may_reclaim || can_pwb) return simulate_preemption(D, cq, borrow);
+  *borrow = b;
+  return PM_NOFIT;
+}
+
+// One workload: Assign + assignFlavors (:540-715) writing PodSetAssignment rows.
+// counts == nullptr => full counts.  Returns the representative mode; *borrowing_out =
+// Assignment.Borrowing.
+__device__ inline int assign_workload(const DevSnap &D, int wl, const int32_t *counts, int *borrowing_out) {
+  const int R = D.R;
+  int cq = D.wl_cq[wl];
+  int ps0 = D.wl_ps_start[wl], ps1 = D.wl_ps_start[wl + 1];
+  i64 lg = D.wl_last_gen[wl];
+  bool use_last = lg >= 0 && !(D.cq_generation[cq] > lg);  // lastAssignmentOutdated :532-534
+  bool fung = D.flags & KB_F_FLAVOR_FUNGIBILITY;
+  bool covers_pods = D.pods_res >= 0 && rg_by_resource(D, cq, D.pods_res) >= 0;
+  int pref = D.cq_preference[cq];
+  int wcb = D.cq_when_can_borrow[cq], wcp = D.cq_when_can_preempt[cq];
+  int borrowing = 0, rep = KB_MODE_FIT;
+  if (ps1 == ps0) rep = KB_MODE_NOFIT;  // RepresentativeMode :148-151
+  bool stop = false;
+  for (int row = ps0; row < ps1; row++) {
+    int8_t *oflv = D.ps_flavor + (size_t)row * R;
+    int8_t *omode = D.ps_res_mode + (size_t)row * R;
+    int8_t *otried = D.ps_tried + (size_t)row * R;
+    for (int r = 0; r < R; r++) { oflv[r] = -1; omode[r] = -1; otried[r] = -1; }
+    int full = D.ps_count[row];
+    int count = (counts && full != 0) ? counts[row - ps0] : full;
+    D.ps_count_out[row] = count;
+    if (stop) { D.ps_count_out[row] = full; continue; }
+    uint32_t mask = D.ps_req_mask[row];
+    if (covers_pods) mask |= 1u << D.pods_res;
+    u64 ok = D.ps_flavor_ok[row];
+    bool has_reasons = false, failed = false;
+    int ps_borrow = 0;
+    for (int r0 = 0; r0 < R; r0++) {  // :639-661
+      if (!(mask & (1u << r0))) continue;
+      if (oflv[r0] >= 0) continue;  // got the flavor of its resource group already
+      int g = rg_by_resource(D, cq, r0);
+      if (g < 0) {
+        if (ps_request(D, row, r0, count, covers_pods) == 0) continue;  // zero request for an undefined resource
+        has_reasons = true; failed = true; break;                      // :770-772
+      }
+      // findFlavorForPodSets :762-897
+      uint32_t rgm = D.rg_res_mask[g] & mask;
+      int fl0 = D.rg_flavor_start[g], nfl = D.rg_flavor_start[g + 1] - fl0;
+      int best_f = -1, best_pm = PM_NOFIT, best_rb = INT32_MAX, best_maxb = 0;
+      uint32_t best_pmask = 0;  // resources whose FlavorAssignment.Mode is Preempt in the best flavor
+      bool any_reason = false;
+      int attempted = -1;
+      int idx = 0;
+      if (fung && use_last) idx = D.ps_last_tried[(size_t)row * R + r0] + 1;  // NextFlavorToTryForPodSetResource
+      for (; idx < nfl; idx++) {
+        attempted = idx;
+        int f = D.rg_flavors[fl0 + idx];
+        if (!((ok >> f) & 1)) { any_reason = true; continue; }  // checkFlavorForPodSets :798-806
+        int rpm = PM_FIT, rb = 0, maxb = 0;
+        uint32_t pmask = 0;
+        for (int r = 0; r < R; r++) {
+          if (!(rgm & (1u << r))) continue;
+          // quota assumed by the previous podsets of this workload on (f, r): assignmentUsage[fr] :839
+          i64 assumed = 0;
+          for (int prow = ps0; prow < row; prow++)
+            if (D.ps_flavor[(size_t)prow * R + r] == f) assumed += ps_request(D, prow, r, D.ps_count_out[prow], covers_pods);
+          int b;
+          int pm = fits_resource_quota(D, cq, f * R + r, assumed, ps_request(D, row, r, count, covers_pods), &b);
+          if (pm != PM_FIT) any_reason = true;
+          if (gm_preferred(rpm, rb, pm, b, pref)) { rpm = pm; rb = b; }  // :846-848 keep the worst
+          if (rpm == PM_NOFIT) break;                                    // :849-852
+          if (fa_mode(pm) == KB_MODE_PREEMPT) pmask |= 1u << r;
+          if (b > maxb) maxb = b;
+        }
+        bool take = false, done = false;
+        if (fung) {  // :863-872
+          bool try_next = rpm == PM_NOFIT || rpm == PM_NOCAND ||
+                          ((rpm == PM_PREEMPT || rpm == PM_RECLAIM) && wcp == KB_FUNG_TRY_NEXT_FLAVOR) ||
+                          (rb != 0 && wcb == KB_FUNG_TRY_NEXT_FLAVOR);  // shouldTryNextFlavor :946-963
+          if (!try_next) { take = true; done = true; }
+          else if (gm_preferred(rpm, rb, best_pm, best_rb, pref)) take = true;
+        } else if (rpm > best_pm) {  // :873-880
+          take = true;
+          done = rpm == PM_FIT;
+        }
+        if (take) { best_f = f; best_pm = rpm; best_rb = rb; best_maxb = maxb; best_pmask = pmask; }
+        if (done) break;
+      }
+      if (best_f < 0) { has_reasons = true; failed = true; break; }  // :652-656
+      int tried = fung ? (attempted == nfl - 1 ? -1 : attempted) : 0;  // :883-891
+      for (int r = 0; r < R; r++) {
+        if (!(rgm & (1u << r))) continue;
+        oflv[r] = (int8_t)best_f;
+        omode[r] = (best_pmask >> r) & 1 ? KB_MODE_PREEMPT : KB_MODE_FIT;
+        otried[r] = (int8_t)tried;
+      }
+      if (best_maxb > ps_borrow) ps_borrow = best_maxb;
+      if (best_pm != PM_FIT && any_reason) has_reasons = true;  // status is nil when the best mode is fit :892-894
+    }
+    int psmode;
+    if (failed) {
+      for (int r = 0; r < R; r++) { oflv[r] = -1; omode[r] = -1; otried[r] = -1; }
+      psmode = KB_MODE_NOFIT;
+      stop = true;  // :677-679 return assignment
+    } else {
+      if (ps_borrow > borrowing) borrowing = ps_borrow;  // Assignment.append :721-723
+      psmode = KB_MODE_FIT;  // PodSetAssignment.RepresentativeMode :277-295
+      if (has_reasons) {
+        int nfl_assigned = 0;
+        for (int r = 0; r < R; r++) if (oflv[r] >= 0) { nfl_assigned++; if (omode[r] < psmode) psmode = omode[r]; }
+        if (nfl_assigned == 0) psmode = KB_MODE_NOFIT;
+      }
+    }
+    if (psmode < rep) rep = psmode;
+  }
+  *borrowing_out = borrowing;
+  return rep;
+}
+
+__global__ void __launch_bounds__(128) k_nominate(DevSnap D) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= D.H) return;
+  int wl = D.heads[e];
+  int borrowing;
+  int mode = assign_workload(D, wl, nullptr, &borrowing);  // getInitialAssignments scheduler.go:584-625
+  D.mode[e] = (uint8_t)mode;
+  D.borrow[e] = borrowing;
+  D.decision[e] = KB_DEC_NOFIT;
+  D.rank[e] = -1;
+  atomicAdd(&D.root_count[D.root_slot[D.wl_cq[wl]]], 1);
+}
+
+// ---------------------------------------------------------------------------
+// K3: group entries by root (counting sort: count in K2, scan, scatter)
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) k_scan_roots(DevSnap D) {
+  __shared__ int32_t warp_sums[32];
+  __shared__ int32_t carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  int n = D.nRoots;
+  for (int base = 0; base < n; base += blockDim.x) {
+    int i = base + threadIdx.x;
+    int v = i < n ? D.root_count[i] : 0;
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int x = v;
+    for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+    if (lane == 31) warp_sums[w] = x;
+    __syncthreads();
+    if (w == 0) {
+      int s = warp_sums[lane];
+      for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, s, o); if (lane >= o) s += y; }
+      warp_sums[lane] = s;
+    }
+    __syncthreads();
+    int excl = carry + (w ? warp_sums[w - 1] : 0) + x - v;
+    if (i < n) { D.root_offset[i] = excl; D.root_cursor[i] = 0; }
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1) carry = excl + v;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) D.root_offset[n] = carry;
+}
+__global__ void k_scatter(DevSnap D) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= D.H) return;
+  int slot = D.root_slot[D.wl_cq[D.heads[e]]];
+  int pos = D.root_offset[slot] + atomicAdd(&D.root_cursor[slot], 1);
+  D.root_entries[pos] = e;
+}
+
+// ---------------------------------------------------------------------------
+// K5: ordered admit loop, one CTA per root.
+// ---------------------------------------------------------------------------
+// classical iterator order scheduler.go:778-817 + canonical tie-break (cq, uid)
+__device__ __forceinline__ bool entry_before(const DevSnap &D, int a, int b) {
+  if (a == b) return false;
+  if (a < 0) return false;  // padding sorts last
+  if (b < 0) return true;
+  int ba = D.borrow[a], bb = D.borrow[b];
+  if (ba != bb) return ba < bb;
+  int wa = D.heads[a], wb = D.heads[b];
+  if (D.flags & KB_F_PRIORITY_SORTING_WITHIN_COHORT) {
+    int pa = D.wl_priority[wa], pb = D.wl_priority[wb];
+    if (pa != pb) return pa > pb;
+  }
+  i64 ta = D.wl_ts[wa], tb = D.wl_ts[wb];
+  if (ta != tb) return ta < tb;
+  int ca = D.wl_cq[wa], cb = D.wl_cq[wb];
+  if (ca != cb) return ca < cb;
+  return D.wl_uid[wa] < D.wl_uid[wb];
+}
+
+#define KB_SORT_SMEM 2048
+#define KB_MAX_CELLS 128
+
+// available() on the live usage for one cell, walking the CQ's path (resource_node.go:104-118)
+__device__ inline i64 live_available(const DevSnap &D, const int *path, int plen, int fr) {
+  int FR = D.FR;
+  size_t c = (size_t)path[plen - 1] * FR + fr;
+  i64 a = D.subtree[c] - __ldcg(&D.usage[c]);
+  for (int k = plen - 2; k >= 0; k--) {
+    c = (size_t)path[k] * FR + fr;
+    i64 sub = D.subtree[c], u = __ldcg(&D.usage[c]);
+    i64 lq = local_quota(sub, D.llimit[c]);
+    i64 bl = D.blimit[c];
+    i64 pa = a;
+    if (bl != KB_NO_LIMIT) pa = imin((sub - lq) - imax(0, u - lq) + bl, pa);
+    a = imax(0, lq - u) + pa;
+  }
+  return a;
+}
+// addUsage resource_node.go:137-145
+__device__ inline void live_add_usage(const DevSnap &D, const int *path, int plen, int fr, i64 val) {
+  int FR = D.FR;
+  for (int k = 0; k < plen; k++) {
+    size_t c = (size_t)path[k] * FR + fr;
+    i64 u = __ldcg(&D.usage[c]);
+    i64 la = imax(0, local_quota(D.subtree[c], D.llimit[c]) - u);
+    __stcg(&D.usage[c], u + val);
+    if (!(k + 1 < plen && val > la)) break;
+    val -= la;
+  }
+}
+
+__global__ void __launch_bounds__(128) k_admit(DevSnap D) {
+  __shared__ int32_t s_idx[KB_SORT_SMEM];
+  __shared__ int s_path[KB_MAX_DEPTH + 1];
+  __shared__ int s_cell_fr[KB_MAX_CELLS];
+  __shared__ i64 s_cell_q[KB_MAX_CELLS];
+  __shared__ int s_ncell, s_plen;
+  int slot = blockIdx.x;
+  int off = D.root_offset[slot];
+  int n = D.root_offset[slot + 1] - off;
+  if (n == 0) return;
+  int32_t *ent = D.root_entries + off;
+  // ---- sort the root's entries (bitonic, padded to a power of two with -1) ----
+  int np2 = 1;
+  while (np2 < n) np2 <<= 1;
+  bool in_smem = np2 <= KB_SORT_SMEM;
+  if (in_smem) {
+    for (int i = threadIdx.x; i < np2; i += blockDim.x) s_idx[i] = i < n ? ent[i] : -1;
+    __syncthreads();
+    for (int k = 2; k <= np2; k <<= 1)
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        for (int i = threadIdx.x; i < np2; i += blockDim.x) {
+          int l = i ^ j;
+          if (l > i) {
+            int a = s_idx[i], b = s_idx[l];
+            bool up = (i & k) == 0;
+            if (up ? entry_before(D, b, a) : entry_before(D, a, b)) { s_idx[i] = b; s_idx[l] = a; }
+          }
+        }
+        __syncthreads();
+      }
+    for (int i = threadIdx.x; i < n; i += blockDim.x) ent[i] = s_idx[i];
+    __syncthreads();
+  } else if (n > 1) {
+    // large root: odd-even transposition would be O(n^2); use a global-memory bitonic network on
+    // a virtual padded array (indices >= n behave as -1 and are never written).
+    for (int k = 2; k <= np2; k <<= 1)
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        for (int i = threadIdx.x; i < np2; i += blockDim.x) {
+          int l = i ^ j;
+          if (l > i) {
+            int a = i < n ? ent[i] : -1, b = l < n ? ent[l] : -1;
+            bool up = (i & k) == 0;
+            if (up ? entry_before(D, b, a) : entry_before(D, a, b)) {
+              // padding (-1) sorts last, so a swap never moves a real entry beyond n when ascending
+              if (i < n) ent[i] = b;
+              if (l < n) ent[l] = a;
+            }
+          }
+        }
+        __syncthreads();
+      }
+  }
+  if (threadIdx.x >= 32) return;
+  // ---- sequential commit by warp 0, one lane per flavor-resource cell ----
+  const int lane = threadIdx.x;
+  const int R = D.R;
+  for (int i = 0; i < n; i++) {
+    int e = ent[i];
+    int wl = D.heads[e];
+    int cq = D.wl_cq[wl];
+    int mode = D.mode[e];
+    if (lane == 0) D.rank[e] = i;
+    if (mode == KB_MODE_NOFIT) { if (lane == 0) D.decision[e] = KB_DEC_NOFIT; continue; }
+    if (lane == 0) {
+      // path CQ -> root
+      int pl = 0;
+      for (int t = cq; t >= 0 && pl <= KB_MAX_DEPTH; t = D.parent[t]) s_path[pl++] = t;
+      s_plen = pl;
+      // aggregated assignment usage (Assignment.Usage.Quota, append :734)
+      bool covers_pods = D.pods_res >= 0 && rg_by_resource(D, cq, D.pods_res) >= 0;
+      int nc = 0;
+      for (int row = D.wl_ps_start[wl]; row < D.wl_ps_start[wl + 1]; row++)
+        for (int r = 0; r < R; r++) {
+          int f = D.ps_flavor[(size_t)row * R + r];
+          if (f < 0) continue;
+          int fr = f * R + r;
+          i64 q = ps_request(D, row, r, D.ps_count_out[row], covers_pods);
+          int k = 0;
+          while (k < nc && s_cell_fr[k] != fr) k++;
+          if (k == nc) {
+            if (nc == KB_MAX_CELLS) { atomicOr(D.status, KBS_TARGET_OVERFLOW); continue; }
+            s_cell_fr[nc] = fr; s_cell_q[nc] = 0; nc++;
+          }
+          s_cell_q[k] += q;
+        }
+      s_ncell = nc;
+    }
+    __syncwarp();
+    int nc = s_ncell, plen = s_plen;
+    if (mode == KB_MODE_PREEMPT) {  // no targets in this build: scheduler.go:303-318
+      if (lane == 0) D.decision[e] = KB_DEC_PREEMPT_NO_TARGETS;
+      if (D.cq_reclaim_within[cq] != KB_POLICY_ANY) {  // !CanAlwaysReclaim policy.go:27-29
+        int borrowing = D.borrow[e];
+        for (int k = lane; k < nc; k += 32) {  // quotaResourcesToReserve :530-548
+          int fr = s_cell_fr[k];
+          size_t c = (size_t)cq * D.FR + fr;
+          i64 u = s_cell_q[k], nominal = D.nominal[c], bl = D.blimit[c], cur = __ldcg(&D.usage[c]);
+          i64 rsv;
+          if (borrowing > 0) rsv = bl == KB_NO_LIMIT ? u : imin(u, nominal + bl - cur);
+          else rsv = imax(0, imin(u, nominal - cur));
+          live_add_usage(D, s_path, plen, fr, rsv);
+        }
+      }
+      __syncwarp();
+      continue;
+    }
+    // fits :503-511 / ClusterQueueSnapshot.Fits :121-136
+    bool ok = true;
+    for (int k = lane; k < nc; k += 32)
+      if (imax(0, live_available(D, s_path, plen, s_cell_fr[k])) < s_cell_q[k]) ok = false;
+    ok = __all_sync(0xffffffffu, ok);
+    if (!ok) { if (lane == 0) D.decision[e] = KB_DEC_SKIPPED_NO_FIT; __syncwarp(); continue; }
+    for (int k = lane; k < nc; k += 32) live_add_usage(D, s_path, plen, s_cell_fr[k], s_cell_q[k]);  // cq.AddUsage :336
+    if (lane == 0) D.decision[e] = KB_DEC_ASSUMED;
+    __syncwarp();
+  }
+}

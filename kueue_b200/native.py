@@ -1,0 +1,99 @@
+"""ctypes binding of libkueue_b200.so — the same C-ABI a cgo shim binds
+(include/kueue_b200.h).  There is NO CPU fallback: if the CUDA
+library is missing or no device is present, construction raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from . import abi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libkueue_b200.so")
+_LIB = None
+
+EXPORTS = ["kb_create", "kb_destroy", "kb_last_error", "kb_alloc_pinned", "kb_free_pinned", "kb_version",
+           "kb_tree_eval", "kb_run_cycle", "kb_upload", "kb_cycle_resident", "kb_download", "kb_get_stats", "kb_set_profile"]
+
+
+class KueueB200Error(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"libkueue_b200 error {code}: {msg}")
+        self.code = code
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise FileNotFoundError(f"{LIB_PATH} not built; run `python -c 'import __graft_entry__ as g; g.build()'`")
+        L = C.CDLL(LIB_PATH)
+        L.kb_last_error.restype = C.c_char_p
+        L.kb_last_error.argtypes = [C.c_void_p]
+        for name in EXPORTS:
+            if name not in ("kb_last_error", "kb_destroy"):
+                getattr(L, name).restype = C.c_int32
+        L.kb_destroy.restype = None
+        L.kb_destroy.argtypes = [C.c_void_p]
+        _LIB = L
+    return _LIB
+
+
+class Evaluator:
+    """One kb_handle (one CUDA device, one stream)."""
+
+    def __init__(self, device: int = 0):
+        self._h = C.c_void_p()
+        cfg = abi.kb_config(device, 0)
+        rc = lib().kb_create(C.byref(cfg), C.byref(self._h))
+        if rc != 0:
+            raise KueueB200Error(rc, lib().kb_last_error(None).decode())
+
+    def close(self):
+        if self._h:
+            lib().kb_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int):
+        if rc != 0:
+            raise KueueB200Error(rc, lib().kb_last_error(self._h).decode())
+
+    def tree_eval(self, snap: abi.FlatSnapshot) -> abi.TreeOut:
+        out = abi.TreeOut(snap)
+        s = snap.as_struct()
+        self._check(lib().kb_tree_eval(self._h, C.byref(s), C.byref(out.struct)))
+        return out
+
+    def run_cycle(self, snap: abi.FlatSnapshot, out: abi.CycleOut | None = None) -> abi.CycleOut:
+        out = out or abi.CycleOut(snap)
+        s = snap.as_struct()
+        self._check(lib().kb_run_cycle(self._h, C.byref(s), C.byref(out.struct)))
+        out.n_targets = out.struct.n_targets
+        return out
+
+    def upload(self, snap: abi.FlatSnapshot):
+        s = snap.as_struct()
+        self._check(lib().kb_upload(self._h, C.byref(s)))
+
+    def cycle_resident(self):
+        self._check(lib().kb_cycle_resident(self._h))
+
+    def download(self, snap: abi.FlatSnapshot, out: abi.CycleOut | None = None) -> abi.CycleOut:
+        out = out or abi.CycleOut(snap)
+        self._check(lib().kb_download(self._h, C.byref(out.struct)))
+        out.n_targets = out.struct.n_targets
+        return out
+
+    def set_profile(self, on: bool):
+        self._check(lib().kb_set_profile(self._h, 1 if on else 0))
+
+    def stats(self) -> abi.kb_stats:
+        st = abi.kb_stats()
+        self._check(lib().kb_get_stats(self._h, C.byref(st)))
+        return st

@@ -1024,7 +1024,7 @@ class Oracle {
 
   void writeOut(std::vector<Entry> &entries, kb_cycle_out *out) {
     int H = s.n_heads;
-    int row = 0, nt = 0;
+    int nt = 0;
     for (int i = 0; i < H; i++) {
       Entry &e = entries[i];
       out->decision[i] = (uint8_t)e.decision;
@@ -1032,16 +1032,17 @@ class Oracle {
       out->borrow[i] = e.a.borrowing;
       out->commit_rank[i] = e.rank;
       int np = s.wl_ps_start[e.wl + 1] - s.wl_ps_start[e.wl];
-      for (int k = 0; k < np; k++, row++) {
-        for (int r = 0; r < R; r++) { out->ps_flavor[(size_t)row * R + r] = -1; out->ps_res_mode[(size_t)row * R + r] = -1; out->ps_tried_idx[(size_t)row * R + r] = -1; }
-        out->ps_count[row] = s.ps_count[s.wl_ps_start[e.wl] + k];
+      for (int k = 0; k < np; k++) {
+        size_t row = (size_t)s.wl_ps_start[e.wl] + k;
+        for (int r = 0; r < R; r++) { out->ps_flavor[row * R + r] = -1; out->ps_res_mode[row * R + r] = -1; out->ps_tried_idx[row * R + r] = -1; }
+        out->ps_count[row] = s.ps_count[row];
         if (k < (int)e.a.ps.size()) {
           const PodSetAssign &p = e.a.ps[k];
           out->ps_count[row] = p.count;
           for (int r = 0; r < R; r++) {
-            out->ps_flavor[(size_t)row * R + r] = p.flavor[r];
-            out->ps_res_mode[(size_t)row * R + r] = p.flavor[r] >= 0 ? p.mode[r] : (int8_t)-1;
-            out->ps_tried_idx[(size_t)row * R + r] = p.flavor[r] >= 0 ? p.tried[r] : (int8_t)-1;
+            out->ps_flavor[row * R + r] = p.flavor[r];
+            out->ps_res_mode[row * R + r] = p.flavor[r] >= 0 ? p.mode[r] : (int8_t)-1;
+            out->ps_tried_idx[row * R + r] = p.flavor[r] >= 0 ? p.tried[r] : (int8_t)-1;
           }
         }
       }

@@ -1,0 +1,59 @@
+"""GPU parity: the CUDA path through the C-ABI vs the CPU oracle, bit-exact."""
+import numpy as np
+import pytest
+
+import oracle
+from kueue_b200 import abi, synth
+from kueue_b200.api import flatten
+from tests.golden.tree_cases import TREE_CASES
+from tests.helpers import assert_cycle_equal
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ev():
+    from kueue_b200 import native
+    e = native.Evaluator(0)
+    yield e
+    e.close()
+
+
+@pytest.mark.parametrize("name", list(TREE_CASES))
+def test_tree_golden(ev, name):
+    tc = TREE_CASES[name]
+    snap, idx = flatten(tc["cqs"], tc["cohorts"], usage=tc["usage"])
+    out = ev.tree_eval(snap)
+    for cq, m in tc["want_available"].items():
+        for (f, r), v in m.items():
+            assert out.available[idx.cqs.index(cq), idx.fr(f, r)] == v
+    for cq, m in tc["want_potential"].items():
+        for (f, r), v in m.items():
+            assert out.potential_available[idx.cqs.index(cq), idx.fr(f, r)] == v
+
+
+@pytest.mark.parametrize("config,kw", [(1, {}), (2, dict(W=5000, Q=50)), (2, dict(W=20000, Q=200, podsets_max=3)),
+                                        (4, dict(W=4000, Q=200))])
+def test_tree_matches_oracle(ev, config, kw):
+    snap = synth.make_snapshot(config, **kw)
+    got, want = ev.tree_eval(snap), oracle.tree_eval(snap)
+    for f in ("subtree_quota", "usage", "available", "potential_available", "drs_rounded", "drs_resource", "drs_borrowing"):
+        assert np.array_equal(getattr(got, f), getattr(want, f)), f
+
+
+@pytest.mark.parametrize("config,kw", [
+    (1, {}), (1, dict(heads="one_per_cq")),
+    (2, dict(W=5000, Q=50)), (2, dict(W=5000, Q=50, heads="one_per_cq")),
+    (2, dict(W=20000, Q=200, podsets_max=3)),
+    (4, dict(W=4000, Q=200)), (4, dict(W=4000, Q=200, heads="one_per_cq", podsets_max=2)),
+])
+def test_cycle_matches_oracle(ev, config, kw):
+    snap = synth.make_snapshot(config, **kw)
+    got, want = ev.run_cycle(snap), oracle.run_cycle(snap)
+    assert_cycle_equal(got, want)
+
+
+def test_full_size_config2(ev):
+    snap = synth.make_snapshot(2)
+    got, want = ev.run_cycle(snap), oracle.run_cycle(snap)
+    assert_cycle_equal(got, want)
