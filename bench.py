@@ -152,7 +152,8 @@ def main():
     # each rank owns its own shard of the cluster: independent root cohorts => no collective on the data path
     snap = synth.make_snapshot(args.config, seed=args.config * 1000 + rank)
     ev = native.Evaluator(local_rank)
-    out = abi.CycleOut(snap)
+    snap = native.pin_snapshot(snap)            # host SoA buffers are page-locked (kb_alloc_pinned)
+    out = native.pin_cycle_out(abi.CycleOut(snap))
     flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
 
     def barrier():

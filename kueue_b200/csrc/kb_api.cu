@@ -56,7 +56,9 @@ struct kb_handle {
   // tree_eval scratch
   i64 *d_drs_rounded = nullptr; int32_t *d_drs_res = nullptr; uint8_t *d_drs_borrowing = nullptr;
   // host-side derived topology
-  std::vector<int32_t> root_slot, depth, height, tree_start, tree_nodes, tree_level, lone, cq_adm_start, cq_adm;
+  std::vector<int32_t> root_slot, depth, height, tree_start, tree_nodes, tree_level, lone, cq_adm_start, cq_adm, local_idx;
+  int max_tree_nodes = 1;
+  int max_root_entries_hint = 0;
 };
 
 static thread_local std::string g_err;
@@ -196,6 +198,13 @@ static int32_t build_topology(kb_handle *h, const kb_snapshot *s) {
       h->tree_nodes[h->tree_start[t] + pos] = n;
     }
   }
+  h->local_idx.assign(N, 0);
+  h->max_tree_nodes = 1;
+  for (int t = 0; t < ntrees; t++) {
+    int nn = h->tree_start[t + 1] - h->tree_start[t];
+    h->max_tree_nodes = std::max(h->max_tree_nodes, nn);
+    for (int i = 0; i < nn; i++) h->local_idx[h->tree_nodes[h->tree_start[t] + i]] = i;
+  }
   // admitted workloads grouped by CQ (ClusterQueueSnapshot.Workloads)
   h->cq_adm_start.assign(Q + 1, 0);
   for (int a = 0; a < s->n_adm; a++) {
@@ -255,7 +264,7 @@ extern "C" int32_t kb_upload(kb_handle *h, const kb_snapshot *s) {
   need(A, 4); need(A, 4); need(A, 8); need(A, 8); need(A, 8); need(A, 1); need(A + 1, 4); need(s->n_adm_use, 4); need(s->n_adm_use, 8);
   need(H, 4);
   need(N, 4); need(N, 4); need(N, 4); need(ntrees + 1, 4); need(h->tree_nodes.size(), 4); need(h->tree_level.size(), 4);
-  need(h->lone.size(), 4); need(Q + 1, 4); need(h->cq_adm.size(), 4);
+  need(h->lone.size(), 4); need(Q + 1, 4); need(h->cq_adm.size(), 4); need(N, 4);
   need(NF, 8); need(NF, 8); need(NF, 8); need(NF, 8);
   need(nroots, 4); need(nroots + 1, 4); need(nroots, 4); need(H, 4);
   need(H, 1); need(H, 1); need(H, 4); need(H, 4); need(P * R, 1); need(P * R, 1); need(P * R, 1); need(P, 4);
@@ -285,6 +294,7 @@ extern "C" int32_t kb_upload(kb_handle *h, const kb_snapshot *s) {
   UP(root_slot, h->root_slot.data(), N); UP(depth, h->depth.data(), N); UP(height, h->height.data(), N);
   UP(tree_start, h->tree_start.data(), ntrees + 1); UP(tree_nodes, h->tree_nodes.data(), h->tree_nodes.size());
   UP(tree_level, h->tree_level.data(), h->tree_level.size()); UP(lone_cqs, h->lone.data(), h->lone.size());
+  UP(local_idx, h->local_idx.data(), N);
   UP(cq_adm_start, h->cq_adm_start.data(), Q + 1); UP(cq_adm, h->cq_adm.data(), h->cq_adm.size());
 #undef UP
   D.subtree = h->arena.take<i64>(NF); D.usage = h->arena.take<i64>(NF);
@@ -301,6 +311,7 @@ extern "C" int32_t kb_upload(kb_handle *h, const kb_snapshot *s) {
   CUDA_TRY(h, cudaMemsetAsync(D.ps_flavor, 0xff, P * R, h->stream));
   CUDA_TRY(h, cudaMemsetAsync(D.ps_res_mode, 0xff, P * R, h->stream));
   CUDA_TRY(h, cudaMemsetAsync(D.ps_tried, 0xff, P * R, h->stream));
+  CUDA_TRY(h, cudaMemsetAsync(D.ps_count_out, 0, P * 4, h->stream));
   CUDA_TRY(h, cudaEventRecord(h->ev1, h->stream));
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));  // host vectors / caller buffers may be released after return
   float ms = 0; cudaEventElapsedTime(&ms, h->ev0, h->ev1);
@@ -322,6 +333,45 @@ static int32_t launch_tree(kb_handle *h, int *launches) {
   return KB_OK;
 }
 
+// admit kernel launches: lone-CQ roots (slots [0, nLone)) and cohort-tree roots
+// (slots [nLone, nRoots)) separately so each class gets the shared memory it needs.
+static size_t admit_smem(int nn_tables, int FR, int sort_cap) {
+  size_t tb = (size_t)nn_tables * FR * 32;
+  size_t mid = std::max((size_t)sort_cap * 20, (size_t)KB_TILE * FR * 8);
+  return tb + mid + 8 + (size_t)nn_tables * 4 + KB_TILE * 16 + (KB_MAX_DEPTH + 1) * 4 + 64;
+}
+static int32_t launch_admit(kb_handle *h, int *launches) {
+  DevSnap &D = h->D;
+  const size_t kMaxSmem = 200 * 1024;
+  // sort capacity: entries per root are at most H; cap by what shared memory allows
+  auto pick_cap = [&](int nn_tables) {
+    int cap = 64;
+    while (cap < KB_SORT_CAP && cap < D.H && admit_smem(nn_tables, D.FR, cap * 2) <= kMaxSmem) cap *= 2;
+    return cap;
+  };
+  if (D.nLone) {
+    int cap = pick_cap(1);
+    size_t sm = admit_smem(1, D.FR, cap);
+    CUDA_TRY(h, cudaFuncSetAttribute(k_admit<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
+    k_admit<true><<<D.nLone, 128, sm, h->stream>>>(D, 0, cap); (*launches)++;
+  }
+  if (D.nTrees) {
+    bool fits = admit_smem(h->max_tree_nodes, D.FR, 64) <= kMaxSmem;
+    if (fits) {
+      int cap = pick_cap(h->max_tree_nodes);
+      size_t sm = admit_smem(h->max_tree_nodes, D.FR, cap);
+      CUDA_TRY(h, cudaFuncSetAttribute(k_admit<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
+      k_admit<true><<<D.nTrees, 128, sm, h->stream>>>(D, D.nLone, cap); (*launches)++;
+    } else {
+      int cap = pick_cap(0);
+      size_t sm = admit_smem(0, D.FR, cap);
+      CUDA_TRY(h, cudaFuncSetAttribute(k_admit<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
+      k_admit<false><<<D.nTrees, 128, sm, h->stream>>>(D, D.nLone, cap); (*launches)++;
+    }
+  }
+  return KB_OK;
+}
+
 extern "C" int32_t kb_cycle_resident(kb_handle *h) {
   if (!h || !h->uploaded) return fail(h, KB_ERR_INVALID, "kb_upload first");
   cudaSetDevice(h->device);
@@ -331,16 +381,19 @@ extern "C" int32_t kb_cycle_resident(kb_handle *h) {
   CUDA_TRY(h, cudaMemsetAsync(D.status, 0, 4, h->stream));
   CUDA_TRY(h, cudaMemsetAsync(D.root_count, 0, sizeof(int32_t) * (size_t)std::max(1, D.nRoots), h->stream));
   h->kev_n = 0;
+  int32_t rc_admit = KB_OK;
   if ((D.flags & KB_F_FAIR_SHARING) && D.H) return fail(h, KB_ERR_UNSUPPORTED, "fair sharing iterator not built yet");
   launch_tree(h, &launches);
   if (D.H) {
     kmark(h, KB_K_NOMINATE); k_nominate<<<(D.H + 127) / 128, 128, 0, h->stream>>>(D); launches++;
     kmark(h, KB_K_SCAN); k_scan_roots<<<1, 1024, 0, h->stream>>>(D); launches++;
     kmark(h, KB_K_SCATTER); k_scatter<<<(D.H + 255) / 256, 256, 0, h->stream>>>(D); launches++;
-    kmark(h, KB_K_ADMIT); k_admit<<<D.nRoots, 128, 0, h->stream>>>(D); launches++;
+    kmark(h, KB_K_ADMIT);
+    rc_admit = launch_admit(h, &launches);
   }
   kmark(h, -1);
   CUDA_TRY(h, cudaEventRecord(h->ev3, h->stream));
+  if (rc_admit != KB_OK) return rc_admit;
   CUDA_TRY(h, cudaGetLastError());
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
   float ms = 0; cudaEventElapsedTime(&ms, h->ev2, h->ev3);

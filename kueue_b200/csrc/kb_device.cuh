@@ -56,6 +56,7 @@ struct DevSnap {
   const int32_t *tree_start;  // [nTrees+1] into tree_nodes (cohort-rooted trees)
   const int32_t *tree_nodes;  // per tree: nodes ordered by depth ascending (root first)
   const int32_t *tree_level;  // [nTrees][KB_LEVELS] start (relative) of each depth level
+  const int32_t *local_idx;   // [N] position of the node inside its tree (0 for lone CQs)
   const int32_t *lone_cqs;    // CQs without a cohort
   const int32_t *cq_adm_start;// [Q+1] admitted workloads grouped by CQ
   const int32_t *cq_adm;      // [A]

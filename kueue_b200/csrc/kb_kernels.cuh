@@ -379,173 +379,232 @@ __global__ void k_scatter(DevSnap D) {
 }
 
 // ---------------------------------------------------------------------------
-// K5: ordered admit loop, one CTA per root.
+// K5: ordered admit loop, one CTA per root (scheduler.go:269-401).
+//
+// Layout of the work inside the CTA:
+//   1. sort the root's entries by the classical iterator order (scheduler.go:778-817)
+//      with packed keys in shared memory (bitonic network, all threads);
+//   2. stage the root's quota tree (usage, SubtreeQuota, localQuota, BorrowingLimit
+//      per (node, fr)) in shared memory when it fits — the cohort tree of one root is
+//      the whole coupling domain of the admit loop, so the sequential part never
+//      touches HBM;
+//   3. per tile of KB_TILE entries: all threads expand the assignments into a dense
+//      request matrix q[entry][fr] in shared memory (coalesced reads of the podset
+//      rows), then warp 0 commits the tile in order — lane l owns the flavor-resource
+//      columns l, l+32, ...; columns are independent in the quota tree, so fit checks
+//      and addUsage run lane-parallel with one __all_sync per entry.
 // ---------------------------------------------------------------------------
-// classical iterator order scheduler.go:778-817 + canonical tie-break (cq, uid)
-__device__ __forceinline__ bool entry_before(const DevSnap &D, int a, int b) {
-  if (a == b) return false;
-  if (a < 0) return false;  // padding sorts last
-  if (b < 0) return true;
-  int ba = D.borrow[a], bb = D.borrow[b];
-  if (ba != bb) return ba < bb;
-  int wa = D.heads[a], wb = D.heads[b];
-  if (D.flags & KB_F_PRIORITY_SORTING_WITHIN_COHORT) {
-    int pa = D.wl_priority[wa], pb = D.wl_priority[wb];
-    if (pa != pb) return pa > pb;
-  }
-  i64 ta = D.wl_ts[wa], tb = D.wl_ts[wb];
-  if (ta != tb) return ta < tb;
-  int ca = D.wl_cq[wa], cb = D.wl_cq[wb];
-  if (ca != cb) return ca < cb;
-  return D.wl_uid[wa] < D.wl_uid[wb];
+#define KB_TILE 64
+#define KB_SORT_CAP 1024  // entries per root sortable in shared memory
+
+// sort key: (borrow asc, priority desc, ts asc, workload index asc)
+__device__ __forceinline__ void entry_key(const DevSnap &D, int e, u64 *k0, u64 *k1) {
+  int wl = D.heads[e];
+  unsigned prio = 0;
+  if (D.flags & KB_F_PRIORITY_SORTING_WITHIN_COHORT) prio = 0x7fffffffu - (unsigned)(D.wl_priority[wl] ^ 0x80000000);  // desc
+  *k0 = ((u64)(unsigned)D.borrow[e] << 32) | prio;
+  *k1 = (u64)D.wl_ts[wl] ^ 0x8000000000000000ull;
+}
+__device__ __forceinline__ bool key_less(u64 a0, u64 a1, int aw, u64 b0, u64 b1, int bw) {
+  if (a0 != b0) return a0 < b0;
+  if (a1 != b1) return a1 < b1;
+  return aw < bw;
 }
 
-#define KB_SORT_SMEM 2048
-#define KB_MAX_CELLS 128
+struct AdmitSmem {  // carve-up of the dynamic shared memory
+  i64 *usage, *sub, *lq, *bl;  // [nn][FR] (tables-in-smem mode)
+  int *lparent;                // [nn] local parent index or -1
+  i64 *q;                      // [KB_TILE][FR]; absent cell = -1
+  u64 *k0, *k1;                // [np2] sort keys (aliases q/tile region: sort happens first)
+  int *kidx;                   // [np2]
+  int *t_e, *t_node, *t_mode, *t_borrow;  // [KB_TILE] tile meta
+  int *path;                   // [KB_MAX_DEPTH+1]
+};
 
-// available() on the live usage for one cell, walking the CQ's path (resource_node.go:104-118)
-__device__ inline i64 live_available(const DevSnap &D, const int *path, int plen, int fr) {
-  int FR = D.FR;
-  size_t c = (size_t)path[plen - 1] * FR + fr;
-  i64 a = D.subtree[c] - __ldcg(&D.usage[c]);
-  for (int k = plen - 2; k >= 0; k--) {
-    c = (size_t)path[k] * FR + fr;
-    i64 sub = D.subtree[c], u = __ldcg(&D.usage[c]);
-    i64 lq = local_quota(sub, D.llimit[c]);
-    i64 bl = D.blimit[c];
-    i64 pa = a;
-    if (bl != KB_NO_LIMIT) pa = imin((sub - lq) - imax(0, u - lq) + bl, pa);
-    a = imax(0, lq - u) + pa;
-  }
-  return a;
-}
-// addUsage resource_node.go:137-145
-__device__ inline void live_add_usage(const DevSnap &D, const int *path, int plen, int fr, i64 val) {
-  int FR = D.FR;
-  for (int k = 0; k < plen; k++) {
-    size_t c = (size_t)path[k] * FR + fr;
-    i64 u = __ldcg(&D.usage[c]);
-    i64 la = imax(0, local_quota(D.subtree[c], D.llimit[c]) - u);
-    __stcg(&D.usage[c], u + val);
-    if (!(k + 1 < plen && val > la)) break;
-    val -= la;
-  }
-}
-
-__global__ void __launch_bounds__(128) k_admit(DevSnap D) {
-  __shared__ int32_t s_idx[KB_SORT_SMEM];
-  __shared__ int s_path[KB_MAX_DEPTH + 1];
-  __shared__ int s_cell_fr[KB_MAX_CELLS];
-  __shared__ i64 s_cell_q[KB_MAX_CELLS];
-  __shared__ int s_ncell, s_plen;
-  int slot = blockIdx.x;
+template <bool kSmemTables>
+__global__ void __launch_bounds__(128) k_admit(DevSnap D, int slot_base, int sort_cap) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int FR = D.FR, R = D.R;
+  int slot = slot_base + blockIdx.x;
   int off = D.root_offset[slot];
   int n = D.root_offset[slot + 1] - off;
   if (n == 0) return;
   int32_t *ent = D.root_entries + off;
-  // ---- sort the root's entries (bitonic, padded to a power of two with -1) ----
+  // nodes of this root
+  const int32_t *nodes; int nn; int lone_node = -1;
+  if (slot < D.nLone) { lone_node = D.lone_cqs[slot]; nodes = &D.lone_cqs[slot]; nn = 1; }
+  else { int t = slot - D.nLone; nodes = D.tree_nodes + D.tree_start[t]; nn = D.tree_start[t + 1] - D.tree_start[t]; }
+  (void)lone_node;
+  // ---- smem carve-up ----
+  AdmitSmem S;
+  unsigned char *p = smem_raw;
+  size_t tb = kSmemTables ? (size_t)nn * FR : 0;
+  S.usage = (i64 *)p; p += tb * 8; S.sub = (i64 *)p; p += tb * 8; S.lq = (i64 *)p; p += tb * 8; S.bl = (i64 *)p; p += tb * 8;
+  S.q = (i64 *)p;
+  S.k0 = (u64 *)p; S.k1 = S.k0 + sort_cap; S.kidx = (int *)(S.k1 + sort_cap);
+  size_t sort_bytes = (size_t)sort_cap * 20, tile_bytes = (size_t)KB_TILE * FR * 8;
+  p += (sort_bytes > tile_bytes ? sort_bytes : tile_bytes);
+  p = (unsigned char *)(((uintptr_t)p + 7) & ~(uintptr_t)7);
+  S.lparent = (int *)p; p += (kSmemTables ? nn : 0) * 4;
+  S.t_e = (int *)p; p += KB_TILE * 4; S.t_node = (int *)p; p += KB_TILE * 4; S.t_mode = (int *)p; p += KB_TILE * 4; S.t_borrow = (int *)p; p += KB_TILE * 4;
+  S.path = (int *)p;
+
+  // ---- 1. sort ----
   int np2 = 1;
   while (np2 < n) np2 <<= 1;
-  bool in_smem = np2 <= KB_SORT_SMEM;
-  if (in_smem) {
-    for (int i = threadIdx.x; i < np2; i += blockDim.x) s_idx[i] = i < n ? ent[i] : -1;
+  if (n > 1 && np2 <= sort_cap) {
+    for (int i = threadIdx.x; i < np2; i += blockDim.x) {
+      if (i < n) { int e = ent[i]; entry_key(D, e, &S.k0[i], &S.k1[i]); S.kidx[i] = e; }
+      else { S.k0[i] = ~0ull; S.k1[i] = ~0ull; S.kidx[i] = INT32_MAX; }
+    }
     __syncthreads();
     for (int k = 2; k <= np2; k <<= 1)
       for (int j = k >> 1; j > 0; j >>= 1) {
         for (int i = threadIdx.x; i < np2; i += blockDim.x) {
           int l = i ^ j;
           if (l > i) {
-            int a = s_idx[i], b = s_idx[l];
+            u64 a0 = S.k0[i], a1 = S.k1[i], b0 = S.k0[l], b1 = S.k1[l];
+            int ai = S.kidx[i], bi = S.kidx[l];
+            int aw = ai == INT32_MAX ? INT32_MAX : D.heads[ai], bw = bi == INT32_MAX ? INT32_MAX : D.heads[bi];
             bool up = (i & k) == 0;
-            if (up ? entry_before(D, b, a) : entry_before(D, a, b)) { s_idx[i] = b; s_idx[l] = a; }
+            bool sw = up ? key_less(b0, b1, bw, a0, a1, aw) : key_less(a0, a1, aw, b0, b1, bw);
+            if (sw) { S.k0[i] = b0; S.k1[i] = b1; S.kidx[i] = bi; S.k0[l] = a0; S.k1[l] = a1; S.kidx[l] = ai; }
           }
         }
         __syncthreads();
       }
-    for (int i = threadIdx.x; i < n; i += blockDim.x) ent[i] = s_idx[i];
+    for (int i = threadIdx.x; i < n; i += blockDim.x) ent[i] = S.kidx[i];
     __syncthreads();
   } else if (n > 1) {
-    // large root: odd-even transposition would be O(n^2); use a global-memory bitonic network on
-    // a virtual padded array (indices >= n behave as -1 and are never written).
-    for (int k = 2; k <= np2; k <<= 1)
-      for (int j = k >> 1; j > 0; j >>= 1) {
-        for (int i = threadIdx.x; i < np2; i += blockDim.x) {
-          int l = i ^ j;
-          if (l > i) {
-            int a = i < n ? ent[i] : -1, b = l < n ? ent[l] : -1;
-            bool up = (i & k) == 0;
-            if (up ? entry_before(D, b, a) : entry_before(D, a, b)) {
-              // padding (-1) sorts last, so a swap never moves a real entry beyond n when ascending
-              if (i < n) ent[i] = b;
-              if (l < n) ent[l] = a;
-            }
-          }
-        }
+    // root with more entries than the shared-memory sort holds: ascending-only bitonic
+    // network over the global index array (virtual +inf padding beyond n never moves),
+    // keys re-read through L2.
+    auto ce = [&](int i, int l) {  // compare-exchange, minimum to the lower index
+      int a = ent[i], b = ent[l];
+      u64 a0, a1, b0, b1; entry_key(D, a, &a0, &a1); entry_key(D, b, &b0, &b1);
+      if (key_less(b0, b1, D.heads[b], a0, a1, D.heads[a])) { ent[i] = b; ent[l] = a; }
+    };
+    for (int k = 2; k <= np2; k <<= 1) {
+      for (int i = threadIdx.x; i < n; i += blockDim.x) { int l = i ^ (k - 1); if (l > i && l < n) ce(i, l); }
+      __syncthreads();
+      for (int j = k >> 2; j > 0; j >>= 1) {
+        for (int i = threadIdx.x; i < n; i += blockDim.x) { int l = i ^ j; if (l > i && l < n) ce(i, l); }
         __syncthreads();
       }
+    }
   }
-  if (threadIdx.x >= 32) return;
-  // ---- sequential commit by warp 0, one lane per flavor-resource cell ----
-  const int lane = threadIdx.x;
-  const int R = D.R;
-  for (int i = 0; i < n; i++) {
-    int e = ent[i];
-    int wl = D.heads[e];
-    int cq = D.wl_cq[wl];
-    int mode = D.mode[e];
-    if (lane == 0) D.rank[e] = i;
-    if (mode == KB_MODE_NOFIT) { if (lane == 0) D.decision[e] = KB_DEC_NOFIT; continue; }
-    if (lane == 0) {
-      // path CQ -> root
-      int pl = 0;
-      for (int t = cq; t >= 0 && pl <= KB_MAX_DEPTH; t = D.parent[t]) s_path[pl++] = t;
-      s_plen = pl;
-      // aggregated assignment usage (Assignment.Usage.Quota, append :734)
+  // ---- 2. stage the tree ----
+  if (kSmemTables) {
+    for (int i = threadIdx.x; i < nn * FR; i += blockDim.x) {
+      int nd = nodes[i / FR], fr = i % FR;
+      size_t c = (size_t)nd * FR + fr;
+      i64 sub = D.subtree[c];
+      S.usage[i] = D.usage[c]; S.sub[i] = sub; S.lq[i] = local_quota(sub, D.llimit[c]); S.bl[i] = D.blimit[c];
+    }
+    for (int i = threadIdx.x; i < nn; i += blockDim.x) {
+      int pn = D.parent[nodes[i]];
+      S.lparent[i] = pn < 0 ? -1 : D.local_idx[pn];
+    }
+  }
+  __syncthreads();
+
+  // accessors: node handle = local index (smem tables) or global node id
+  auto getU = [&](int nd, int fr) -> i64 { return kSmemTables ? S.usage[nd * FR + fr] : __ldcg(&D.usage[(size_t)nd * FR + fr]); };
+  auto setU = [&](int nd, int fr, i64 v) { if (kSmemTables) S.usage[nd * FR + fr] = v; else __stcg(&D.usage[(size_t)nd * FR + fr], v); };
+  auto getSub = [&](int nd, int fr) -> i64 { return kSmemTables ? S.sub[nd * FR + fr] : D.subtree[(size_t)nd * FR + fr]; };
+  auto getLQ = [&](int nd, int fr) -> i64 { return kSmemTables ? S.lq[nd * FR + fr] : local_quota(D.subtree[(size_t)nd * FR + fr], D.llimit[(size_t)nd * FR + fr]); };
+  auto getBL = [&](int nd, int fr) -> i64 { return kSmemTables ? S.bl[nd * FR + fr] : D.blimit[(size_t)nd * FR + fr]; };
+  auto parentOf = [&](int nd) -> int { return kSmemTables ? S.lparent[nd] : D.parent[nd]; };
+  // available() resource_node.go:104-118 along the staged path (path[0] = CQ ... path[plen-1] = root)
+  auto liveAvail = [&](int plen, int fr) -> i64 {
+    int rt = S.path[plen - 1];
+    i64 a = getSub(rt, fr) - getU(rt, fr);
+    for (int k = plen - 2; k >= 0; k--) {
+      int nd = S.path[k];
+      i64 u = getU(nd, fr), lq = getLQ(nd, fr), bl = getBL(nd, fr);
+      i64 pa = a;
+      if (bl != KB_NO_LIMIT) pa = imin((getSub(nd, fr) - lq) - imax(0, u - lq) + bl, pa);
+      a = imax(0, lq - u) + pa;
+    }
+    return a;
+  };
+  auto liveAdd = [&](int plen, int fr, i64 val) {  // addUsage :137-145
+    for (int k = 0; k < plen; k++) {
+      int nd = S.path[k];
+      i64 u = getU(nd, fr);
+      i64 la = imax(0, getLQ(nd, fr) - u);
+      setU(nd, fr, u + val);
+      if (!(k + 1 < plen && val > la)) break;
+      val -= la;
+    }
+  };
+
+  // ---- 3. tiles ----
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int base = 0; base < n; base += KB_TILE) {
+    int tn = min(KB_TILE, n - base);
+    // 3a. expand: dense request matrix + meta
+    for (int i = threadIdx.x; i < tn; i += blockDim.x) {
+      int e = ent[base + i];
+      int wl = D.heads[e];
+      int cq = D.wl_cq[wl];
+      S.t_e[i] = e; S.t_node[i] = kSmemTables ? D.local_idx[cq] : cq;
+      S.t_mode[i] = D.mode[e]; S.t_borrow[i] = D.borrow[e];
+    }
+    for (int c = threadIdx.x; c < tn * FR; c += blockDim.x) {
+      int i = c / FR, fr = c % FR, f = fr / R, r = fr % R;
+      int e = ent[base + i];
+      int wl = D.heads[e];
+      int cq = D.wl_cq[wl];
       bool covers_pods = D.pods_res >= 0 && rg_by_resource(D, cq, D.pods_res) >= 0;
-      int nc = 0;
+      i64 q = -1;
       for (int row = D.wl_ps_start[wl]; row < D.wl_ps_start[wl + 1]; row++)
-        for (int r = 0; r < R; r++) {
-          int f = D.ps_flavor[(size_t)row * R + r];
-          if (f < 0) continue;
-          int fr = f * R + r;
-          i64 q = ps_request(D, row, r, D.ps_count_out[row], covers_pods);
-          int k = 0;
-          while (k < nc && s_cell_fr[k] != fr) k++;
-          if (k == nc) {
-            if (nc == KB_MAX_CELLS) { atomicOr(D.status, KBS_TARGET_OVERFLOW); continue; }
-            s_cell_fr[nc] = fr; s_cell_q[nc] = 0; nc++;
+        if (D.ps_flavor[(size_t)row * R + r] == f) q = (q < 0 ? 0 : q) + ps_request(D, row, r, D.ps_count_out[row], covers_pods);
+      S.q[c] = q;
+    }
+    __syncthreads();
+    // 3b. commit in order (warp 0)
+    if (warp == 0) {
+      for (int i = 0; i < tn; i++) {
+        int e = S.t_e[i], mode = S.t_mode[i], nd = S.t_node[i];
+        if (lane == 0) D.rank[e] = base + i;
+        if (mode == KB_MODE_NOFIT) { if (lane == 0) D.decision[e] = KB_DEC_NOFIT; continue; }
+        if (lane == 0) { int pl = 0; for (int t = nd; t >= 0; t = parentOf(t)) S.path[pl++] = t; S.path[KB_MAX_DEPTH] = pl; }
+        __syncwarp();
+        int plen = S.path[KB_MAX_DEPTH];
+        const i64 *qrow = S.q + (size_t)i * FR;
+        if (mode == KB_MODE_PREEMPT) {  // Preempt without targets: scheduler.go:303-318
+          if (lane == 0) D.decision[e] = KB_DEC_PREEMPT_NO_TARGETS;
+          int cq = D.wl_cq[D.heads[e]];
+          if (D.cq_reclaim_within[cq] != KB_POLICY_ANY) {  // !CanAlwaysReclaim policy.go:27-29
+            int borrowing = S.t_borrow[i];
+            for (int fr = lane; fr < FR; fr += 32) {  // quotaResourcesToReserve :530-548
+              i64 u = qrow[fr];
+              if (u < 0) continue;
+              i64 nominal = getSub(nd, fr), bl = getBL(nd, fr), cur = getU(nd, fr);  // CQ: SubtreeQuota == Nominal
+              i64 rsv;
+              if (borrowing > 0) rsv = bl == KB_NO_LIMIT ? u : imin(u, nominal + bl - cur);
+              else rsv = imax(0, imin(u, nominal - cur));
+              liveAdd(plen, fr, rsv);
+            }
           }
-          s_cell_q[k] += q;
+          __syncwarp();
+          continue;
         }
-      s_ncell = nc;
-    }
-    __syncwarp();
-    int nc = s_ncell, plen = s_plen;
-    if (mode == KB_MODE_PREEMPT) {  // no targets in this build: scheduler.go:303-318
-      if (lane == 0) D.decision[e] = KB_DEC_PREEMPT_NO_TARGETS;
-      if (D.cq_reclaim_within[cq] != KB_POLICY_ANY) {  // !CanAlwaysReclaim policy.go:27-29
-        int borrowing = D.borrow[e];
-        for (int k = lane; k < nc; k += 32) {  // quotaResourcesToReserve :530-548
-          int fr = s_cell_fr[k];
-          size_t c = (size_t)cq * D.FR + fr;
-          i64 u = s_cell_q[k], nominal = D.nominal[c], bl = D.blimit[c], cur = __ldcg(&D.usage[c]);
-          i64 rsv;
-          if (borrowing > 0) rsv = bl == KB_NO_LIMIT ? u : imin(u, nominal + bl - cur);
-          else rsv = imax(0, imin(u, nominal - cur));
-          live_add_usage(D, s_path, plen, fr, rsv);
+        bool ok = true;  // fits :503-511
+        for (int fr = lane; fr < FR; fr += 32) {
+          i64 q = qrow[fr];
+          if (q > 0 && imax(0, liveAvail(plen, fr)) < q) ok = false;
         }
+        ok = __all_sync(0xffffffffu, ok);
+        if (ok) for (int fr = lane; fr < FR; fr += 32) { i64 q = qrow[fr]; if (q > 0) liveAdd(plen, fr, q); }  // cq.AddUsage :336
+        if (lane == 0) D.decision[e] = ok ? KB_DEC_ASSUMED : KB_DEC_SKIPPED_NO_FIT;
+        __syncwarp();
       }
-      __syncwarp();
-      continue;
     }
-    // fits :503-511 / ClusterQueueSnapshot.Fits :121-136
-    bool ok = true;
-    for (int k = lane; k < nc; k += 32)
-      if (imax(0, live_available(D, s_path, plen, s_cell_fr[k])) < s_cell_q[k]) ok = false;
-    ok = __all_sync(0xffffffffu, ok);
-    if (!ok) { if (lane == 0) D.decision[e] = KB_DEC_SKIPPED_NO_FIT; __syncwarp(); continue; }
-    for (int k = lane; k < nc; k += 32) live_add_usage(D, s_path, plen, s_cell_fr[k], s_cell_q[k]);  // cq.AddUsage :336
-    if (lane == 0) D.decision[e] = KB_DEC_ASSUMED;
-    __syncwarp();
+    __syncthreads();
   }
+  // ---- 4. publish the final usage ----
+  if (kSmemTables)
+    for (int i = threadIdx.x; i < nn * FR; i += blockDim.x) D.usage[(size_t)nodes[i / FR] * FR + i % FR] = S.usage[i];
 }

@@ -39,6 +39,49 @@ def lib():
     return _LIB
 
 
+def pinned_array(shape, dtype) -> "np.ndarray":
+    """numpy view over page-locked host memory from kb_alloc_pinned (what the Go shim
+    uses for its SoA buffers so the GC never moves them and H2D copies are DMA)."""
+    import numpy as np
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape)) if shape != () else 1
+    ptr = C.c_void_p()
+    rc = lib().kb_alloc_pinned(C.byref(ptr), C.c_uint64(max(1, n * dtype.itemsize)))
+    if rc != 0:
+        raise KueueB200Error(rc, "kb_alloc_pinned failed")
+    buf = (C.c_char * max(1, n * dtype.itemsize)).from_address(ptr.value)
+    arr = np.frombuffer(buf, dtype=dtype, count=n).reshape(shape)
+    return arr
+
+
+def pin_snapshot(snap: abi.FlatSnapshot) -> abi.FlatSnapshot:
+    """Copy of `snap` whose arrays live in pinned host memory."""
+    out = abi.FlatSnapshot(n_cq=snap.n_cq, n_cohort=snap.n_cohort, n_flavor=snap.n_flavor, n_resource=snap.n_resource,
+                           pods_resource=snap.pods_resource, flags=snap.flags, now_ns=snap.now_ns)
+    for k, v in snap.arrays.items():
+        a = pinned_array(v.shape, v.dtype)
+        a[...] = v
+        out.arrays[k] = a
+    return out
+
+
+def pin_cycle_out(out: abi.CycleOut) -> abi.CycleOut:
+    """Re-point the output buffers at pinned host memory."""
+    import numpy as np
+    for name, ctype in (("decision", C.c_uint8), ("mode", C.c_uint8), ("borrow", C.c_int32), ("commit_rank", C.c_int32),
+                        ("ps_flavor", C.c_int8), ("ps_res_mode", C.c_int8), ("ps_tried_idx", C.c_int8),
+                        ("ps_count", C.c_int32), ("tgt_start", C.c_int32), ("tgt_adm", C.c_int32),
+                        ("tgt_reason", C.c_uint8), ("node_usage", C.c_int64)):
+        old = getattr(out, name)
+        if old is None:
+            continue
+        a = pinned_array(old.shape, old.dtype)
+        a[...] = old
+        setattr(out, name, a)
+        setattr(out.struct, name, a.ctypes.data_as(C.POINTER(ctype)))
+    return out
+
+
 class Evaluator:
     """One kb_handle (one CUDA device, one stream)."""
 

@@ -16,7 +16,7 @@
 //
 // Canonical tie-breaks where the reference is nondeterministic:
 //   * classical iterator ties (scheduler.go:779 unstable sort, comparator 0 at
-//     :816): break by (cq index, uid).
+//     :816): break by the workload's index in the pending table.
 //   * child iteration (hierarchy/cohort.go:44-50 UnsortedList): child cohorts
 //     ascending node index, then child CQs ascending index.
 //   * resource iteration inside findFlavorForPodSets / assignFlavors (Go map
@@ -957,8 +957,7 @@ class Oracle {
         if (a.a.borrowing != b.a.borrowing) return a.a.borrowing < b.a.borrowing;
         if (prio && s.wl_priority[a.wl] != s.wl_priority[b.wl]) return s.wl_priority[a.wl] > s.wl_priority[b.wl];
         if (s.wl_ts[a.wl] != s.wl_ts[b.wl]) return s.wl_ts[a.wl] < s.wl_ts[b.wl];
-        if (s.wl_cq[a.wl] != s.wl_cq[b.wl]) return s.wl_cq[a.wl] < s.wl_cq[b.wl];  // canonical tie-break
-        return s.wl_uid[a.wl] < s.wl_uid[b.wl];
+        return a.wl < b.wl;  // canonical tie-break: index in the pending table
       });
     }
     std::vector<char> preempted(s.n_adm, 0);  // PreemptedWorkloads
