@@ -41,6 +41,11 @@ WORKLOADS = {
 }
 
 
+# cfg3 runs the fair-sharing iterator, which holds one entry per ClusterQueue
+# (fair_sharing_iterator.go:52-54): its step is one reference cycle over the Q heads.
+HEADS = {1: "all", 2: "all", 3: "one_per_cq", 4: "all"}
+
+
 def algorithmic_bytes(snap) -> dict:
     """B = W_eval*(P*R*8 + 24) + W_eval*out_B + (Q+C)*FR*32 + (Q+C)*16."""
     W = snap.n_heads
@@ -109,7 +114,7 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     import oracle
-    snap = synth.make_snapshot(args.config)
+    snap = synth.make_snapshot(args.config, heads=HEADS[args.config])
     for _ in range(args.warmup):
         oracle.run_cycle(snap)
     t0 = time.perf_counter()
@@ -150,7 +155,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     # each rank owns its own shard of the cluster: independent root cohorts => no collective on the data path
-    snap = synth.make_snapshot(args.config, seed=args.config * 1000 + rank)
+    snap = synth.make_snapshot(args.config, seed=args.config * 1000 + rank, heads=HEADS[args.config])
     ev = native.Evaluator(local_rank)
     snap = native.pin_snapshot(snap)            # host SoA buffers are page-locked (kb_alloc_pinned)
     out = native.pin_cycle_out(abi.CycleOut(snap))
@@ -224,7 +229,7 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int64", "data": "synthetic",
-            "config": {"workload": WORKLOADS[args.config], "heads": "all pending workloads (batched evaluator)",
+            "config": {"workload": WORKLOADS[args.config], "heads": "all pending workloads (batched evaluator)" if HEADS[args.config] == "all" else "one head per ClusterQueue (reference cycle)",
                        "decisions_per_step_per_gpu": snap.n_heads, "l2": "512 MiB flush buffer written between timed steps",
                        "timing": "CUDA events on the library stream around the cycle's kernels, summed over steps, max over ranks",
                        "wall_ms_per_step_incl_flush": wall_ms / args.steps},

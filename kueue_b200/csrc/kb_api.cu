@@ -56,7 +56,7 @@ struct kb_handle {
   // tree_eval scratch
   i64 *d_drs_rounded = nullptr; int32_t *d_drs_res = nullptr; uint8_t *d_drs_borrowing = nullptr;
   // host-side derived topology
-  std::vector<int32_t> root_slot, depth, height, tree_start, tree_nodes, tree_level, lone, cq_adm_start, cq_adm, local_idx;
+  std::vector<int32_t> root_slot, depth, height, tree_start, tree_nodes, tree_level, lone, cq_adm_start, cq_adm, local_idx, child_start, child_list;
   int max_tree_nodes = 1;
   int max_root_entries_hint = 0;
 };
@@ -198,6 +198,16 @@ static int32_t build_topology(kb_handle *h, const kb_snapshot *s) {
       h->tree_nodes[h->tree_start[t] + pos] = n;
     }
   }
+  // children CSR (cohort children first: their node ids are >= Q, so sort descending by class)
+  h->child_start.assign(N + 1, 0);
+  for (int n = 0; n < N; n++) if (s->parent[n] >= 0) h->child_start[s->parent[n] + 1]++;
+  for (int n = 0; n < N; n++) h->child_start[n + 1] += h->child_start[n];
+  h->child_list.assign(std::max(1, h->child_start[N]), 0);
+  {
+    std::vector<int32_t> cur(h->child_start.begin(), h->child_start.end() - 1);
+    for (int n = Q; n < N; n++) if (s->parent[n] >= 0) h->child_list[cur[s->parent[n]]++] = n;  // cohorts ascending
+    for (int n = 0; n < Q; n++) if (s->parent[n] >= 0) h->child_list[cur[s->parent[n]]++] = n;  // then CQs ascending
+  }
   h->local_idx.assign(N, 0);
   h->max_tree_nodes = 1;
   for (int t = 0; t < ntrees; t++) {
@@ -225,6 +235,14 @@ static int32_t build_topology(kb_handle *h, const kb_snapshot *s) {
     if (s->wl_ps_start[w + 1] < s->wl_ps_start[w]) return fail(h, KB_ERR_INVALID, "wl_ps_start not monotone");
   }
   if (s->n_wl && s->wl_ps_start[s->n_wl] != s->n_podset) return fail(h, KB_ERR_INVALID, "wl_ps_start[n_wl] != n_podset");
+  if (s->flags & KB_F_FAIR_SHARING) {  // fairSharingIterator keeps one entry per CQ (fair_sharing_iterator.go:52-54)
+    std::vector<char> seen(Q, 0);
+    for (int i = 0; i < s->n_heads; i++) {
+      int c = s->wl_cq[s->heads[i]];
+      if (seen[c]) return fail(h, KB_ERR_INVALID, "fair sharing: more than one head for a ClusterQueue");
+      seen[c] = 1;
+    }
+  }
   h->D.nTrees = ntrees;
   h->D.nLone = (int)h->lone.size();
   h->D.nRoots = nroots;
@@ -264,11 +282,13 @@ extern "C" int32_t kb_upload(kb_handle *h, const kb_snapshot *s) {
   need(A, 4); need(A, 4); need(A, 8); need(A, 8); need(A, 8); need(A, 1); need(A + 1, 4); need(s->n_adm_use, 4); need(s->n_adm_use, 8);
   need(H, 4);
   need(N, 4); need(N, 4); need(N, 4); need(ntrees + 1, 4); need(h->tree_nodes.size(), 4); need(h->tree_level.size(), 4);
-  need(h->lone.size(), 4); need(Q + 1, 4); need(h->cq_adm.size(), 4); need(N, 4);
+  need(h->lone.size(), 4); need(Q + 1, 4); need(h->cq_adm.size(), 4); need(N, 4); need(N + 1, 4); need(h->child_list.size(), 4);
   need(NF, 8); need(NF, 8); need(NF, 8); need(NF, 8);
   need(nroots, 4); need(nroots + 1, 4); need(nroots, 4); need(H, 4);
   need(H, 1); need(H, 1); need(H, 4); need(H, 4); need(P * R, 1); need(P * R, 1); need(P * R, 1); need(P, 4);
   need(1, 4); need(N, 8); need(N, 4); need(N, 1);
+  bool fair = (s->flags & KB_F_FAIR_SHARING) != 0;
+  if (fair) { need(H * FR, 8); need(H * KB_MAX_DEPTH, 16); need(N, 4); need(N, 4); }
   if (!h->arena.reserve(tot + 4096)) return fail(h, KB_ERR_CUDA, "cudaMalloc failed");
   h->arena.reset();
   int64_t bytes = 0;
@@ -295,6 +315,7 @@ extern "C" int32_t kb_upload(kb_handle *h, const kb_snapshot *s) {
   UP(tree_start, h->tree_start.data(), ntrees + 1); UP(tree_nodes, h->tree_nodes.data(), h->tree_nodes.size());
   UP(tree_level, h->tree_level.data(), h->tree_level.size()); UP(lone_cqs, h->lone.data(), h->lone.size());
   UP(local_idx, h->local_idx.data(), N);
+  UP(child_start, h->child_start.data(), N + 1); UP(child_list, h->child_list.data(), h->child_list.size());
   UP(cq_adm_start, h->cq_adm_start.data(), Q + 1); UP(cq_adm, h->cq_adm.data(), h->cq_adm.size());
 #undef UP
   D.subtree = h->arena.take<i64>(NF); D.usage = h->arena.take<i64>(NF);
@@ -306,6 +327,10 @@ extern "C" int32_t kb_upload(kb_handle *h, const kb_snapshot *s) {
   D.ps_flavor = h->arena.take<int8_t>(P * R); D.ps_res_mode = h->arena.take<int8_t>(P * R); D.ps_tried = h->arena.take<int8_t>(P * R);
   D.ps_count_out = h->arena.take<int32_t>(P);
   D.status = h->arena.take<uint32_t>(1);
+  if (fair) {
+    D.q_scratch = h->arena.take<i64>(H * FR); D.fs_drs = h->arena.take<double2>(H * KB_MAX_DEPTH);
+    D.fs_cq_entry = h->arena.take<int32_t>(N); D.fs_winner = h->arena.take<int32_t>(N);
+  }
   h->d_drs_rounded = h->arena.take<i64>(N); h->d_drs_res = h->arena.take<int32_t>(N); h->d_drs_borrowing = h->arena.take<uint8_t>(N);
   // rows of workloads that are not heads stay at -1
   CUDA_TRY(h, cudaMemsetAsync(D.ps_flavor, 0xff, P * R, h->stream));
@@ -338,7 +363,7 @@ static int32_t launch_tree(kb_handle *h, int *launches) {
 static size_t admit_smem(int nn_tables, int FR, int sort_cap) {
   size_t tb = (size_t)nn_tables * FR * 32;
   size_t mid = std::max((size_t)sort_cap * 20, (size_t)KB_TILE * FR * 8);
-  return tb + mid + 8 + (size_t)nn_tables * 4 + KB_TILE * 16 + (KB_MAX_DEPTH + 1) * 4 + 64;
+  return tb + mid + 16 + (size_t)nn_tables * 4 + KB_TILE * 16 + (KB_MAX_DEPTH + 2) * 4 + 64;
 }
 static int32_t launch_admit(kb_handle *h, int *launches) {
   DevSnap &D = h->D;
@@ -355,7 +380,15 @@ static int32_t launch_admit(kb_handle *h, int *launches) {
     CUDA_TRY(h, cudaFuncSetAttribute(k_admit<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
     k_admit<true><<<D.nLone, 128, sm, h->stream>>>(D, 0, cap); (*launches)++;
   }
-  if (D.nTrees) {
+  if (D.nTrees && (D.flags & KB_F_FAIR_SHARING)) {
+    size_t tb = (size_t)h->max_tree_nodes * D.FR * 32 + (size_t)h->max_tree_nodes * 4 + 8 + (KB_MAX_DEPTH + 2) * 4 + 64;
+    if (tb <= kMaxSmem) {
+      CUDA_TRY(h, cudaFuncSetAttribute(k_admit_fair<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
+      k_admit_fair<true><<<D.nTrees, 128, tb, h->stream>>>(D, D.nLone); (*launches)++;
+    } else {
+      k_admit_fair<false><<<D.nTrees, 128, (KB_MAX_DEPTH + 2) * 4 + 64, h->stream>>>(D, D.nLone); (*launches)++;
+    }
+  } else if (D.nTrees) {
     bool fits = admit_smem(h->max_tree_nodes, D.FR, 64) <= kMaxSmem;
     if (fits) {
       int cap = pick_cap(h->max_tree_nodes);
@@ -382,7 +415,6 @@ extern "C" int32_t kb_cycle_resident(kb_handle *h) {
   CUDA_TRY(h, cudaMemsetAsync(D.root_count, 0, sizeof(int32_t) * (size_t)std::max(1, D.nRoots), h->stream));
   h->kev_n = 0;
   int32_t rc_admit = KB_OK;
-  if ((D.flags & KB_F_FAIR_SHARING) && D.H) return fail(h, KB_ERR_UNSUPPORTED, "fair sharing iterator not built yet");
   launch_tree(h, &launches);
   if (D.H) {
     kmark(h, KB_K_NOMINATE); k_nominate<<<(D.H + 127) / 128, 128, 0, h->stream>>>(D); launches++;

@@ -58,6 +58,8 @@ struct DevSnap {
   const int32_t *tree_level;  // [nTrees][KB_LEVELS] start (relative) of each depth level
   const int32_t *local_idx;   // [N] position of the node inside its tree (0 for lone CQs)
   const int32_t *lone_cqs;    // CQs without a cohort
+  const int32_t *child_start; // [N+1] children CSR: child cohorts ascending, then child CQs ascending
+  const int32_t *child_list;
   const int32_t *cq_adm_start;// [Q+1] admitted workloads grouped by CQ
   const int32_t *cq_adm;      // [A]
   int nTrees, nLone, nRoots;
@@ -77,6 +79,11 @@ struct DevSnap {
   int8_t *ps_flavor, *ps_res_mode, *ps_tried;
   int32_t *ps_count_out;
   uint32_t *status;  // [1] KBS_* bits
+  // ---- fair-sharing scratch ----
+  i64 *q_scratch;        // [H][FR] dense Assignment.Usage.Quota per entry (absent = -1)
+  double2 *fs_drs;       // [H][KB_MAX_DEPTH] (unweightedRatio, fairWeight) per path level
+  int32_t *fs_cq_entry;  // [N] entry of a CQ still waiting in this cycle, or -1
+  int32_t *fs_winner;    // [N] tournament winner of a cohort, or -1
 };
 
 __device__ __forceinline__ i64 imax(i64 a, i64 b) { return a > b ? a : b; }

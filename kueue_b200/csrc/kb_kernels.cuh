@@ -411,51 +411,159 @@ __device__ __forceinline__ bool key_less(u64 a0, u64 a1, int aw, u64 b0, u64 b1,
   return aw < bw;
 }
 
-struct AdmitSmem {  // carve-up of the dynamic shared memory
-  i64 *usage, *sub, *lq, *bl;  // [nn][FR] (tables-in-smem mode)
-  int *lparent;                // [nn] local parent index or -1
-  i64 *q;                      // [KB_TILE][FR]; absent cell = -1
-  u64 *k0, *k1;                // [np2] sort keys (aliases q/tile region: sort happens first)
-  int *kidx;                   // [np2]
-  int *t_e, *t_node, *t_mode, *t_borrow;  // [KB_TILE] tile meta
-  int *path;                   // [KB_MAX_DEPTH+1]
+// Quota-tree tables of one root, either staged in shared memory (node handle = local
+// index inside the tree) or left in global memory (node handle = global node id).
+template <bool kSmem>
+struct Tab {
+  const DevSnap *D;
+  i64 *usage; const i64 *sub, *lq, *bl;  // smem mode only
+  const int *lparent;                    // smem mode only
+  int FR;
+  __device__ __forceinline__ i64 U(int nd, int fr) const { return kSmem ? usage[nd * FR + fr] : __ldcg(&D->usage[(size_t)nd * FR + fr]); }
+  __device__ __forceinline__ void setU(int nd, int fr, i64 v) const { if (kSmem) usage[nd * FR + fr] = v; else __stcg(&D->usage[(size_t)nd * FR + fr], v); }
+  __device__ __forceinline__ i64 Sub(int nd, int fr) const { return kSmem ? sub[nd * FR + fr] : D->subtree[(size_t)nd * FR + fr]; }
+  __device__ __forceinline__ i64 LQ(int nd, int fr) const {
+    return kSmem ? lq[nd * FR + fr] : local_quota(D->subtree[(size_t)nd * FR + fr], D->llimit[(size_t)nd * FR + fr]);
+  }
+  __device__ __forceinline__ i64 BL(int nd, int fr) const { return kSmem ? bl[nd * FR + fr] : D->blimit[(size_t)nd * FR + fr]; }
+  __device__ __forceinline__ int parent(int nd) const { return kSmem ? lparent[nd] : D->parent[nd]; }
+  __device__ __forceinline__ int handle(int node) const { return kSmem ? D->local_idx[node] : node; }
+  // available() resource_node.go:104-118 along a staged path (path[0] = CQ ... path[plen-1] = root)
+  __device__ inline i64 avail(const int *path, int plen, int fr) const {
+    int rt = path[plen - 1];
+    i64 a = Sub(rt, fr) - U(rt, fr);
+    for (int k = plen - 2; k >= 0; k--) {
+      int nd = path[k];
+      i64 u = U(nd, fr), l = LQ(nd, fr), b = BL(nd, fr);
+      i64 pa = a;
+      if (b != KB_NO_LIMIT) pa = imin((Sub(nd, fr) - l) - imax(0, u - l) + b, pa);
+      a = imax(0, l - u) + pa;
+    }
+    return a;
+  }
+  __device__ inline void add(const int *path, int plen, int fr, i64 val) const {  // addUsage :137-145
+    for (int k = 0; k < plen; k++) {
+      int nd = path[k];
+      i64 u = U(nd, fr);
+      i64 la = imax(0, LQ(nd, fr) - u);
+      setU(nd, fr, u + val);
+      if (!(k + 1 < plen && val > la)) break;
+      val -= la;
+    }
+  }
 };
+
+// Stage the tables of the root's nodes (all threads of the CTA).
+template <bool kSmem>
+__device__ inline unsigned char *stage_tables(const DevSnap &D, Tab<kSmem> &T, unsigned char *p, const int32_t *nodes, int nn) {
+  const int FR = D.FR;
+  T.D = &D; T.FR = FR;
+  if (kSmem) {
+    size_t tb = (size_t)nn * FR;
+    i64 *u = (i64 *)p, *sb = u + tb, *lq = sb + tb, *bl = lq + tb;
+    int *lp = (int *)(bl + tb);
+    for (int i = threadIdx.x; i < nn * FR; i += blockDim.x) {
+      int nd = nodes[i / FR], fr = i % FR;
+      size_t c = (size_t)nd * FR + fr;
+      i64 sub = D.subtree[c];
+      u[i] = D.usage[c]; sb[i] = sub; lq[i] = local_quota(sub, D.llimit[c]); bl[i] = D.blimit[c];
+    }
+    for (int i = threadIdx.x; i < nn; i += blockDim.x) { int pn = D.parent[nodes[i]]; lp[i] = pn < 0 ? -1 : D.local_idx[pn]; }
+    T.usage = u; T.sub = sb; T.lq = lq; T.bl = bl; T.lparent = lp;
+    p = (unsigned char *)(lp + nn);
+    p = (unsigned char *)(((uintptr_t)p + 7) & ~(uintptr_t)7);
+  }
+  return p;
+}
+template <bool kSmem>
+__device__ inline void publish_usage(const DevSnap &D, const Tab<kSmem> &T, const int32_t *nodes, int nn) {
+  if (kSmem)
+    for (int i = threadIdx.x; i < nn * D.FR; i += blockDim.x) D.usage[(size_t)nodes[i / D.FR] * D.FR + i % D.FR] = T.usage[i];
+}
+
+// One iteration of the admit loop body (scheduler.go:269-401) for entry e, executed by a
+// full warp: lane l owns the flavor-resource columns l, l+32, ...  qrow[fr] is the
+// aggregated Assignment.Usage.Quota (absent cell = -1).  s_path: KB_MAX_DEPTH+2 ints.
+template <bool kSmem>
+__device__ inline void commit_entry(const DevSnap &D, const Tab<kSmem> &T, int *s_path, int lane, int e, int nd, int mode,
+                                    int borrowing, const i64 *qrow, int rank) {
+  const int FR = D.FR;
+  if (lane == 0) D.rank[e] = rank;
+  if (mode == KB_MODE_NOFIT) { if (lane == 0) D.decision[e] = KB_DEC_NOFIT; return; }
+  if (lane == 0) { int pl = 0; for (int t = nd; t >= 0; t = T.parent(t)) s_path[pl++] = t; s_path[KB_MAX_DEPTH + 1] = pl; }
+  __syncwarp();
+  int plen = s_path[KB_MAX_DEPTH + 1];
+  if (mode == KB_MODE_PREEMPT) {  // Preempt without targets: scheduler.go:303-318
+    if (lane == 0) D.decision[e] = KB_DEC_PREEMPT_NO_TARGETS;
+    int cq = D.wl_cq[D.heads[e]];
+    if (D.cq_reclaim_within[cq] != KB_POLICY_ANY) {  // !CanAlwaysReclaim policy.go:27-29
+      for (int fr = lane; fr < FR; fr += 32) {        // quotaResourcesToReserve :530-548
+        i64 u = qrow[fr];
+        if (u < 0) continue;
+        i64 nominal = T.Sub(nd, fr), bl = T.BL(nd, fr), cur = T.U(nd, fr);  // CQ: SubtreeQuota == Nominal
+        i64 rsv;
+        if (borrowing > 0) rsv = bl == KB_NO_LIMIT ? u : imin(u, nominal + bl - cur);
+        else rsv = imax(0, imin(u, nominal - cur));
+        T.add(s_path, plen, fr, rsv);
+      }
+    }
+    __syncwarp();
+    return;
+  }
+  bool ok = true;  // fits :503-511
+  for (int fr = lane; fr < FR; fr += 32) {
+    i64 q = qrow[fr];
+    if (q > 0 && imax(0, T.avail(s_path, plen, fr)) < q) ok = false;
+  }
+  ok = __all_sync(0xffffffffu, ok);
+  if (ok) for (int fr = lane; fr < FR; fr += 32) { i64 q = qrow[fr]; if (q > 0) T.add(s_path, plen, fr, q); }  // cq.AddUsage :336
+  if (lane == 0) D.decision[e] = ok ? KB_DEC_ASSUMED : KB_DEC_SKIPPED_NO_FIT;
+  __syncwarp();
+}
+
+// dense request row of entry e for column fr (absent = -1)
+__device__ __forceinline__ i64 entry_request(const DevSnap &D, int e, int fr) {
+  const int R = D.R;
+  int f = fr / R, r = fr % R;
+  int wl = D.heads[e];
+  int cq = D.wl_cq[wl];
+  bool covers_pods = D.pods_res >= 0 && rg_by_resource(D, cq, D.pods_res) >= 0;
+  i64 q = -1;
+  for (int row = D.wl_ps_start[wl]; row < D.wl_ps_start[wl + 1]; row++)
+    if (D.ps_flavor[(size_t)row * R + r] == f) q = (q < 0 ? 0 : q) + ps_request(D, row, r, D.ps_count_out[row], covers_pods);
+  return q;
+}
 
 template <bool kSmemTables>
 __global__ void __launch_bounds__(128) k_admit(DevSnap D, int slot_base, int sort_cap) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int FR = D.FR, R = D.R;
+  const int FR = D.FR;
   int slot = slot_base + blockIdx.x;
   int off = D.root_offset[slot];
   int n = D.root_offset[slot + 1] - off;
   if (n == 0) return;
   int32_t *ent = D.root_entries + off;
-  // nodes of this root
-  const int32_t *nodes; int nn; int lone_node = -1;
-  if (slot < D.nLone) { lone_node = D.lone_cqs[slot]; nodes = &D.lone_cqs[slot]; nn = 1; }
+  const int32_t *nodes; int nn;
+  if (slot < D.nLone) { nodes = &D.lone_cqs[slot]; nn = 1; }
   else { int t = slot - D.nLone; nodes = D.tree_nodes + D.tree_start[t]; nn = D.tree_start[t + 1] - D.tree_start[t]; }
-  (void)lone_node;
-  // ---- smem carve-up ----
-  AdmitSmem S;
-  unsigned char *p = smem_raw;
-  size_t tb = kSmemTables ? (size_t)nn * FR : 0;
-  S.usage = (i64 *)p; p += tb * 8; S.sub = (i64 *)p; p += tb * 8; S.lq = (i64 *)p; p += tb * 8; S.bl = (i64 *)p; p += tb * 8;
-  S.q = (i64 *)p;
-  S.k0 = (u64 *)p; S.k1 = S.k0 + sort_cap; S.kidx = (int *)(S.k1 + sort_cap);
+  // ---- smem carve-up: [tables][sort keys | request tile][tile meta][path] ----
+  Tab<kSmemTables> T;
+  unsigned char *p = stage_tables<kSmemTables>(D, T, smem_raw, nodes, nn);
+  i64 *s_q = (i64 *)p;
+  u64 *s_k0 = (u64 *)p, *s_k1 = s_k0 + sort_cap; int *s_kidx = (int *)(s_k1 + sort_cap);
   size_t sort_bytes = (size_t)sort_cap * 20, tile_bytes = (size_t)KB_TILE * FR * 8;
   p += (sort_bytes > tile_bytes ? sort_bytes : tile_bytes);
   p = (unsigned char *)(((uintptr_t)p + 7) & ~(uintptr_t)7);
-  S.lparent = (int *)p; p += (kSmemTables ? nn : 0) * 4;
-  S.t_e = (int *)p; p += KB_TILE * 4; S.t_node = (int *)p; p += KB_TILE * 4; S.t_mode = (int *)p; p += KB_TILE * 4; S.t_borrow = (int *)p; p += KB_TILE * 4;
-  S.path = (int *)p;
+  int *t_e = (int *)p, *t_node = t_e + KB_TILE, *t_mode = t_node + KB_TILE, *t_borrow = t_mode + KB_TILE;
+  int *s_path = t_borrow + KB_TILE;
 
   // ---- 1. sort ----
   int np2 = 1;
   while (np2 < n) np2 <<= 1;
   if (n > 1 && np2 <= sort_cap) {
     for (int i = threadIdx.x; i < np2; i += blockDim.x) {
-      if (i < n) { int e = ent[i]; entry_key(D, e, &S.k0[i], &S.k1[i]); S.kidx[i] = e; }
-      else { S.k0[i] = ~0ull; S.k1[i] = ~0ull; S.kidx[i] = INT32_MAX; }
+      if (i < n) { int e = ent[i]; entry_key(D, e, &s_k0[i], &s_k1[i]); s_kidx[i] = e; }
+      else { s_k0[i] = ~0ull; s_k1[i] = ~0ull; s_kidx[i] = INT32_MAX; }
     }
     __syncthreads();
     for (int k = 2; k <= np2; k <<= 1)
@@ -463,17 +571,17 @@ __global__ void __launch_bounds__(128) k_admit(DevSnap D, int slot_base, int sor
         for (int i = threadIdx.x; i < np2; i += blockDim.x) {
           int l = i ^ j;
           if (l > i) {
-            u64 a0 = S.k0[i], a1 = S.k1[i], b0 = S.k0[l], b1 = S.k1[l];
-            int ai = S.kidx[i], bi = S.kidx[l];
+            u64 a0 = s_k0[i], a1 = s_k1[i], b0 = s_k0[l], b1 = s_k1[l];
+            int ai = s_kidx[i], bi = s_kidx[l];
             int aw = ai == INT32_MAX ? INT32_MAX : D.heads[ai], bw = bi == INT32_MAX ? INT32_MAX : D.heads[bi];
             bool up = (i & k) == 0;
             bool sw = up ? key_less(b0, b1, bw, a0, a1, aw) : key_less(a0, a1, aw, b0, b1, bw);
-            if (sw) { S.k0[i] = b0; S.k1[i] = b1; S.kidx[i] = bi; S.k0[l] = a0; S.k1[l] = a1; S.kidx[l] = ai; }
+            if (sw) { s_k0[i] = b0; s_k1[i] = b1; s_kidx[i] = bi; s_k0[l] = a0; s_k1[l] = a1; s_kidx[l] = ai; }
           }
         }
         __syncthreads();
       }
-    for (int i = threadIdx.x; i < n; i += blockDim.x) ent[i] = S.kidx[i];
+    for (int i = threadIdx.x; i < n; i += blockDim.x) ent[i] = s_kidx[i];
     __syncthreads();
   } else if (n > 1) {
     // root with more entries than the shared-memory sort holds: ascending-only bitonic
@@ -493,118 +601,155 @@ __global__ void __launch_bounds__(128) k_admit(DevSnap D, int slot_base, int sor
       }
     }
   }
-  // ---- 2. stage the tree ----
-  if (kSmemTables) {
-    for (int i = threadIdx.x; i < nn * FR; i += blockDim.x) {
-      int nd = nodes[i / FR], fr = i % FR;
-      size_t c = (size_t)nd * FR + fr;
-      i64 sub = D.subtree[c];
-      S.usage[i] = D.usage[c]; S.sub[i] = sub; S.lq[i] = local_quota(sub, D.llimit[c]); S.bl[i] = D.blimit[c];
-    }
-    for (int i = threadIdx.x; i < nn; i += blockDim.x) {
-      int pn = D.parent[nodes[i]];
-      S.lparent[i] = pn < 0 ? -1 : D.local_idx[pn];
-    }
-  }
   __syncthreads();
-
-  // accessors: node handle = local index (smem tables) or global node id
-  auto getU = [&](int nd, int fr) -> i64 { return kSmemTables ? S.usage[nd * FR + fr] : __ldcg(&D.usage[(size_t)nd * FR + fr]); };
-  auto setU = [&](int nd, int fr, i64 v) { if (kSmemTables) S.usage[nd * FR + fr] = v; else __stcg(&D.usage[(size_t)nd * FR + fr], v); };
-  auto getSub = [&](int nd, int fr) -> i64 { return kSmemTables ? S.sub[nd * FR + fr] : D.subtree[(size_t)nd * FR + fr]; };
-  auto getLQ = [&](int nd, int fr) -> i64 { return kSmemTables ? S.lq[nd * FR + fr] : local_quota(D.subtree[(size_t)nd * FR + fr], D.llimit[(size_t)nd * FR + fr]); };
-  auto getBL = [&](int nd, int fr) -> i64 { return kSmemTables ? S.bl[nd * FR + fr] : D.blimit[(size_t)nd * FR + fr]; };
-  auto parentOf = [&](int nd) -> int { return kSmemTables ? S.lparent[nd] : D.parent[nd]; };
-  // available() resource_node.go:104-118 along the staged path (path[0] = CQ ... path[plen-1] = root)
-  auto liveAvail = [&](int plen, int fr) -> i64 {
-    int rt = S.path[plen - 1];
-    i64 a = getSub(rt, fr) - getU(rt, fr);
-    for (int k = plen - 2; k >= 0; k--) {
-      int nd = S.path[k];
-      i64 u = getU(nd, fr), lq = getLQ(nd, fr), bl = getBL(nd, fr);
-      i64 pa = a;
-      if (bl != KB_NO_LIMIT) pa = imin((getSub(nd, fr) - lq) - imax(0, u - lq) + bl, pa);
-      a = imax(0, lq - u) + pa;
-    }
-    return a;
-  };
-  auto liveAdd = [&](int plen, int fr, i64 val) {  // addUsage :137-145
-    for (int k = 0; k < plen; k++) {
-      int nd = S.path[k];
-      i64 u = getU(nd, fr);
-      i64 la = imax(0, getLQ(nd, fr) - u);
-      setU(nd, fr, u + val);
-      if (!(k + 1 < plen && val > la)) break;
-      val -= la;
-    }
-  };
-
-  // ---- 3. tiles ----
+  // ---- 2. tiles: expand (all threads), commit (warp 0) ----
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int base = 0; base < n; base += KB_TILE) {
     int tn = min(KB_TILE, n - base);
-    // 3a. expand: dense request matrix + meta
     for (int i = threadIdx.x; i < tn; i += blockDim.x) {
       int e = ent[base + i];
-      int wl = D.heads[e];
-      int cq = D.wl_cq[wl];
-      S.t_e[i] = e; S.t_node[i] = kSmemTables ? D.local_idx[cq] : cq;
-      S.t_mode[i] = D.mode[e]; S.t_borrow[i] = D.borrow[e];
+      t_e[i] = e; t_node[i] = T.handle(D.wl_cq[D.heads[e]]);
+      t_mode[i] = D.mode[e]; t_borrow[i] = D.borrow[e];
     }
-    for (int c = threadIdx.x; c < tn * FR; c += blockDim.x) {
-      int i = c / FR, fr = c % FR, f = fr / R, r = fr % R;
-      int e = ent[base + i];
-      int wl = D.heads[e];
-      int cq = D.wl_cq[wl];
-      bool covers_pods = D.pods_res >= 0 && rg_by_resource(D, cq, D.pods_res) >= 0;
-      i64 q = -1;
-      for (int row = D.wl_ps_start[wl]; row < D.wl_ps_start[wl + 1]; row++)
-        if (D.ps_flavor[(size_t)row * R + r] == f) q = (q < 0 ? 0 : q) + ps_request(D, row, r, D.ps_count_out[row], covers_pods);
-      S.q[c] = q;
-    }
+    for (int c = threadIdx.x; c < tn * FR; c += blockDim.x) s_q[c] = entry_request(D, ent[base + c / FR], c % FR);
     __syncthreads();
-    // 3b. commit in order (warp 0)
-    if (warp == 0) {
-      for (int i = 0; i < tn; i++) {
-        int e = S.t_e[i], mode = S.t_mode[i], nd = S.t_node[i];
-        if (lane == 0) D.rank[e] = base + i;
-        if (mode == KB_MODE_NOFIT) { if (lane == 0) D.decision[e] = KB_DEC_NOFIT; continue; }
-        if (lane == 0) { int pl = 0; for (int t = nd; t >= 0; t = parentOf(t)) S.path[pl++] = t; S.path[KB_MAX_DEPTH] = pl; }
-        __syncwarp();
-        int plen = S.path[KB_MAX_DEPTH];
-        const i64 *qrow = S.q + (size_t)i * FR;
-        if (mode == KB_MODE_PREEMPT) {  // Preempt without targets: scheduler.go:303-318
-          if (lane == 0) D.decision[e] = KB_DEC_PREEMPT_NO_TARGETS;
-          int cq = D.wl_cq[D.heads[e]];
-          if (D.cq_reclaim_within[cq] != KB_POLICY_ANY) {  // !CanAlwaysReclaim policy.go:27-29
-            int borrowing = S.t_borrow[i];
-            for (int fr = lane; fr < FR; fr += 32) {  // quotaResourcesToReserve :530-548
-              i64 u = qrow[fr];
-              if (u < 0) continue;
-              i64 nominal = getSub(nd, fr), bl = getBL(nd, fr), cur = getU(nd, fr);  // CQ: SubtreeQuota == Nominal
-              i64 rsv;
-              if (borrowing > 0) rsv = bl == KB_NO_LIMIT ? u : imin(u, nominal + bl - cur);
-              else rsv = imax(0, imin(u, nominal - cur));
-              liveAdd(plen, fr, rsv);
+    if (warp == 0)
+      for (int i = 0; i < tn; i++)
+        commit_entry<kSmemTables>(D, T, s_path, lane, t_e[i], t_node[i], t_mode[i], t_borrow[i], s_q + (size_t)i * FR, base + i);
+    __syncthreads();
+  }
+  publish_usage<kSmemTables>(D, T, nodes, nn);
+}
+
+// ---------------------------------------------------------------------------
+// K4: fair-sharing iterator + admit (fair_sharing_iterator.go:36-229), one CTA per
+// cohort tree.  Each pop: (1) every remaining entry recomputes, one thread per entry,
+// the DominantResourceShare of each node on its CQ->root path as if its own usage were
+// admitted (computeDRS :206-229, without mutating the tree: the usage bubbling of
+// addUsage is replayed functionally per column); (2) the tournament (runTournament
+// :120-153) runs bottom-up over the cohort levels, one warp per cohort with a
+// shuffle reduction over its children; (3) warp 0 commits the winner.
+// ---------------------------------------------------------------------------
+struct FsKey { double ratio, weight; };
+
+// entryComparer.less :166-199 for candidates a, b under parent cohort P (depth dP).
+__device__ inline bool fs_less(const DevSnap &D, int a, int b, int dP) {
+  if (D.flags & KB_F_FS_PRIORITIZE_NON_BORROWING) {
+    bool ab = D.borrow[a] > 0, bb = D.borrow[b] > 0;
+    if (ab != bb) return !ab;
+  }
+  int wa = D.heads[a], wb = D.heads[b];
+  int ka = D.depth[D.wl_cq[wa]] - dP - 1, kb = D.depth[D.wl_cq[wb]] - dP - 1;
+  double2 va = D.fs_drs[(size_t)a * KB_MAX_DEPTH + ka], vb = D.fs_drs[(size_t)b * KB_MAX_DEPTH + kb];
+  DevDRS da{va.y, va.x, -1, false}, db{vb.y, vb.x, -1, false};
+  int c = drs_compare(da, db);
+  if (c != 0) return c < 0;
+  if (D.flags & KB_F_PRIORITY_SORTING_WITHIN_COHORT) {
+    int pa = D.wl_priority[wa], pb = D.wl_priority[wb];
+    if (pa != pb) return pa > pb;
+  }
+  return D.wl_ts[wa] < D.wl_ts[wb];
+}
+
+template <bool kSmemTables>
+__global__ void __launch_bounds__(128) k_admit_fair(DevSnap D, int slot_base) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int FR = D.FR, R = D.R, F = D.F;
+  int slot = slot_base + blockIdx.x;
+  int off = D.root_offset[slot];
+  int n = D.root_offset[slot + 1] - off;
+  if (n == 0) return;
+  int32_t *ent = D.root_entries + off;
+  int t = slot - D.nLone;
+  const int32_t *nodes = D.tree_nodes + D.tree_start[t];
+  int nn = D.tree_start[t + 1] - D.tree_start[t];
+  const int32_t *lvl = D.tree_level + (size_t)t * KB_LEVELS;
+  int nlev = 0;
+  while (nlev + 1 < KB_LEVELS && lvl[nlev + 1] > lvl[nlev]) nlev++;
+  Tab<kSmemTables> T;
+  unsigned char *p = stage_tables<kSmemTables>(D, T, smem_raw, nodes, nn);
+  int *s_path = (int *)p;  // KB_MAX_DEPTH + 2
+  // per-node scratch lives in global memory, indexed by node id: cq_entry / winner
+  int32_t *cq_entry = D.fs_cq_entry, *winner = D.fs_winner;
+  for (int i = threadIdx.x; i < nn; i += blockDim.x) { cq_entry[nodes[i]] = -1; winner[nodes[i]] = -1; }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) { int e = ent[i]; cq_entry[D.wl_cq[D.heads[e]]] = e; }
+  for (int c = threadIdx.x; c < n * FR; c += blockDim.x) { int e = ent[c / FR]; D.q_scratch[(size_t)e * FR + c % FR] = entry_request(D, e, c % FR); }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  for (int it = 0; it < n; it++) {
+    // (1) computeDRS for every remaining entry
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      int e = ent[i];
+      int cq = D.wl_cq[D.heads[e]];
+      if (cq_entry[cq] != e) continue;  // already popped
+      const i64 *q = D.q_scratch + (size_t)e * FR;
+      int X = cq;  // global node ids for the walk; tables addressed through handles
+      for (int k = 0; D.parent[X] >= 0; k++, X = D.parent[X]) {
+        int P = D.parent[X];
+        int hX = T.handle(X);
+        double best = 0.0;
+        for (int r = 0; r < R; r++) {
+          i64 b = 0, lend = 0;
+          for (int f = 0; f < F; f++) {
+            int fr = f * R + r;
+            // usage that entry e adds at node X in column fr: replay addUsage from the CQ up to X
+            i64 d = q[fr] > 0 ? q[fr] : 0;
+            int Y = cq;
+            for (int j = 0; j < k && d > 0; j++, Y = D.parent[Y]) {
+              int hY = T.handle(Y);
+              i64 la = imax(0, T.LQ(hY, fr) - T.U(hY, fr));
+              d = d > la ? d - la : 0;
             }
+            i64 over = T.U(hX, fr) + d - T.Sub(hX, fr);
+            if (over > 0) b += over;
+            lend += D.potential[(size_t)P * FR + fr];  // calculateLendable fair_sharing.go:160-174
           }
-          __syncwarp();
-          continue;
+          if (b > 0 && lend > 0) {
+            double ratio = (double)b * 1000.0 / (double)lend;
+            if (ratio > best) best = ratio;
+          }
         }
-        bool ok = true;  // fits :503-511
-        for (int fr = lane; fr < FR; fr += 32) {
-          i64 q = qrow[fr];
-          if (q > 0 && imax(0, liveAvail(plen, fr)) < q) ok = false;
-        }
-        ok = __all_sync(0xffffffffu, ok);
-        if (ok) for (int fr = lane; fr < FR; fr += 32) { i64 q = qrow[fr]; if (q > 0) liveAdd(plen, fr, q); }  // cq.AddUsage :336
-        if (lane == 0) D.decision[e] = ok ? KB_DEC_ASSUMED : KB_DEC_SKIPPED_NO_FIT;
-        __syncwarp();
+        D.fs_drs[(size_t)e * KB_MAX_DEPTH + k] = make_double2(best, D.fair_weight[X]);
       }
     }
     __syncthreads();
+    // (2) tournament, bottom-up over cohort levels
+    for (int L = nlev - 1; L >= 0; L--) {
+      for (int idx = lvl[L] + warp; idx < lvl[L + 1]; idx += nwarps) {
+        int X = nodes[idx];
+        if (X < D.Q) continue;  // CQs carry entries, cohorts run the tournament
+        int c0 = D.child_start[X], c1 = D.child_start[X + 1];
+        int best = -1, bestpos = INT32_MAX;
+        for (int c = c0 + lane; c < c1; c += 32) {
+          int ch = D.child_list[c];
+          int cand = ch < D.Q ? cq_entry[ch] : winner[ch];
+          if (cand < 0) continue;
+          if (best < 0 || fs_less(D, cand, best, L)) { best = cand; bestpos = c; }  // earlier candidate keeps ties
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+          int ob = __shfl_xor_sync(0xffffffffu, best, o), op = __shfl_xor_sync(0xffffffffu, bestpos, o);
+          if (ob >= 0) {
+            bool take;
+            if (best < 0) take = true;
+            else if (fs_less(D, ob, best, L)) take = true;
+            else if (fs_less(D, best, ob, L)) take = false;
+            else take = op < bestpos;
+            if (take) { best = ob; bestpos = op; }
+          }
+        }
+        if (lane == 0) winner[X] = best;
+      }
+      __syncthreads();
+    }
+    // (3) pop + commit
+    if (warp == 0) {
+      int e = winner[nodes[0]];
+      int cq = D.wl_cq[D.heads[e]];
+      commit_entry<kSmemTables>(D, T, s_path, lane, e, T.handle(cq), D.mode[e], D.borrow[e], D.q_scratch + (size_t)e * FR, it);
+      if (lane == 0) cq_entry[cq] = -1;
+    }
+    __syncthreads();
   }
-  // ---- 4. publish the final usage ----
-  if (kSmemTables)
-    for (int i = threadIdx.x; i < nn * FR; i += blockDim.x) D.usage[(size_t)nodes[i / FR] * FR + i % FR] = S.usage[i];
+  publish_usage<kSmemTables>(D, T, nodes, nn);
 }

@@ -79,7 +79,7 @@ def make_snapshot(config: int = 2, W: int | None = None, Q: int | None = None, F
         blm = rng.random(Q) < 0.3
         bl[:Q][blm] = nominal[:Q][blm]
     snap.set("nominal", nominal); snap.set("borrow_limit", bl); snap.set("lend_limit", ll)
-    lo, hi = (0.6, 0.9) if config in (1, 2) else (0.5, 1.2 if config == 3 else 1.0)
+    lo, hi = {1: (0.6, 0.9), 2: (0.6, 0.9), 3: (0.7, 1.25), 4: (0.75, 1.15)}[config]
     usage = (nominal[:Q] * rng.uniform(lo, hi, (Q, FR))).astype(np.int64)
     if config in (1, 2):
         usage = np.minimum(usage, nominal[:Q])
@@ -102,6 +102,8 @@ def make_snapshot(config: int = 2, W: int | None = None, Q: int | None = None, F
     snap.set("wl_ps_start", st)
     count = rng.integers(1, 9, P)
     per_pod = (rng.uniform(0.05, 1.0, (P, R)) * scale[None, :] / 4).astype(np.int64)
+    big = rng.random(P) < 0.03  # a few podsets larger than any ClusterQueue can ever hold
+    per_pod[big] *= 40
     snap.set("ps_req", per_pod * count[:, None])
     snap.set("ps_req_mask", np.full(P, (1 << R) - 1))
     snap.set("ps_count", count)

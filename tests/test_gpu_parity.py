@@ -53,6 +53,30 @@ def test_cycle_matches_oracle(ev, config, kw):
     assert_cycle_equal(got, want)
 
 
+def _fair(snap):
+    snap.flags |= abi.F_FAIR_SHARING
+    return snap
+
+
+@pytest.mark.parametrize("make", [
+    lambda: synth.make_snapshot(3, W=3000, Q=300, heads="one_per_cq"),
+    lambda: synth.make_snapshot(3, W=30000, Q=1000, heads="one_per_cq", podsets_max=2),
+    lambda: _fair(synth.make_snapshot(4, W=4000, Q=200, heads="one_per_cq")),      # fair sharing over a depth-4 tree
+    lambda: _fair(synth.make_snapshot(4, W=40000, Q=2000, heads="one_per_cq")),    # tree too large for shared memory
+    lambda: _fair(synth.make_snapshot(2, W=2000, Q=100, heads="one_per_cq")),      # fair sharing, CQs without cohorts
+])
+def test_fair_sharing_cycle_matches_oracle(ev, make):
+    snap = make()
+    got, want = ev.run_cycle(snap), oracle.run_cycle(snap)
+    assert_cycle_equal(got, want)
+
+
+def test_full_size_config3_single_cycle(ev):
+    snap = synth.make_snapshot(3, heads="one_per_cq")
+    got, want = ev.run_cycle(snap), oracle.run_cycle(snap)
+    assert_cycle_equal(got, want)
+
+
 def test_full_size_config2(ev):
     snap = synth.make_snapshot(2)
     got, want = ev.run_cycle(snap), oracle.run_cycle(snap)
