@@ -394,7 +394,7 @@ __global__ void k_scatter(DevSnap D) {
 //      columns l, l+32, ...; columns are independent in the quota tree, so fit checks
 //      and addUsage run lane-parallel with one __all_sync per entry.
 // ---------------------------------------------------------------------------
-#define KB_TILE 64
+#define KB_TILE 128
 #define KB_SORT_CAP 1024  // entries per root sortable in shared memory
 
 // sort key: (borrow asc, priority desc, ts asc, workload index asc)
@@ -534,6 +534,24 @@ __device__ __forceinline__ i64 entry_request(const DevSnap &D, int e, int fr) {
   return q;
 }
 
+// scatter the aggregated Assignment.Usage.Quota of entry e into a dense row (pre-filled with -1)
+__device__ inline void expand_entry(const DevSnap &D, int e, i64 *qrow) {
+  const int R = D.R;
+  int wl = D.heads[e];
+  int ps0 = D.wl_ps_start[wl], ps1 = D.wl_ps_start[wl + 1];
+  int cq = D.wl_cq[wl];
+  bool covers_pods = D.pods_res >= 0 && rg_by_resource(D, cq, D.pods_res) >= 0;
+  for (int row = ps0; row < ps1; row++) {
+    int cnt = D.ps_count_out[row];
+    for (int r = 0; r < R; r++) {
+      int f = D.ps_flavor[(size_t)row * R + r];
+      if (f < 0) continue;
+      i64 cur = qrow[f * R + r];
+      qrow[f * R + r] = (cur < 0 ? 0 : cur) + ps_request(D, row, r, cnt, covers_pods);
+    }
+  }
+}
+
 template <bool kSmemTables>
 __global__ void __launch_bounds__(128) k_admit(DevSnap D, int slot_base, int sort_cap) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -611,7 +629,10 @@ __global__ void __launch_bounds__(128) k_admit(DevSnap D, int slot_base, int sor
       t_e[i] = e; t_node[i] = T.handle(D.wl_cq[D.heads[e]]);
       t_mode[i] = D.mode[e]; t_borrow[i] = D.borrow[e];
     }
-    for (int c = threadIdx.x; c < tn * FR; c += blockDim.x) s_q[c] = entry_request(D, ent[base + c / FR], c % FR);
+    for (int c = threadIdx.x; c < tn * FR; c += blockDim.x) s_q[c] = -1;
+    __syncthreads();
+    // one thread per entry walks its podset rows once and scatters the cells of its row
+    for (int i = threadIdx.x; i < tn; i += blockDim.x) expand_entry(D, t_e[i], s_q + (size_t)i * FR);
     __syncthreads();
     if (warp == 0)
       for (int i = 0; i < tn; i++)
