@@ -56,7 +56,11 @@ struct kb_handle {
   // tree_eval scratch
   i64 *d_drs_rounded = nullptr; int32_t *d_drs_res = nullptr; uint8_t *d_drs_borrowing = nullptr;
   // host-side derived topology
-  std::vector<int32_t> root_slot, depth, height, tree_start, tree_nodes, tree_level, lone, cq_adm_start, cq_adm, local_idx, child_start, child_list;
+  std::vector<int32_t> root_slot, depth, height, tree_start, tree_nodes, tree_level, lone, cq_adm_start, cq_adm, local_idx, child_start, child_list, adm_sorted, root_adm_start;
+  int max_root_adm = 1;
+  int search_grid = 1;
+  bool search_smem = true;
+  size_t search_smem_bytes = 0;
   int max_tree_nodes = 1;
   int max_root_entries_hint = 0;
 };
@@ -228,6 +232,27 @@ static int32_t build_topology(kb_handle *h, const kb_snapshot *s) {
     std::vector<int32_t> cur(h->cq_adm_start.begin(), h->cq_adm_start.end() - 1);
     for (int a = 0; a < s->n_adm; a++) h->cq_adm[cur[s->adm_cq[a]]++] = a;
   }
+  // admitted workloads per root, in the preemptor-independent part of CandidatesOrdering
+  // (preemption/common/ordering.go:41-100): evicted first, lower priority first, more recently
+  // reserved first, UID.  TODO(next): radix sort on the device / incremental order kept by the host cache.
+  h->root_adm_start.assign(nroots + 1, 0);
+  for (int a = 0; a < s->n_adm; a++) h->root_adm_start[h->root_slot[s->adm_cq[a]] + 1]++;
+  h->max_root_adm = 1;
+  for (int r = 0; r < nroots; r++) { h->max_root_adm = std::max(h->max_root_adm, h->root_adm_start[r + 1]); h->root_adm_start[r + 1] += h->root_adm_start[r]; }
+  h->adm_sorted.assign(std::max(1, s->n_adm), 0);
+  {
+    std::vector<int32_t> cur(h->root_adm_start.begin(), h->root_adm_start.end() - 1);
+    for (int a = 0; a < s->n_adm; a++) h->adm_sorted[cur[h->root_slot[s->adm_cq[a]]]++] = a;
+    auto qr = [&](int a) { return s->adm_qr_ts[a] == INT64_MIN ? s->now_ns : s->adm_qr_ts[a]; };
+    for (int r = 0; r < nroots; r++)
+      std::sort(h->adm_sorted.begin() + h->root_adm_start[r], h->adm_sorted.begin() + h->root_adm_start[r + 1], [&](int a, int b) {
+        if (s->adm_evicted[a] != s->adm_evicted[b]) return s->adm_evicted[a] > s->adm_evicted[b];
+        if (s->adm_priority[a] != s->adm_priority[b]) return s->adm_priority[a] < s->adm_priority[b];
+        int64_t ta = qr(a), tb = qr(b);
+        if (ta != tb) return ta > tb;
+        return s->adm_uid[a] < s->adm_uid[b];
+      });
+  }
   // light bounds checks on the hot tables
   for (int i = 0; i < s->n_heads; i++) if (s->heads[i] < 0 || s->heads[i] >= s->n_wl) return fail(h, KB_ERR_INVALID, "heads out of range");
   for (int w = 0; w < s->n_wl; w++) {
@@ -287,6 +312,21 @@ extern "C" int32_t kb_upload(kb_handle *h, const kb_snapshot *s) {
   need(nroots, 4); need(nroots + 1, 4); need(nroots, 4); need(H, 4);
   need(H, 1); need(H, 1); need(H, 4); need(H, 4); need(P * R, 1); need(P * R, 1); need(P * R, 1); need(P, 4);
   need(1, 4); need(N, 8); need(N, 4); need(N, 1);
+  // preemption: search kernel configuration + scratch
+  {
+    size_t tb = (size_t)h->max_tree_nodes * FR * 32 + (size_t)h->max_tree_nodes * 4 + 64;
+    h->search_smem = tb <= 190 * 1024;
+    h->search_smem_bytes = h->search_smem ? tb : 0;
+    int per_sm = !h->search_smem ? 2 : (tb <= 24 * 1024 ? 8 : (tb <= 48 * 1024 ? 4 : (tb <= 100 * 1024 ? 2 : 1)));
+    h->search_grid = std::max(1, std::min(h->sm_count * per_sm, std::max(1, s->n_heads)));
+    if (A == 0) h->search_grid = 1;
+  }
+  size_t G = (size_t)h->search_grid, acap = (size_t)h->max_root_adm, ncap = (size_t)h->max_tree_nodes;
+  size_t pool_cap = A * 4 + 1024;
+  need(A, 4); need(nroots + 1, 4); need(H, 4); need(2, 4); need(H, 4); need(H, 4); need(pool_cap, 4); need(pool_cap, 1); need(1, 4);
+  need(A, 1); need(A, 4); need(nroots, 4);
+  need(G * acap, 4); need(G * acap, 4); need(G * ncap, 4); need(G * acap, 1); need(G * acap, 1); need(G * ncap, 1); need(G * ncap, 1);
+  if (!h->search_smem) need(G * ncap * FR, 8);
   bool fair = (s->flags & KB_F_FAIR_SHARING) != 0;
   if (fair) { need(H * FR, 8); need(H * KB_MAX_DEPTH, 16); need(N, 4); need(N, 4); }
   if (!h->arena.reserve(tot + 4096)) return fail(h, KB_ERR_CUDA, "cudaMalloc failed");
@@ -315,6 +355,7 @@ extern "C" int32_t kb_upload(kb_handle *h, const kb_snapshot *s) {
   UP(tree_start, h->tree_start.data(), ntrees + 1); UP(tree_nodes, h->tree_nodes.data(), h->tree_nodes.size());
   UP(tree_level, h->tree_level.data(), h->tree_level.size()); UP(lone_cqs, h->lone.data(), h->lone.size());
   UP(local_idx, h->local_idx.data(), N);
+  UP(adm_sorted, h->adm_sorted.data(), h->adm_sorted.size()); UP(root_adm_start, h->root_adm_start.data(), nroots + 1);
   UP(child_start, h->child_start.data(), N + 1); UP(child_list, h->child_list.data(), h->child_list.size());
   UP(cq_adm_start, h->cq_adm_start.data(), Q + 1); UP(cq_adm, h->cq_adm.data(), h->cq_adm.size());
 #undef UP
@@ -327,6 +368,16 @@ extern "C" int32_t kb_upload(kb_handle *h, const kb_snapshot *s) {
   D.ps_flavor = h->arena.take<int8_t>(P * R); D.ps_res_mode = h->arena.take<int8_t>(P * R); D.ps_tried = h->arena.take<int8_t>(P * R);
   D.ps_count_out = h->arena.take<int32_t>(P);
   D.status = h->arena.take<uint32_t>(1);
+  D.ps_list = h->arena.take<int32_t>(H); D.ps_n = h->arena.take<int32_t>(2); D.ps_cursor = D.ps_n + 1;
+  D.tgt_off = h->arena.take<int32_t>(H); D.tgt_cnt = h->arena.take<int32_t>(H);
+  D.tgt_pool_adm = h->arena.take<int32_t>(pool_cap); D.tgt_pool_reason = h->arena.take<uint8_t>(pool_cap);
+  D.tgt_pool_used = h->arena.take<int32_t>(1); D.tgt_pool_cap = (int)pool_cap;
+  D.preempted = h->arena.take<uint8_t>(A); D.root_pre_list = h->arena.take<int32_t>(A); D.root_pre_count = h->arena.take<int32_t>(nroots);
+  D.sc_cand = h->arena.take<int32_t>(G * acap); D.sc_tgt = h->arena.take<int32_t>(G * acap); D.sc_cq_lca = h->arena.take<int32_t>(G * ncap);
+  D.sc_variant = h->arena.take<uint8_t>(G * acap); D.sc_tgt_reason = h->arena.take<uint8_t>(G * acap);
+  D.sc_cq_class = h->arena.take<int8_t>(G * ncap); D.sc_on_path = h->arena.take<int8_t>(G * ncap);
+  D.sc_usage = h->search_smem ? nullptr : h->arena.take<i64>(G * ncap * FR);
+  D.sc_adm_cap = (int)acap; D.sc_node_cap = (int)ncap;
   if (fair) {
     D.q_scratch = h->arena.take<i64>(H * FR); D.fs_drs = h->arena.take<double2>(H * KB_MAX_DEPTH);
     D.fs_cq_entry = h->arena.take<int32_t>(N); D.fs_winner = h->arena.take<int32_t>(N);
@@ -413,11 +464,25 @@ extern "C" int32_t kb_cycle_resident(kb_handle *h) {
   CUDA_TRY(h, cudaEventRecord(h->ev2, h->stream));
   CUDA_TRY(h, cudaMemsetAsync(D.status, 0, 4, h->stream));
   CUDA_TRY(h, cudaMemsetAsync(D.root_count, 0, sizeof(int32_t) * (size_t)std::max(1, D.nRoots), h->stream));
+  CUDA_TRY(h, cudaMemsetAsync(D.ps_n, 0, 8, h->stream));
+  CUDA_TRY(h, cudaMemsetAsync(D.tgt_pool_used, 0, 4, h->stream));
+  CUDA_TRY(h, cudaMemsetAsync(D.root_pre_count, 0, sizeof(int32_t) * (size_t)std::max(1, D.nRoots), h->stream));
+  if (D.A) CUDA_TRY(h, cudaMemsetAsync(D.preempted, 0, (size_t)D.A, h->stream));
   h->kev_n = 0;
   int32_t rc_admit = KB_OK;
   launch_tree(h, &launches);
   if (D.H) {
     kmark(h, KB_K_NOMINATE); k_nominate<<<(D.H + 127) / 128, 128, 0, h->stream>>>(D); launches++;
+    if (D.A && !(D.flags & KB_F_FAIR_SHARING)) {  // target search for the entries k_nominate deferred
+      kmark(h, KB_K_PREEMPT);
+      if (h->search_smem) {
+        CUDA_TRY(h, cudaFuncSetAttribute(k_nominate_search<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        k_nominate_search<true><<<h->search_grid, 128, h->search_smem_bytes, h->stream>>>(D);
+      } else {
+        k_nominate_search<false><<<h->search_grid, 128, 0, h->stream>>>(D);
+      }
+      launches++;
+    }
     kmark(h, KB_K_SCAN); k_scan_roots<<<1, 1024, 0, h->stream>>>(D); launches++;
     kmark(h, KB_K_SCATTER); k_scatter<<<(D.H + 255) / 256, 256, 0, h->stream>>>(D); launches++;
     kmark(h, KB_K_ADMIT);
@@ -438,7 +503,7 @@ extern "C" int32_t kb_cycle_resident(kb_handle *h) {
   }
   uint32_t st = 0;
   CUDA_TRY(h, cudaMemcpy(&st, D.status, 4, cudaMemcpyDeviceToHost));
-  if (st & KBS_UNSUPPORTED_PREEMPTION) return fail(h, KB_ERR_UNSUPPORTED, "snapshot needs the preemption search (not in this build)");
+  if (st & KBS_UNSUPPORTED_PREEMPTION) return fail(h, KB_ERR_UNSUPPORTED, "fair-sharing preemption search is not on the device yet");
   if (st & KBS_TARGET_OVERFLOW) return fail(h, KB_ERR_CAPACITY, "per-entry usage cell capacity exceeded");
   return KB_OK;
 }
@@ -458,8 +523,30 @@ extern "C" int32_t kb_download(kb_handle *h, kb_cycle_out *out) {
 #undef DOWN
   CUDA_TRY(h, cudaEventRecord(h->ev1, h->stream));
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
-  if (out->tgt_start) memset(out->tgt_start, 0, sizeof(int32_t) * (H + 1));
   out->n_targets = 0;
+  if (out->tgt_start) {
+    memset(out->tgt_start, 0, sizeof(int32_t) * (H + 1));
+    int32_t used = 0;
+    if (D.A && H) CUDA_TRY(h, cudaMemcpy(&used, D.tgt_pool_used, 4, cudaMemcpyDeviceToHost));
+    if (used > 0) {  // gather the per-entry target lists into CSR order
+      std::vector<int32_t> off(H), cnt(H), padm(used);
+      std::vector<uint8_t> preason(used);
+      CUDA_TRY(h, cudaMemcpy(off.data(), D.tgt_off, H * 4, cudaMemcpyDeviceToHost));
+      CUDA_TRY(h, cudaMemcpy(cnt.data(), D.tgt_cnt, H * 4, cudaMemcpyDeviceToHost));
+      CUDA_TRY(h, cudaMemcpy(padm.data(), D.tgt_pool_adm, (size_t)used * 4, cudaMemcpyDeviceToHost));
+      CUDA_TRY(h, cudaMemcpy(preason.data(), D.tgt_pool_reason, (size_t)used, cudaMemcpyDeviceToHost));
+      bytes += (int64_t)H * 8 + (int64_t)used * 5;
+      int32_t nt = 0;
+      for (size_t e = 0; e < H; e++) {
+        out->tgt_start[e] = nt;
+        for (int k = 0; k < cnt[e]; k++, nt++)
+          if (nt < out->tgt_capacity && out->tgt_adm && out->tgt_reason) { out->tgt_adm[nt] = padm[off[e] + k]; out->tgt_reason[nt] = preason[off[e] + k]; }
+      }
+      out->tgt_start[H] = nt;
+      out->n_targets = nt;
+      if (nt > out->tgt_capacity) return fail(h, KB_ERR_CAPACITY, "target buffer too small");
+    }
+  }
   float ms = 0; cudaEventElapsedTime(&ms, h->ev0, h->ev1);
   h->stats.last_d2h_ms = ms; h->stats.d2h_bytes = bytes;
   return KB_OK;

@@ -15,6 +15,7 @@ typedef long long i64;
 typedef unsigned long long u64;
 
 #define KB_LEVELS (KB_MAX_DEPTH + 2)
+#define KB_MAX_CELLS 128  // distinct flavor-resource cells in one workload's usage
 
 // Status word bits written by kernels (checked by the host after a cycle).
 enum { KBS_UNSUPPORTED_PREEMPTION = 1u << 0, KBS_TARGET_OVERFLOW = 1u << 1, KBS_PATH_TOO_DEEP = 1u << 2 };
@@ -79,6 +80,19 @@ struct DevSnap {
   int8_t *ps_flavor, *ps_res_mode, *ps_tried;
   int32_t *ps_count_out;
   uint32_t *status;  // [1] KBS_* bits
+  // ---- preemption ----
+  const int32_t *adm_sorted;     // [A] admitted workloads ordered by (root, evicted desc, priority asc, newer first, uid)
+  const int32_t *root_adm_start; // [nRoots+1] segments of adm_sorted
+  int32_t *ps_list, *ps_n, *ps_cursor;  // entries deferred to the target search
+  int32_t *tgt_off, *tgt_cnt;    // [H] targets of an entry inside the pool
+  int32_t *tgt_pool_adm; uint8_t *tgt_pool_reason; int32_t *tgt_pool_used; int tgt_pool_cap;
+  uint8_t *preempted;            // [A] PreemptedWorkloads membership (admit loop)
+  int32_t *root_pre_list;        // [A] per-root lists (segments of root_adm_start) of preempted workloads
+  int32_t *root_pre_count;       // [nRoots]
+  // per-CTA scratch of k_nominate_search
+  int32_t *sc_cand, *sc_tgt, *sc_cq_lca; uint8_t *sc_variant, *sc_tgt_reason; int8_t *sc_cq_class, *sc_on_path;
+  i64 *sc_usage;
+  int sc_adm_cap, sc_node_cap;
   // ---- fair-sharing scratch ----
   i64 *q_scratch;        // [H][FR] dense Assignment.Usage.Quota per entry (absent = -1)
   double2 *fs_drs;       // [H][KB_MAX_DEPTH] (unweightedRatio, fairWeight) per path level

@@ -17,6 +17,7 @@
 #pragma once
 
 #include "kb_device.cuh"
+#include "kb_preempt.cuh"
 
 // ---------------------------------------------------------------------------
 // K1: tree pass, one CTA per cohort-rooted tree.
@@ -187,19 +188,38 @@ __device__ __forceinline__ i64 ps_request(const DevSnap &D, int row, int r, int 
   return q;
 }
 
-// SimulatePreemption (preemption_oracle.go:41-71).  This build evaluates the cases in
-// which no candidate can exist; anything else raises KBS_UNSUPPORTED_PREEMPTION so the
-// host fails loudly (the Go shim then runs the reference path for the cycle).
-__device__ inline int simulate_preemption(const DevSnap &D, int cq, int *borrow_after) {
-  bool own = D.cq_within_cq[cq] != KB_POLICY_NEVER && D.cq_adm_start[cq + 1] > D.cq_adm_start[cq];
-  bool cohort = D.parent[cq] >= 0 && D.cq_reclaim_within[cq] != KB_POLICY_NEVER && D.A > 0;
-  if (own || cohort) atomicOr(D.status, KBS_UNSUPPORTED_PREEMPTION);
-  *borrow_after = 0;
-  return PM_NOCAND;
+// Can a preemption candidate exist at all for workloads of this CQ?  (own CQ: policy
+// WithinClusterQueue != Never and the CQ has admitted workloads; cohort: ReclaimWithinCohort
+// != Never and another CQ of the root has admitted workloads.)  When not, getTargets returns
+// nil and SimulatePreemption returns NoCandidates without any search.
+__device__ __forceinline__ bool candidates_possible(const DevSnap &D, int cq) {
+  int own_n = D.cq_adm_start[cq + 1] - D.cq_adm_start[cq];
+  if (D.cq_within_cq[cq] != KB_POLICY_NEVER && own_n > 0) return true;
+  if (D.parent[cq] >= 0 && D.cq_reclaim_within[cq] != KB_POLICY_NEVER) {
+    int slot = D.root_slot[cq];
+    if (D.root_adm_start[slot + 1] - D.root_adm_start[slot] - own_n > 0) return true;
+  }
+  return false;
 }
 
+// Oracle policy of the thread-per-entry nominate pass: everything that needs a target
+// search is deferred to k_nominate_search (the entry is re-evaluated there).
+struct NomThread {
+  bool need_search = false;
+  __device__ __forceinline__ int simulate(const DevSnap &D, int wl, int cq, int fr, i64 val, int *borrow_after) {
+    if (candidates_possible(D, cq)) need_search = true;
+    *borrow_after = 0;
+    return PM_NOCAND;  // preemption_oracle.go:52-54 when there are no candidates
+  }
+  __device__ __forceinline__ int get_targets(const DevSnap &D, int wl) {
+    if (candidates_possible(D, D.wl_cq[wl])) need_search = true;
+    return 0;
+  }
+};
+
 // fitsResourceQuota :1017-1047
-__device__ inline int fits_resource_quota(const DevSnap &D, int cq, int fr, i64 assumed, i64 request, int *borrow) {
+template <typename Oracle>
+__device__ inline int fits_resource_quota(const DevSnap &D, Oracle &orc, int wl, int cq, int fr, i64 assumed, i64 request, int *borrow) {
   size_t c = (size_t)cq * D.FR + fr;
   i64 avail = imax(0, D.avail[c]);
   i64 val = assumed + request;
@@ -209,7 +229,7 @@ __device__ inline int fits_resource_quota(const DevSnap &D, int cq, int fr, i64 
   if (val <= avail) { *borrow = b; return PM_FIT; }
   bool can_pwb = D.cq_borrow_within[cq] != KB_POLICY_NEVER ||
                  ((D.flags & KB_F_FAIR_SHARING) && D.cq_reclaim_within[cq] != KB_POLICY_NEVER);  // :1049-1052
-  if (val <= D.nominal[c] || may_reclaim || can_pwb) return simulate_preemption(D, cq, borrow);
+  if (val <= D.nominal[c] || may_reclaim || can_pwb) return orc.simulate(D, wl, cq, fr, val, borrow);
   *borrow = b;
   return PM_NOFIT;
 }
@@ -217,7 +237,8 @@ __device__ inline int fits_resource_quota(const DevSnap &D, int cq, int fr, i64 
 // One workload: Assign + assignFlavors (:540-715) writing PodSetAssignment rows.
 // counts == nullptr => full counts.  Returns the representative mode; *borrowing_out =
 // Assignment.Borrowing.
-__device__ inline int assign_workload(const DevSnap &D, int wl, const int32_t *counts, int *borrowing_out) {
+template <typename Oracle>
+__device__ inline int assign_workload(const DevSnap &D, Oracle &orc, int wl, const int32_t *counts, int *borrowing_out) {
   const int R = D.R;
   int cq = D.wl_cq[wl];
   int ps0 = D.wl_ps_start[wl], ps1 = D.wl_ps_start[wl + 1];
@@ -274,7 +295,7 @@ __device__ inline int assign_workload(const DevSnap &D, int wl, const int32_t *c
           for (int prow = ps0; prow < row; prow++)
             if (D.ps_flavor[(size_t)prow * R + r] == f) assumed += ps_request(D, prow, r, D.ps_count_out[prow], covers_pods);
           int b;
-          int pm = fits_resource_quota(D, cq, f * R + r, assumed, ps_request(D, row, r, count, covers_pods), &b);
+          int pm = fits_resource_quota(D, orc, wl, cq, f * R + r, assumed, ps_request(D, row, r, count, covers_pods), &b);
           if (pm != PM_FIT) any_reason = true;
           if (gm_preferred(rpm, rb, pm, b, pref)) { rpm = pm; rb = b; }  // :846-848 keep the worst
           if (rpm == PM_NOFIT) break;                                    // :849-852
@@ -326,17 +347,214 @@ __device__ inline int assign_workload(const DevSnap &D, int wl, const int32_t *c
   return rep;
 }
 
+#define KB_MAX_PODSETS 16
+
+// getInitialAssignments scheduler.go:584-625 incl. PodSetReducer.Search podset_reducer.go:56-86.
+// Leaves the final PodSetAssignment rows in the output tables; returns the representative
+// mode, *borrowing_out = Assignment.Borrowing, *ntargets = len(preemptionTargets).
+template <typename Oracle>
+__device__ inline int get_assignments(const DevSnap &D, Oracle &orc, int wl, int *borrowing_out, int *ntargets) {
+  *ntargets = 0;
+  int mode = assign_workload(D, orc, wl, nullptr, borrowing_out);
+  if (mode == KB_MODE_FIT) return mode;
+  if (mode == KB_MODE_PREEMPT) {
+    int nt = orc.get_targets(D, wl);
+    if (nt > 0) { *ntargets = nt; return mode; }
+  }
+  if (!(D.flags & KB_F_PARTIAL_ADMISSION)) return mode;
+  int ps0 = D.wl_ps_start[wl], np = D.wl_ps_start[wl + 1] - ps0;
+  if (np > KB_MAX_PODSETS) return mode;
+  int total = 0; bool can = false;  // CanBePartiallyAdmitted workload.go:514-522; deltas podset_reducer.go:47-53
+  for (int i = 0; i < np; i++) {
+    int mc = D.ps_min_count[ps0 + i], full = D.ps_count[ps0 + i];
+    if (mc >= 0) { total += full - mc; if (full > mc) can = true; }
+  }
+  if (!can || total == 0) return mode;
+  int32_t counts[KB_MAX_PODSETS];
+  auto fill = [&](int i) {  // fillPodSetSizesForSearchIndex :56-62
+    for (int k = 0; k < np; k++) {
+      int mc = D.ps_min_count[ps0 + k], full = D.ps_count[ps0 + k];
+      int delta = mc >= 0 ? full - mc : 0;
+      counts[k] = full - (int32_t)((i64)delta * i / total);
+    }
+  };
+  int last_good = -1, lo = 0, hi = total + 1;
+  while (lo < hi) {  // sort.Search(total+1, fits)
+    int mid = lo + (hi - lo) / 2;
+    fill(mid);
+    int b;
+    int m = assign_workload(D, orc, wl, counts, &b);
+    bool good = m == KB_MODE_FIT;
+    if (!good && m == KB_MODE_PREEMPT) good = orc.get_targets(D, wl) > 0;
+    if (good) { last_good = mid; hi = mid; } else lo = mid + 1;
+  }
+  if (last_good >= 0 && lo == last_good) {
+    fill(last_good);
+    mode = assign_workload(D, orc, wl, counts, borrowing_out);
+    if (mode == KB_MODE_PREEMPT) *ntargets = orc.get_targets(D, wl);
+    return mode;
+  }
+  mode = assign_workload(D, orc, wl, nullptr, borrowing_out);  // :624 return fullAssignment, nil
+  return mode;
+}
+
 __global__ void __launch_bounds__(128) k_nominate(DevSnap D) {
   int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= D.H) return;
   int wl = D.heads[e];
-  int borrowing;
-  int mode = assign_workload(D, wl, nullptr, &borrowing);  // getInitialAssignments scheduler.go:584-625
+  NomThread orc;
+  int borrowing, nt;
+  int mode = get_assignments(D, orc, wl, &borrowing, &nt);
   D.mode[e] = (uint8_t)mode;
   D.borrow[e] = borrowing;
   D.decision[e] = KB_DEC_NOFIT;
   D.rank[e] = -1;
+  D.tgt_cnt[e] = 0;
+  D.tgt_off[e] = 0;
+  if (orc.need_search) {
+    if (D.flags & KB_F_FAIR_SHARING) atomicOr(D.status, KBS_UNSUPPORTED_PREEMPTION);  // fair preemption: not on the device yet
+    else D.ps_list[atomicAdd(D.ps_n, 1)] = e;
+  }
   atomicAdd(&D.root_count[D.root_slot[D.wl_cq[wl]]], 1);
+}
+
+// ---------------------------------------------------------------------------
+// K6: nominate with target search.  Persistent CTAs pull the deferred entries; all threads
+// of the CTA run the (scalar) flavor-assignment control flow uniformly and cooperate inside
+// the search (kb_preempt.cuh).
+// ---------------------------------------------------------------------------
+template <bool kSmem>
+struct NomSearch {
+  const PTab<kSmem> *T;
+  PreCtx *c;
+  PreScratch S;
+  int *s_res;  // [2] shared result slots
+  // SimulatePreemption preemption_oracle.go:41-71
+  __device__ inline int simulate(const DevSnap &D, int wl, int cq, int fr, i64 val, int *borrow_after) {
+    if (!candidates_possible(D, cq)) { *borrow_after = 0; return PM_NOCAND; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      c->cq = cq; c->prio = D.wl_priority[wl]; c->ts = D.wl_ts[wl];
+      c->n_use = 1; c->use_fr[0] = fr; c->use_q[0] = val;
+      c->n_need = 1; c->need_fr[0] = fr;
+    }
+    __syncthreads();
+    classical_search<kSmem>(D, *T, c, S);
+    if (threadIdx.x == 0) {
+      int nt = c->n_targets, pm = PM_NOCAND, ba = 0;
+      if (nt > 0) {
+        int hcq = T->handle(cq);
+        for (int k = 0; k < nt; k++) T->remove_adm(S.tgt[k]);
+        ba = T->find_height(hcq, fr, val);
+        for (int k = 0; k < nt; k++) T->add_adm(S.tgt[k]);
+        pm = PM_RECLAIM;
+        for (int k = 0; k < nt; k++) if (D.adm_cq[S.tgt[k]] == cq) pm = PM_PREEMPT;
+      }
+      s_res[0] = pm; s_res[1] = ba;
+    }
+    __syncthreads();
+    *borrow_after = s_res[1];
+    return s_res[0];
+  }
+  // GetTargets preemption.go:127-146 for the assignment currently in the output rows
+  __device__ inline int get_targets(const DevSnap &D, int wl) {
+    int cq = D.wl_cq[wl];
+    if (!candidates_possible(D, cq)) return 0;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const int R = D.R;
+      c->cq = cq; c->prio = D.wl_priority[wl]; c->ts = D.wl_ts[wl];
+      bool covers_pods = D.pods_res >= 0 && rg_by_resource(D, cq, D.pods_res) >= 0;
+      int nu = 0, nn = 0;
+      for (int row = D.wl_ps_start[wl]; row < D.wl_ps_start[wl + 1]; row++)
+        for (int r = 0; r < R; r++) {
+          int f = D.ps_flavor[(size_t)row * R + r];
+          if (f < 0) continue;
+          int fr = f * R + r;
+          if (D.ps_res_mode[(size_t)row * R + r] == KB_MODE_PREEMPT) {  // flavorResourcesNeedPreemption :480-490
+            int j = 0; while (j < nn && c->need_fr[j] != fr) j++;
+            if (j == nn && nn < KB_MAX_CELLS) c->need_fr[nn++] = fr;
+          }
+          i64 q = ps_request(D, row, r, D.ps_count_out[row], covers_pods);  // TotalRequestsFor flavorassigner.go:198-218
+          if (q == 0) continue;
+          int j = 0; while (j < nu && c->use_fr[j] != fr) j++;
+          if (j == nu) { if (nu == KB_MAX_CELLS) continue; c->use_fr[nu] = fr; c->use_q[nu] = 0; nu++; }
+          c->use_q[j] += q;
+        }
+      c->n_use = nu; c->n_need = nn;
+    }
+    __syncthreads();
+    classical_search<kSmem>(D, *T, c, S);
+    return c->n_targets;
+  }
+};
+
+template <bool kSmem>
+__global__ void __launch_bounds__(128) k_nominate_search(DevSnap D) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ PreCtx ctx;
+  __shared__ int s_item, s_res[2];
+  const int FR = D.FR;
+  PreScratch S;
+  {
+    size_t b = blockIdx.x;
+    S.cand = D.sc_cand + b * D.sc_adm_cap; S.variant = D.sc_variant + b * D.sc_adm_cap;
+    S.tgt = D.sc_tgt + b * D.sc_adm_cap; S.tgt_reason = D.sc_tgt_reason + b * D.sc_adm_cap;
+    S.cq_class = D.sc_cq_class + b * D.sc_node_cap; S.on_path = D.sc_on_path + b * D.sc_node_cap;
+    S.cq_lca = D.sc_cq_lca + b * D.sc_node_cap;
+  }
+  PTab<kSmem> T;
+  T.D = &D; T.FR = FR;
+  int cur_slot = -1;
+  while (true) {
+    __syncthreads();
+    if (threadIdx.x == 0) s_item = atomicAdd(D.ps_cursor, 1);
+    __syncthreads();
+    int item = s_item;
+    if (item >= *D.ps_n) break;
+    int e = D.ps_list[item];
+    int wl = D.heads[e];
+    int cq = D.wl_cq[wl];
+    int slot = D.root_slot[cq];
+    if (slot != cur_slot) {  // stage a private copy of the root's tree (the search restores it after use)
+      cur_slot = slot;
+      if (slot < D.nLone) { T.nodes = &D.lone_cqs[slot]; T.nn = 1; }
+      else { int t = slot - D.nLone; T.nodes = D.tree_nodes + D.tree_start[t]; T.nn = D.tree_start[t + 1] - D.tree_start[t]; }
+      size_t tb = (size_t)T.nn * FR;
+      if (kSmem) {
+        i64 *u = (i64 *)smem_raw, *sb = u + tb, *lq = sb + tb, *bl = lq + tb;
+        int *lp = (int *)(bl + tb);
+        for (int i = threadIdx.x; i < (int)tb; i += blockDim.x) {
+          size_t c = (size_t)T.nodes[i / FR] * FR + i % FR;
+          i64 sub = D.subtree[c];
+          u[i] = D.usage[c]; sb[i] = sub; lq[i] = local_quota(sub, D.llimit[c]); bl[i] = D.blimit[c];
+        }
+        for (int i = threadIdx.x; i < T.nn; i += blockDim.x) { int pn = D.parent[T.nodes[i]]; lp[i] = pn < 0 ? -1 : D.local_idx[pn]; }
+        T.usage = u; T.sub = sb; T.lq = lq; T.bl = bl; T.lparent = lp;
+      } else {
+        i64 *u = D.sc_usage + (size_t)blockIdx.x * D.sc_node_cap * FR;
+        for (int i = threadIdx.x; i < (int)tb; i += blockDim.x) u[i] = D.usage[(size_t)T.nodes[i / FR] * FR + i % FR];
+        T.usage = u;
+      }
+      __syncthreads();
+    }
+    NomSearch<kSmem> orc{&T, &ctx, S, s_res};
+    int borrowing, nt;
+    int mode = get_assignments(D, orc, wl, &borrowing, &nt);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      D.mode[e] = (uint8_t)mode;
+      D.borrow[e] = borrowing;
+      int off = 0;
+      if (nt > 0) {
+        off = atomicAdd(D.tgt_pool_used, nt);
+        if (off + nt <= D.tgt_pool_cap) {
+          for (int k = 0; k < nt; k++) { D.tgt_pool_adm[off + k] = S.tgt[k]; D.tgt_pool_reason[off + k] = S.tgt_reason[k]; }
+        } else { atomicOr(D.status, KBS_TARGET_OVERFLOW); nt = 0; }
+      }
+      D.tgt_cnt[e] = nt; D.tgt_off[e] = off;
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------
@@ -441,6 +659,24 @@ struct Tab {
     }
     return a;
   }
+  __device__ inline void add_node(int nd, int fr, i64 val) const {  // addUsage :137-145 walking parents
+    while (true) {
+      i64 u = U(nd, fr), la = imax(0, LQ(nd, fr) - u);
+      setU(nd, fr, u + val);
+      int p = parent(nd);
+      if (p < 0 || !(val > la)) break;
+      val -= la; nd = p;
+    }
+  }
+  __device__ inline void remove_node(int nd, int fr, i64 val) const {  // removeUsage :149-158
+    while (true) {
+      i64 u = U(nd, fr), stored = u - LQ(nd, fr);
+      setU(nd, fr, u - val);
+      int p = parent(nd);
+      if (stored <= 0 || p < 0) break;
+      val = imin(val, stored); nd = p;
+    }
+  }
   __device__ inline void add(const int *path, int plen, int fr, i64 val) const {  // addUsage :137-145
     for (int k = 0; k < plen; k++) {
       int nd = path[k];
@@ -493,7 +729,7 @@ __device__ inline void commit_entry(const DevSnap &D, const Tab<kSmem> &T, int *
   if (lane == 0) { int pl = 0; for (int t = nd; t >= 0; t = T.parent(t)) s_path[pl++] = t; s_path[KB_MAX_DEPTH + 1] = pl; }
   __syncwarp();
   int plen = s_path[KB_MAX_DEPTH + 1];
-  if (mode == KB_MODE_PREEMPT) {  // Preempt without targets: scheduler.go:303-318
+  if (mode == KB_MODE_PREEMPT && D.tgt_cnt[e] == 0) {  // Preempt without targets: scheduler.go:303-318
     if (lane == 0) D.decision[e] = KB_DEC_PREEMPT_NO_TARGETS;
     int cq = D.wl_cq[D.heads[e]];
     if (D.cq_reclaim_within[cq] != KB_POLICY_ANY) {  // !CanAlwaysReclaim policy.go:27-29
@@ -510,14 +746,48 @@ __device__ inline void commit_entry(const DevSnap &D, const Tab<kSmem> &T, int *
     __syncwarp();
     return;
   }
+  // entries with preemption targets: overlap check (:321-325) and fits() with the usage of
+  // every workload preempted so far in this root plus the new targets removed (:503-511)
+  int ntg = D.tgt_cnt[e], toff = D.tgt_off[e];
+  int slot = D.root_slot[D.wl_cq[D.heads[e]]];
+  int *plist = D.root_pre_list + D.root_adm_start[slot];
+  int npre = D.root_pre_count[slot];
+  if (ntg > 0) {
+    bool overlap = false;
+    for (int k = lane; k < ntg; k += 32) if (D.preempted[D.tgt_pool_adm[toff + k]]) overlap = true;
+    if (__any_sync(0xffffffffu, overlap)) { if (lane == 0) D.decision[e] = KB_DEC_SKIPPED_OVERLAP; __syncwarp(); return; }
+  }
+  auto apply = [&](int a, bool remove) {  // one admitted workload: its cells are distinct columns -> one lane each
+    int nd2 = T.handle(D.adm_cq[a]);
+    for (int k = D.adm_use_start[a] + lane; k < D.adm_use_start[a + 1]; k += 32) {
+      if (remove) T.remove_node(nd2, D.adm_use_fr[k], D.adm_use_qty[k]);
+      else T.add_node(nd2, D.adm_use_fr[k], D.adm_use_qty[k]);
+    }
+    __syncwarp();
+  };
+  if (npre > 0 || ntg > 0) {  // SimulateWorkloadRemoval snapshot.go:67-84
+    for (int k = 0; k < npre; k++) apply(plist[k], true);
+    for (int k = 0; k < ntg; k++) apply(D.tgt_pool_adm[toff + k], true);
+  }
   bool ok = true;  // fits :503-511
   for (int fr = lane; fr < FR; fr += 32) {
     i64 q = qrow[fr];
     if (q > 0 && imax(0, T.avail(s_path, plen, fr)) < q) ok = false;
   }
   ok = __all_sync(0xffffffffu, ok);
-  if (ok) for (int fr = lane; fr < FR; fr += 32) { i64 q = qrow[fr]; if (q > 0) T.add(s_path, plen, fr, q); }  // cq.AddUsage :336
-  if (lane == 0) D.decision[e] = ok ? KB_DEC_ASSUMED : KB_DEC_SKIPPED_NO_FIT;
+  if (npre > 0 || ntg > 0) {
+    for (int k = 0; k < npre; k++) apply(plist[k], false);
+    for (int k = 0; k < ntg; k++) apply(D.tgt_pool_adm[toff + k], false);
+  }
+  if (ok) {
+    if (ntg > 0) {  // preemptedWorkloads.Insert :335
+      for (int k = lane; k < ntg; k += 32) { int a = D.tgt_pool_adm[toff + k]; D.preempted[a] = 1; plist[npre + k] = a; }
+      if (lane == 0) D.root_pre_count[slot] = npre + ntg;
+      __syncwarp();
+    }
+    for (int fr = lane; fr < FR; fr += 32) { i64 q = qrow[fr]; if (q > 0) T.add(s_path, plen, fr, q); }  // cq.AddUsage :336
+  }
+  if (lane == 0) D.decision[e] = ok ? (mode == KB_MODE_PREEMPT ? KB_DEC_PREEMPTING : KB_DEC_ASSUMED) : KB_DEC_SKIPPED_NO_FIT;
   __syncwarp();
 }
 

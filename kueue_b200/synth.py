@@ -28,7 +28,8 @@ def _cohort_forest(n_root: int, fanouts, cqs_per_leaf: int):
 
 def make_snapshot(config: int = 2, W: int | None = None, Q: int | None = None, F: int | None = None,
                   R: int | None = None, seed: int | None = None, heads: str = "all",
-                  podsets_max: int = 1) -> abi.FlatSnapshot:
+                  podsets_max: int = 1, admitted: int | None = None, preemption: bool | None = None,
+                  partial: bool = False, tight: float = 1.0) -> abi.FlatSnapshot:
     """config 1: 100 wl x 10 CQ x 2 flavors x 3 resources, no cohort
        config 2: 100k x 1k x 8 x 4, StrictFIFO, no cohort, usage 60-90% of nominal
        config 3: 1M x 10k, 100 flat cohorts x 100 CQ, BestEffortFIFO, fair sharing
@@ -79,11 +80,47 @@ def make_snapshot(config: int = 2, W: int | None = None, Q: int | None = None, F
         blm = rng.random(Q) < 0.3
         bl[:Q][blm] = nominal[:Q][blm]
     snap.set("nominal", nominal); snap.set("borrow_limit", bl); snap.set("lend_limit", ll)
-    lo, hi = {1: (0.6, 0.9), 2: (0.6, 0.9), 3: (0.7, 1.25), 4: (0.75, 1.15)}[config]
-    usage = (nominal[:Q] * rng.uniform(lo, hi, (Q, FR))).astype(np.int64)
-    if config in (1, 2):
-        usage = np.minimum(usage, nominal[:Q])
+    lo, hi = {1: (0.6, 0.9), 2: (0.6, 0.9), 3: (0.7, 1.25), 4: (0.85, 1.2)}[config]
+    lo, hi = lo * tight, hi * tight
+    if preemption is None:
+        preemption = config == 4
+    if admitted is None:
+        admitted = max(W // 5, 2 * Q * F) if preemption else 0
+    if admitted:
+        # admitted workloads (preemption candidates); ClusterQueue usage is exactly their sum
+        A = admitted
+        pair = rng.permutation(A) % (Q * F)        # round-robin over (ClusterQueue, flavor) pairs
+        a_cq, a_f = pair // F, pair % F
+        per = np.bincount(pair, minlength=Q * F)[pair].astype(np.float64)
+        frac = rng.uniform(lo, hi, Q * F)[pair]      # target usage of the pair as a fraction of nominal
+        qty = (nominal[:Q].reshape(Q, F, R)[a_cq, a_f] * (frac / per)[:, None] * rng.uniform(0.7, 1.3, (A, R))).astype(np.int64)
+        usage = np.zeros((Q, F, R), np.int64)
+        np.add.at(usage, (a_cq, a_f), qty)
+        usage = usage.reshape(Q, FR)
+        snap.set("adm_cq", a_cq); snap.set("adm_priority", rng.integers(0, 4, A) * 100)
+        snap.set("adm_ts", 1_600_000_000_000_000_000 + rng.permutation(A).astype(np.int64) * 1_000_000)
+        qr = 1_650_000_000_000_000_000 + rng.permutation(A).astype(np.int64) * 1_000_000
+        qr[rng.random(A) < 0.02] = abi.KB_TS_UNSET
+        snap.set("adm_qr_ts", qr); snap.set("adm_uid", rng.permutation(A) + 10_000_000)
+        snap.set("adm_evicted", rng.random(A) < 0.01)
+        snap.set("adm_use_start", np.arange(A + 1) * R)
+        snap.set("adm_use_fr", (a_f[:, None] * R + np.arange(R)[None, :]).reshape(-1))
+        snap.set("adm_use_qty", qty.reshape(-1))
+        snap.now_ns = 1_700_000_000_000_000_000
+    else:
+        usage = (nominal[:Q] * rng.uniform(lo, hi, (Q, FR))).astype(np.int64)
+        if config in (1, 2):
+            usage = np.minimum(usage, nominal[:Q])
     snap.set("cq_usage", usage)
+    if preemption:
+        snap.set("cq_within_cq", rng.choice([abi.POLICY_NEVER, abi.POLICY_LOWER_PRIORITY, abi.POLICY_LOWER_OR_NEWER_EQUAL_PRIORITY], Q))
+        if C:
+            snap.set("cq_reclaim_within", rng.choice([abi.POLICY_NEVER, abi.POLICY_LOWER_PRIORITY, abi.POLICY_ANY], Q))
+            bw = rng.random(Q) < 0.4
+            bw &= snap.arrays["cq_reclaim_within"] != abi.POLICY_NEVER  # API validation: reclaim=Never excludes borrowWithinCohort
+            snap.set("cq_borrow_within", np.where(bw, abi.POLICY_LOWER_PRIORITY, abi.POLICY_NEVER))
+            thr = bw & (rng.random(Q) < 0.5)
+            snap.set("cq_has_bwc_threshold", thr); snap.set("cq_bwc_threshold", np.where(thr, 100, 0))
     # ---- CQ attributes: one resource group covering all resources, all flavors ----
     snap.set("cq_strategy", np.full(Q, abi.QUEUE_STRICT_FIFO if config == 2 else abi.QUEUE_BEST_EFFORT_FIFO))
     snap.set("cq_rg_start", np.arange(Q + 1))
@@ -107,6 +144,9 @@ def make_snapshot(config: int = 2, W: int | None = None, Q: int | None = None, F
     snap.set("ps_req", per_pod * count[:, None])
     snap.set("ps_req_mask", np.full(P, (1 << R) - 1))
     snap.set("ps_count", count)
+    if partial:
+        mc = np.where(rng.random(P) < 0.5, np.maximum(1, count // 2), -1)
+        snap.set("ps_min_count", mc)
     ok = rng.integers(0, 2**63, P, dtype=np.uint64) | rng.integers(0, 2**63, P, dtype=np.uint64) | np.uint64(1 << (F - 1))
     snap.set("ps_flavor_ok", ok)  # ~75% of flavors eligible, last flavor always
     if heads == "all":

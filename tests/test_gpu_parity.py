@@ -61,8 +61,8 @@ def _fair(snap):
 @pytest.mark.parametrize("make", [
     lambda: synth.make_snapshot(3, W=3000, Q=300, heads="one_per_cq"),
     lambda: synth.make_snapshot(3, W=30000, Q=1000, heads="one_per_cq", podsets_max=2),
-    lambda: _fair(synth.make_snapshot(4, W=4000, Q=200, heads="one_per_cq")),      # fair sharing over a depth-4 tree
-    lambda: _fair(synth.make_snapshot(4, W=40000, Q=2000, heads="one_per_cq")),    # tree too large for shared memory
+    lambda: _fair(synth.make_snapshot(4, W=4000, Q=200, heads="one_per_cq", preemption=False)),      # fair sharing over a depth-4 tree
+    lambda: _fair(synth.make_snapshot(4, W=40000, Q=2000, heads="one_per_cq", preemption=False)),    # tree too large for shared memory
     lambda: _fair(synth.make_snapshot(2, W=2000, Q=100, heads="one_per_cq")),      # fair sharing, CQs without cohorts
 ])
 def test_fair_sharing_cycle_matches_oracle(ev, make):
@@ -74,6 +74,39 @@ def test_fair_sharing_cycle_matches_oracle(ev, make):
 def test_full_size_config3_single_cycle(ev):
     snap = synth.make_snapshot(3, heads="one_per_cq")
     got, want = ev.run_cycle(snap), oracle.run_cycle(snap)
+    assert_cycle_equal(got, want)
+
+
+def _classical(snap):
+    snap.flags &= ~abi.F_FAIR_SHARING
+    return snap
+
+
+@pytest.mark.parametrize("make", [
+    lambda: synth.make_snapshot(2, W=5000, Q=50, preemption=True, tight=1.2),                      # within-ClusterQueue preemption
+    lambda: synth.make_snapshot(2, W=5000, Q=50, preemption=True, tight=1.2, podsets_max=3, seed=9),
+    lambda: _classical(synth.make_snapshot(3, W=3000, Q=300, preemption=True, heads="one_per_cq", tight=1.1)),  # flat cohorts: reclaim
+    lambda: synth.make_snapshot(4, W=4000, Q=200, heads="one_per_cq", tight=1.1),                  # depth-4 tree, heavy preemption
+    lambda: synth.make_snapshot(4, W=2000, Q=100, tight=1.06),                                      # batched heads
+    lambda: synth.make_snapshot(4, W=40000, Q=2000, heads="one_per_cq"),                            # trees too large for shared memory
+])
+def test_preemption_cycle_matches_oracle(ev, make):
+    snap = make()
+    cap = 40 * snap.n_adm + 10000
+    got, want = ev.run_cycle(snap, abi.CycleOut(snap, cap)), oracle.run_cycle(snap, cap)
+    assert want.n_targets > 0
+    assert_cycle_equal(got, want)
+
+
+@pytest.mark.parametrize("make", [
+    lambda: synth.make_snapshot(2, W=5000, Q=50, partial=True, podsets_max=2),
+    lambda: synth.make_snapshot(4, W=2000, Q=100, partial=True, podsets_max=3, tight=1.06),
+])
+def test_partial_admission_matches_oracle(ev, make):
+    snap = make()
+    cap = 40 * snap.n_adm + 10000
+    got, want = ev.run_cycle(snap, abi.CycleOut(snap, cap)), oracle.run_cycle(snap, cap)
+    assert (want.ps_count != snap.ps_count).any(), "fixture must exercise reduced counts"
     assert_cycle_equal(got, want)
 
 
