@@ -28,6 +28,8 @@ _QRE = re.compile(r"^([+-]?[0-9]*\.?[0-9]+)(m|k|M|G|T|P|Ki|Mi|Gi|Ti|Pi)?$")
 
 def resource_value(name: str, q) -> int:
     """ResourceValue: milli-units for cpu, absolute units otherwise."""
+    if getattr(q, "_raw_units", False):
+        return int(q)
     if isinstance(q, (int, np.integer)):
         return int(q) * (1000 if name == "cpu" else 1)
     m = _QRE.match(str(q))

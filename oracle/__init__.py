@@ -55,3 +55,16 @@ def run_cycle(snap, tgt_capacity=None):
     assert rc == 0, rc
     out.n_targets = out.struct.n_targets
     return out
+
+
+def get_targets(snap, wl, ps_flavor, ps_res_mode, ps_count=None, cap=4096):
+    """Preemptor.GetTargets for workload `wl` with an explicit assignment (TestPreemption-style)."""
+    import numpy as np
+    s = snap.as_struct()
+    f = np.ascontiguousarray(ps_flavor, np.int8); m = np.ascontiguousarray(ps_res_mode, np.int8)
+    cnt = None if ps_count is None else np.ascontiguousarray(ps_count, np.int32)
+    adm = np.zeros(cap, np.int32); reason = np.zeros(cap, np.uint8)
+    n = lib().ko_get_targets(C.byref(s), C.c_int32(wl), f.ctypes.data_as(C.POINTER(C.c_int8)), m.ctypes.data_as(C.POINTER(C.c_int8)),
+                             None if cnt is None else cnt.ctypes.data_as(C.POINTER(C.c_int32)),
+                             adm.ctypes.data_as(C.POINTER(C.c_int32)), reason.ctypes.data_as(C.POINTER(C.c_uint8)), C.c_int32(cap))
+    return [(int(adm[i]), int(reason[i])) for i in range(n)]

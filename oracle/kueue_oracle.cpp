@@ -1094,12 +1094,12 @@ int32_t ko_run_cycle(const kb_snapshot *s, kb_cycle_out *out) {
 // Single preemption query (TestPreemption-style goldens): targets for workload
 // `wl` given an explicit assignment (flavor per podset/resource + mode).
 int32_t ko_get_targets(const kb_snapshot *s, int32_t wl, const int8_t *ps_flavor, const int8_t *ps_res_mode,
-                       int32_t *tgt_adm, uint8_t *tgt_reason, int32_t cap) {
+                       const int32_t *ps_assigned_count, int32_t *tgt_adm, uint8_t *tgt_reason, int32_t cap) {
   Oracle o(*s);
   Assignment a;
   int ps0 = s->wl_ps_start[wl], np = s->wl_ps_start[wl + 1] - ps0;
   for (int k = 0; k < np; k++) {
-    PodSetAssign p; p.count = s->ps_count[ps0 + k]; p.hasReasons = true;
+    PodSetAssign p; p.count = ps_assigned_count ? ps_assigned_count[k] : s->ps_count[ps0 + k]; p.hasReasons = true;
     for (int r = 0; r < o.R; r++) {
       p.flavor[r] = ps_flavor[(size_t)k * o.R + r]; p.mode[r] = ps_res_mode[(size_t)k * o.R + r];
       if (p.flavor[r] >= 0) p.nFlavors++;

@@ -110,6 +110,26 @@ def test_partial_admission_matches_oracle(ev, make):
     assert_cycle_equal(got, want)
 
 
+def _golden_cases():
+    import json, os
+    here = os.path.dirname(__file__)
+    out = []
+    for f in ("preemption_cases.json", "preemption_hierarchical_cases.json"):
+        for name, tc in json.load(open(os.path.join(here, "golden", f))).items():
+            out.append(pytest.param(tc, id=f"{f.split('_cases')[0]}:{name[:60]}"))
+    return out
+
+
+@pytest.mark.parametrize("tc", _golden_cases())
+def test_reference_preemption_scenarios_cycle(ev, tc):
+    """The reference's TestPreemption / TestHierarchicalPreemptions scenarios as one scheduling cycle
+    with the incoming workload as the only head: device vs oracle, bit-exact."""
+    from tests.golden_loader import build_preemption_case
+    snap, idx = build_preemption_case(tc)
+    got, want = ev.run_cycle(snap), oracle.run_cycle(snap)
+    assert_cycle_equal(got, want)
+
+
 def test_full_size_config2(ev):
     snap = synth.make_snapshot(2)
     got, want = ev.run_cycle(snap), oracle.run_cycle(snap)
