@@ -154,8 +154,18 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    # each rank owns its own shard of the cluster: independent root cohorts => no collective on the data path
-    snap = synth.make_snapshot(args.config, seed=args.config * 1000 + rank, heads=HEADS[args.config])
+    # weak scaling: the cluster grows with the number of GPUs (world x the config's ClusterQueues and pending
+    # workloads); every rank keeps the root cohorts kueue_b200.shard assigns to it — root cohorts are independent
+    # coupling domains, so there is no collective on the data path and the host concatenates the decisions.
+    if world > 1:
+        from kueue_b200 import shard as kshard
+        base = synth.make_snapshot(args.config, W=1, Q=1) if False else None
+        dflt = {1: (100, 10), 2: (100_000, 1_000), 3: (1_000_000, 10_000), 4: (1_000_000, 10_000)}[args.config]
+        glob = synth.make_snapshot(args.config, W=dflt[0] * world, Q=dflt[1] * world, heads=HEADS[args.config])
+        snap, _ = kshard.shard(glob, rank, world)
+        del glob
+    else:
+        snap = synth.make_snapshot(args.config, heads=HEADS[args.config])
     ev = native.Evaluator(local_rank)
     snap = native.pin_snapshot(snap)            # host SoA buffers are page-locked (kb_alloc_pinned)
     out = native.pin_cycle_out(abi.CycleOut(snap))
