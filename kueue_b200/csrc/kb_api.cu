@@ -317,7 +317,7 @@ extern "C" int32_t kb_upload(kb_handle *h, const kb_snapshot *s) {
     size_t tb = (size_t)h->max_tree_nodes * FR * 32 + (size_t)h->max_tree_nodes * 4 + 64;
     h->search_smem = tb <= 190 * 1024;
     h->search_smem_bytes = h->search_smem ? tb : 0;
-    int per_sm = !h->search_smem ? 2 : (tb <= 24 * 1024 ? 8 : (tb <= 48 * 1024 ? 4 : (tb <= 100 * 1024 ? 2 : 1)));
+    int per_sm = !h->search_smem ? 8 : (tb <= 6 * 1024 ? 32 : (tb <= 12 * 1024 ? 16 : (tb <= 24 * 1024 ? 8 : (tb <= 48 * 1024 ? 4 : (tb <= 100 * 1024 ? 2 : 1)))));
     h->search_grid = std::max(1, std::min(h->sm_count * per_sm, std::max(1, s->n_heads)));
     if (A == 0) h->search_grid = 1;
   }
@@ -325,7 +325,7 @@ extern "C" int32_t kb_upload(kb_handle *h, const kb_snapshot *s) {
   size_t pool_cap = A * 4 + 1024;
   need(A, 4); need(nroots + 1, 4); need(H, 4); need(2, 4); need(H, 4); need(H, 4); need(pool_cap, 4); need(pool_cap, 1); need(1, 4);
   need(A, 1); need(A, 4); need(nroots, 4);
-  need(G * acap, 4); need(G * acap, 4); need(G * ncap, 4); need(G * acap, 1); need(G * acap, 1); need(G * ncap, 1); need(G * ncap, 1);
+  need(G * acap, 4); need(G * acap, 4); need(G * acap, 4); need(G * acap, 4); need(G * ncap, 4); need(G * acap, 1); need(G * acap, 1); need(G * ncap, 1); need(G * ncap, 1);
   if (!h->search_smem) need(G * ncap * FR, 8);
   bool fair = (s->flags & KB_F_FAIR_SHARING) != 0;
   if (fair) { need(H * FR, 8); need(H * KB_MAX_DEPTH, 16); need(N, 4); need(N, 4); }
@@ -374,6 +374,7 @@ extern "C" int32_t kb_upload(kb_handle *h, const kb_snapshot *s) {
   D.tgt_pool_used = h->arena.take<int32_t>(1); D.tgt_pool_cap = (int)pool_cap;
   D.preempted = h->arena.take<uint8_t>(A); D.root_pre_list = h->arena.take<int32_t>(A); D.root_pre_count = h->arena.take<int32_t>(nroots);
   D.sc_cand = h->arena.take<int32_t>(G * acap); D.sc_tgt = h->arena.take<int32_t>(G * acap); D.sc_cq_lca = h->arena.take<int32_t>(G * ncap);
+  D.sc_aux1 = h->arena.take<int32_t>(G * acap); D.sc_aux2 = h->arena.take<int32_t>(G * acap);
   D.sc_variant = h->arena.take<uint8_t>(G * acap); D.sc_tgt_reason = h->arena.take<uint8_t>(G * acap);
   D.sc_cq_class = h->arena.take<int8_t>(G * ncap); D.sc_on_path = h->arena.take<int8_t>(G * ncap);
   D.sc_usage = h->search_smem ? nullptr : h->arena.take<i64>(G * ncap * FR);
@@ -473,13 +474,13 @@ extern "C" int32_t kb_cycle_resident(kb_handle *h) {
   launch_tree(h, &launches);
   if (D.H) {
     kmark(h, KB_K_NOMINATE); k_nominate<<<(D.H + 127) / 128, 128, 0, h->stream>>>(D); launches++;
-    if (D.A && !(D.flags & KB_F_FAIR_SHARING)) {  // target search for the entries k_nominate deferred
+    if (D.A) {  // target search for the entries k_nominate deferred
       kmark(h, KB_K_PREEMPT);
       if (h->search_smem) {
         CUDA_TRY(h, cudaFuncSetAttribute(k_nominate_search<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        k_nominate_search<true><<<h->search_grid, 128, h->search_smem_bytes, h->stream>>>(D);
+        k_nominate_search<true><<<h->search_grid, 32, h->search_smem_bytes, h->stream>>>(D);
       } else {
-        k_nominate_search<false><<<h->search_grid, 128, 0, h->stream>>>(D);
+        k_nominate_search<false><<<h->search_grid, 32, 0, h->stream>>>(D);
       }
       launches++;
     }
@@ -505,6 +506,7 @@ extern "C" int32_t kb_cycle_resident(kb_handle *h) {
   CUDA_TRY(h, cudaMemcpy(&st, D.status, 4, cudaMemcpyDeviceToHost));
   if (st & KBS_UNSUPPORTED_PREEMPTION) return fail(h, KB_ERR_UNSUPPORTED, "fair-sharing preemption search is not on the device yet");
   if (st & KBS_TARGET_OVERFLOW) return fail(h, KB_ERR_CAPACITY, "per-entry usage cell capacity exceeded");
+  if (st & KBS_INTERNAL_LOOP) return fail(h, KB_ERR_CUDA, "internal: iteration guard tripped in the target search");
   return KB_OK;
 }
 

@@ -18,7 +18,7 @@ typedef unsigned long long u64;
 #define KB_MAX_CELLS 128  // distinct flavor-resource cells in one workload's usage
 
 // Status word bits written by kernels (checked by the host after a cycle).
-enum { KBS_UNSUPPORTED_PREEMPTION = 1u << 0, KBS_TARGET_OVERFLOW = 1u << 1, KBS_PATH_TOO_DEEP = 1u << 2 };
+enum { KBS_UNSUPPORTED_PREEMPTION = 1u << 0, KBS_TARGET_OVERFLOW = 1u << 1, KBS_PATH_TOO_DEEP = 1u << 2, KBS_INTERNAL_LOOP = 1u << 3 };
 
 struct DevSnap {
   // dimensions
@@ -90,7 +90,7 @@ struct DevSnap {
   int32_t *root_pre_list;        // [A] per-root lists (segments of root_adm_start) of preempted workloads
   int32_t *root_pre_count;       // [nRoots]
   // per-CTA scratch of k_nominate_search
-  int32_t *sc_cand, *sc_tgt, *sc_cq_lca; uint8_t *sc_variant, *sc_tgt_reason; int8_t *sc_cq_class, *sc_on_path;
+  int32_t *sc_cand, *sc_tgt, *sc_cq_lca, *sc_aux1, *sc_aux2; uint8_t *sc_variant, *sc_tgt_reason; int8_t *sc_cq_class, *sc_on_path;
   i64 *sc_usage;
   int sc_adm_cap, sc_node_cap;
   // ---- fair-sharing scratch ----
@@ -128,4 +128,25 @@ __device__ inline int find_height(const DevSnap &D, const i64 *usage, int cq, in
   }
   *may_reclaim = false;
   return D.height[last];
+}
+
+// DominantResourceShare value (fair_sharing.go:43-100)
+struct DevDRS {
+  double weight, ratio;
+  int res;
+  bool borrowing;
+};
+__device__ __forceinline__ bool drs_zero_weight_borrows(const DevDRS &d) { return d.weight == 0 && d.ratio != 0; }
+__device__ __forceinline__ double drs_precise(const DevDRS &d) {  // :75-83
+  if (d.ratio == 0) return 0.0;
+  if (d.weight == 0) return __longlong_as_double(0x7ff0000000000000LL);
+  return d.ratio / d.weight;
+}
+__device__ __forceinline__ int cmp_d(double a, double b) { return a < b ? -1 : (a > b ? 1 : 0); }
+__device__ inline int drs_compare(const DevDRS &a, const DevDRS &b) {  // CompareDRS :89-100
+  bool za = drs_zero_weight_borrows(a), zb = drs_zero_weight_borrows(b);
+  if (za && zb) return cmp_d(a.ratio, b.ratio);
+  if (za) return 1;
+  if (zb) return -1;
+  return cmp_d(drs_precise(a), drs_precise(b));
 }

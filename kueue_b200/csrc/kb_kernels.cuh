@@ -98,25 +98,6 @@ __global__ void k_lone(DevSnap D) {
 // ---------------------------------------------------------------------------
 // K1d: DominantResourceShare of every node (fair_sharing.go:126-156, wlReq = nil).
 // ---------------------------------------------------------------------------
-struct DevDRS {
-  double weight, ratio;
-  int res;
-  bool borrowing;
-};
-__device__ __forceinline__ bool drs_zero_weight_borrows(const DevDRS &d) { return d.weight == 0 && d.ratio != 0; }
-__device__ __forceinline__ double drs_precise(const DevDRS &d) {  // :75-83
-  if (d.ratio == 0) return 0.0;
-  if (d.weight == 0) return __longlong_as_double(0x7ff0000000000000LL);
-  return d.ratio / d.weight;
-}
-__device__ __forceinline__ int cmp_d(double a, double b) { return a < b ? -1 : (a > b ? 1 : 0); }
-__device__ inline int drs_compare(const DevDRS &a, const DevDRS &b) {  // CompareDRS :89-100
-  bool za = drs_zero_weight_borrows(a), zb = drs_zero_weight_borrows(b);
-  if (za && zb) return cmp_d(a.ratio, b.ratio);
-  if (za) return 1;
-  if (zb) return -1;
-  return cmp_d(drs_precise(a), drs_precise(b));
-}
 // DRS of node n when its usage row is `u[fr] + extra[fr]` (extra may be null).
 template <typename UsageFn>
 __device__ inline DevDRS drs_node(const DevSnap &D, int n, UsageFn usage_of) {
@@ -412,8 +393,7 @@ __global__ void __launch_bounds__(128) k_nominate(DevSnap D) {
   D.tgt_cnt[e] = 0;
   D.tgt_off[e] = 0;
   if (orc.need_search) {
-    if (D.flags & KB_F_FAIR_SHARING) atomicOr(D.status, KBS_UNSUPPORTED_PREEMPTION);  // fair preemption: not on the device yet
-    else D.ps_list[atomicAdd(D.ps_n, 1)] = e;
+    D.ps_list[atomicAdd(D.ps_n, 1)] = e;
   }
   atomicAdd(&D.root_count[D.root_slot[D.wl_cq[wl]]], 1);
 }
@@ -423,77 +403,65 @@ __global__ void __launch_bounds__(128) k_nominate(DevSnap D) {
 // of the CTA run the (scalar) flavor-assignment control flow uniformly and cooperate inside
 // the search (kb_preempt.cuh).
 // ---------------------------------------------------------------------------
+// Oracle policy of k_nominate_search: flavor assignment and target searches of one deferred
+// entry run on lane 0 of a single-warp CTA (single writer of the output rows).
 template <bool kSmem>
 struct NomSearch {
   const PTab<kSmem> *T;
   PreCtx *c;
   PreScratch S;
-  int *s_res;  // [2] shared result slots
+  __device__ inline void run_search(const DevSnap &D) { target_search<kSmem>(D, *T, c, S); }
   // SimulatePreemption preemption_oracle.go:41-71
   __device__ inline int simulate(const DevSnap &D, int wl, int cq, int fr, i64 val, int *borrow_after) {
-    if (!candidates_possible(D, cq)) { *borrow_after = 0; return PM_NOCAND; }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      c->cq = cq; c->prio = D.wl_priority[wl]; c->ts = D.wl_ts[wl];
-      c->n_use = 1; c->use_fr[0] = fr; c->use_q[0] = val;
-      c->n_need = 1; c->need_fr[0] = fr;
-    }
-    __syncthreads();
-    classical_search<kSmem>(D, *T, c, S);
-    if (threadIdx.x == 0) {
-      int nt = c->n_targets, pm = PM_NOCAND, ba = 0;
-      if (nt > 0) {
-        int hcq = T->handle(cq);
-        for (int k = 0; k < nt; k++) T->remove_adm(S.tgt[k]);
-        ba = T->find_height(hcq, fr, val);
-        for (int k = 0; k < nt; k++) T->add_adm(S.tgt[k]);
-        pm = PM_RECLAIM;
-        for (int k = 0; k < nt; k++) if (D.adm_cq[S.tgt[k]] == cq) pm = PM_PREEMPT;
-      }
-      s_res[0] = pm; s_res[1] = ba;
-    }
-    __syncthreads();
-    *borrow_after = s_res[1];
-    return s_res[0];
+    *borrow_after = 0;
+    if (!candidates_possible(D, cq)) return PM_NOCAND;
+    c->cq = cq; c->prio = D.wl_priority[wl]; c->ts = D.wl_ts[wl];
+    c->n_use = 1; c->use_fr[0] = fr; c->use_q[0] = val;
+    c->n_need = 1; c->need_fr[0] = fr;
+    run_search(D);
+    int nt = c->n_targets;
+    if (nt == 0) return PM_NOCAND;
+    int hcq = T->handle(cq);
+    for (int k = 0; k < nt; k++) T->remove_adm(S.tgt[k]);
+    *borrow_after = T->find_height(hcq, fr, val);
+    for (int k = 0; k < nt; k++) T->add_adm(S.tgt[k]);
+    for (int k = 0; k < nt; k++) if (D.adm_cq[S.tgt[k]] == cq) return PM_PREEMPT;
+    return PM_RECLAIM;
   }
   // GetTargets preemption.go:127-146 for the assignment currently in the output rows
   __device__ inline int get_targets(const DevSnap &D, int wl) {
     int cq = D.wl_cq[wl];
     if (!candidates_possible(D, cq)) return 0;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      const int R = D.R;
-      c->cq = cq; c->prio = D.wl_priority[wl]; c->ts = D.wl_ts[wl];
-      bool covers_pods = D.pods_res >= 0 && rg_by_resource(D, cq, D.pods_res) >= 0;
-      int nu = 0, nn = 0;
-      for (int row = D.wl_ps_start[wl]; row < D.wl_ps_start[wl + 1]; row++)
-        for (int r = 0; r < R; r++) {
-          int f = D.ps_flavor[(size_t)row * R + r];
-          if (f < 0) continue;
-          int fr = f * R + r;
-          if (D.ps_res_mode[(size_t)row * R + r] == KB_MODE_PREEMPT) {  // flavorResourcesNeedPreemption :480-490
-            int j = 0; while (j < nn && c->need_fr[j] != fr) j++;
-            if (j == nn && nn < KB_MAX_CELLS) c->need_fr[nn++] = fr;
-          }
-          i64 q = ps_request(D, row, r, D.ps_count_out[row], covers_pods);  // TotalRequestsFor flavorassigner.go:198-218
-          if (q == 0) continue;
-          int j = 0; while (j < nu && c->use_fr[j] != fr) j++;
-          if (j == nu) { if (nu == KB_MAX_CELLS) continue; c->use_fr[nu] = fr; c->use_q[nu] = 0; nu++; }
-          c->use_q[j] += q;
+    const int R = D.R;
+    c->cq = cq; c->prio = D.wl_priority[wl]; c->ts = D.wl_ts[wl];
+    bool covers_pods = D.pods_res >= 0 && rg_by_resource(D, cq, D.pods_res) >= 0;
+    int nu = 0, nn = 0;
+    for (int row = D.wl_ps_start[wl]; row < D.wl_ps_start[wl + 1]; row++)
+      for (int r = 0; r < R; r++) {
+        int f = D.ps_flavor[(size_t)row * R + r];
+        if (f < 0) continue;
+        int fr = f * R + r;
+        if (D.ps_res_mode[(size_t)row * R + r] == KB_MODE_PREEMPT) {  // flavorResourcesNeedPreemption :480-490
+          int j = 0; while (j < nn && c->need_fr[j] != fr) j++;
+          if (j == nn && nn < KB_MAX_CELLS) c->need_fr[nn++] = fr;
         }
-      c->n_use = nu; c->n_need = nn;
-    }
-    __syncthreads();
-    classical_search<kSmem>(D, *T, c, S);
+        i64 q = ps_request(D, row, r, D.ps_count_out[row], covers_pods);  // TotalRequestsFor flavorassigner.go:198-218
+        if (q == 0) continue;
+        int j = 0; while (j < nu && c->use_fr[j] != fr) j++;
+        if (j == nu) { if (nu == KB_MAX_CELLS) continue; c->use_fr[nu] = fr; c->use_q[nu] = 0; nu++; }
+        c->use_q[j] += q;
+      }
+    c->n_use = nu; c->n_need = nn;
+    run_search(D);
     return c->n_targets;
   }
 };
 
 template <bool kSmem>
-__global__ void __launch_bounds__(128) k_nominate_search(DevSnap D) {
+__global__ void __launch_bounds__(32) k_nominate_search(DevSnap D) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ PreCtx ctx;
-  __shared__ int s_item, s_res[2];
+  __shared__ int s_item;
   const int FR = D.FR;
   PreScratch S;
   {
@@ -502,6 +470,7 @@ __global__ void __launch_bounds__(128) k_nominate_search(DevSnap D) {
     S.tgt = D.sc_tgt + b * D.sc_adm_cap; S.tgt_reason = D.sc_tgt_reason + b * D.sc_adm_cap;
     S.cq_class = D.sc_cq_class + b * D.sc_node_cap; S.on_path = D.sc_on_path + b * D.sc_node_cap;
     S.cq_lca = D.sc_cq_lca + b * D.sc_node_cap;
+    S.aux1 = D.sc_aux1 + b * D.sc_adm_cap; S.aux2 = D.sc_aux2 + b * D.sc_adm_cap;
   }
   PTab<kSmem> T;
   T.D = &D; T.FR = FR;
@@ -538,11 +507,10 @@ __global__ void __launch_bounds__(128) k_nominate_search(DevSnap D) {
       }
       __syncthreads();
     }
-    NomSearch<kSmem> orc{&T, &ctx, S, s_res};
-    int borrowing, nt;
-    int mode = get_assignments(D, orc, wl, &borrowing, &nt);
-    __syncthreads();
     if (threadIdx.x == 0) {
+      NomSearch<kSmem> orc{&T, &ctx, S};
+      int borrowing, nt;
+      int mode = get_assignments(D, orc, wl, &borrowing, &nt);
       D.mode[e] = (uint8_t)mode;
       D.borrow[e] = borrowing;
       int off = 0;
@@ -556,6 +524,7 @@ __global__ void __launch_bounds__(128) k_nominate_search(DevSnap D) {
     }
   }
 }
+
 
 // ---------------------------------------------------------------------------
 // K3: group entries by root (counting sort: count in K2, scan, scatter)

@@ -7,12 +7,13 @@
 //
 // The search mutates the quota tree (remove candidate / fill back / restore), so every CTA
 // works on a PRIVATE copy of the preemptor's root tree: in shared memory when the tree fits,
-// else in a per-CTA global scratch.  Parallel parts (all threads of the CTA): classifying
-// the ClusterQueues of the tree against the preemptor (which subtree collected them, with or
-// without hierarchical advantage) and building the ordered candidate list by stable stream
-// compaction of the root's admitted workloads, which are pre-sorted once per cycle by the
-// preemptor-independent keys of CandidatesOrdering.  The greedy remove / fill-back walk is
-// inherently sequential and runs on thread 0.
+// else in a per-CTA global scratch.  One search is a data-dependent sequential walk (classify,
+// remove, re-check, fill back), so it runs on ONE thread; parallelism comes from running many
+// searches at once (one single-warp CTA each; the other lanes only stage the tree).  The
+// ordered candidate list is a filtered pass over the root's admitted workloads, which are
+// pre-sorted once per cycle by the preemptor-independent keys of CandidatesOrdering — no sort
+// per preemptor.  (A barrier-based master/worker split inside one warp is not expressible:
+// bar.sync is warp-aligned.)
 #pragma once
 
 #include "kb_device.cuh"
@@ -109,8 +110,6 @@ struct PreCtx {
   int plen; int path[KB_MAX_DEPTH + 1]; int adv_at[KB_MAX_DEPTH + 1];
   int seg_count[6];
   int n_all, n_targets;
-  int wsum[4];
-  int scan_base;
 };
 
 // per-CTA global scratch
@@ -122,6 +121,7 @@ struct PreScratch {
   int8_t *cq_class;  // per tree node (handle): 0 none, 1 hierarchy candidates, 2 priority candidates
   int8_t *on_path;   // per tree node (handle): level on the preemptor's path or -1
   int32_t *cq_lca;   // per tree node (handle): handle of the subtree root that collected it
+  int32_t *aux1, *aux2;  // [adm cap] fair sharing: next-in-queue links, retry candidates
 };
 
 __device__ __forceinline__ bool satisfies_policy(const DevSnap &D, const PreCtx &c, int a, int policy) {  // preemption_policy.go:30-48
@@ -178,23 +178,9 @@ __device__ inline bool workload_fits(const PTab<kSmem> &T, const PreCtx &c, int 
   return true;
 }
 
-// block-wide exclusive scan of one flag per thread (blockDim <= 128); returns the thread's
-// offset, *total = number of set flags.  All threads must call it.
-__device__ inline int block_flag_scan(PreCtx *c, bool flag, int *total) {
-  unsigned b = __ballot_sync(0xffffffffu, flag);
-  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  if (lane == 0) c->wsum[w] = __popc(b);
-  __syncthreads();
-  int base = 0, tot = 0;
-  for (int i = 0; i < (int)(blockDim.x >> 5); i++) { if (i < w) base += c->wsum[i]; tot += c->wsum[i]; }
-  __syncthreads();
-  *total = tot;
-  return base + __popc(b & ((1u << lane) - 1));
-}
-
-// classicalPreemptions preemption.go:238-293.  Called by ALL threads of the CTA with the
-// context filled in (cq, prio, ts, use_*, need_*).  On return c->n_targets / S.tgt hold
-// the targets (0 = none); the private tree is restored.
+// classicalPreemptions preemption.go:238-293.  Called by ONE thread with the context filled
+// in (cq, prio, ts, use_*, need_*).  On return c->n_targets / S.tgt hold the targets
+// (0 = none); the private tree is restored.
 template <bool kSmem>
 __device__ inline void classical_search(const DevSnap &D, const PTab<kSmem> &T, PreCtx *c, const PreScratch &S) {
   const int cq = c->cq;
@@ -203,7 +189,7 @@ __device__ inline void classical_search(const DevSnap &D, const PTab<kSmem> &T, 
   const bool cohort_cands = has_parent && D.cq_reclaim_within[cq] != KB_POLICY_NEVER;
   const bool own_cands = D.cq_within_cq[cq] != KB_POLICY_NEVER;
   // ---- 1. preemptor path and hierarchical advantage per level (collectCandidatesForHierarchicalReclaim :151-177)
-  if (threadIdx.x == 0) {
+  {
     int pl = 0;
     for (int t = hcq; t >= 0; t = T.parent(t)) c->path[pl++] = t;
     c->plen = pl;
@@ -226,12 +212,10 @@ __device__ inline void classical_search(const DevSnap &D, const PTab<kSmem> &T, 
     }
     c->n_targets = 0;
   }
-  for (int h = threadIdx.x; h < T.nn; h += blockDim.x) S.on_path[h] = -1;
-  __syncthreads();
-  for (int k = threadIdx.x; k < c->plen; k += blockDim.x) S.on_path[c->path[k]] = (int8_t)k;
-  __syncthreads();
+  for (int h = 0; h < T.nn; h++) S.on_path[h] = -1;
+  for (int k = 0; k < c->plen; k++) S.on_path[c->path[k]] = (int8_t)k;
   // ---- 2. which ClusterQueues are collected, and by which subtree (collectCandidatesInSubtree :181-199)
-  for (int h = threadIdx.x; h < T.nn; h += blockDim.x) {
+  for (int h = 0; h < T.nn; h++) {
     int cls = 0, lca = -1;
     if (cohort_cands && T.nodes[h] < D.Q && h != hcq && !within_nominal(T, *c, h)) {
       bool ok = true;
@@ -245,9 +229,8 @@ __device__ inline void classical_search(const DevSnap &D, const PTab<kSmem> &T, 
     S.cq_class[h] = (int8_t)cls;
     S.cq_lca[h] = lca;
   }
-  __syncthreads();
   // ---- 3. ordered candidate list: evicted{hier, prio, same} then non-evicted{hier, prio, same}
-  //         (NewCandidateIterator candidate_generator.go:77-121), by stable compaction of the
+  //         (NewCandidateIterator candidate_generator.go:77-121): six filtered passes over the
   //         root's admitted workloads pre-sorted by (evicted, priority asc, newer first, uid).
   int slot = D.root_slot[cq];
   int a0 = D.root_adm_start[slot], a1 = D.root_adm_start[slot + 1];
@@ -256,29 +239,23 @@ __device__ inline void classical_search(const DevSnap &D, const PTab<kSmem> &T, 
     int ev = seg < 3 ? 1 : 0, cls = seg % 3 + 1;
     int seg_n = 0;
     if ((cls == 3 && own_cands) || (cls != 3 && cohort_cands)) {
-      for (int base = a0; base < a1; base += blockDim.x) {
-        int i = base + threadIdx.x;
-        bool flag = false; int a = -1, v = PV_NEVER;
-        if (i < a1) {
-          a = D.adm_sorted[i];
-          if ((int)D.adm_evicted[a] == ev) {
-            int acq = D.adm_cq[a];
-            int acls = acq == cq ? 3 : S.cq_class[T.handle(acq)];
-            if (acls == cls) { v = classify_variant(D, *c, a, cls == 1); flag = v != PV_NEVER; }
-          }
-        }
-        int tot;
-        int pos = block_flag_scan(c, flag, &tot);
-        if (flag) { S.cand[nall + seg_n + pos] = a; S.variant[nall + seg_n + pos] = (uint8_t)v; }
-        seg_n += tot;
+      for (int i = a0; i < a1; i++) {
+        int a = D.adm_sorted[i];
+        int aev = D.adm_evicted[a];
+        if (aev != ev) { if (ev == 1) break; continue; }  // evicted workloads form the prefix of the segment
+        int acq = D.adm_cq[a];
+        int acls = acq == cq ? 3 : S.cq_class[T.handle(acq)];
+        if (acls != cls) continue;
+        int v = classify_variant(D, *c, a, cls == 1);
+        if (v == PV_NEVER) continue;
+        S.cand[nall + seg_n] = a; S.variant[nall + seg_n] = (uint8_t)v; seg_n++;
       }
     }
-    if (threadIdx.x == 0) c->seg_count[seg] = seg_n;
+    c->seg_count[seg] = seg_n;
     nall += seg_n;
   }
-  __syncthreads();
-  // ---- 4. greedy remove / fill back (thread 0)
-  if (threadIdx.x == 0) {
+  // ---- 4. greedy remove / fill back
+  {
     int n_hier = c->seg_count[0] + c->seg_count[3], n_prio = c->seg_count[1] + c->seg_count[4];
     bool no_other = n_hier == 0 && n_prio == 0, no_hier = n_hier == 0;
     bool forbidden = D.cq_borrow_within[cq] == KB_POLICY_NEVER;
@@ -321,5 +298,233 @@ __device__ inline void classical_search(const DevSnap &D, const PTab<kSmem> &T, 
     }
     c->n_targets = found ? nt : 0;
   }
-  __syncthreads();
+}
+
+// ---------------------------------------------------------------------------
+// Fair-sharing preemption (preemption.go:338-478, fairsharing/ordering.go:46-208,
+// fairsharing/target.go, least_common_ancestor.go, strategy.go).
+// ---------------------------------------------------------------------------
+// CandidatesOrdering common/ordering.go:41-100 (AdmissionFairSharing keys not modelled)
+__device__ inline int cand_ordering(const DevSnap &D, int a, int b, int cq) {
+  int ea = D.adm_evicted[a], eb = D.adm_evicted[b];
+  if (ea != eb) return ea ? -1 : 1;
+  bool ain = D.adm_cq[a] == cq, bin = D.adm_cq[b] == cq;
+  if (ain != bin) return bin ? -1 : 1;
+  int pa = D.adm_priority[a], pb = D.adm_priority[b];
+  if (pa != pb) return pa < pb ? -1 : 1;
+  i64 ta = D.adm_qr_ts[a] == INT64_MIN ? D.now_ns : D.adm_qr_ts[a], tb = D.adm_qr_ts[b] == INT64_MIN ? D.now_ns : D.adm_qr_ts[b];
+  if (ta != tb) return tb < ta ? -1 : 1;
+  i64 ua = D.adm_uid[a], ub = D.adm_uid[b];
+  if (ua != ub) return ua < ub ? -1 : 1;
+  return 0;
+}
+template <bool kSmem>
+__device__ inline DevDRS fair_drs(const DevSnap &D, const PTab<kSmem> &T, int h) {  // dominantResourceShare fair_sharing.go:126-156
+  int node = T.nodes[h];
+  DevDRS d{D.fair_weight[node], 0.0, -1, false};
+  int p = D.parent[node];
+  if (p < 0) return d;
+  const int R = D.R, F = D.F, FR = D.FR;
+  for (int r = 0; r < R; r++) {
+    i64 b = 0, lend = 0;
+    for (int f = 0; f < F; f++) {
+      int fr = f * R + r;
+      i64 over = T.U(h, fr) - T.Sub(h, fr);
+      if (over > 0) b += over;
+      lend += D.potential[(size_t)p * FR + fr];
+    }
+    if (b > 0) {
+      d.borrowing = true;
+      if (lend > 0) {
+        double ratio = (double)b * 1000.0 / (double)lend;
+        if (ratio > d.ratio) { d.ratio = ratio; d.res = r; }
+      }
+    }
+  }
+  return d;
+}
+
+// fairPreemptions preemption.go:433-478.  Called by ONE thread.
+template <bool kSmem>
+__device__ inline void fair_search(const DevSnap &D, const PTab<kSmem> &T, PreCtx *c, const PreScratch &S) {
+  const int cq = c->cq;
+  const int hcq = T.handle(cq);
+  const bool has_parent = D.parent[cq] >= 0;
+  const bool cohort_cands = has_parent && D.cq_reclaim_within[cq] != KB_POLICY_NEVER;
+  const bool own_cands = D.cq_within_cq[cq] != KB_POLICY_NEVER;
+  {
+    int pl = 0;
+    for (int t = hcq; t >= 0; t = T.parent(t)) c->path[pl++] = t;
+    c->plen = pl;
+    c->n_targets = 0;
+  }
+  for (int h = 0; h < T.nn; h++) { S.on_path[h] = -1; S.cq_class[h] = 0; S.cq_lca[h] = -1; }
+  for (int k = 1; k < c->plen; k++) S.on_path[c->path[k]] = (int8_t)k;  // preemptorAncestors
+  // ---- findCandidates :514-533, sorted by CandidatesOrdering: evicted first, other CQs before the preemptor's
+  int slot = D.root_slot[cq];
+  int a0 = D.root_adm_start[slot], a1 = D.root_adm_start[slot + 1];
+  int nall = 0;
+  for (int seg = 0; seg < 4; seg++) {
+    int ev = seg < 2 ? 1 : 0; bool own = seg & 1;
+    if (!(own ? own_cands : cohort_cands)) continue;
+    for (int i = a0; i < a1; i++) {
+      int a = D.adm_sorted[i];
+      int aev = D.adm_evicted[a];
+      if (aev != ev) { if (ev == 1) break; continue; }
+      int acq = D.adm_cq[a];
+      if ((acq == cq) != own) continue;
+      int policy = own ? D.cq_within_cq[cq] : D.cq_reclaim_within[cq];
+      if (!satisfies_policy(D, *c, a, policy) || !uses_resources(D, *c, a)) continue;
+      if (!own) {  // cqIsBorrowing :535-545
+        int h = T.handle(acq);
+        bool borrowing = false;
+        for (int j = 0; j < c->n_need; j++) if (T.borrowing_with(h, c->need_fr[j], 0)) borrowing = true;
+        if (!borrowing) continue;
+      }
+      S.cand[nall++] = a;
+    }
+  }
+  if (nall == 0) { c->n_targets = 0; return; }
+  int32_t *head = S.cq_lca;   // per node: index (into the current candidate list) of the queue head, or -1
+  int32_t *next = S.aux1;
+  int8_t *pruned = S.cq_class;
+  auto build_queues = [&](const int32_t *list, int n) {  // MakeClusterQueueOrdering ordering.go:62-83
+    for (int h = 0; h < T.nn; h++) { head[h] = -1; pruned[h] = 0; }
+    for (int i = n - 1; i >= 0; i--) { int h = T.handle(D.adm_cq[list[i]]); next[i] = head[h]; head[h] = i; }
+  };
+  auto usage_add = [&](bool add) {  // SimulateUsageAddition / Removal of the incoming workload
+    for (int j = 0; j < c->n_use; j++) { if (add) T.add(hcq, c->use_fr[j], c->use_q[j]); else T.remove(hcq, c->use_fr[j], c->use_q[j]); }
+  };
+  auto fits_fs = [&]() {  // workloadFitsForFairSharing :567-572
+    usage_add(false);
+    bool r = workload_fits(T, *c, hcq, true);
+    usage_add(true);
+    return r;
+  };
+  const int32_t *list = S.cand;
+  auto next_target = [&](int root) -> int {  // nextTarget ordering.go:141-208 (tail recursion unrolled)
+    int cohort = root;
+    for (int guard = 0;; guard++) {
+      if (guard > T.nn + 2) { atomicOr(D.status, KBS_INTERNAL_LOOP); pruned[root] = 1; return -1; }
+      int cnode = T.nodes[cohort];
+      int highest_cq = -1; DevDRS hcq_drs{1.0, -1.0, -1, false};
+      int highest_co = -1; DevDRS hco_drs{1.0, -1.0, -1, false};
+      for (int k = D.child_start[cnode]; k < D.child_start[cnode + 1]; k++) {
+        int ch = D.child_list[k];
+        if (ch >= D.Q) continue;
+        int h = T.handle(ch);
+        if (pruned[h]) continue;
+        DevDRS drs = fair_drs(D, T, h);
+        if ((!drs.borrowing && h != hcq) || head[h] < 0) pruned[h] = 1;
+        else {
+          int cmp = drs_compare(drs, hcq_drs);
+          if (cmp == 0) {
+            if (cand_ordering(D, list[head[h]], list[head[highest_cq]], cq) < 0) highest_cq = h;
+          } else if (cmp == 1) { hcq_drs = drs; highest_cq = h; }
+        }
+      }
+      for (int k = D.child_start[cnode]; k < D.child_start[cnode + 1]; k++) {
+        int ch = D.child_list[k];
+        if (ch < D.Q) continue;
+        int h = T.handle(ch);
+        if (pruned[h]) continue;
+        DevDRS drs = fair_drs(D, T, h);
+        if (!drs.borrowing && S.on_path[h] < 0) pruned[h] = 1;
+        else if (drs_compare(drs, hco_drs) >= 0) { hco_drs = drs; highest_co = h; }
+      }
+      if (highest_co < 0 && highest_cq < 0) { pruned[cohort] = 1; return -1; }
+      if (drs_compare(hco_drs, hcq_drs) >= 0) { cohort = highest_co; continue; }
+      return highest_cq;
+    }
+  };
+  auto almost_lcas = [&](int htarget, int *pre_al, int *tgt_al) {  // least_common_ancestor.go:27-58
+    int lca = -1;
+    for (int t = T.parent(htarget); t >= 0; t = T.parent(t)) if (S.on_path[t] >= 0) { lca = t; break; }
+    auto al = [&](int h) { int a = h; for (int t = T.parent(h); t >= 0; t = T.parent(t)) { if (t == lca) return a; a = t; } return a; };
+    *pre_al = al(hcq); *tgt_al = al(htarget);
+  };
+  // parseStrategies :319-333
+  bool s2a = D.flags & KB_F_FS_STRATEGY_S2A, s2b = D.flags & KB_F_FS_STRATEGY_S2B;
+  int strat[2], nstrat;
+  if (!s2a && !s2b) { strat[0] = 0; strat[1] = 1; nstrat = 2; }
+  else if (s2a && s2b) { if (D.flags & KB_F_FS_STRATEGY_S2B_FIRST) { strat[0] = 1; strat[1] = 0; } else { strat[0] = 0; strat[1] = 1; } nstrat = 2; }
+  else { strat[0] = s2a ? 0 : 1; nstrat = 1; }
+
+  usage_add(true);  // :446 DRS values must include the incoming workload
+  int nt = 0, nretry = 0;
+  int32_t *retry = S.aux2;
+  bool fits = false;
+  {  // runFirstFsStrategy :338-403
+    build_queues(S.cand, nall);
+    bool within_nominal = false;
+    if (D.flags & KB_F_FS_PREEMPT_WITHIN_NOMINAL) {  // queueWithinNominalInResourcesNeedingPreemption :591-598
+      within_nominal = true;
+      for (int j = 0; j < c->n_need; j++) if (T.borrowing_with(hcq, c->need_fr[j], 0)) within_nominal = false;
+    }
+    auto pop = [&](int h) { int i = head[h]; head[h] = next[i]; return list[i]; };
+    auto take = [&](int a, int reason) { T.remove_adm(a); S.tgt[nt] = a; S.tgt_reason[nt] = (uint8_t)reason; nt++; };
+    auto step = [&](int h) -> bool {
+      if (h == hcq) { take(pop(h), KB_REASON_IN_CLUSTER_QUEUE); return fits_fs(); }
+      if (within_nominal) { take(pop(h), KB_REASON_IN_COHORT_RECLAMATION); return fits_fs(); }
+      int pa, ta; almost_lcas(h, &pa, &ta);
+      DevDRS pre_new = fair_drs(D, T, pa), tgt_old = fair_drs(D, T, ta);  // ComputeShares target.go:53-56
+      while (head[h] >= 0) {
+        int a = pop(h);
+        T.remove_adm(a);  // ComputeTargetShareAfterRemoval :66-73
+        int p2, t2; almost_lcas(h, &p2, &t2);
+        DevDRS tgt_new = fair_drs(D, T, t2);
+        T.add_adm(a);
+        bool ok = strat[0] == 0 ? drs_compare(pre_new, tgt_new) <= 0 : drs_compare(pre_new, tgt_old) < 0;  // strategy.go:41-48
+        if (ok) { take(a, KB_REASON_IN_COHORT_FAIR_SHARING); if (fits_fs()) return true; break; }
+        retry[nretry++] = a;
+      }
+      return false;
+    };
+    if (!has_parent) {
+      while (head[hcq] >= 0) if (step(hcq)) { fits = true; break; }
+    } else {
+      int root = c->path[c->plen - 1];
+      for (int guard = 0; !pruned[root]; guard++) {
+        if (guard > 4 * (T.nn + nall) + 64) { atomicOr(D.status, KBS_INTERNAL_LOOP); break; }
+        int h = next_target(root);
+        if (h < 0) continue;
+        if (step(h)) { fits = true; break; }
+      }
+    }
+  }
+  if (!fits && nstrat > 1 && has_parent) {  // runSecondFsStrategy :407-431
+    list = retry;
+    build_queues(retry, nretry);
+    int root = c->path[c->plen - 1];
+    for (int guard = 0; !pruned[root]; guard++) {
+      if (guard > 4 * (T.nn + nall) + 64) { atomicOr(D.status, KBS_INTERNAL_LOOP); break; }
+      int h = next_target(root);
+      if (h < 0) continue;
+      int pa, ta; almost_lcas(h, &pa, &ta);
+      DevDRS pre_new = fair_drs(D, T, pa), tgt_old = fair_drs(D, T, ta);
+      if (drs_compare(pre_new, tgt_old) < 0) {
+        int i = head[h]; head[h] = next[i];
+        int a = retry[i];
+        T.remove_adm(a); S.tgt[nt] = a; S.tgt_reason[nt] = KB_REASON_IN_COHORT_FAIR_SHARING; nt++;
+        if (fits_fs()) { fits = true; break; }
+      }
+      pruned[h] = 1;  // DropQueue
+    }
+  }
+  usage_add(false);  // revertSimulation :459
+  if (fits) {
+    for (int k = nt - 2; k >= 0; k--) {  // fillBackWorkloads(allowBorrowing = true) :469
+      T.add_adm(S.tgt[k]);
+      if (workload_fits(T, *c, hcq, true)) { S.tgt[k] = S.tgt[nt - 1]; S.tgt_reason[k] = S.tgt_reason[nt - 1]; nt--; }
+      else T.remove_adm(S.tgt[k]);
+    }
+  }
+  for (int k = 0; k < nt; k++) T.add_adm(S.tgt[k]);  // restoreSnapshot
+  c->n_targets = fits ? nt : 0;
+}
+
+template <bool kSmem>
+__device__ __forceinline__ void target_search(const DevSnap &D, const PTab<kSmem> &T, PreCtx *c, const PreScratch &S) {
+  if (D.flags & KB_F_FAIR_SHARING) fair_search<kSmem>(D, T, c, S);  // getTargets preemption.go:148-153
+  else classical_search<kSmem>(D, T, c, S);
 }

@@ -110,6 +110,40 @@ def test_partial_admission_matches_oracle(ev, make):
     assert_cycle_equal(got, want)
 
 
+def _fair_golden_cases():
+    import json, os
+    from tests.test_oracle_golden_preemption2 import fair_flags
+    here = os.path.dirname(__file__)
+    out = []
+    for name, tc in json.load(open(os.path.join(here, "golden", "preemption_fair_cases.json"))).items():
+        out.append(pytest.param((tc, fair_flags(tc)), id=f"fair:{name[:60]}"))
+    return out
+
+
+@pytest.mark.parametrize("tcf", _fair_golden_cases())
+def test_reference_fair_preemption_scenarios_cycle(ev, tcf):
+    """TestFairPreemptions scenarios (preemption_fair_test.go:46) as one fair-sharing cycle: device vs oracle."""
+    from tests.golden_loader import build_preemption_case
+    tc, flags = tcf
+    snap, idx = build_preemption_case(tc, flags)
+    got, want = ev.run_cycle(snap), oracle.run_cycle(snap)
+    assert_cycle_equal(got, want)
+
+
+@pytest.mark.parametrize("make", [
+    lambda: synth.make_snapshot(3, W=3000, Q=300, preemption=True, heads="one_per_cq", tight=1.1),
+    lambda: synth.make_snapshot(3, W=3000, Q=300, preemption=True, heads="one_per_cq", tight=1.05, seed=11, podsets_max=2),
+    lambda: _fair(synth.make_snapshot(4, W=4000, Q=200, heads="one_per_cq", tight=1.1)),
+    lambda: _fair(synth.make_snapshot(4, W=40000, Q=2000, heads="one_per_cq")),
+])
+def test_fair_preemption_cycle_matches_oracle(ev, make):
+    snap = make()
+    cap = 40 * snap.n_adm + 10000
+    got, want = ev.run_cycle(snap, abi.CycleOut(snap, cap)), oracle.run_cycle(snap, cap)
+    assert want.n_targets > 0
+    assert_cycle_equal(got, want)
+
+
 def _golden_cases():
     import json, os
     here = os.path.dirname(__file__)
