@@ -135,15 +135,45 @@ class MakeCohort(_QuotaHolder):
     def Obj(self): return self
 
 
+class MakeResourceFlavor:
+    """kueue.ResourceFlavor: node labels, taints and tolerations (wrappers.go MakeResourceFlavor)."""
+
+    def __init__(self, name: str):
+        self.name = name
+        self.node_labels: Dict[str, str] = {}
+        self.taints: List[dict] = []
+        self.tolerations: List[dict] = []
+
+    def NodeLabel(self, k: str, v: str): self.node_labels[k] = v; return self
+    def Taint(self, **t): self.taints.append(t); return self
+    def Toleration(self, **t): self.tolerations.append(t); return self
+    def Obj(self): return self
+
+    def spec(self) -> dict:
+        return {"nodeLabels": self.node_labels, "taints": self.taints, "tolerations": self.tolerations}
+
+
 class MakePodSet:
     def __init__(self, name: str = "main", count: int = 1):
         self.name = name
         self.count = count
         self.min_count: Optional[int] = None
         self.requests: Dict[str, str] = {}   # PER-POD requests, like PodSpec containers
-        self.flavor_ok: Optional[Sequence[str]] = None  # flavors passing taints/affinity; None = all
+        self.flavor_ok: Optional[Sequence[str]] = None  # flavors passing taints/affinity; None = derive / all
+        self.tolerations: List[dict] = []
+        self.node_selector: Optional[Dict[str, str]] = None
+        self.affinity_terms: Optional[List[dict]] = None
 
     def Request(self, res: str, q): self.requests[res] = q; return self
+    def Toleration(self, **t): self.tolerations.append(t); return self
+    def NodeSelector(self, kv: Dict[str, str]): self.node_selector = dict(kv); return self
+
+    def RequiredDuringSchedulingIgnoredDuringExecution(self, terms: List[dict]):
+        self.affinity_terms = (self.affinity_terms or []) + list(terms)
+        return self
+
+    def spec(self) -> dict:
+        return {"tolerations": self.tolerations, "nodeSelector": self.node_selector, "affinityTerms": self.affinity_terms}
     def SetMinimumCount(self, m: int): self.min_count = m; return self
     def EligibleFlavors(self, *flavors: str): self.flavor_ok = list(flavors); return self
     def Obj(self): return self
@@ -230,7 +260,8 @@ def flatten(cqs: Sequence[MakeClusterQueue], cohorts: Sequence[MakeCohort] = (),
             pending: Sequence[MakeWorkload] = (), admitted: Sequence[MakeWorkload] = (),
             usage: Optional[Dict[str, Dict[tuple, int]]] = None, flags: int = abi.FLAGS_DEFAULT,
             heads: Optional[Sequence[str]] = None, now_ns: int = 0,
-            flavors: Optional[Sequence[str]] = None, extra_resources: Sequence[str] = ()):
+            flavors: Optional[Sequence[str]] = None, extra_resources: Sequence[str] = (),
+            resource_flavors: Optional[Sequence["MakeResourceFlavor"]] = None):
     """Build (FlatSnapshot, Index).
 
     `usage` optionally overrides ClusterQueue usage as {cq: {(flavor, resource): int64}}
@@ -361,6 +392,20 @@ def flatten(cqs: Sequence[MakeClusterQueue], cohorts: Sequence[MakeCohort] = (),
                 ok = 0
                 for f in ps.flavor_ok:
                     ok |= 1 << fl.index(f)
+            elif resource_flavors is not None:
+                # checkFlavorForPodSets (flavorassigner.go:899-944) evaluated on the host per (podset, flavor)
+                from .eligibility import flavor_eligible
+                rf = {f.name: f for f in resource_flavors}
+                ok = 0
+                cq_obj = cqs[idx.cqs.index(w.cq)]
+                for rg in cq_obj.resource_groups:
+                    keys = set()
+                    for fq in rg:
+                        if fq.name in rf:
+                            keys.update(rf[fq.name].node_labels.keys())  # ResourceGroup.LabelKeys resource.go:31-38
+                    for fq in rg:
+                        if fq.name in rf and flavor_eligible(ps.spec(), rf[fq.name].spec(), keys):
+                            ok |= 1 << fl.index(fq.name)
             p_ok.append(ok)
             lt = np.full(R, -1, np.int8)
             if w.last_tried is not None and pi < len(w.last_tried):

@@ -68,3 +68,20 @@ def get_targets(snap, wl, ps_flavor, ps_res_mode, ps_count=None, cap=4096):
                              None if cnt is None else cnt.ctypes.data_as(C.POINTER(C.c_int32)),
                              adm.ctypes.data_as(C.POINTER(C.c_int32)), reason.ctypes.data_as(C.POINTER(C.c_uint8)), C.c_int32(cap))
     return [(int(adm[i]), int(reason[i])) for i in range(n)]
+
+
+def assign_stub(snap, wl, stub_mode=None, stub_borrow=None):
+    """FlavorAssigner.Assign with the reference's testOracle stub; returns a dict."""
+    import numpy as np
+    s = snap.as_struct()
+    R, FR = snap.n_resource, snap.n_fr
+    np_ = int(snap.wl_ps_start[wl + 1] - snap.wl_ps_start[wl])
+    sm = np.full(FR, -1, np.int8) if stub_mode is None else np.ascontiguousarray(stub_mode, np.int8)
+    sb = np.zeros(FR, np.int32) if stub_borrow is None else np.ascontiguousarray(stub_borrow, np.int32)
+    fl = np.full((np_, R), -1, np.int8); md = np.full((np_, R), -1, np.int8); tr = np.full((np_, R), -1, np.int8)
+    bor = C.c_int32(0); use = np.zeros(FR, np.int64)
+    P8, P32, P64 = C.POINTER(C.c_int8), C.POINTER(C.c_int32), C.POINTER(C.c_int64)
+    lib().ko_assign_stub.restype = C.c_int32
+    mode = lib().ko_assign_stub(C.byref(s), C.c_int32(wl), sm.ctypes.data_as(P8), sb.ctypes.data_as(P32), fl.ctypes.data_as(P8),
+                                md.ctypes.data_as(P8), tr.ctypes.data_as(P8), C.byref(bor), use.ctypes.data_as(P64))
+    return {"mode": mode, "flavor": fl, "res_mode": md, "tried": tr, "borrowing": bor.value, "usage": use}

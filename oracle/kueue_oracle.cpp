@@ -141,6 +141,9 @@ class Oracle {
   std::vector<int> height;
   std::vector<std::vector<int>> cqAdm;  // ClusterQueueSnapshot.Workloads
   bool fair;
+  const int8_t *stubMode = nullptr;   // testOracle (flavorassigner_test.go:145-158): per-FR stub result
+  const int32_t *stubBorrow = nullptr;
+  bool useStub = false;
 
   explicit Oracle(const kb_snapshot &snap) : s(snap) {
     Q = s.n_cq; C = s.n_cohort; N = Q + C; F = s.n_flavor; R = s.n_resource; FR = F * R;
@@ -668,6 +671,10 @@ class Oracle {
   }
   // preemption_oracle.go:41-71
   std::pair<int, int> simulatePreemption(const Preemptor &p, int fr, i64 quantity) {
+    if (useStub) {  // testOracle.SimulatePreemption: table lookup, default (Preempt, 0)
+      if (stubMode && stubMode[fr] >= 0) return {stubMode[fr], stubBorrow[fr]};
+      return {P_PREEMPT, 0};
+    }
     PCtx c; c.p = p; c.frsNeed = {fr}; c.workloadUsage.add(fr, quantity);
     std::vector<Target> cand = getTargets(c);
     if (cand.empty()) return {P_NOCAND, 0};
@@ -1089,6 +1096,28 @@ int32_t ko_run_cycle(const kb_snapshot *s, kb_cycle_out *out) {
   Oracle o(*s);
   o.schedule(out);
   return out->n_targets > out->tgt_capacity ? KB_ERR_CAPACITY : 0;
+}
+
+// flavorassigner.Assign(nil) for workload `wl` with the reference's stub preemption oracle
+// (TestAssignFlavors flavorassigner_test.go:165): stub_mode[fr] in {1 NoCandidates, 2 Preempt,
+// 3 Reclaim} or -1 for the default (Preempt, 0).  Outputs like one entry of ko_run_cycle.
+int32_t ko_assign_stub(const kb_snapshot *s, int32_t wl, const int8_t *stub_mode, const int32_t *stub_borrow,
+                       int8_t *ps_flavor, int8_t *ps_res_mode, int8_t *ps_tried, int32_t *borrowing, int64_t *usage_fr) {
+  Oracle o(*s);
+  o.useStub = true; o.stubMode = stub_mode; o.stubBorrow = stub_borrow;
+  Assignment a = o.assign(wl, nullptr);
+  int np = s->wl_ps_start[wl + 1] - s->wl_ps_start[wl];
+  for (int k = 0; k < np; k++)
+    for (int r = 0; r < o.R; r++) {
+      bool have = k < (int)a.ps.size() && a.ps[k].flavor[r] >= 0;
+      ps_flavor[(size_t)k * o.R + r] = have ? a.ps[k].flavor[r] : (int8_t)-1;
+      ps_res_mode[(size_t)k * o.R + r] = have ? a.ps[k].mode[r] : (int8_t)-1;
+      ps_tried[(size_t)k * o.R + r] = have ? a.ps[k].tried[r] : (int8_t)-1;
+    }
+  *borrowing = a.borrowing;
+  for (int fr = 0; fr < o.FR; fr++) usage_fr[fr] = -1;
+  for (auto &p : a.usage.v) usage_fr[p.first] = p.second;
+  return a.repMode();
 }
 
 // Single preemption query (TestPreemption-style goldens): targets for workload

@@ -144,6 +144,22 @@ def test_fair_preemption_cycle_matches_oracle(ev, make):
     assert_cycle_equal(got, want)
 
 
+def _assign_golden_cases():
+    import json, os
+    d = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "assign_flavors_cases.json")))
+    return [pytest.param(tc, id=f"assign:{name[:60]}") for name, tc in d["cases"].items()]
+
+
+@pytest.mark.parametrize("tc", _assign_golden_cases())
+def test_reference_assign_flavors_scenarios_cycle(ev, tc):
+    """TestAssignFlavors snapshots (flavorassigner_test.go:165) as one cycle: device vs oracle (both with the real
+    preemption search instead of the test's stub)."""
+    from tests.test_oracle_golden_assign import build
+    snap, idx = build(tc)
+    got, want = ev.run_cycle(snap), oracle.run_cycle(snap)
+    assert_cycle_equal(got, want)
+
+
 def _golden_cases():
     import json, os
     here = os.path.dirname(__file__)

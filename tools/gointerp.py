@@ -11,6 +11,7 @@ CONST = {
     "corev1.ResourceCPU": "cpu", "corev1.ResourceMemory": "memory", "corev1.ResourcePods": "pods",
     "corev1.ResourceEphemeralStorage": "ephemeral-storage",
     "kueue.DefaultPodSetName": "main",
+    "utiltesting.Ki": 2**10, "utiltesting.Mi": 2**20, "utiltesting.Gi": 2**30, "utiltesting.Ti": 2**40,
     "metav1.ConditionTrue": "True", "metav1.ConditionFalse": "False",
 }
 IGNORED = set()
@@ -32,6 +33,27 @@ def strip(v):
     if isinstance(v, (list, tuple)):
         return [strip(x) for x in v]
     return v
+
+
+def _symtail(v):
+    if isinstance(v, tuple) and v and v[0] == "sym":
+        v = v[1].split(".")[-1]
+        for pre in ("TaintEffect", "TolerationOp", "NodeSelectorOp"):
+            if v.startswith(pre):
+                return v[len(pre):]
+    return v
+
+
+def _k8s(d):
+    """corev1.Taint / corev1.Toleration literal -> lower-case keyed dict with plain strings."""
+    return {k[0].lower() + k[1:]: _symtail(v) for k, v in d.items() if not str(k).startswith("_")}
+
+
+def _term(t):
+    exprs = []
+    for e in t.get("MatchExpressions") or []:
+        exprs.append({"key": e.get("Key"), "operator": _symtail(e.get("Operator")), "values": list(e.get("Values") or [])})
+    return {"matchExpressions": exprs}
 
 
 class Interp:
@@ -144,6 +166,9 @@ class Interp:
                 return vals[0] if len(vals) == 1 else vals
             if q == "sets.New":
                 return [self.ev(a) for a in args]
+            if q == "utiltesting.SingleContainerForRequest":
+                m = self.ev(args[0])
+                return [{"_container": True, "requests": {k2: v2 for k2, v2 in m.items() if not str(k2).startswith("_")}}]
         if fn[0] == "sel" and not (q and q in CONST):
             base = self.ev(fn[1])
             if isinstance(base, Obj):
@@ -177,13 +202,13 @@ class Interp:
                        podsets=[{"name": "main", "count": 1, "minCount": None, "requests": {}}], admission=None,
                        reservedAt=None, conditions=[], queue=None)
         if short == "MakePodSet":
-            return Obj("PodSet", name=a[0], count=a[1], minCount=None, requests={})
+            return Obj("PodSet", name=a[0], count=a[1], minCount=None, requests={}, tolerations=[], nodeSelector=None, affinityTerms=None)
         if short == "MakeAdmission":
             return Obj("Admission", cq=a[0], podsets=[{"name": nm, "count": 1, "assignments": {}} for nm in (a[1:] or ["main"])])
         if short == "MakePodSetAssignment":
             return Obj("PodSetAssignment", name=a[0], count=1, assignments={})
         if short == "MakeResourceFlavor":
-            return Obj("ResourceFlavor", name=a[0])
+            return Obj("ResourceFlavor", name=a[0], nodeLabels={}, taints=[], tolerations=[])
         return Obj(short, args=a)
 
     def method(self, o, m, a):
@@ -240,6 +265,18 @@ class Interp:
         if k == "PodSet":
             if m == "Request": o["requests"][a[0]] = a[1]; return o
             if m == "SetMinimumCount": o["minCount"] = a[0]; return o
+            if m == "Containers":
+                cs = [c for x in a for c in (x if isinstance(x, list) else [x])]
+                o["requests"] = dict(cs[0]["requests"]) if cs else {}
+                return o
+            if m == "Toleration": o["tolerations"].append(_k8s(a[0])); return o
+            if m == "NodeSelector": o["nodeSelector"] = {k2: v2 for k2, v2 in a[0].items() if not str(k2).startswith("_")}; return o
+            if m == "RequiredDuringSchedulingIgnoredDuringExecution":
+                o["affinityTerms"] = (o["affinityTerms"] or []) + [_term(t) for t in a[0]]; return o
+        if k == "ResourceFlavor":
+            if m == "NodeLabel": o["nodeLabels"][a[0]] = a[1]; return o
+            if m == "Taint": o["taints"].append(_k8s(a[0])); return o
+            if m == "Toleration": o["tolerations"].append(_k8s(a[0])); return o
         if k == "Admission":
             if m == "PodSets": o["podsets"] = [strip(x) for x in a]; return o
             if m == "Assignment": o["podsets"][0]["assignments"][a[0]] = [a[1], a[2]]; return o

@@ -179,3 +179,98 @@ if __name__ == "__main__":
     c = preemption_cases("pkg/scheduler/preemption/preemption_fair_test.go", "TestFairPreemptions", fair=True)
     json.dump(c, open(os.path.join(dst, "preemption_fair_cases.json"), "w"), indent=1, default=str)
     print("TestFairPreemptions:", len(c), "cases; ignored:", sorted(gointerp.IGNORED))
+
+
+# ---------------------------------------------------------------------------
+# TestAssignFlavors  pkg/scheduler/flavorassigner/flavorassigner_test.go:165
+# ---------------------------------------------------------------------------
+PP = {"preemptioncommon.NoCandidates": 1, "preemptioncommon.Preempt": 2, "preemptioncommon.Reclaim": 3}
+AMODE = {"NoFit": 0, "Preempt": 1, "Fit": 2}
+
+
+def _frq(d):
+    out = []
+    for k, v in (d or {}).items():
+        if str(k).startswith("_"):
+            continue
+        kk = dict(k)
+        out.append([kk.get("Flavor"), kk.get("Resource"), v])
+    return out
+
+
+def norm_podset(o):
+    return {"name": o["name"], "count": o["count"], "minCount": o.get("minCount"), "requests": o["requests"],
+            "tolerations": o.get("tolerations") or [], "nodeSelector": o.get("nodeSelector"), "affinityTerms": o.get("affinityTerms")}
+
+
+def assign_cases():
+    path = "pkg/scheduler/flavorassigner/flavorassigner_test.go"
+    interp, cases, lines = eval_function_tables(path, "TestAssignFlavors", extra_env={"Fit": ("sym", "Fit"), "Preempt": ("sym", "Preempt"), "NoFit": ("sym", "NoFit")})
+    flavors = {k: gointerp.strip(v) for k, v in interp.env["resourceFlavors"].items() if not str(k).startswith("_")}
+    out, skipped = {}, {}
+    src = open(REF + path).read()
+    lit_text = {}
+    ks = sorted((ln, k) for k, ln in lines.items())
+    src_lines = src.split("\n")
+    for i, (ln, k) in enumerate(ks):
+        end = ks[i + 1][0] if i + 1 < len(ks) else ln + 400
+        lit_text[k] = "\n".join(src_lines[ln - 1:end - 1])
+    for key, v in cases:
+        tc = interp.ev(v)
+        if tc.get("elasticJobsViaWorkloadSlicesEnabled") or tc.get("preemptWorkloadSlice") or tc.get("wlReclaimablePods"):
+            skipped[key] = "workload slices / reclaimable pods (out of scope)"
+            continue
+        if tc.get("featureGates"):
+            skipped[key] = "non-default feature gates"
+            continue
+        wa = tc.get("wantAssignment") or {}
+        want_ps = []
+        tas = False
+        for ps in wa.get("PodSets", []) or []:
+            fl = {}
+            for res, fa in (ps.get("Flavors") or {}).items():
+                if str(res).startswith("_"):
+                    continue
+                fl[res] = {"name": fa.get("Name"), "mode": AMODE.get(sym(fa.get("Mode")), 0), "tried": fa.get("TriedFlavorIdx", 0)}
+            if ps.get("TopologyAssignment") or ps.get("DelayedTopologyRequest"):
+                tas = True
+            want_ps.append({"name": ps.get("Name"), "count": ps.get("Count"), "flavors": fl})
+        if tas:
+            skipped[key] = "TAS"
+            continue
+        if "PodSetGroup(" in lit_text.get(key, ""):
+            skipped[key] = "TAS podset groups"
+            continue
+        sim = []
+        for k, r in (tc.get("simulationResult") or {}).items():
+            if str(k).startswith("_"):
+                continue
+            kk = dict(k)
+            if isinstance(r, list):
+                pp, ba = r[0], (r[1] if len(r) > 1 else 0)
+            else:
+                pp, ba = r.get("preemptionPossiblity"), r.get("borrowingAfterSimulation", 0)
+            sim.append([kk.get("Flavor"), kk.get("Resource"), PP[sym(pp)], ba])
+        cq = tc["clusterQueue"]
+        case = {
+            "source": f"{path}:{lines.get(key, 0)}",
+            "wlPods": [norm_podset(p) for p in tc.get("wlPods") or []],
+            "clusterQueue": norm_cq(cq),
+            "clusterQueueUsage": _frq(tc.get("clusterQueueUsage")),
+            "secondaryClusterQueue": norm_cq(tc["secondaryClusterQueue"]) if tc.get("secondaryClusterQueue") else None,
+            "secondaryClusterQueueUsage": _frq(tc.get("secondaryClusterQueueUsage")),
+            "enableFairSharing": bool(tc.get("enableFairSharing")),
+            "simulationResult": sim,
+            "wantRepMode": AMODE[sym(tc.get("wantRepMode"))] if tc.get("wantRepMode") is not None else 0,
+            "wantPodSets": want_ps,
+            "wantUsage": _frq(((wa.get("Usage") or {}).get("Quota")) or {}),
+            "wantBorrowing": wa.get("Borrowing", 0),
+        }
+        out[key] = gointerp.strip(case)
+    return out, skipped, flavors
+
+
+if __name__ == "__main__":
+    c, skipped, flavors = assign_cases()
+    json.dump({"resourceFlavors": flavors, "cases": c, "skipped": skipped}, open(os.path.join(dst, "assign_flavors_cases.json"), "w"), indent=1, default=str)
+    print("TestAssignFlavors:", len(c), "cases transcribed,", len(skipped), "skipped; ignored:", sorted(gointerp.IGNORED))
