@@ -268,6 +268,13 @@ static int32_t build_topology(kb_handle *h, const kb_snapshot *s) {
       seen[c] = 1;
     }
   }
+  // warp-per-root admit for cohort-less CQs: only when none of them can ever get preemption targets
+  {
+    bool any = false;
+    for (int q = 0; q < Q && !any; q++)
+      if (s->parent[q] < 0 && s->cq_within_cq[q] != KB_POLICY_NEVER && h->cq_adm_start[q + 1] > h->cq_adm_start[q]) any = true;
+    h->D.lone_fast = !any && s->n_flavor * s->n_resource <= 64;
+  }
   h->D.nTrees = ntrees;
   h->D.nLone = (int)h->lone.size();
   h->D.nRoots = nroots;
@@ -328,7 +335,7 @@ extern "C" int32_t kb_upload(kb_handle *h, const kb_snapshot *s) {
   need(G * acap, 4); need(G * acap, 4); need(G * acap, 4); need(G * acap, 4); need(G * ncap, 4); need(G * acap, 1); need(G * acap, 1); need(G * ncap, 1); need(G * ncap, 1);
   if (!h->search_smem) need(G * ncap * FR, 8);
   bool fair = (s->flags & KB_F_FAIR_SHARING) != 0;
-  if (fair) { need(H * FR, 8); need(H * KB_MAX_DEPTH, 16); need(N, 4); need(N, 4); }
+  if (fair) { need(H * FR, 8); need(H * (48 + 16 * KB_MAX_DEPTH), 1); need(N, 4); need(N, 4); }
   if (!h->arena.reserve(tot + 4096)) return fail(h, KB_ERR_CUDA, "cudaMalloc failed");
   h->arena.reset();
   int64_t bytes = 0;
@@ -380,7 +387,7 @@ extern "C" int32_t kb_upload(kb_handle *h, const kb_snapshot *s) {
   D.sc_usage = h->search_smem ? nullptr : h->arena.take<i64>(G * ncap * FR);
   D.sc_adm_cap = (int)acap; D.sc_node_cap = (int)ncap;
   if (fair) {
-    D.q_scratch = h->arena.take<i64>(H * FR); D.fs_drs = h->arena.take<double2>(H * KB_MAX_DEPTH);
+    D.q_scratch = h->arena.take<i64>(H * FR); D.fs_state = h->arena.take<unsigned char>(H * (48 + 16 * KB_MAX_DEPTH));
     D.fs_cq_entry = h->arena.take<int32_t>(N); D.fs_winner = h->arena.take<int32_t>(N);
   }
   h->d_drs_rounded = h->arena.take<i64>(N); h->d_drs_res = h->arena.take<int32_t>(N); h->d_drs_borrowing = h->arena.take<uint8_t>(N);
@@ -426,6 +433,11 @@ static int32_t launch_admit(kb_handle *h, int *launches) {
     while (cap < KB_SORT_CAP && cap < D.H && admit_smem(nn_tables, D.FR, cap * 2) <= kMaxSmem) cap *= 2;
     return cap;
   };
+  if (D.nLone && D.lone_fast) {
+    size_t sm = (size_t)KB_LONE_WARPS * ((size_t)KB_LONE_CAP * 20 + (size_t)32 * D.FR * 8);
+    CUDA_TRY(h, cudaFuncSetAttribute(k_admit_lone, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
+    k_admit_lone<<<(D.nLone + KB_LONE_WARPS - 1) / KB_LONE_WARPS, KB_LONE_WARPS * 32, sm, h->stream>>>(D); (*launches)++;
+  }
   if (D.nLone) {
     int cap = pick_cap(1);
     size_t sm = admit_smem(1, D.FR, cap);
@@ -433,12 +445,18 @@ static int32_t launch_admit(kb_handle *h, int *launches) {
     k_admit<true><<<D.nLone, 128, sm, h->stream>>>(D, 0, cap); (*launches)++;
   }
   if (D.nTrees && (D.flags & KB_F_FAIR_SHARING)) {
-    size_t tb = (size_t)h->max_tree_nodes * D.FR * 32 + (size_t)h->max_tree_nodes * 4 + 8 + (KB_MAX_DEPTH + 2) * 4 + 64;
-    if (tb <= kMaxSmem) {
-      CUDA_TRY(h, cudaFuncSetAttribute(k_admit_fair<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
-      k_admit_fair<true><<<D.nTrees, 128, tb, h->stream>>>(D, D.nLone); (*launches)++;
+    // shared memory: [quota tables][path][per-entry tournament state]; entries per tree <= its ClusterQueues
+    size_t tables = (size_t)h->max_tree_nodes * D.FR * 32 + (size_t)h->max_tree_nodes * 4 + 16;
+    size_t misc = (KB_MAX_DEPTH + 2) * 4 + 32;
+    size_t state = (size_t)h->max_tree_nodes * (48 + 16 * KB_MAX_DEPTH);
+    CUDA_TRY(h, cudaFuncSetAttribute(k_admit_fair<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
+    CUDA_TRY(h, cudaFuncSetAttribute(k_admit_fair<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
+    if (tables + misc <= kMaxSmem) {
+      int in_smem = tables + misc + state <= kMaxSmem;
+      k_admit_fair<true><<<D.nTrees, 128, tables + misc + (in_smem ? state : 0), h->stream>>>(D, D.nLone, in_smem); (*launches)++;
     } else {
-      k_admit_fair<false><<<D.nTrees, 128, (KB_MAX_DEPTH + 2) * 4 + 64, h->stream>>>(D, D.nLone); (*launches)++;
+      int in_smem = misc + state <= kMaxSmem;
+      k_admit_fair<false><<<D.nTrees, 128, misc + (in_smem ? state : 0), h->stream>>>(D, D.nLone, in_smem); (*launches)++;
     }
   } else if (D.nTrees) {
     bool fits = admit_smem(h->max_tree_nodes, D.FR, 64) <= kMaxSmem;

@@ -64,6 +64,7 @@ struct DevSnap {
   const int32_t *cq_adm_start;// [Q+1] admitted workloads grouped by CQ
   const int32_t *cq_adm;      // [A]
   int nTrees, nLone, nRoots;
+  int lone_fast;  // cohort-less CQs take the warp-per-root admit kernel (no preemption targets possible, FR <= 64)
   // ---- derived per cycle ----
   i64 *subtree;    // [N][FR] resourceNode.SubtreeQuota
   i64 *usage;      // [N][FR] resourceNode.Usage (mutated by the admit kernel)
@@ -95,7 +96,7 @@ struct DevSnap {
   int sc_adm_cap, sc_node_cap;
   // ---- fair-sharing scratch ----
   i64 *q_scratch;        // [H][FR] dense Assignment.Usage.Quota per entry (absent = -1)
-  double2 *fs_drs;       // [H][KB_MAX_DEPTH] (unweightedRatio, fairWeight) per path level
+  unsigned char *fs_state; // [H] x (48 + 16*KB_MAX_DEPTH) B: per-entry tournament state when it does not fit shared memory
   int32_t *fs_cq_entry;  // [N] entry of a CQ still waiting in this cycle, or -1
   int32_t *fs_winner;    // [N] tournament winner of a cohort, or -1
 };

@@ -582,6 +582,8 @@ __global__ void k_scatter(DevSnap D) {
 //      and addUsage run lane-parallel with one __all_sync per entry.
 // ---------------------------------------------------------------------------
 #define KB_TILE 128
+#define KB_LONE_CAP 256
+#define KB_LONE_WARPS 4
 #define KB_SORT_CAP 1024  // entries per root sortable in shared memory
 
 // sort key: (borrow asc, priority desc, ts asc, workload index asc)
@@ -800,6 +802,7 @@ __global__ void __launch_bounds__(128) k_admit(DevSnap D, int slot_base, int sor
   int n = D.root_offset[slot + 1] - off;
   if (n == 0) return;
   int32_t *ent = D.root_entries + off;
+  if (slot < D.nLone && D.lone_fast && n <= KB_LONE_CAP) return;  // handled by k_admit_lone
   const int32_t *nodes; int nn;
   if (slot < D.nLone) { nodes = &D.lone_cqs[slot]; nn = 1; }
   else { int t = slot - D.nLone; nodes = D.tree_nodes + D.tree_start[t]; nn = D.tree_start[t + 1] - D.tree_start[t]; }
@@ -882,6 +885,98 @@ __global__ void __launch_bounds__(128) k_admit(DevSnap D, int slot_base, int sor
 }
 
 // ---------------------------------------------------------------------------
+// K5b: admit loop for ClusterQueues WITHOUT a cohort (every such CQ is its own root): one
+// WARP per ClusterQueue, four per CTA.  The quota "tree" is one row: lane l keeps the usage
+// and nominal quota of its flavor-resource columns l, l+32 in REGISTERS, so the ordered
+// commit loop (scheduler.go:269-401) touches memory only for the entries themselves.  Entries
+// are sorted with a warp-synchronous bitonic network over packed keys in shared memory and
+// expanded 32 at a time into a dense request matrix (one lane per entry).
+// Roots with more than KB_LONE_CAP entries, or with preemption targets in play, are left
+// to the general kernel.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(KB_LONE_WARPS * 32) k_admit_lone(DevSnap D) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int FR = D.FR;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int slot = blockIdx.x * KB_LONE_WARPS + warp;
+  if (slot >= D.nLone) return;
+  int off = D.root_offset[slot];
+  int n = D.root_offset[slot + 1] - off;
+  if (n == 0 || n > KB_LONE_CAP) return;
+  int32_t *ent = D.root_entries + off;
+  int cq = D.lone_cqs[slot];
+  // per-warp shared memory: keys (KB_LONE_CAP x 20 B) | dense request chunk (32 x FR x 8 B)
+  size_t per_warp = (size_t)KB_LONE_CAP * 20 + (size_t)32 * FR * 8;
+  unsigned char *base = smem_raw + (size_t)warp * per_warp;
+  u64 *k0 = (u64 *)base, *k1 = k0 + KB_LONE_CAP;
+  int *kidx = (int *)(k1 + KB_LONE_CAP);
+  i64 *qm = (i64 *)(base + (size_t)KB_LONE_CAP * 20);
+  // ---- sort (classical iterator order) ----
+  int np2 = 1;
+  while (np2 < n) np2 <<= 1;
+  for (int i = lane; i < np2; i += 32) {
+    if (i < n) { int e = ent[i]; entry_key(D, e, &k0[i], &k1[i]); kidx[i] = e; }
+    else { k0[i] = ~0ull; k1[i] = ~0ull; kidx[i] = INT32_MAX; }
+  }
+  __syncwarp();
+  for (int k = 2; k <= np2; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = lane; i < np2; i += 32) {
+        int l = i ^ j;
+        if (l > i) {
+          u64 a0 = k0[i], a1 = k1[i], b0 = k0[l], b1 = k1[l];
+          int ai = kidx[i], bi = kidx[l];
+          int aw = ai == INT32_MAX ? INT32_MAX : D.heads[ai], bw = bi == INT32_MAX ? INT32_MAX : D.heads[bi];
+          bool up = (i & k) == 0;
+          bool sw = up ? key_less(b0, b1, bw, a0, a1, aw) : key_less(a0, a1, aw, b0, b1, bw);
+          if (sw) { k0[i] = b0; k1[i] = b1; kidx[i] = bi; k0[l] = a0; k1[l] = a1; kidx[l] = ai; }
+        }
+      }
+      __syncwarp();
+    }
+  // ---- the CQ's row in registers (two columns per lane: FR <= 64; more columns loop through memory) ----
+  const bool two = FR > 32;
+  int c0 = lane, c1 = lane + 32;
+  i64 u0 = 0, u1 = 0, nom0 = 0, nom1 = 0;
+  if (c0 < FR) { u0 = D.usage[(size_t)cq * FR + c0]; nom0 = D.subtree[(size_t)cq * FR + c0]; }
+  if (two && c1 < FR) { u1 = D.usage[(size_t)cq * FR + c1]; nom1 = D.subtree[(size_t)cq * FR + c1]; }
+  bool reserve_ok = D.cq_reclaim_within[cq] != KB_POLICY_ANY;  // !CanAlwaysReclaim policy.go:27-29
+  // ---- chunks of 32 entries: expand (lane = entry), then commit in order (lane = column) ----
+  for (int basei = 0; basei < n; basei += 32) {
+    int cn = min(32, n - basei);
+    for (int c = lane; c < cn * FR; c += 32) qm[c] = -1;
+    __syncwarp();
+    int my_e = lane < cn ? kidx[basei + lane] : -1;
+    int my_mode = 0;
+    if (my_e >= 0) { expand_entry(D, my_e, qm + (size_t)lane * FR); my_mode = D.mode[my_e]; }
+    __syncwarp();
+    for (int j = 0; j < cn; j++) {
+      int e = __shfl_sync(0xffffffffu, my_e, j), mode = __shfl_sync(0xffffffffu, my_mode, j);
+      const i64 *qrow = qm + (size_t)j * FR;
+      i64 q0 = c0 < FR ? qrow[c0] : -1, q1 = (two && c1 < FR) ? qrow[c1] : -1;
+      int dec;
+      if (mode == KB_MODE_NOFIT) dec = KB_DEC_NOFIT;
+      else if (mode == KB_MODE_PREEMPT) {  // Preempt without targets (targets exclude this kernel): :303-318
+        dec = KB_DEC_PREEMPT_NO_TARGETS;
+        if (reserve_ok) {  // quotaResourcesToReserve :530-548 with Borrowing == 0 (no cohort)
+          if (q0 >= 0) u0 += imax(0, imin(q0, nom0 - u0));
+          if (q1 >= 0) u1 += imax(0, imin(q1, nom1 - u1));
+        }
+      } else {
+        bool ok = !(q0 > 0 && imax(0, nom0 - u0) < q0) && !(q1 > 0 && imax(0, nom1 - u1) < q1);  // Fits :121-136
+        ok = __all_sync(0xffffffffu, ok);
+        if (ok) { if (q0 > 0) u0 += q0; if (q1 > 0) u1 += q1; }
+        dec = ok ? KB_DEC_ASSUMED : KB_DEC_SKIPPED_NO_FIT;
+      }
+      if (lane == 0) { D.decision[e] = (uint8_t)dec; D.rank[e] = basei + j; }
+    }
+    __syncwarp();
+  }
+  if (c0 < FR) D.usage[(size_t)cq * FR + c0] = u0;
+  if (two && c1 < FR) D.usage[(size_t)cq * FR + c1] = u1;
+}
+
+// ---------------------------------------------------------------------------
 // K4: fair-sharing iterator + admit (fair_sharing_iterator.go:36-229), one CTA per
 // cohort tree.  Each pop: (1) every remaining entry recomputes, one thread per entry,
 // the DominantResourceShare of each node on its CQ->root path as if its own usage were
@@ -890,31 +985,42 @@ __global__ void __launch_bounds__(128) k_admit(DevSnap D, int slot_base, int sor
 // :120-153) runs bottom-up over the cohort levels, one warp per cohort with a
 // shuffle reduction over its children; (3) warp 0 commits the winner.
 // ---------------------------------------------------------------------------
-struct FsKey { double ratio, weight; };
+// Per-entry state of one cohort tree's tournament, staged once per cycle (slot = position of
+// the entry in the root's entry list).  Shared memory when `n * (32 + 16*nlev)` bytes fit,
+// else the global scratch of the same layout.
+struct FsState {
+  int *e_id;        // [n] global entry index
+  int *e_cq;        // [n] ClusterQueue (global node id)
+  int *e_prio;      // [n]
+  i64 *e_ts;        // [n]
+  int *e_flags;     // [n] bit0 requiresBorrowing, bit1 alive, bit2 dirty (DRS must be recomputed)
+  int *e_top;       // [n] ancestor of the CQ directly below the root (the CQ itself in a flat cohort)
+  double2 *drs;     // [n][nlev] (unweightedRatio, fairWeight) per path level
+  int nlev;
+};
 
-// entryComparer.less :166-199 for candidates a, b under parent cohort P (depth dP).
-__device__ inline bool fs_less(const DevSnap &D, int a, int b, int dP) {
+// entryComparer.less fair_sharing_iterator.go:166-199 for slots a, b under a parent cohort of depth dP
+__device__ __forceinline__ bool fs_less(const DevSnap &D, const FsState &F, int a, int b, int dP) {
   if (D.flags & KB_F_FS_PRIORITIZE_NON_BORROWING) {
-    bool ab = D.borrow[a] > 0, bb = D.borrow[b] > 0;
+    bool ab = F.e_flags[a] & 1, bb = F.e_flags[b] & 1;
     if (ab != bb) return !ab;
   }
-  int wa = D.heads[a], wb = D.heads[b];
-  int ka = D.depth[D.wl_cq[wa]] - dP - 1, kb = D.depth[D.wl_cq[wb]] - dP - 1;
-  double2 va = D.fs_drs[(size_t)a * KB_MAX_DEPTH + ka], vb = D.fs_drs[(size_t)b * KB_MAX_DEPTH + kb];
+  int ka = D.depth[F.e_cq[a]] - dP - 1, kb = D.depth[F.e_cq[b]] - dP - 1;
+  double2 va = F.drs[(size_t)a * F.nlev + ka], vb = F.drs[(size_t)b * F.nlev + kb];
   DevDRS da{va.y, va.x, -1, false}, db{vb.y, vb.x, -1, false};
   int c = drs_compare(da, db);
   if (c != 0) return c < 0;
   if (D.flags & KB_F_PRIORITY_SORTING_WITHIN_COHORT) {
-    int pa = D.wl_priority[wa], pb = D.wl_priority[wb];
+    int pa = F.e_prio[a], pb = F.e_prio[b];
     if (pa != pb) return pa > pb;
   }
-  return D.wl_ts[wa] < D.wl_ts[wb];
+  return F.e_ts[a] < F.e_ts[b];
 }
 
 template <bool kSmemTables>
-__global__ void __launch_bounds__(128) k_admit_fair(DevSnap D, int slot_base) {
+__global__ void __launch_bounds__(128) k_admit_fair(DevSnap D, int slot_base, int state_in_smem) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int FR = D.FR, R = D.R, F = D.F;
+  const int FR = D.FR, R = D.R, Fn = D.F;
   int slot = slot_base + blockIdx.x;
   int off = D.root_offset[slot];
   int n = D.root_offset[slot + 1] - off;
@@ -928,32 +1034,52 @@ __global__ void __launch_bounds__(128) k_admit_fair(DevSnap D, int slot_base) {
   while (nlev + 1 < KB_LEVELS && lvl[nlev + 1] > lvl[nlev]) nlev++;
   Tab<kSmemTables> T;
   unsigned char *p = stage_tables<kSmemTables>(D, T, smem_raw, nodes, nn);
-  int *s_path = (int *)p;  // KB_MAX_DEPTH + 2
-  // per-node scratch lives in global memory, indexed by node id: cq_entry / winner
-  int32_t *cq_entry = D.fs_cq_entry, *winner = D.fs_winner;
-  for (int i = threadIdx.x; i < nn; i += blockDim.x) { cq_entry[nodes[i]] = -1; winner[nodes[i]] = -1; }
+  int *s_path = (int *)p; p += (KB_MAX_DEPTH + 2) * 4;
+  p = (unsigned char *)(((uintptr_t)p + 15) & ~(uintptr_t)15);
+  FsState F;
+  F.nlev = nlev > 1 ? nlev - 1 : 1;  // a CQ at depth d has d path levels; d <= nlev-1
+  {
+    unsigned char *q = state_in_smem ? p : (unsigned char *)(D.fs_state + (size_t)off * (size_t)(48 + 16 * KB_MAX_DEPTH));
+    F.drs = (double2 *)q; q += (size_t)n * F.nlev * 16;
+    F.e_ts = (i64 *)q; q += (size_t)n * 8;
+    F.e_id = (int *)q; q += (size_t)n * 4; F.e_cq = (int *)q; q += (size_t)n * 4; F.e_prio = (int *)q; q += (size_t)n * 4;
+    F.e_flags = (int *)q; q += (size_t)n * 4; F.e_top = (int *)q; q += (size_t)n * 4;
+  }
+  int32_t *cq_slot = D.fs_cq_entry, *winner = D.fs_winner;  // per node (global id): waiting slot / tournament winner
+  for (int i = threadIdx.x; i < nn; i += blockDim.x) { cq_slot[nodes[i]] = -1; winner[nodes[i]] = -1; }
   __syncthreads();
-  for (int i = threadIdx.x; i < n; i += blockDim.x) { int e = ent[i]; cq_entry[D.wl_cq[D.heads[e]]] = e; }
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    int e = ent[i];
+    int wl = D.heads[e];
+    int cq = D.wl_cq[wl];
+    F.e_id[i] = e; F.e_cq[i] = cq; F.e_prio[i] = D.wl_priority[wl]; F.e_ts[i] = D.wl_ts[wl];
+    F.e_flags[i] = (D.borrow[e] > 0 ? 1 : 0) | 2 | 4;
+    int top = cq;
+    while (D.parent[top] >= 0 && D.parent[D.parent[top]] >= 0) top = D.parent[top];
+    F.e_top[i] = top;
+    cq_slot[cq] = i;
+  }
   for (int c = threadIdx.x; c < n * FR; c += blockDim.x) { int e = ent[c / FR]; D.q_scratch[(size_t)e * FR + c % FR] = entry_request(D, e, c % FR); }
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   for (int it = 0; it < n; it++) {
-    // (1) computeDRS for every remaining entry
+    // (1) computeDRS (:206-229) for the entries whose path saw a usage change since their last evaluation
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
-      int e = ent[i];
-      int cq = D.wl_cq[D.heads[e]];
-      if (cq_entry[cq] != e) continue;  // already popped
+      int fl = F.e_flags[i];
+      if ((fl & 6) != 6) continue;  // popped or clean
+      F.e_flags[i] = fl & ~4;
+      int e = F.e_id[i], cq = F.e_cq[i];
       const i64 *q = D.q_scratch + (size_t)e * FR;
-      int X = cq;  // global node ids for the walk; tables addressed through handles
+      int X = cq;
       for (int k = 0; D.parent[X] >= 0; k++, X = D.parent[X]) {
         int P = D.parent[X];
         int hX = T.handle(X);
         double best = 0.0;
         for (int r = 0; r < R; r++) {
           i64 b = 0, lend = 0;
-          for (int f = 0; f < F; f++) {
+          for (int f = 0; f < Fn; f++) {
             int fr = f * R + r;
-            // usage that entry e adds at node X in column fr: replay addUsage from the CQ up to X
+            // usage that the entry adds at node X in column fr: replay addUsage from the CQ up to X
             i64 d = q[fr] > 0 ? q[fr] : 0;
             int Y = cq;
             for (int j = 0; j < k && d > 0; j++, Y = D.parent[Y]) {
@@ -970,11 +1096,11 @@ __global__ void __launch_bounds__(128) k_admit_fair(DevSnap D, int slot_base) {
             if (ratio > best) best = ratio;
           }
         }
-        D.fs_drs[(size_t)e * KB_MAX_DEPTH + k] = make_double2(best, D.fair_weight[X]);
+        F.drs[(size_t)i * F.nlev + k] = make_double2(best, D.fair_weight[X]);
       }
     }
     __syncthreads();
-    // (2) tournament, bottom-up over cohort levels
+    // (2) tournament (runTournament :120-153), bottom-up over cohort levels, one warp per cohort
     for (int L = nlev - 1; L >= 0; L--) {
       for (int idx = lvl[L] + warp; idx < lvl[L + 1]; idx += nwarps) {
         int X = nodes[idx];
@@ -983,17 +1109,17 @@ __global__ void __launch_bounds__(128) k_admit_fair(DevSnap D, int slot_base) {
         int best = -1, bestpos = INT32_MAX;
         for (int c = c0 + lane; c < c1; c += 32) {
           int ch = D.child_list[c];
-          int cand = ch < D.Q ? cq_entry[ch] : winner[ch];
+          int cand = ch < D.Q ? cq_slot[ch] : winner[ch];
           if (cand < 0) continue;
-          if (best < 0 || fs_less(D, cand, best, L)) { best = cand; bestpos = c; }  // earlier candidate keeps ties
+          if (best < 0 || fs_less(D, F, cand, best, L)) { best = cand; bestpos = c; }  // the earlier candidate keeps ties
         }
         for (int o = 16; o > 0; o >>= 1) {
           int ob = __shfl_xor_sync(0xffffffffu, best, o), op = __shfl_xor_sync(0xffffffffu, bestpos, o);
           if (ob >= 0) {
             bool take;
             if (best < 0) take = true;
-            else if (fs_less(D, ob, best, L)) take = true;
-            else if (fs_less(D, best, ob, L)) take = false;
+            else if (fs_less(D, F, ob, best, L)) take = true;
+            else if (fs_less(D, F, best, ob, L)) take = false;
             else take = op < bestpos;
             if (take) { best = ob; bestpos = op; }
           }
@@ -1002,12 +1128,23 @@ __global__ void __launch_bounds__(128) k_admit_fair(DevSnap D, int slot_base) {
       }
       __syncthreads();
     }
-    // (3) pop + commit
+    // (3) pop + commit (warp 0), then mark the entries whose DRS inputs changed
+    int w = winner[nodes[0]];
+    int wcq = F.e_cq[w], we = F.e_id[w];
     if (warp == 0) {
-      int e = winner[nodes[0]];
-      int cq = D.wl_cq[D.heads[e]];
-      commit_entry<kSmemTables>(D, T, s_path, lane, e, T.handle(cq), D.mode[e], D.borrow[e], D.q_scratch + (size_t)e * FR, it);
-      if (lane == 0) cq_entry[cq] = -1;
+      commit_entry<kSmemTables>(D, T, s_path, lane, we, T.handle(wcq), D.mode[we], D.borrow[we], D.q_scratch + (size_t)we * FR, it);
+      __syncwarp();
+      if (lane == 0) {
+        int dec = D.decision[we];  // every branch that may have touched the tree's usage
+        bool changed = dec == KB_DEC_ASSUMED || dec == KB_DEC_PREEMPTING || dec == KB_DEC_PREEMPT_NO_TARGETS;
+        cq_slot[wcq] = -1; F.e_flags[w] &= ~2; s_path[KB_MAX_DEPTH] = changed;
+      }
+    }
+    __syncthreads();
+    if (s_path[KB_MAX_DEPTH]) {  // usage changed along path(wcq): entries below the same child-of-root share nodes with it
+      int top = F.e_top[w];
+      if (top != wcq)  // flat cohort: the popped CQ shares no non-root node with anyone else
+        for (int i = threadIdx.x; i < n; i += blockDim.x) if (F.e_top[i] == top) F.e_flags[i] |= 4;
     }
     __syncthreads();
   }
