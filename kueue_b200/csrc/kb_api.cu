@@ -447,7 +447,7 @@ static int32_t launch_admit(kb_handle *h, int *launches) {
   if (D.nTrees && (D.flags & KB_F_FAIR_SHARING)) {
     // shared memory: [quota tables][path][per-entry tournament state]; entries per tree <= its ClusterQueues
     size_t tables = (size_t)h->max_tree_nodes * D.FR * 32 + (size_t)h->max_tree_nodes * 4 + 16;
-    size_t misc = (KB_MAX_DEPTH + 2) * 4 + 32;
+    size_t misc = (KB_MAX_DEPTH + 2) * 4 + ((size_t)h->max_tree_nodes * 4 + 1) * 4 + 128 * 4 + 64;
     size_t state = (size_t)h->max_tree_nodes * (48 + 16 * KB_MAX_DEPTH);
     CUDA_TRY(h, cudaFuncSetAttribute(k_admit_fair<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
     CUDA_TRY(h, cudaFuncSetAttribute(k_admit_fair<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));

@@ -395,7 +395,12 @@ __global__ void __launch_bounds__(128) k_nominate(DevSnap D) {
   if (orc.need_search) {
     D.ps_list[atomicAdd(D.ps_n, 1)] = e;
   }
-  atomicAdd(&D.root_count[D.root_slot[D.wl_cq[wl]]], 1);
+  {  // count entries per root: one atomic per distinct root in the warp (heads are usually grouped by CQ)
+    int slot = D.root_slot[D.wl_cq[wl]];
+    unsigned act = __activemask();
+    unsigned m = __match_any_sync(act, slot);
+    if ((threadIdx.x & 31) == __ffs(m) - 1) atomicAdd(&D.root_count[slot], __popc(m));
+  }
 }
 
 // ---------------------------------------------------------------------------
@@ -561,8 +566,14 @@ __global__ void k_scatter(DevSnap D) {
   int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= D.H) return;
   int slot = D.root_slot[D.wl_cq[D.heads[e]]];
-  int pos = D.root_offset[slot] + atomicAdd(&D.root_cursor[slot], 1);
-  D.root_entries[pos] = e;
+  // warp-aggregated cursor bump: one atomic per distinct root in the warp
+  unsigned act = __activemask();
+  unsigned m = __match_any_sync(act, slot);
+  int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+  int base = 0;
+  if (lane == leader) base = atomicAdd(&D.root_cursor[slot], __popc(m));
+  base = __shfl_sync(m, base, leader);
+  D.root_entries[D.root_offset[slot] + base + __popc(m & ((1u << lane) - 1))] = e;
 }
 
 // ---------------------------------------------------------------------------
@@ -586,7 +597,7 @@ __global__ void k_scatter(DevSnap D) {
 #define KB_LONE_WARPS 4
 #define KB_SORT_CAP 1024  // entries per root sortable in shared memory
 
-// sort key: (borrow asc, priority desc, ts asc, workload index asc)
+// sort key: (borrow asc, priority desc, ts asc, entry index asc)
 __device__ __forceinline__ void entry_key(const DevSnap &D, int e, u64 *k0, u64 *k1) {
   int wl = D.heads[e];
   unsigned prio = 0;
@@ -833,7 +844,7 @@ __global__ void __launch_bounds__(128) k_admit(DevSnap D, int slot_base, int sor
           if (l > i) {
             u64 a0 = s_k0[i], a1 = s_k1[i], b0 = s_k0[l], b1 = s_k1[l];
             int ai = s_kidx[i], bi = s_kidx[l];
-            int aw = ai == INT32_MAX ? INT32_MAX : D.heads[ai], bw = bi == INT32_MAX ? INT32_MAX : D.heads[bi];
+            int aw = ai, bw = bi;  // canonical tie-break: position in the cycle's entry list
             bool up = (i & k) == 0;
             bool sw = up ? key_less(b0, b1, bw, a0, a1, aw) : key_less(a0, a1, aw, b0, b1, bw);
             if (sw) { s_k0[i] = b0; s_k1[i] = b1; s_kidx[i] = bi; s_k0[l] = a0; s_k1[l] = a1; s_kidx[l] = ai; }
@@ -850,7 +861,7 @@ __global__ void __launch_bounds__(128) k_admit(DevSnap D, int slot_base, int sor
     auto ce = [&](int i, int l) {  // compare-exchange, minimum to the lower index
       int a = ent[i], b = ent[l];
       u64 a0, a1, b0, b1; entry_key(D, a, &a0, &a1); entry_key(D, b, &b0, &b1);
-      if (key_less(b0, b1, D.heads[b], a0, a1, D.heads[a])) { ent[i] = b; ent[l] = a; }
+      if (key_less(b0, b1, b, a0, a1, a)) { ent[i] = b; ent[l] = a; }
     };
     for (int k = 2; k <= np2; k <<= 1) {
       for (int i = threadIdx.x; i < n; i += blockDim.x) { int l = i ^ (k - 1); if (l > i && l < n) ce(i, l); }
@@ -926,7 +937,7 @@ __global__ void __launch_bounds__(KB_LONE_WARPS * 32) k_admit_lone(DevSnap D) {
         if (l > i) {
           u64 a0 = k0[i], a1 = k1[i], b0 = k0[l], b1 = k1[l];
           int ai = kidx[i], bi = kidx[l];
-          int aw = ai == INT32_MAX ? INT32_MAX : D.heads[ai], bw = bi == INT32_MAX ? INT32_MAX : D.heads[bi];
+          int aw = ai, bw = bi;  // canonical tie-break: position in the cycle's entry list
           bool up = (i & k) == 0;
           bool sw = up ? key_less(b0, b1, bw, a0, a1, aw) : key_less(a0, a1, aw, b0, b1, bw);
           if (sw) { k0[i] = b0; k1[i] = b1; kidx[i] = bi; k0[l] = a0; k1[l] = a1; kidx[l] = ai; }
@@ -986,18 +997,21 @@ __global__ void __launch_bounds__(KB_LONE_WARPS * 32) k_admit_lone(DevSnap D) {
 // shuffle reduction over its children; (3) warp 0 commits the winner.
 // ---------------------------------------------------------------------------
 // Per-entry state of one cohort tree's tournament, staged once per cycle (slot = position of
-// the entry in the root's entry list).  Shared memory when `n * (32 + 16*nlev)` bytes fit,
-// else the global scratch of the same layout.
+// the entry in the root's entry list).  Shared memory when it fits, else a global scratch of
+// the same layout.
 struct FsState {
+  double2 *drs;     // [n][nlev] (unweightedRatio, fairWeight) per path level
+  i64 *e_ts;        // [n]
   int *e_id;        // [n] global entry index
   int *e_cq;        // [n] ClusterQueue (global node id)
   int *e_prio;      // [n]
-  i64 *e_ts;        // [n]
   int *e_flags;     // [n] bit0 requiresBorrowing, bit1 alive, bit2 dirty (DRS must be recomputed)
-  int *e_top;       // [n] ancestor of the CQ directly below the root (the CQ itself in a flat cohort)
-  double2 *drs;     // [n][nlev] (unweightedRatio, fairWeight) per path level
+  int *e_top;       // [n] local index of the ancestor directly below the root (the CQ itself in a flat cohort)
+  int *e_depth;     // [n] depth of the ClusterQueue
+  int *e_mode;      // [n] RepresentativeMode | Borrowing << 8
   int nlev;
 };
+#define KB_FS_ENTRY_BYTES (48 + 16 * KB_MAX_DEPTH)
 
 // entryComparer.less fair_sharing_iterator.go:166-199 for slots a, b under a parent cohort of depth dP
 __device__ __forceinline__ bool fs_less(const DevSnap &D, const FsState &F, int a, int b, int dP) {
@@ -1005,7 +1019,7 @@ __device__ __forceinline__ bool fs_less(const DevSnap &D, const FsState &F, int 
     bool ab = F.e_flags[a] & 1, bb = F.e_flags[b] & 1;
     if (ab != bb) return !ab;
   }
-  int ka = D.depth[F.e_cq[a]] - dP - 1, kb = D.depth[F.e_cq[b]] - dP - 1;
+  int ka = F.e_depth[a] - dP - 1, kb = F.e_depth[b] - dP - 1;
   double2 va = F.drs[(size_t)a * F.nlev + ka], vb = F.drs[(size_t)b * F.nlev + kb];
   DevDRS da{va.y, va.x, -1, false}, db{vb.y, vb.x, -1, false};
   int c = drs_compare(da, db);
@@ -1035,35 +1049,61 @@ __global__ void __launch_bounds__(128) k_admit_fair(DevSnap D, int slot_base, in
   Tab<kSmemTables> T;
   unsigned char *p = stage_tables<kSmemTables>(D, T, smem_raw, nodes, nn);
   int *s_path = (int *)p; p += (KB_MAX_DEPTH + 2) * 4;
+  // tree index arrays in LOCAL node ids (always shared memory): children CSR, waiting slot of a CQ, winner of a cohort
+  int *s_cstart = (int *)p; p += (size_t)(nn + 1) * 4;
+  int *s_child = (int *)p; p += (size_t)nn * 4;
+  int *s_slot = (int *)p; p += (size_t)nn * 4;
+  int *s_winner = (int *)p; p += (size_t)nn * 4;
+  int *s_order = (int *)p; p += (size_t)(state_in_smem ? 128 : 0) * 4;  // flat-cohort order (n <= 128 when used)
   p = (unsigned char *)(((uintptr_t)p + 15) & ~(uintptr_t)15);
   FsState F;
   F.nlev = nlev > 1 ? nlev - 1 : 1;  // a CQ at depth d has d path levels; d <= nlev-1
   {
-    unsigned char *q = state_in_smem ? p : (unsigned char *)(D.fs_state + (size_t)off * (size_t)(48 + 16 * KB_MAX_DEPTH));
+    unsigned char *q = state_in_smem ? p : D.fs_state + (size_t)off * KB_FS_ENTRY_BYTES;
     F.drs = (double2 *)q; q += (size_t)n * F.nlev * 16;
     F.e_ts = (i64 *)q; q += (size_t)n * 8;
     F.e_id = (int *)q; q += (size_t)n * 4; F.e_cq = (int *)q; q += (size_t)n * 4; F.e_prio = (int *)q; q += (size_t)n * 4;
     F.e_flags = (int *)q; q += (size_t)n * 4; F.e_top = (int *)q; q += (size_t)n * 4;
+    F.e_depth = (int *)q; q += (size_t)n * 4; F.e_mode = (int *)q; q += (size_t)n * 4;
   }
-  int32_t *cq_slot = D.fs_cq_entry, *winner = D.fs_winner;  // per node (global id): waiting slot / tournament winner
-  for (int i = threadIdx.x; i < nn; i += blockDim.x) { cq_slot[nodes[i]] = -1; winner[nodes[i]] = -1; }
+  for (int i = threadIdx.x; i < nn; i += blockDim.x) {
+    int nd = nodes[i];
+    (void)nd;
+    s_slot[i] = -1; s_winner[i] = -1;
+  }
   __syncthreads();
+  // children CSR in local ids: count, scan (thread 0; nn is small), fill
+  if (threadIdx.x == 0) {
+    int acc = 0;
+    for (int i = 0; i < nn; i++) { int nd = nodes[i]; s_cstart[i] = acc; acc += D.child_start[nd + 1] - D.child_start[nd]; }
+    s_cstart[nn] = acc;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < nn; i += blockDim.x) {
+    int nd = nodes[i];
+    int c0 = D.child_start[nd], cn = D.child_start[nd + 1] - c0;
+    for (int k = 0; k < cn; k++) s_child[s_cstart[i] + k] = D.local_idx[D.child_list[c0 + k]];
+  }
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     int e = ent[i];
     int wl = D.heads[e];
     int cq = D.wl_cq[wl];
     F.e_id[i] = e; F.e_cq[i] = cq; F.e_prio[i] = D.wl_priority[wl]; F.e_ts[i] = D.wl_ts[wl];
-    F.e_flags[i] = (D.borrow[e] > 0 ? 1 : 0) | 2 | 4;
+    int bw = D.borrow[e];
+    F.e_flags[i] = (bw > 0 ? 1 : 0) | 2 | 4;
+    F.e_mode[i] = (int)D.mode[e] | (bw << 8);
+    F.e_depth[i] = D.depth[cq];
     int top = cq;
     while (D.parent[top] >= 0 && D.parent[D.parent[top]] >= 0) top = D.parent[top];
-    F.e_top[i] = top;
-    cq_slot[cq] = i;
+    F.e_top[i] = D.local_idx[top];
+    s_slot[D.local_idx[cq]] = i;
   }
   for (int c = threadIdx.x; c < n * FR; c += blockDim.x) { int e = ent[c / FR]; D.q_scratch[(size_t)e * FR + c % FR] = entry_request(D, e, c % FR); }
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  for (int it = 0; it < n; it++) {
-    // (1) computeDRS (:206-229) for the entries whose path saw a usage change since their last evaluation
+
+  // computeDRS (:206-229) for the dirty entries: DRS of every node on the CQ->root path as if the entry were admitted
+  auto compute_drs = [&]() {
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
       int fl = F.e_flags[i];
       if ((fl & 6) != 6) continue;  // popped or clean
@@ -1099,17 +1139,55 @@ __global__ void __launch_bounds__(128) k_admit_fair(DevSnap D, int slot_base, in
         F.drs[(size_t)i * F.nlev + k] = make_double2(best, D.fair_weight[X]);
       }
     }
+  };
+
+  if (nlev == 2 && state_in_smem && n <= 128) {
+    // ---- flat cohort: the DRS of a ClusterQueue only depends on its own usage, which only its own entry changes,
+    //      so every pop of the tournament sees the same keys: the pop sequence is the order of
+    //      (entryComparer.less, child position) — sort once, then commit in that order.
+    compute_drs();
+    for (int i = threadIdx.x; i < 128; i += blockDim.x) s_order[i] = i < n ? i : -1;
+    __syncthreads();
+    auto before = [&](int a, int b) {  // a pops before b
+      if (a < 0) return false;
+      if (b < 0) return true;
+      if (fs_less(D, F, a, b, 0)) return true;
+      if (fs_less(D, F, b, a, 0)) return false;
+      return F.e_cq[a] < F.e_cq[b];  // candidates are the child CQs in ascending order; the earlier one keeps ties
+    };
+    for (int k = 2; k <= 128; k <<= 1)
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        int i = threadIdx.x, l = i ^ j;
+        if (l > i) {
+          int a = s_order[i], b = s_order[l];
+          bool up = (i & k) == 0;
+          if (up ? before(b, a) : before(a, b)) { s_order[i] = b; s_order[l] = a; }
+        }
+        __syncthreads();
+      }
+    if (warp == 0)
+      for (int it = 0; it < n; it++) {
+        int w = s_order[it];
+        int we = F.e_id[w], md = F.e_mode[w];
+        commit_entry<kSmemTables>(D, T, s_path, lane, we, T.handle(F.e_cq[w]), md & 0xff, md >> 8, D.q_scratch + (size_t)we * FR, it);
+      }
+    __syncthreads();
+    publish_usage<kSmemTables>(D, T, nodes, nn);
+    return;
+  }
+
+  for (int it = 0; it < n; it++) {
+    compute_drs();  // (1)
     __syncthreads();
     // (2) tournament (runTournament :120-153), bottom-up over cohort levels, one warp per cohort
     for (int L = nlev - 1; L >= 0; L--) {
       for (int idx = lvl[L] + warp; idx < lvl[L + 1]; idx += nwarps) {
-        int X = nodes[idx];
-        if (X < D.Q) continue;  // CQs carry entries, cohorts run the tournament
-        int c0 = D.child_start[X], c1 = D.child_start[X + 1];
+        if (nodes[idx] < D.Q) continue;  // CQs carry entries, cohorts run the tournament
+        int c0 = s_cstart[idx], c1 = s_cstart[idx + 1];
         int best = -1, bestpos = INT32_MAX;
         for (int c = c0 + lane; c < c1; c += 32) {
-          int ch = D.child_list[c];
-          int cand = ch < D.Q ? cq_slot[ch] : winner[ch];
+          int ch = s_child[c];
+          int cand = nodes[ch] < D.Q ? s_slot[ch] : s_winner[ch];
           if (cand < 0) continue;
           if (best < 0 || fs_less(D, F, cand, best, L)) { best = cand; bestpos = c; }  // the earlier candidate keeps ties
         }
@@ -1124,26 +1202,27 @@ __global__ void __launch_bounds__(128) k_admit_fair(DevSnap D, int slot_base, in
             if (take) { best = ob; bestpos = op; }
           }
         }
-        if (lane == 0) winner[X] = best;
+        if (lane == 0) s_winner[idx] = best;
       }
       __syncthreads();
     }
     // (3) pop + commit (warp 0), then mark the entries whose DRS inputs changed
-    int w = winner[nodes[0]];
+    int w = s_winner[0];
     int wcq = F.e_cq[w], we = F.e_id[w];
     if (warp == 0) {
-      commit_entry<kSmemTables>(D, T, s_path, lane, we, T.handle(wcq), D.mode[we], D.borrow[we], D.q_scratch + (size_t)we * FR, it);
+      int md = F.e_mode[w];
+      commit_entry<kSmemTables>(D, T, s_path, lane, we, T.handle(wcq), md & 0xff, md >> 8, D.q_scratch + (size_t)we * FR, it);
       __syncwarp();
       if (lane == 0) {
         int dec = D.decision[we];  // every branch that may have touched the tree's usage
         bool changed = dec == KB_DEC_ASSUMED || dec == KB_DEC_PREEMPTING || dec == KB_DEC_PREEMPT_NO_TARGETS;
-        cq_slot[wcq] = -1; F.e_flags[w] &= ~2; s_path[KB_MAX_DEPTH] = changed;
+        s_slot[D.local_idx[wcq]] = -1; F.e_flags[w] &= ~2; s_path[KB_MAX_DEPTH] = changed;
       }
     }
     __syncthreads();
     if (s_path[KB_MAX_DEPTH]) {  // usage changed along path(wcq): entries below the same child-of-root share nodes with it
       int top = F.e_top[w];
-      if (top != wcq)  // flat cohort: the popped CQ shares no non-root node with anyone else
+      if (top != D.local_idx[wcq])  // directly under the root: shares no non-root node with anyone else
         for (int i = threadIdx.x; i < n; i += blockDim.x) if (F.e_top[i] == top) F.e_flags[i] |= 4;
     }
     __syncthreads();

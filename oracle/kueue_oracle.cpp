@@ -16,7 +16,7 @@
 //
 // Canonical tie-breaks where the reference is nondeterministic:
 //   * classical iterator ties (scheduler.go:779 unstable sort, comparator 0 at
-//     :816): break by the workload's index in the pending table.
+//     :816): break by the entry's position in the cycle's entry list (heads[]).
 //   * child iteration (hierarchy/cohort.go:44-50 UnsortedList): child cohorts
 //     ascending node index, then child CQs ascending index.
 //   * resource iteration inside findFlavorForPodSets / assignFlavors (Go map
@@ -964,7 +964,7 @@ class Oracle {
         if (a.a.borrowing != b.a.borrowing) return a.a.borrowing < b.a.borrowing;
         if (prio && s.wl_priority[a.wl] != s.wl_priority[b.wl]) return s.wl_priority[a.wl] > s.wl_priority[b.wl];
         if (s.wl_ts[a.wl] != s.wl_ts[b.wl]) return s.wl_ts[a.wl] < s.wl_ts[b.wl];
-        return a.wl < b.wl;  // canonical tie-break: index in the pending table
+        return x < y;  // canonical tie-break: position in the cycle's entry list
       });
     }
     std::vector<char> preempted(s.n_adm, 0);  // PreemptedWorkloads
