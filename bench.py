@@ -115,6 +115,8 @@ def run_reference(args, rank, world):
         return
     import oracle
     snap = synth.make_snapshot(args.config, heads=HEADS[args.config])
+    if HEADS[args.config] == "one_per_cq":
+        snap = synth.compact_to_heads(snap)
     for _ in range(args.warmup):
         oracle.run_cycle(snap)
     t0 = time.perf_counter()
@@ -166,6 +168,8 @@ def main():
         del glob
     else:
         snap = synth.make_snapshot(args.config, heads=HEADS[args.config])
+    if HEADS[args.config] == "one_per_cq":
+        snap = synth.compact_to_heads(snap)  # the cycle only ever receives the heads (queues.Heads())
     ev = native.Evaluator(local_rank)
     snap = native.pin_snapshot(snap)            # host SoA buffers are page-locked (kb_alloc_pinned)
     out = native.pin_cycle_out(abi.CycleOut(snap))

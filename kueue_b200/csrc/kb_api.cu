@@ -43,7 +43,7 @@ struct kb_handle {
   int device = 0;
   int sm_count = 0;
   cudaStream_t stream = nullptr;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr, ev4 = nullptr, ev5 = nullptr;
   Arena arena;
   DevSnap D{};
   bool uploaded = false;
@@ -53,6 +53,9 @@ struct kb_handle {
   int kev_n = 0;
   std::string err;
   kb_stats stats{};
+  uint32_t *host_words = nullptr;  // pinned: [0] status bits, [1] targets used
+  int last_launches = 0;
+  int64_t last_d2h_bytes = 0;
   // tree_eval scratch
   i64 *d_drs_rounded = nullptr; int32_t *d_drs_res = nullptr; uint8_t *d_drs_borrowing = nullptr;
   // host-side derived topology
@@ -106,8 +109,9 @@ int32_t kb_create(const kb_config *cfg, kb_handle **out) {
   if (cudaSetDevice(dev) != cudaSuccess) { delete h; return fail(nullptr, KB_ERR_CUDA, "cudaSetDevice failed"); }
   cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, dev);
   if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return fail(nullptr, KB_ERR_CUDA, "stream"); }
-  cudaEventCreate(&h->ev0); cudaEventCreate(&h->ev1); cudaEventCreate(&h->ev2); cudaEventCreate(&h->ev3);
+  cudaEventCreate(&h->ev0); cudaEventCreate(&h->ev1); cudaEventCreate(&h->ev2); cudaEventCreate(&h->ev3); cudaEventCreate(&h->ev4); cudaEventCreate(&h->ev5);
   for (int i = 0; i <= KB_N_KERNELS; i++) cudaEventCreate(&h->kev[i]);
+  cudaHostAlloc((void **)&h->host_words, 64, cudaHostAllocDefault);
   h->stats.sm_count = h->sm_count;
   *out = h;
   return KB_OK;
@@ -117,11 +121,14 @@ void kb_destroy(kb_handle *h) {
   if (!h) return;
   cudaSetDevice(h->device);
   if (h->arena.base) cudaFree(h->arena.base);
+  if (h->host_words) cudaFreeHost(h->host_words);
   if (h->stream) cudaStreamDestroy(h->stream);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->ev2) cudaEventDestroy(h->ev2);
   if (h->ev3) cudaEventDestroy(h->ev3);
+  if (h->ev4) cudaEventDestroy(h->ev4);
+  if (h->ev5) cudaEventDestroy(h->ev5);
   for (int i = 0; i <= KB_N_KERNELS; i++) if (h->kev[i]) cudaEventDestroy(h->kev[i]);
   delete h;
 }
@@ -290,7 +297,7 @@ static cudaError_t up(kb_handle *h, const T *&dst, const T *src, size_t n, int64
   return cudaMemcpyAsync(d, src, n * sizeof(T), cudaMemcpyHostToDevice, h->stream);
 }
 
-extern "C" int32_t kb_upload(kb_handle *h, const kb_snapshot *s) {
+static int32_t upload_impl(kb_handle *h, const kb_snapshot *s, bool sync) {
   if (!h || !s) return KB_ERR_INVALID;
   cudaSetDevice(h->device);
   h->uploaded = false;
@@ -397,12 +404,17 @@ extern "C" int32_t kb_upload(kb_handle *h, const kb_snapshot *s) {
   CUDA_TRY(h, cudaMemsetAsync(D.ps_tried, 0xff, P * R, h->stream));
   CUDA_TRY(h, cudaMemsetAsync(D.ps_count_out, 0, P * 4, h->stream));
   CUDA_TRY(h, cudaEventRecord(h->ev1, h->stream));
-  CUDA_TRY(h, cudaStreamSynchronize(h->stream));  // host vectors / caller buffers may be released after return
-  float ms = 0; cudaEventElapsedTime(&ms, h->ev0, h->ev1);
-  h->stats.last_h2d_ms = ms; h->stats.h2d_bytes = bytes;
+  h->stats.h2d_bytes = bytes;
   h->uploaded = true;
+  if (sync) {  // caller buffers may be released after return
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    float ms = 0; cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+    h->stats.last_h2d_ms = ms;
+  }
   return KB_OK;
 }
+
+extern "C" int32_t kb_upload(kb_handle *h, const kb_snapshot *s) { return upload_impl(h, s, true); }
 
 // per-kernel timing: an event before each kernel (and one after the last) when profiling
 static inline void kmark(kb_handle *h, int id) {
@@ -475,7 +487,7 @@ static int32_t launch_admit(kb_handle *h, int *launches) {
   return KB_OK;
 }
 
-extern "C" int32_t kb_cycle_resident(kb_handle *h) {
+static int32_t cycle_enqueue(kb_handle *h) {
   if (!h || !h->uploaded) return fail(h, KB_ERR_INVALID, "kb_upload first");
   cudaSetDevice(h->device);
   DevSnap &D = h->D;
@@ -511,43 +523,63 @@ extern "C" int32_t kb_cycle_resident(kb_handle *h) {
   CUDA_TRY(h, cudaEventRecord(h->ev3, h->stream));
   if (rc_admit != KB_OK) return rc_admit;
   CUDA_TRY(h, cudaGetLastError());
-  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  h->last_launches = launches;
+  CUDA_TRY(h, cudaMemcpyAsync(&h->host_words[0], D.status, 4, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaMemcpyAsync(&h->host_words[1], D.tgt_pool_used, 4, cudaMemcpyDeviceToHost, h->stream));
+  return KB_OK;
+}
+
+// after the stream has been synchronized: timings + device status word
+static int32_t cycle_finish(kb_handle *h) {
   float ms = 0; cudaEventElapsedTime(&ms, h->ev2, h->ev3);
   h->stats.last_cycle_gpu_ms = ms;
-  h->stats.kernel_launches = launches;
+  h->stats.kernel_launches = h->last_launches;
   for (int i = 0; i < KB_N_KERNELS; i++) h->stats.kernel_ms[i] = 0.f;
   for (int i = 0; i + 1 < h->kev_n; i++) {
     float kms = 0; cudaEventElapsedTime(&kms, h->kev[i], h->kev[i + 1]);
     if (h->kev_id[i] >= 0) h->stats.kernel_ms[h->kev_id[i]] += kms;
   }
-  uint32_t st = 0;
-  CUDA_TRY(h, cudaMemcpy(&st, D.status, 4, cudaMemcpyDeviceToHost));
-  if (st & KBS_UNSUPPORTED_PREEMPTION) return fail(h, KB_ERR_UNSUPPORTED, "fair-sharing preemption search is not on the device yet");
-  if (st & KBS_TARGET_OVERFLOW) return fail(h, KB_ERR_CAPACITY, "per-entry usage cell capacity exceeded");
+  uint32_t st = h->host_words[0];
+  if (st & KBS_UNSUPPORTED_PREEMPTION) return fail(h, KB_ERR_UNSUPPORTED, "unsupported preemption configuration");
+  if (st & KBS_TARGET_OVERFLOW) return fail(h, KB_ERR_CAPACITY, "per-entry usage cell / target pool capacity exceeded");
   if (st & KBS_INTERNAL_LOOP) return fail(h, KB_ERR_CUDA, "internal: iteration guard tripped in the target search");
   return KB_OK;
 }
 
-extern "C" int32_t kb_download(kb_handle *h, kb_cycle_out *out) {
+extern "C" int32_t kb_cycle_resident(kb_handle *h) {
+  int32_t rc = cycle_enqueue(h);
+  if (rc != KB_OK) return rc;
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  return cycle_finish(h);
+}
+
+static int32_t download_enqueue(kb_handle *h, kb_cycle_out *out) {
   if (!h || !h->uploaded || !out) return fail(h, KB_ERR_INVALID, "nothing to download");
   cudaSetDevice(h->device);
   DevSnap &D = h->D;
   size_t H = D.H, PR = (size_t)D.P * D.R;
   int64_t bytes = 0;
-  CUDA_TRY(h, cudaEventRecord(h->ev0, h->stream));
+  CUDA_TRY(h, cudaEventRecord(h->ev4, h->stream));
 #define DOWN(dst, src, n, T) if (out->dst && (n)) { CUDA_TRY(h, cudaMemcpyAsync(out->dst, D.src, (n) * sizeof(T), cudaMemcpyDeviceToHost, h->stream)); bytes += (n) * sizeof(T); }
   DOWN(decision, decision, H, uint8_t); DOWN(mode, mode, H, uint8_t); DOWN(borrow, borrow, H, int32_t); DOWN(commit_rank, rank, H, int32_t);
   DOWN(ps_flavor, ps_flavor, PR, int8_t); DOWN(ps_res_mode, ps_res_mode, PR, int8_t); DOWN(ps_tried_idx, ps_tried, PR, int8_t);
   DOWN(ps_count, ps_count_out, (size_t)D.P, int32_t);
   DOWN(node_usage, usage, (size_t)D.N * D.FR, i64);
 #undef DOWN
-  CUDA_TRY(h, cudaEventRecord(h->ev1, h->stream));
-  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  CUDA_TRY(h, cudaEventRecord(h->ev5, h->stream));
+  h->last_d2h_bytes = bytes;
+  return KB_OK;
+}
+
+// after the stream has been synchronized (and cycle_finish filled host_words): preemption targets -> CSR
+static int32_t download_finish(kb_handle *h, kb_cycle_out *out) {
+  DevSnap &D = h->D;
+  size_t H = D.H;
+  int64_t bytes = h->last_d2h_bytes;
   out->n_targets = 0;
   if (out->tgt_start) {
     memset(out->tgt_start, 0, sizeof(int32_t) * (H + 1));
-    int32_t used = 0;
-    if (D.A && H) CUDA_TRY(h, cudaMemcpy(&used, D.tgt_pool_used, 4, cudaMemcpyDeviceToHost));
+    int32_t used = (D.A && H) ? (int32_t)h->host_words[1] : 0;
     if (used > 0) {  // gather the per-entry target lists into CSR order
       std::vector<int32_t> off(H), cnt(H), padm(used);
       std::vector<uint8_t> preason(used);
@@ -567,17 +599,33 @@ extern "C" int32_t kb_download(kb_handle *h, kb_cycle_out *out) {
       if (nt > out->tgt_capacity) return fail(h, KB_ERR_CAPACITY, "target buffer too small");
     }
   }
-  float ms = 0; cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+  float ms = 0; cudaEventElapsedTime(&ms, h->ev4, h->ev5);
   h->stats.last_d2h_ms = ms; h->stats.d2h_bytes = bytes;
   return KB_OK;
 }
 
+extern "C" int32_t kb_download(kb_handle *h, kb_cycle_out *out) {
+  int32_t rc = download_enqueue(h, out);
+  if (rc != KB_OK) return rc;
+  // the target count of the last cycle is re-read here in case kb_cycle_resident ran several times
+  CUDA_TRY(h, cudaMemcpyAsync(&h->host_words[1], h->D.tgt_pool_used, 4, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  return download_finish(h, out);
+}
+
+// One blocking call, one stream synchronisation: H2D copies, kernels and D2H copies are all enqueued first.
 extern "C" int32_t kb_run_cycle(kb_handle *h, const kb_snapshot *s, kb_cycle_out *out) {
-  int32_t rc = kb_upload(h, s);
+  int32_t rc = upload_impl(h, s, false);
   if (rc != KB_OK) return rc;
-  rc = kb_cycle_resident(h);
+  rc = cycle_enqueue(h);
   if (rc != KB_OK) return rc;
-  return kb_download(h, out);
+  rc = download_enqueue(h, out);
+  if (rc != KB_OK) return rc;
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  { float ms = 0; cudaEventElapsedTime(&ms, h->ev0, h->ev1); h->stats.last_h2d_ms = ms; }
+  rc = cycle_finish(h);
+  if (rc != KB_OK) return rc;
+  return download_finish(h, out);
 }
 
 extern "C" int32_t kb_tree_eval(kb_handle *h, const kb_snapshot *s, kb_tree_out *out) {

@@ -157,3 +157,26 @@ def make_snapshot(config: int = 2, W: int | None = None, Q: int | None = None, F
         first = np.concatenate([[True], snap.wl_cq[order][1:] != snap.wl_cq[order][:-1]])
         snap.set("heads", order[first])
     return snap.finalize()
+
+
+def compact_to_heads(snap: abi.FlatSnapshot) -> abi.FlatSnapshot:
+    """The pending tables reduced to the entries of the cycle — what `queues.Heads()` hands the
+    reference scheduler (manager.go:721-794): the cycle never sees the workloads deeper in the queues."""
+    from .shard import _csr_take
+    a = snap.arrays
+    R = snap.n_resource
+    h = a["heads"].astype(np.int64)
+    out = abi.FlatSnapshot(n_cq=snap.n_cq, n_cohort=snap.n_cohort, n_flavor=snap.n_flavor, n_resource=R,
+                           pods_resource=snap.pods_resource, flags=snap.flags, now_ns=snap.now_ns)
+    for k, v in a.items():
+        if not (k.startswith("wl_") or k.startswith("ps_") or k == "heads"):
+            out.arrays[k] = v
+    for nm in ("wl_cq", "wl_priority", "wl_ts", "wl_uid", "wl_last_gen"):
+        out.set(nm, a[nm][h])
+    st, rows = _csr_take(a["wl_ps_start"].astype(np.int64), h)
+    out.set("wl_ps_start", st)
+    out.set("ps_req", a["ps_req"].reshape(-1, R)[rows]); out.set("ps_last_tried", a["ps_last_tried"].reshape(-1, R)[rows])
+    for nm in ("ps_req_mask", "ps_count", "ps_min_count", "ps_flavor_ok"):
+        out.set(nm, a[nm][rows])
+    out.set("heads", np.arange(len(h)))
+    return out.finalize()
