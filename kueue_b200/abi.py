@@ -98,7 +98,7 @@ class kb_stats(C.Structure):
     ]
 
 
-KERNEL_NAMES = ["k_tree", "k_lone", "k_nominate", "k_scan_roots", "k_scatter", "k_admit", "k_fair", "k_preempt"]
+KERNEL_NAMES = ["k_tree", "k_lone", "k_nominate", "k_scan_roots", "k_scatter", "k_admit", "k_rank", "k_nominate_search"]
 
 
 class kb_config(C.Structure):

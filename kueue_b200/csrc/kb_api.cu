@@ -60,6 +60,7 @@ struct kb_handle {
   i64 *d_drs_rounded = nullptr; int32_t *d_drs_res = nullptr; uint8_t *d_drs_borrowing = nullptr;
   // host-side derived topology
   std::vector<int32_t> root_slot, depth, height, tree_start, tree_nodes, tree_level, lone, cq_adm_start, cq_adm, local_idx, child_start, child_list, adm_sorted, root_adm_start;
+  std::vector<uint8_t> tree_flat;
   int max_root_adm = 1;
   int search_grid = 1;
   bool search_smem = true;
@@ -219,6 +220,8 @@ static int32_t build_topology(kb_handle *h, const kb_snapshot *s) {
     for (int n = Q; n < N; n++) if (s->parent[n] >= 0) h->child_list[cur[s->parent[n]]++] = n;  // cohorts ascending
     for (int n = 0; n < Q; n++) if (s->parent[n] >= 0) h->child_list[cur[s->parent[n]]++] = n;  // then CQs ascending
   }
+  h->tree_flat.assign(std::max(1, ntrees), 1);
+  for (int n = 0; n < Q; n++) { int t = tree_of_root[root[n]]; if (t >= 0 && h->depth[n] != 1) h->tree_flat[t] = 0; }
   h->local_idx.assign(N, 0);
   h->max_tree_nodes = 1;
   for (int t = 0; t < ntrees; t++) {
@@ -323,7 +326,7 @@ static int32_t upload_impl(kb_handle *h, const kb_snapshot *s, bool sync) {
   need(N, 4); need(N, 4); need(N, 4); need(ntrees + 1, 4); need(h->tree_nodes.size(), 4); need(h->tree_level.size(), 4);
   need(h->lone.size(), 4); need(Q + 1, 4); need(h->cq_adm.size(), 4); need(N, 4); need(N + 1, 4); need(h->child_list.size(), 4);
   need(NF, 8); need(NF, 8); need(NF, 8); need(NF, 8);
-  need(nroots, 4); need(nroots + 1, 4); need(nroots, 4); need(H, 4);
+  need(nroots, 4); need(nroots + 1, 4); need(nroots, 4); need(H, 4); need(H, 4); need(H * 4, 8); need(H * 4, 8); need((size_t)Q * R, 8); need((size_t)N * R, 8); need(h->tree_flat.size(), 1);
   need(H, 1); need(H, 1); need(H, 4); need(H, 4); need(P * R, 1); need(P * R, 1); need(P * R, 1); need(P, 4);
   need(1, 4); need(N, 8); need(N, 4); need(N, 1);
   // preemption: search kernel configuration + scratch
@@ -369,6 +372,7 @@ static int32_t upload_impl(kb_handle *h, const kb_snapshot *s, bool sync) {
   UP(tree_start, h->tree_start.data(), ntrees + 1); UP(tree_nodes, h->tree_nodes.data(), h->tree_nodes.size());
   UP(tree_level, h->tree_level.data(), h->tree_level.size()); UP(lone_cqs, h->lone.data(), h->lone.size());
   UP(local_idx, h->local_idx.data(), N);
+  UP(tree_flat, h->tree_flat.data(), h->tree_flat.size());
   UP(adm_sorted, h->adm_sorted.data(), h->adm_sorted.size()); UP(root_adm_start, h->root_adm_start.data(), nroots + 1);
   UP(child_start, h->child_start.data(), N + 1); UP(child_list, h->child_list.data(), h->child_list.size());
   UP(cq_adm_start, h->cq_adm_start.data(), Q + 1); UP(cq_adm, h->cq_adm.data(), h->cq_adm.size());
@@ -377,6 +381,8 @@ static int32_t upload_impl(kb_handle *h, const kb_snapshot *s, bool sync) {
   D.avail = h->arena.take<i64>(NF); D.potential = h->arena.take<i64>(NF);
   D.root_count = h->arena.take<int32_t>(nroots); D.root_offset = h->arena.take<int32_t>(nroots + 1);
   D.root_cursor = h->arena.take<int32_t>(nroots); D.root_entries = h->arena.take<int32_t>(H);
+  D.sorted = h->arena.take<int32_t>(H); D.ekey = h->arena.take<u64>(H * 4); D.skey = h->arena.take<u64>(H * 4);
+  D.fs_over = h->arena.take<i64>((size_t)Q * R); D.fs_lend = h->arena.take<i64>((size_t)N * R);
   D.decision = h->arena.take<uint8_t>(H); D.mode = h->arena.take<uint8_t>(H);
   D.borrow = h->arena.take<int32_t>(H); D.rank = h->arena.take<int32_t>(H);
   D.ps_flavor = h->arena.take<int8_t>(P * R); D.ps_res_mode = h->arena.take<int8_t>(P * R); D.ps_tried = h->arena.take<int8_t>(P * R);
@@ -433,8 +439,8 @@ static int32_t launch_tree(kb_handle *h, int *launches) {
 // (slots [nLone, nRoots)) separately so each class gets the shared memory it needs.
 static size_t admit_smem(int nn_tables, int FR, int sort_cap) {
   size_t tb = (size_t)nn_tables * FR * 32;
-  size_t mid = std::max((size_t)sort_cap * 20, (size_t)KB_TILE * FR * 8);
-  return tb + mid + 16 + (size_t)nn_tables * 4 + KB_TILE * 16 + (KB_MAX_DEPTH + 2) * 4 + 64;
+  size_t mid = (size_t)KB_TILE * FR * 8; (void)sort_cap;
+  return tb + mid + 16 + (size_t)nn_tables * 4 + KB_TILE * 28 + (KB_MAX_DEPTH + 2) * 4 + 64;
 }
 static int32_t launch_admit(kb_handle *h, int *launches) {
   DevSnap &D = h->D;
@@ -446,7 +452,7 @@ static int32_t launch_admit(kb_handle *h, int *launches) {
     return cap;
   };
   if (D.nLone && D.lone_fast) {
-    size_t sm = (size_t)KB_LONE_WARPS * ((size_t)KB_LONE_CAP * 20 + (size_t)32 * D.FR * 8);
+    size_t sm = (size_t)KB_LONE_WARPS * 32 * D.FR * 8;
     CUDA_TRY(h, cudaFuncSetAttribute(k_admit_lone, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
     k_admit_lone<<<(D.nLone + KB_LONE_WARPS - 1) / KB_LONE_WARPS, KB_LONE_WARPS * 32, sm, h->stream>>>(D); (*launches)++;
   }
@@ -456,7 +462,10 @@ static int32_t launch_admit(kb_handle *h, int *launches) {
     CUDA_TRY(h, cudaFuncSetAttribute(k_admit<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
     k_admit<true><<<D.nLone, 128, sm, h->stream>>>(D, 0, cap); (*launches)++;
   }
-  if (D.nTrees && (D.flags & KB_F_FAIR_SHARING)) {
+  bool fair_trees = D.nTrees && (D.flags & KB_F_FAIR_SHARING);
+  bool any_deep = false;
+  for (uint8_t f : h->tree_flat) if (!f) any_deep = true;
+  if (fair_trees && any_deep) {  // tournament kernel for the non-flat trees (flat ones exit at once)
     // shared memory: [quota tables][path][per-entry tournament state]; entries per tree <= its ClusterQueues
     size_t tables = (size_t)h->max_tree_nodes * D.FR * 32 + (size_t)h->max_tree_nodes * 4 + 16;
     size_t misc = (KB_MAX_DEPTH + 2) * 4 + ((size_t)h->max_tree_nodes * 4 + 1) * 4 + 128 * 4 + 64;
@@ -470,7 +479,8 @@ static int32_t launch_admit(kb_handle *h, int *launches) {
       int in_smem = misc + state <= kMaxSmem;
       k_admit_fair<false><<<D.nTrees, 128, misc + (in_smem ? state : 0), h->stream>>>(D, D.nLone, in_smem); (*launches)++;
     }
-  } else if (D.nTrees) {
+  }
+  if (D.nTrees) {  // classical order, and fair sharing in flat cohorts (static key order)
     bool fits = admit_smem(h->max_tree_nodes, D.FR, 64) <= kMaxSmem;
     if (fits) {
       int cap = pick_cap(h->max_tree_nodes);
@@ -514,8 +524,10 @@ static int32_t cycle_enqueue(kb_handle *h) {
       }
       launches++;
     }
+    if (D.flags & KB_F_FAIR_SHARING) { k_fair_prep<<<(D.N * D.R + 255) / 256, 256, 0, h->stream>>>(D); launches++; }
     kmark(h, KB_K_SCAN); k_scan_roots<<<1, 1024, 0, h->stream>>>(D); launches++;
     kmark(h, KB_K_SCATTER); k_scatter<<<(D.H + 255) / 256, 256, 0, h->stream>>>(D); launches++;
+    kmark(h, KB_K_FAIR); k_rank<<<(D.H + 255) / 256, 256, 0, h->stream>>>(D); launches++;
     kmark(h, KB_K_ADMIT);
     rc_admit = launch_admit(h, &launches);
   }

@@ -75,6 +75,12 @@ struct DevSnap {
   int32_t *root_offset;  // [nRoots+1]
   int32_t *root_cursor;  // [nRoots]
   int32_t *root_entries; // [H]
+  int32_t *sorted;       // [H] entries of every root in iterator order (k_rank)
+  u64 *ekey;             // [H][4] iterator order key of every entry
+  u64 *skey;             // [H][4] the same keys in root-segment order
+  i64 *fs_over;          // [Q][R]  sum_f max(0, usage - SubtreeQuota)
+  i64 *fs_lend;          // [N][R]  sum_f potentialAvailable
+  const uint8_t *tree_flat; // [nTrees] every ClusterQueue of the tree hangs directly off the root cohort
   // ---- outputs (device) ----
   uint8_t *decision, *mode;
   int32_t *borrow, *rank;

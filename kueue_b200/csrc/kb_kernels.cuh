@@ -19,6 +19,8 @@
 #include "kb_device.cuh"
 #include "kb_preempt.cuh"
 
+#define KB_RANK_CAP 2048  // roots up to this many entries are ordered by the all-pairs k_rank kernel
+
 // ---------------------------------------------------------------------------
 // K1: tree pass, one CTA per cohort-rooted tree.
 // ---------------------------------------------------------------------------
@@ -531,6 +533,77 @@ __global__ void __launch_bounds__(32) k_nominate_search(DevSnap D) {
 }
 
 
+// dense request of entry e for column fr (absent = -1); defined before the key computation
+__device__ __forceinline__ i64 entry_request_early(const DevSnap &D, int e, int fr) {
+  const int R = D.R;
+  int f = fr / R, r = fr % R;
+  int wl = D.heads[e];
+  int cq = D.wl_cq[wl];
+  bool covers_pods = D.pods_res >= 0 && rg_by_resource(D, cq, D.pods_res) >= 0;
+  i64 q = -1;
+  for (int row = D.wl_ps_start[wl]; row < D.wl_ps_start[wl + 1]; row++)
+    if (D.ps_flavor[(size_t)row * R + r] == f) q = (q < 0 ? 0 : q) + ps_request(D, row, r, D.ps_count_out[row], covers_pods);
+  return q;
+}
+
+// Iterator order as a 4 x u64 lexicographic key per entry (D.ekey):
+//   classical (scheduler.go:778-817): [Borrowing | priority desc] [queue-order timestamp] [entry index] [0]
+//   fair sharing in a FLAT cohort (every ClusterQueue directly under the root): the DominantResourceShare a
+//   ClusterQueue would have with its entry admitted depends only on its own usage, which no other pop changes,
+//   so the tournament's pop sequence (fair_sharing_iterator.go:120-199) is the order of
+//   [requiresBorrowing, zeroWeightBorrows | share hi] [share lo | priority desc] [timestamp] [cq index].
+__device__ inline void compute_entry_key(const DevSnap &D, int e, u64 *k) {
+  int wl = D.heads[e];
+  int cq = D.wl_cq[wl];
+  unsigned prio = 0;
+  if (D.flags & KB_F_PRIORITY_SORTING_WITHIN_COHORT) prio = 0x7fffffffu - (unsigned)(D.wl_priority[wl] ^ 0x80000000);  // desc
+  u64 ts = (u64)D.wl_ts[wl] ^ 0x8000000000000000ull;
+  int P = D.parent[cq];
+  bool fair_flat = (D.flags & KB_F_FAIR_SHARING) && P >= 0 && D.tree_flat[D.root_slot[cq] - D.nLone];
+  if (!fair_flat) {
+    k[0] = ((u64)(unsigned)D.borrow[e] << 32) | prio; k[1] = ts; k[2] = (u64)(unsigned)e; k[3] = 0;
+    return;
+  }
+  // dominantResourceShare(cq) with the entry's usage added (computeDRS fair_sharing_iterator.go:206-229).
+  // borrowed[r] = sum_f max(0, usage + q - SubtreeQuota); only the cells the entry is assigned to differ from the
+  // ClusterQueue's own over-usage, which k_fair_prep precomputed per (cq, resource) together with lendable[r].
+  const int R = D.R, FR = D.FR;
+  bool covers_pods = D.pods_res >= 0 && rg_by_resource(D, cq, D.pods_res) >= 0;
+  double best = 0.0;
+  for (int r = 0; r < R; r++) {
+    i64 b = D.fs_over[(size_t)cq * R + r];
+    // flavors this entry uses for resource r (aggregated over its podsets)
+    int ps0 = D.wl_ps_start[wl], ps1 = D.wl_ps_start[wl + 1];
+    for (int row = ps0; row < ps1; row++) {
+      int f = D.ps_flavor[(size_t)row * R + r];
+      if (f < 0) continue;
+      bool first = true;  // count each (f, r) cell once, with the summed request of all podsets on it
+      for (int prow = ps0; prow < row; prow++) if (D.ps_flavor[(size_t)prow * R + r] == f) first = false;
+      if (!first) continue;
+      i64 q = 0;
+      for (int prow = row; prow < ps1; prow++)
+        if (D.ps_flavor[(size_t)prow * R + r] == f) q += ps_request(D, prow, r, D.ps_count_out[prow], covers_pods);
+      size_t c = (size_t)cq * FR + (size_t)f * R + r;
+      i64 base = D.usage[c] - D.subtree[c];
+      b += imax(0, base + (q > 0 ? q : 0)) - imax(0, base);
+    }
+    i64 lend = D.fs_lend[(size_t)P * R + r];
+    if (b > 0 && lend > 0) { double ratio = (double)b * 1000.0 / (double)lend; if (ratio > best) best = ratio; }
+  }
+  double w = D.fair_weight[cq];
+  bool zwb = w == 0 && best != 0;
+  double value = zwb ? best : (best == 0 ? 0.0 : best / w);
+  u64 vb = (u64)__double_as_longlong(value);  // value >= 0: the bit pattern is monotone
+  u64 flags = ((D.flags & KB_F_FS_PRIORITIZE_NON_BORROWING) && D.borrow[e] > 0 ? 2 : 0) | (zwb ? 1 : 0);
+  k[0] = (flags << 32) | (vb >> 32); k[1] = (vb << 32) | prio; k[2] = ts; k[3] = (u64)(unsigned)cq;
+}
+__device__ __forceinline__ bool key4_less(const u64 *a, const u64 *b) {
+  if (a[0] != b[0]) return a[0] < b[0];
+  if (a[1] != b[1]) return a[1] < b[1];
+  if (a[2] != b[2]) return a[2] < b[2];
+  return a[3] < b[3];
+}
+
 // ---------------------------------------------------------------------------
 // K3: group entries by root (counting sort: count in K2, scan, scatter)
 // ---------------------------------------------------------------------------
@@ -574,6 +647,54 @@ __global__ void k_scatter(DevSnap D) {
   if (lane == leader) base = atomicAdd(&D.root_cursor[slot], __popc(m));
   base = __shfl_sync(m, base, leader);
   D.root_entries[D.root_offset[slot] + base + __popc(m & ((1u << lane) - 1))] = e;
+  u64 k[4];
+  compute_entry_key(D, e, k);
+  ulonglong2 *dst = (ulonglong2 *)(D.ekey + (size_t)e * 4);
+  dst[0] = make_ulonglong2(k[0], k[1]); dst[1] = make_ulonglong2(k[2], k[3]);
+  int pos = D.root_offset[slot] + base + __popc(m & ((1u << lane) - 1));
+  ulonglong2 *sd = (ulonglong2 *)(D.skey + (size_t)pos * 4);  // the same key in segment order, for k_rank's scan
+  sd[0] = make_ulonglong2(k[0], k[1]); sd[1] = make_ulonglong2(k[2], k[3]);
+}
+
+// Fair sharing: per (ClusterQueue, resource) the usage above SubtreeQuota summed over flavors, and per
+// (node, resource) the lendable capacity sum_f potentialAvailable(node, f) (calculateLendable fair_sharing.go:160-174).
+__global__ void k_fair_prep(DevSnap D) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int R = D.R, F = D.F, FR = D.FR;
+  if (i >= D.N * R) return;
+  int n = i / R, r = i % R;
+  i64 over = 0, lend = 0;
+  for (int f = 0; f < F; f++) {
+    size_t c = (size_t)n * FR + (size_t)f * R + r;
+    lend += D.potential[c];
+    if (n < D.Q) { i64 o = D.usage[c] - D.subtree[c]; if (o > 0) over += o; }
+  }
+  D.fs_lend[i] = lend;
+  if (n < D.Q) D.fs_over[i] = over;
+}
+
+// Rank of every entry among the entries of its root (roots with at most KB_RANK_CAP entries): a fully parallel
+// all-pairs count — the threads of a warp mostly share the root, so the scanned keys are broadcast loads.
+// Writes the root's entries in iterator order to D.sorted.
+__global__ void __launch_bounds__(256) k_rank(DevSnap D) {
+  int pos = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pos >= D.H) return;
+  int e = D.root_entries[pos];
+  int slot = D.root_slot[D.wl_cq[D.heads[e]]];
+  int off = D.root_offset[slot], n = D.root_offset[slot + 1] - off;
+  if (n > KB_RANK_CAP) return;
+  const ulonglong2 *src = (const ulonglong2 *)(D.skey + (size_t)pos * 4);
+  ulonglong2 m0 = src[0], m1 = src[1];
+  u64 mine[4] = {m0.x, m0.y, m1.x, m1.y};
+  int rank = 0;
+  const ulonglong2 *seg = (const ulonglong2 *)(D.skey + (size_t)off * 4);
+#pragma unroll 4
+  for (int j = 0; j < n; j++) {
+    ulonglong2 a = seg[2 * j], b = seg[2 * j + 1];
+    u64 other[4] = {a.x, a.y, b.x, b.y};
+    rank += key4_less(other, mine) ? 1 : 0;
+  }
+  D.sorted[off + rank] = e;
 }
 
 // ---------------------------------------------------------------------------
@@ -596,20 +717,6 @@ __global__ void k_scatter(DevSnap D) {
 #define KB_LONE_CAP 256
 #define KB_LONE_WARPS 4
 #define KB_SORT_CAP 1024  // entries per root sortable in shared memory
-
-// sort key: (borrow asc, priority desc, ts asc, entry index asc)
-__device__ __forceinline__ void entry_key(const DevSnap &D, int e, u64 *k0, u64 *k1) {
-  int wl = D.heads[e];
-  unsigned prio = 0;
-  if (D.flags & KB_F_PRIORITY_SORTING_WITHIN_COHORT) prio = 0x7fffffffu - (unsigned)(D.wl_priority[wl] ^ 0x80000000);  // desc
-  *k0 = ((u64)(unsigned)D.borrow[e] << 32) | prio;
-  *k1 = (u64)D.wl_ts[wl] ^ 0x8000000000000000ull;
-}
-__device__ __forceinline__ bool key_less(u64 a0, u64 a1, int aw, u64 b0, u64 b1, int bw) {
-  if (a0 != b0) return a0 < b0;
-  if (a1 != b1) return a1 < b1;
-  return aw < bw;
-}
 
 // Quota-tree tables of one root, either staged in shared memory (node handle = local
 // index inside the tree) or left in global memory (node handle = global node id).
@@ -702,18 +809,19 @@ __device__ inline void publish_usage(const DevSnap &D, const Tab<kSmem> &T, cons
 // One iteration of the admit loop body (scheduler.go:269-401) for entry e, executed by a
 // full warp: lane l owns the flavor-resource columns l, l+32, ...  qrow[fr] is the
 // aggregated Assignment.Usage.Quota (absent cell = -1).  s_path: KB_MAX_DEPTH+2 ints.
+// cq = global id of the entry's ClusterQueue, slot = root slot, ntg/toff = its preemption targets in the pool,
+// s_npre = shared-memory count of the workloads preempted so far in this root.
 template <bool kSmem>
 __device__ inline void commit_entry(const DevSnap &D, const Tab<kSmem> &T, int *s_path, int lane, int e, int nd, int mode,
-                                    int borrowing, const i64 *qrow, int rank) {
+                                    int borrowing, const i64 *qrow, int rank, int cq, int slot, int ntg, int toff, int *s_npre) {
   const int FR = D.FR;
   if (lane == 0) D.rank[e] = rank;
   if (mode == KB_MODE_NOFIT) { if (lane == 0) D.decision[e] = KB_DEC_NOFIT; return; }
   if (lane == 0) { int pl = 0; for (int t = nd; t >= 0; t = T.parent(t)) s_path[pl++] = t; s_path[KB_MAX_DEPTH + 1] = pl; }
   __syncwarp();
   int plen = s_path[KB_MAX_DEPTH + 1];
-  if (mode == KB_MODE_PREEMPT && D.tgt_cnt[e] == 0) {  // Preempt without targets: scheduler.go:303-318
+  if (mode == KB_MODE_PREEMPT && ntg == 0) {  // Preempt without targets: scheduler.go:303-318
     if (lane == 0) D.decision[e] = KB_DEC_PREEMPT_NO_TARGETS;
-    int cq = D.wl_cq[D.heads[e]];
     if (D.cq_reclaim_within[cq] != KB_POLICY_ANY) {  // !CanAlwaysReclaim policy.go:27-29
       for (int fr = lane; fr < FR; fr += 32) {        // quotaResourcesToReserve :530-548
         i64 u = qrow[fr];
@@ -730,10 +838,8 @@ __device__ inline void commit_entry(const DevSnap &D, const Tab<kSmem> &T, int *
   }
   // entries with preemption targets: overlap check (:321-325) and fits() with the usage of
   // every workload preempted so far in this root plus the new targets removed (:503-511)
-  int ntg = D.tgt_cnt[e], toff = D.tgt_off[e];
-  int slot = D.root_slot[D.wl_cq[D.heads[e]]];
-  int *plist = D.root_pre_list + D.root_adm_start[slot];
-  int npre = D.root_pre_count[slot];
+  int npre = *s_npre;
+  int *plist = (npre > 0 || ntg > 0) ? D.root_pre_list + D.root_adm_start[slot] : nullptr;
   if (ntg > 0) {
     bool overlap = false;
     for (int k = lane; k < ntg; k += 32) if (D.preempted[D.tgt_pool_adm[toff + k]]) overlap = true;
@@ -764,7 +870,8 @@ __device__ inline void commit_entry(const DevSnap &D, const Tab<kSmem> &T, int *
   if (ok) {
     if (ntg > 0) {  // preemptedWorkloads.Insert :335
       for (int k = lane; k < ntg; k += 32) { int a = D.tgt_pool_adm[toff + k]; D.preempted[a] = 1; plist[npre + k] = a; }
-      if (lane == 0) D.root_pre_count[slot] = npre + ntg;
+      __syncwarp();
+      if (lane == 0) *s_npre = npre + ntg;
       __syncwarp();
     }
     for (int fr = lane; fr < FR; fr += 32) { i64 q = qrow[fr]; if (q > 0) T.add(s_path, plen, fr, q); }  // cq.AddUsage :336
@@ -813,7 +920,8 @@ __global__ void __launch_bounds__(128) k_admit(DevSnap D, int slot_base, int sor
   int n = D.root_offset[slot + 1] - off;
   if (n == 0) return;
   int32_t *ent = D.root_entries + off;
-  if (slot < D.nLone && D.lone_fast && n <= KB_LONE_CAP) return;  // handled by k_admit_lone
+  if (slot < D.nLone && D.lone_fast && n <= KB_RANK_CAP) return;  // handled by k_admit_lone
+  if (slot >= D.nLone && (D.flags & KB_F_FAIR_SHARING) && !D.tree_flat[slot - D.nLone]) return;  // tournament kernel
   const int32_t *nodes; int nn;
   if (slot < D.nLone) { nodes = &D.lone_cqs[slot]; nn = 1; }
   else { int t = slot - D.nLone; nodes = D.tree_nodes + D.tree_start[t]; nn = D.tree_start[t + 1] - D.tree_start[t]; }
@@ -821,47 +929,24 @@ __global__ void __launch_bounds__(128) k_admit(DevSnap D, int slot_base, int sor
   Tab<kSmemTables> T;
   unsigned char *p = stage_tables<kSmemTables>(D, T, smem_raw, nodes, nn);
   i64 *s_q = (i64 *)p;
-  u64 *s_k0 = (u64 *)p, *s_k1 = s_k0 + sort_cap; int *s_kidx = (int *)(s_k1 + sort_cap);
-  size_t sort_bytes = (size_t)sort_cap * 20, tile_bytes = (size_t)KB_TILE * FR * 8;
-  p += (sort_bytes > tile_bytes ? sort_bytes : tile_bytes);
+  p += (size_t)KB_TILE * FR * 8;
+  (void)sort_cap;
   p = (unsigned char *)(((uintptr_t)p + 7) & ~(uintptr_t)7);
   int *t_e = (int *)p, *t_node = t_e + KB_TILE, *t_mode = t_node + KB_TILE, *t_borrow = t_mode + KB_TILE;
-  int *s_path = t_borrow + KB_TILE;
+  int *t_cq = t_borrow + KB_TILE, *t_ntg = t_cq + KB_TILE, *t_toff = t_ntg + KB_TILE;
+  int *s_path = t_toff + KB_TILE;
+  int *s_npre = s_path + KB_MAX_DEPTH + 2;
+  if (threadIdx.x == 0) *s_npre = 0;
 
-  // ---- 1. sort ----
-  int np2 = 1;
-  while (np2 < n) np2 <<= 1;
-  if (n > 1 && np2 <= sort_cap) {
-    for (int i = threadIdx.x; i < np2; i += blockDim.x) {
-      if (i < n) { int e = ent[i]; entry_key(D, e, &s_k0[i], &s_k1[i]); s_kidx[i] = e; }
-      else { s_k0[i] = ~0ull; s_k1[i] = ~0ull; s_kidx[i] = INT32_MAX; }
-    }
-    __syncthreads();
-    for (int k = 2; k <= np2; k <<= 1)
-      for (int j = k >> 1; j > 0; j >>= 1) {
-        for (int i = threadIdx.x; i < np2; i += blockDim.x) {
-          int l = i ^ j;
-          if (l > i) {
-            u64 a0 = s_k0[i], a1 = s_k1[i], b0 = s_k0[l], b1 = s_k1[l];
-            int ai = s_kidx[i], bi = s_kidx[l];
-            int aw = ai, bw = bi;  // canonical tie-break: position in the cycle's entry list
-            bool up = (i & k) == 0;
-            bool sw = up ? key_less(b0, b1, bw, a0, a1, aw) : key_less(a0, a1, aw, b0, b1, bw);
-            if (sw) { s_k0[i] = b0; s_k1[i] = b1; s_kidx[i] = bi; s_k0[l] = a0; s_k1[l] = a1; s_kidx[l] = ai; }
-          }
-        }
-        __syncthreads();
-      }
-    for (int i = threadIdx.x; i < n; i += blockDim.x) ent[i] = s_kidx[i];
-    __syncthreads();
-  } else if (n > 1) {
-    // root with more entries than the shared-memory sort holds: ascending-only bitonic
-    // network over the global index array (virtual +inf padding beyond n never moves),
-    // keys re-read through L2.
+  // ---- 1. iterator order: k_rank already produced it for roots up to KB_RANK_CAP entries; larger roots sort here
+  //         with an ascending-only bitonic network over the global index array (virtual +inf padding never moves).
+  if (n <= KB_RANK_CAP) ent = D.sorted + off;
+  else {
+    int np2 = 1;
+    while (np2 < n) np2 <<= 1;
     auto ce = [&](int i, int l) {  // compare-exchange, minimum to the lower index
       int a = ent[i], b = ent[l];
-      u64 a0, a1, b0, b1; entry_key(D, a, &a0, &a1); entry_key(D, b, &b0, &b1);
-      if (key_less(b0, b1, b, a0, a1, a)) { ent[i] = b; ent[l] = a; }
+      if (key4_less(D.ekey + (size_t)b * 4, D.ekey + (size_t)a * 4)) { ent[i] = b; ent[l] = a; }
     };
     for (int k = 2; k <= np2; k <<= 1) {
       for (int i = threadIdx.x; i < n; i += blockDim.x) { int l = i ^ (k - 1); if (l > i && l < n) ce(i, l); }
@@ -879,8 +964,9 @@ __global__ void __launch_bounds__(128) k_admit(DevSnap D, int slot_base, int sor
     int tn = min(KB_TILE, n - base);
     for (int i = threadIdx.x; i < tn; i += blockDim.x) {
       int e = ent[base + i];
-      t_e[i] = e; t_node[i] = T.handle(D.wl_cq[D.heads[e]]);
-      t_mode[i] = D.mode[e]; t_borrow[i] = D.borrow[e];
+      int cqn = D.wl_cq[D.heads[e]];
+      t_e[i] = e; t_node[i] = T.handle(cqn); t_cq[i] = cqn;
+      t_mode[i] = D.mode[e]; t_borrow[i] = D.borrow[e]; t_ntg[i] = D.tgt_cnt[e]; t_toff[i] = D.tgt_off[e];
     }
     for (int c = threadIdx.x; c < tn * FR; c += blockDim.x) s_q[c] = -1;
     __syncthreads();
@@ -889,7 +975,8 @@ __global__ void __launch_bounds__(128) k_admit(DevSnap D, int slot_base, int sor
     __syncthreads();
     if (warp == 0)
       for (int i = 0; i < tn; i++)
-        commit_entry<kSmemTables>(D, T, s_path, lane, t_e[i], t_node[i], t_mode[i], t_borrow[i], s_q + (size_t)i * FR, base + i);
+        commit_entry<kSmemTables>(D, T, s_path, lane, t_e[i], t_node[i], t_mode[i], t_borrow[i], s_q + (size_t)i * FR, base + i,
+                                  t_cq[i], slot, t_ntg[i], t_toff[i], s_npre);
     __syncthreads();
   }
   publish_usage<kSmemTables>(D, T, nodes, nn);
@@ -900,9 +987,9 @@ __global__ void __launch_bounds__(128) k_admit(DevSnap D, int slot_base, int sor
 // WARP per ClusterQueue, four per CTA.  The quota "tree" is one row: lane l keeps the usage
 // and nominal quota of its flavor-resource columns l, l+32 in REGISTERS, so the ordered
 // commit loop (scheduler.go:269-401) touches memory only for the entries themselves.  Entries
-// are sorted with a warp-synchronous bitonic network over packed keys in shared memory and
-// expanded 32 at a time into a dense request matrix (one lane per entry).
-// Roots with more than KB_LONE_CAP entries, or with preemption targets in play, are left
+// arrive in iterator order (k_rank) and are expanded 32 at a time into a dense request matrix
+// (one lane per entry).
+// Roots with more than KB_RANK_CAP entries, or with preemption targets in play, are left
 // to the general kernel.
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(KB_LONE_WARPS * 32) k_admit_lone(DevSnap D) {
@@ -913,74 +1000,61 @@ __global__ void __launch_bounds__(KB_LONE_WARPS * 32) k_admit_lone(DevSnap D) {
   if (slot >= D.nLone) return;
   int off = D.root_offset[slot];
   int n = D.root_offset[slot + 1] - off;
-  if (n == 0 || n > KB_LONE_CAP) return;
-  int32_t *ent = D.root_entries + off;
+  if (n == 0 || n > KB_RANK_CAP) return;
+  const int32_t *order = D.sorted + off;  // iterator order from k_rank
   int cq = D.lone_cqs[slot];
-  // per-warp shared memory: keys (KB_LONE_CAP x 20 B) | dense request chunk (32 x FR x 8 B)
-  size_t per_warp = (size_t)KB_LONE_CAP * 20 + (size_t)32 * FR * 8;
-  unsigned char *base = smem_raw + (size_t)warp * per_warp;
-  u64 *k0 = (u64 *)base, *k1 = k0 + KB_LONE_CAP;
-  int *kidx = (int *)(k1 + KB_LONE_CAP);
-  i64 *qm = (i64 *)(base + (size_t)KB_LONE_CAP * 20);
-  // ---- sort (classical iterator order) ----
-  int np2 = 1;
-  while (np2 < n) np2 <<= 1;
-  for (int i = lane; i < np2; i += 32) {
-    if (i < n) { int e = ent[i]; entry_key(D, e, &k0[i], &k1[i]); kidx[i] = e; }
-    else { k0[i] = ~0ull; k1[i] = ~0ull; kidx[i] = INT32_MAX; }
-  }
-  __syncwarp();
-  for (int k = 2; k <= np2; k <<= 1)
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int i = lane; i < np2; i += 32) {
-        int l = i ^ j;
-        if (l > i) {
-          u64 a0 = k0[i], a1 = k1[i], b0 = k0[l], b1 = k1[l];
-          int ai = kidx[i], bi = kidx[l];
-          int aw = ai, bw = bi;  // canonical tie-break: position in the cycle's entry list
-          bool up = (i & k) == 0;
-          bool sw = up ? key_less(b0, b1, bw, a0, a1, aw) : key_less(a0, a1, aw, b0, b1, bw);
-          if (sw) { k0[i] = b0; k1[i] = b1; kidx[i] = bi; k0[l] = a0; k1[l] = a1; kidx[l] = ai; }
-        }
-      }
-      __syncwarp();
-    }
-  // ---- the CQ's row in registers (two columns per lane: FR <= 64; more columns loop through memory) ----
+  // per-warp shared memory: dense request chunk (32 x FR x 8 B)
+  i64 *qm = (i64 *)(smem_raw + (size_t)warp * 32 * FR * 8);
+  // ---- the CQ's row in registers (two columns per lane: FR <= 64) ----
   const bool two = FR > 32;
-  int c0 = lane, c1 = lane + 32;
+  const int c0 = lane, c1 = lane + 32;
   i64 u0 = 0, u1 = 0, nom0 = 0, nom1 = 0;
   if (c0 < FR) { u0 = D.usage[(size_t)cq * FR + c0]; nom0 = D.subtree[(size_t)cq * FR + c0]; }
   if (two && c1 < FR) { u1 = D.usage[(size_t)cq * FR + c1]; nom1 = D.subtree[(size_t)cq * FR + c1]; }
-  bool reserve_ok = D.cq_reclaim_within[cq] != KB_POLICY_ANY;  // !CanAlwaysReclaim policy.go:27-29
+  const bool reserve_ok = D.cq_reclaim_within[cq] != KB_POLICY_ANY;  // !CanAlwaysReclaim policy.go:27-29
   // ---- chunks of 32 entries: expand (lane = entry), then commit in order (lane = column) ----
   for (int basei = 0; basei < n; basei += 32) {
     int cn = min(32, n - basei);
     for (int c = lane; c < cn * FR; c += 32) qm[c] = -1;
     __syncwarp();
-    int my_e = lane < cn ? kidx[basei + lane] : -1;
-    int my_mode = 0;
+    int my_e = lane < cn ? order[basei + lane] : -1;
+    int my_mode = 0, my_dec = 0;
     if (my_e >= 0) { expand_entry(D, my_e, qm + (size_t)lane * FR); my_mode = D.mode[my_e]; }
     __syncwarp();
-    for (int j = 0; j < cn; j++) {
-      int e = __shfl_sync(0xffffffffu, my_e, j), mode = __shfl_sync(0xffffffffu, my_mode, j);
-      const i64 *qrow = qm + (size_t)j * FR;
-      i64 q0 = c0 < FR ? qrow[c0] : -1, q1 = (two && c1 < FR) ? qrow[c1] : -1;
-      int dec;
-      if (mode == KB_MODE_NOFIT) dec = KB_DEC_NOFIT;
-      else if (mode == KB_MODE_PREEMPT) {  // Preempt without targets (targets exclude this kernel): :303-318
-        dec = KB_DEC_PREEMPT_NO_TARGETS;
-        if (reserve_ok) {  // quotaResourcesToReserve :530-548 with Borrowing == 0 (no cohort)
-          if (q0 >= 0) u0 += imax(0, imin(q0, nom0 - u0));
-          if (q1 >= 0) u1 += imax(0, imin(q1, nom1 - u1));
-        }
-      } else {
-        bool ok = !(q0 > 0 && imax(0, nom0 - u0) < q0) && !(q1 > 0 && imax(0, nom1 - u1) < q1);  // Fits :121-136
-        ok = __all_sync(0xffffffffu, ok);
-        if (ok) { if (q0 > 0) u0 += q0; if (q1 > 0) u1 += q1; }
-        dec = ok ? KB_DEC_ASSUMED : KB_DEC_SKIPPED_NO_FIT;
+    for (int jb = 0; jb < cn; jb += 8) {
+      // batch the state-independent loads of 8 entries, then walk them with a short dependent chain
+      i64 q0[8], q1[8]; int md[8];
+#pragma unroll
+      for (int t = 0; t < 8; t++) {
+        int j = jb + t;
+        bool in = j < cn;
+        md[t] = __shfl_sync(0xffffffffu, my_mode, j & 31);
+        q0[t] = (in && c0 < FR) ? qm[(size_t)j * FR + c0] : -1;
+        q1[t] = (in && two && c1 < FR) ? qm[(size_t)j * FR + c1] : -1;
+        if (!in) md[t] = -1;
       }
-      if (lane == 0) { D.decision[e] = (uint8_t)dec; D.rank[e] = basei + j; }
+#pragma unroll
+      for (int t = 0; t < 8; t++) {
+        int mode = md[t];
+        if (mode < 0) break;
+        int dec;
+        if (mode == KB_MODE_NOFIT) dec = KB_DEC_NOFIT;
+        else if (mode == KB_MODE_PREEMPT) {  // Preempt without targets (entries with targets never reach this kernel): :303-318
+          dec = KB_DEC_PREEMPT_NO_TARGETS;
+          if (reserve_ok) {  // quotaResourcesToReserve :530-548 with Borrowing == 0 (no cohort)
+            if (q0[t] >= 0) u0 += imax(0, imin(q0[t], nom0 - u0));
+            if (q1[t] >= 0) u1 += imax(0, imin(q1[t], nom1 - u1));
+          }
+        } else {
+          bool ok = !(q0[t] > 0 && imax(0, nom0 - u0) < q0[t]) && !(q1[t] > 0 && imax(0, nom1 - u1) < q1[t]);  // Fits :121-136
+          ok = __all_sync(0xffffffffu, ok);
+          if (ok) { if (q0[t] > 0) u0 += q0[t]; if (q1[t] > 0) u1 += q1[t]; }
+          dec = ok ? KB_DEC_ASSUMED : KB_DEC_SKIPPED_NO_FIT;
+        }
+        if (lane == jb + t) my_dec = dec;
+      }
     }
+    if (my_e >= 0) { D.decision[my_e] = (uint8_t)my_dec; D.rank[my_e] = basei + lane; }
     __syncwarp();
   }
   if (c0 < FR) D.usage[(size_t)cq * FR + c0] = u0;
@@ -1041,6 +1115,7 @@ __global__ void __launch_bounds__(128) k_admit_fair(DevSnap D, int slot_base, in
   if (n == 0) return;
   int32_t *ent = D.root_entries + off;
   int t = slot - D.nLone;
+  if (D.tree_flat[t]) return;  // flat cohorts: the pop order is a static key order -> k_rank + k_admit
   const int32_t *nodes = D.tree_nodes + D.tree_start[t];
   int nn = D.tree_start[t + 1] - D.tree_start[t];
   const int32_t *lvl = D.tree_level + (size_t)t * KB_LEVELS;
@@ -1049,12 +1124,13 @@ __global__ void __launch_bounds__(128) k_admit_fair(DevSnap D, int slot_base, in
   Tab<kSmemTables> T;
   unsigned char *p = stage_tables<kSmemTables>(D, T, smem_raw, nodes, nn);
   int *s_path = (int *)p; p += (KB_MAX_DEPTH + 2) * 4;
+  int *s_npre = (int *)p; p += 8;
+  if (threadIdx.x == 0) *s_npre = 0;
   // tree index arrays in LOCAL node ids (always shared memory): children CSR, waiting slot of a CQ, winner of a cohort
   int *s_cstart = (int *)p; p += (size_t)(nn + 1) * 4;
   int *s_child = (int *)p; p += (size_t)nn * 4;
   int *s_slot = (int *)p; p += (size_t)nn * 4;
   int *s_winner = (int *)p; p += (size_t)nn * 4;
-  int *s_order = (int *)p; p += (size_t)(state_in_smem ? 128 : 0) * 4;  // flat-cohort order (n <= 128 when used)
   p = (unsigned char *)(((uintptr_t)p + 15) & ~(uintptr_t)15);
   FsState F;
   F.nlev = nlev > 1 ? nlev - 1 : 1;  // a CQ at depth d has d path levels; d <= nlev-1
@@ -1141,41 +1217,6 @@ __global__ void __launch_bounds__(128) k_admit_fair(DevSnap D, int slot_base, in
     }
   };
 
-  if (nlev == 2 && state_in_smem && n <= 128) {
-    // ---- flat cohort: the DRS of a ClusterQueue only depends on its own usage, which only its own entry changes,
-    //      so every pop of the tournament sees the same keys: the pop sequence is the order of
-    //      (entryComparer.less, child position) — sort once, then commit in that order.
-    compute_drs();
-    for (int i = threadIdx.x; i < 128; i += blockDim.x) s_order[i] = i < n ? i : -1;
-    __syncthreads();
-    auto before = [&](int a, int b) {  // a pops before b
-      if (a < 0) return false;
-      if (b < 0) return true;
-      if (fs_less(D, F, a, b, 0)) return true;
-      if (fs_less(D, F, b, a, 0)) return false;
-      return F.e_cq[a] < F.e_cq[b];  // candidates are the child CQs in ascending order; the earlier one keeps ties
-    };
-    for (int k = 2; k <= 128; k <<= 1)
-      for (int j = k >> 1; j > 0; j >>= 1) {
-        int i = threadIdx.x, l = i ^ j;
-        if (l > i) {
-          int a = s_order[i], b = s_order[l];
-          bool up = (i & k) == 0;
-          if (up ? before(b, a) : before(a, b)) { s_order[i] = b; s_order[l] = a; }
-        }
-        __syncthreads();
-      }
-    if (warp == 0)
-      for (int it = 0; it < n; it++) {
-        int w = s_order[it];
-        int we = F.e_id[w], md = F.e_mode[w];
-        commit_entry<kSmemTables>(D, T, s_path, lane, we, T.handle(F.e_cq[w]), md & 0xff, md >> 8, D.q_scratch + (size_t)we * FR, it);
-      }
-    __syncthreads();
-    publish_usage<kSmemTables>(D, T, nodes, nn);
-    return;
-  }
-
   for (int it = 0; it < n; it++) {
     compute_drs();  // (1)
     __syncthreads();
@@ -1211,7 +1252,8 @@ __global__ void __launch_bounds__(128) k_admit_fair(DevSnap D, int slot_base, in
     int wcq = F.e_cq[w], we = F.e_id[w];
     if (warp == 0) {
       int md = F.e_mode[w];
-      commit_entry<kSmemTables>(D, T, s_path, lane, we, T.handle(wcq), md & 0xff, md >> 8, D.q_scratch + (size_t)we * FR, it);
+      commit_entry<kSmemTables>(D, T, s_path, lane, we, T.handle(wcq), md & 0xff, md >> 8, D.q_scratch + (size_t)we * FR, it,
+                                wcq, slot, D.tgt_cnt[we], D.tgt_off[we], s_npre);
       __syncwarp();
       if (lane == 0) {
         int dec = D.decision[we];  // every branch that may have touched the tree's usage
