@@ -3,9 +3,11 @@
 
     python bench.py --gpus N --steps K --warmup W [--config 2] [--impl reference]
 
-One "step" = one pass of the hot path (tree pass -> nominate -> group -> ordered
-admit) over one synthetic snapshot of BASELINE.json's configuration, every pending
-workload evaluated as an entry of the cycle (the north star's batched evaluator).
+One "step" = one scheduling cycle (tree pass -> nominate [+ target search] -> group ->
+order -> admit) over one synthetic snapshot of a BASELINE.json configuration.  Default
+workload = cfg3, the configuration the north star's target is quoted on (1M pending x 10k
+ClusterQueues, flat cohorts, DRF fair sharing): one reference cycle = the 10k queue heads.
+cfg2 / cfg4 evaluate every pending workload as an entry (the batched evaluator).
 `value` = decisions/sec with the snapshot already resident in HBM (device time from
 CUDA events on the library's launching stream, L2 flushed between steps); `e2e` =
 the same metric through the reference-facing C-ABI call kb_run_cycle with host
@@ -37,13 +39,13 @@ WORKLOADS = {
     1: "cfg1: 100 pending x 10 CQ x 2 flavors x 3 resources",
     2: "cfg2: 100k pending x 1k ClusterQueues x 8 flavors x 4 resources, StrictFIFO, no borrowing",
     3: "cfg3: 1M pending x 10k ClusterQueues, BestEffortFIFO + flat cohorts + DRF fair sharing",
-    4: "cfg4: 1M pending x 10k ClusterQueues, depth-4 hierarchical cohorts (classical order)",
+    4: "cfg4: 1M pending x 10k ClusterQueues, depth-4 hierarchical cohorts + within-cohort/reclaim preemption, 200k admitted",
 }
 
 
 # cfg3 runs the fair-sharing iterator, which holds one entry per ClusterQueue
 # (fair_sharing_iterator.go:52-54): its step is one reference cycle over the Q heads.
-HEADS = {1: "all", 2: "all", 3: "one_per_cq", 4: "all"}
+HEADS = {1: "all", 2: "all", 3: "one_per_cq", 4: "one_per_cq"}
 
 
 def algorithmic_bytes(snap) -> dict:
@@ -142,7 +144,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", type=int, default=2)
+    ap.add_argument("--config", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -205,6 +207,9 @@ def main():
     ev.set_profile(False)
 
     # ---- end-to-end through the C-ABI with host buffers (e2e) ----
+    # steady state of the controller: ClusterQueue / Cohort specs do not change between cycles, so the shim keeps
+    # static_generation constant and only usage + entries + admitted workloads cross PCIe every cycle.
+    snap.static_generation = 1
     for _ in range(2):
         ev.run_cycle(snap, out)
     barrier()
@@ -246,7 +251,9 @@ def main():
             "config": {"workload": WORKLOADS[args.config], "heads": "all pending workloads (batched evaluator)" if HEADS[args.config] == "all" else "one head per ClusterQueue (reference cycle)",
                        "decisions_per_step_per_gpu": snap.n_heads, "l2": "512 MiB flush buffer written between timed steps",
                        "timing": "CUDA events on the library stream around the cycle's kernels, summed over steps, max over ranks",
-                       "wall_ms_per_step_incl_flush": wall_ms / args.steps},
+                       "wall_ms_per_step_incl_flush": wall_ms / args.steps,
+                       "e2e_static_tables": "quota / policy / topology tables uploaded once (static_generation constant), "
+                                            "usage + entries + admitted workloads copied every step"},
             "clocks": clocks,
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches,

@@ -178,6 +178,15 @@ typedef struct kb_snapshot {
   const int32_t *heads;        /* [n_heads] indices into the pending tables.
                                   Reference mode: one per CQ (manager.go:770-794);
                                   batched mode: any subset, e.g. all of them.            */
+
+  /* ---- upload hint ---- */
+  int64_t static_generation;   /* 0 = none.  When non-zero and equal to the value of the previous call on
+                                  this handle (with unchanged n_cq/n_cohort/n_flavor/n_resource/n_rg), the
+                                  STATIC tables — parent, fair_weight, nominal, borrow_limit, lend_limit, all
+                                  cq_* policy tables and the resource-group tables — are not read again: the
+                                  device copies and the cohort topology derived from them are reused.  The Go
+                                  shim bumps it whenever a ClusterQueue / Cohort spec changes (the event that
+                                  increments AllocatableResourceGeneration, clusterqueue_snapshot.go:51-53). */
 } kb_snapshot;
 
 /* ------------------------------------------------------------------------

@@ -68,6 +68,7 @@ class kb_snapshot(C.Structure):
         ("adm_qr_ts", _P(C.c_int64)), ("adm_uid", _P(C.c_int64)), ("adm_evicted", _P(C.c_uint8)),
         ("adm_use_start", _P(C.c_int32)), ("adm_use_fr", _P(C.c_int32)), ("adm_use_qty", _P(C.c_int64)),
         ("heads", _P(C.c_int32)),
+        ("static_generation", C.c_int64),
     ]
 
 
@@ -140,6 +141,7 @@ class FlatSnapshot:
     pods_resource: int = -1
     flags: int = FLAGS_DEFAULT
     now_ns: int = 0
+    static_generation: int = 0
     arrays: dict = field(default_factory=dict)
 
     def __getattr__(self, name):
@@ -233,6 +235,7 @@ class FlatSnapshot:
         s.n_adm_use = len(self.arrays["adm_use_fr"])
         s.n_heads = self.n_heads
         s.pods_resource, s.flags, s.now_ns = self.pods_resource, self.flags, self.now_ns
+        s.static_generation = self.static_generation
         for name in ARRAY_FIELDS:
             arr = self.arrays[name]
             setattr(s, name, _ptr(arr, _CT[_DT[name]]))

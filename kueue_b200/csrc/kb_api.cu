@@ -44,7 +44,10 @@ struct kb_handle {
   int sm_count = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr, ev4 = nullptr, ev5 = nullptr;
-  Arena arena;
+  Arena arena;   // per-cycle tables, scratch, outputs
+  Arena sarena;  // static tables (quotas, policies, topology): kept while kb_snapshot.static_generation is unchanged
+  int64_t static_gen = 0;
+  int s_dims[6] = {-1, -1, -1, -1, -1, -1};
   DevSnap D{};
   bool uploaded = false;
   bool profile = false;
@@ -122,6 +125,7 @@ void kb_destroy(kb_handle *h) {
   if (!h) return;
   cudaSetDevice(h->device);
   if (h->arena.base) cudaFree(h->arena.base);
+  if (h->sarena.base) cudaFree(h->sarena.base);
   if (h->host_words) cudaFreeHost(h->host_words);
   if (h->stream) cudaStreamDestroy(h->stream);
   if (h->ev0) cudaEventDestroy(h->ev0);
@@ -139,7 +143,8 @@ void kb_destroy(kb_handle *h) {
 // ---------------------------------------------------------------------------
 // validation + static topology
 // ---------------------------------------------------------------------------
-static int32_t build_topology(kb_handle *h, const kb_snapshot *s) {
+// static part: validation of the node tables + everything derived from the cohort forest alone
+static int32_t build_static(kb_handle *h, const kb_snapshot *s) {
   int Q = s->n_cq, C = s->n_cohort, N = Q + C;
   if (Q < 0 || C < 0 || s->n_flavor < 1 || s->n_flavor > KB_MAX_FLAVORS || s->n_resource < 1 ||
       s->n_resource > KB_MAX_RESOURCES || s->n_wl < 0 || s->n_podset < 0 || s->n_adm < 0 || s->n_heads < 0)
@@ -229,6 +234,17 @@ static int32_t build_topology(kb_handle *h, const kb_snapshot *s) {
     h->max_tree_nodes = std::max(h->max_tree_nodes, nn);
     for (int i = 0; i < nn; i++) h->local_idx[h->tree_nodes[h->tree_start[t] + i]] = i;
   }
+  h->D.nTrees = ntrees;
+  h->D.nLone = (int)h->lone.size();
+  h->D.nRoots = nroots;
+  return KB_OK;
+}
+
+// per-cycle part: admitted workloads (grouping, candidate pre-order) and bounds checks of the entry tables
+static int32_t build_dynamic(kb_handle *h, const kb_snapshot *s) {
+  int Q = s->n_cq;
+  int nroots = h->D.nRoots;
+  if (s->n_wl < 0 || s->n_podset < 0 || s->n_adm < 0 || s->n_heads < 0) return fail(h, KB_ERR_INVALID, "bad dimensions");
   // admitted workloads grouped by CQ (ClusterQueueSnapshot.Workloads)
   h->cq_adm_start.assign(Q + 1, 0);
   for (int a = 0; a < s->n_adm; a++) {
@@ -285,15 +301,12 @@ static int32_t build_topology(kb_handle *h, const kb_snapshot *s) {
       if (s->parent[q] < 0 && s->cq_within_cq[q] != KB_POLICY_NEVER && h->cq_adm_start[q + 1] > h->cq_adm_start[q]) any = true;
     h->D.lone_fast = !any && s->n_flavor * s->n_resource <= 64;
   }
-  h->D.nTrees = ntrees;
-  h->D.nLone = (int)h->lone.size();
-  h->D.nRoots = nroots;
   return KB_OK;
 }
 
 template <typename T>
-static cudaError_t up(kb_handle *h, const T *&dst, const T *src, size_t n, int64_t *bytes) {
-  T *d = h->arena.take<T>(n);
+static cudaError_t up(kb_handle *h, Arena &arena, const T *&dst, const T *src, size_t n, int64_t *bytes) {
+  T *d = arena.take<T>(n);
   dst = d;
   if (n == 0) return cudaSuccess;
   *bytes += (int64_t)(n * sizeof(T));
@@ -304,29 +317,64 @@ static int32_t upload_impl(kb_handle *h, const kb_snapshot *s, bool sync) {
   if (!h || !s) return KB_ERR_INVALID;
   cudaSetDevice(h->device);
   h->uploaded = false;
-  int32_t rc = build_topology(h, s);
-  if (rc != KB_OK) return rc;
   DevSnap &D = h->D;
   int Q = s->n_cq, C = s->n_cohort, N = Q + C, F = s->n_flavor, R = s->n_resource, FR = F * R;
+  size_t NF = (size_t)N * FR, P = (size_t)s->n_podset, W = (size_t)s->n_wl, A = (size_t)s->n_adm, H = (size_t)s->n_heads;
+  int n_rg_fl = (s->n_rg > 0 && s->rg_flavor_start) ? s->rg_flavor_start[s->n_rg] : 0;
+  int dims[6] = {Q, C, F, R, s->n_rg, n_rg_fl};
+  bool reuse = s->static_generation != 0 && s->static_generation == h->static_gen && memcmp(dims, h->s_dims, sizeof(dims)) == 0;
+  int64_t bytes = 0;
+  CUDA_TRY(h, cudaEventRecord(h->ev0, h->stream));
+  int32_t rc;
+  if (!reuse) {
+    h->static_gen = 0;
+    rc = build_static(h, s);
+    if (rc != KB_OK) return rc;
+    size_t stot = 0;
+    auto sneed = [&](size_t n, size_t sz) { stot += pad256(n * sz); };
+    sneed(N, 4); sneed(N, 8); sneed(NF, 8); sneed(NF, 8); sneed(NF, 8);
+    for (int k = 0; k < 4; k++) sneed(Q, 1);
+    sneed(Q, 4); for (int k = 0; k < 4; k++) sneed(Q, 1); sneed(Q, 8);
+    sneed(Q + 1, 4); sneed(s->n_rg, 4); sneed(s->n_rg + 1, 4); sneed(n_rg_fl, 4);
+    sneed(N, 4); sneed(N, 4); sneed(N, 4); sneed(D.nTrees + 1, 4); sneed(h->tree_nodes.size(), 4); sneed(h->tree_level.size(), 4);
+    sneed(h->lone.size(), 4); sneed(N, 4); sneed(h->tree_flat.size(), 1); sneed(N + 1, 4); sneed(h->child_list.size(), 4);
+    if (!h->sarena.reserve(stot + 4096)) return fail(h, KB_ERR_CUDA, "cudaMalloc failed");
+    h->sarena.reset();
+#define SUP(field, src, n) CUDA_TRY(h, up(h, h->sarena, D.field, src, (size_t)(n), &bytes))
+    SUP(parent, s->parent, N); SUP(fair_weight, s->fair_weight, N);
+    SUP(nominal, (const i64 *)s->nominal, NF); SUP(blimit, (const i64 *)s->borrow_limit, NF); SUP(llimit, (const i64 *)s->lend_limit, NF);
+    SUP(cq_within_cq, s->cq_within_cq, Q); SUP(cq_reclaim_within, s->cq_reclaim_within, Q); SUP(cq_borrow_within, s->cq_borrow_within, Q);
+    SUP(cq_has_bwc_threshold, s->cq_has_bwc_threshold, Q); SUP(cq_bwc_threshold, s->cq_bwc_threshold, Q);
+    SUP(cq_when_can_borrow, s->cq_when_can_borrow, Q); SUP(cq_when_can_preempt, s->cq_when_can_preempt, Q);
+    SUP(cq_preference, s->cq_preference, Q); SUP(cq_strategy, s->cq_strategy, Q); SUP(cq_generation, (const i64 *)s->cq_generation, Q);
+    SUP(cq_rg_start, s->cq_rg_start, Q + 1); SUP(rg_res_mask, s->rg_res_mask, s->n_rg); SUP(rg_flavor_start, s->rg_flavor_start, s->n_rg + 1);
+    SUP(rg_flavors, s->rg_flavors, n_rg_fl);
+    SUP(root_slot, h->root_slot.data(), N); SUP(depth, h->depth.data(), N); SUP(height, h->height.data(), N);
+    SUP(tree_start, h->tree_start.data(), D.nTrees + 1); SUP(tree_nodes, h->tree_nodes.data(), h->tree_nodes.size());
+    SUP(tree_level, h->tree_level.data(), h->tree_level.size()); SUP(lone_cqs, h->lone.data(), h->lone.size());
+    SUP(local_idx, h->local_idx.data(), N);
+    SUP(tree_flat, h->tree_flat.data(), h->tree_flat.size());
+    SUP(child_start, h->child_start.data(), N + 1); SUP(child_list, h->child_list.data(), h->child_list.size());
+#undef SUP
+    memcpy(h->s_dims, dims, sizeof(dims));
+    h->static_gen = s->static_generation;
+  }
+  rc = build_dynamic(h, s);
+  if (rc != KB_OK) return rc;
   D.Q = Q; D.C = C; D.N = N; D.F = F; D.R = R; D.FR = FR; D.W = s->n_wl; D.P = s->n_podset; D.A = s->n_adm;
   D.AU = s->n_adm_use; D.H = s->n_heads; D.NRG = s->n_rg; D.pods_res = s->pods_resource; D.flags = s->flags; D.now_ns = s->now_ns;
-  size_t NF = (size_t)N * FR, P = (size_t)s->n_podset, W = (size_t)s->n_wl, A = (size_t)s->n_adm, H = (size_t)s->n_heads;
-  int ntrees = D.nTrees, nroots = D.nRoots;
-  // exact arena size
+  int nroots = D.nRoots;
+  // exact size of the per-cycle arena
   size_t tot = 0;
   auto need = [&](size_t n, size_t sz) { tot += pad256(n * sz); };
-  need(N, 4); need(N, 8); need(NF, 8); need(NF, 8); need(NF, 8); need((size_t)Q * FR, 8);
-  for (int k = 0; k < 4; k++) need(Q, 1);
-  need(Q, 4); for (int k = 0; k < 4; k++) need(Q, 1); need(Q, 8);
-  need(Q + 1, 4); need(s->n_rg, 4); need(s->n_rg + 1, 4); need(s->n_rg ? s->rg_flavor_start[s->n_rg] : 0, 4);
+  need((size_t)Q * FR, 8);
   need(W, 4); need(W, 4); need(W, 8); need(W, 8); need(W, 8); need(W + 1, 4);
   need(P * R, 8); need(P, 4); need(P, 4); need(P, 4); need(P, 8); need(P * R, 1);
   need(A, 4); need(A, 4); need(A, 8); need(A, 8); need(A, 8); need(A, 1); need(A + 1, 4); need(s->n_adm_use, 4); need(s->n_adm_use, 8);
   need(H, 4);
-  need(N, 4); need(N, 4); need(N, 4); need(ntrees + 1, 4); need(h->tree_nodes.size(), 4); need(h->tree_level.size(), 4);
-  need(h->lone.size(), 4); need(Q + 1, 4); need(h->cq_adm.size(), 4); need(N, 4); need(N + 1, 4); need(h->child_list.size(), 4);
+  need(Q + 1, 4); need(h->cq_adm.size(), 4);
   need(NF, 8); need(NF, 8); need(NF, 8); need(NF, 8);
-  need(nroots, 4); need(nroots + 1, 4); need(nroots, 4); need(H, 4); need(H, 4); need(H * 4, 8); need(H * 4, 8); need((size_t)Q * R, 8); need((size_t)N * R, 8); need(h->tree_flat.size(), 1);
+  need(nroots, 4); need(nroots + 1, 4); need(nroots, 4); need(H, 4); need(H, 4); need(H * 4, 8); need(H * 4, 8); need((size_t)Q * R, 8); need((size_t)N * R, 8);
   need(H, 1); need(H, 1); need(H, 4); need(H, 4); need(P * R, 1); need(P * R, 1); need(P * R, 1); need(P, 4);
   need(1, 4); need(N, 8); need(N, 4); need(N, 1);
   // preemption: search kernel configuration + scratch
@@ -348,18 +396,8 @@ static int32_t upload_impl(kb_handle *h, const kb_snapshot *s, bool sync) {
   if (fair) { need(H * FR, 8); need(H * (48 + 16 * KB_MAX_DEPTH), 1); need(N, 4); need(N, 4); }
   if (!h->arena.reserve(tot + 4096)) return fail(h, KB_ERR_CUDA, "cudaMalloc failed");
   h->arena.reset();
-  int64_t bytes = 0;
-  CUDA_TRY(h, cudaEventRecord(h->ev0, h->stream));
-#define UP(field, src, n) CUDA_TRY(h, up(h, D.field, src, (size_t)(n), &bytes))
-  UP(parent, s->parent, N); UP(fair_weight, s->fair_weight, N);
-  UP(nominal, (const i64 *)s->nominal, NF); UP(blimit, (const i64 *)s->borrow_limit, NF); UP(llimit, (const i64 *)s->lend_limit, NF);
+#define UP(field, src, n) CUDA_TRY(h, up(h, h->arena, D.field, src, (size_t)(n), &bytes))
   UP(cq_usage, (const i64 *)s->cq_usage, (size_t)Q * FR);
-  UP(cq_within_cq, s->cq_within_cq, Q); UP(cq_reclaim_within, s->cq_reclaim_within, Q); UP(cq_borrow_within, s->cq_borrow_within, Q);
-  UP(cq_has_bwc_threshold, s->cq_has_bwc_threshold, Q); UP(cq_bwc_threshold, s->cq_bwc_threshold, Q);
-  UP(cq_when_can_borrow, s->cq_when_can_borrow, Q); UP(cq_when_can_preempt, s->cq_when_can_preempt, Q);
-  UP(cq_preference, s->cq_preference, Q); UP(cq_strategy, s->cq_strategy, Q); UP(cq_generation, (const i64 *)s->cq_generation, Q);
-  UP(cq_rg_start, s->cq_rg_start, Q + 1); UP(rg_res_mask, s->rg_res_mask, s->n_rg); UP(rg_flavor_start, s->rg_flavor_start, s->n_rg + 1);
-  UP(rg_flavors, s->rg_flavors, s->n_rg ? s->rg_flavor_start[s->n_rg] : 0);
   UP(wl_cq, s->wl_cq, W); UP(wl_priority, s->wl_priority, W); UP(wl_ts, (const i64 *)s->wl_ts, W); UP(wl_uid, (const i64 *)s->wl_uid, W);
   UP(wl_last_gen, (const i64 *)s->wl_last_gen, W); UP(wl_ps_start, s->wl_ps_start, W + 1);
   UP(ps_req, (const i64 *)s->ps_req, P * R); UP(ps_req_mask, s->ps_req_mask, P); UP(ps_count, s->ps_count, P);
@@ -368,13 +406,7 @@ static int32_t upload_impl(kb_handle *h, const kb_snapshot *s, bool sync) {
   UP(adm_qr_ts, (const i64 *)s->adm_qr_ts, A); UP(adm_uid, (const i64 *)s->adm_uid, A); UP(adm_evicted, s->adm_evicted, A);
   UP(adm_use_start, s->adm_use_start, A + 1); UP(adm_use_fr, s->adm_use_fr, s->n_adm_use); UP(adm_use_qty, (const i64 *)s->adm_use_qty, s->n_adm_use);
   UP(heads, s->heads, H);
-  UP(root_slot, h->root_slot.data(), N); UP(depth, h->depth.data(), N); UP(height, h->height.data(), N);
-  UP(tree_start, h->tree_start.data(), ntrees + 1); UP(tree_nodes, h->tree_nodes.data(), h->tree_nodes.size());
-  UP(tree_level, h->tree_level.data(), h->tree_level.size()); UP(lone_cqs, h->lone.data(), h->lone.size());
-  UP(local_idx, h->local_idx.data(), N);
-  UP(tree_flat, h->tree_flat.data(), h->tree_flat.size());
   UP(adm_sorted, h->adm_sorted.data(), h->adm_sorted.size()); UP(root_adm_start, h->root_adm_start.data(), nroots + 1);
-  UP(child_start, h->child_start.data(), N + 1); UP(child_list, h->child_list.data(), h->child_list.size());
   UP(cq_adm_start, h->cq_adm_start.data(), Q + 1); UP(cq_adm, h->cq_adm.data(), h->cq_adm.size());
 #undef UP
   D.subtree = h->arena.take<i64>(NF); D.usage = h->arena.take<i64>(NF);
@@ -513,7 +545,11 @@ static int32_t cycle_enqueue(kb_handle *h) {
   int32_t rc_admit = KB_OK;
   launch_tree(h, &launches);
   if (D.H) {
-    kmark(h, KB_K_NOMINATE); k_nominate<<<(D.H + 127) / 128, 128, 0, h->stream>>>(D); launches++;
+    kmark(h, KB_K_NOMINATE);
+    // few entries: latency-bound -> KB_NG lanes per entry; many entries: throughput-bound -> one thread per entry
+    if ((size_t)D.H * KB_NG <= (size_t)h->sm_count * 2048) k_nominate_coop<<<(int)(((size_t)D.H * KB_NG + 127) / 128), 128, 0, h->stream>>>(D);
+    else k_nominate<<<(D.H + 127) / 128, 128, 0, h->stream>>>(D);
+    launches++;
     if (D.A) {  // target search for the entries k_nominate deferred
       kmark(h, KB_K_PREEMPT);
       if (h->search_smem) {

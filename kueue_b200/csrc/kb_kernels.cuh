@@ -381,6 +381,237 @@ __device__ inline int get_assignments(const DevSnap &D, Oracle &orc, int wl, int
   return mode;
 }
 
+// ---------------------------------------------------------------------------
+// K2 (cooperative form): KB_NG lanes per entry.  Every lane runs the same (scalar) flavor
+// assignment control flow on register state; the flavors of a resource group are evaluated
+// one per lane (each lane walks the resources of "its" flavor), and a short ordered scan with
+// shuffles applies the selection rules of findFlavorForPodSets (:794-897) exactly as the
+// sequential loop would.  This cuts the dependent-load chain of one entry by ~KB_NG and keeps
+// the lanes of a warp converged.  Lane 0 of the group is the single writer of the output rows.
+// Cells that would need the preemption oracle are only *flagged* (when the scan reaches them):
+// the entry is then re-evaluated by k_nominate_search, like in the thread-per-entry kernel.
+// ---------------------------------------------------------------------------
+#define KB_NG 8
+enum { PM_NEED = 5 };
+
+// fitsResourceQuota :1017-1047 without the oracle call: PM_NEED where SimulatePreemption would run.
+__device__ __forceinline__ int cell_eval(const DevSnap &D, int cq, int fr, i64 assumed, i64 request, int *borrow) {
+  size_t c = (size_t)cq * D.FR + fr;
+  i64 avail = imax(0, D.avail[c]);
+  i64 val = assumed + request;
+  if (val > D.potential[c]) { *borrow = 0; return PM_NOFIT; }
+  bool may_reclaim;
+  int b = find_height(D, D.usage, cq, fr, val, &may_reclaim);
+  *borrow = b;
+  if (val <= avail) return PM_FIT;
+  bool can_pwb = D.cq_borrow_within[cq] != KB_POLICY_NEVER ||
+                 ((D.flags & KB_F_FAIR_SHARING) && D.cq_reclaim_within[cq] != KB_POLICY_NEVER);
+  if (val <= D.nominal[c] || may_reclaim || can_pwb) return PM_NEED;
+  return PM_NOFIT;
+}
+
+__device__ inline int assign_workload_coop(const DevSnap &D, bool *need_search, int wl, const int32_t *counts, int *borrowing_out,
+                                           unsigned gmask, int gbase, int glane) {
+  const int R = D.R;
+  int cq = D.wl_cq[wl];
+  int ps0 = D.wl_ps_start[wl], ps1 = D.wl_ps_start[wl + 1];
+  i64 lg = D.wl_last_gen[wl];
+  bool use_last = lg >= 0 && !(D.cq_generation[cq] > lg);
+  bool fung = D.flags & KB_F_FLAVOR_FUNGIBILITY;
+  bool covers_pods = D.pods_res >= 0 && rg_by_resource(D, cq, D.pods_res) >= 0;
+  int pref = D.cq_preference[cq];
+  int wcb = D.cq_when_can_borrow[cq], wcp = D.cq_when_can_preempt[cq];
+  bool cand_possible = candidates_possible(D, cq);
+  int borrowing = 0, rep = KB_MODE_FIT;
+  if (ps1 == ps0) rep = KB_MODE_NOFIT;
+  bool stop = false;
+  for (int row = ps0; row < ps1; row++) {
+    int8_t *oflv = D.ps_flavor + (size_t)row * R;
+    int8_t *omode = D.ps_res_mode + (size_t)row * R;
+    int8_t *otried = D.ps_tried + (size_t)row * R;
+    int full = D.ps_count[row];
+    int count = (counts && full != 0) ? counts[row - ps0] : full;
+    if (glane == 0) {
+      for (int r = 0; r < R; r++) { oflv[r] = -1; omode[r] = -1; otried[r] = -1; }
+      D.ps_count_out[row] = stop ? full : count;
+    }
+    if (stop) continue;
+    uint32_t mask = D.ps_req_mask[row];
+    if (covers_pods) mask |= 1u << D.pods_res;
+    u64 ok = D.ps_flavor_ok[row];
+    bool has_reasons = false, failed = false;
+    int ps_borrow = 0;
+    uint32_t assigned = 0, ps_pmask = 0;  // resources with a flavor / with Mode == Preempt in this podset
+    for (int r0 = 0; r0 < R; r0++) {
+      if (!(mask & (1u << r0))) continue;
+      if (assigned & (1u << r0)) continue;
+      int g = rg_by_resource(D, cq, r0);
+      if (g < 0) {
+        if (ps_request(D, row, r0, count, covers_pods) == 0) continue;
+        has_reasons = true; failed = true; break;
+      }
+      uint32_t rgm = D.rg_res_mask[g] & mask;
+      int fl0 = D.rg_flavor_start[g], nfl = D.rg_flavor_start[g + 1] - fl0;
+      int best_f = -1, best_pm = PM_NOFIT, best_rb = INT32_MAX, best_maxb = 0;
+      uint32_t best_pmask = 0;
+      bool any_reason = false;
+      int attempted = -1;
+      int idx0 = 0;
+      if (fung && use_last) idx0 = D.ps_last_tried[(size_t)row * R + r0] + 1;
+      bool done = false;
+      for (int base = idx0; base < nfl && !done; base += KB_NG) {
+        // ---- one flavor per lane ----
+        int idx = base + glane;
+        u64 res = 0;  // [0..2] rpm [3..9] rb [10..16] maxb [17] any_reason [18] need [19] eligible [32..47] pmask
+        int myf = -1;
+        if (idx < nfl) {
+          int f = D.rg_flavors[fl0 + idx];
+          myf = f;
+          if ((ok >> f) & 1) {
+            int rpm = PM_FIT, rb = 0, maxb = 0; uint32_t pmask = 0; bool reason = false, need = false;
+            for (int r = 0; r < R; r++) {
+              if (!(rgm & (1u << r))) continue;
+              i64 assumed = 0;
+              for (int prow = ps0; prow < row; prow++)
+                if (D.ps_flavor[(size_t)prow * R + r] == f) assumed += ps_request(D, prow, r, D.ps_count_out[prow], covers_pods);
+              int b;
+              int pm = cell_eval(D, cq, f * R + r, assumed, ps_request(D, row, r, count, covers_pods), &b);
+              if (pm == PM_NEED) { pm = PM_NOCAND; b = 0; need = need || cand_possible; }  // what the deferring oracle returns
+              if (pm != PM_FIT) reason = true;
+              if (gm_preferred(rpm, rb, pm, b, pref)) { rpm = pm; rb = b; }
+              if (rpm == PM_NOFIT) break;
+              if (fa_mode(pm) == KB_MODE_PREEMPT) pmask |= 1u << r;
+              if (b > maxb) maxb = b;
+            }
+            res = (u64)rpm | ((u64)(rb & 127) << 3) | ((u64)(maxb & 127) << 10) | ((u64)reason << 17) | ((u64)need << 18) | (1ull << 19) |
+                  ((u64)pmask << 32);
+          }
+        }
+        // ---- ordered scan over the KB_NG flavors of this round ----
+        for (int j = 0; j < KB_NG && base + j < nfl; j++) {
+          u64 rj = __shfl_sync(gmask, res, gbase + j);
+          int fj = __shfl_sync(gmask, myf, gbase + j);
+          attempted = base + j;
+          if (!((rj >> 19) & 1)) { any_reason = true; continue; }  // checkFlavorForPodSets failed
+          int rpm = (int)(rj & 7), rb = (int)((rj >> 3) & 127), maxb = (int)((rj >> 10) & 127);
+          uint32_t pmask = (uint32_t)(rj >> 32) & 0xffffu;
+          if ((rj >> 17) & 1) any_reason = true;
+          if ((rj >> 18) & 1) *need_search = true;  // the sequential walk would have called SimulatePreemption here
+          bool take = false;
+          if (fung) {
+            bool try_next = rpm == PM_NOFIT || rpm == PM_NOCAND ||
+                            ((rpm == PM_PREEMPT || rpm == PM_RECLAIM) && wcp == KB_FUNG_TRY_NEXT_FLAVOR) ||
+                            (rb != 0 && wcb == KB_FUNG_TRY_NEXT_FLAVOR);
+            if (!try_next) { take = true; done = true; }
+            else if (gm_preferred(rpm, rb, best_pm, best_rb, pref)) take = true;
+          } else if (rpm > best_pm) {
+            take = true;
+            done = rpm == PM_FIT;
+          }
+          if (take) { best_f = fj; best_pm = rpm; best_rb = rb; best_maxb = maxb; best_pmask = pmask; }
+          if (done) break;
+        }
+      }
+      if (best_f < 0) { has_reasons = true; failed = true; break; }
+      int tried = fung ? (attempted == nfl - 1 ? -1 : attempted) : 0;
+      if (glane == 0)
+        for (int r = 0; r < R; r++) {
+          if (!(rgm & (1u << r))) continue;
+          oflv[r] = (int8_t)best_f;
+          omode[r] = (best_pmask >> r) & 1 ? KB_MODE_PREEMPT : KB_MODE_FIT;
+          otried[r] = (int8_t)tried;
+        }
+      assigned |= rgm;
+      ps_pmask |= best_pmask & rgm;
+      if (best_maxb > ps_borrow) ps_borrow = best_maxb;
+      if (best_pm != PM_FIT && any_reason) has_reasons = true;
+    }
+    int psmode;
+    if (failed) {
+      if (glane == 0) for (int r = 0; r < R; r++) { oflv[r] = -1; omode[r] = -1; otried[r] = -1; }
+      psmode = KB_MODE_NOFIT;
+      stop = true;
+    } else {
+      if (ps_borrow > borrowing) borrowing = ps_borrow;
+      psmode = KB_MODE_FIT;
+      if (has_reasons) {
+        if (assigned == 0) psmode = KB_MODE_NOFIT;
+        else if (ps_pmask) psmode = KB_MODE_PREEMPT;
+      }
+    }
+    if (psmode < rep) rep = psmode;
+    __syncwarp(gmask);  // rows written by lane 0 are read by every lane for the next podset's assumed usage
+  }
+  *borrowing_out = borrowing;
+  return rep;
+}
+
+// getInitialAssignments (scheduler.go:584-625) in cooperative form; targets are never produced here (deferred).
+__device__ inline int get_assignments_coop(const DevSnap &D, bool *need_search, int wl, int *borrowing_out, unsigned gmask, int gbase, int glane) {
+  int mode = assign_workload_coop(D, need_search, wl, nullptr, borrowing_out, gmask, gbase, glane);
+  if (mode == KB_MODE_FIT) return mode;
+  if (mode == KB_MODE_PREEMPT && candidates_possible(D, D.wl_cq[wl])) *need_search = true;  // GetTargets might find targets
+  if (!(D.flags & KB_F_PARTIAL_ADMISSION)) return mode;
+  int ps0 = D.wl_ps_start[wl], np = D.wl_ps_start[wl + 1] - ps0;
+  if (np > KB_MAX_PODSETS) return mode;
+  int total = 0; bool can = false;
+  for (int i = 0; i < np; i++) {
+    int mc = D.ps_min_count[ps0 + i], full = D.ps_count[ps0 + i];
+    if (mc >= 0) { total += full - mc; if (full > mc) can = true; }
+  }
+  if (!can || total == 0) return mode;
+  int32_t counts[KB_MAX_PODSETS];
+  auto fill = [&](int i) {
+    for (int k = 0; k < np; k++) {
+      int mc = D.ps_min_count[ps0 + k], full = D.ps_count[ps0 + k];
+      int delta = mc >= 0 ? full - mc : 0;
+      counts[k] = full - (int32_t)((i64)delta * i / total);
+    }
+  };
+  int last_good = -1, lo = 0, hi = total + 1;
+  while (lo < hi) {
+    int mid = lo + (hi - lo) / 2;
+    fill(mid);
+    int b;
+    __syncwarp(gmask);
+    int m = assign_workload_coop(D, need_search, wl, counts, &b, gmask, gbase, glane);
+    bool good = m == KB_MODE_FIT;  // Preempt with targets is only decidable by the search kernel (entry already flagged)
+    if (good) { last_good = mid; hi = mid; } else lo = mid + 1;
+  }
+  __syncwarp(gmask);
+  if (last_good >= 0 && lo == last_good) {
+    fill(last_good);
+    return assign_workload_coop(D, need_search, wl, counts, borrowing_out, gmask, gbase, glane);
+  }
+  return assign_workload_coop(D, need_search, wl, nullptr, borrowing_out, gmask, gbase, glane);
+}
+
+__global__ void __launch_bounds__(128) k_nominate_coop(DevSnap D) {
+  int gid = (blockIdx.x * blockDim.x + threadIdx.x) / KB_NG;
+  int lane = threadIdx.x & 31, glane = lane % KB_NG, gbase = lane - glane;
+  unsigned gmask = (KB_NG == 32 ? 0xffffffffu : ((1u << KB_NG) - 1u)) << gbase;
+  if (gid >= D.H) return;
+  int e = gid;
+  int wl = D.heads[e];
+  bool need_search = false;
+  int borrowing;
+  int mode = get_assignments_coop(D, &need_search, wl, &borrowing, gmask, gbase, glane);
+  if (glane != 0) return;
+  D.mode[e] = (uint8_t)mode;
+  D.borrow[e] = borrowing;
+  D.decision[e] = KB_DEC_NOFIT;
+  D.rank[e] = -1;
+  D.tgt_cnt[e] = 0;
+  D.tgt_off[e] = 0;
+  if (need_search) D.ps_list[atomicAdd(D.ps_n, 1)] = e;
+  {
+    int slot = D.root_slot[D.wl_cq[wl]];
+    unsigned act = __activemask();
+    unsigned m = __match_any_sync(act, slot);
+    if (lane == __ffs(m) - 1) atomicAdd(&D.root_count[slot], __popc(m));
+  }
+}
+
 __global__ void __launch_bounds__(128) k_nominate(DevSnap D) {
   int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= D.H) return;

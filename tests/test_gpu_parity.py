@@ -180,6 +180,25 @@ def test_reference_preemption_scenarios_cycle(ev, tc):
     assert_cycle_equal(got, want)
 
 
+def test_static_generation_reuse(ev):
+    """kb_snapshot.static_generation: unchanged generation => quota/topology tables are not re-read; a bumped
+    generation picks up new quotas."""
+    snap = synth.make_snapshot(3, W=3000, Q=300, heads="one_per_cq")
+    snap.static_generation = 41
+    want = oracle.run_cycle(snap)
+    assert_cycle_equal(ev.run_cycle(snap), want)
+    h2d_full = ev.stats().h2d_bytes
+    # only the usage changes between cycles
+    snap.arrays["cq_usage"][:] = (snap.arrays["cq_usage"] * 0.9).astype(np.int64)
+    want2 = oracle.run_cycle(snap)
+    assert_cycle_equal(ev.run_cycle(snap), want2)
+    assert ev.stats().h2d_bytes < h2d_full - 3 * snap.n_nodes * snap.n_fr * 8 + 1, "static tables were uploaded again"
+    # a spec change comes with a new generation
+    snap.arrays["nominal"][:] = (snap.arrays["nominal"] * 1.5).astype(np.int64)
+    snap.static_generation = 42
+    assert_cycle_equal(ev.run_cycle(snap), oracle.run_cycle(snap))
+
+
 def test_full_size_config2(ev):
     snap = synth.make_snapshot(2)
     got, want = ev.run_cycle(snap), oracle.run_cycle(snap)
