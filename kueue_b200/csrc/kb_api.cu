@@ -62,7 +62,7 @@ struct kb_handle {
   // tree_eval scratch
   i64 *d_drs_rounded = nullptr; int32_t *d_drs_res = nullptr; uint8_t *d_drs_borrowing = nullptr;
   // host-side derived topology
-  std::vector<int32_t> root_slot, depth, height, tree_start, tree_nodes, tree_level, lone, cq_adm_start, cq_adm, local_idx, child_start, child_list, adm_sorted, root_adm_start;
+  std::vector<int32_t> root_slot, depth, height, tree_start, tree_nodes, tree_level, lone, cq_adm_start, cq_adm, local_idx, child_start, child_list, adm_sorted, root_adm_start, adm_rank, cq_adm_nev, root_cq_start;
   std::vector<uint8_t> tree_flat;
   int max_root_adm = 1;
   int search_grid = 1;
@@ -234,6 +234,9 @@ static int32_t build_static(kb_handle *h, const kb_snapshot *s) {
     h->max_tree_nodes = std::max(h->max_tree_nodes, nn);
     for (int i = 0; i < nn; i++) h->local_idx[h->tree_nodes[h->tree_start[t] + i]] = i;
   }
+  h->root_cq_start.assign(nroots + 1, 0);
+  for (int q = 0; q < Q; q++) h->root_cq_start[h->root_slot[q] + 1]++;
+  for (int r = 0; r < nroots; r++) h->root_cq_start[r + 1] += h->root_cq_start[r];
   h->D.nTrees = ntrees;
   h->D.nLone = (int)h->lone.size();
   h->D.nRoots = nroots;
@@ -254,10 +257,6 @@ static int32_t build_dynamic(kb_handle *h, const kb_snapshot *s) {
   }
   for (int q = 0; q < Q; q++) h->cq_adm_start[q + 1] += h->cq_adm_start[q];
   h->cq_adm.assign(std::max(1, s->n_adm), 0);
-  {
-    std::vector<int32_t> cur(h->cq_adm_start.begin(), h->cq_adm_start.end() - 1);
-    for (int a = 0; a < s->n_adm; a++) h->cq_adm[cur[s->adm_cq[a]]++] = a;
-  }
   // admitted workloads per root, in the preemptor-independent part of CandidatesOrdering
   // (preemption/common/ordering.go:41-100): evicted first, lower priority first, more recently
   // reserved first, UID.  TODO(next): radix sort on the device / incremental order kept by the host cache.
@@ -278,6 +277,19 @@ static int32_t build_dynamic(kb_handle *h, const kb_snapshot *s) {
         if (ta != tb) return ta > tb;
         return s->adm_uid[a] < s->adm_uid[b];
       });
+  }
+  if (h->max_root_adm >= (1 << 28)) return fail(h, KB_ERR_INVALID, "more than 2^28 admitted workloads under one root");
+  {  // per-CQ lists in the same order (evicted workloads first), rank of every workload inside its root
+    h->adm_rank.assign(std::max(1, s->n_adm), 0);
+    h->cq_adm_nev.assign(std::max(1, Q), 0);
+    std::vector<int32_t> cur(h->cq_adm_start.begin(), h->cq_adm_start.end() - 1);
+    for (int r = 0; r < nroots; r++)
+      for (int i = h->root_adm_start[r]; i < h->root_adm_start[r + 1]; i++) {
+        int a = h->adm_sorted[i];
+        h->adm_rank[a] = i - h->root_adm_start[r];
+        h->cq_adm[cur[s->adm_cq[a]]++] = a;
+        if (s->adm_evicted[a]) h->cq_adm_nev[s->adm_cq[a]]++;
+      }
   }
   // light bounds checks on the hot tables
   for (int i = 0; i < s->n_heads; i++) if (s->heads[i] < 0 || s->heads[i] >= s->n_wl) return fail(h, KB_ERR_INVALID, "heads out of range");
@@ -337,7 +349,7 @@ static int32_t upload_impl(kb_handle *h, const kb_snapshot *s, bool sync) {
     sneed(Q, 4); for (int k = 0; k < 4; k++) sneed(Q, 1); sneed(Q, 8);
     sneed(Q + 1, 4); sneed(s->n_rg, 4); sneed(s->n_rg + 1, 4); sneed(n_rg_fl, 4);
     sneed(N, 4); sneed(N, 4); sneed(N, 4); sneed(D.nTrees + 1, 4); sneed(h->tree_nodes.size(), 4); sneed(h->tree_level.size(), 4);
-    sneed(h->lone.size(), 4); sneed(N, 4); sneed(h->tree_flat.size(), 1); sneed(N + 1, 4); sneed(h->child_list.size(), 4);
+    sneed(h->lone.size(), 4); sneed(N, 4); sneed(h->tree_flat.size(), 1); sneed(N + 1, 4); sneed(h->child_list.size(), 4); sneed(h->root_cq_start.size(), 4);
     if (!h->sarena.reserve(stot + 4096)) return fail(h, KB_ERR_CUDA, "cudaMalloc failed");
     h->sarena.reset();
 #define SUP(field, src, n) CUDA_TRY(h, up(h, h->sarena, D.field, src, (size_t)(n), &bytes))
@@ -355,6 +367,7 @@ static int32_t upload_impl(kb_handle *h, const kb_snapshot *s, bool sync) {
     SUP(local_idx, h->local_idx.data(), N);
     SUP(tree_flat, h->tree_flat.data(), h->tree_flat.size());
     SUP(child_start, h->child_start.data(), N + 1); SUP(child_list, h->child_list.data(), h->child_list.size());
+    SUP(root_cq_start, h->root_cq_start.data(), h->root_cq_start.size());
 #undef SUP
     memcpy(h->s_dims, dims, sizeof(dims));
     h->static_gen = s->static_generation;
@@ -372,7 +385,7 @@ static int32_t upload_impl(kb_handle *h, const kb_snapshot *s, bool sync) {
   need(P * R, 8); need(P, 4); need(P, 4); need(P, 4); need(P, 8); need(P * R, 1);
   need(A, 4); need(A, 4); need(A, 8); need(A, 8); need(A, 8); need(A, 1); need(A + 1, 4); need(s->n_adm_use, 4); need(s->n_adm_use, 8);
   need(H, 4);
-  need(Q + 1, 4); need(h->cq_adm.size(), 4);
+  need(Q + 1, 4); need(h->cq_adm.size(), 4); need(h->adm_rank.size(), 4); need(h->cq_adm_nev.size(), 4); need(Q, 4); need(nroots, 4);
   need(NF, 8); need(NF, 8); need(NF, 8); need(NF, 8);
   need(nroots, 4); need(nroots + 1, 4); need(nroots, 4); need(H, 4); need(H, 4); need(H * 4, 8); need(H * 4, 8); need((size_t)Q * R, 8); need((size_t)N * R, 8);
   need(H, 1); need(H, 1); need(H, 4); need(H, 4); need(P * R, 1); need(P * R, 1); need(P * R, 1); need(P, 4);
@@ -389,7 +402,7 @@ static int32_t upload_impl(kb_handle *h, const kb_snapshot *s, bool sync) {
   size_t G = (size_t)h->search_grid, acap = (size_t)h->max_root_adm, ncap = (size_t)h->max_tree_nodes;
   size_t pool_cap = A * 4 + 1024;
   need(A, 4); need(nroots + 1, 4); need(H, 4); need(2, 4); need(H, 4); need(H, 4); need(pool_cap, 4); need(pool_cap, 1); need(1, 4);
-  need(A, 1); need(A, 4); need(nroots, 4);
+  need(A, 1); need(A, 4); need(nroots, 4); need(A ? NF : 1, 8);
   need(G * acap, 4); need(G * acap, 4); need(G * acap, 4); need(G * acap, 4); need(G * ncap, 4); need(G * acap, 1); need(G * acap, 1); need(G * ncap, 1); need(G * ncap, 1);
   if (!h->search_smem) need(G * ncap * FR, 8);
   bool fair = (s->flags & KB_F_FAIR_SHARING) != 0;
@@ -408,7 +421,9 @@ static int32_t upload_impl(kb_handle *h, const kb_snapshot *s, bool sync) {
   UP(heads, s->heads, H);
   UP(adm_sorted, h->adm_sorted.data(), h->adm_sorted.size()); UP(root_adm_start, h->root_adm_start.data(), nroots + 1);
   UP(cq_adm_start, h->cq_adm_start.data(), Q + 1); UP(cq_adm, h->cq_adm.data(), h->cq_adm.size());
+  UP(adm_rank, h->adm_rank.data(), h->adm_rank.size()); UP(cq_adm_nev, h->cq_adm_nev.data(), h->cq_adm_nev.size());
 #undef UP
+  D.over_list = h->arena.take<int32_t>(Q); D.over_count = h->arena.take<int32_t>(nroots);
   D.subtree = h->arena.take<i64>(NF); D.usage = h->arena.take<i64>(NF);
   D.avail = h->arena.take<i64>(NF); D.potential = h->arena.take<i64>(NF);
   D.root_count = h->arena.take<int32_t>(nroots); D.root_offset = h->arena.take<int32_t>(nroots + 1);
@@ -425,6 +440,7 @@ static int32_t upload_impl(kb_handle *h, const kb_snapshot *s, bool sync) {
   D.tgt_pool_adm = h->arena.take<int32_t>(pool_cap); D.tgt_pool_reason = h->arena.take<uint8_t>(pool_cap);
   D.tgt_pool_used = h->arena.take<int32_t>(1); D.tgt_pool_cap = (int)pool_cap;
   D.preempted = h->arena.take<uint8_t>(A); D.root_pre_list = h->arena.take<int32_t>(A); D.root_pre_count = h->arena.take<int32_t>(nroots);
+  D.usage_shadow = h->arena.take<i64>(A ? NF : 1);
   D.sc_cand = h->arena.take<int32_t>(G * acap); D.sc_tgt = h->arena.take<int32_t>(G * acap); D.sc_cq_lca = h->arena.take<int32_t>(G * ncap);
   D.sc_aux1 = h->arena.take<int32_t>(G * acap); D.sc_aux2 = h->arena.take<int32_t>(G * acap);
   D.sc_variant = h->arena.take<uint8_t>(G * acap); D.sc_tgt_reason = h->arena.take<uint8_t>(G * acap);
@@ -436,6 +452,7 @@ static int32_t upload_impl(kb_handle *h, const kb_snapshot *s, bool sync) {
     D.fs_cq_entry = h->arena.take<int32_t>(N); D.fs_winner = h->arena.take<int32_t>(N);
   }
   h->d_drs_rounded = h->arena.take<i64>(N); h->d_drs_res = h->arena.take<int32_t>(N); h->d_drs_borrowing = h->arena.take<uint8_t>(N);
+  if (h->arena.used > h->arena.cap) return fail(h, KB_ERR_CUDA, "device arena accounting");
   // rows of workloads that are not heads stay at -1
   CUDA_TRY(h, cudaMemsetAsync(D.ps_flavor, 0xff, P * R, h->stream));
   CUDA_TRY(h, cudaMemsetAsync(D.ps_res_mode, 0xff, P * R, h->stream));
@@ -552,6 +569,8 @@ static int32_t cycle_enqueue(kb_handle *h) {
     launches++;
     if (D.A) {  // target search for the entries k_nominate deferred
       kmark(h, KB_K_PREEMPT);
+      CUDA_TRY(h, cudaMemsetAsync(D.over_count, 0, sizeof(int32_t) * (size_t)std::max(1, D.nRoots), h->stream));
+      k_over<<<(D.Q + 255) / 256, 256, 0, h->stream>>>(D); launches++;
       if (h->search_smem) {
         CUDA_TRY(h, cudaFuncSetAttribute(k_nominate_search<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         k_nominate_search<true><<<h->search_grid, 32, h->search_smem_bytes, h->stream>>>(D);

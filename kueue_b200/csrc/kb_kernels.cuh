@@ -636,6 +636,20 @@ __global__ void __launch_bounds__(128) k_nominate(DevSnap D) {
   }
 }
 
+// ClusterQueues (with a cohort) whose usage exceeds nominal in some flavor-resource at cycle
+// start, listed per root: the only queues a target search can take cohort candidates from
+// (IsWithinNominalInResources resource_node.go:248-255 is false only for them).
+__global__ void k_over(DevSnap D) {
+  int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= D.Q || D.parent[q] < 0) return;
+  const int FR = D.FR;
+  bool over = false;
+  for (int fr = 0; fr < FR; fr++) over |= D.usage[(size_t)q * FR + fr] > D.subtree[(size_t)q * FR + fr];
+  if (!over) return;
+  int slot = D.root_slot[q];
+  D.over_list[D.root_cq_start[slot] + atomicAdd(&D.over_count[slot], 1)] = q;
+}
+
 // ---------------------------------------------------------------------------
 // K6: nominate with target search.  Persistent CTAs pull the deferred entries; all threads
 // of the CTA run the (scalar) flavor-assignment control flow uniformly and cooperate inside
@@ -957,8 +971,17 @@ struct Tab {
   i64 *usage; const i64 *sub, *lq, *bl;  // smem mode only
   const int *lparent;                    // smem mode only
   int FR;
+  // shadow usage table (global, [N][FR]): the root's usage WITHOUT the workloads preempted so far in this
+  // cycle; live once *shadow_on != 0.  fits() (scheduler.go:503-511) evaluates on it instead of removing
+  // and re-adding every preempted workload per entry.  Usage is a pure function of the ClusterQueue rows
+  // (cohort usage = sum of max(0, child usage - child localQuota), resource_node.go:137-158), so keeping the
+  // shadow in step with add/remove is exact.
+  i64 *shadow; const int32_t *tnodes; int tnn; int *shadow_on;
   __device__ __forceinline__ i64 U(int nd, int fr) const { return kSmem ? usage[nd * FR + fr] : __ldcg(&D->usage[(size_t)nd * FR + fr]); }
   __device__ __forceinline__ void setU(int nd, int fr, i64 v) const { if (kSmem) usage[nd * FR + fr] = v; else __stcg(&D->usage[(size_t)nd * FR + fr], v); }
+  __device__ __forceinline__ size_t scell(int nd, int fr) const { return (size_t)(kSmem ? tnodes[nd] : nd) * FR + fr; }
+  template <bool S> __device__ __forceinline__ i64 Ux(int nd, int fr) const { return S ? shadow[scell(nd, fr)] : U(nd, fr); }
+  template <bool S> __device__ __forceinline__ void setUx(int nd, int fr, i64 v) const { if (S) shadow[scell(nd, fr)] = v; else setU(nd, fr, v); }
   __device__ __forceinline__ i64 Sub(int nd, int fr) const { return kSmem ? sub[nd * FR + fr] : D->subtree[(size_t)nd * FR + fr]; }
   __device__ __forceinline__ i64 LQ(int nd, int fr) const {
     return kSmem ? lq[nd * FR + fr] : local_quota(D->subtree[(size_t)nd * FR + fr], D->llimit[(size_t)nd * FR + fr]);
@@ -967,42 +990,46 @@ struct Tab {
   __device__ __forceinline__ int parent(int nd) const { return kSmem ? lparent[nd] : D->parent[nd]; }
   __device__ __forceinline__ int handle(int node) const { return kSmem ? D->local_idx[node] : node; }
   // available() resource_node.go:104-118 along a staged path (path[0] = CQ ... path[plen-1] = root)
+  template <bool S = false>
   __device__ inline i64 avail(const int *path, int plen, int fr) const {
     int rt = path[plen - 1];
-    i64 a = Sub(rt, fr) - U(rt, fr);
+    i64 a = Sub(rt, fr) - Ux<S>(rt, fr);
     for (int k = plen - 2; k >= 0; k--) {
       int nd = path[k];
-      i64 u = U(nd, fr), l = LQ(nd, fr), b = BL(nd, fr);
+      i64 u = Ux<S>(nd, fr), l = LQ(nd, fr), b = BL(nd, fr);
       i64 pa = a;
       if (b != KB_NO_LIMIT) pa = imin((Sub(nd, fr) - l) - imax(0, u - l) + b, pa);
       a = imax(0, l - u) + pa;
     }
     return a;
   }
+  template <bool S = false>
   __device__ inline void add_node(int nd, int fr, i64 val) const {  // addUsage :137-145 walking parents
     while (true) {
-      i64 u = U(nd, fr), la = imax(0, LQ(nd, fr) - u);
-      setU(nd, fr, u + val);
+      i64 u = Ux<S>(nd, fr), la = imax(0, LQ(nd, fr) - u);
+      setUx<S>(nd, fr, u + val);
       int p = parent(nd);
       if (p < 0 || !(val > la)) break;
       val -= la; nd = p;
     }
   }
+  template <bool S = false>
   __device__ inline void remove_node(int nd, int fr, i64 val) const {  // removeUsage :149-158
     while (true) {
-      i64 u = U(nd, fr), stored = u - LQ(nd, fr);
-      setU(nd, fr, u - val);
+      i64 u = Ux<S>(nd, fr), stored = u - LQ(nd, fr);
+      setUx<S>(nd, fr, u - val);
       int p = parent(nd);
       if (stored <= 0 || p < 0) break;
       val = imin(val, stored); nd = p;
     }
   }
+  template <bool S = false>
   __device__ inline void add(const int *path, int plen, int fr, i64 val) const {  // addUsage :137-145
     for (int k = 0; k < plen; k++) {
       int nd = path[k];
-      i64 u = U(nd, fr);
+      i64 u = Ux<S>(nd, fr);
       i64 la = imax(0, LQ(nd, fr) - u);
-      setU(nd, fr, u + val);
+      setUx<S>(nd, fr, u + val);
       if (!(k + 1 < plen && val > la)) break;
       val -= la;
     }
@@ -1014,6 +1041,7 @@ template <bool kSmem>
 __device__ inline unsigned char *stage_tables(const DevSnap &D, Tab<kSmem> &T, unsigned char *p, const int32_t *nodes, int nn) {
   const int FR = D.FR;
   T.D = &D; T.FR = FR;
+  T.shadow = D.usage_shadow; T.tnodes = nodes; T.tnn = nn; T.shadow_on = nullptr;
   if (kSmem) {
     size_t tb = (size_t)nn * FR;
     i64 *u = (i64 *)p, *sb = u + tb, *lq = sb + tb, *bl = lq + tb;
@@ -1040,17 +1068,18 @@ __device__ inline void publish_usage(const DevSnap &D, const Tab<kSmem> &T, cons
 // One iteration of the admit loop body (scheduler.go:269-401) for entry e, executed by a
 // full warp: lane l owns the flavor-resource columns l, l+32, ...  qrow[fr] is the
 // aggregated Assignment.Usage.Quota (absent cell = -1).  s_path: KB_MAX_DEPTH+2 ints.
-// cq = global id of the entry's ClusterQueue, slot = root slot, ntg/toff = its preemption targets in the pool,
-// s_npre = shared-memory count of the workloads preempted so far in this root.
+// cq = global id of the entry's ClusterQueue, ntg/toff = its preemption targets in the pool.
+// T.shadow_on points at a shared-memory flag (0 at kernel start).
 template <bool kSmem>
 __device__ inline void commit_entry(const DevSnap &D, const Tab<kSmem> &T, int *s_path, int lane, int e, int nd, int mode,
-                                    int borrowing, const i64 *qrow, int rank, int cq, int slot, int ntg, int toff, int *s_npre) {
+                                    int borrowing, const i64 *qrow, int rank, int cq, int ntg, int toff) {
   const int FR = D.FR;
   if (lane == 0) D.rank[e] = rank;
   if (mode == KB_MODE_NOFIT) { if (lane == 0) D.decision[e] = KB_DEC_NOFIT; return; }
   if (lane == 0) { int pl = 0; for (int t = nd; t >= 0; t = T.parent(t)) s_path[pl++] = t; s_path[KB_MAX_DEPTH + 1] = pl; }
   __syncwarp();
   int plen = s_path[KB_MAX_DEPTH + 1];
+  bool shadow = *T.shadow_on != 0;
   if (mode == KB_MODE_PREEMPT && ntg == 0) {  // Preempt without targets: scheduler.go:303-318
     if (lane == 0) D.decision[e] = KB_DEC_PREEMPT_NO_TARGETS;
     if (D.cq_reclaim_within[cq] != KB_POLICY_ANY) {  // !CanAlwaysReclaim policy.go:27-29
@@ -1062,50 +1091,49 @@ __device__ inline void commit_entry(const DevSnap &D, const Tab<kSmem> &T, int *
         if (borrowing > 0) rsv = bl == KB_NO_LIMIT ? u : imin(u, nominal + bl - cur);
         else rsv = imax(0, imin(u, nominal - cur));
         T.add(s_path, plen, fr, rsv);
+        if (shadow) T.template add<true>(s_path, plen, fr, rsv);
       }
     }
     __syncwarp();
     return;
   }
-  // entries with preemption targets: overlap check (:321-325) and fits() with the usage of
-  // every workload preempted so far in this root plus the new targets removed (:503-511)
-  int npre = *s_npre;
-  int *plist = (npre > 0 || ntg > 0) ? D.root_pre_list + D.root_adm_start[slot] : nullptr;
+  // entries with preemption targets: overlap check (:321-325); fits() sees the usage without every
+  // workload preempted so far in this root and without the new targets (:503-511) = the shadow table
   if (ntg > 0) {
     bool overlap = false;
     for (int k = lane; k < ntg; k += 32) if (D.preempted[D.tgt_pool_adm[toff + k]]) overlap = true;
     if (__any_sync(0xffffffffu, overlap)) { if (lane == 0) D.decision[e] = KB_DEC_SKIPPED_OVERLAP; __syncwarp(); return; }
+    if (!shadow) {  // first targets of this root: the shadow starts as a copy of the current usage
+      for (int i = lane; i < T.tnn * FR; i += 32) { int h = kSmem ? i / FR : T.tnodes[i / FR]; T.shadow[T.scell(h, i % FR)] = T.U(h, i % FR); }
+      __syncwarp();
+      if (lane == 0) *T.shadow_on = 1;
+      shadow = true;
+      __syncwarp();
+    }
   }
-  auto apply = [&](int a, bool remove) {  // one admitted workload: its cells are distinct columns -> one lane each
+  auto apply = [&](int a, bool remove) {  // one admitted workload on the shadow: its cells are distinct columns -> one lane each
     int nd2 = T.handle(D.adm_cq[a]);
     for (int k = D.adm_use_start[a] + lane; k < D.adm_use_start[a + 1]; k += 32) {
-      if (remove) T.remove_node(nd2, D.adm_use_fr[k], D.adm_use_qty[k]);
-      else T.add_node(nd2, D.adm_use_fr[k], D.adm_use_qty[k]);
+      if (remove) T.template remove_node<true>(nd2, D.adm_use_fr[k], D.adm_use_qty[k]);
+      else T.template add_node<true>(nd2, D.adm_use_fr[k], D.adm_use_qty[k]);
     }
     __syncwarp();
   };
-  if (npre > 0 || ntg > 0) {  // SimulateWorkloadRemoval snapshot.go:67-84
-    for (int k = 0; k < npre; k++) apply(plist[k], true);
-    for (int k = 0; k < ntg; k++) apply(D.tgt_pool_adm[toff + k], true);
-  }
+  for (int k = 0; k < ntg; k++) apply(D.tgt_pool_adm[toff + k], true);  // SimulateWorkloadRemoval snapshot.go:67-84
   bool ok = true;  // fits :503-511
   for (int fr = lane; fr < FR; fr += 32) {
     i64 q = qrow[fr];
-    if (q > 0 && imax(0, T.avail(s_path, plen, fr)) < q) ok = false;
+    if (q > 0 && imax(0, shadow ? T.template avail<true>(s_path, plen, fr) : T.avail(s_path, plen, fr)) < q) ok = false;
   }
   ok = __all_sync(0xffffffffu, ok);
-  if (npre > 0 || ntg > 0) {
-    for (int k = 0; k < npre; k++) apply(plist[k], false);
-    for (int k = 0; k < ntg; k++) apply(D.tgt_pool_adm[toff + k], false);
-  }
   if (ok) {
-    if (ntg > 0) {  // preemptedWorkloads.Insert :335
-      for (int k = lane; k < ntg; k += 32) { int a = D.tgt_pool_adm[toff + k]; D.preempted[a] = 1; plist[npre + k] = a; }
-      __syncwarp();
-      if (lane == 0) *s_npre = npre + ntg;
-      __syncwarp();
+    for (int k = lane; k < ntg; k += 32) D.preempted[D.tgt_pool_adm[toff + k]] = 1;  // preemptedWorkloads.Insert :335 (stay removed in the shadow)
+    for (int fr = lane; fr < FR; fr += 32) {  // cq.AddUsage :336
+      i64 q = qrow[fr];
+      if (q > 0) { T.add(s_path, plen, fr, q); if (shadow) T.template add<true>(s_path, plen, fr, q); }
     }
-    for (int fr = lane; fr < FR; fr += 32) { i64 q = qrow[fr]; if (q > 0) T.add(s_path, plen, fr, q); }  // cq.AddUsage :336
+  } else {
+    for (int k = 0; k < ntg; k++) apply(D.tgt_pool_adm[toff + k], false);
   }
   if (lane == 0) D.decision[e] = ok ? (mode == KB_MODE_PREEMPT ? KB_DEC_PREEMPTING : KB_DEC_ASSUMED) : KB_DEC_SKIPPED_NO_FIT;
   __syncwarp();
@@ -1166,8 +1194,9 @@ __global__ void __launch_bounds__(128) k_admit(DevSnap D, int slot_base, int sor
   int *t_e = (int *)p, *t_node = t_e + KB_TILE, *t_mode = t_node + KB_TILE, *t_borrow = t_mode + KB_TILE;
   int *t_cq = t_borrow + KB_TILE, *t_ntg = t_cq + KB_TILE, *t_toff = t_ntg + KB_TILE;
   int *s_path = t_toff + KB_TILE;
-  int *s_npre = s_path + KB_MAX_DEPTH + 2;
-  if (threadIdx.x == 0) *s_npre = 0;
+  int *s_shadow_on = s_path + KB_MAX_DEPTH + 2;
+  if (threadIdx.x == 0) *s_shadow_on = 0;
+  T.shadow_on = s_shadow_on;
 
   // ---- 1. iterator order: k_rank already produced it for roots up to KB_RANK_CAP entries; larger roots sort here
   //         with an ascending-only bitonic network over the global index array (virtual +inf padding never moves).
@@ -1207,7 +1236,7 @@ __global__ void __launch_bounds__(128) k_admit(DevSnap D, int slot_base, int sor
     if (warp == 0)
       for (int i = 0; i < tn; i++)
         commit_entry<kSmemTables>(D, T, s_path, lane, t_e[i], t_node[i], t_mode[i], t_borrow[i], s_q + (size_t)i * FR, base + i,
-                                  t_cq[i], slot, t_ntg[i], t_toff[i], s_npre);
+                                  t_cq[i], t_ntg[i], t_toff[i]);
     __syncthreads();
   }
   publish_usage<kSmemTables>(D, T, nodes, nn);
@@ -1355,8 +1384,9 @@ __global__ void __launch_bounds__(128) k_admit_fair(DevSnap D, int slot_base, in
   Tab<kSmemTables> T;
   unsigned char *p = stage_tables<kSmemTables>(D, T, smem_raw, nodes, nn);
   int *s_path = (int *)p; p += (KB_MAX_DEPTH + 2) * 4;
-  int *s_npre = (int *)p; p += 8;
-  if (threadIdx.x == 0) *s_npre = 0;
+  int *s_shadow_on = (int *)p; p += 8;
+  if (threadIdx.x == 0) *s_shadow_on = 0;
+  T.shadow_on = s_shadow_on;
   // tree index arrays in LOCAL node ids (always shared memory): children CSR, waiting slot of a CQ, winner of a cohort
   int *s_cstart = (int *)p; p += (size_t)(nn + 1) * 4;
   int *s_child = (int *)p; p += (size_t)nn * 4;
@@ -1484,7 +1514,7 @@ __global__ void __launch_bounds__(128) k_admit_fair(DevSnap D, int slot_base, in
     if (warp == 0) {
       int md = F.e_mode[w];
       commit_entry<kSmemTables>(D, T, s_path, lane, we, T.handle(wcq), md & 0xff, md >> 8, D.q_scratch + (size_t)we * FR, it,
-                                wcq, slot, D.tgt_cnt[we], D.tgt_off[we], s_npre);
+                                wcq, D.tgt_cnt[we], D.tgt_off[we]);
       __syncwarp();
       if (lane == 0) {
         int dec = D.decision[we];  // every branch that may have touched the tree's usage

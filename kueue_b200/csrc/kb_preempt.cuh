@@ -164,6 +164,34 @@ __device__ __forceinline__ int variant_reason(int v) {  // PreemptionReason :49-
   return 0;
 }
 
+
+// ---------------------------------------------------------------------------
+// Ordered candidate gathering.  The host orders the admitted workloads of every root once per
+// cycle by the preemptor-independent part of CandidatesOrdering (common/ordering.go:41-100:
+// evicted first, lower priority first, more recently reserved first, UID) -> adm_rank; the
+// per-CQ lists (cq_adm) are in that order.  A search only touches the lists of the ClusterQueues it
+// can take candidates from: gather the accepted workloads, then heap sort on (segment << 28 | rank).
+// ---------------------------------------------------------------------------
+// heap sort of (key, cand, variant) triples by key
+__device__ inline void sort_candidates(int32_t *key, int32_t *cand, uint8_t *var, int n) {
+  auto swp = [&](int i, int j) {
+    int32_t t = key[i]; key[i] = key[j]; key[j] = t;
+    t = cand[i]; cand[i] = cand[j]; cand[j] = t;
+    uint8_t v = var[i]; var[i] = var[j]; var[j] = v;
+  };
+  auto sift = [&](int i, int len) {
+    while (true) {
+      int l = 2 * i + 1, r = l + 1, b = i;
+      if (l < len && key[l] > key[b]) b = l;
+      if (r < len && key[r] > key[b]) b = r;
+      if (b == i) return;
+      swp(i, b); i = b;
+    }
+  };
+  for (int i = n / 2 - 1; i >= 0; i--) sift(i, n);
+  for (int len = n - 1; len > 0; len--) { swp(0, len); sift(0, len); }
+}
+
 template <bool kSmem>
 __device__ __forceinline__ bool within_nominal(const PTab<kSmem> &T, const PreCtx &c, int h) {  // IsWithinNominalInResources resource_node.go:248-255
   for (int j = 0; j < c.n_need; j++) if (T.U(h, c.need_fr[j]) > T.Sub(h, c.need_fr[j])) return false;
@@ -214,10 +242,17 @@ __device__ inline void classical_search(const DevSnap &D, const PTab<kSmem> &T, 
   }
   for (int h = 0; h < T.nn; h++) S.on_path[h] = -1;
   for (int k = 0; k < c->plen; k++) S.on_path[c->path[k]] = (int8_t)k;
-  // ---- 2. which ClusterQueues are collected, and by which subtree (collectCandidatesInSubtree :181-199)
-  for (int h = 0; h < T.nn; h++) {
+  // ---- 2. which ClusterQueues are collected, and by which subtree (collectCandidatesInSubtree :181-199).
+  //         Only ClusterQueues above nominal in some flavor-resource at cycle start can qualify
+  //         (searches only ever remove usage from other queues): k_over listed them per root.
+  const int slot = D.root_slot[cq];
+  const int32_t *over = D.over_list + D.root_cq_start[slot];
+  const int n_over = cohort_cands ? D.over_count[slot] : 0;
+  for (int i = 0; i < n_over; i++) {
+    int q = over[i];
+    int h = T.handle(q);
     int cls = 0, lca = -1;
-    if (cohort_cands && T.nodes[h] < D.Q && h != hcq && !within_nominal(T, *c, h)) {
+    if (h != hcq && !within_nominal(T, *c, h)) {
       bool ok = true;
       int t = T.parent(h);
       while (t >= 0 && S.on_path[t] < 0) {  // cohorts strictly between the CQ and the subtree root
@@ -230,30 +265,27 @@ __device__ inline void classical_search(const DevSnap &D, const PTab<kSmem> &T, 
     S.cq_lca[h] = lca;
   }
   // ---- 3. ordered candidate list: evicted{hier, prio, same} then non-evicted{hier, prio, same}
-  //         (NewCandidateIterator candidate_generator.go:77-121): six filtered passes over the
-  //         root's admitted workloads pre-sorted by (evicted, priority asc, newer first, uid).
-  int slot = D.root_slot[cq];
-  int a0 = D.root_adm_start[slot], a1 = D.root_adm_start[slot + 1];
+  //         (NewCandidateIterator candidate_generator.go:77-121)
   int nall = 0;
-  for (int seg = 0; seg < 6; seg++) {
-    int ev = seg < 3 ? 1 : 0, cls = seg % 3 + 1;
-    int seg_n = 0;
-    if ((cls == 3 && own_cands) || (cls != 3 && cohort_cands)) {
-      for (int i = a0; i < a1; i++) {
-        int a = D.adm_sorted[i];
-        int aev = D.adm_evicted[a];
-        if (aev != ev) { if (ev == 1) break; continue; }  // evicted workloads form the prefix of the segment
-        int acq = D.adm_cq[a];
-        int acls = acq == cq ? 3 : S.cq_class[T.handle(acq)];
-        if (acls != cls) continue;
-        int v = classify_variant(D, *c, a, cls == 1);
-        if (v == PV_NEVER) continue;
-        S.cand[nall + seg_n] = a; S.variant[nall + seg_n] = (uint8_t)v; seg_n++;
-      }
+  for (int sgi = 0; sgi < 6; sgi++) c->seg_count[sgi] = 0;
+  auto gather = [&](int q, int cls) {  // cls: 0 hierarchy, 1 priority, 2 same queue
+    for (int i = D.cq_adm_start[q]; i < D.cq_adm_start[q + 1]; i++) {
+      int a = D.cq_adm[i];
+      int v = classify_variant(D, *c, a, cls == 0);
+      if (v == PV_NEVER) continue;
+      int seg = (D.adm_evicted[a] ? 0 : 3) + cls;
+      S.cand[nall] = a; S.variant[nall] = (uint8_t)v; S.aux1[nall] = (seg << 28) | D.adm_rank[a];
+      nall++;
+      c->seg_count[seg]++;
     }
-    c->seg_count[seg] = seg_n;
-    nall += seg_n;
+  };
+  if (own_cands) gather(cq, 2);
+  for (int i = 0; i < n_over; i++) {
+    int q = over[i];
+    int h = T.handle(q);
+    if (h != hcq && S.cq_class[h]) gather(q, S.cq_class[h] - 1);
   }
+  sort_candidates(S.aux1, S.cand, S.variant, nall);
   // ---- 4. greedy remove / fill back
   {
     int n_hier = c->seg_count[0] + c->seg_count[3], n_prio = c->seg_count[1] + c->seg_count[4];
@@ -360,30 +392,32 @@ __device__ inline void fair_search(const DevSnap &D, const PTab<kSmem> &T, PreCt
   }
   for (int h = 0; h < T.nn; h++) { S.on_path[h] = -1; S.cq_class[h] = 0; S.cq_lca[h] = -1; }
   for (int k = 1; k < c->plen; k++) S.on_path[c->path[k]] = (int8_t)k;  // preemptorAncestors
-  // ---- findCandidates :514-533, sorted by CandidatesOrdering: evicted first, other CQs before the preemptor's
-  int slot = D.root_slot[cq];
-  int a0 = D.root_adm_start[slot], a1 = D.root_adm_start[slot + 1];
+  // ---- findCandidates :514-533, sorted by CandidatesOrdering: evicted first, other CQs before the preemptor's.
+  //         Other ClusterQueues qualify only while borrowing (cqIsBorrowing :535-545) -> subset of k_over's list.
+  const int slot = D.root_slot[cq];
+  const int32_t *over = D.over_list + D.root_cq_start[slot];
+  const int n_over = cohort_cands ? D.over_count[slot] : 0;
+  auto is_borrowing = [&](int q) {
+    int h = T.handle(q);
+    for (int j = 0; j < c->n_need; j++) if (T.borrowing_with(h, c->need_fr[j], 0)) return true;
+    return false;
+  };
   int nall = 0;
-  for (int seg = 0; seg < 4; seg++) {
-    int ev = seg < 2 ? 1 : 0; bool own = seg & 1;
-    if (!(own ? own_cands : cohort_cands)) continue;
-    for (int i = a0; i < a1; i++) {
-      int a = D.adm_sorted[i];
-      int aev = D.adm_evicted[a];
-      if (aev != ev) { if (ev == 1) break; continue; }
-      int acq = D.adm_cq[a];
-      if ((acq == cq) != own) continue;
-      int policy = own ? D.cq_within_cq[cq] : D.cq_reclaim_within[cq];
+  auto gather = [&](int q, int cls) {  // cls: 0 other ClusterQueue, 1 the preemptor's
+    int policy = cls == 1 ? D.cq_within_cq[cq] : D.cq_reclaim_within[cq];
+    for (int i = D.cq_adm_start[q]; i < D.cq_adm_start[q + 1]; i++) {
+      int a = D.cq_adm[i];
       if (!satisfies_policy(D, *c, a, policy) || !uses_resources(D, *c, a)) continue;
-      if (!own) {  // cqIsBorrowing :535-545
-        int h = T.handle(acq);
-        bool borrowing = false;
-        for (int j = 0; j < c->n_need; j++) if (T.borrowing_with(h, c->need_fr[j], 0)) borrowing = true;
-        if (!borrowing) continue;
-      }
-      S.cand[nall++] = a;
+      S.cand[nall] = a; S.variant[nall] = 0; S.aux1[nall] = (((D.adm_evicted[a] ? 0 : 2) + cls) << 28) | D.adm_rank[a];
+      nall++;
     }
+  };
+  if (own_cands) gather(cq, 1);
+  for (int i = 0; i < n_over; i++) {
+    int q = over[i];
+    if (q != cq && is_borrowing(q)) gather(q, 0);
   }
+  sort_candidates(S.aux1, S.cand, S.variant, nall);
   if (nall == 0) { c->n_targets = 0; return; }
   int32_t *head = S.cq_lca;   // per node: index (into the current candidate list) of the queue head, or -1
   int32_t *next = S.aux1;
