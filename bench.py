@@ -49,7 +49,15 @@ HEADS = {1: "all", 2: "all", 3: "one_per_cq", 4: "one_per_cq"}
 
 
 def algorithmic_bytes(snap) -> dict:
-    """B = W_eval*(P*R*8 + 24) + W_eval*out_B + (Q+C)*FR*32 + (Q+C)*16."""
+    """Algorithmic bytes per launch of each kernel.
+
+    nominate is SURVEY.md §8(d): B = W_eval*(P*R*8 + 24) + W_eval*out_B + (Q+C)*FR*32 + (Q+C)*16.
+    tree: nominal/borrow/lend limits + CQ usage in, SubtreeQuota/usage/available/potentialAvailable out.
+    rank: the 32-byte iterator key of every entry in, its rank out.
+    admit: per entry the assignment rows (flavor 1 B + request 8 B per podset x resource) and 16 B of
+           mode/borrow/targets, the root's quota tables (usage, SubtreeQuota, lendingLimit, borrowingLimit)
+           in, usage back out, 5 B of decision + rank out.
+    """
     W = snap.n_heads
     P = snap.n_podset / max(1, snap.n_wl)
     R, FR, N = snap.n_resource, snap.n_fr, snap.n_nodes
@@ -57,7 +65,20 @@ def algorithmic_bytes(snap) -> dict:
     wl_in = W * (P * R * 8 + 24)
     wl_out = W * (8 + P * nrg)
     nodes = N * FR * 32 + N * 16
-    return {"nominate": wl_in + wl_out + nodes, "tree": nodes + N * FR * 16, "total": wl_in + wl_out + nodes}
+    return {"k_nominate": wl_in + wl_out + nodes, "k_nominate_search": wl_in + wl_out + nodes,
+            "k_tree": N * FR * 64 + N * 16, "k_lone": N * FR * 64,
+            "k_rank": W * 36, "k_scatter": W * 72, "k_scan_roots": N * 8,
+            "k_admit": W * (P * R * 9 + 16) + N * FR * 40 + W * 5,
+            "total": wl_in + wl_out + nodes}
+
+
+def measured_traffic(config: int, kernel: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        return t[f"cfg{config}"][kernel]
+    except Exception:
+        return None
 
 
 class ClockSampler(threading.Thread):
@@ -174,7 +195,7 @@ def main():
         snap = synth.compact_to_heads(snap)  # the cycle only ever receives the heads (queues.Heads())
     ev = native.Evaluator(local_rank)
     snap = native.pin_snapshot(snap)            # host SoA buffers are page-locked (kb_alloc_pinned)
-    out = native.pin_cycle_out(abi.CycleOut(snap))
+    out = native.pin_cycle_out(abi.CycleOut(snap, with_usage=False))  # decisions only: the host cache applies usage itself (cache.AssumeWorkload)
     flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
 
     def barrier():
@@ -242,7 +263,7 @@ def main():
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
         kname = abi.KERNEL_NAMES[top]
-        kbytes = ab["nominate"] if kname == "k_nominate" else (ab["tree"] if kname in ("k_tree", "k_lone") else ab["total"])
+        kbytes = ab.get(kname, ab["total"])
         achieved = kbytes / (top_ms / 1e3) / 1e9 if top_ms > 0 else 0.0
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
@@ -259,7 +280,7 @@ def main():
             "gpu_launches": launches,
             "kernel_ms_per_step": {abi.KERNEL_NAMES[i]: kms[i] / args.steps for i in range(8) if kms[i] > 0},
             "roofline": {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak if peak else None, "traffic": None,
+                         "unit": "GB/s", "frac": achieved / peak if peak else None, "traffic": measured_traffic(args.config, kname),
                          "algorithmic_bytes_per_launch": kbytes, "kernel_ms": top_ms,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)"},
         }

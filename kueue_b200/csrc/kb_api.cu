@@ -387,7 +387,7 @@ static int32_t upload_impl(kb_handle *h, const kb_snapshot *s, bool sync) {
   need(H, 4);
   need(Q + 1, 4); need(h->cq_adm.size(), 4); need(h->adm_rank.size(), 4); need(h->cq_adm_nev.size(), 4); need(Q, 4); need(nroots, 4);
   need(NF, 8); need(NF, 8); need(NF, 8); need(NF, 8);
-  need(nroots, 4); need(nroots + 1, 4); need(nroots, 4); need(H, 4); need(H, 4); need(H * 4, 8); need(H * 4, 8); need((size_t)Q * R, 8); need((size_t)N * R, 8);
+  need(nroots, 4); need(nroots + 1, 4); need(nroots, 4); need(H, 4); need(H, 4); need(H, 4); need(H * 4, 8); need(H * 4, 8); need((size_t)Q * R, 8); need((size_t)N * R, 8);
   need(H, 1); need(H, 1); need(H, 4); need(H, 4); need(P * R, 1); need(P * R, 1); need(P * R, 1); need(P, 4);
   need(1, 4); need(N, 8); need(N, 4); need(N, 1);
   // preemption: search kernel configuration + scratch
@@ -428,7 +428,7 @@ static int32_t upload_impl(kb_handle *h, const kb_snapshot *s, bool sync) {
   D.avail = h->arena.take<i64>(NF); D.potential = h->arena.take<i64>(NF);
   D.root_count = h->arena.take<int32_t>(nroots); D.root_offset = h->arena.take<int32_t>(nroots + 1);
   D.root_cursor = h->arena.take<int32_t>(nroots); D.root_entries = h->arena.take<int32_t>(H);
-  D.sorted = h->arena.take<int32_t>(H); D.ekey = h->arena.take<u64>(H * 4); D.skey = h->arena.take<u64>(H * 4);
+  D.sorted = h->arena.take<int32_t>(H); D.pos_slot = h->arena.take<int32_t>(H); D.ekey = h->arena.take<u64>(H * 4); D.skey = h->arena.take<u64>(H * 4);
   D.fs_over = h->arena.take<i64>((size_t)Q * R); D.fs_lend = h->arena.take<i64>((size_t)N * R);
   D.decision = h->arena.take<uint8_t>(H); D.mode = h->arena.take<uint8_t>(H);
   D.borrow = h->arena.take<int32_t>(H); D.rank = h->arena.take<int32_t>(H);
@@ -479,7 +479,7 @@ static inline void kmark(kb_handle *h, int id) {
 }
 static int32_t launch_tree(kb_handle *h, int *launches) {
   DevSnap &D = h->D;
-  if (D.nTrees) { kmark(h, KB_K_TREE); k_tree<<<D.nTrees, 256, 0, h->stream>>>(D); (*launches)++; }
+  if (D.nTrees) { kmark(h, KB_K_TREE); k_tree<<<D.nTrees, 1024, 0, h->stream>>>(D); (*launches)++; }
   if (D.nLone) { kmark(h, KB_K_LONE); int n = D.nLone * D.FR; k_lone<<<(n + 255) / 256, 256, 0, h->stream>>>(D); (*launches)++; }
   return KB_OK;
 }
@@ -509,7 +509,7 @@ static int32_t launch_admit(kb_handle *h, int *launches) {
     int cap = pick_cap(1);
     size_t sm = admit_smem(1, D.FR, cap);
     CUDA_TRY(h, cudaFuncSetAttribute(k_admit<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
-    k_admit<true><<<D.nLone, 128, sm, h->stream>>>(D, 0, cap); (*launches)++;
+    k_admit<true><<<D.nLone, KB_ADMIT_THREADS, sm, h->stream>>>(D, 0, cap); (*launches)++;
   }
   bool fair_trees = D.nTrees && (D.flags & KB_F_FAIR_SHARING);
   bool any_deep = false;
@@ -535,12 +535,12 @@ static int32_t launch_admit(kb_handle *h, int *launches) {
       int cap = pick_cap(h->max_tree_nodes);
       size_t sm = admit_smem(h->max_tree_nodes, D.FR, cap);
       CUDA_TRY(h, cudaFuncSetAttribute(k_admit<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
-      k_admit<true><<<D.nTrees, 128, sm, h->stream>>>(D, D.nLone, cap); (*launches)++;
+      k_admit<true><<<D.nTrees, KB_ADMIT_THREADS, sm, h->stream>>>(D, D.nLone, cap); (*launches)++;
     } else {
       int cap = pick_cap(0);
       size_t sm = admit_smem(0, D.FR, cap);
       CUDA_TRY(h, cudaFuncSetAttribute(k_admit<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
-      k_admit<false><<<D.nTrees, 128, sm, h->stream>>>(D, D.nLone, cap); (*launches)++;
+      k_admit<false><<<D.nTrees, KB_ADMIT_THREADS, sm, h->stream>>>(D, D.nLone, cap); (*launches)++;
     }
   }
   return KB_OK;

@@ -76,6 +76,7 @@ struct DevSnap {
   int32_t *root_cursor;  // [nRoots]
   int32_t *root_entries; // [H]
   int32_t *sorted;       // [H] entries of every root in iterator order (k_rank)
+  int32_t *pos_slot;     // [H] root slot of every position of root_entries (k_scatter)
   u64 *ekey;             // [H][4] iterator order key of every entry
   u64 *skey;             // [H][4] the same keys in root-segment order
   i64 *fs_over;          // [Q][R]  sum_f max(0, usage - SubtreeQuota)

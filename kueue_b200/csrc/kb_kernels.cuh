@@ -24,7 +24,7 @@
 // ---------------------------------------------------------------------------
 // K1: tree pass, one CTA per cohort-rooted tree.
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_tree(DevSnap D) {
+__global__ void __launch_bounds__(1024) k_tree(DevSnap D) {
   int t = blockIdx.x;
   int FR = D.FR;
   const int32_t *nodes = D.tree_nodes + D.tree_start[t];
@@ -897,6 +897,7 @@ __global__ void k_scatter(DevSnap D) {
   ulonglong2 *dst = (ulonglong2 *)(D.ekey + (size_t)e * 4);
   dst[0] = make_ulonglong2(k[0], k[1]); dst[1] = make_ulonglong2(k[2], k[3]);
   int pos = D.root_offset[slot] + base + __popc(m & ((1u << lane) - 1));
+  D.pos_slot[pos] = slot;
   ulonglong2 *sd = (ulonglong2 *)(D.skey + (size_t)pos * 4);  // the same key in segment order, for k_rank's scan
   sd[0] = make_ulonglong2(k[0], k[1]); sd[1] = make_ulonglong2(k[2], k[3]);
 }
@@ -919,25 +920,58 @@ __global__ void k_fair_prep(DevSnap D) {
 }
 
 // Rank of every entry among the entries of its root (roots with at most KB_RANK_CAP entries): a fully parallel
-// all-pairs count — the threads of a warp mostly share the root, so the scanned keys are broadcast loads.
+// all-pairs count.  The segments of the roots a CTA's 256 positions belong to are contiguous in skey; when that
+// span fits KB_RANK_STAGE keys it is staged in shared memory with coalesced loads and scanned from there
+// (threads of a warp mostly share the root -> broadcast reads), else the scan reads global memory.
 // Writes the root's entries in iterator order to D.sorted.
+#define KB_RANK_STAGE 1024
 __global__ void __launch_bounds__(256) k_rank(DevSnap D) {
-  int pos = blockIdx.x * blockDim.x + threadIdx.x;
-  if (pos >= D.H) return;
-  int e = D.root_entries[pos];
-  int slot = D.root_slot[D.wl_cq[D.heads[e]]];
-  int off = D.root_offset[slot], n = D.root_offset[slot + 1] - off;
-  if (n > KB_RANK_CAP) return;
-  const ulonglong2 *src = (const ulonglong2 *)(D.skey + (size_t)pos * 4);
-  ulonglong2 m0 = src[0], m1 = src[1];
-  u64 mine[4] = {m0.x, m0.y, m1.x, m1.y};
+  __shared__ ulonglong2 s_key[KB_RANK_STAGE * 2];
+  __shared__ int s_lo, s_hi;
+  const int p0 = blockIdx.x * blockDim.x;
+  const int plast = min(p0 + (int)blockDim.x, D.H) - 1;
+  const int pos = p0 + threadIdx.x;
+  if (threadIdx.x == 0) {
+    s_lo = D.root_offset[D.pos_slot[p0]];
+    s_hi = D.root_offset[D.pos_slot[plast] + 1];
+  }
+  int e = -1, off = 0, n = 0;
+  if (pos < D.H) {
+    e = D.root_entries[pos];
+    int slot = D.pos_slot[pos];
+    off = D.root_offset[slot]; n = D.root_offset[slot + 1] - off;
+  }
+  __syncthreads();
+  const int lo = s_lo, span = s_hi - lo;
+  const bool staged = span <= KB_RANK_STAGE;
+  if (staged) {
+    const ulonglong2 *g = (const ulonglong2 *)(D.skey + (size_t)lo * 4);
+    for (int i = threadIdx.x; i < span * 2; i += blockDim.x) s_key[i] = g[i];
+  }
+  __syncthreads();
+  if (e < 0 || n > KB_RANK_CAP) return;
   int rank = 0;
-  const ulonglong2 *seg = (const ulonglong2 *)(D.skey + (size_t)off * 4);
+  if (staged) {
+    ulonglong2 m0 = s_key[2 * (pos - lo)], m1 = s_key[2 * (pos - lo) + 1];
+    u64 mine[4] = {m0.x, m0.y, m1.x, m1.y};
+    const ulonglong2 *seg = s_key + 2 * (off - lo);
 #pragma unroll 4
-  for (int j = 0; j < n; j++) {
-    ulonglong2 a = seg[2 * j], b = seg[2 * j + 1];
-    u64 other[4] = {a.x, a.y, b.x, b.y};
-    rank += key4_less(other, mine) ? 1 : 0;
+    for (int j = 0; j < n; j++) {
+      ulonglong2 a = seg[2 * j], b = seg[2 * j + 1];
+      u64 other[4] = {a.x, a.y, b.x, b.y};
+      rank += key4_less(other, mine) ? 1 : 0;
+    }
+  } else {
+    const ulonglong2 *src = (const ulonglong2 *)(D.skey + (size_t)pos * 4);
+    ulonglong2 m0 = src[0], m1 = src[1];
+    u64 mine[4] = {m0.x, m0.y, m1.x, m1.y};
+    const ulonglong2 *seg = (const ulonglong2 *)(D.skey + (size_t)off * 4);
+#pragma unroll 4
+    for (int j = 0; j < n; j++) {
+      ulonglong2 a = seg[2 * j], b = seg[2 * j + 1];
+      u64 other[4] = {a.x, a.y, b.x, b.y};
+      rank += key4_less(other, mine) ? 1 : 0;
+    }
   }
   D.sorted[off + rank] = e;
 }
@@ -959,6 +993,7 @@ __global__ void __launch_bounds__(256) k_rank(DevSnap D) {
 //      and addUsage run lane-parallel with one __all_sync per entry.
 // ---------------------------------------------------------------------------
 #define KB_TILE 128
+#define KB_ADMIT_THREADS 256
 #define KB_LONE_CAP 256
 #define KB_LONE_WARPS 4
 #define KB_SORT_CAP 1024  // entries per root sortable in shared memory
@@ -1046,6 +1081,7 @@ __device__ inline unsigned char *stage_tables(const DevSnap &D, Tab<kSmem> &T, u
     size_t tb = (size_t)nn * FR;
     i64 *u = (i64 *)p, *sb = u + tb, *lq = sb + tb, *bl = lq + tb;
     int *lp = (int *)(bl + tb);
+#pragma unroll 4
     for (int i = threadIdx.x; i < nn * FR; i += blockDim.x) {
       int nd = nodes[i / FR], fr = i % FR;
       size_t c = (size_t)nd * FR + fr;
@@ -1139,6 +1175,69 @@ __device__ inline void commit_entry(const DevSnap &D, const Tab<kSmem> &T, int *
   __syncwarp();
 }
 
+// Commit loop of one tile for a FLAT cohort tree staged in shared memory (node 0 = root cohort, every other node a
+// ClusterQueue whose parent is the root).  Lane l owns columns l and l+32; the root's usage and SubtreeQuota of
+// those columns stay in registers for the whole tile, and the operands of entry i+1 that do not depend on earlier
+// commits (request row, localQuota, BorrowingLimit, nominal quota of its ClusterQueue) are loaded while entry i
+// is being decided, so the dependent chain per entry is one shared-memory load of the ClusterQueue's usage, the
+// available() arithmetic (resource_node.go:104-118 for a two-node path), one vote, and the addUsage stores.
+// Entries in Preempt mode, with targets, or after the shadow table went live take the generic commit_entry.
+__device__ inline void commit_tile_flat(const DevSnap &D, const Tab<true> &T, int *s_path, int lane, int tn, int base, const i64 *s_q,
+                                        const int *t_e, const int *t_node, const int *t_mode, const int *t_borrow,
+                                        const int *t_cq, const int *t_ntg, const int *t_toff) {
+  const int FR = D.FR;
+  const int fr0 = lane, fr1 = lane + 32;
+  const bool c0 = fr0 < FR, c1 = fr1 < FR;
+  i64 urt0 = c0 ? T.usage[fr0] : 0, urt1 = c1 ? T.usage[fr1] : 0;
+  const i64 srt0 = c0 ? T.sub[fr0] : 0, srt1 = c1 ? T.sub[fr1] : 0;
+  struct Ops { int e, nd, mode, ntg; i64 q0, q1, l0, l1, b0, b1, s0, s1; };
+  auto load = [&](int i, Ops &o) {
+    o.e = t_e[i]; o.nd = t_node[i]; o.mode = t_mode[i]; o.ntg = t_ntg[i];
+    o.q0 = c0 ? s_q[(size_t)i * FR + fr0] : -1; o.q1 = c1 ? s_q[(size_t)i * FR + fr1] : -1;
+    int r0 = o.nd * FR + fr0, r1 = o.nd * FR + fr1;
+    o.l0 = o.l1 = o.b0 = o.b1 = o.s0 = o.s1 = 0;
+    if (o.q0 > 0) { o.l0 = T.lq[r0]; o.b0 = T.bl[r0]; o.s0 = T.sub[r0]; }
+    if (o.q1 > 0) { o.l1 = T.lq[r1]; o.b1 = T.bl[r1]; o.s1 = T.sub[r1]; }
+  };
+  auto avail2 = [](i64 srt, i64 urt, i64 sub, i64 u, i64 l, i64 b) {  // available() of the ClusterQueue, root above it
+    i64 pa = srt - urt;
+    if (b != KB_NO_LIMIT) pa = imin((sub - l) - imax(0, u - l) + b, pa);
+    return imax(0, l - u) + pa;
+  };
+  Ops cur, nxt;
+  load(0, cur);
+  for (int i = 0; i < tn; i++) {
+    if (i + 1 < tn) load(i + 1, nxt);
+    if (lane == 0) D.rank[cur.e] = base + i;
+    if (cur.mode == KB_MODE_NOFIT) {
+      if (lane == 0) D.decision[cur.e] = KB_DEC_NOFIT;
+    } else if (cur.mode == KB_MODE_PREEMPT || cur.ntg > 0 || *T.shadow_on) {
+      if (c0) T.usage[fr0] = urt0;
+      if (c1) T.usage[fr1] = urt1;
+      __syncwarp();
+      commit_entry<true>(D, T, s_path, lane, cur.e, cur.nd, cur.mode, t_borrow[i], s_q + (size_t)i * FR, base + i, t_cq[i], cur.ntg, t_toff[i]);
+      __syncwarp();
+      if (c0) urt0 = T.usage[fr0];
+      if (c1) urt1 = T.usage[fr1];
+    } else {
+      i64 u0 = 0, u1 = 0;
+      bool ok = true;
+      if (cur.q0 > 0) { u0 = T.usage[cur.nd * FR + fr0]; if (imax(0, avail2(srt0, urt0, cur.s0, u0, cur.l0, cur.b0)) < cur.q0) ok = false; }
+      if (cur.q1 > 0) { u1 = T.usage[cur.nd * FR + fr1]; if (imax(0, avail2(srt1, urt1, cur.s1, u1, cur.l1, cur.b1)) < cur.q1) ok = false; }
+      ok = __all_sync(0xffffffffu, ok);
+      if (ok) {  // addUsage resource_node.go:137-145: the part above the ClusterQueue's local availability goes to the root
+        if (cur.q0 > 0) { i64 la = imax(0, cur.l0 - u0); T.usage[cur.nd * FR + fr0] = u0 + cur.q0; if (cur.q0 > la) urt0 += cur.q0 - la; }
+        if (cur.q1 > 0) { i64 la = imax(0, cur.l1 - u1); T.usage[cur.nd * FR + fr1] = u1 + cur.q1; if (cur.q1 > la) urt1 += cur.q1 - la; }
+      }
+      if (lane == 0) D.decision[cur.e] = ok ? KB_DEC_ASSUMED : KB_DEC_SKIPPED_NO_FIT;
+    }
+    cur = nxt;
+  }
+  if (c0) T.usage[fr0] = urt0;
+  if (c1) T.usage[fr1] = urt1;
+  __syncwarp();
+}
+
 // dense request row of entry e for column fr (absent = -1)
 __device__ __forceinline__ i64 entry_request(const DevSnap &D, int e, int fr) {
   const int R = D.R;
@@ -1171,7 +1270,7 @@ __device__ inline void expand_entry(const DevSnap &D, int e, i64 *qrow) {
 }
 
 template <bool kSmemTables>
-__global__ void __launch_bounds__(128) k_admit(DevSnap D, int slot_base, int sort_cap) {
+__global__ void __launch_bounds__(KB_ADMIT_THREADS) k_admit(DevSnap D, int slot_base, int sort_cap) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int FR = D.FR;
   int slot = slot_base + blockIdx.x;
@@ -1220,6 +1319,8 @@ __global__ void __launch_bounds__(128) k_admit(DevSnap D, int slot_base, int sor
   __syncthreads();
   // ---- 2. tiles: expand (all threads), commit (warp 0) ----
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // flat cohort (every ClusterQueue directly under the root), tables in shared memory, at most two columns per lane
+  const bool flat = kSmemTables && FR <= 64 && slot >= D.nLone && D.tree_flat[slot - D.nLone];
   for (int base = 0; base < n; base += KB_TILE) {
     int tn = min(KB_TILE, n - base);
     for (int i = threadIdx.x; i < tn; i += blockDim.x) {
@@ -1233,10 +1334,13 @@ __global__ void __launch_bounds__(128) k_admit(DevSnap D, int slot_base, int sor
     // one thread per entry walks its podset rows once and scatters the cells of its row
     for (int i = threadIdx.x; i < tn; i += blockDim.x) expand_entry(D, t_e[i], s_q + (size_t)i * FR);
     __syncthreads();
-    if (warp == 0)
-      for (int i = 0; i < tn; i++)
-        commit_entry<kSmemTables>(D, T, s_path, lane, t_e[i], t_node[i], t_mode[i], t_borrow[i], s_q + (size_t)i * FR, base + i,
-                                  t_cq[i], t_ntg[i], t_toff[i]);
+    if (warp == 0) {
+      if constexpr (kSmemTables) { if (flat) commit_tile_flat(D, T, s_path, lane, tn, base, s_q, t_e, t_node, t_mode, t_borrow, t_cq, t_ntg, t_toff); }
+      if (!flat)
+        for (int i = 0; i < tn; i++)
+          commit_entry<kSmemTables>(D, T, s_path, lane, t_e[i], t_node[i], t_mode[i], t_borrow[i], s_q + (size_t)i * FR, base + i,
+                                    t_cq[i], t_ntg[i], t_toff[i]);
+    }
     __syncthreads();
   }
   publish_usage<kSmemTables>(D, T, nodes, nn);
