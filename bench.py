@@ -150,7 +150,10 @@ def run_reference(args, rank, world):
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "int64", "data": "synthetic",
-            "config": {"workload": WORKLOADS[args.config], "heads": "all pending workloads"},
+            "config": {"workload": WORKLOADS[args.config],
+                       "heads": "all pending workloads (batched evaluator)" if HEADS[args.config] == "all" else "one head per ClusterQueue (reference cycle)",
+                       "decisions_per_step_per_gpu": snap.n_heads,
+                       "sample": "every step is one full pass of the N=1 snapshot on rank 0's host cores"},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "kind": "port",
                              "sample": f"{args.steps} full passes ({snap.n_heads} decisions each); C++ restatement of "
                                        "pkg/scheduler (Go toolchain absent), 1 thread like the reference's cycle"},

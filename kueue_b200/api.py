@@ -210,6 +210,7 @@ class MakeWorkload:
         self.admission: Optional[MakeAdmission] = None
         self.quota_reserved_ns: Optional[int] = None
         self.evicted = False
+        self.conditions: Dict[str, tuple] = {}  # type -> (status, reason, lastTransitionTime ns); SetStatusCondition keeps one per type
         self.last_tried: Optional[List[Dict[str, int]]] = None
         self.last_gen = 0
         MakeWorkload._uid += 1
@@ -223,6 +224,12 @@ class MakeWorkload:
     def Request(self, res: str, q): self.podsets[0].Request(res, q); return self
     def PodSets(self, *ps: MakePodSet): self.podsets = list(ps); return self
     def Evicted(self): self.evicted = True; return self
+
+    def Condition(self, type: str, status: bool, reason: str = "", last_transition_ns: int = 0):
+        self.conditions[type] = (bool(status), reason, int(last_transition_ns))
+        if type == "Evicted":
+            self.evicted = bool(status)
+        return self
 
     def ReserveQuota(self, a: MakeAdmission, at_ns: Optional[int] = None):
         self.admission = a
@@ -256,12 +263,33 @@ class Index:
         return self.flavors.index(flavor) * len(self.resources) + self.resources.index(res)
 
 
+def queue_order_timestamp(w: "MakeWorkload", pods_ready_requeuing: str = "Eviction", priority_sorting: bool = True) -> int:
+    """Ordering.GetQueueOrderTimestamp (pkg/workload/workload.go:1174-1193), in ns.
+
+    The timestamp the iterators (scheduler.go:808, fair_sharing_iterator.go:196) and the
+    LowerOrNewerEqualPriority policy (preemption_policy.go:39) compare: the PodsReady-timeout eviction time when
+    requeuing by eviction timestamp, the admission-check eviction time, the reclaim-while-borrowing preemption
+    time + 1 ms when priority sorting within the cohort is off, else the creation time."""
+    ev = w.conditions.get("Evicted")
+    if ev and ev[0]:
+        if pods_ready_requeuing == "Eviction" and ev[1] == "PodsReadyTimeout":
+            return ev[2]
+        if ev[1] == "AdmissionCheck":
+            return ev[2]
+    if not priority_sorting:
+        pre = w.conditions.get("Preempted")
+        if pre and pre[0] and pre[1] == "InCohortReclaimWhileBorrowing":
+            return pre[2] + 1_000_000
+    return w.creation_ns
+
+
 def flatten(cqs: Sequence[MakeClusterQueue], cohorts: Sequence[MakeCohort] = (),
             pending: Sequence[MakeWorkload] = (), admitted: Sequence[MakeWorkload] = (),
             usage: Optional[Dict[str, Dict[tuple, int]]] = None, flags: int = abi.FLAGS_DEFAULT,
             heads: Optional[Sequence[str]] = None, now_ns: int = 0,
             flavors: Optional[Sequence[str]] = None, extra_resources: Sequence[str] = (),
-            resource_flavors: Optional[Sequence["MakeResourceFlavor"]] = None):
+            resource_flavors: Optional[Sequence["MakeResourceFlavor"]] = None,
+            pods_ready_requeuing: str = "Eviction"):
     """Build (FlatSnapshot, Index).
 
     `usage` optionally overrides ClusterQueue usage as {cq: {(flavor, resource): int64}}
@@ -310,7 +338,7 @@ def flatten(cqs: Sequence[MakeClusterQueue], cohorts: Sequence[MakeCohort] = (),
     for n, holder in enumerate(list(cqs) + cohorts):
         par = holder.cohort if isinstance(holder, MakeClusterQueue) else holder.parent
         if par:
-            parent[n] = idx.node(par)
+            parent[n] = len(idx.cqs) + idx.cohorts.index(par)  # a parent is always a Cohort (a ClusterQueue may share its name)
         fw[n] = holder.fair_weight
         for rg in holder.resource_groups:
             mask = 0
@@ -377,7 +405,8 @@ def flatten(cqs: Sequence[MakeClusterQueue], cohorts: Sequence[MakeCohort] = (),
     p_req, p_mask, p_cnt, p_min, p_ok, p_lt = [], [], [], [], [], []
     for w in pending:
         assert w.cq is not None, f"pending workload {w.name} has no ClusterQueue"
-        w_cq.append(idx.cqs.index(w.cq)); w_pr.append(w.priority); w_ts.append(w.creation_ns); w_uid.append(w.uid)
+        w_cq.append(idx.cqs.index(w.cq)); w_pr.append(w.priority); w_uid.append(w.uid)
+        w_ts.append(queue_order_timestamp(w, pods_ready_requeuing, bool(flags & abi.F_PRIORITY_SORTING_WITHIN_COHORT)))
         w_lg.append(w.last_gen if w.last_tried is not None else -1)
         for pi, ps in enumerate(w.podsets):
             row = np.zeros(R, np.int64); mask = 0

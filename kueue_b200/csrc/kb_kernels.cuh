@@ -191,8 +191,9 @@ struct NomThread {
   bool need_search = false;
   __device__ __forceinline__ int simulate(const DevSnap &D, int wl, int cq, int fr, i64 val, int *borrow_after) {
     if (candidates_possible(D, cq)) need_search = true;
-    *borrow_after = 0;
-    return PM_NOCAND;  // preemption_oracle.go:52-54 when there are no candidates
+    bool may_reclaim;
+    *borrow_after = find_height(D, D.usage, cq, fr, val, &may_reclaim);
+    return PM_NOCAND;  // preemption_oracle.go:52-56 when there are no candidates: height on the untouched snapshot
   }
   __device__ __forceinline__ int get_targets(const DevSnap &D, int wl) {
     if (candidates_possible(D, D.wl_cq[wl])) need_search = true;
@@ -476,7 +477,7 @@ __device__ inline int assign_workload_coop(const DevSnap &D, bool *need_search, 
                 if (D.ps_flavor[(size_t)prow * R + r] == f) assumed += ps_request(D, prow, r, D.ps_count_out[prow], covers_pods);
               int b;
               int pm = cell_eval(D, cq, f * R + r, assumed, ps_request(D, row, r, count, covers_pods), &b);
-              if (pm == PM_NEED) { pm = PM_NOCAND; b = 0; need = need || cand_possible; }  // what the deferring oracle returns
+              if (pm == PM_NEED) { pm = PM_NOCAND; need = need || cand_possible; }  // what the deferring oracle returns (b = height on the untouched snapshot)
               if (pm != PM_FIT) reason = true;
               if (gm_preferred(rpm, rb, pm, b, pref)) { rpm = pm; rb = b; }
               if (rpm == PM_NOFIT) break;
@@ -665,7 +666,8 @@ struct NomSearch {
   __device__ inline void run_search(const DevSnap &D) { target_search<kSmem>(D, *T, c, S); }
   // SimulatePreemption preemption_oracle.go:41-71
   __device__ inline int simulate(const DevSnap &D, int wl, int cq, int fr, i64 val, int *borrow_after) {
-    *borrow_after = 0;
+    int hcq = T->handle(cq);
+    *borrow_after = T->find_height(hcq, fr, val);  // no candidates: height on the untouched snapshot (:53-56)
     if (!candidates_possible(D, cq)) return PM_NOCAND;
     c->cq = cq; c->prio = D.wl_priority[wl]; c->ts = D.wl_ts[wl];
     c->n_use = 1; c->use_fr[0] = fr; c->use_q[0] = val;
@@ -673,7 +675,6 @@ struct NomSearch {
     run_search(D);
     int nt = c->n_targets;
     if (nt == 0) return PM_NOCAND;
-    int hcq = T->handle(cq);
     for (int k = 0; k < nt; k++) T->remove_adm(S.tgt[k]);
     *borrow_after = T->find_height(hcq, fr, val);
     for (int k = 0; k < nt; k++) T->add_adm(S.tgt[k]);

@@ -85,3 +85,15 @@ def assign_stub(snap, wl, stub_mode=None, stub_borrow=None):
     mode = lib().ko_assign_stub(C.byref(s), C.c_int32(wl), sm.ctypes.data_as(P8), sb.ctypes.data_as(P32), fl.ctypes.data_as(P8),
                                 md.ctypes.data_as(P8), tr.ctypes.data_as(P8), C.byref(bor), use.ctypes.data_as(P64))
     return {"mode": mode, "flavor": fl, "res_mode": md, "tried": tr, "borrowing": bor.value, "usage": use}
+
+
+def resources_to_reserve(snap, cq, mode, borrowing, usage):
+    """resourcesToReserve (scheduler.go:530-548): usage / result are [F*R] arrays, -1 = absent cell."""
+    import numpy as np
+    s = snap.as_struct()
+    u = np.ascontiguousarray(usage, np.int64)
+    out = np.full(snap.n_fr, -1, np.int64)
+    rc = lib().ko_resources_to_reserve(C.byref(s), C.c_int32(cq), C.c_int32(mode), C.c_int32(borrowing),
+                                       u.ctypes.data_as(C.POINTER(C.c_int64)), out.ctypes.data_as(C.POINTER(C.c_int64)))
+    assert rc == 0, rc
+    return out

@@ -677,7 +677,7 @@ class Oracle {
     }
     PCtx c; c.p = p; c.frsNeed = {fr}; c.workloadUsage.add(fr, quantity);
     std::vector<Target> cand = getTargets(c);
-    if (cand.empty()) return {P_NOCAND, 0};
+    if (cand.empty()) return {P_NOCAND, findHeight(p.cq, fr, quantity).first};  // :53-56
     for (auto &t : cand) removeAdm(t.adm);
     int borrowAfter = findHeight(p.cq, fr, quantity).first;
     for (auto &t : cand) addAdm(t.adm);
@@ -1141,4 +1141,20 @@ int32_t ko_get_targets(const kb_snapshot *s, int32_t wl, const int8_t *ps_flavor
   return n;
 }
 
+
+// resourcesToReserve (scheduler.go:530-548) for one ClusterQueue and an explicit assignment, the surface
+// TestResourcesToReserve (scheduler_test.go:9705) checks.  usage / out: [F*R], -1 = cell absent.
+int32_t ko_resources_to_reserve(const kb_snapshot *s, int32_t cq, int32_t mode, int32_t borrowing, const int64_t *usage, int64_t *out) {
+  Oracle o(*s);
+  Entry e;
+  e.wl = -1;
+  PodSetAssign p;
+  p.count = 1; p.hasReasons = mode != KB_MODE_FIT; p.nFlavors = 1; p.flavor[0] = 0; p.mode[0] = (int8_t)mode;
+  e.a.ps.push_back(p);
+  e.a.borrowing = borrowing;
+  for (int fr = 0; fr < o.FR; fr++) { out[fr] = -1; if (usage[fr] >= 0) e.a.usage.add(fr, usage[fr]); }
+  UsageVec r = o.resourcesToReserve(e, cq);
+  for (auto &c : r.v) out[c.first] = c.second;
+  return 0;
+}
 }  // extern "C"

@@ -203,3 +203,35 @@ def test_full_size_config2(ev):
     snap = synth.make_snapshot(2)
     got, want = ev.run_cycle(snap), oracle.run_cycle(snap)
     assert_cycle_equal(got, want)
+
+
+def _entry_ordering_cases():
+    from tests.golden.schedule_cases import ENTRY_ORDERING_CASES
+    return [pytest.param(tc, id=f"order:{name[:60]}") for name, tc in ENTRY_ORDERING_CASES.items()]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tc", _entry_ordering_cases())
+def test_reference_entry_ordering_cycle(ev, tc):
+    """TestEntryOrdering (scheduler_test.go:8291) replayed as one cycle: the device's commit order is the
+    reference's wantOrder (and equals the oracle's)."""
+    from tests.schedule_golden import entry_ordering_snapshot, order_of
+    snap, idx, want_borrow = entry_ordering_snapshot(tc)
+    got, want = ev.run_cycle(snap), oracle.run_cycle(snap)
+    assert_cycle_equal(got, want)
+    assert (got.borrow == want_borrow).all()
+    assert order_of(got, tc) == tc["want"]
+
+
+def _schedule_cycle_cases():
+    from tests.test_oracle_golden_schedule_cycle import schedule_cases
+    return [pytest.param(n, id=f"schedule:{n[:60]}") for n in schedule_cases()]
+
+
+@pytest.mark.parametrize("name", _schedule_cycle_cases())
+def test_reference_schedule_scenarios_cycle(ev, name):
+    """TestSchedule (scheduler_test.go:69) replayed on the device: the reference's wantAssignments / preempted
+    workloads / skipped preemptions, and bit-exact agreement with the oracle."""
+    from tests.test_oracle_golden_schedule_cycle import DOC, check_schedule_case
+    snap, got = check_schedule_case(DOC["cases"][name], ev.run_cycle)
+    assert_cycle_equal(got, oracle.run_cycle(snap))

@@ -80,7 +80,7 @@ class Interp:
         if k == "type":
             return ("sym", n[1])
         if k == "func":
-            return None
+            return ("funclit", n[1]) if n[1] is not None else None
         if k == "unary":
             v = self.ev(n[2])
             if n[1] == "-":
@@ -175,6 +175,17 @@ class Interp:
                 return self.method(base, fn[2], [self.ev(a) for a in args])
         f = self.ev(fn)
         vals = [self.ev(a) for a in args]
+        if isinstance(f, tuple) and f[0] == "funclit":  # immediately-invoked helper: run its assignments, return its value
+            saved = dict(self.env)
+            try:
+                for kind, name, expr in f[1]:
+                    if kind == "assign":
+                        self.env[name] = self.ev(expr)
+                    else:
+                        return self.ev(expr)
+                return None
+            finally:
+                self.env = saved
         if isinstance(f, tuple) and f[0] == "method":
             return self.method(f[1], f[2], vals)
         if isinstance(f, tuple) and f[0] == "timefn":
@@ -209,6 +220,8 @@ class Interp:
             return Obj("PodSetAssignment", name=a[0], count=1, assignments={})
         if short == "MakeResourceFlavor":
             return Obj("ResourceFlavor", name=a[0], nodeLabels={}, taints=[], tolerations=[])
+        if short == "MakeLocalQueue":
+            return Obj("LocalQueue", name=a[0], ns=a[1], cq=None)
         return Obj(short, args=a)
 
     def method(self, o, m, a):
@@ -241,6 +254,9 @@ class Interp:
             if m == "Preemption": o["preemption"] = a[0]; return o
             if m == "FlavorFungibility": o["flavorFungibility"] = a[0]; return o
             if m == "QueueingStrategy": o["queueingStrategy"] = a[0]; return o
+            if m == "NamespaceSelector": o["namespaceSelector"] = a[0]; return o
+        if k == "LocalQueue":
+            if m == "ClusterQueue": o["cq"] = a[0]; return o
         if k == "Workload":
             if m == "Priority": o["priority"] = a[0]; return o
             if m == "Name": o["name"] = a[0]; return o
@@ -253,6 +269,7 @@ class Interp:
                 o["admission"] = strip(a[0]); o["reservedAt"] = a[1] if len(a) > 1 else NOW; o["conditions"] = []; return o
             if m in ("Condition", "SetOrReplaceCondition"): o["conditions"].append(a[0]); return o
             if m == "Admitted": return o
+            if m == "Admission": o["admission"] = strip(a[0]) if a[0] is not None else None; return o
             if m == "SimpleReserveQuota":  # wrappers.go:150-164: every request of podset 0 on one flavor, x Count
                 ps = o["podsets"][0]
                 o["admission"] = {"cq": a[0], "_kind": "Admission", "podsets": [{
@@ -264,6 +281,7 @@ class Interp:
             if m == "QuotaReservedTime": o["reservedAt"] = a[0]; return o
         if k == "PodSet":
             if m == "Request": o["requests"][a[0]] = a[1]; return o
+            if m == "Limit": o.setdefault("limits", {})[a[0]] = a[1]; return o
             if m == "SetMinimumCount": o["minCount"] = a[0]; return o
             if m == "Containers":
                 cs = [c for x in a for c in (x if isinstance(x, list) else [x])]

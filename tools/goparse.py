@@ -57,6 +57,11 @@ class Parser:
         self.i += 1
         return tok
 
+    def _skip_nl(self, j):
+        while self.t[j][0] == "nl":
+            j += 1
+        return j
+
     def expect(self, val):
         tok = self.next()
         if tok[1] != val:
@@ -162,18 +167,46 @@ class Parser:
                 return self.parse_comp_body(typ)
             return typ
         if tok[1] == "func":
-            # skip a function literal
+            # function literal: keep `name := expr` / `return expr` statements of the body (enough for the
+            # immediately-invoked table helpers); anything else makes the body opaque
             self.next()
             depth = 0
-            while True:
-                t = self.next()
-                if t[1] == "{":
-                    depth += 1
-                elif t[1] == "}":
-                    depth -= 1
-                    if depth == 0:
-                        break
-            return ("func", None)
+            while True:  # skip the signature up to the body's opening brace
+                t = self.peek()
+                if t[1] == "{" and depth == 0:
+                    break
+                depth += t[1] in ("(", "[")
+                depth -= t[1] in (")", "]")
+                self.next()
+            start = self.i
+            try:
+                self.expect("{")
+                stmts = []
+                while self.peek()[1] != "}":
+                    t = self.peek()
+                    if t[1] == "return":
+                        self.next()
+                        stmts.append(("return", None, self.parse_expr()))
+                    elif t[0] == "id" and self.t[self._skip_nl(self.i) + 1][1] in (":=", "="):
+                        name = self.next()[1]
+                        self.next()
+                        stmts.append(("assign", name, self.parse_expr()))
+                    else:
+                        raise SyntaxError("opaque statement")
+                self.expect("}")
+                return ("func", stmts)
+            except SyntaxError:
+                self.i = start
+                depth = 0
+                while True:
+                    t = self.next()
+                    if t[1] == "{":
+                        depth += 1
+                    elif t[1] == "}":
+                        depth -= 1
+                        if depth == 0:
+                            break
+                return ("func", None)
         if tok[0] == "id":
             self.next()
             return ("id", tok[1])
