@@ -120,7 +120,7 @@ def _selector_matches(sel, labels):
     return True
 
 
-def build_schedule_case(doc, tc):
+def build_schedule_case(doc, tc, capture=None):
     """One scheduling cycle of a TestSchedule case.  Returns (snap, idx, keys of the entries, info) where the host
     side does what the queue manager / cache do before schedule(): LocalQueue -> ClusterQueue resolution, inactive
     ClusterQueues (missing ResourceFlavor, cache/clusterqueue.go), namespace selector (scheduler.go:589-595), one head
@@ -163,6 +163,8 @@ def build_schedule_case(doc, tc):
             continue
         pending.append(w.ClusterQueue(cq))
     snap, idx = flatten(cqs, cohorts, pending=pending, admitted=admitted, flags=flags, now_ns=BASE, flavors=list(doc["resourceFlavors"]))
+    if capture is not None:
+        capture.update(cqs=cqs, cohorts=cohorts, pending=pending, admitted=admitted, flags=flags)
     return snap, idx, [w.name for w in pending], [w.name for w in admitted]
 
 
