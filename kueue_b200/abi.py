@@ -121,6 +121,10 @@ _DT = {
     "heads": np.int32,
 }
 ARRAY_FIELDS = list(_DT.keys())
+# tables the library keeps resident while kb_snapshot.static_generation is unchanged (include/kueue_b200.h)
+STATIC_FIELDS = ("parent", "fair_weight", "nominal", "borrow_limit", "lend_limit", "cq_within_cq", "cq_reclaim_within",
+                 "cq_borrow_within", "cq_has_bwc_threshold", "cq_bwc_threshold", "cq_when_can_borrow", "cq_when_can_preempt",
+                 "cq_preference", "cq_strategy", "cq_generation", "cq_rg_start", "rg_res_mask", "rg_flavor_start", "rg_flavors")
 
 
 def _ptr(arr: np.ndarray, ctype):
@@ -152,6 +156,7 @@ class FlatSnapshot:
 
     def set(self, name: str, value) -> None:
         self.arrays[name] = np.ascontiguousarray(value, dtype=_DT[name])
+        self.__dict__["_struct"] = None
 
     @property
     def n_nodes(self) -> int:
@@ -228,7 +233,13 @@ class FlatSnapshot:
         st = self.arrays["wl_ps_start"]; h = self.arrays["heads"]
         return int((st[h + 1] - st[h]).sum()) if len(h) else 0
 
-    def as_struct(self) -> kb_snapshot:
+    def as_struct(self, cached: bool = False) -> kb_snapshot:
+        """ctypes view of the snapshot.  cached=True reuses the struct built by the previous call (only the scalar
+        header is refreshed) — valid while no array was replaced through set()."""
+        if cached and getattr(self, "_struct", None) is not None:
+            s = self._struct
+            s.flags, s.now_ns, s.static_generation = self.flags, self.now_ns, self.static_generation
+            return s
         s = kb_snapshot()
         s.n_cq, s.n_cohort, s.n_flavor, s.n_resource = self.n_cq, self.n_cohort, self.n_flavor, self.n_resource
         s.n_rg, s.n_wl, s.n_podset, s.n_adm = self.n_rg, self.n_wl, self.n_podset, self.n_adm
@@ -240,6 +251,7 @@ class FlatSnapshot:
             arr = self.arrays[name]
             setattr(s, name, _ptr(arr, _CT[_DT[name]]))
         s._keepalive = self  # noqa: keep numpy buffers alive with the struct
+        self._struct = s
         return s
 
 

@@ -7,6 +7,8 @@
 #include <cstring>
 #include <string>
 #include <vector>
+#include <map>
+#include <mutex>
 
 #include "kb_kernels.cuh"
 
@@ -90,14 +92,28 @@ int32_t kb_version(void) { return KB_VERSION; }
 
 const char *kb_last_error(const kb_handle *h) { return h ? h->err.c_str() : g_err.c_str(); }
 
+// blocks handed out by kb_alloc_pinned: a span upload only ever reads inside ONE of them
+static std::mutex g_pin_mu;
+static std::map<uintptr_t, size_t> g_pinned;
+static bool inside_one_pinned_block(uintptr_t lo, uintptr_t hi) {
+  std::lock_guard<std::mutex> lk(g_pin_mu);
+  auto it = g_pinned.upper_bound(lo);
+  if (it == g_pinned.begin()) return false;
+  --it;
+  return lo >= it->first && hi <= it->first + it->second;
+}
+
 int32_t kb_alloc_pinned(void **ptr, uint64_t bytes) {
   if (!ptr) return KB_ERR_INVALID;
   cudaError_t e = cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocDefault);
   if (e != cudaSuccess) { g_err = cudaGetErrorString(e); return KB_ERR_CUDA; }
+  std::lock_guard<std::mutex> lk(g_pin_mu);
+  g_pinned[(uintptr_t)*ptr] = bytes ? bytes : 1;
   return KB_OK;
 }
 int32_t kb_free_pinned(void *ptr) {
   if (!ptr) return KB_OK;
+  { std::lock_guard<std::mutex> lk(g_pin_mu); g_pinned.erase((uintptr_t)ptr); }
   return cudaFreeHost(ptr) == cudaSuccess ? KB_OK : KB_ERR_CUDA;
 }
 
@@ -407,9 +423,16 @@ static int32_t upload_impl(kb_handle *h, const kb_snapshot *s, bool sync) {
   if (!h->search_smem) need(G * ncap * FR, 8);
   bool fair = (s->flags & KB_F_FAIR_SHARING) != 0;
   if (fair) { need(H * FR, 8); need(H * (48 + 16 * KB_MAX_DEPTH), 1); need(N, 4); need(N, 4); }
-  if (!h->arena.reserve(tot + 4096)) return fail(h, KB_ERR_CUDA, "cudaMalloc failed");
+  const size_t span_cap = tot;  // the input tables are part of tot: a span of up to that size is covered by the slack below
+  if (!h->arena.reserve(tot + tot / 2 + (1u << 20))) return fail(h, KB_ERR_CUDA, "cudaMalloc failed");
   h->arena.reset();
-#define UP(field, src, n) CUDA_TRY(h, up(h, h->arena, D.field, src, (size_t)(n), &bytes))
+  // Per-cycle input tables.  The caller's tables (dynamic part of kb_snapshot) usually sit close together in
+  // one pinned block (kb_alloc_pinned carved by the shim): when their host span is not much larger than their
+  // total size the whole span goes to the device with ONE DMA and the device tables alias into it at the same
+  // offsets; otherwise every table is copied on its own.
+  struct Tab { const void *src; size_t bytes; const void **dst; };
+  std::vector<Tab> tabs;
+#define UP(field, src, n) tabs.push_back(Tab{(const void *)(src), (size_t)(n) * sizeof(*D.field), (const void **)&D.field})
   UP(cq_usage, (const i64 *)s->cq_usage, (size_t)Q * FR);
   UP(wl_cq, s->wl_cq, W); UP(wl_priority, s->wl_priority, W); UP(wl_ts, (const i64 *)s->wl_ts, W); UP(wl_uid, (const i64 *)s->wl_uid, W);
   UP(wl_last_gen, (const i64 *)s->wl_last_gen, W); UP(wl_ps_start, s->wl_ps_start, W + 1);
@@ -419,10 +442,33 @@ static int32_t upload_impl(kb_handle *h, const kb_snapshot *s, bool sync) {
   UP(adm_qr_ts, (const i64 *)s->adm_qr_ts, A); UP(adm_uid, (const i64 *)s->adm_uid, A); UP(adm_evicted, s->adm_evicted, A);
   UP(adm_use_start, s->adm_use_start, A + 1); UP(adm_use_fr, s->adm_use_fr, s->n_adm_use); UP(adm_use_qty, (const i64 *)s->adm_use_qty, s->n_adm_use);
   UP(heads, s->heads, H);
+  size_t caller_tabs = tabs.size();
   UP(adm_sorted, h->adm_sorted.data(), h->adm_sorted.size()); UP(root_adm_start, h->root_adm_start.data(), nroots + 1);
   UP(cq_adm_start, h->cq_adm_start.data(), Q + 1); UP(cq_adm, h->cq_adm.data(), h->cq_adm.size());
   UP(adm_rank, h->adm_rank.data(), h->adm_rank.size()); UP(cq_adm_nev, h->cq_adm_nev.data(), h->cq_adm_nev.size());
 #undef UP
+  {
+    uintptr_t lo = UINTPTR_MAX, hi = 0; size_t sum = 0;
+    for (size_t i = 0; i < caller_tabs; i++) {
+      if (!tabs[i].bytes) continue;
+      if (!tabs[i].src) return fail(h, KB_ERR_INVALID, "null table with non-zero length");
+      lo = std::min(lo, (uintptr_t)tabs[i].src); hi = std::max(hi, (uintptr_t)tabs[i].src + tabs[i].bytes); sum += tabs[i].bytes;
+    }
+    uintptr_t lo_al = lo & ~(uintptr_t)255;
+    bool span = sum > 0 && (hi - lo) <= sum + sum / 4 + (64u << 10) && (hi - lo) <= span_cap && inside_one_pinned_block(lo_al, hi);
+    char *dspan = span ? h->arena.take<char>(hi - lo_al) : nullptr;
+    if (span) {
+      CUDA_TRY(h, cudaMemcpyAsync(dspan, (const void *)lo_al, hi - lo_al, cudaMemcpyHostToDevice, h->stream));
+      bytes += (int64_t)(hi - lo_al);
+    }
+    for (size_t i = 0; i < tabs.size(); i++) {
+      const Tab &t = tabs[i];
+      if (span && i < caller_tabs && t.bytes) { *t.dst = dspan + ((uintptr_t)t.src - lo_al); continue; }
+      char *d = h->arena.take<char>(t.bytes);
+      *t.dst = d;
+      if (t.bytes) { CUDA_TRY(h, cudaMemcpyAsync(d, t.src, t.bytes, cudaMemcpyHostToDevice, h->stream)); bytes += (int64_t)t.bytes; }
+    }
+  }
   D.over_list = h->arena.take<int32_t>(Q); D.over_count = h->arena.take<int32_t>(nroots);
   D.subtree = h->arena.take<i64>(NF); D.usage = h->arena.take<i64>(NF);
   D.avail = h->arena.take<i64>(NF); D.potential = h->arena.take<i64>(NF);

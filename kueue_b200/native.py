@@ -55,13 +55,27 @@ def pinned_array(shape, dtype) -> "np.ndarray":
 
 
 def pin_snapshot(snap: abi.FlatSnapshot) -> abi.FlatSnapshot:
-    """Copy of `snap` whose arrays live in pinned host memory."""
+    """Copy of `snap` whose arrays live in ONE block of pinned host memory (256 B aligned sub-arrays, the static
+    tables first).  The library recognises per-cycle tables that sit close together in host memory and moves them
+    with a single DMA (span upload, kb_api.cu) — the layout the Go shim gets by carving its SoA buffers out of one
+    kb_alloc_pinned block."""
+    import numpy as np
     out = abi.FlatSnapshot(n_cq=snap.n_cq, n_cohort=snap.n_cohort, n_flavor=snap.n_flavor, n_resource=snap.n_resource,
                            pods_resource=snap.pods_resource, flags=snap.flags, now_ns=snap.now_ns)
-    for k, v in snap.arrays.items():
-        a = pinned_array(v.shape, v.dtype)
+    static = [k for k in snap.arrays if k in abi.STATIC_FIELDS]
+    order = static + [k for k in snap.arrays if k not in abi.STATIC_FIELDS]
+    pad = lambda n: (max(1, n) + 255) & ~255  # noqa: E731
+    total = sum(pad(snap.arrays[k].nbytes) for k in order)
+    block = pinned_array((total,), np.uint8)
+    off = 0
+    for k in order:
+        v = snap.arrays[k]
+        a = block[off:off + v.nbytes].view(v.dtype).reshape(v.shape)
         a[...] = v
         out.arrays[k] = a
+        off += pad(v.nbytes)
+    out._pinned_block = block
+    out.static_generation = snap.static_generation
     return out
 
 
@@ -115,7 +129,7 @@ class Evaluator:
 
     def run_cycle(self, snap: abi.FlatSnapshot, out: abi.CycleOut | None = None) -> abi.CycleOut:
         out = out or abi.CycleOut(snap)
-        s = snap.as_struct()
+        s = snap.as_struct(cached=True)
         self._check(lib().kb_run_cycle(self._h, C.byref(s), C.byref(out.struct)))
         out.n_targets = out.struct.n_targets
         return out

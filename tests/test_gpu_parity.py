@@ -235,3 +235,20 @@ def test_reference_schedule_scenarios_cycle(ev, name):
     from tests.test_oracle_golden_schedule_cycle import DOC, check_schedule_case
     snap, got = check_schedule_case(DOC["cases"][name], ev.run_cycle)
     assert_cycle_equal(got, oracle.run_cycle(snap))
+
+
+def test_span_upload_from_one_pinned_block(ev):
+    """Tables carved out of one kb_alloc_pinned block travel in a single DMA (span upload) — same decisions."""
+    from kueue_b200 import native
+    for make in (lambda: synth.make_snapshot(3, W=3000, Q=300, preemption=True, heads="one_per_cq", tight=1.1),
+                 lambda: synth.make_snapshot(4, W=4000, Q=200, heads="one_per_cq", tight=1.1),
+                 lambda: synth.make_snapshot(2, W=5000, Q=50, podsets_max=3)):
+        snap = make()
+        pinned = native.pin_snapshot(snap)
+        cap = 40 * snap.n_adm + 10000
+        want = oracle.run_cycle(snap, cap)
+        got = ev.run_cycle(pinned, abi.CycleOut(pinned, cap))
+        assert_cycle_equal(got, want)
+        pinned.static_generation = 7
+        assert_cycle_equal(ev.run_cycle(pinned, abi.CycleOut(pinned, cap)), want)
+        assert_cycle_equal(ev.run_cycle(pinned, abi.CycleOut(pinned, cap)), want)  # static tables reused, span upload again
