@@ -411,7 +411,15 @@ static int32_t upload_impl(kb_handle *h, const kb_snapshot *s, bool sync) {
     size_t tb = (size_t)h->max_tree_nodes * FR * 32 + (size_t)h->max_tree_nodes * 4 + 64;
     h->search_smem = tb <= 190 * 1024;
     h->search_smem_bytes = h->search_smem ? tb : 0;
-    int per_sm = !h->search_smem ? 8 : (tb <= 6 * 1024 ? 32 : (tb <= 12 * 1024 ? 16 : (tb <= 24 * 1024 ? 8 : (tb <= 48 * 1024 ? 4 : (tb <= 100 * 1024 ? 2 : 1)))));
+    // resident single-warp CTAs per SM as the occupancy calculator sees them (registers / shared memory)
+    int per_sm = 1;
+    if (h->search_smem) {
+      cudaFuncSetAttribute(k_nominate_search<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_nominate_search<true>, 32, h->search_smem_bytes);
+    } else {
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_nominate_search<false>, 32, 0);
+    }
+    per_sm = std::max(1, std::min(per_sm, 16));
     h->search_grid = std::max(1, std::min(h->sm_count * per_sm, std::max(1, s->n_heads)));
     if (A == 0) h->search_grid = 1;
   }
@@ -421,6 +429,9 @@ static int32_t upload_impl(kb_handle *h, const kb_snapshot *s, bool sync) {
   need(A, 1); need(A, 4); need(nroots, 4); need(A ? NF : 1, 8);
   need(G * acap, 4); need(G * acap, 4); need(G * acap, 4); need(G * acap, 4); need(G * ncap, 4); need(G * acap, 1); need(G * acap, 1); need(G * ncap, 1); need(G * ncap, 1);
   if (!h->search_smem) need(G * ncap * FR, 8);
+  size_t GL = A ? G * 32 : 1, lcap = std::min<size_t>(acap, 8192);
+  need(GL * lcap, 4); need(GL * lcap, 4); need(GL * lcap, 4); need(GL * ncap, 4); need(GL * lcap, 1); need(GL * lcap, 1); need(GL * ncap, 1); need(GL * ncap, 1);
+  need(GL * ncap, 8); need(GL * sizeof(PreCtx), 1);
   bool fair = (s->flags & KB_F_FAIR_SHARING) != 0;
   if (fair) { need(H * FR, 8); need(H * (48 + 16 * KB_MAX_DEPTH), 1); need(N, 4); need(N, 4); }
   const size_t span_cap = tot;  // the input tables are part of tot: a span of up to that size is covered by the slack below
@@ -493,6 +504,12 @@ static int32_t upload_impl(kb_handle *h, const kb_snapshot *s, bool sync) {
   D.sc_cq_class = h->arena.take<int8_t>(G * ncap); D.sc_on_path = h->arena.take<int8_t>(G * ncap);
   D.sc_usage = h->search_smem ? nullptr : h->arena.take<i64>(G * ncap * FR);
   D.sc_adm_cap = (int)acap; D.sc_node_cap = (int)ncap;
+  D.sl_cand = h->arena.take<int32_t>(GL * lcap); D.sl_tgt = h->arena.take<int32_t>(GL * lcap); D.sl_aux1 = h->arena.take<int32_t>(GL * lcap);
+  D.sl_cq_lca = h->arena.take<int32_t>(GL * ncap);
+  D.sl_variant = h->arena.take<uint8_t>(GL * lcap); D.sl_tgt_reason = h->arena.take<uint8_t>(GL * lcap);
+  D.sl_cq_class = h->arena.take<int8_t>(GL * ncap); D.sl_on_path = h->arena.take<int8_t>(GL * ncap);
+  D.sl_col = h->arena.take<i64>(GL * ncap); D.sl_ctx = h->arena.take<unsigned char>(GL * sizeof(PreCtx));
+  D.sl_adm_cap = (int)lcap;
   if (fair) {
     D.q_scratch = h->arena.take<i64>(H * FR); D.fs_state = h->arena.take<unsigned char>(H * (48 + 16 * KB_MAX_DEPTH));
     D.fs_cq_entry = h->arena.take<int32_t>(N); D.fs_winner = h->arena.take<int32_t>(N);

@@ -107,6 +107,11 @@ struct DevSnap {
   int32_t *sc_cand, *sc_tgt, *sc_cq_lca, *sc_aux1, *sc_aux2; uint8_t *sc_variant, *sc_tgt_reason; int8_t *sc_cq_class, *sc_on_path;
   i64 *sc_usage;
   int sc_adm_cap, sc_node_cap;
+  // per-LANE scratch of the speculative single-cell searches (k_nominate_search phase A)
+  int32_t *sl_cand, *sl_tgt, *sl_cq_lca, *sl_aux1; uint8_t *sl_variant, *sl_tgt_reason; int8_t *sl_cq_class, *sl_on_path;
+  i64 *sl_col;            // [G*32][node cap] one usage column per lane
+  unsigned char *sl_ctx;  // [G*32] PreCtx
+  int sl_adm_cap;
   // ---- fair-sharing scratch ----
   i64 *q_scratch;        // [H][FR] dense Assignment.Usage.Quota per entry (absent = -1)
   unsigned char *fs_state; // [H] x (48 + 16*KB_MAX_DEPTH) B: per-entry tournament state when it does not fit shared memory

@@ -658,28 +658,41 @@ __global__ void k_over(DevSnap D) {
 // ---------------------------------------------------------------------------
 // Oracle policy of k_nominate_search: flavor assignment and target searches of one deferred
 // entry run on lane 0 of a single-warp CTA (single writer of the output rows).
+// SimulatePreemption preemption_oracle.go:41-71 on the private tree T (full, or the single column `fr`).
+template <bool kSmem>
+__device__ inline int simulate_on(const DevSnap &D, const PTab<kSmem> &T, PreCtx *c, const PreScratch &S, int wl, int cq, int fr, i64 val,
+                                  int *borrow_after) {
+  int hcq = T.handle(cq);
+  *borrow_after = T.find_height(hcq, fr, val);  // no candidates: height on the untouched snapshot (:53-56)
+  c->overflow = 0;
+  if (!candidates_possible(D, cq)) return PM_NOCAND;
+  c->cq = cq; c->prio = D.wl_priority[wl]; c->ts = D.wl_ts[wl];
+  c->n_use = 1; c->use_fr[0] = fr; c->use_q[0] = val;
+  c->n_need = 1; c->need_fr[0] = fr;
+  target_search<kSmem>(D, T, c, S);
+  int nt = c->n_targets;
+  if (nt == 0) return PM_NOCAND;
+  for (int k = 0; k < nt; k++) T.remove_adm(S.tgt[k]);
+  *borrow_after = T.find_height(hcq, fr, val);
+  for (int k = 0; k < nt; k++) T.add_adm(S.tgt[k]);
+  for (int k = 0; k < nt; k++) if (D.adm_cq[S.tgt[k]] == cq) return PM_PREEMPT;
+  return PM_RECLAIM;
+}
+
+// Results of the speculative lane-parallel oracle calls of one entry (k_nominate_search phase A): the sequential
+// flavor walk looks a (cell, quantity) up here before running the search itself.
+struct SimMemo { i64 val; int pm, borrow; };
+
 template <bool kSmem>
 struct NomSearch {
   const PTab<kSmem> *T;
   PreCtx *c;
   PreScratch S;
+  const SimMemo *memo;  // [FR] or nullptr
   __device__ inline void run_search(const DevSnap &D) { target_search<kSmem>(D, *T, c, S); }
-  // SimulatePreemption preemption_oracle.go:41-71
   __device__ inline int simulate(const DevSnap &D, int wl, int cq, int fr, i64 val, int *borrow_after) {
-    int hcq = T->handle(cq);
-    *borrow_after = T->find_height(hcq, fr, val);  // no candidates: height on the untouched snapshot (:53-56)
-    if (!candidates_possible(D, cq)) return PM_NOCAND;
-    c->cq = cq; c->prio = D.wl_priority[wl]; c->ts = D.wl_ts[wl];
-    c->n_use = 1; c->use_fr[0] = fr; c->use_q[0] = val;
-    c->n_need = 1; c->need_fr[0] = fr;
-    run_search(D);
-    int nt = c->n_targets;
-    if (nt == 0) return PM_NOCAND;
-    for (int k = 0; k < nt; k++) T->remove_adm(S.tgt[k]);
-    *borrow_after = T->find_height(hcq, fr, val);
-    for (int k = 0; k < nt; k++) T->add_adm(S.tgt[k]);
-    for (int k = 0; k < nt; k++) if (D.adm_cq[S.tgt[k]] == cq) return PM_PREEMPT;
-    return PM_RECLAIM;
+    if (memo && memo[fr].val == val) { *borrow_after = memo[fr].borrow; return memo[fr].pm; }
+    return simulate_on<kSmem>(D, *T, c, S, wl, cq, fr, val, borrow_after);
   }
   // GetTargets preemption.go:127-146 for the assignment currently in the output rows
   __device__ inline int get_targets(const DevSnap &D, int wl) {
@@ -715,8 +728,11 @@ __global__ void __launch_bounds__(32) k_nominate_search(DevSnap D) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ PreCtx ctx;
   __shared__ int s_item;
-  const int FR = D.FR;
-  PreScratch S;
+  __shared__ SimMemo s_memo[KB_MAX_CELLS];
+  const int FR = D.FR, R = D.R;
+  const int lane = threadIdx.x;
+  PreScratch S;   // scratch of the CTA's sequential searcher (lane 0)
+  PreScratch SL;  // scratch of this lane's speculative single-cell searches
   {
     size_t b = blockIdx.x;
     S.cand = D.sc_cand + b * D.sc_adm_cap; S.variant = D.sc_variant + b * D.sc_adm_cap;
@@ -724,7 +740,16 @@ __global__ void __launch_bounds__(32) k_nominate_search(DevSnap D) {
     S.cq_class = D.sc_cq_class + b * D.sc_node_cap; S.on_path = D.sc_on_path + b * D.sc_node_cap;
     S.cq_lca = D.sc_cq_lca + b * D.sc_node_cap;
     S.aux1 = D.sc_aux1 + b * D.sc_adm_cap; S.aux2 = D.sc_aux2 + b * D.sc_adm_cap;
+    S.cap = D.sc_adm_cap;
+    size_t w = b * 32 + lane;
+    SL.cand = D.sl_cand + w * D.sl_adm_cap; SL.variant = D.sl_variant + w * D.sl_adm_cap;
+    SL.tgt = D.sl_tgt + w * D.sl_adm_cap; SL.tgt_reason = D.sl_tgt_reason + w * D.sl_adm_cap;
+    SL.cq_class = D.sl_cq_class + w * D.sc_node_cap; SL.on_path = D.sl_on_path + w * D.sc_node_cap;
+    SL.cq_lca = D.sl_cq_lca + w * D.sc_node_cap;
+    SL.aux1 = D.sl_aux1 + w * D.sl_adm_cap; SL.aux2 = nullptr;  // aux2 is only used by the fair search (never speculative)
+    SL.cap = D.sl_adm_cap;
   }
+  PreCtx *lctx = (PreCtx *)D.sl_ctx + (size_t)blockIdx.x * 32 + lane;
   PTab<kSmem> T;
   T.D = &D; T.FR = FR;
   int cur_slot = -1;
@@ -760,8 +785,37 @@ __global__ void __launch_bounds__(32) k_nominate_search(DevSnap D) {
       }
       __syncthreads();
     }
+    // ---- phase A: the oracle calls of the entry's first podset are independent single-cell searches
+    //      (one flavor-resource column each) -> one per lane, on a private copy of that column.  Classical
+    //      preemption only: the fair search reads every column for the DominantResourceShare.
+    const bool speculate = !(D.flags & KB_F_FAIR_SHARING);
+    if (speculate) {
+      for (int c = lane; c < FR; c += 32) s_memo[c].val = -1;
+      const int row = D.wl_ps_start[wl];
+      const bool covers_pods = D.pods_res >= 0 && rg_by_resource(D, cq, D.pods_res) >= 0;
+      for (int c = lane; c < FR; c += 32) {
+        int f = c / R, r = c % R;
+        if (!((D.ps_req_mask[row] >> r) & 1) || !((D.ps_flavor_ok[row] >> f) & 1)) continue;
+        int g = rg_by_resource(D, cq, r);
+        if (g < 0) continue;
+        bool in_rg = false;
+        for (int k = D.rg_flavor_start[g]; k < D.rg_flavor_start[g + 1]; k++) in_rg |= D.rg_flavors[k] == f;
+        if (!in_rg) continue;
+        i64 req = ps_request(D, row, r, D.ps_count[row], covers_pods);
+        int b0;
+        if (cell_eval(D, cq, c, 0, req, &b0) != PM_NEED) continue;
+        PTab<kSmem> TL = T;  // same static tables, private usage column
+        TL.col_fr = c;
+        TL.usage = D.sl_col + ((size_t)blockIdx.x * 32 + lane) * D.sc_node_cap;
+        for (int h = 0; h < T.nn; h++) TL.usage[h] = D.usage[(size_t)T.nodes[h] * FR + c];
+        int borrow;
+        int pm = simulate_on<kSmem>(D, TL, lctx, SL, wl, cq, c, req, &borrow);
+        if (!lctx->overflow) { s_memo[c].pm = pm; s_memo[c].borrow = borrow; s_memo[c].val = req; }
+      }
+    }
+    __syncwarp();
     if (threadIdx.x == 0) {
-      NomSearch<kSmem> orc{&T, &ctx, S};
+      NomSearch<kSmem> orc{&T, &ctx, S, speculate ? s_memo : nullptr};
       int borrowing, nt;
       int mode = get_assignments(D, orc, wl, &borrowing, &nt);
       D.mode[e] = (uint8_t)mode;

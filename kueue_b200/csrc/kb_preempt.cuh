@@ -26,11 +26,13 @@ struct PTab {
   const DevSnap *D;
   const int32_t *nodes;  // local -> global node id
   int nn, FR;
-  i64 *usage;            // [nn][FR] private copy (smem or global scratch)
+  i64 *usage;            // [nn][FR] private copy (smem or global scratch); [nn] in column mode
+  int col_fr = -1;       // column mode: the view holds ONE flavor-resource column (single-cell searches of the
+                         // preemption oracle only ever read and write that column: columns are independent)
   const i64 *sub, *lq, *bl;  // smem copies (kSmem) — unused otherwise
   const int *lparent;        // smem (kSmem) — unused otherwise
-  __device__ __forceinline__ i64 U(int h, int fr) const { return usage[h * FR + fr]; }
-  __device__ __forceinline__ void setU(int h, int fr, i64 v) const { usage[h * FR + fr] = v; }
+  __device__ __forceinline__ i64 U(int h, int fr) const { return usage[col_fr >= 0 ? h : h * FR + fr]; }
+  __device__ __forceinline__ void setU(int h, int fr, i64 v) const { usage[col_fr >= 0 ? h : h * FR + fr] = v; }
   __device__ __forceinline__ i64 Sub(int h, int fr) const { return kSmem ? sub[h * FR + fr] : D->subtree[(size_t)nodes[h] * FR + fr]; }
   __device__ __forceinline__ i64 LQ(int h, int fr) const {
     if (kSmem) return lq[h * FR + fr];
@@ -94,11 +96,11 @@ struct PTab {
   }
   __device__ inline void remove_adm(int a) const {  // Snapshot.RemoveWorkload snapshot.go:49-55
     int h = handle(D->adm_cq[a]);
-    for (int k = D->adm_use_start[a]; k < D->adm_use_start[a + 1]; k++) remove(h, D->adm_use_fr[k], D->adm_use_qty[k]);
+    for (int k = D->adm_use_start[a]; k < D->adm_use_start[a + 1]; k++) { int fr = D->adm_use_fr[k]; if (col_fr < 0 || fr == col_fr) remove(h, fr, D->adm_use_qty[k]); }
   }
   __device__ inline void add_adm(int a) const {  // Snapshot.AddWorkload :59-64
     int h = handle(D->adm_cq[a]);
-    for (int k = D->adm_use_start[a]; k < D->adm_use_start[a + 1]; k++) add(h, D->adm_use_fr[k], D->adm_use_qty[k]);
+    for (int k = D->adm_use_start[a]; k < D->adm_use_start[a + 1]; k++) { int fr = D->adm_use_fr[k]; if (col_fr < 0 || fr == col_fr) add(h, fr, D->adm_use_qty[k]); }
   }
 };
 
@@ -110,6 +112,7 @@ struct PreCtx {
   int plen; int path[KB_MAX_DEPTH + 1]; int adv_at[KB_MAX_DEPTH + 1];
   int seg_count[6];
   int n_all, n_targets;
+  int overflow;  // the candidate list did not fit the scratch of this searcher (speculative lane searches only)
 };
 
 // per-CTA global scratch
@@ -122,6 +125,7 @@ struct PreScratch {
   int8_t *on_path;   // per tree node (handle): level on the preemptor's path or -1
   int32_t *cq_lca;   // per tree node (handle): handle of the subtree root that collected it
   int32_t *aux1, *aux2;  // [adm cap] fair sharing: next-in-queue links, retry candidates
+  int cap;               // capacity of the [adm cap] arrays
 };
 
 __device__ __forceinline__ bool satisfies_policy(const DevSnap &D, const PreCtx &c, int a, int policy) {  // preemption_policy.go:30-48
@@ -239,6 +243,7 @@ __device__ inline void classical_search(const DevSnap &D, const PTab<kSmem> &T, 
       adv = adv || fits;
     }
     c->n_targets = 0;
+    c->overflow = 0;
   }
   for (int h = 0; h < T.nn; h++) S.on_path[h] = -1;
   for (int k = 0; k < c->plen; k++) S.on_path[c->path[k]] = (int8_t)k;
@@ -273,6 +278,7 @@ __device__ inline void classical_search(const DevSnap &D, const PTab<kSmem> &T, 
       int a = D.cq_adm[i];
       int v = classify_variant(D, *c, a, cls == 0);
       if (v == PV_NEVER) continue;
+      if (nall >= S.cap) { c->overflow = 1; return; }
       int seg = (D.adm_evicted[a] ? 0 : 3) + cls;
       S.cand[nall] = a; S.variant[nall] = (uint8_t)v; S.aux1[nall] = (seg << 28) | D.adm_rank[a];
       nall++;
@@ -285,6 +291,7 @@ __device__ inline void classical_search(const DevSnap &D, const PTab<kSmem> &T, 
     int h = T.handle(q);
     if (h != hcq && S.cq_class[h]) gather(q, S.cq_class[h] - 1);
   }
+  if (c->overflow) { c->n_targets = 0; return; }
   sort_candidates(S.aux1, S.cand, S.variant, nall);
   // ---- 4. greedy remove / fill back
   {
@@ -389,6 +396,7 @@ __device__ inline void fair_search(const DevSnap &D, const PTab<kSmem> &T, PreCt
     for (int t = hcq; t >= 0; t = T.parent(t)) c->path[pl++] = t;
     c->plen = pl;
     c->n_targets = 0;
+    c->overflow = 0;
   }
   for (int h = 0; h < T.nn; h++) { S.on_path[h] = -1; S.cq_class[h] = 0; S.cq_lca[h] = -1; }
   for (int k = 1; k < c->plen; k++) S.on_path[c->path[k]] = (int8_t)k;  // preemptorAncestors
