@@ -90,7 +90,10 @@ enum {
   KB_F_FS_PREEMPT_WITHIN_NOMINAL = 1u << 5,    /* preemption.go:350                                    */
   KB_F_FS_STRATEGY_S2A = 1u << 6,              /* LessThanOrEqualToFinalShare configured (strategy.go) */
   KB_F_FS_STRATEGY_S2B = 1u << 7,              /* LessThanInitialShare configured                      */
-  KB_F_FS_STRATEGY_S2B_FIRST = 1u << 8         /* strategies = [S2-b, ...] instead of [S2-a, S2-b]     */
+  KB_F_FS_STRATEGY_S2B_FIRST = 1u << 8,        /* strategies = [S2-b, ...] instead of [S2-a, S2-b]     */
+  KB_F_TS_PREEMPTION_BUFFER = 1u << 9          /* features.SchedulerTimestampPreemptionBuffer (alpha, default off):
+                                                  LowerOrNewerEqualPriority needs the candidate > 5 min newer
+                                                  (preemption_policy.go:28,44-46)                       */
 };
 #define KB_FLAGS_DEFAULT (KB_F_PARTIAL_ADMISSION | KB_F_FLAVOR_FUNGIBILITY | \
   KB_F_PRIORITY_SORTING_WITHIN_COHORT | KB_F_FS_PRIORITIZE_NON_BORROWING |   \

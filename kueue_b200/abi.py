@@ -32,6 +32,7 @@ F_FAIR_SHARING = 1 << 0
 F_PARTIAL_ADMISSION = 1 << 1
 F_FLAVOR_FUNGIBILITY = 1 << 2
 F_PRIORITY_SORTING_WITHIN_COHORT = 1 << 3
+F_TS_PREEMPTION_BUFFER = 1 << 9
 F_FS_PRIORITIZE_NON_BORROWING = 1 << 4
 F_FS_PREEMPT_WITHIN_NOMINAL = 1 << 5
 F_FS_STRATEGY_S2A = 1 << 6

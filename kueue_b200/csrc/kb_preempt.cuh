@@ -132,7 +132,11 @@ __device__ __forceinline__ bool satisfies_policy(const DevSnap &D, const PreCtx 
   int cp = D.adm_priority[a];
   bool lower = c.prio > cp;
   if (policy == KB_POLICY_LOWER_PRIORITY) return lower;
-  if (policy == KB_POLICY_LOWER_OR_NEWER_EQUAL_PRIORITY) return lower || (c.prio == cp && c.ts < D.adm_ts[a]);
+  if (policy == KB_POLICY_LOWER_OR_NEWER_EQUAL_PRIORITY) {
+    bool newer = c.prio == cp && c.ts < D.adm_ts[a];
+    if (newer && (D.flags & KB_F_TS_PREEMPTION_BUFFER)) newer = D.adm_ts[a] - c.ts > 300ll * 1000000000ll;  // timestampPreemptionBuffer :28
+    return lower || newer;
+  }
   return policy == KB_POLICY_ANY;
 }
 __device__ __forceinline__ bool uses_resources(const DevSnap &D, const PreCtx &c, int a) {  // WorkloadUsesResources candidate_generator.go:52-61

@@ -97,3 +97,25 @@ def resources_to_reserve(snap, cq, mode, borrowing, usage):
                                        u.ctypes.data_as(C.POINTER(C.c_int64)), out.ctypes.data_as(C.POINTER(C.c_int64)))
     assert rc == 0, rc
     return out
+
+
+def entry_less(flags, a, b):
+    """entryComparer.less (fair_sharing_iterator.go:166-199); a, b = (borrowing, priority, ts_ns, drs_ratio, drs_weight)."""
+    f = lib().ko_entry_less
+    f.restype = C.c_int32
+    f.argtypes = [C.c_uint32] + [C.c_int32, C.c_int32, C.c_int64, C.c_double, C.c_double] * 2
+    return bool(f(flags, *a, *b))
+
+
+def satisfies_policy(snap, pre_prio, pre_ts, adm, policy):
+    s = snap.as_struct()
+    return bool(lib().ko_satisfies_policy(C.byref(s), C.c_int32(pre_prio), C.c_int64(pre_ts), C.c_int32(adm), C.c_int32(policy)))
+
+
+def sort_candidates(snap, cq):
+    import numpy as np
+    s = snap.as_struct()
+    order = np.zeros(snap.n_adm, np.int32)
+    rc = lib().ko_sort_candidates(C.byref(s), C.c_int32(cq), order.ctypes.data_as(C.POINTER(C.c_int32)))
+    assert rc == 0
+    return order.tolist()

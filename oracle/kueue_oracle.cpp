@@ -324,6 +324,7 @@ class Oracle {
     if (policy == KB_POLICY_LOWER_PRIORITY) return lower;
     if (policy == KB_POLICY_LOWER_OR_NEWER_EQUAL_PRIORITY) {
       bool newerEq = (p.priority == s.adm_priority[a]) && p.ts < s.adm_ts[a];
+      if (newerEq && (s.flags & KB_F_TS_PREEMPTION_BUFFER)) newerEq = s.adm_ts[a] - p.ts > 300ll * 1000000000ll;  // timestampPreemptionBuffer :28
       return lower || newerEq;
     }
     return policy == KB_POLICY_ANY;
@@ -922,18 +923,20 @@ class Oracle {
     return r;
   }
   // entryComparer.less fair_sharing_iterator.go:166-199
-  bool fsLess(const Entry &a, const Entry &b, const DRS &da, const DRS &db) {
-    if (s.flags & KB_F_FS_PRIORITIZE_NON_BORROWING) {
-      bool ab = a.a.borrowing > 0, bb = b.a.borrowing > 0;
+  static bool fsLessRaw(uint32_t flags, int aBorrowing, int aPrio, i64 aTs, const DRS &da, int bBorrowing, int bPrio, i64 bTs, const DRS &db) {
+    if (flags & KB_F_FS_PRIORITIZE_NON_BORROWING) {
+      bool ab = aBorrowing > 0, bb = bBorrowing > 0;
       if (ab != bb) return !ab;
     }
     int c = compareDRS(da, db);
     if (c != 0) return c == -1;
-    if (s.flags & KB_F_PRIORITY_SORTING_WITHIN_COHORT) {
-      int p1 = s.wl_priority[a.wl], p2 = s.wl_priority[b.wl];
-      if (p1 != p2) return p1 > p2;
+    if (flags & KB_F_PRIORITY_SORTING_WITHIN_COHORT) {
+      if (aPrio != bPrio) return aPrio > bPrio;
     }
-    return s.wl_ts[a.wl] < s.wl_ts[b.wl];
+    return aTs < bTs;
+  }
+  bool fsLess(const Entry &a, const Entry &b, const DRS &da, const DRS &db) {
+    return fsLessRaw(s.flags, a.a.borrowing, s.wl_priority[a.wl], s.wl_ts[a.wl], da, b.a.borrowing, s.wl_priority[b.wl], s.wl_ts[b.wl], db);
   }
   // runTournament :120-153 ; drs[node][entry] looked up by (parent cohort, entry)
   int runTournament(int cohort, std::vector<Entry> &entries, const std::vector<int> &cqToEntry,
@@ -1155,6 +1158,34 @@ int32_t ko_resources_to_reserve(const kb_snapshot *s, int32_t cq, int32_t mode, 
   for (int fr = 0; fr < o.FR; fr++) { out[fr] = -1; if (usage[fr] >= 0) e.a.usage.add(fr, usage[fr]); }
   UsageVec r = o.resourcesToReserve(e, cq);
   for (auto &c : r.v) out[c.first] = c.second;
+  return 0;
+}
+
+// entryComparer.less (fair_sharing_iterator.go:166-199) on explicit operands, the surface TestEntryComparerLess
+// (scheduler_test.go:9577) checks.  ratio / weight are DRS.unweightedRatio / fairWeight.
+int32_t ko_entry_less(uint32_t flags, int32_t a_borrowing, int32_t a_prio, int64_t a_ts, double a_ratio, double a_weight,
+                      int32_t b_borrowing, int32_t b_prio, int64_t b_ts, double b_ratio, double b_weight) {
+  DRS da, db;
+  da.unweightedRatio = a_ratio; da.fairWeight = a_weight; db.unweightedRatio = b_ratio; db.fairWeight = b_weight;
+  return Oracle::fsLessRaw(flags, a_borrowing, a_prio, a_ts, da, b_borrowing, b_prio, b_ts, db) ? 1 : 0;
+}
+
+// SatisfiesPreemptionPolicy (preemption/common/preemption_policy.go:30-48) of preemptor (priority, timestamp) against
+// admitted workload `adm` — TestSatisfiesPreemptionPolicy (preemption_policy_test.go:32).
+int32_t ko_satisfies_policy(const kb_snapshot *s, int32_t pre_prio, int64_t pre_ts, int32_t adm, int32_t policy) {
+  Oracle o(*s);
+  Preemptor p{0, pre_prio, pre_ts};
+  return o.satisfiesPreemptionPolicy(p, adm, policy) ? 1 : 0;
+}
+
+// Every admitted workload of the snapshot sorted by CandidatesOrdering (preemption/common/ordering.go:41-100) for
+// a preemptor in ClusterQueue `cq` — TestCandidatesOrdering (preemption_test.go:4525).
+int32_t ko_sort_candidates(const kb_snapshot *s, int32_t cq, int32_t *order) {
+  Oracle o(*s);
+  std::vector<int> v(s->n_adm);
+  for (int i = 0; i < s->n_adm; i++) v[i] = i;
+  std::stable_sort(v.begin(), v.end(), [&](int a, int b) { return o.candidatesOrdering(a, b, cq) < 0; });
+  for (int i = 0; i < s->n_adm; i++) order[i] = v[i];
   return 0;
 }
 }  // extern "C"

@@ -93,3 +93,48 @@ RESERVE_CASES = {
         mode="Preempt", borrowing=1, usage={("on-demand", MEM): 50, ("model-b", GPU): 2}, cq_usage=CQ_USAGE_C,
         want={("on-demand", MEM): 50, ("model-b", GPU): 2}),
 }
+
+# ---- TestEntryComparerLess scheduler_test.go:9577: (name, creation offset s, Borrowing, DRS (ratio, weight) | None)
+#      a missing drsValues entry is Go's zero DRS{} (ratio 0, weight 0); NegativeDRS() = (ratio -1, weight 1)
+ENTRY_LESS_CASES = {
+    "nominal preferred over borrowing": dict(a=("nominal", 1, 0, None), b=("borrowing", 0, 1, None), want=True),
+    "both borrowing at different levels falls through to FIFO": dict(a=("borrow-level-1", 1, 1, None), b=("borrow-level-2", 0, 2, None), want=False),
+    "lower DRS preferred when both borrow": dict(a=("lower-drs", 1, 2, (-1.0, 1.0)), b=("higher-drs", 0, 1, (0.0, 0.0)), want=True),
+    "both nominal falls through to FIFO": dict(a=("older", 0, 0, None), b=("newer", 1, 0, None), want=True),
+}
+
+# ---- TestSatisfiesPreemptionPolicy preemption/common/preemption_policy_test.go:32:
+#      (preemptor priority, creation offset min), (candidate priority, creation offset min), policy, buffer gate, want
+POLICY_CASES = {
+    "LowerPriority: preemptor has higher priority": ((10, 0), (5, 0), "LowerPriority", False, True),
+    "LowerPriority: preemptor has same priority": ((10, 0), (10, 0), "LowerPriority", False, False),
+    "LowerOrNewerEqualPriority: preemptor has same priority, same timestamp": ((10, 0), (10, 0), "LowerOrNewerEqualPriority", False, False),
+    "LowerOrNewerEqualPriority: preemptor has same priority, newer timestamp (within 5min buffer)": ((10, 1), (10, 0), "LowerOrNewerEqualPriority", False, False),
+    "LowerOrNewerEqualPriority: preemptor has same priority, older timestamp (within 5min buffer)": ((10, 0), (10, 1), "LowerOrNewerEqualPriority", False, True),
+    "LowerOrNewerEqualPriority with SchedulerTimestampPreemptionBuffer: ... older timestamp (within 5min buffer)": ((10, 0), (10, 1), "LowerOrNewerEqualPriority", True, False),
+    "LowerOrNewerEqualPriority with SchedulerTimestampPreemptionBuffer: ... older timestamp (outside 5min buffer)": ((10, 0), (10, 6), "LowerOrNewerEqualPriority", True, True),
+    "PreemptionPolicyAny": ((10, 0), (10, 6), "Any", False, True),
+    "PreemptionPolicyNever": ((10, 0), (10, 6), "Never", False, False),
+}
+
+# ---- TestCandidatesOrdering preemption/preemption_test.go:4525 (the two AdmissionFairSharing cases are out of scope):
+#      candidates (name, ClusterQueue, priority, quota reserved at offset s | None, evicted); preemptor CQ = "preemptor"
+CANDIDATE_ORDER_CASES = {
+    "workloads sorted by priority": dict(cands=[("high", "preemptor", 10, 0, False), ("low", "preemptor", -10, 0, False)], want=["low", "high"]),
+    "evicted workload first": dict(cands=[("other", "preemptor", 10, 0, False), ("evicted", "other", 0, None, True)], want=["evicted", "other"]),
+    "workload from different CQ first": dict(cands=[("preemptorCq", "preemptor", 10, 0, False), ("other", "other", 10, 0, False)], want=["other", "preemptorCq"]),
+    "old workloads last": dict(cands=[("older", "preemptor", 0, -1, False), ("younger", "preemptor", 0, 1, False), ("current", "preemptor", 0, 0, False)],
+                               want=["younger", "current", "older"]),
+}
+
+# ---- TestSearch flavorassigner/podset_reducer_test.go:26: podsets (count, minCount | None), countLimit -> (found, count)
+#      ("empty" and "podset with replica count 0" have no pods to place and are not expressible as a workload)
+REDUCER_CASES = {
+    "partial not available": dict(podsets=[(1, None), (2, 2)], limit=2, found=False, count=0),
+    "partial available": dict(podsets=[(5, 3), (5, 4), (5, 1), (5, 2)], limit=15, found=True, count=15),
+    "one partial available": dict(podsets=[(5, 3), (5, None), (5, None), (5, None)], limit=19, found=True, count=19),
+    "to min": dict(podsets=[(5, 3), (5, 4), (5, 1), (5, 2)], limit=10, found=True, count=10),
+    "to max": dict(podsets=[(5, 3), (5, 4), (5, 1), (5, 2)], limit=20, found=True, count=20),
+    "no overflow": dict(podsets=[(150_000, 1)] * 8, limit=150_000, found=True, count=150_000),
+    "max pods on 1.27": dict(podsets=[(150_000, 1)] + [(1, None)] * 7, limit=150_000, found=True, count=150_000),
+}

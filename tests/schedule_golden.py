@@ -40,3 +40,17 @@ def entry_ordering_snapshot(tc):
 def order_of(out, tc):
     names = [n for n, *_ in tc["input"]]
     return [names[i] for i in np.argsort(out.commit_rank, kind="stable")]
+
+
+def reducer_snapshot(tc):
+    """TestSearch's predicate `total pods <= countLimit` as a quota: every pod asks for one unit of a resource whose
+    nominal quota is countLimit, so PodSetReducer.Search (podset_reducer.go:56-86) runs inside the real cycle."""
+    cq = MakeClusterQueue("cq").ResourceGroup(MakeFlavorQuotas("default").Resource("example.com/slot", str(tc["limit"])))
+    pss = []
+    for i, (count, min_count) in enumerate(tc["podsets"]):
+        p = MakePodSet(f"ps{i + 1}", count).Request("example.com/slot", "1")
+        if min_count is not None:
+            p.SetMinimumCount(min_count)
+        pss.append(p)
+    w = MakeWorkload("wl").ClusterQueue("cq").PodSets(*pss)
+    return flatten([cq], pending=[w], now_ns=NOW)

@@ -252,3 +252,24 @@ def test_span_upload_from_one_pinned_block(ev):
         pinned.static_generation = 7
         assert_cycle_equal(ev.run_cycle(pinned, abi.CycleOut(pinned, cap)), want)
         assert_cycle_equal(ev.run_cycle(pinned, abi.CycleOut(pinned, cap)), want)  # static tables reused, span upload again
+
+
+def test_reference_podset_reducer_cycle(ev):
+    """TestSearch (podset_reducer_test.go:26) inside the cycle: device == oracle, total admitted pods == wantCount."""
+    from tests.golden.schedule_cases import REDUCER_CASES
+    from tests.schedule_golden import reducer_snapshot
+    for name, tc in REDUCER_CASES.items():
+        snap, idx = reducer_snapshot(tc)
+        got, want = ev.run_cycle(snap), oracle.run_cycle(snap)
+        assert_cycle_equal(got, want)
+        if tc["found"]:
+            assert got.decision[0] == abi.DEC_ASSUMED and int(got.ps_count.sum()) == tc["count"], name
+
+
+def test_reference_assign_in_cohorts_cycle(ev):
+    """TestHierarchical / TestReclaimBeforePriorityPreemption environments (no stub oracle here): device == oracle."""
+    from tests.test_oracle_golden_assign_extra import DATA, build_assign_extra
+    for func, tab in DATA.items():
+        for name, tc in tab.items():
+            snap, idx = build_assign_extra(func, tc)
+            assert_cycle_equal(ev.run_cycle(snap), oracle.run_cycle(snap))

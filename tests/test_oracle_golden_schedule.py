@@ -45,3 +45,61 @@ def test_resources_to_reserve(name):  # scheduler_test.go:9705
     for (f, r), v in tc["want"].items():
         want[idx.fr(f, r)] = v
     assert got.tolist() == want.tolist()
+
+
+def test_entry_comparer_less():  # scheduler_test.go:9577
+    from tests.golden.schedule_cases import ENTRY_LESS_CASES, S
+    for name, tc in ENTRY_LESS_CASES.items():
+        def op(e):
+            _, created, borrowing, drs = e
+            ratio, weight = drs if drs is not None else (0.0, 0.0)
+            return (borrowing, 0, NOW + created * S, ratio, weight)
+        assert oracle.entry_less(abi.FLAGS_DEFAULT, op(tc["a"]), op(tc["b"])) == tc["want"], name
+
+
+def _two_cq_snapshot(admitted, flags=abi.FLAGS_DEFAULT):
+    from kueue_b200.api import MakeAdmission
+    cqs = [MakeClusterQueue(n).Cohort("co").ResourceGroup(MakeFlavorQuotas("default").Resource("cpu", "100")) for n in ("preemptor", "other")]
+    return flatten(cqs, admitted=admitted, flags=flags, now_ns=NOW)
+
+
+def test_satisfies_preemption_policy():  # preemption_policy_test.go:32
+    from kueue_b200.api import MakeAdmission
+    from tests.golden.schedule_cases import POLICY_CASES
+    pol = {"Never": abi.POLICY_NEVER, "LowerPriority": abi.POLICY_LOWER_PRIORITY,
+           "LowerOrNewerEqualPriority": abi.POLICY_LOWER_OR_NEWER_EQUAL_PRIORITY, "Any": abi.POLICY_ANY}
+    MIN = 60 * 10**9
+    for name, ((pp, pt), (cp, ct), policy, buffer_gate, want) in POLICY_CASES.items():
+        cand = MakeWorkload("candidate").Priority(cp).Creation(NOW + ct * MIN).ReserveQuota(MakeAdmission("other").Assignment("cpu", "default", "1"), NOW)
+        flags = abi.FLAGS_DEFAULT | (abi.F_TS_PREEMPTION_BUFFER if buffer_gate else 0)
+        snap, idx = _two_cq_snapshot([cand], flags)
+        assert oracle.satisfies_policy(snap, pp, NOW + pt * MIN, 0, pol[policy]) == want, name
+
+
+def test_candidates_ordering():  # preemption_test.go:4525
+    from kueue_b200.api import MakeAdmission
+    from tests.golden.schedule_cases import CANDIDATE_ORDER_CASES, S
+    for name, tc in CANDIDATE_ORDER_CASES.items():
+        adm = []
+        for uid, (wname, cq, prio, reserved, evicted) in enumerate(tc["cands"]):
+            w = MakeWorkload(wname).Priority(prio).UID(uid + 1).ReserveQuota(MakeAdmission(cq).Assignment("cpu", "default", "1"),
+                                                                         None if reserved is None else NOW + reserved * S)
+            if evicted:
+                w.Evicted()
+            adm.append(w)
+        snap, idx = _two_cq_snapshot(adm)
+        got = [tc["cands"][i][0] for i in oracle.sort_candidates(snap, idx.cqs.index("preemptor"))]
+        assert got == tc["want"], name
+
+
+def test_podset_reducer_search():  # podset_reducer_test.go:26
+    from tests.golden.schedule_cases import REDUCER_CASES
+    from tests.schedule_golden import reducer_snapshot
+    for name, tc in REDUCER_CASES.items():
+        snap, idx = reducer_snapshot(tc)
+        out = oracle.run_cycle(snap)
+        if tc["found"]:
+            assert out.decision[0] == abi.DEC_ASSUMED and int(out.ps_count.sum()) == tc["count"], name
+            assert all(int(c) >= (m if m is not None else n) for c, (n, m) in zip(out.ps_count, tc["podsets"])), name
+        else:
+            assert out.decision[0] != abi.DEC_ASSUMED, name

@@ -252,7 +252,7 @@ class Parser:
     def _is_typeish(self, e):
         # composite literal after a (qualified) type name: Foo{...} / pkg.Foo{...}
         if e[0] == "id":
-            return e[1][0].isupper() or e[1] in ("struct",)
+            return e[1][0].isupper() or e[1] in ("struct", "rfMap")  # rfMap: local map type alias in flavorassigner_test.go
         if e[0] == "sel":
             return e[1][0] == "id" and e[2][0].isupper()
         return False
