@@ -27,12 +27,13 @@ struct PTab {
   const int32_t *nodes;  // local -> global node id
   int nn, FR;
   i64 *usage;            // [nn][FR] private copy (smem or global scratch); [nn] in column mode
+  int col_stride = 1;    // element stride of the column in column mode (interleaved lane columns)
   int col_fr = -1;       // column mode: the view holds ONE flavor-resource column (single-cell searches of the
                          // preemption oracle only ever read and write that column: columns are independent)
   const i64 *sub, *lq, *bl;  // smem copies (kSmem) — unused otherwise
   const int *lparent;        // smem (kSmem) — unused otherwise
-  __device__ __forceinline__ i64 U(int h, int fr) const { return usage[col_fr >= 0 ? h : h * FR + fr]; }
-  __device__ __forceinline__ void setU(int h, int fr, i64 v) const { usage[col_fr >= 0 ? h : h * FR + fr] = v; }
+  __device__ __forceinline__ i64 U(int h, int fr) const { return usage[col_fr >= 0 ? (size_t)h * col_stride : (size_t)(h * FR + fr)]; }
+  __device__ __forceinline__ void setU(int h, int fr, i64 v) const { usage[col_fr >= 0 ? (size_t)h * col_stride : (size_t)(h * FR + fr)] = v; }
   __device__ __forceinline__ i64 Sub(int h, int fr) const { return kSmem ? sub[h * FR + fr] : D->subtree[(size_t)nodes[h] * FR + fr]; }
   __device__ __forceinline__ i64 LQ(int h, int fr) const {
     if (kSmem) return lq[h * FR + fr];
@@ -115,17 +116,25 @@ struct PreCtx {
   int overflow;  // the candidate list did not fit the scratch of this searcher (speculative lane searches only)
 };
 
-// per-CTA global scratch
+// Strided view of a scratch array: element i lives at p[i * stride] (stride 1 everywhere today; an interleaved
+// layout for the lane searchers was tried and measured slower, see k_nominate_search).
+template <typename T>
+struct SArr {
+  T *p; int stride;
+  __device__ __forceinline__ T &operator[](int i) const { return p[(size_t)i * stride]; }
+};
+
+// global scratch of one searcher
 struct PreScratch {
-  int32_t *cand;     // ordered candidate list
-  uint8_t *variant;  // preemptionVariant per candidate
-  int32_t *tgt;      // targets of the current search (adm index)
-  uint8_t *tgt_reason;
-  int8_t *cq_class;  // per tree node (handle): 0 none, 1 hierarchy candidates, 2 priority candidates
-  int8_t *on_path;   // per tree node (handle): level on the preemptor's path or -1
-  int32_t *cq_lca;   // per tree node (handle): handle of the subtree root that collected it
-  int32_t *aux1, *aux2;  // [adm cap] fair sharing: next-in-queue links, retry candidates
-  int cap;               // capacity of the [adm cap] arrays
+  SArr<int32_t> cand;     // ordered candidate list
+  SArr<uint8_t> variant;  // preemptionVariant per candidate
+  SArr<int32_t> tgt;      // targets of the current search (adm index)
+  SArr<uint8_t> tgt_reason;
+  SArr<int8_t> cq_class;  // per tree node (handle): 0 none, 1 hierarchy candidates, 2 priority candidates
+  SArr<int8_t> on_path;   // per tree node (handle): level on the preemptor's path or -1
+  SArr<int32_t> cq_lca;   // per tree node (handle): handle of the subtree root that collected it
+  SArr<int32_t> aux1, aux2;  // [adm cap] sort keys / fair sharing: next-in-queue links, retry candidates
+  int cap;                // capacity of the [adm cap] arrays
 };
 
 __device__ __forceinline__ bool satisfies_policy(const DevSnap &D, const PreCtx &c, int a, int policy) {  // preemption_policy.go:30-48
@@ -181,7 +190,7 @@ __device__ __forceinline__ int variant_reason(int v) {  // PreemptionReason :49-
 // can take candidates from: gather the accepted workloads, then heap sort on (segment << 28 | rank).
 // ---------------------------------------------------------------------------
 // heap sort of (key, cand, variant) triples by key
-__device__ inline void sort_candidates(int32_t *key, int32_t *cand, uint8_t *var, int n) {
+__device__ inline void sort_candidates(const SArr<int32_t> &key, const SArr<int32_t> &cand, const SArr<uint8_t> &var, int n) {
   auto swp = [&](int i, int j) {
     int32_t t = key[i]; key[i] = key[j]; key[j] = t;
     t = cand[i]; cand[i] = cand[j]; cand[j] = t;
@@ -431,10 +440,10 @@ __device__ inline void fair_search(const DevSnap &D, const PTab<kSmem> &T, PreCt
   }
   sort_candidates(S.aux1, S.cand, S.variant, nall);
   if (nall == 0) { c->n_targets = 0; return; }
-  int32_t *head = S.cq_lca;   // per node: index (into the current candidate list) of the queue head, or -1
-  int32_t *next = S.aux1;
-  int8_t *pruned = S.cq_class;
-  auto build_queues = [&](const int32_t *list, int n) {  // MakeClusterQueueOrdering ordering.go:62-83
+  SArr<int32_t> head = S.cq_lca;   // per node: index (into the current candidate list) of the queue head, or -1
+  SArr<int32_t> next = S.aux1;
+  SArr<int8_t> pruned = S.cq_class;
+  auto build_queues = [&](const SArr<int32_t> &list, int n) {  // MakeClusterQueueOrdering ordering.go:62-83
     for (int h = 0; h < T.nn; h++) { head[h] = -1; pruned[h] = 0; }
     for (int i = n - 1; i >= 0; i--) { int h = T.handle(D.adm_cq[list[i]]); next[i] = head[h]; head[h] = i; }
   };
@@ -447,7 +456,7 @@ __device__ inline void fair_search(const DevSnap &D, const PTab<kSmem> &T, PreCt
     usage_add(true);
     return r;
   };
-  const int32_t *list = S.cand;
+  SArr<int32_t> list = S.cand;
   auto next_target = [&](int root) -> int {  // nextTarget ordering.go:141-208 (tail recursion unrolled)
     int cohort = root;
     for (int guard = 0;; guard++) {
@@ -498,7 +507,7 @@ __device__ inline void fair_search(const DevSnap &D, const PTab<kSmem> &T, PreCt
 
   usage_add(true);  // :446 DRS values must include the incoming workload
   int nt = 0, nretry = 0;
-  int32_t *retry = S.aux2;
+  SArr<int32_t> retry = S.aux2;
   bool fits = false;
   {  // runFirstFsStrategy :338-403
     build_queues(S.cand, nall);
