@@ -724,7 +724,7 @@ struct NomSearch {
 };
 
 template <bool kSmem>
-__global__ void __launch_bounds__(32) k_nominate_search(DevSnap D) {
+__global__ void __launch_bounds__(32, 16) k_nominate_search(DevSnap D) {  // <= 128 registers: 16 single-warp CTAs per SM
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ PreCtx ctx;
   __shared__ int s_item;
@@ -735,21 +735,21 @@ __global__ void __launch_bounds__(32) k_nominate_search(DevSnap D) {
   PreScratch SL;  // scratch of this lane's speculative single-cell searches
   {
     size_t b = blockIdx.x;
-    S.cand = {D.sc_cand + b * D.sc_adm_cap, 1}; S.variant = {D.sc_variant + b * D.sc_adm_cap, 1};
-    S.tgt = {D.sc_tgt + b * D.sc_adm_cap, 1}; S.tgt_reason = {D.sc_tgt_reason + b * D.sc_adm_cap, 1};
-    S.cq_class = {D.sc_cq_class + b * D.sc_node_cap, 1}; S.on_path = {D.sc_on_path + b * D.sc_node_cap, 1};
-    S.cq_lca = {D.sc_cq_lca + b * D.sc_node_cap, 1};
-    S.aux1 = {D.sc_aux1 + b * D.sc_adm_cap, 1}; S.aux2 = {D.sc_aux2 + b * D.sc_adm_cap, 1};
+    S.cand = {D.sc_cand + b * D.sc_adm_cap}; S.variant = {D.sc_variant + b * D.sc_adm_cap};
+    S.tgt = {D.sc_tgt + b * D.sc_adm_cap}; S.tgt_reason = {D.sc_tgt_reason + b * D.sc_adm_cap};
+    S.cq_class = {D.sc_cq_class + b * D.sc_node_cap}; S.on_path = {D.sc_on_path + b * D.sc_node_cap};
+    S.cq_lca = {D.sc_cq_lca + b * D.sc_node_cap};
+    S.aux1 = {D.sc_aux1 + b * D.sc_adm_cap}; S.aux2 = {D.sc_aux2 + b * D.sc_adm_cap};
     S.cap = D.sc_adm_cap;
     // lane scratch: contiguous per lane.  (Interleaving the 32 lanes' arrays, stride 32, was measured slower on
     // cfg4 — 264 vs 221 ms: the lanes do not walk their lists in lock step, so it only destroys each lane's own
     // spatial locality.)
     size_t w = b * 32 + lane;
-    SL.cand = {D.sl_cand + w * D.sl_adm_cap, 1}; SL.variant = {D.sl_variant + w * D.sl_adm_cap, 1};
-    SL.tgt = {D.sl_tgt + w * D.sl_adm_cap, 1}; SL.tgt_reason = {D.sl_tgt_reason + w * D.sl_adm_cap, 1};
-    SL.cq_class = {D.sl_cq_class + w * D.sc_node_cap, 1}; SL.on_path = {D.sl_on_path + w * D.sc_node_cap, 1};
-    SL.cq_lca = {D.sl_cq_lca + w * D.sc_node_cap, 1};
-    SL.aux1 = {D.sl_aux1 + w * D.sl_adm_cap, 1}; SL.aux2 = {nullptr, 1};  // aux2 is only used by the fair search (never speculative)
+    SL.cand = {D.sl_cand + w * D.sl_adm_cap}; SL.variant = {D.sl_variant + w * D.sl_adm_cap};
+    SL.tgt = {D.sl_tgt + w * D.sl_adm_cap}; SL.tgt_reason = {D.sl_tgt_reason + w * D.sl_adm_cap};
+    SL.cq_class = {D.sl_cq_class + w * D.sc_node_cap}; SL.on_path = {D.sl_on_path + w * D.sc_node_cap};
+    SL.cq_lca = {D.sl_cq_lca + w * D.sc_node_cap};
+    SL.aux1 = {D.sl_aux1 + w * D.sl_adm_cap}; SL.aux2 = {nullptr};  // aux2 is only used by the fair search (never speculative)
     SL.cap = D.sl_adm_cap;
   }
   PreCtx *lctx = (PreCtx *)D.sl_ctx + (size_t)blockIdx.x * 32 + lane;

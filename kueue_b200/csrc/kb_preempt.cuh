@@ -27,13 +27,12 @@ struct PTab {
   const int32_t *nodes;  // local -> global node id
   int nn, FR;
   i64 *usage;            // [nn][FR] private copy (smem or global scratch); [nn] in column mode
-  int col_stride = 1;    // element stride of the column in column mode (interleaved lane columns)
   int col_fr = -1;       // column mode: the view holds ONE flavor-resource column (single-cell searches of the
                          // preemption oracle only ever read and write that column: columns are independent)
   const i64 *sub, *lq, *bl;  // smem copies (kSmem) — unused otherwise
   const int *lparent;        // smem (kSmem) — unused otherwise
-  __device__ __forceinline__ i64 U(int h, int fr) const { return usage[col_fr >= 0 ? (size_t)h * col_stride : (size_t)(h * FR + fr)]; }
-  __device__ __forceinline__ void setU(int h, int fr, i64 v) const { usage[col_fr >= 0 ? (size_t)h * col_stride : (size_t)(h * FR + fr)] = v; }
+  __device__ __forceinline__ i64 U(int h, int fr) const { return usage[col_fr >= 0 ? h : h * FR + fr]; }
+  __device__ __forceinline__ void setU(int h, int fr, i64 v) const { usage[col_fr >= 0 ? h : h * FR + fr] = v; }
   __device__ __forceinline__ i64 Sub(int h, int fr) const { return kSmem ? sub[h * FR + fr] : D->subtree[(size_t)nodes[h] * FR + fr]; }
   __device__ __forceinline__ i64 LQ(int h, int fr) const {
     if (kSmem) return lq[h * FR + fr];
@@ -116,12 +115,12 @@ struct PreCtx {
   int overflow;  // the candidate list did not fit the scratch of this searcher (speculative lane searches only)
 };
 
-// Strided view of a scratch array: element i lives at p[i * stride] (stride 1 everywhere today; an interleaved
-// layout for the lane searchers was tried and measured slower, see k_nominate_search).
+// View of a scratch array of one searcher (contiguous; an interleaved layout for the 32 lane searchers of a CTA
+// was tried and measured slower, see k_nominate_search).
 template <typename T>
 struct SArr {
-  T *p; int stride;
-  __device__ __forceinline__ T &operator[](int i) const { return p[(size_t)i * stride]; }
+  T *p;
+  __device__ __forceinline__ T &operator[](int i) const { return p[i]; }
 };
 
 // global scratch of one searcher
