@@ -64,7 +64,7 @@ struct kb_handle {
   // tree_eval scratch
   i64 *d_drs_rounded = nullptr; int32_t *d_drs_res = nullptr; uint8_t *d_drs_borrowing = nullptr;
   // host-side derived topology
-  std::vector<int32_t> root_slot, depth, height, tree_start, tree_nodes, tree_level, lone, cq_adm_start, cq_adm, local_idx, child_start, child_list, adm_sorted, root_adm_start, adm_rank, cq_adm_nev, root_cq_start;
+  std::vector<int32_t> root_slot, depth, height, tree_start, tree_nodes, tree_level, lone, cq_adm_start, cq_adm, local_idx, child_start, child_list, adm_sorted, root_adm_start, adm_rank, root_cq_start;
   std::vector<uint8_t> tree_flat;
   int max_root_adm = 1;
   int search_grid = 1;
@@ -297,14 +297,12 @@ static int32_t build_dynamic(kb_handle *h, const kb_snapshot *s) {
   if (h->max_root_adm >= (1 << 28)) return fail(h, KB_ERR_INVALID, "more than 2^28 admitted workloads under one root");
   {  // per-CQ lists in the same order (evicted workloads first), rank of every workload inside its root
     h->adm_rank.assign(std::max(1, s->n_adm), 0);
-    h->cq_adm_nev.assign(std::max(1, Q), 0);
     std::vector<int32_t> cur(h->cq_adm_start.begin(), h->cq_adm_start.end() - 1);
     for (int r = 0; r < nroots; r++)
       for (int i = h->root_adm_start[r]; i < h->root_adm_start[r + 1]; i++) {
         int a = h->adm_sorted[i];
         h->adm_rank[a] = i - h->root_adm_start[r];
         h->cq_adm[cur[s->adm_cq[a]]++] = a;
-        if (s->adm_evicted[a]) h->cq_adm_nev[s->adm_cq[a]]++;
       }
   }
   // light bounds checks on the hot tables
@@ -401,7 +399,7 @@ static int32_t upload_impl(kb_handle *h, const kb_snapshot *s, bool sync) {
   need(P * R, 8); need(P, 4); need(P, 4); need(P, 4); need(P, 8); need(P * R, 1);
   need(A, 4); need(A, 4); need(A, 8); need(A, 8); need(A, 8); need(A, 1); need(A + 1, 4); need(s->n_adm_use, 4); need(s->n_adm_use, 8);
   need(H, 4);
-  need(Q + 1, 4); need(h->cq_adm.size(), 4); need(h->adm_rank.size(), 4); need(h->cq_adm_nev.size(), 4); need(Q, 4); need(nroots, 4);
+  need(Q + 1, 4); need(h->cq_adm.size(), 4); need(h->adm_rank.size(), 4); need(Q, 4); need(nroots, 4);
   need(NF, 8); need(NF, 8); need(NF, 8); need(NF, 8);
   need(nroots, 4); need(nroots + 1, 4); need(nroots, 4); need(H, 4); need(H, 4); need(H, 4); need(H * 4, 8); need(H * 4, 8); need((size_t)Q * R, 8); need((size_t)N * R, 8);
   need(H, 1); need(H, 1); need(H, 4); need(H, 4); need(P * R, 1); need(P * R, 1); need(P * R, 1); need(P, 4);
@@ -454,9 +452,9 @@ static int32_t upload_impl(kb_handle *h, const kb_snapshot *s, bool sync) {
   UP(adm_use_start, s->adm_use_start, A + 1); UP(adm_use_fr, s->adm_use_fr, s->n_adm_use); UP(adm_use_qty, (const i64 *)s->adm_use_qty, s->n_adm_use);
   UP(heads, s->heads, H);
   size_t caller_tabs = tabs.size();
-  UP(adm_sorted, h->adm_sorted.data(), h->adm_sorted.size()); UP(root_adm_start, h->root_adm_start.data(), nroots + 1);
+  UP(root_adm_start, h->root_adm_start.data(), nroots + 1);
   UP(cq_adm_start, h->cq_adm_start.data(), Q + 1); UP(cq_adm, h->cq_adm.data(), h->cq_adm.size());
-  UP(adm_rank, h->adm_rank.data(), h->adm_rank.size()); UP(cq_adm_nev, h->cq_adm_nev.data(), h->cq_adm_nev.size());
+  UP(adm_rank, h->adm_rank.data(), h->adm_rank.size());
 #undef UP
   {
     uintptr_t lo = UINTPTR_MAX, hi = 0; size_t sum = 0;
@@ -496,7 +494,7 @@ static int32_t upload_impl(kb_handle *h, const kb_snapshot *s, bool sync) {
   D.tgt_off = h->arena.take<int32_t>(H); D.tgt_cnt = h->arena.take<int32_t>(H);
   D.tgt_pool_adm = h->arena.take<int32_t>(pool_cap); D.tgt_pool_reason = h->arena.take<uint8_t>(pool_cap);
   D.tgt_pool_used = h->arena.take<int32_t>(1); D.tgt_pool_cap = (int)pool_cap;
-  D.preempted = h->arena.take<uint8_t>(A); D.root_pre_list = h->arena.take<int32_t>(A); D.root_pre_count = h->arena.take<int32_t>(nroots);
+  D.preempted = h->arena.take<uint8_t>(A);
   D.usage_shadow = h->arena.take<i64>(A ? NF : 1);
   D.sc_cand = h->arena.take<int32_t>(G * acap); D.sc_tgt = h->arena.take<int32_t>(G * acap); D.sc_cq_lca = h->arena.take<int32_t>(G * ncap);
   D.sc_aux1 = h->arena.take<int32_t>(G * acap); D.sc_aux2 = h->arena.take<int32_t>(G * acap);
@@ -619,7 +617,6 @@ static int32_t cycle_enqueue(kb_handle *h) {
   CUDA_TRY(h, cudaMemsetAsync(D.root_count, 0, sizeof(int32_t) * (size_t)std::max(1, D.nRoots), h->stream));
   CUDA_TRY(h, cudaMemsetAsync(D.ps_n, 0, 8, h->stream));
   CUDA_TRY(h, cudaMemsetAsync(D.tgt_pool_used, 0, 4, h->stream));
-  CUDA_TRY(h, cudaMemsetAsync(D.root_pre_count, 0, sizeof(int32_t) * (size_t)std::max(1, D.nRoots), h->stream));
   if (D.A) CUDA_TRY(h, cudaMemsetAsync(D.preempted, 0, (size_t)D.A, h->stream));
   h->kev_n = 0;
   int32_t rc_admit = KB_OK;

@@ -89,10 +89,9 @@ struct DevSnap {
   int32_t *ps_count_out;
   uint32_t *status;  // [1] KBS_* bits
   // ---- preemption ----
-  const int32_t *adm_sorted;     // [A] admitted workloads ordered by (root, evicted desc, priority asc, newer first, uid)
-  const int32_t *root_adm_start; // [nRoots+1] segments of adm_sorted
-  const int32_t *adm_rank;       // [A] position of the workload inside its root's segment of adm_sorted
-  const int32_t *cq_adm_nev;     // [Q] evicted workloads of the CQ (prefix of its cq_adm list, which is in adm_rank order)
+  const int32_t *root_adm_start; // [nRoots+1] admitted workloads per root (prefix sums)
+  const int32_t *adm_rank;       // [A] position of the workload among its root's admitted workloads ordered by
+                                 //     (evicted desc, priority asc, more recently reserved first, uid) — host sort per cycle
   const int32_t *root_cq_start;  // [nRoots+1] ClusterQueues per root (segments of over_list)
   int32_t *over_list;            // [Q] per root: ClusterQueues above nominal in some flavor-resource at cycle start (k_over)
   int32_t *over_count;           // [nRoots]
@@ -101,8 +100,6 @@ struct DevSnap {
   int32_t *tgt_pool_adm; uint8_t *tgt_pool_reason; int32_t *tgt_pool_used; int tgt_pool_cap;
   uint8_t *preempted;            // [A] PreemptedWorkloads membership (admit loop)
   i64 *usage_shadow;             // [N][FR] usage without the workloads preempted so far (admit loop, see Tab)
-  int32_t *root_pre_list;        // [A] per-root lists (segments of root_adm_start) of preempted workloads
-  int32_t *root_pre_count;       // [nRoots]
   // per-CTA scratch of k_nominate_search
   int32_t *sc_cand, *sc_tgt, *sc_cq_lca, *sc_aux1, *sc_aux2; uint8_t *sc_variant, *sc_tgt_reason; int8_t *sc_cq_class, *sc_on_path;
   i64 *sc_usage;

@@ -791,7 +791,7 @@ __global__ void __launch_bounds__(32, 16) k_nominate_search(DevSnap D) {  // <= 
     // ---- phase A: the oracle calls of the entry's first podset are independent single-cell searches
     //      (one flavor-resource column each) -> one per lane, on a private copy of that column.  Classical
     //      preemption only: the fair search reads every column for the DominantResourceShare.
-    const bool speculate = !(D.flags & KB_F_FAIR_SHARING);
+    const bool speculate = !(D.flags & KB_F_FAIR_SHARING) && FR <= KB_MAX_CELLS;  // s_memo holds one slot per cell
     if (speculate) {
       for (int c = lane; c < FR; c += 32) s_memo[c].val = -1;
       const int row = D.wl_ps_start[wl];

@@ -10,9 +10,12 @@
 // (recursive available(), per-head nominate, sequential admit loop, greedy
 // remove/fill-back preemption) on dense arrays instead of Go maps.
 //
-// Pinning: checked against the reference's own table tests transcribed under
-// tests/golden/ (TestAvailable, TestDominantResourceShare, TestAssignFlavors,
-// TestPreemption, TestSchedule subsets) — see tests/test_oracle_golden.py.
+// Pinning (parity pinned): checked against the reference's own table tests, transcribed under tests/golden/
+// (scripts in tools/, the Go literals are parsed, never executed): TestAvailable, TestDominantResourceShare,
+// TestAssignFlavors, TestReclaimBeforePriorityPreemption, TestHierarchical, TestSearch (podset reducer),
+// TestPreemption, TestHierarchicalPreemptions, TestFairPreemptions, TestCandidatesOrdering,
+// TestSatisfiesPreemptionPolicy, TestSchedule (whole cycle), TestEntryOrdering, TestEntryComparerLess,
+// TestResourcesToReserve — tests/test_oracle_golden_*.py; DESIGN.md (c) has the case counts.
 //
 // Canonical tie-breaks where the reference is nondeterministic:
 //   * classical iterator ties (scheduler.go:779 unstable sort, comparator 0 at

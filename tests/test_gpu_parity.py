@@ -273,3 +273,15 @@ def test_reference_assign_in_cohorts_cycle(ev):
         for name, tc in tab.items():
             snap, idx = build_assign_extra(func, tc)
             assert_cycle_equal(ev.run_cycle(snap), oracle.run_cycle(snap))
+
+
+@pytest.mark.parametrize("make", [
+    lambda: synth.make_snapshot(2, W=3000, Q=40, F=20, R=8, podsets_max=2),                          # FR = 160: no register / two-column fast paths
+    lambda: synth.make_snapshot(3, W=600, Q=60, F=12, R=8, heads="one_per_cq", preemption=True, tight=1.1),  # FR = 96, fair
+    lambda: synth.make_snapshot(4, W=2000, Q=100, F=20, R=8, heads="one_per_cq", tight=1.25),         # FR = 160 > KB_MAX_CELLS: no speculative searches
+    lambda: synth.make_snapshot(4, W=2000, Q=100, F=10, R=8, heads="one_per_cq", tight=1.25),         # FR = 80: speculative, three cells per lane
+])
+def test_wide_flavor_resource_tables(ev, make):
+    snap = make()
+    cap = 40 * snap.n_adm + 10000
+    assert_cycle_equal(ev.run_cycle(snap, abi.CycleOut(snap, cap)), oracle.run_cycle(snap, cap))
