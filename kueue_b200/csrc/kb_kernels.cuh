@@ -1240,57 +1240,85 @@ __device__ inline void commit_entry(const DevSnap &D, const Tab<kSmem> &T, int *
 // is being decided, so the dependent chain per entry is one shared-memory load of the ClusterQueue's usage, the
 // available() arithmetic (resource_node.go:104-118 for a two-node path), one vote, and the addUsage stores.
 // Entries in Preempt mode, with targets, or after the shadow table went live take the generic commit_entry.
+template <bool kTwo>  // kTwo: FR > 32, the lane also owns column lane + 32
 __device__ inline void commit_tile_flat(const DevSnap &D, const Tab<true> &T, int *s_path, int lane, int tn, int base, const i64 *s_q,
-                                        const int *t_e, const int *t_node, const int *t_mode, const int *t_borrow,
+                                        const int *t_e, const int *t_node, int *t_mode, const int *t_borrow,
                                         const int *t_cq, const int *t_ntg, const int *t_toff) {
   const int FR = D.FR;
   const int fr0 = lane, fr1 = lane + 32;
-  const bool c0 = fr0 < FR, c1 = fr1 < FR;
+  const bool c0 = fr0 < FR, c1 = kTwo && fr1 < FR;
   i64 urt0 = c0 ? T.usage[fr0] : 0, urt1 = c1 ? T.usage[fr1] : 0;
   const i64 srt0 = c0 ? T.sub[fr0] : 0, srt1 = c1 ? T.sub[fr1] : 0;
-  struct Ops { int e, nd, mode, ntg; i64 q0, q1, l0, l1, b0, b1, s0, s1; };
+  // Per entry and column, everything of available() that does not involve the ROOT's usage is evaluated when the
+  // entry is prefetched: A = LocalAvailable of the ClusterQueue, cap = its borrowing cap
+  // (storedInParent - usedInParent + BorrowingLimit, resource_node.go:111-116).  The chain from one entry to the
+  // next is then  pa = min(SubtreeQuota_root - usage_root, cap); fits = A + pa >= q; usage_root += q - A.
+  // Decisions go to t_mode[i] (KB_DEC_* | 0x100) and are flushed to global memory by the whole CTA after the tile.
+  struct Ops { int nd, mode, ntg; i64 q0, q1, u0, u1, A0, A1, cap0, cap1; };
+  auto prep = [&](Ops &o) {  // reads the ClusterQueue's current usage
+    o.u0 = o.A0 = 0; o.cap0 = INT64_MAX;
+    if (o.q0 > 0) {
+      int r = o.nd * FR + fr0;
+      i64 u = T.usage[r], l = T.lq[r], bl = T.bl[r];
+      o.u0 = u; o.A0 = imax(0, l - u);
+      if (bl != KB_NO_LIMIT) o.cap0 = (T.sub[r] - l) - imax(0, u - l) + bl;
+    }
+    if (kTwo) {
+      o.u1 = o.A1 = 0; o.cap1 = INT64_MAX;
+      if (o.q1 > 0) {
+        int r = o.nd * FR + fr1;
+        i64 u = T.usage[r], l = T.lq[r], bl = T.bl[r];
+        o.u1 = u; o.A1 = imax(0, l - u);
+        if (bl != KB_NO_LIMIT) o.cap1 = (T.sub[r] - l) - imax(0, u - l) + bl;
+      }
+    }
+  };
   auto load = [&](int i, Ops &o) {
-    o.e = t_e[i]; o.nd = t_node[i]; o.mode = t_mode[i]; o.ntg = t_ntg[i];
-    o.q0 = c0 ? s_q[(size_t)i * FR + fr0] : -1; o.q1 = c1 ? s_q[(size_t)i * FR + fr1] : -1;
-    int r0 = o.nd * FR + fr0, r1 = o.nd * FR + fr1;
-    o.l0 = o.l1 = o.b0 = o.b1 = o.s0 = o.s1 = 0;
-    if (o.q0 > 0) { o.l0 = T.lq[r0]; o.b0 = T.bl[r0]; o.s0 = T.sub[r0]; }
-    if (o.q1 > 0) { o.l1 = T.lq[r1]; o.b1 = T.bl[r1]; o.s1 = T.sub[r1]; }
+    o.nd = t_node[i]; o.mode = t_mode[i]; o.ntg = t_ntg[i];
+    o.q0 = c0 ? s_q[(size_t)i * FR + fr0] : -1;
+    if (kTwo) o.q1 = c1 ? s_q[(size_t)i * FR + fr1] : -1;
+    prep(o);
   };
-  auto avail2 = [](i64 srt, i64 urt, i64 sub, i64 u, i64 l, i64 b) {  // available() of the ClusterQueue, root above it
-    i64 pa = srt - urt;
-    if (b != KB_NO_LIMIT) pa = imin((sub - l) - imax(0, u - l) + b, pa);
-    return imax(0, l - u) + pa;
-  };
-  Ops cur, nxt;
-  load(0, cur);
-  for (int i = 0; i < tn; i++) {
-    if (i + 1 < tn) load(i + 1, nxt);
-    if (lane == 0) D.rank[cur.e] = base + i;
+  int prev_nd = -1;  // ClusterQueue whose usage row the previous entry may have written after this one was prefetched
+  bool shadow = *T.shadow_on != 0;
+  auto step = [&](int i, Ops &cur) {
     if (cur.mode == KB_MODE_NOFIT) {
-      if (lane == 0) D.decision[cur.e] = KB_DEC_NOFIT;
-    } else if (cur.mode == KB_MODE_PREEMPT || cur.ntg > 0 || *T.shadow_on) {
+      if (lane == 0) t_mode[i] = KB_DEC_NOFIT | 0x100;
+      prev_nd = -1;
+    } else if (cur.mode == KB_MODE_PREEMPT || cur.ntg > 0 || shadow) {
       if (c0) T.usage[fr0] = urt0;
       if (c1) T.usage[fr1] = urt1;
       __syncwarp();
-      commit_entry<true>(D, T, s_path, lane, cur.e, cur.nd, cur.mode, t_borrow[i], s_q + (size_t)i * FR, base + i, t_cq[i], cur.ntg, t_toff[i]);
+      commit_entry<true>(D, T, s_path, lane, t_e[i], cur.nd, cur.mode, t_borrow[i], s_q + (size_t)i * FR, base + i, t_cq[i], cur.ntg, t_toff[i]);
+      if (lane == 0) t_mode[i] = -1;  // rank and decision already written
       __syncwarp();
       if (c0) urt0 = T.usage[fr0];
       if (c1) urt1 = T.usage[fr1];
+      shadow = *T.shadow_on != 0;
+      prev_nd = cur.nd;
     } else {
-      i64 u0 = 0, u1 = 0;
-      bool ok = true;
-      if (cur.q0 > 0) { u0 = T.usage[cur.nd * FR + fr0]; if (imax(0, avail2(srt0, urt0, cur.s0, u0, cur.l0, cur.b0)) < cur.q0) ok = false; }
-      if (cur.q1 > 0) { u1 = T.usage[cur.nd * FR + fr1]; if (imax(0, avail2(srt1, urt1, cur.s1, u1, cur.l1, cur.b1)) < cur.q1) ok = false; }
+      if (cur.nd == prev_nd) prep(cur);  // same ClusterQueue as the entry before: its usage row changed after the prefetch
+      bool ok = !(cur.q0 > 0 && imax(0, cur.A0 + imin(srt0 - urt0, cur.cap0)) < cur.q0);
+      if (kTwo) ok = ok && !(cur.q1 > 0 && imax(0, cur.A1 + imin(srt1 - urt1, cur.cap1)) < cur.q1);
       ok = __all_sync(0xffffffffu, ok);
       if (ok) {  // addUsage resource_node.go:137-145: the part above the ClusterQueue's local availability goes to the root
-        if (cur.q0 > 0) { i64 la = imax(0, cur.l0 - u0); T.usage[cur.nd * FR + fr0] = u0 + cur.q0; if (cur.q0 > la) urt0 += cur.q0 - la; }
-        if (cur.q1 > 0) { i64 la = imax(0, cur.l1 - u1); T.usage[cur.nd * FR + fr1] = u1 + cur.q1; if (cur.q1 > la) urt1 += cur.q1 - la; }
+        if (cur.q0 > 0) { T.usage[cur.nd * FR + fr0] = cur.u0 + cur.q0; if (cur.q0 > cur.A0) urt0 += cur.q0 - cur.A0; }
+        if (kTwo) if (cur.q1 > 0) { T.usage[cur.nd * FR + fr1] = cur.u1 + cur.q1; if (cur.q1 > cur.A1) urt1 += cur.q1 - cur.A1; }
       }
-      if (lane == 0) D.decision[cur.e] = ok ? KB_DEC_ASSUMED : KB_DEC_SKIPPED_NO_FIT;
+      if (lane == 0) t_mode[i] = (ok ? KB_DEC_ASSUMED : KB_DEC_SKIPPED_NO_FIT) | 0x100;
+      prev_nd = ok ? cur.nd : -1;
     }
-    cur = nxt;
+  };
+  Ops a, b;  // ping-pong: one is being decided while the other is prefetched
+  load(0, a);
+  int i = 0;
+  for (; i + 1 < tn; i += 2) {
+    load(i + 1, b);
+    step(i, a);
+    if (i + 2 < tn) load(i + 2, a);
+    step(i + 1, b);
   }
+  if (i < tn) step(i, a);
   if (c0) T.usage[fr0] = urt0;
   if (c1) T.usage[fr1] = urt1;
   __syncwarp();
@@ -1393,13 +1421,25 @@ __global__ void __launch_bounds__(KB_ADMIT_THREADS) k_admit(DevSnap D, int slot_
     for (int i = threadIdx.x; i < tn; i += blockDim.x) expand_entry(D, t_e[i], s_q + (size_t)i * FR);
     __syncthreads();
     if (warp == 0) {
-      if constexpr (kSmemTables) { if (flat) commit_tile_flat(D, T, s_path, lane, tn, base, s_q, t_e, t_node, t_mode, t_borrow, t_cq, t_ntg, t_toff); }
+      if constexpr (kSmemTables) {
+        if (flat) {
+          if (FR > 32) commit_tile_flat<true>(D, T, s_path, lane, tn, base, s_q, t_e, t_node, t_mode, t_borrow, t_cq, t_ntg, t_toff);
+          else commit_tile_flat<false>(D, T, s_path, lane, tn, base, s_q, t_e, t_node, t_mode, t_borrow, t_cq, t_ntg, t_toff);
+        }
+      }
       if (!flat)
         for (int i = 0; i < tn; i++)
           commit_entry<kSmemTables>(D, T, s_path, lane, t_e[i], t_node[i], t_mode[i], t_borrow[i], s_q + (size_t)i * FR, base + i,
                                     t_cq[i], t_ntg[i], t_toff[i]);
     }
     __syncthreads();
+    if (flat) {  // decisions of the flat commit loop (t_mode[i] = KB_DEC_* | 0x100), written by the whole CTA
+      for (int i = threadIdx.x; i < tn; i += blockDim.x) {
+        int m = t_mode[i];
+        if (m >= 0x100) { D.decision[t_e[i]] = (uint8_t)(m & 0xff); D.rank[t_e[i]] = base + i; }
+      }
+      __syncthreads();
+    }
   }
   publish_usage<kSmemTables>(D, T, nodes, nn);
 }
