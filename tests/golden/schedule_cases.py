@@ -138,3 +138,18 @@ REDUCER_CASES = {
     "no overflow": dict(podsets=[(150_000, 1)] * 8, limit=150_000, found=True, count=150_000),
     "max pods on 1.27": dict(podsets=[(150_000, 1)] + [(1, None)] * 7, limit=150_000, found=True, count=150_000),
 }
+
+# ---- TestSnapshotAddRemoveWorkloadWithLendingLimit pkg/cache/scheduler/snapshot_test.go:1131
+#      lend-a: cpu nominal 10, lendingLimit 4; lend-b: cpu nominal 10, lendingLimit 6 (cohort "lend");
+#      workloads lend-a-1 (1 cpu), lend-a-2 (9), lend-a-3 (6) in lend-a, lend-b-1 (4) in lend-b.
+#      remaining workloads after the case's remove/add -> Usage (milli-cpu) of cohort, lend-a, lend-b
+LENDING_WORKLOADS = {"lend-a-1": ("lend-a", 1), "lend-a-2": ("lend-a", 9), "lend-a-3": ("lend-a", 6), "lend-b-1": ("lend-b", 4)}
+LENDING_CASES = {
+    "remove all": ([], (0, 0, 0)),
+    "remove workload, but still using quota over GuaranteedQuota": (["lend-a-1", "lend-a-3", "lend-b-1"], (1_000, 7_000, 4_000)),
+    "remove wokload, using same quota as GuaranteedQuota": (["lend-a-3", "lend-b-1"], (0, 6_000, 4_000)),
+    "remove workload, using less quota than GuaranteedQuota": (["lend-a-1", "lend-b-1"], (0, 1_000, 4_000)),
+    "remove all then add workload, using less quota than GuaranteedQuota": (["lend-a-1"], (0, 1_000, 0)),
+    "remove all then add workload, using same quota as GuaranteedQuota": (["lend-a-3"], (0, 6_000, 0)),
+    "remove all then add workload, using quota over GuaranteedQuota": (["lend-a-2"], (3_000, 9_000, 0)),
+}

@@ -54,3 +54,13 @@ def reducer_snapshot(tc):
         pss.append(p)
     w = MakeWorkload("wl").ClusterQueue("cq").PodSets(*pss)
     return flatten([cq], pending=[w], now_ns=NOW)
+
+
+def lending_snapshot(remaining):
+    from kueue_b200.api import MakeAdmission
+    from tests.golden.schedule_cases import LENDING_WORKLOADS
+    cqs = [MakeClusterQueue("lend-a").Cohort("lend").ResourceGroup(MakeFlavorQuotas("default").Resource("cpu", "10", "", "4")).Preemption("LowerPriority", "LowerPriority"),
+           MakeClusterQueue("lend-b").Cohort("lend").ResourceGroup(MakeFlavorQuotas("default").Resource("cpu", "10", "", "6")).Preemption("Never", "Any")]
+    adm = [MakeWorkload(n).Request("cpu", str(LENDING_WORKLOADS[n][1])).ReserveQuota(MakeAdmission(LENDING_WORKLOADS[n][0]).Assignment("cpu", "default", str(LENDING_WORKLOADS[n][1])), NOW)
+           for n in remaining]
+    return flatten(cqs, admitted=adm, now_ns=NOW)

@@ -285,3 +285,14 @@ def test_wide_flavor_resource_tables(ev, make):
     snap = make()
     cap = 40 * snap.n_adm + 10000
     assert_cycle_equal(ev.run_cycle(snap, abi.CycleOut(snap, cap)), oracle.run_cycle(snap, cap))
+
+
+def test_reference_usage_with_lending_limit(ev):
+    """TestSnapshotAddRemoveWorkloadWithLendingLimit (snapshot_test.go:1131): k_tree's cohort usage."""
+    from tests.golden.schedule_cases import LENDING_CASES
+    from tests.schedule_golden import lending_snapshot
+    for name, (remaining, (cohort, a, b)) in LENDING_CASES.items():
+        snap, idx = lending_snapshot(remaining)
+        out = ev.tree_eval(snap)
+        fr = idx.fr("default", "cpu")
+        assert (int(out.usage[idx.node("lend"), fr]), int(out.usage[idx.node("lend-a"), fr]), int(out.usage[idx.node("lend-b"), fr])) == (cohort, a, b), name

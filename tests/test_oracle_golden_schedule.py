@@ -103,3 +103,14 @@ def test_podset_reducer_search():  # podset_reducer_test.go:26
             assert all(int(c) >= (m if m is not None else n) for c, (n, m) in zip(out.ps_count, tc["podsets"])), name
         else:
             assert out.decision[0] != abi.DEC_ASSUMED, name
+
+
+def test_usage_with_lending_limit():  # snapshot_test.go:1131 — cohort usage is a function of the ClusterQueue usages
+    from tests.golden.schedule_cases import LENDING_CASES
+    from tests.schedule_golden import lending_snapshot
+    for name, (remaining, (cohort, a, b)) in LENDING_CASES.items():
+        snap, idx = lending_snapshot(remaining)
+        out = oracle.tree_eval(snap)
+        fr = idx.fr("default", "cpu")
+        assert (int(out.usage[idx.node("lend"), fr]), int(out.usage[idx.node("lend-a"), fr]), int(out.usage[idx.node("lend-b"), fr])) == (cohort, a, b), name
+        assert int(out.subtree_quota[idx.node("lend"), fr]) == 10_000, name
