@@ -119,3 +119,8 @@ def sort_candidates(snap, cq):
     rc = lib().ko_sort_candidates(C.byref(s), C.c_int32(cq), order.ctypes.data_as(C.POINTER(C.c_int32)))
     assert rc == 0
     return order.tolist()
+
+
+def is_preferred(a, b, pref):
+    """isPreferred (flavorassigner.go:410-441); a, b = (preemption mode 0..4, borrowing level)."""
+    return bool(lib().ko_is_preferred(C.c_int32(a[0]), C.c_int32(a[1]), C.c_int32(b[0]), C.c_int32(b[1]), C.c_int32(pref)))

@@ -1191,4 +1191,12 @@ int32_t ko_sort_candidates(const kb_snapshot *s, int32_t cq, int32_t *order) {
   for (int i = 0; i < s->n_adm; i++) order[i] = v[i];
   return 0;
 }
+
+// isPreferred (flavorassigner.go:410-441) on explicit granular modes — TestIsPreferred (flavorassigner_test.go:3885).
+// pm: 0 noFit, 1 noCandidates, 2 preempt, 3 reclaim, 4 fit; pref: KB_PREF_*.
+int32_t ko_is_preferred(int32_t a_pm, int32_t a_borrow, int32_t b_pm, int32_t b_borrow, int32_t pref) {
+  kb_snapshot z{};
+  Oracle o(z);
+  return o.isPreferred(GranularMode{a_pm, a_borrow}, GranularMode{b_pm, b_borrow}, pref) ? 1 : 0;
+}
 }  // extern "C"

@@ -296,3 +296,13 @@ def test_reference_usage_with_lending_limit(ev):
         out = ev.tree_eval(snap)
         fr = idx.fr("default", "cpu")
         assert (int(out.usage[idx.node("lend"), fr]), int(out.usage[idx.node("lend-a"), fr]), int(out.usage[idx.node("lend-b"), fr])) == (cohort, a, b), name
+
+
+def test_reference_last_assignment_outdated_cycle(ev):
+    """TestLastAssignmentOutdated (flavorassigner_test.go:3705) through the cycle: device == oracle."""
+    from tests.test_oracle_golden_schedule import _last_assignment_snapshot
+    for cq_gen, wl_gen, flavor in ((1, 0, "one"), (0, 0, "two")):
+        snap, idx = _last_assignment_snapshot(cq_gen, wl_gen)
+        got = ev.run_cycle(snap)
+        assert_cycle_equal(got, oracle.run_cycle(snap))
+        assert idx.flavors[int(got.ps_flavor[0, idx.resources.index("cpu")])] == flavor

@@ -114,3 +114,35 @@ def test_usage_with_lending_limit():  # snapshot_test.go:1131 — cohort usage i
         fr = idx.fr("default", "cpu")
         assert (int(out.usage[idx.node("lend"), fr]), int(out.usage[idx.node("lend-a"), fr]), int(out.usage[idx.node("lend-b"), fr])) == (cohort, a, b), name
         assert int(out.subtree_quota[idx.node("lend"), fr]) == 10_000, name
+
+
+def test_is_preferred():  # flavorassigner_test.go:3885 (granular modes: 2 preempt, 4 fit)
+    FIT, PREEMPT = 4, 2
+    cases = {
+        "feature gate disabled prioritises preemption": ((FIT, 0), (PREEMPT, 0), abi.PREF_UNSET, True),
+        "explicit BorrowingOverPreemption prioritises borrowing distance": ((PREEMPT, 1), (FIT, 2), abi.PREF_BORROWING_OVER_PREEMPTION, False),
+        "explicit PreemptionOverBorrowing prioritises lower preemption": ((PREEMPT, 1), (FIT, 2), abi.PREF_PREEMPTION_OVER_BORROWING, True),
+        "explicit PreemptionOverBorrowing breaks borrowing ties with preemption": ((PREEMPT, 1), (FIT, 1), abi.PREF_PREEMPTION_OVER_BORROWING, False),
+    }
+    for name, (a, b, pref, want) in cases.items():
+        assert oracle.is_preferred(a, b, pref) == want, name
+
+
+def _last_assignment_snapshot(cq_generation, wl_generation):
+    """A workload that tried flavor index 0 last time: it resumes at index 1 only while the ClusterQueue's
+    AllocatableResourceGeneration has not moved past the generation it remembered (lastAssignmentOutdated,
+    flavorassigner.go:749-752; TestLastAssignmentOutdated flavorassigner_test.go:3705)."""
+    from kueue_b200.api import MakePodSet
+    cq = (MakeClusterQueue("cq").Generation(cq_generation).FlavorFungibility("TryNextFlavor", "TryNextFlavor")
+          .ResourceGroup(MakeFlavorQuotas("one").Resource("cpu", "10"), MakeFlavorQuotas("two").Resource("cpu", "10")))
+    w = MakeWorkload("wl").ClusterQueue("cq").PodSets(MakePodSet("main", 1).Request("cpu", "1")).LastAssignment([{"cpu": 0}], wl_generation)
+    return flatten([cq], pending=[w], now_ns=NOW)
+
+
+def test_last_assignment_outdated():
+    for name, cq_gen, wl_gen, flavor in (("Cluster queue allocatableResourceIncreasedGen increased", 1, 0, "one"),
+                                         ("AllocatableResourceGeneration not increased", 0, 0, "two")):
+        snap, idx = _last_assignment_snapshot(cq_gen, wl_gen)
+        out = oracle.run_cycle(snap)
+        assert out.decision[0] == abi.DEC_ASSUMED, name
+        assert idx.flavors[int(out.ps_flavor[0, idx.resources.index("cpu")])] == flavor, name
