@@ -306,3 +306,14 @@ def test_reference_last_assignment_outdated_cycle(ev):
         got = ev.run_cycle(snap)
         assert_cycle_equal(got, oracle.run_cycle(snap))
         assert idx.flavors[int(got.ps_flavor[0, idx.resources.index("cpu")])] == flavor
+
+
+@pytest.mark.parametrize("make", [
+    lambda: synth.make_snapshot(3, W=900, Q=90, F=12, R=4, heads="one_per_cq"),                 # FR = 48: two columns per lane in the flat commit loop
+    lambda: _classical(synth.make_snapshot(3, W=900, Q=90, F=12, R=4, heads="one_per_cq")),
+    lambda: _classical(synth.make_snapshot(3, W=3000, Q=60, F=16, R=4)),                         # FR = 64, several entries per ClusterQueue (stale prefetch path)
+    lambda: _classical(synth.make_snapshot(3, W=3000, Q=60)),                                    # FR = 32, batched heads: same-CQ neighbours
+])
+def test_flat_commit_loop_variants(ev, make):
+    snap = make()
+    assert_cycle_equal(ev.run_cycle(snap), oracle.run_cycle(snap))
