@@ -110,6 +110,24 @@ struct Entry {
   std::vector<Target> targets;
 };
 
+// queues.Heads (pkg/cache/queue/manager.go:770-794): the first workload of every ClusterQueue in queueOrderingFunc
+// order (cluster_queue.go:636-685: higher priority, then queue-order timestamp, then UID).  One workload per
+// ClusterQueue, in first-appearance order of the ClusterQueues.
+inline std::vector<WorkloadInfo> selectHeads(const std::vector<WorkloadInfo> &pending) {
+  auto before = [](const WorkloadInfo &a, const WorkloadInfo &b) {
+    if (a.priority != b.priority) return a.priority > b.priority;
+    if (a.queueOrderTimestampNs != b.queueOrderTimestampNs) return a.queueOrderTimestampNs < b.queueOrderTimestampNs;
+    return a.uid < b.uid;
+  };
+  std::vector<WorkloadInfo> heads;
+  for (const WorkloadInfo &w : pending) {
+    auto it = std::find_if(heads.begin(), heads.end(), [&](const WorkloadInfo &h) { return h.clusterQueue == w.clusterQueue; });
+    if (it == heads.end()) heads.push_back(w);
+    else if (before(w, *it)) *it = w;
+  }
+  return heads;
+}
+
 // Owns the SoA buffers a kb_snapshot points into.
 class FlatSnapshot {
  public:

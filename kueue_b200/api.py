@@ -283,6 +283,24 @@ def queue_order_timestamp(w: "MakeWorkload", pods_ready_requeuing: str = "Evicti
     return w.creation_ns
 
 
+def queue_order_key(w: "MakeWorkload", pods_ready_requeuing: str = "Eviction", priority_sorting: bool = True):
+    """Sort key of queueOrderingFunc (pkg/cache/queue/cluster_queue.go:636-685): higher priority first, then the
+    queue-order timestamp, then UID.  (AdmissionFairSharing usage and the sticky workload are not modelled.)"""
+    return (-w.priority, queue_order_timestamp(w, pods_ready_requeuing, priority_sorting), w.uid)
+
+
+def select_heads(pending: Sequence["MakeWorkload"], pods_ready_requeuing: str = "Eviction", priority_sorting: bool = True):
+    """queues.Heads (manager.go:770-794): the first workload of every ClusterQueue's heap in queueOrderingFunc order.
+    Returns one workload per ClusterQueue, in first-appearance order of the ClusterQueues."""
+    best: Dict[str, "MakeWorkload"] = {}
+    for w in pending:
+        assert w.cq is not None, f"pending workload {w.name} has no ClusterQueue"
+        cur = best.get(w.cq)
+        if cur is None or queue_order_key(w, pods_ready_requeuing, priority_sorting) < queue_order_key(cur, pods_ready_requeuing, priority_sorting):
+            best[w.cq] = w
+    return list(best.values())
+
+
 def flatten(cqs: Sequence[MakeClusterQueue], cohorts: Sequence[MakeCohort] = (),
             pending: Sequence[MakeWorkload] = (), admitted: Sequence[MakeWorkload] = (),
             usage: Optional[Dict[str, Dict[tuple, int]]] = None, flags: int = abi.FLAGS_DEFAULT,

@@ -153,3 +153,14 @@ LENDING_CASES = {
     "remove all then add workload, using same quota as GuaranteedQuota": (["lend-a-3"], (0, 6_000, 0)),
     "remove all then add workload, using quota over GuaranteedQuota": (["lend-a-2"], (3_000, 9_000, 0)),
 }
+
+# ---- TestStrictFIFO pkg/cache/queue/cluster_queue_test.go:892: which of w1 / w2 the ClusterQueue pops first.
+#      (creation offset s, priority, evicted-by-PodsReadyTimeout at offset s | None) x2, ordering, expected
+HIGH, LOW = 1000, -1000
+STRICT_FIFO_CASES = {
+    "w1.priority is higher than w2.priority": ((0, HIGH, None), (1, LOW, None), "Eviction", "w1"),
+    "w1.priority equals w2.priority and w1.create time is earlier than w2.create time": ((0, 0, None), (1, 0, None), "Eviction", "w1"),
+    "... but w1 was evicted": ((0, 0, 2), (1, 0, None), "Eviction", "w2"),
+    "... w1 was evicted but kueue is configured to always use the creation timestamp": ((0, 0, 2), (1, 0, None), "Creation", "w1"),
+    "p1.priority is lower than p2.priority and w1.create time is earlier than w2.create time": ((0, LOW, None), (1, HIGH, None), "Eviction", "w2"),
+}

@@ -155,9 +155,10 @@ def build_schedule_case(doc, tc, capture=None):
             continue  # unknown LocalQueue / ClusterQueue, or inactive ClusterQueue: never reaches the cycle
         pending_by_cq.setdefault(cq, []).append((w, spec))
     pending, dropped = [], []
+    from kueue_b200.api import select_heads
     for cq, lst in pending_by_cq.items():
-        lst.sort(key=lambda t: (-t[0].priority, queue_order_timestamp(t[0]), names.index(t[0].name)))
-        w, spec = lst[0]
+        w = select_heads([t[0].ClusterQueue(cq) for t in lst])[0]  # uid = rank of the key, the reference's UID tie-break
+        spec = next(sp for ww, sp in lst if ww is w)
         if not _selector_matches(cq_by_name[cq]["namespaceSelector"], doc["namespaces"].get(spec["ns"], {})):
             dropped.append(w.name)  # nominate: "Workload namespace doesn't match ClusterQueue selector" -> never an entry
             continue

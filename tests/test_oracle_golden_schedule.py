@@ -146,3 +146,17 @@ def test_last_assignment_outdated():
         out = oracle.run_cycle(snap)
         assert out.decision[0] == abi.DEC_ASSUMED, name
         assert idx.flavors[int(out.ps_flavor[0, idx.resources.index("cpu")])] == flavor, name
+
+
+def test_strict_fifo_head_selection():  # cluster_queue_test.go:892 (host-side queues.Heads mirror)
+    from kueue_b200.api import select_heads
+    from tests.golden.schedule_cases import STRICT_FIFO_CASES, S
+    for name, (a, b, ordering, want) in STRICT_FIFO_CASES.items():
+        ws = []
+        for wname, (created, prio, evicted_at) in (("w1", a), ("w2", b)):
+            w = MakeWorkload(wname).ClusterQueue("cq").Priority(prio).Creation(NOW + created * S)
+            if evicted_at is not None:
+                w.Condition("Evicted", True, "PodsReadyTimeout", NOW + evicted_at * S)
+            ws.append(w)
+        for order in (ws, ws[::-1]):  # push order must not matter
+            assert select_heads(order, ordering)[0].name == want, name
