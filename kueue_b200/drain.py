@@ -1,0 +1,144 @@
+"""Drain mode: iterate scheduling cycles over a snapshot whose pending tables hold whole queues.
+
+Host-side loop around the unchanged single-cycle evaluator — the queue layer stays on the host this round
+(SURVEY §8 f1 is the device version):
+
+  * per ClusterQueue the pending workloads are ordered once by queueOrderingFunc
+    (pkg/cache/queue/cluster_queue.go:636-685: priority desc, queue-order timestamp, UID);
+  * every cycle takes the current head of every ClusterQueue (queues.Heads, manager.go:770-794), runs ONE cycle
+    (`run_cycle`: the device library or, in tests, the oracle) and applies its decisions:
+      - Assumed: the workload leaves the queue, its Assignment.Usage is added to the ClusterQueue usage and it joins
+        the admitted tables (a preemption candidate of later cycles);
+      - not admitted, StrictFIFO: it stays the head (RequeueIfNotPresent is immediate, cluster_queue.go:622-624);
+      - not admitted, BestEffortFIFO: NoFit / Preempt-without-targets go to the inadmissible set and the next workload
+        becomes the head; skipped entries (FailedAfterNomination) and pending preemptions stay (:625-629);
+  * the drain ends with the first cycle that admits nothing (evictions are asynchronous in the reference and are not
+    replayed here: a Preempting entry keeps its place and its targets stay admitted).
+
+The result is defined by this loop; parity between the device and the oracle follows cycle by cycle.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Callable, List
+
+import numpy as np
+
+from . import abi
+from .shard import _csr_take
+
+
+@dataclass
+class DrainResult:
+    cycles: int = 0
+    admitted: List[np.ndarray] = field(default_factory=list)   # per cycle: global pending indices admitted
+    heads: List[np.ndarray] = field(default_factory=list)      # per cycle: global pending indices evaluated
+    decisions: List[np.ndarray] = field(default_factory=list)  # per cycle: KB_DEC_* per entry
+    cq_usage: np.ndarray | None = None                         # final ClusterQueue usage [Q][FR]
+
+    @property
+    def n_admitted(self) -> int:
+        return int(sum(len(a) for a in self.admitted))
+
+    @property
+    def n_decisions(self) -> int:
+        return int(sum(len(h) for h in self.heads))
+
+
+def _queue_order(a, Q):
+    """Pending workloads of every ClusterQueue in queueOrderingFunc order: (order, start[Q+1])."""
+    cq = a["wl_cq"].astype(np.int64)
+    order = np.lexsort((a["wl_uid"], a["wl_ts"], -a["wl_priority"].astype(np.int64), cq))
+    start = np.zeros(Q + 1, np.int64)
+    np.add.at(start, cq + 1, 1)
+    return order, np.cumsum(start)
+
+
+def drain(snap: abi.FlatSnapshot, run_cycle: Callable[[abi.FlatSnapshot], abi.CycleOut], max_cycles: int = 10_000) -> DrainResult:
+    a = snap.arrays
+    Q, R, FR = snap.n_cq, snap.n_resource, snap.n_fr
+    order, qstart = _queue_order(a, Q)
+    qlen = np.diff(qstart)
+    cursor = np.zeros(Q, np.int64)
+    strict = a["cq_strategy"].astype(bool)  # KB_QUEUE_STRICT_FIFO = 1
+    usage = a["cq_usage"].reshape(Q, FR).astype(np.int64).copy()
+    adm = {k: a[k].copy() for k in ("adm_cq", "adm_priority", "adm_ts", "adm_qr_ts", "adm_uid", "adm_evicted", "adm_use_start",
+                                    "adm_use_fr", "adm_use_qty")}
+    ps_start = a["wl_ps_start"].astype(np.int64)
+    ps_req = a["ps_req"].reshape(-1, R)
+    res = DrainResult()
+    static = {k: v for k, v in a.items() if not (k.startswith(("wl_", "ps_", "adm_")) or k in ("heads", "cq_usage"))}
+    covers_pods = np.zeros(Q, bool)
+    if snap.pods_resource >= 0:
+        for q in range(Q):
+            masks = a["rg_res_mask"][a["cq_rg_start"][q]:a["cq_rg_start"][q + 1]]
+            covers_pods[q] = bool(np.any(masks & (1 << snap.pods_resource)))
+    for cyc in range(max_cycles):
+        live = np.flatnonzero(cursor < qlen)
+        if len(live) == 0:
+            break
+        heads = order[qstart[live] + cursor[live]]  # global pending indices, one per ClusterQueue with work left
+        cs = abi.FlatSnapshot(n_cq=Q, n_cohort=snap.n_cohort, n_flavor=snap.n_flavor, n_resource=R, pods_resource=snap.pods_resource,
+                              flags=snap.flags, now_ns=snap.now_ns + cyc, static_generation=snap.static_generation)
+        cs.arrays.update(static)
+        cs.set("cq_usage", usage)
+        for k, v in adm.items():
+            cs.set(k, v)
+        for nm in ("wl_cq", "wl_priority", "wl_ts", "wl_uid", "wl_last_gen"):
+            cs.set(nm, a[nm][heads])
+        st, rows = _csr_take(ps_start, heads)
+        cs.set("wl_ps_start", st)
+        cs.set("ps_req", ps_req[rows]); cs.set("ps_last_tried", a["ps_last_tried"].reshape(-1, R)[rows])
+        for nm in ("ps_req_mask", "ps_count", "ps_min_count", "ps_flavor_ok"):
+            cs.set(nm, a[nm][rows])
+        cs.set("heads", np.arange(len(heads)))
+        cs.finalize()
+        out = run_cycle(cs)
+        dec = np.asarray(out.decision).copy()
+        res.cycles += 1
+        res.heads.append(heads); res.decisions.append(dec)
+        ok = dec == abi.DEC_ASSUMED
+        res.admitted.append(heads[ok])
+        # ---- apply the admissions: Assignment.Usage (flavorassigner.go:198-218) with the admitted counts
+        new_fr, new_qty, new_start = [], [], [int(adm["adm_use_start"][-1])]
+        for e in np.flatnonzero(ok):
+            cqi = int(cs.arrays["wl_cq"][e])
+            cells = {}
+            for row in range(int(st[e]), int(st[e + 1])):
+                full, cnt = int(cs.arrays["ps_count"][row]), int(out.ps_count[row])
+                for r in range(R):
+                    f = int(out.ps_flavor[row, r])
+                    if f < 0:
+                        continue
+                    if covers_pods[cqi] and r == snap.pods_resource:
+                        q = cnt
+                    else:
+                        q = int(cs.arrays["ps_req"].reshape(-1, R)[row, r])
+                        if full != 0 and full != cnt:
+                            q = q // full * cnt  # ScaledTo workload.go:258-275
+                    cells[f * R + r] = cells.get(f * R + r, 0) + q
+            for fr, q in cells.items():
+                usage[cqi, fr] += q
+                new_fr.append(fr); new_qty.append(q)
+            new_start.append(new_start[-1] + len(cells))
+        n_new = int(ok.sum())
+        if n_new:
+            g = heads[ok]
+            adm["adm_cq"] = np.concatenate([adm["adm_cq"], a["wl_cq"][g]])
+            adm["adm_priority"] = np.concatenate([adm["adm_priority"], a["wl_priority"][g]])
+            adm["adm_ts"] = np.concatenate([adm["adm_ts"], a["wl_ts"][g]])
+            adm["adm_qr_ts"] = np.concatenate([adm["adm_qr_ts"], np.full(n_new, snap.now_ns + cyc, np.int64)])
+            adm["adm_uid"] = np.concatenate([adm["adm_uid"], a["wl_uid"][g]])
+            adm["adm_evicted"] = np.concatenate([adm["adm_evicted"], np.zeros(n_new, np.uint8)])
+            adm["adm_use_start"] = np.concatenate([adm["adm_use_start"], np.asarray(new_start[1:], np.int32)])
+            adm["adm_use_fr"] = np.concatenate([adm["adm_use_fr"], np.asarray(new_fr, np.int32)])
+            adm["adm_use_qty"] = np.concatenate([adm["adm_use_qty"], np.asarray(new_qty, np.int64)])
+        # ---- queue movement (cluster_queue.go:609-633)
+        cqs = live
+        inadmissible = (dec == abi.DEC_NOFIT) | (dec == abi.DEC_PREEMPT_NO_TARGETS)
+        advance = ok | (inadmissible & ~strict[cqs])
+        cursor[cqs[advance]] += 1
+        if n_new == 0:
+            break
+    res.cq_usage = usage
+    return res

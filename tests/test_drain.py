@@ -1,0 +1,74 @@
+"""Drain mode (kueue_b200/drain.py): iterated cycles over whole queues.  CPU: the loop's bookkeeping on the oracle;
+GPU: the same drain through the device library is identical cycle by cycle."""
+import numpy as np
+import pytest
+
+import oracle
+from kueue_b200 import abi, synth
+from kueue_b200.drain import drain
+
+CASES = [
+    lambda: synth.make_snapshot(1),                                                   # 100 workloads, 10 cohort-less ClusterQueues
+    lambda: synth.make_snapshot(2, W=3000, Q=30, podsets_max=2),                      # StrictFIFO: a blocked head stops its queue
+    lambda: synth.make_snapshot(3, W=2000, Q=40),                                     # BestEffortFIFO + fair sharing in flat cohorts
+    lambda: synth.make_snapshot(3, W=1500, Q=60, partial=True, podsets_max=2),                # partial admission: reduced counts enter the usage
+]
+
+
+def _check(snap, res):
+    a = snap.arrays
+    Q, FR = snap.n_cq, snap.n_fr
+    assert res.cycles >= 1 and len(res.heads) == res.cycles
+    adm = np.concatenate(res.admitted) if res.admitted else np.zeros(0, np.int64)
+    assert len(np.unique(adm)) == len(adm), "a workload was admitted twice"
+    for heads, dec in zip(res.heads, res.decisions):
+        cqs = a["wl_cq"][heads]
+        assert len(np.unique(cqs)) == len(cqs), "more than one head of a ClusterQueue in a cycle"
+    # every head is the best not-yet-admitted, not-set-aside workload of its queue: priorities never increase along a queue
+    seen = {}
+    for heads in res.heads:
+        for w in heads:
+            c = int(a["wl_cq"][w])
+            key = (-int(a["wl_priority"][w]), int(a["wl_ts"][w]), int(a["wl_uid"][w]))
+            if c in seen and seen[c][1] != int(w):
+                assert seen[c][0] < key, "queue order violated"
+            seen[c] = (key, int(w))
+    assert (res.cq_usage >= a["cq_usage"].reshape(Q, FR)).all()
+    assert len(res.admitted[-1]) == 0 or res.cycles == 10_000 or all(len(h) for h in res.heads)
+
+
+@pytest.mark.parametrize("make", CASES)
+def test_drain_on_oracle(make):
+    snap = make()
+    res = drain(snap, oracle.run_cycle)
+    _check(snap, res)
+    assert res.n_admitted > 0 and res.cycles > 1
+    again = drain(snap, oracle.run_cycle)
+    assert again.cycles == res.cycles and all(np.array_equal(x, y) for x, y in zip(again.decisions, res.decisions))
+
+
+def test_first_drain_cycle_is_the_reference_cycle():
+    snap = synth.make_snapshot(3, W=2000, Q=40, heads="one_per_cq")
+    one = oracle.run_cycle(synth.compact_to_heads(snap))
+    res = drain(synth.make_snapshot(3, W=2000, Q=40), oracle.run_cycle, max_cycles=1)
+    # same heads (queues.Heads) in ClusterQueue order, same decisions
+    assert np.array_equal(np.sort(res.heads[0]), np.sort(snap.arrays["heads"]))
+    by_cq = {int(snap.arrays["wl_cq"][w]): int(d) for w, d in zip(snap.arrays["heads"], one.decision)}
+    assert [by_cq[int(snap.arrays["wl_cq"][w])] for w in res.heads[0]] == res.decisions[0].tolist()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("make", CASES)
+def test_drain_device_equals_oracle(make):
+    from kueue_b200 import native
+    ev = native.Evaluator(0)
+    try:
+        snap = make()
+        want = drain(snap, oracle.run_cycle)
+        got = drain(snap, ev.run_cycle)
+        assert got.cycles == want.cycles
+        for k in range(want.cycles):
+            assert np.array_equal(got.heads[k], want.heads[k]) and np.array_equal(got.decisions[k], want.decisions[k]), k
+        assert np.array_equal(got.cq_usage, want.cq_usage)
+    finally:
+        ev.close()
