@@ -1,0 +1,352 @@
+// Package scheduler — drop-in shim that routes the decision part of Scheduler.schedule()
+// (pkg/scheduler/scheduler.go:245-405) through libkueue_b200.
+//
+// STATUS: reference-side binding for maintainers.  It is NOT compiled in the repository's build image (there is
+// no Go toolchain there); it restates, in the reference's own language and against the reference's own types, the
+// host layer that IS built and tested in C++ (include/kueue_b200_host.hpp, tests/test_cpp_host.py) and Python
+// (kueue_b200/api.py).  Field-by-field mapping: INTEGRATION.md §3.
+//
+// Placement: pkg/scheduler/kueue_b200_shim.go, build tag `kueue_b200`.  Nothing else in Kueue changes.
+
+//go:build kueue_b200
+
+package scheduler
+
+/*
+#cgo CFLAGS: -I${SRCDIR}/../../third_party/kueue_b200/include
+#cgo LDFLAGS: -L${SRCDIR}/../../third_party/kueue_b200 -lkueue_b200
+#include "kueue_b200.h"
+*/
+import "C"
+
+import (
+	"fmt"
+	"runtime"
+	"slices"
+	"sort"
+	"unsafe"
+
+	corev1 "k8s.io/api/core/v1"
+
+	kueue "sigs.k8s.io/kueue/apis/kueue/v1beta2"
+	schdcache "sigs.k8s.io/kueue/pkg/cache/scheduler"
+	"sigs.k8s.io/kueue/pkg/features"
+	"sigs.k8s.io/kueue/pkg/resources"
+	"sigs.k8s.io/kueue/pkg/util/priority"
+	"sigs.k8s.io/kueue/pkg/workload"
+)
+
+// kbEvaluator owns one kb_handle (one CUDA device, one stream).  schedule() is single-goroutine
+// (scheduler.go:188-194), which is exactly the library's threading contract.
+type kbEvaluator struct {
+	h         *C.kb_handle
+	staticGen int64 // bumped by the cache whenever a ClusterQueue / Cohort spec changes
+}
+
+func newKBEvaluator(device int) (*kbEvaluator, error) {
+	var h *C.kb_handle
+	cfg := C.kb_config{device: C.int32_t(device)}
+	if rc := C.kb_create(&cfg, &h); rc != 0 {
+		return nil, fmt.Errorf("kb_create: %d %s", int(rc), C.GoString(C.kb_last_error(nil)))
+	}
+	return &kbEvaluator{h: h}, nil
+}
+
+// pinned returns a slice over page-locked memory owned by the library: the Go GC never moves it and C keeps no Go
+// pointer after the call returns (cgo pointer rules).  In production all tables are carved out of ONE block so
+// the library moves the per-cycle tables with a single DMA (INTEGRATION.md §3).
+func pinned[T any](n int) []T {
+	var p unsafe.Pointer
+	var zero T
+	C.kb_alloc_pinned(&p, C.uint64_t(uintptr(max(n, 1))*unsafe.Sizeof(zero)))
+	return unsafe.Slice((*T)(p), n)
+}
+
+// flatSnapshot is kb_snapshot plus the name tables needed to read the outputs back.
+type flatSnapshot struct {
+	c         C.kb_snapshot
+	cqs       []*schdcache.ClusterQueueSnapshot
+	flavors   []kueue.ResourceFlavorReference
+	resources []corev1.ResourceName
+	admitted  []*workload.Info
+}
+
+func (f *flatSnapshot) fr(flavor kueue.ResourceFlavorReference, res corev1.ResourceName) int {
+	return slices.Index(f.flavors, flavor)*len(f.resources) + slices.Index(f.resources, res)
+}
+
+const noLimit = int64(^uint64(0) >> 1) // KB_NO_LIMIT
+
+// flatten: cache.Snapshot + queues.Heads -> SoA.  Same layout rules as kb::FlatSnapshot (kueue_b200_host.hpp):
+// ClusterQueues first then Cohorts, fr = flavor*R + resource, resources sorted by name.
+func (s *Scheduler) flatten(snap *schdcache.Snapshot, heads []workload.Info, gen int64) *flatSnapshot {
+	f := &flatSnapshot{}
+	cqNames := snap.ClusterQueuesNames()
+	slices.Sort(cqNames)
+	cohortNames := make([]kueue.CohortReference, 0)
+	for name := range snap.Cohorts() {
+		cohortNames = append(cohortNames, name)
+	}
+	slices.Sort(cohortNames)
+	resSet := map[corev1.ResourceName]struct{}{}
+	for _, n := range cqNames {
+		cq := snap.ClusterQueue(n)
+		f.cqs = append(f.cqs, cq)
+		for _, rg := range cq.ResourceGroups {
+			for _, fl := range rg.Flavors {
+				if !slices.Contains(f.flavors, fl) {
+					f.flavors = append(f.flavors, fl)
+				}
+			}
+			for r := range rg.CoveredResources {
+				resSet[r] = struct{}{}
+			}
+		}
+	}
+	for i := range heads {
+		for _, ps := range heads[i].TotalRequests {
+			for r := range ps.Requests {
+				resSet[r] = struct{}{}
+			}
+		}
+	}
+	for r := range resSet {
+		f.resources = append(f.resources, r)
+	}
+	sort.Slice(f.resources, func(i, j int) bool { return f.resources[i] < f.resources[j] }) // DRS tie-break compares names
+	Q, C_, F, R := len(cqNames), len(cohortNames), len(f.flavors), len(f.resources)
+	N, FR := Q+C_, F*R
+
+	parent := pinned[int32](N)
+	weight := pinned[float64](N)
+	nominal, blimit, llimit := pinned[int64](N*FR), pinned[int64](N*FR), pinned[int64](N*FR)
+	usage := pinned[int64](Q * FR)
+	for i := range blimit {
+		blimit[i], llimit[i] = noLimit, noLimit
+	}
+	quotas := func(n int, q map[resources.FlavorResource]schdcache.ResourceQuota) {
+		for fr, rq := range q {
+			c := n*FR + f.fr(fr.Flavor, fr.Resource)
+			nominal[c] = rq.Nominal
+			if rq.BorrowingLimit != nil {
+				blimit[c] = *rq.BorrowingLimit
+			}
+			if rq.LendingLimit != nil {
+				llimit[c] = *rq.LendingLimit
+			}
+		}
+	}
+	cohortIdx := func(name kueue.CohortReference) int32 { return int32(Q + slices.Index(cohortNames, name)) }
+	// ---- ClusterQueue tables
+	within, reclaim, bwc := pinned[uint8](Q), pinned[uint8](Q), pinned[uint8](Q)
+	hasThr, thr := pinned[uint8](Q), pinned[int32](Q)
+	wcb, wcp, pref, strat, cqGen := pinned[uint8](Q), pinned[uint8](Q), pinned[uint8](Q), pinned[uint8](Q), pinned[int64](Q)
+	var rgStart, rgMask, rgFlStart, rgFl []int32
+	rgStart, rgFlStart = append(rgStart, 0), append(rgFlStart, 0)
+	for i, cq := range f.cqs {
+		parent[i] = -1
+		if cq.HasParent() {
+			parent[i] = cohortIdx(cq.Parent().GetName())
+		}
+		weight[i] = cq.FairWeight
+		quotas(i, cq.ResourceNode.Quotas)
+		for fr, q := range cq.ResourceNode.Usage {
+			usage[i*FR+f.fr(fr.Flavor, fr.Resource)] = q
+		}
+		within[i], reclaim[i] = policyCode(cq.Preemption.WithinClusterQueue), policyCode(cq.Preemption.ReclaimWithinCohort)
+		if b := cq.Preemption.BorrowWithinCohort; b != nil && b.Policy != kueue.BorrowWithinCohortPolicyNever {
+			bwc[i] = C.KB_POLICY_LOWER_PRIORITY
+			if b.MaxPriorityThreshold != nil {
+				hasThr[i], thr[i] = 1, *b.MaxPriorityThreshold
+			}
+		}
+		wcb[i], wcp[i], pref[i] = fungibilityCodes(cq.FlavorFungibility)
+		cqGen[i] = cq.AllocatableResourceGeneration
+		for _, rg := range cq.ResourceGroups {
+			var mask int32
+			for r := range rg.CoveredResources {
+				mask |= 1 << slices.Index(f.resources, r)
+			}
+			rgMask = append(rgMask, mask)
+			for _, fl := range rg.Flavors {
+				rgFl = append(rgFl, int32(slices.Index(f.flavors, fl)))
+			}
+			rgFlStart = append(rgFlStart, int32(len(rgFl)))
+		}
+		rgStart = append(rgStart, int32(len(rgMask)))
+	}
+	for j, name := range cohortNames {
+		co := snap.Cohort(name)
+		parent[Q+j] = -1
+		if co.HasParent() {
+			parent[Q+j] = cohortIdx(co.Parent().GetName())
+		}
+		weight[Q+j] = co.FairWeight
+		quotas(Q+j, co.ResourceNode.Quotas)
+	}
+	// ---- admitted workloads (preemption candidates), per ClusterQueue in name order
+	var admCq, admPrio, admUseStart, admFr []int32
+	var admTs, admQr, admUID, admQty []int64
+	var admEv []uint8
+	admUseStart = append(admUseStart, 0)
+	for i, cq := range f.cqs {
+		keys := make([]workload.Reference, 0, len(cq.Workloads))
+		for k := range cq.Workloads {
+			keys = append(keys, k)
+		}
+		slices.Sort(keys)
+		for _, k := range keys {
+			wi := cq.Workloads[k]
+			f.admitted = append(f.admitted, wi)
+			admCq, admPrio = append(admCq, int32(i)), append(admPrio, priority.Priority(wi.Obj))
+			admTs = append(admTs, s.workloadOrdering.GetQueueOrderTimestamp(wi.Obj).UnixNano())
+			admQr = append(admQr, quotaReservedNs(wi.Obj)) // INT64_MIN when the condition is missing (ordering.go:93-100)
+			admEv = append(admEv, b2u(workload.IsEvicted(wi.Obj)))
+			for fr, q := range wi.FlavorResourceUsage() {
+				admFr, admQty = append(admFr, int32(f.fr(fr.Flavor, fr.Resource))), append(admQty, q)
+			}
+			admUseStart = append(admUseStart, int32(len(admFr)))
+		}
+	}
+	uidRank(f.admitted, &admUID) // dense ranks consistent with the UID string order
+	// ---- entries of this cycle
+	var wlCq, wlPrio, wlPsStart, psCount, psMin, psMask []int32
+	var wlTs, wlUID, wlGen, psReq []int64
+	var psOk []uint64
+	var psLast []int8
+	wlPsStart = append(wlPsStart, 0)
+	for i := range heads {
+		w := &heads[i]
+		ci := slices.IndexFunc(f.cqs, func(c *schdcache.ClusterQueueSnapshot) bool { return c.Name == w.ClusterQueue })
+		wlCq, wlPrio = append(wlCq, int32(ci)), append(wlPrio, priority.Priority(w.Obj))
+		wlTs = append(wlTs, s.workloadOrdering.GetQueueOrderTimestamp(w.Obj).UnixNano())
+		gen := int64(-1)
+		if w.LastAssignment != nil {
+			gen = w.LastAssignment.ClusterQueueGeneration
+		}
+		wlGen = append(wlGen, gen)
+		for pi, ps := range w.TotalRequests {
+			row := make([]int64, R)
+			last := make([]int8, R)
+			var mask int32
+			for r, q := range ps.Requests {
+				ri := slices.Index(f.resources, r)
+				row[ri], mask = q, mask|1<<ri // TotalRequests already holds Count pods (workload.go:567-598)
+			}
+			for ri := range last {
+				last[ri] = -1
+			}
+			if w.LastAssignment != nil && pi < len(w.LastAssignment.LastTriedFlavorIdx) {
+				for r, idx := range w.LastAssignment.LastTriedFlavorIdx[pi] {
+					last[slices.Index(f.resources, r)] = int8(idx)
+				}
+			}
+			minCount := int32(-1)
+			if mc := w.Obj.Spec.PodSets[pi].MinCount; mc != nil && features.Enabled(features.PartialAdmission) {
+				minCount = *mc
+			}
+			psReq, psLast = append(psReq, row...), append(psLast, last...)
+			psMask, psCount, psMin = append(psMask, mask), append(psCount, ps.Count), append(psMin, minCount)
+			psOk = append(psOk, s.eligibleFlavors(w, pi, f.cqs[ci], f.flavors)) // checkFlavorForPodSets flavorassigner.go:899-944
+		}
+		wlPsStart = append(wlPsStart, int32(len(psCount)))
+	}
+	wlUIDRank(heads, &wlUID)
+	headsIdx := make([]int32, len(heads))
+	for i := range headsIdx {
+		headsIdx[i] = int32(i)
+	}
+	// ---- struct (every table copied into pinned memory; copyPinned omitted for brevity: pinned[T](len) + copy)
+	c := &f.c
+	c.n_cq, c.n_cohort, c.n_flavor, c.n_resource = C.int32_t(Q), C.int32_t(C_), C.int32_t(F), C.int32_t(R)
+	c.n_rg, c.n_wl, c.n_podset = C.int32_t(len(rgMask)), C.int32_t(len(heads)), C.int32_t(len(psCount))
+	c.n_adm, c.n_adm_use, c.n_heads = C.int32_t(len(admCq)), C.int32_t(len(admFr)), C.int32_t(len(heads))
+	c.pods_resource = C.int32_t(slices.Index(f.resources, corev1.ResourcePods))
+	c.flags, c.now_ns, c.static_generation = C.uint32_t(s.kbFlags()), C.int64_t(s.clock.Now().UnixNano()), C.int64_t(gen)
+	c.parent, c.fair_weight = (*C.int32_t)(&parent[0]), (*C.double)(&weight[0])
+	c.nominal, c.borrow_limit, c.lend_limit = (*C.int64_t)(&nominal[0]), (*C.int64_t)(&blimit[0]), (*C.int64_t)(&llimit[0])
+	c.cq_usage = (*C.int64_t)(&usage[0])
+	c.cq_within_cq, c.cq_reclaim_within, c.cq_borrow_within = (*C.uint8_t)(&within[0]), (*C.uint8_t)(&reclaim[0]), (*C.uint8_t)(&bwc[0])
+	c.cq_has_bwc_threshold, c.cq_bwc_threshold = (*C.uint8_t)(&hasThr[0]), (*C.int32_t)(&thr[0])
+	c.cq_when_can_borrow, c.cq_when_can_preempt, c.cq_preference = (*C.uint8_t)(&wcb[0]), (*C.uint8_t)(&wcp[0]), (*C.uint8_t)(&pref[0])
+	c.cq_strategy, c.cq_generation = (*C.uint8_t)(&strat[0]), (*C.int64_t)(&cqGen[0])
+	c.cq_rg_start, c.rg_res_mask = cp32(rgStart), (*C.uint32_t)(unsafe.Pointer(cp32(rgMask)))
+	c.rg_flavor_start, c.rg_flavors = cp32(rgFlStart), cp32(rgFl)
+	c.wl_cq, c.wl_priority, c.wl_ts, c.wl_uid, c.wl_last_gen = cp32(wlCq), cp32(wlPrio), cp64(wlTs), cp64(wlUID), cp64(wlGen)
+	c.wl_ps_start, c.ps_req, c.ps_req_mask = cp32(wlPsStart), cp64(psReq), (*C.uint32_t)(unsafe.Pointer(cp32(psMask)))
+	c.ps_count, c.ps_min_count, c.ps_flavor_ok, c.ps_last_tried = cp32(psCount), cp32(psMin), cpU64(psOk), cpI8(psLast)
+	c.adm_cq, c.adm_priority, c.adm_ts, c.adm_qr_ts, c.adm_uid = cp32(admCq), cp32(admPrio), cp64(admTs), cp64(admQr), cp64(admUID)
+	c.adm_evicted, c.adm_use_start, c.adm_use_fr, c.adm_use_qty = cpU8(admEv), cp32(admUseStart), cp32(admFr), cp64(admQty)
+	c.heads = cp32(headsIdx)
+	return f
+}
+
+// scheduleKB replaces nominate + makeIterator + the decision part of the loop (scheduler.go:255-401) and replays
+// the side effects in the order the library committed the entries.
+func (s *Scheduler) scheduleKB(heads []workload.Info, snap *schdcache.Snapshot) ([]entry, error) {
+	f := s.flatten(snap, heads, s.kb.staticGen)
+	H, P, R := len(heads), int(f.c.n_podset), len(f.resources)
+	decision, mode := pinned[uint8](H), pinned[uint8](H)
+	borrow, rank := pinned[int32](H), pinned[int32](H)
+	psFlavor, psMode, psTried := pinned[int8](P*R), pinned[int8](P*R), pinned[int8](P*R)
+	psCount, tgtStart := pinned[int32](P), pinned[int32](H+1)
+	capT := 4*int(f.c.n_adm) + 1024
+	tgtAdm, tgtReason := pinned[int32](capT), pinned[uint8](capT)
+	out := C.kb_cycle_out{decision: (*C.uint8_t)(&decision[0]), mode: (*C.uint8_t)(&mode[0]), borrow: (*C.int32_t)(&borrow[0]),
+		commit_rank: (*C.int32_t)(&rank[0]), ps_flavor: (*C.int8_t)(&psFlavor[0]), ps_res_mode: (*C.int8_t)(&psMode[0]),
+		ps_tried_idx: (*C.int8_t)(&psTried[0]), ps_count: (*C.int32_t)(&psCount[0]), tgt_start: (*C.int32_t)(&tgtStart[0]),
+		tgt_adm: (*C.int32_t)(&tgtAdm[0]), tgt_reason: (*C.uint8_t)(&tgtReason[0]), tgt_capacity: C.int32_t(capT)}
+	runtime.LockOSThread() // CUDA context affinity; kb_run_cycle is blocking and not re-entrant per handle
+	rc := C.kb_run_cycle(s.kb.h, &f.c, &out)
+	runtime.UnlockOSThread()
+	if rc != 0 { // any error: the caller runs the stock Go cycle, outputs are not consumed
+		return nil, fmt.Errorf("kb_run_cycle: %d %s", int(rc), C.GoString(C.kb_last_error(s.kb.h)))
+	}
+	entries := make([]entry, H)
+	row := 0
+	for e := range heads {
+		en := &entries[e]
+		en.Info = heads[e]
+		en.clusterQueueSnapshot = f.cqs[slices.IndexFunc(f.cqs, func(c *schdcache.ClusterQueueSnapshot) bool { return c.Name == heads[e].ClusterQueue })]
+		en.assignment = s.assignmentFromRows(f, &heads[e], row, psFlavor, psMode, psTried, psCount, int(borrow[e])) // Flavors/Mode/TriedFlavorIdx/Count/Usage
+		row += len(heads[e].TotalRequests)
+		for k := tgtStart[e]; k < tgtStart[e+1]; k++ {
+			en.preemptionTargets = append(en.preemptionTargets, s.targetFrom(f.admitted[tgtAdm[k]], tgtReason[k])) // preemption.go:111-115
+		}
+		switch decision[e] {
+		case C.KB_DEC_ASSUMED:
+			en.status = assumed // admit() is replayed by the caller (scheduler.go:397-400)
+		case C.KB_DEC_PREEMPTING:
+			en.status = nominated // IssuePreemptions (:344-359)
+		case C.KB_DEC_SKIPPED_OVERLAP, C.KB_DEC_SKIPPED_NO_FIT:
+			en.status = skipped
+		}
+	}
+	// replay order: per root cohort by commit_rank (the iterator's pop order, scheduler.go:269)
+	sort.SliceStable(entries, func(i, j int) bool { return rank[i] < rank[j] })
+	return entries, nil
+}
+
+func policyCode(p kueue.PreemptionPolicy) uint8 {
+	switch p {
+	case kueue.PreemptionPolicyLowerPriority:
+		return C.KB_POLICY_LOWER_PRIORITY
+	case kueue.PreemptionPolicyLowerOrNewerEqualPriority:
+		return C.KB_POLICY_LOWER_OR_NEWER_EQUAL_PRIORITY
+	case kueue.PreemptionPolicyAny:
+		return C.KB_POLICY_ANY
+	}
+	return C.KB_POLICY_NEVER
+}
+
+func b2u(b bool) uint8 {
+	if b {
+		return 1
+	}
+	return 0
+}
+
+// Small helpers left to the integrator (each a few lines): fungibilityCodes, quotaReservedNs, uidRank / wlUIDRank,
+// cp32 / cp64 / cpU8 / cpI8 / cpU64 (copy a Go slice into pinned memory and return the C pointer),
+// (*Scheduler).eligibleFlavors (checkFlavorForPodSets per flavor -> bitmask), kbFlags (feature gates -> KB_F_*),
+// assignmentFromRows and targetFrom (output rows -> flavorassigner.Assignment / preemption.Target).
