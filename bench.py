@@ -65,7 +65,17 @@ def algorithmic_bytes(snap) -> dict:
     wl_in = W * (P * R * 8 + 24)
     wl_out = W * (8 + P * nrg)
     nodes = N * FR * 32 + N * 16
-    return {"k_nominate": wl_in + wl_out + nodes, "k_nominate_search": wl_in + wl_out + nodes,
+    A = snap.n_adm
+    AU = len(snap.arrays["adm_use_fr"])
+    return {"k_nominate": wl_in + wl_out + nodes, "k_nominate_search_fair": wl_in + wl_out + nodes,
+            # ranking of the admitted workloads: cq, priority, reservation time, uid, evicted in; sorted index, rank, per-CQ list out
+            "k_rank_admitted": A * 37,
+            # search tables: the four [node][FR] quota tables in, transposed usage + 32 B cell record + mask out; usage cells in, 32 B bucket records out
+            "k_search_tables": N * FR * (32 + 44) + AU * (12 + 32),
+            # target searches stream 32 B candidate records; the count is data dependent and reported by the library
+            # (kb_stats.search_records); this entry is the per-entry floor used when the counter is absent
+            "k_search_cells": wl_in + nodes, "k_nominate_walk": wl_in + wl_out + nodes,
+            "k_fair_prep": N * FR * 16 + N * R * 16, "k_drain": W * 64, "k_tas": 0, "-": 0,
             "k_tree": N * FR * 64 + N * 16, "k_lone": N * FR * 64,
             "k_rank": W * 36, "k_scatter": W * 72, "k_scan_roots": N * 8,
             "k_admit": W * (P * R * 9 + 16) + N * FR * 40 + W * 5,
@@ -216,7 +226,7 @@ def main():
     barrier()
     t_wall0 = time.perf_counter()
     dev_ms = 0.0
-    kms = np.zeros(8)
+    kms = np.zeros(16)
     launches = 0
     for _ in range(args.steps):
         flush.zero_(); torch.cuda.synchronize()  # L2 flush between timed iterations
@@ -281,7 +291,7 @@ def main():
             "clocks": clocks,
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches,
-            "kernel_ms_per_step": {abi.KERNEL_NAMES[i]: kms[i] / args.steps for i in range(8) if kms[i] > 0},
+            "kernel_ms_per_step": {abi.KERNEL_NAMES[i]: kms[i] / args.steps for i in range(16) if kms[i] > 0},
             "roofline": {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak if peak else None, "traffic": measured_traffic(args.config, kname),
                          "algorithmic_bytes_per_launch": kbytes, "kernel_ms": top_ms,

@@ -66,7 +66,16 @@ struct kb_handle {
   // host-side derived topology
   std::vector<int32_t> root_slot, depth, height, tree_start, tree_nodes, tree_level, lone, cq_adm_start, cq_adm, local_idx, child_start, child_list, adm_sorted, root_adm_start, adm_rank, root_cq_start;
   std::vector<uint8_t> tree_flat;
+  std::vector<int32_t> sn_node, slot_base, nd_tin, nd_tout;
   int max_root_adm = 1;
+  int max_frl_len = 1;      // longest (root, flavor-resource) candidate bucket of this cycle
+  int max_head_podsets = 1; // most podsets of one entry (bounds the columns a GetTargets search tracks)
+  // launch configuration of the warp-cooperative classical search (k_search_cells / k_nominate_walk)
+  int sa_wpb = 1, sa_grid = 1, sa_col_elems = 0, sa_codes = 0; size_t sa_smem = 0;
+  int sb_wpb = 1, sb_grid = 1, sb_col_elems = 0; size_t sb_smem = 0;
+  int sa_list_cap = 32, sb_list_cap = 32;
+  // device ranking of the admitted workloads (kb_rank.cuh)
+  u64 *rk_keys[2] = {nullptr, nullptr}; int32_t *rk_vals[2] = {nullptr, nullptr}; void *rk_temp = nullptr; size_t rk_temp_bytes = 0;
   int search_grid = 1;
   bool search_smem = true;
   size_t search_smem_bytes = 0;
@@ -256,6 +265,34 @@ static int32_t build_static(kb_handle *h, const kb_snapshot *s) {
   h->D.nTrees = ntrees;
   h->D.nLone = (int)h->lone.size();
   h->D.nRoots = nroots;
+  {  // slot-node numbering (cohort-less ClusterQueues, then the trees) and Euler-tour intervals inside every tree
+    int nl = (int)h->lone.size();
+    h->sn_node.assign(std::max(1, N), 0); h->nd_tin.assign(std::max(1, N), 0); h->nd_tout.assign(std::max(1, N), 1);
+    h->slot_base.assign(nroots + 1, 0);
+    for (int i = 0; i < nl; i++) { h->sn_node[i] = h->lone[i]; h->slot_base[i] = i; }
+    for (int t = 0; t < ntrees; t++) h->slot_base[nl + t] = nl + h->tree_start[t];
+    h->slot_base[nroots] = N;
+    for (size_t i = 0; i < h->tree_nodes.size(); i++) h->sn_node[nl + i] = h->tree_nodes[i];
+    std::vector<int32_t> stack, it;
+    for (int t = 0; t < ntrees; t++) {
+      int base = nl + h->tree_start[t];
+      int rootn = h->tree_nodes[h->tree_start[t]];
+      int clock = 0;
+      stack.assign(1, rootn); it.assign(1, h->child_start[rootn]);
+      h->nd_tin[base + h->local_idx[rootn]] = clock++;
+      while (!stack.empty()) {
+        int n = stack.back();
+        if (it.back() < h->child_start[n + 1]) {
+          int c = h->child_list[it.back()++];
+          h->nd_tin[base + h->local_idx[c]] = clock++;
+          stack.push_back(c); it.push_back(h->child_start[c]);
+        } else {
+          h->nd_tout[base + h->local_idx[n]] = clock;
+          stack.pop_back(); it.pop_back();
+        }
+      }
+    }
+  }
   return KB_OK;
 }
 
@@ -272,38 +309,32 @@ static int32_t build_dynamic(kb_handle *h, const kb_snapshot *s) {
     h->cq_adm_start[c + 1]++;
   }
   for (int q = 0; q < Q; q++) h->cq_adm_start[q + 1] += h->cq_adm_start[q];
-  h->cq_adm.assign(std::max(1, s->n_adm), 0);
-  // admitted workloads per root, in the preemptor-independent part of CandidatesOrdering
-  // (preemption/common/ordering.go:41-100): evicted first, lower priority first, more recently
-  // reserved first, UID.  TODO(next): radix sort on the device / incremental order kept by the host cache.
+  // admitted workloads per root: only the counts are needed on the host (scratch sizing); the ranking by the
+  // preemptor-independent part of CandidatesOrdering runs on the device every cycle (kb_rank.cuh)
   h->root_adm_start.assign(nroots + 1, 0);
   for (int a = 0; a < s->n_adm; a++) h->root_adm_start[h->root_slot[s->adm_cq[a]] + 1]++;
   h->max_root_adm = 1;
   for (int r = 0; r < nroots; r++) { h->max_root_adm = std::max(h->max_root_adm, h->root_adm_start[r + 1]); h->root_adm_start[r + 1] += h->root_adm_start[r]; }
-  h->adm_sorted.assign(std::max(1, s->n_adm), 0);
-  {
-    std::vector<int32_t> cur(h->root_adm_start.begin(), h->root_adm_start.end() - 1);
-    for (int a = 0; a < s->n_adm; a++) h->adm_sorted[cur[h->root_slot[s->adm_cq[a]]]++] = a;
-    auto qr = [&](int a) { return s->adm_qr_ts[a] == INT64_MIN ? s->now_ns : s->adm_qr_ts[a]; };
-    for (int r = 0; r < nroots; r++)
-      std::sort(h->adm_sorted.begin() + h->root_adm_start[r], h->adm_sorted.begin() + h->root_adm_start[r + 1], [&](int a, int b) {
-        if (s->adm_evicted[a] != s->adm_evicted[b]) return s->adm_evicted[a] > s->adm_evicted[b];
-        if (s->adm_priority[a] != s->adm_priority[b]) return s->adm_priority[a] < s->adm_priority[b];
-        int64_t ta = qr(a), tb = qr(b);
-        if (ta != tb) return ta > tb;
-        return s->adm_uid[a] < s->adm_uid[b];
-      });
-  }
   if (h->max_root_adm >= (1 << 28)) return fail(h, KB_ERR_INVALID, "more than 2^28 admitted workloads under one root");
-  {  // per-CQ lists in the same order (evicted workloads first), rank of every workload inside its root
-    h->adm_rank.assign(std::max(1, s->n_adm), 0);
-    std::vector<int32_t> cur(h->cq_adm_start.begin(), h->cq_adm_start.end() - 1);
-    for (int r = 0; r < nroots; r++)
-      for (int i = h->root_adm_start[r]; i < h->root_adm_start[r + 1]; i++) {
-        int a = h->adm_sorted[i];
-        h->adm_rank[a] = i - h->root_adm_start[r];
-        h->cq_adm[cur[s->adm_cq[a]]++] = a;
+  {  // longest (root, flavor-resource) bucket: sizes the per-warp candidate-code scratch of the single-cell searches
+    int FRn = s->n_flavor * s->n_resource;
+    std::vector<int32_t> cnt((size_t)nroots * FRn + 1, 0);
+    for (int a = 0; a < s->n_adm; a++) {
+      if (s->adm_use_start[a + 1] < s->adm_use_start[a]) return fail(h, KB_ERR_INVALID, "adm_use_start not monotone");
+      size_t b = (size_t)h->root_slot[s->adm_cq[a]] * FRn;
+      for (int k = s->adm_use_start[a]; k < s->adm_use_start[a + 1]; k++) {
+        int fr = s->adm_use_fr[k];
+        if (fr < 0 || fr >= FRn) return fail(h, KB_ERR_INVALID, "adm_use_fr out of range");
+        cnt[b + fr]++;
       }
+    }
+    h->max_frl_len = 1;
+    for (int32_t c : cnt) h->max_frl_len = std::max(h->max_frl_len, c);
+    h->max_head_podsets = 1;
+    for (int i = 0; i < s->n_heads; i++) {
+      int w = s->heads[i];
+      if (w >= 0 && w < s->n_wl) h->max_head_podsets = std::max(h->max_head_podsets, s->wl_ps_start[w + 1] - s->wl_ps_start[w]);
+    }
   }
   // light bounds checks on the hot tables
   for (int i = 0; i < s->n_heads; i++) if (s->heads[i] < 0 || s->heads[i] >= s->n_wl) return fail(h, KB_ERR_INVALID, "heads out of range");
@@ -364,6 +395,7 @@ static int32_t upload_impl(kb_handle *h, const kb_snapshot *s, bool sync) {
     sneed(Q + 1, 4); sneed(s->n_rg, 4); sneed(s->n_rg + 1, 4); sneed(n_rg_fl, 4);
     sneed(N, 4); sneed(N, 4); sneed(N, 4); sneed(D.nTrees + 1, 4); sneed(h->tree_nodes.size(), 4); sneed(h->tree_level.size(), 4);
     sneed(h->lone.size(), 4); sneed(N, 4); sneed(h->tree_flat.size(), 1); sneed(N + 1, 4); sneed(h->child_list.size(), 4); sneed(h->root_cq_start.size(), 4);
+    sneed(h->sn_node.size(), 4); sneed(h->slot_base.size(), 4); sneed(h->nd_tin.size(), 4); sneed(h->nd_tout.size(), 4);
     if (!h->sarena.reserve(stot + 4096)) return fail(h, KB_ERR_CUDA, "cudaMalloc failed");
     h->sarena.reset();
 #define SUP(field, src, n) CUDA_TRY(h, up(h, h->sarena, D.field, src, (size_t)(n), &bytes))
@@ -382,6 +414,8 @@ static int32_t upload_impl(kb_handle *h, const kb_snapshot *s, bool sync) {
     SUP(tree_flat, h->tree_flat.data(), h->tree_flat.size());
     SUP(child_start, h->child_start.data(), N + 1); SUP(child_list, h->child_list.data(), h->child_list.size());
     SUP(root_cq_start, h->root_cq_start.data(), h->root_cq_start.size());
+    SUP(sn_node, h->sn_node.data(), h->sn_node.size()); SUP(slot_base, h->slot_base.data(), h->slot_base.size());
+    SUP(nd_tin, h->nd_tin.data(), h->nd_tin.size()); SUP(nd_tout, h->nd_tout.data(), h->nd_tout.size());
 #undef SUP
     memcpy(h->s_dims, dims, sizeof(dims));
     h->static_gen = s->static_generation;
@@ -399,38 +433,84 @@ static int32_t upload_impl(kb_handle *h, const kb_snapshot *s, bool sync) {
   need(P * R, 8); need(P, 4); need(P, 4); need(P, 4); need(P, 8); need(P * R, 1);
   need(A, 4); need(A, 4); need(A, 8); need(A, 8); need(A, 8); need(A, 1); need(A + 1, 4); need(s->n_adm_use, 4); need(s->n_adm_use, 8);
   need(H, 4);
-  need(Q + 1, 4); need(h->cq_adm.size(), 4); need(h->adm_rank.size(), 4); need(Q, 4); need(nroots, 4);
+  need(Q + 1, 4); need(A, 4); need(A, 4); need(Q, 4); need(nroots, 4);
+  need(nroots + 2, 4); need(Q + 2, 4); need(A, 8); need(A, 8); need(A, 4); need(A, 4);
+  size_t rk_temp_bytes = 0;
+  if (A) {
+    size_t b1 = 0, b2 = 0;
+    cub::DoubleBuffer<u64> dk(nullptr, nullptr); cub::DoubleBuffer<int32_t> dv(nullptr, nullptr);
+    cub::DeviceRadixSort::SortPairs(nullptr, b1, dk, dv, (int)A, 0, 64, h->stream);
+    cub::DeviceRadixSort::SortPairs(nullptr, b2, (const u64 *)nullptr, (u64 *)nullptr, (const int32_t *)nullptr, (int32_t *)nullptr, (int)A, 0, 32, h->stream);
+    rk_temp_bytes = std::max(b1, b2) + 256;
+  }
+  need(rk_temp_bytes, 1);
   need(NF, 8); need(NF, 8); need(NF, 8); need(NF, 8);
   need(nroots, 4); need(nroots + 1, 4); need(nroots, 4); need(H, 4); need(H, 4); need(H, 4); need(H * 4, 8); need(H * 4, 8); need((size_t)Q * R, 8); need((size_t)N * R, 8);
   need(H, 1); need(H, 1); need(H, 4); need(H, 4); need(P * R, 1); need(P * R, 1); need(P * R, 1); need(P, 4);
   need(1, 4); need(N, 8); need(N, 4); need(N, 1);
-  // preemption: search kernel configuration + scratch
-  {
+  // fair-sharing preemption: search kernel configuration (single-warp CTAs on a private copy of the whole tree)
+  bool fair = (s->flags & KB_F_FAIR_SHARING) != 0;
+  h->search_grid = 1; h->search_smem = true; h->search_smem_bytes = 0;
+  if (fair && A) {
     size_t tb = (size_t)h->max_tree_nodes * FR * 32 + (size_t)h->max_tree_nodes * 4 + 64;
     h->search_smem = tb <= 190 * 1024;
     h->search_smem_bytes = h->search_smem ? tb : 0;
     // resident single-warp CTAs per SM as the occupancy calculator sees them (registers / shared memory)
     int per_sm = 1;
     if (h->search_smem) {
-      cudaFuncSetAttribute(k_nominate_search<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_nominate_search<true>, 32, h->search_smem_bytes);
+      cudaFuncSetAttribute(k_nominate_search_fair<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_nominate_search_fair<true>, 32, h->search_smem_bytes);
     } else {
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_nominate_search<false>, 32, 0);
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_nominate_search_fair<false>, 32, 0);
     }
     per_sm = std::max(1, std::min(per_sm, 16));
     h->search_grid = std::max(1, std::min(h->sm_count * per_sm, std::max(1, s->n_heads)));
-    if (A == 0) h->search_grid = 1;
   }
-  size_t G = (size_t)h->search_grid, acap = (size_t)h->max_root_adm, ncap = (size_t)h->max_tree_nodes;
+  // warp-cooperative classical search: shared memory per warp = context + private column(s) + candidate codes
+  size_t ws_warps = 1, ws_col_stride = 0, memo_items = 0, ws_list_total = 32;
+  if (A && !fair) {
+    const size_t kSmemBudget = 200 * 1024;
+    size_t ncap_s = (size_t)h->max_tree_nodes;
+    // k_search_cells: one column, codes of the longest bucket
+    size_t ctxA = (sizeof(WCtx<1>) + 15) & ~(size_t)15;
+    size_t colA = ncap_s * 8 <= 48 * 1024 ? ncap_s : 0;
+    size_t codesA = (size_t)h->max_frl_len <= 8192 ? (((size_t)h->max_frl_len + 31) & ~(size_t)31) : 0;
+    size_t perA = ctxA + ((colA * 8 + 15) & ~(size_t)15) + ((codesA + 15) & ~(size_t)15);
+    int wpbA = (int)std::max<size_t>(1, std::min<size_t>(16, kSmemBudget / perA));
+    int bpsA = (int)std::max<size_t>(1, std::min<size_t>(32 / wpbA, (220 * 1024) / (perA * wpbA + 1024)));
+    h->sa_wpb = wpbA; h->sa_col_elems = (int)colA; h->sa_codes = (int)codesA; h->sa_smem = perA * wpbA;
+    h->sa_grid = std::max(1, std::min(h->sm_count * bpsA, (int)((H * (size_t)FR + 31) / 32)));
+    // k_nominate_walk: up to Kcap columns (cells of one workload's assignment)
+    size_t kcap = std::min<size_t>(std::min<size_t>((size_t)FR, KB_MAX_CELLS), (size_t)h->max_head_podsets * R);
+    size_t ctxB = (sizeof(WCtx<KB_MAX_CELLS>) + 15) & ~(size_t)15;
+    size_t colB = std::min<size_t>(kcap * ncap_s, 5120);
+    if (colB < ncap_s) colB = 0;  // not even one column fits: global columns
+    size_t perB = ctxB + ((colB * 8 + 15) & ~(size_t)15);
+    int wpbB = (int)std::max<size_t>(1, std::min<size_t>(8, kSmemBudget / perB));
+    int bpsB = (int)std::max<size_t>(1, std::min<size_t>(16 / wpbB, (220 * 1024) / (perB * wpbB + 1024)));
+    h->sb_wpb = wpbB; h->sb_col_elems = (int)colB; h->sb_smem = perB * wpbB;
+    h->sb_grid = std::max(1, std::min(h->sm_count * bpsB, (int)((H + wpbB - 1) / wpbB)));
+    ws_warps = std::max((size_t)h->sa_grid * wpbA, (size_t)h->sb_grid * wpbB);
+    // per-warp candidate-code / target scratch: a single-cell search sees one bucket, GetTargets at most the root's list
+    h->sa_list_cap = (int)(((size_t)h->max_frl_len + 31) & ~(size_t)31);
+    h->sb_list_cap = (int)(((size_t)h->max_root_adm + 31) & ~(size_t)31);
+    ws_list_total = std::max((size_t)h->sa_grid * wpbA * h->sa_list_cap, (size_t)h->sb_grid * wpbB * h->sb_list_cap);
+    if (colA == 0) ws_col_stride = ncap_s;
+    if (kcap * ncap_s > colB) ws_col_stride = std::max(ws_col_stride, std::min<size_t>((size_t)FR, KB_MAX_CELLS) * ncap_s);
+    memo_items = std::min<size_t>(H, (64u << 20) / ((size_t)FR * sizeof(SimMemo)));
+  }
+  size_t G = (fair && A) ? (size_t)h->search_grid : 1, acap = (fair && A) ? (size_t)h->max_root_adm : 1, ncap = (size_t)h->max_tree_nodes;
   size_t pool_cap = A * 4 + 1024;
   need(A, 4); need(nroots + 1, 4); need(H, 4); need(2, 4); need(H, 4); need(H, 4); need(pool_cap, 4); need(pool_cap, 1); need(1, 4);
   need(A, 1); need(A, 4); need(nroots, 4); need(A ? NF : 1, 8);
   need(G * acap, 4); need(G * acap, 4); need(G * acap, 4); need(G * acap, 4); need(G * ncap, 4); need(G * acap, 1); need(G * acap, 1); need(G * ncap, 1); need(G * ncap, 1);
-  if (!h->search_smem) need(G * ncap * FR, 8);
-  size_t GL = A ? G * 32 : 1, lcap = std::min<size_t>(acap, 8192);
-  need(GL * lcap, 4); need(GL * lcap, 4); need(GL * lcap, 4); need(GL * ncap, 4); need(GL * lcap, 1); need(GL * lcap, 1); need(GL * ncap, 1); need(GL * ncap, 1);
-  need(GL * ncap, 8); need(GL * sizeof(PreCtx), 1);
-  bool fair = (s->flags & KB_F_FAIR_SHARING) != 0;
+  if (fair && A && !h->search_smem) need(G * ncap * FR, 8);
+  // classical search tables + per-warp scratch
+  const size_t nbuckets = (size_t)nroots * FR;
+  const size_t sNF = A ? NF : 1, sAU = A ? (size_t)s->n_adm_use : 1;
+  need(A, 4); need(sNF, 8); need(sNF, sizeof(ColStat)); need(sNF, 4); need(A ? nbuckets + 1 : 1, 4); need(A ? nbuckets + 2 : 1, 4); need(sAU, sizeof(FrRec));
+  need(memo_items * FR, sizeof(SimMemo)); need(1, 4);
+  need(ws_warps * ws_col_stride, 8); need(ws_list_total, 1); need(ws_list_total, 4); need(ws_list_total, 1);
   if (fair) { need(H * FR, 8); need(H * (48 + 16 * KB_MAX_DEPTH), 1); need(N, 4); need(N, 4); }
   const size_t span_cap = tot;  // the input tables are part of tot: a span of up to that size is covered by the slack below
   if (!h->arena.reserve(tot + tot / 2 + (1u << 20))) return fail(h, KB_ERR_CUDA, "cudaMalloc failed");
@@ -452,9 +532,6 @@ static int32_t upload_impl(kb_handle *h, const kb_snapshot *s, bool sync) {
   UP(adm_use_start, s->adm_use_start, A + 1); UP(adm_use_fr, s->adm_use_fr, s->n_adm_use); UP(adm_use_qty, (const i64 *)s->adm_use_qty, s->n_adm_use);
   UP(heads, s->heads, H);
   size_t caller_tabs = tabs.size();
-  UP(root_adm_start, h->root_adm_start.data(), nroots + 1);
-  UP(cq_adm_start, h->cq_adm_start.data(), Q + 1); UP(cq_adm, h->cq_adm.data(), h->cq_adm.size());
-  UP(adm_rank, h->adm_rank.data(), h->adm_rank.size());
 #undef UP
   {
     uintptr_t lo = UINTPTR_MAX, hi = 0; size_t sum = 0;
@@ -479,6 +556,17 @@ static int32_t upload_impl(kb_handle *h, const kb_snapshot *s, bool sync) {
     }
   }
   D.over_list = h->arena.take<int32_t>(Q); D.over_count = h->arena.take<int32_t>(nroots);
+  D.root_adm_start = h->arena.take<int32_t>(nroots + 1); D.cq_adm_start = h->arena.take<int32_t>(Q + 1);
+  D.cq_adm = h->arena.take<int32_t>(A); D.adm_rank = h->arena.take<int32_t>(A);
+  D.root_adm_count = h->arena.take<int32_t>(nroots + 2); D.cq_adm_count = h->arena.take<int32_t>(Q + 2);
+  h->rk_keys[0] = h->arena.take<u64>(A); h->rk_keys[1] = h->arena.take<u64>(A);
+  h->rk_vals[0] = h->arena.take<int32_t>(A); h->rk_vals[1] = h->arena.take<int32_t>(A);
+  h->rk_temp = h->arena.take<char>(rk_temp_bytes); h->rk_temp_bytes = rk_temp_bytes;
+  D.adm_sorted = h->rk_vals[0];
+  if (!A) {  // candidates_possible() reads the (empty) group tables
+    CUDA_TRY(h, cudaMemsetAsync(D.root_adm_start, 0, sizeof(int32_t) * (size_t)(nroots + 1), h->stream));
+    CUDA_TRY(h, cudaMemsetAsync(D.cq_adm_start, 0, sizeof(int32_t) * (size_t)(Q + 1), h->stream));
+  }
   D.subtree = h->arena.take<i64>(NF); D.usage = h->arena.take<i64>(NF);
   D.avail = h->arena.take<i64>(NF); D.potential = h->arena.take<i64>(NF);
   D.root_count = h->arena.take<int32_t>(nroots); D.root_offset = h->arena.take<int32_t>(nroots + 1);
@@ -500,14 +588,16 @@ static int32_t upload_impl(kb_handle *h, const kb_snapshot *s, bool sync) {
   D.sc_aux1 = h->arena.take<int32_t>(G * acap); D.sc_aux2 = h->arena.take<int32_t>(G * acap);
   D.sc_variant = h->arena.take<uint8_t>(G * acap); D.sc_tgt_reason = h->arena.take<uint8_t>(G * acap);
   D.sc_cq_class = h->arena.take<int8_t>(G * ncap); D.sc_on_path = h->arena.take<int8_t>(G * ncap);
-  D.sc_usage = h->search_smem ? nullptr : h->arena.take<i64>(G * ncap * FR);
+  D.sc_usage = (fair && A && !h->search_smem) ? h->arena.take<i64>(G * ncap * FR) : nullptr;
   D.sc_adm_cap = (int)acap; D.sc_node_cap = (int)ncap;
-  D.sl_cand = h->arena.take<int32_t>(GL * lcap); D.sl_tgt = h->arena.take<int32_t>(GL * lcap); D.sl_aux1 = h->arena.take<int32_t>(GL * lcap);
-  D.sl_cq_lca = h->arena.take<int32_t>(GL * ncap);
-  D.sl_variant = h->arena.take<uint8_t>(GL * lcap); D.sl_tgt_reason = h->arena.take<uint8_t>(GL * lcap);
-  D.sl_cq_class = h->arena.take<int8_t>(GL * ncap); D.sl_on_path = h->arena.take<int8_t>(GL * ncap);
-  D.sl_col = h->arena.take<i64>(GL * ncap); D.sl_ctx = h->arena.take<unsigned char>(GL * sizeof(PreCtx));
-  D.sl_adm_cap = (int)lcap;
+  D.colU = h->arena.take<i64>(sNF); D.colS = h->arena.take<ColStat>(sNF); D.ovm = h->arena.take<uint32_t>(sNF);
+  D.frl_count = h->arena.take<int32_t>(A ? nbuckets + 1 : 1); D.frl_start = h->arena.take<int32_t>(A ? nbuckets + 2 : 1);
+  D.frl = h->arena.take<FrRec>(sAU);
+  D.memo = h->arena.take<SimMemo>(memo_items * FR); D.memo_items = (int)memo_items;
+  D.cell_cursor = h->arena.take<int32_t>(1);
+  D.ws_col = h->arena.take<i64>(ws_warps * ws_col_stride); D.ws_col_stride = ws_col_stride;
+  D.ws_codes = h->arena.take<uint8_t>(ws_list_total); D.ws_tgt = h->arena.take<int32_t>(ws_list_total);
+  D.ws_tgt_reason = h->arena.take<uint8_t>(ws_list_total);
   if (fair) {
     D.q_scratch = h->arena.take<i64>(H * FR); D.fs_state = h->arena.take<unsigned char>(H * (48 + 16 * KB_MAX_DEPTH));
     D.fs_cq_entry = h->arena.take<int32_t>(N); D.fs_winner = h->arena.take<int32_t>(N);
@@ -620,6 +710,33 @@ static int32_t cycle_enqueue(kb_handle *h) {
   if (D.A) CUDA_TRY(h, cudaMemsetAsync(D.preempted, 0, (size_t)D.A, h->stream));
   h->kev_n = 0;
   int32_t rc_admit = KB_OK;
+  if (D.A) {  // rank the admitted workloads (kb_rank.cuh): stable LSD passes UID -> reservation time -> (root | evicted | priority)
+    kmark(h, KB_K_RANKADM);
+    const int A = D.A, tb = 256, nb = (A + tb - 1) / tb;
+    CUDA_TRY(h, cudaMemsetAsync(D.root_adm_count, 0, sizeof(int32_t) * (size_t)(D.nRoots + 2), h->stream));
+    CUDA_TRY(h, cudaMemsetAsync(D.cq_adm_count, 0, sizeof(int32_t) * (size_t)(D.Q + 2), h->stream));
+    cub::DoubleBuffer<u64> dk(h->rk_keys[0], h->rk_keys[1]);
+    cub::DoubleBuffer<int32_t> dv(h->rk_vals[0], h->rk_vals[1]);
+    size_t bytes = h->rk_temp_bytes;
+    k_rank_keys_uid<<<nb, tb, 0, h->stream>>>(D, dk.Current(), dv.Current()); launches++;
+    CUDA_TRY(h, cub::DeviceRadixSort::SortPairs(h->rk_temp, bytes, dk, dv, A, 0, 64, h->stream));
+    k_rank_keys_qr<<<nb, tb, 0, h->stream>>>(D, dv.Current(), dk.Current()); launches++;
+    CUDA_TRY(h, cub::DeviceRadixSort::SortPairs(h->rk_temp, bytes, dk, dv, A, 0, 64, h->stream));
+    k_rank_keys_root<<<nb, tb, 0, h->stream>>>(D, dv.Current(), dk.Current()); launches++;
+    int root_bits = 1; while ((1ll << root_bits) < (long long)D.nRoots) root_bits++;
+    CUDA_TRY(h, cub::DeviceRadixSort::SortPairs(h->rk_temp, bytes, dk, dv, A, 0, 33 + root_bits, h->stream));
+    D.adm_sorted = dv.Current();
+    int32_t *other_vals = dv.Alternate();
+    k_scan_i32<<<1, 1024, 0, h->stream>>>(D.root_adm_count, D.root_adm_start, D.nRoots); launches++;
+    k_rank_positions<<<nb, tb, 0, h->stream>>>(D); launches++;
+    // per-ClusterQueue lists in the same order: one more stable pass keyed by the ClusterQueue
+    k_rank_keys_cq<<<nb, tb, 0, h->stream>>>(D, D.adm_sorted, dk.Current()); launches++;
+    int cq_bits = 1; while ((1ll << cq_bits) < (long long)D.Q) cq_bits++;
+    CUDA_TRY(h, cub::DeviceRadixSort::SortPairs(h->rk_temp, bytes, (const u64 *)dk.Current(), dk.Alternate(), (const int32_t *)D.adm_sorted, D.cq_adm, A, 0, cq_bits, h->stream));
+    (void)other_vals;
+    k_scan_i32<<<1, 1024, 0, h->stream>>>(D.cq_adm_count, D.cq_adm_start, D.Q); launches++;
+    launches += 8;  // radix-sort passes (cub): histogram + onesweep kernels, counted coarsely
+  }
   launch_tree(h, &launches);
   if (D.H) {
     kmark(h, KB_K_NOMINATE);
@@ -628,21 +745,40 @@ static int32_t cycle_enqueue(kb_handle *h) {
     else k_nominate<<<(D.H + 127) / 128, 128, 0, h->stream>>>(D);
     launches++;
     if (D.A) {  // target search for the entries k_nominate deferred
-      kmark(h, KB_K_PREEMPT);
-      CUDA_TRY(h, cudaMemsetAsync(D.over_count, 0, sizeof(int32_t) * (size_t)std::max(1, D.nRoots), h->stream));
-      k_over<<<(D.Q + 255) / 256, 256, 0, h->stream>>>(D); launches++;
-      if (h->search_smem) {
-        CUDA_TRY(h, cudaFuncSetAttribute(k_nominate_search<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        k_nominate_search<true><<<h->search_grid, 32, h->search_smem_bytes, h->stream>>>(D);
+      if (D.flags & KB_F_FAIR_SHARING) {
+        kmark(h, KB_K_PREEMPT);
+        CUDA_TRY(h, cudaMemsetAsync(D.over_count, 0, sizeof(int32_t) * (size_t)std::max(1, D.nRoots), h->stream));
+        k_over<<<(D.Q + 255) / 256, 256, 0, h->stream>>>(D); launches++;
+        if (h->search_smem) {
+          CUDA_TRY(h, cudaFuncSetAttribute(k_nominate_search_fair<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+          k_nominate_search_fair<true><<<h->search_grid, 32, h->search_smem_bytes, h->stream>>>(D);
+        } else {
+          k_nominate_search_fair<false><<<h->search_grid, 32, 0, h->stream>>>(D);
+        }
+        launches++;
       } else {
-        k_nominate_search<false><<<h->search_grid, 32, 0, h->stream>>>(D);
+        // per-cycle search tables: transposed columns + above-nominal masks, candidate buckets per (root, flavor-resource)
+        kmark(h, KB_K_SEARCH_TABLES);
+        size_t nf = (size_t)D.N * D.FR;
+        int nb = D.nRoots * D.FR;
+        k_columns<<<(unsigned)((nf + 255) / 256), 256, 0, h->stream>>>(D); launches++;
+        CUDA_TRY(h, cudaMemsetAsync(D.frl_count, 0, sizeof(int32_t) * (size_t)(nb + 1), h->stream));
+        CUDA_TRY(h, cudaMemsetAsync(D.cell_cursor, 0, 4, h->stream));
+        if (D.AU) { k_frl_count<<<(D.AU + 255) / 256, 256, 0, h->stream>>>(D); launches++; }
+        k_scan_i32<<<1, 1024, 0, h->stream>>>(D.frl_count, D.frl_start, nb); launches++;
+        if (D.AU) { k_frl_fill<<<(unsigned)(((size_t)nb * 32 + 127) / 128), 128, 0, h->stream>>>(D); launches++; }
+        CUDA_TRY(h, cudaFuncSetAttribute(k_search_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+        CUDA_TRY(h, cudaFuncSetAttribute(k_nominate_walk, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+        kmark(h, KB_K_SEARCH_CELLS);
+        k_search_cells<<<h->sa_grid, h->sa_wpb * 32, h->sa_smem, h->stream>>>(D, h->sa_col_elems, h->sa_codes, h->sa_list_cap); launches++;
+        kmark(h, KB_K_WALK);
+        k_nominate_walk<<<h->sb_grid, h->sb_wpb * 32, h->sb_smem, h->stream>>>(D, h->sb_col_elems, h->sb_list_cap); launches++;
       }
-      launches++;
     }
-    if (D.flags & KB_F_FAIR_SHARING) { k_fair_prep<<<(D.N * D.R + 255) / 256, 256, 0, h->stream>>>(D); launches++; }
+    if (D.flags & KB_F_FAIR_SHARING) { kmark(h, KB_K_FAIR_PREP); k_fair_prep<<<(D.N * D.R + 255) / 256, 256, 0, h->stream>>>(D); launches++; }
     kmark(h, KB_K_SCAN); k_scan_roots<<<1, 1024, 0, h->stream>>>(D); launches++;
     kmark(h, KB_K_SCATTER); k_scatter<<<(D.H + 255) / 256, 256, 0, h->stream>>>(D); launches++;
-    kmark(h, KB_K_FAIR); k_rank<<<(D.H + 255) / 256, 256, 0, h->stream>>>(D); launches++;
+    kmark(h, KB_K_RANK); k_rank<<<(D.H + 255) / 256, 256, 0, h->stream>>>(D); launches++;
     kmark(h, KB_K_ADMIT);
     rc_admit = launch_admit(h, &launches);
   }

@@ -20,6 +20,23 @@ typedef unsigned long long u64;
 // Status word bits written by kernels (checked by the host after a cycle).
 enum { KBS_UNSUPPORTED_PREEMPTION = 1u << 0, KBS_TARGET_OVERFLOW = 1u << 1, KBS_PATH_TOO_DEEP = 1u << 2, KBS_INTERNAL_LOOP = 1u << 3 };
 
+// Static + per-cycle state of one (node, flavor-resource) cell, transposed per root (kb_search.cuh): everything the
+// column arithmetic of a target search reads besides the usage itself.  32 B, loaded as two 16 B words.
+struct __align__(16) ColStat {
+  i64 sub, lq, bl;     // SubtreeQuota, localQuota, BorrowingLimit
+  int32_t parent;      // local handle of the parent inside the root's tree, -1 = root
+  int16_t depth, height;
+};
+// One candidate record of a (root, flavor-resource) bucket, in CandidatesOrdering rank order.
+struct __align__(16) FrRec {
+  int32_t adm, hcq, prio;  // admitted workload, local handle of its ClusterQueue, priority
+  uint32_t info;           // bit 0 evicted | depth of the ClusterQueue << 1 | above-nominal mask of its ancestors << 8
+  i64 qty;                 // quantity in this flavor-resource
+  int32_t tin, cq;         // Euler-tour entry time of the ClusterQueue inside its tree; global ClusterQueue id
+};
+// Memoised result of one SimulatePreemption call: (cell, quantity) -> (preemption mode, borrow height)
+struct SimMemo { i64 val; int pm, borrow; };
+
 struct DevSnap {
   // dimensions
   int Q, C, N, F, R, FR, W, P, A, AU, H, NRG, pods_res;
@@ -61,8 +78,8 @@ struct DevSnap {
   const int32_t *lone_cqs;    // CQs without a cohort
   const int32_t *child_start; // [N+1] children CSR: child cohorts ascending, then child CQs ascending
   const int32_t *child_list;
-  const int32_t *cq_adm_start;// [Q+1] admitted workloads grouped by CQ
-  const int32_t *cq_adm;      // [A]
+  int32_t *cq_adm_start;      // [Q+1] admitted workloads grouped by CQ (device-built, kb_rank.cuh)
+  int32_t *cq_adm;            // [A] in adm_rank order inside every ClusterQueue
   int nTrees, nLone, nRoots;
   int lone_fast;  // cohort-less CQs take the warp-per-root admit kernel (no preemption targets possible, FR <= 64)
   // ---- derived per cycle ----
@@ -89,9 +106,10 @@ struct DevSnap {
   int32_t *ps_count_out;
   uint32_t *status;  // [1] KBS_* bits
   // ---- preemption ----
-  const int32_t *root_adm_start; // [nRoots+1] admitted workloads per root (prefix sums)
-  const int32_t *adm_rank;       // [A] position of the workload among its root's admitted workloads ordered by
-                                 //     (evicted desc, priority asc, more recently reserved first, uid) — host sort per cycle
+  int32_t *root_adm_start;       // [nRoots+1] admitted workloads per root (prefix sums)
+  int32_t *adm_rank;             // [A] position of the workload among its root's admitted workloads ordered by
+                                 //     (evicted desc, priority asc, more recently reserved first, uid) — kb_rank.cuh
+  int32_t *root_adm_count, *cq_adm_count;  // [nRoots+1] / [Q+1] histograms of the ranking pass
   const int32_t *root_cq_start;  // [nRoots+1] ClusterQueues per root (segments of over_list)
   int32_t *over_list;            // [Q] per root: ClusterQueues above nominal in some flavor-resource at cycle start (k_over)
   int32_t *over_count;           // [nRoots]
@@ -109,6 +127,18 @@ struct DevSnap {
   i64 *sl_col;            // [G*32][node cap] one usage column per lane
   unsigned char *sl_ctx;  // [G*32] PreCtx
   int sl_adm_cap;
+  // ---- warp-cooperative classical search (kb_search.cuh) ----
+  const int32_t *sn_node;     // [N] slot-node numbering -> global node id (cohort-less ClusterQueues first, then the trees)
+  const int32_t *slot_base;   // [nRoots+1] first slot-node of every root
+  const int32_t *nd_tin, *nd_tout;  // [N] Euler-tour interval of every slot-node inside its tree
+  int32_t *adm_sorted;        // [A] admitted workloads of every root in adm_rank order (segments root_adm_start)
+  i64 *colU; ColStat *colS; uint32_t *ovm;  // [N*FR] transposed per root: index = slot_base*FR + fr*nn + h
+  int32_t *frl_count, *frl_start;  // [nRoots*FR (+1)] buckets of the fr-lists
+  FrRec *frl;                 // [AU]
+  SimMemo *memo; int memo_items;  // [memo_items][FR] results of the speculative single-cell searches (item = position in ps_list)
+  int32_t *cell_cursor;       // work counter of k_search_cells
+  i64 *ws_col; size_t ws_col_stride;  // per-warp global column storage when shared memory is too small (stride in i64)
+  uint8_t *ws_codes; int32_t *ws_tgt; uint8_t *ws_tgt_reason;  // per-warp [list_cap of the kernel]
   // ---- fair-sharing scratch ----
   i64 *q_scratch;        // [H][FR] dense Assignment.Usage.Quota per entry (absent = -1)
   unsigned char *fs_state; // [H] x (48 + 16*KB_MAX_DEPTH) B: per-entry tournament state when it does not fit shared memory

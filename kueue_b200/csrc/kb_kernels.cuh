@@ -18,6 +18,8 @@
 
 #include "kb_device.cuh"
 #include "kb_preempt.cuh"
+#include "kb_search.cuh"
+#include "kb_rank.cuh"
 
 #define KB_RANK_CAP 2048  // roots up to this many entries are ordered by the all-pairs k_rank kernel
 
@@ -652,47 +654,200 @@ __global__ void k_over(DevSnap D) {
 }
 
 // ---------------------------------------------------------------------------
-// K6: nominate with target search.  Persistent CTAs pull the deferred entries; all threads
-// of the CTA run the (scalar) flavor-assignment control flow uniformly and cooperate inside
-// the search (kb_preempt.cuh).
+// K6: nominate with target search for the entries k_nominate deferred.
+//
+// Classical / hierarchical preemption: k_search_cells runs every SimulatePreemption call the flavor walks of
+// the deferred entries can make for their first podset (one warp per (entry, flavor-resource) cell, results
+// memoised by quantity), then k_nominate_walk replays getInitialAssignments per entry (one warp each, all lanes
+// executing the scalar control flow redundantly and cooperating inside the searches, kb_search.cuh).
+// Fair sharing: k_nominate_search_fair (the DominantResourceShare tournament reads every column of the tree).
 // ---------------------------------------------------------------------------
-// Oracle policy of k_nominate_search: flavor assignment and target searches of one deferred
-// entry run on lane 0 of a single-warp CTA (single writer of the output rows).
-// SimulatePreemption preemption_oracle.go:41-71 on the private tree T (full, or the single column `fr`).
-template <bool kSmem>
-__device__ inline int simulate_on(const DevSnap &D, const PTab<kSmem> &T, PreCtx *c, const PreScratch &S, int wl, int cq, int fr, i64 val,
-                                  int *borrow_after) {
-  int hcq = T.handle(cq);
-  *borrow_after = T.find_height(hcq, fr, val);  // no candidates: height on the untouched snapshot (:53-56)
-  c->overflow = 0;
-  if (!candidates_possible(D, cq)) return PM_NOCAND;
-  c->cq = cq; c->prio = D.wl_priority[wl]; c->ts = D.wl_ts[wl];
-  c->n_use = 1; c->use_fr[0] = fr; c->use_q[0] = val;
-  c->n_need = 1; c->need_fr[0] = fr;
-  target_search<kSmem>(D, T, c, S);
-  int nt = c->n_targets;
-  if (nt == 0) return PM_NOCAND;
-  for (int k = 0; k < nt; k++) T.remove_adm(S.tgt[k]);
-  *borrow_after = T.find_height(hcq, fr, val);
-  for (int k = 0; k < nt; k++) T.add_adm(S.tgt[k]);
-  for (int k = 0; k < nt; k++) if (D.adm_cq[S.tgt[k]] == cq) return PM_PREEMPT;
-  return PM_RECLAIM;
+__device__ __forceinline__ size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
+
+__global__ void __launch_bounds__(512) k_search_cells(DevSnap D, int col_smem_elems, int codes_smem, int list_cap) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  const size_t gw = (size_t)blockIdx.x * wpb + warp;
+  const size_t ctx_b = align16(sizeof(WCtx<1>)), col_b = align16((size_t)col_smem_elems * 8), codes_b = align16((size_t)codes_smem);
+  unsigned char *base = smem_raw + (size_t)warp * (ctx_b + col_b + codes_b);
+  WCtx<1> *w = reinterpret_cast<WCtx<1> *>(base);
+  WScratch S;
+  S.col = col_smem_elems ? reinterpret_cast<i64 *>(base + ctx_b) : D.ws_col + gw * D.ws_col_stride;
+  S.codes = codes_smem ? base + ctx_b + col_b : D.ws_codes + gw * list_cap;
+  S.tgt = D.ws_tgt + gw * list_cap; S.tgt_reason = D.ws_tgt_reason + gw * list_cap;
+  const int FR = D.FR, R = D.R;
+  const int n_items = min(*D.ps_n, D.memo_items);
+  const long long total = (long long)n_items * FR;
+  while (true) {
+    int chunk = 0;
+    if (lane == 0) chunk = atomicAdd(D.cell_cursor, 1);
+    chunk = __shfl_sync(0xffffffffu, chunk, 0);
+    long long idx = (long long)chunk * 32 + lane;
+    if ((long long)chunk * 32 >= total) break;
+    // ---- one (entry, flavor-resource) cell per lane: would the flavor walk of the first podset call the oracle here?
+    bool need = false; int item = 0, fr = 0, wl = 0, cq = 0; i64 req = 0;
+    if (idx < total) {
+      item = (int)(idx / FR); fr = (int)(idx % FR);
+      wl = D.heads[D.ps_list[item]]; cq = D.wl_cq[wl];
+      int row = D.wl_ps_start[wl];
+      if (D.wl_ps_start[wl + 1] > row && candidates_possible(D, cq)) {
+        int f = fr / R, r = fr % R;
+        bool covers_pods = D.pods_res >= 0 && rg_by_resource(D, cq, D.pods_res) >= 0;
+        uint32_t mask = D.ps_req_mask[row] | (covers_pods ? 1u << D.pods_res : 0u);
+        int g = ((mask >> r) & 1) && ((D.ps_flavor_ok[row] >> f) & 1) ? rg_by_resource(D, cq, r) : -1;
+        bool in_rg = false;
+        if (g >= 0) for (int k = D.rg_flavor_start[g]; k < D.rg_flavor_start[g + 1]; k++) in_rg |= D.rg_flavors[k] == f;
+        if (in_rg) {
+          req = ps_request(D, row, r, D.ps_count[row], covers_pods);
+          int b0;
+          need = cell_eval(D, cq, fr, 0, req, &b0) == PM_NEED;
+        }
+      }
+    }
+    if (idx < total && !need) D.memo[idx].val = -1;  // memo row index = item * FR + fr: no oracle call expected here
+    unsigned m = __ballot_sync(0xffffffffu, need);
+    while (m) {
+      int src = __ffs(m) - 1; m &= m - 1;
+      int s_item = __shfl_sync(0xffffffffu, item, src), s_fr = __shfl_sync(0xffffffffu, fr, src);
+      int s_wl = __shfl_sync(0xffffffffu, wl, src), s_cq = __shfl_sync(0xffffffffu, cq, src);
+      i64 s_req = __shfl_sync(0xffffffffu, req, src);
+      int borrow;
+      int pm = ws_simulate<1>(D, w, S, s_wl, s_cq, s_fr, s_req, &borrow);
+      if (lane == 0) { SimMemo mm; mm.val = s_req; mm.pm = pm; mm.borrow = borrow; D.memo[(size_t)s_item * FR + s_fr] = mm; }
+      __syncwarp();
+    }
+  }
 }
 
-// Results of the speculative lane-parallel oracle calls of one entry (k_nominate_search phase A): the sequential
-// flavor walk looks a (cell, quantity) up here before running the search itself.
-struct SimMemo { i64 val; int pm, borrow; };
+// Oracle policy of k_nominate_walk: every lane of the warp executes the flavor walk; searches are warp-cooperative.
+struct NomWarp {
+  WCtx<KB_MAX_CELLS> *w;
+  WScratch S;
+  i64 *col_smem; int col_smem_elems; i64 *col_glob;
+  const SimMemo *memo;  // [FR] speculative results of this entry, or nullptr
+  __device__ __forceinline__ void pick_col(const DevSnap &D, int cq, int K) {
+    int slot = D.root_slot[cq];
+    int nn = D.slot_base[slot + 1] - D.slot_base[slot];
+    S.col = ((size_t)K * nn <= (size_t)col_smem_elems) ? col_smem : col_glob;
+  }
+  __device__ inline int simulate(const DevSnap &D, int wl, int cq, int fr, i64 val, int *borrow_after) {
+    if (memo) { SimMemo m = memo[fr]; if (m.val == val) { *borrow_after = m.borrow; return m.pm; } }
+    if (!candidates_possible(D, cq)) {
+      bool may_reclaim;
+      *borrow_after = find_height(D, D.usage, cq, fr, val, &may_reclaim);
+      return PM_NOCAND;
+    }
+    pick_col(D, cq, 1);
+    return ws_simulate<KB_MAX_CELLS>(D, w, S, wl, cq, fr, val, borrow_after);
+  }
+  // GetTargets preemption.go:127-146 for the assignment currently in the output rows
+  __device__ inline int get_targets(const DevSnap &D, int wl) {
+    const int lane = threadIdx.x & 31;
+    int cq = D.wl_cq[wl];
+    if (!candidates_possible(D, cq)) return 0;
+    const int R = D.R;
+    __syncwarp();
+    if (lane == 0) {
+      w->cq = cq; w->prio = D.wl_priority[wl]; w->ts = D.wl_ts[wl];
+      bool covers_pods = D.pods_res >= 0 && rg_by_resource(D, cq, D.pods_res) >= 0;
+      int K = 0, nn = 0;
+      for (int i = 0; i < 32; i++) w->need_bits[i] = 0;
+      auto slot_of = [&](int fr) { int j = 0; while (j < K && w->tfr[j] != fr) j++; return j; };
+      for (int row = D.wl_ps_start[wl]; row < D.wl_ps_start[wl + 1]; row++)
+        for (int r = 0; r < R; r++) {
+          int f = D.ps_flavor[(size_t)row * R + r];
+          if (f < 0) continue;
+          int fr = f * R + r;
+          if (D.ps_res_mode[(size_t)row * R + r] == KB_MODE_PREEMPT) {  // flavorResourcesNeedPreemption :480-490
+            int j = slot_of(fr);
+            if (j == K && K < KB_MAX_CELLS) { w->tfr[K] = (uint16_t)fr; w->tflag[K] = 0; w->tq[K] = 0; K++; }
+            if (j < K && !(w->tflag[j] & TC_NEED)) { w->tflag[j] |= TC_NEED; w->need_bits[fr >> 5] |= 1u << (fr & 31); nn++; }
+          }
+          i64 q = ps_request(D, row, r, D.ps_count_out[row], covers_pods);  // TotalRequestsFor flavorassigner.go:198-218
+          if (q == 0) continue;
+          int j = slot_of(fr);
+          if (j == K) { if (K == KB_MAX_CELLS) continue; w->tfr[K] = (uint16_t)fr; w->tflag[K] = 0; w->tq[K] = 0; K++; }
+          w->tflag[j] |= TC_USE; w->tq[j] += q;
+        }
+      w->K = K; w->n_need = nn;
+    }
+    __syncwarp();
+    const int K = w->K;
+    if (w->n_need == 0 || K == 0) return 0;
+    pick_col(D, cq, K);
+    if (K <= 32) {
+      i64 myq[1] = {lane < K ? w->tq[lane] : 0};
+      return ws_classical<KB_MAX_CELLS, 1>(D, w, S, myq);
+    }
+    i64 myq[4];
+#pragma unroll
+    for (int s = 0; s < 4; s++) myq[s] = lane + 32 * s < K ? w->tq[lane + 32 * s] : 0;
+    return ws_classical<KB_MAX_CELLS, 4>(D, w, S, myq);
+  }
+};
 
+__global__ void __launch_bounds__(256) k_nominate_walk(DevSnap D, int col_smem_elems, int list_cap) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  const size_t gw = (size_t)blockIdx.x * wpb + warp;
+  const size_t ctx_b = align16(sizeof(WCtx<KB_MAX_CELLS>)), col_b = align16((size_t)col_smem_elems * 8);
+  unsigned char *base = smem_raw + (size_t)warp * (ctx_b + col_b);
+  NomWarp orc;
+  orc.w = reinterpret_cast<WCtx<KB_MAX_CELLS> *>(base);
+  orc.col_smem = reinterpret_cast<i64 *>(base + ctx_b); orc.col_smem_elems = col_smem_elems;
+  orc.col_glob = D.ws_col + gw * D.ws_col_stride;
+  orc.S.col = orc.col_glob;
+  orc.S.codes = D.ws_codes + gw * list_cap;
+  orc.S.tgt = D.ws_tgt + gw * list_cap; orc.S.tgt_reason = D.ws_tgt_reason + gw * list_cap;
+  const int n_items = *D.ps_n;
+  while (true) {
+    int item = 0;
+    if (lane == 0) item = atomicAdd(D.ps_cursor, 1);
+    item = __shfl_sync(0xffffffffu, item, 0);
+    if (item >= n_items) break;
+    int e = D.ps_list[item];
+    int wl = D.heads[e];
+    orc.memo = item < D.memo_items ? D.memo + (size_t)item * D.FR : nullptr;
+    int borrowing, nt;
+    int mode = get_assignments(D, orc, wl, &borrowing, &nt);
+    __syncwarp();
+    int off = 0;
+    if (nt > 0) {
+      if (lane == 0) off = atomicAdd(D.tgt_pool_used, nt);
+      off = __shfl_sync(0xffffffffu, off, 0);
+      if (off + nt <= D.tgt_pool_cap) {
+        for (int k = lane; k < nt; k += 32) { D.tgt_pool_adm[off + k] = orc.S.tgt[k]; D.tgt_pool_reason[off + k] = orc.S.tgt_reason[k]; }
+      } else { if (lane == 0) atomicOr(D.status, KBS_TARGET_OVERFLOW); nt = 0; }
+    }
+    if (lane == 0) { D.mode[e] = (uint8_t)mode; D.borrow[e] = borrowing; D.tgt_cnt[e] = nt; D.tgt_off[e] = off; }
+    __syncwarp();
+  }
+}
+
+// Fair-sharing preemption (kb_preempt.cuh): flavor assignment and target searches of one deferred entry run on
+// lane 0 of a single-warp CTA on a private copy of the root's whole tree (the DominantResourceShare reads every
+// column); the other lanes only stage the tree.
 template <bool kSmem>
 struct NomSearch {
   const PTab<kSmem> *T;
   PreCtx *c;
   PreScratch S;
-  const SimMemo *memo;  // [FR] or nullptr
-  __device__ inline void run_search(const DevSnap &D) { target_search<kSmem>(D, *T, c, S); }
+  // SimulatePreemption preemption_oracle.go:41-71 on the private tree
   __device__ inline int simulate(const DevSnap &D, int wl, int cq, int fr, i64 val, int *borrow_after) {
-    if (memo && memo[fr].val == val) { *borrow_after = memo[fr].borrow; return memo[fr].pm; }
-    return simulate_on<kSmem>(D, *T, c, S, wl, cq, fr, val, borrow_after);
+    int hcq = T->handle(cq);
+    *borrow_after = T->find_height(hcq, fr, val);  // no candidates: height on the untouched snapshot (:53-56)
+    if (!candidates_possible(D, cq)) return PM_NOCAND;
+    c->cq = cq; c->prio = D.wl_priority[wl]; c->ts = D.wl_ts[wl];
+    c->n_use = 1; c->use_fr[0] = fr; c->use_q[0] = val;
+    c->n_need = 1; c->need_fr[0] = fr;
+    fair_search<kSmem>(D, *T, c, S);
+    int nt = c->n_targets;
+    if (nt == 0) return PM_NOCAND;
+    for (int k = 0; k < nt; k++) T->remove_adm(S.tgt[k]);
+    *borrow_after = T->find_height(hcq, fr, val);
+    for (int k = 0; k < nt; k++) T->add_adm(S.tgt[k]);
+    for (int k = 0; k < nt; k++) if (D.adm_cq[S.tgt[k]] == cq) return PM_PREEMPT;
+    return PM_RECLAIM;
   }
   // GetTargets preemption.go:127-146 for the assignment currently in the output rows
   __device__ inline int get_targets(const DevSnap &D, int wl) {
@@ -718,21 +873,18 @@ struct NomSearch {
         c->use_q[j] += q;
       }
     c->n_use = nu; c->n_need = nn;
-    run_search(D);
+    fair_search<kSmem>(D, *T, c, S);
     return c->n_targets;
   }
 };
 
 template <bool kSmem>
-__global__ void __launch_bounds__(32, 16) k_nominate_search(DevSnap D) {  // <= 128 registers: 16 single-warp CTAs per SM
+__global__ void __launch_bounds__(32, 16) k_nominate_search_fair(DevSnap D) {  // <= 128 registers: 16 single-warp CTAs per SM
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ PreCtx ctx;
   __shared__ int s_item;
-  __shared__ SimMemo s_memo[KB_MAX_CELLS];
-  const int FR = D.FR, R = D.R;
-  const int lane = threadIdx.x;
+  const int FR = D.FR;
   PreScratch S;   // scratch of the CTA's sequential searcher (lane 0)
-  PreScratch SL;  // scratch of this lane's speculative single-cell searches
   {
     size_t b = blockIdx.x;
     S.cand = {D.sc_cand + b * D.sc_adm_cap}; S.variant = {D.sc_variant + b * D.sc_adm_cap};
@@ -741,18 +893,7 @@ __global__ void __launch_bounds__(32, 16) k_nominate_search(DevSnap D) {  // <= 
     S.cq_lca = {D.sc_cq_lca + b * D.sc_node_cap};
     S.aux1 = {D.sc_aux1 + b * D.sc_adm_cap}; S.aux2 = {D.sc_aux2 + b * D.sc_adm_cap};
     S.cap = D.sc_adm_cap;
-    // lane scratch: contiguous per lane.  (Interleaving the 32 lanes' arrays, stride 32, was measured slower on
-    // cfg4 — 264 vs 221 ms: the lanes do not walk their lists in lock step, so it only destroys each lane's own
-    // spatial locality.)
-    size_t w = b * 32 + lane;
-    SL.cand = {D.sl_cand + w * D.sl_adm_cap}; SL.variant = {D.sl_variant + w * D.sl_adm_cap};
-    SL.tgt = {D.sl_tgt + w * D.sl_adm_cap}; SL.tgt_reason = {D.sl_tgt_reason + w * D.sl_adm_cap};
-    SL.cq_class = {D.sl_cq_class + w * D.sc_node_cap}; SL.on_path = {D.sl_on_path + w * D.sc_node_cap};
-    SL.cq_lca = {D.sl_cq_lca + w * D.sc_node_cap};
-    SL.aux1 = {D.sl_aux1 + w * D.sl_adm_cap}; SL.aux2 = {nullptr};  // aux2 is only used by the fair search (never speculative)
-    SL.cap = D.sl_adm_cap;
   }
-  PreCtx *lctx = (PreCtx *)D.sl_ctx + (size_t)blockIdx.x * 32 + lane;
   PTab<kSmem> T;
   T.D = &D; T.FR = FR;
   int cur_slot = -1;
@@ -788,37 +929,8 @@ __global__ void __launch_bounds__(32, 16) k_nominate_search(DevSnap D) {  // <= 
       }
       __syncthreads();
     }
-    // ---- phase A: the oracle calls of the entry's first podset are independent single-cell searches
-    //      (one flavor-resource column each) -> one per lane, on a private copy of that column.  Classical
-    //      preemption only: the fair search reads every column for the DominantResourceShare.
-    const bool speculate = !(D.flags & KB_F_FAIR_SHARING) && FR <= KB_MAX_CELLS;  // s_memo holds one slot per cell
-    if (speculate) {
-      for (int c = lane; c < FR; c += 32) s_memo[c].val = -1;
-      const int row = D.wl_ps_start[wl];
-      const bool covers_pods = D.pods_res >= 0 && rg_by_resource(D, cq, D.pods_res) >= 0;
-      for (int c = lane; c < FR; c += 32) {
-        int f = c / R, r = c % R;
-        if (!((D.ps_req_mask[row] >> r) & 1) || !((D.ps_flavor_ok[row] >> f) & 1)) continue;
-        int g = rg_by_resource(D, cq, r);
-        if (g < 0) continue;
-        bool in_rg = false;
-        for (int k = D.rg_flavor_start[g]; k < D.rg_flavor_start[g + 1]; k++) in_rg |= D.rg_flavors[k] == f;
-        if (!in_rg) continue;
-        i64 req = ps_request(D, row, r, D.ps_count[row], covers_pods);
-        int b0;
-        if (cell_eval(D, cq, c, 0, req, &b0) != PM_NEED) continue;
-        PTab<kSmem> TL = T;  // same static tables, private usage column
-        TL.col_fr = c;
-        TL.usage = D.sl_col + ((size_t)blockIdx.x * 32 + lane) * D.sc_node_cap;
-        for (int h = 0; h < T.nn; h++) TL.usage[h] = D.usage[(size_t)T.nodes[h] * FR + c];
-        int borrow;
-        int pm = simulate_on<kSmem>(D, TL, lctx, SL, wl, cq, c, req, &borrow);
-        if (!lctx->overflow) { s_memo[c].pm = pm; s_memo[c].borrow = borrow; s_memo[c].val = req; }
-      }
-    }
-    __syncwarp();
     if (threadIdx.x == 0) {
-      NomSearch<kSmem> orc{&T, &ctx, S, speculate ? s_memo : nullptr};
+      NomSearch<kSmem> orc{&T, &ctx, S};
       int borrowing, nt;
       int mode = get_assignments(D, orc, wl, &borrowing, &nt);
       D.mode[e] = (uint8_t)mode;
@@ -859,7 +971,7 @@ __device__ inline void compute_entry_key(const DevSnap &D, int e, u64 *k) {
   int wl = D.heads[e];
   int cq = D.wl_cq[wl];
   unsigned prio = 0;
-  if (D.flags & KB_F_PRIORITY_SORTING_WITHIN_COHORT) prio = 0x7fffffffu - (unsigned)(D.wl_priority[wl] ^ 0x80000000);  // desc
+  if (D.flags & KB_F_PRIORITY_SORTING_WITHIN_COHORT) prio = ~((unsigned)D.wl_priority[wl] ^ 0x80000000u);  // signed priority, descending
   u64 ts = (u64)D.wl_ts[wl] ^ 0x8000000000000000ull;
   int P = D.parent[cq];
   bool fair_flat = (D.flags & KB_F_FAIR_SHARING) && P >= 0 && D.tree_flat[D.root_slot[cq] - D.nLone];

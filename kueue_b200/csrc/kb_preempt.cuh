@@ -1,4 +1,4 @@
-// kb_preempt.cuh — classical / hierarchical preemption target search on the device.
+// kb_preempt.cuh — fair-sharing preemption target search on the device (classical / hierarchical: kb_search.cuh).
 //
 // Reference: pkg/scheduler/preemption/preemption.go:127-153,238-314,547-584,
 // preemption_oracle.go:41-71, classical/candidate_generator.go:52-162,
@@ -17,8 +17,6 @@
 #pragma once
 
 #include "kb_device.cuh"
-
-enum { PV_NEVER = 0, PV_WITHIN_CQ = 1, PV_HIER_RECLAIM = 2, PV_RECLAIM_NO_BORROW = 3, PV_RECLAIM_WHILE_BORROW = 4 };
 
 // Private, mutable view of one root tree; node handle = local index inside the tree.
 template <bool kSmem>
@@ -154,32 +152,6 @@ __device__ __forceinline__ bool uses_resources(const DevSnap &D, const PreCtx &c
   }
   return false;
 }
-// classifyPreemptionVariant hierarchical_preemption.go:82-114
-__device__ inline int classify_variant(const DevSnap &D, const PreCtx &c, int a, bool hier_adv) {
-  if (!uses_resources(D, c, a)) return PV_NEVER;
-  bool same = D.adm_cq[a] == c.cq;
-  int policy = same ? D.cq_within_cq[c.cq] : D.cq_reclaim_within[c.cq];
-  if (!satisfies_policy(D, c, a, policy)) return PV_NEVER;
-  if (same) return PV_WITHIN_CQ;
-  if (hier_adv) return PV_HIER_RECLAIM;
-  if (D.cq_borrow_within[c.cq] == KB_POLICY_NEVER) return PV_RECLAIM_NO_BORROW;  // IsBorrowingWithinCohortForbidden :72-78
-  int cp = D.adm_priority[a];
-  bool above;  // isAboveBorrowingThreshold :116-124
-  if (cp >= c.prio) above = true;
-  else if (!D.cq_has_bwc_threshold[c.cq]) above = false;
-  else above = cp > D.cq_bwc_threshold[c.cq];
-  return above ? PV_RECLAIM_NO_BORROW : PV_RECLAIM_WHILE_BORROW;
-}
-__device__ __forceinline__ int variant_reason(int v) {  // PreemptionReason :49-61
-  switch (v) {
-    case PV_WITHIN_CQ: return KB_REASON_IN_CLUSTER_QUEUE;
-    case PV_HIER_RECLAIM: return KB_REASON_IN_COHORT_RECLAMATION;
-    case PV_RECLAIM_WHILE_BORROW: return KB_REASON_IN_COHORT_RECLAIM_WHILE_BORROWING;
-    case PV_RECLAIM_NO_BORROW: return KB_REASON_IN_COHORT_RECLAMATION;
-  }
-  return 0;
-}
-
 
 // ---------------------------------------------------------------------------
 // Ordered candidate gathering.  The host orders the admitted workloads of every root once per
@@ -220,135 +192,6 @@ __device__ inline bool workload_fits(const PTab<kSmem> &T, const PreCtx &c, int 
     if (c.use_q[j] > T.avail(hcq, c.use_fr[j])) return false;
   }
   return true;
-}
-
-// classicalPreemptions preemption.go:238-293.  Called by ONE thread with the context filled
-// in (cq, prio, ts, use_*, need_*).  On return c->n_targets / S.tgt hold the targets
-// (0 = none); the private tree is restored.
-template <bool kSmem>
-__device__ inline void classical_search(const DevSnap &D, const PTab<kSmem> &T, PreCtx *c, const PreScratch &S) {
-  const int cq = c->cq;
-  const int hcq = T.handle(cq);
-  const bool has_parent = D.parent[cq] >= 0;
-  const bool cohort_cands = has_parent && D.cq_reclaim_within[cq] != KB_POLICY_NEVER;
-  const bool own_cands = D.cq_within_cq[cq] != KB_POLICY_NEVER;
-  // ---- 1. preemptor path and hierarchical advantage per level (collectCandidatesForHierarchicalReclaim :151-177)
-  {
-    int pl = 0;
-    for (int t = hcq; t >= 0; t = T.parent(t)) c->path[pl++] = t;
-    c->plen = pl;
-    i64 rem[KB_MAX_CELLS];
-    for (int j = 0; j < c->n_use; j++) rem[j] = c->use_q[j];
-    auto qfiq = [&](int h) {  // QuantitiesFitInQuota resource_node.go:234-244
-      bool fits = true;
-      for (int j = 0; j < c->n_use; j++) {
-        int fr = c->use_fr[j];
-        if (T.U(h, fr) + rem[j] > T.Sub(h, fr)) fits = false;
-        rem[j] = imax(0, rem[j] - T.local_avail(h, fr));
-      }
-      return fits;
-    };
-    bool adv = qfiq(hcq);
-    for (int k = 1; k < pl; k++) {
-      c->adv_at[k] = adv;
-      bool fits = qfiq(c->path[k]);
-      adv = adv || fits;
-    }
-    c->n_targets = 0;
-    c->overflow = 0;
-  }
-  for (int h = 0; h < T.nn; h++) S.on_path[h] = -1;
-  for (int k = 0; k < c->plen; k++) S.on_path[c->path[k]] = (int8_t)k;
-  // ---- 2. which ClusterQueues are collected, and by which subtree (collectCandidatesInSubtree :181-199).
-  //         Only ClusterQueues above nominal in some flavor-resource at cycle start can qualify
-  //         (searches only ever remove usage from other queues): k_over listed them per root.
-  const int slot = D.root_slot[cq];
-  const int32_t *over = D.over_list + D.root_cq_start[slot];
-  const int n_over = cohort_cands ? D.over_count[slot] : 0;
-  for (int i = 0; i < n_over; i++) {
-    int q = over[i];
-    int h = T.handle(q);
-    int cls = 0, lca = -1;
-    if (h != hcq && !within_nominal(T, *c, h)) {
-      bool ok = true;
-      int t = T.parent(h);
-      while (t >= 0 && S.on_path[t] < 0) {  // cohorts strictly between the CQ and the subtree root
-        if (within_nominal(T, *c, t)) { ok = false; break; }
-        t = T.parent(t);
-      }
-      if (ok && t >= 0) { lca = t; cls = c->adv_at[S.on_path[t]] ? 1 : 2; }
-    }
-    S.cq_class[h] = (int8_t)cls;
-    S.cq_lca[h] = lca;
-  }
-  // ---- 3. ordered candidate list: evicted{hier, prio, same} then non-evicted{hier, prio, same}
-  //         (NewCandidateIterator candidate_generator.go:77-121)
-  int nall = 0;
-  for (int sgi = 0; sgi < 6; sgi++) c->seg_count[sgi] = 0;
-  auto gather = [&](int q, int cls) {  // cls: 0 hierarchy, 1 priority, 2 same queue
-    for (int i = D.cq_adm_start[q]; i < D.cq_adm_start[q + 1]; i++) {
-      int a = D.cq_adm[i];
-      int v = classify_variant(D, *c, a, cls == 0);
-      if (v == PV_NEVER) continue;
-      if (nall >= S.cap) { c->overflow = 1; return; }
-      int seg = (D.adm_evicted[a] ? 0 : 3) + cls;
-      S.cand[nall] = a; S.variant[nall] = (uint8_t)v; S.aux1[nall] = (seg << 28) | D.adm_rank[a];
-      nall++;
-      c->seg_count[seg]++;
-    }
-  };
-  if (own_cands) gather(cq, 2);
-  for (int i = 0; i < n_over; i++) {
-    int q = over[i];
-    int h = T.handle(q);
-    if (h != hcq && S.cq_class[h]) gather(q, S.cq_class[h] - 1);
-  }
-  if (c->overflow) { c->n_targets = 0; return; }
-  sort_candidates(S.aux1, S.cand, S.variant, nall);
-  // ---- 4. greedy remove / fill back
-  {
-    int n_hier = c->seg_count[0] + c->seg_count[3], n_prio = c->seg_count[1] + c->seg_count[4];
-    bool no_other = n_hier == 0 && n_prio == 0, no_hier = n_hier == 0;
-    bool forbidden = D.cq_borrow_within[cq] == KB_POLICY_NEVER;
-    bool under_nominal = true;  // queueUnderNominalInResourcesNeedingPreemption :577-584
-    for (int j = 0; j < c->n_need; j++) if (T.U(hcq, c->need_fr[j]) >= T.Sub(hcq, c->need_fr[j])) under_nominal = false;
-    bool opts[2]; int nopts;
-    if (no_other || (forbidden && !under_nominal)) { opts[0] = true; nopts = 1; }   // :266-267
-    else if (forbidden && no_hier) { opts[0] = false; opts[1] = true; nopts = 2; }  // :268-269
-    else { opts[0] = true; opts[1] = false; nopts = 2; }                            // :270-271
-    int nt = 0; bool found = false;
-    for (int oi = 0; oi < nopts && !found; oi++) {
-      bool borrow = opts[oi];
-      nt = 0;
-      for (int i = 0; i < nall; i++) {
-        int a = S.cand[i], v = S.variant[i];
-        int acq = D.adm_cq[a];
-        if (acq != cq) {  // candidateIsValid candidate_generator.go:140-162
-          if (borrow && v == PV_RECLAIM_NO_BORROW) continue;
-          int h = T.handle(acq);
-          if (within_nominal(T, *c, h)) continue;
-          bool valid = true;
-          int lca = S.cq_lca[h];
-          for (int t = T.parent(h); t >= 0 && t != lca; t = T.parent(t))
-            if (within_nominal(T, *c, t)) { valid = false; break; }
-          if (!valid) continue;
-        }
-        T.remove_adm(a);
-        S.tgt[nt] = a; S.tgt_reason[nt] = (uint8_t)variant_reason(v); nt++;
-        if (workload_fits(T, *c, hcq, borrow)) {
-          for (int k = nt - 2; k >= 0; k--) {  // fillBackWorkloads :295-308
-            T.add_adm(S.tgt[k]);
-            if (workload_fits(T, *c, hcq, borrow)) { S.tgt[k] = S.tgt[nt - 1]; S.tgt_reason[k] = S.tgt_reason[nt - 1]; nt--; }
-            else T.remove_adm(S.tgt[k]);
-          }
-          found = true;
-          break;
-        }
-      }
-      for (int k = 0; k < nt; k++) T.add_adm(S.tgt[k]);  // restoreSnapshot :310-314
-    }
-    c->n_targets = found ? nt : 0;
-  }
 }
 
 // ---------------------------------------------------------------------------
@@ -577,8 +420,3 @@ __device__ inline void fair_search(const DevSnap &D, const PTab<kSmem> &T, PreCt
   c->n_targets = fits ? nt : 0;
 }
 
-template <bool kSmem>
-__device__ __forceinline__ void target_search(const DevSnap &D, const PTab<kSmem> &T, PreCtx *c, const PreScratch &S) {
-  if (D.flags & KB_F_FAIR_SHARING) fair_search<kSmem>(D, T, c, S);  // getTargets preemption.go:148-153
-  else classical_search<kSmem>(D, T, c, S);
-}

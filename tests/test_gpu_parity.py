@@ -317,3 +317,64 @@ def test_reference_last_assignment_outdated_cycle(ev):
 def test_flat_commit_loop_variants(ev, make):
     snap = make()
     assert_cycle_equal(ev.run_cycle(snap), oracle.run_cycle(snap))
+
+
+@pytest.mark.parametrize("fair", [False, True])
+def test_mixed_sign_priorities_in_one_cohort(ev, fair):
+    """Priorities of both signs (incl. INT32_MIN / INT32_MAX) inside one root cohort: the iterator key must order
+    them as signed ints (scheduler.go:799-805, fair_sharing_iterator.go:184-190) on the classical and the
+    fair flat-cohort paths."""
+    snap = synth.make_snapshot(3, W=3000, Q=300, heads="one_per_cq")
+    if not fair:
+        snap = _classical(snap)
+    rng = np.random.default_rng(5)
+    snap.arrays["wl_priority"][:] = rng.choice(np.array([-5, 0, 7, -2**31, 2**31 - 1, -1, 1], np.int64), snap.n_wl).astype(np.int32)
+    # identical timestamps inside a cohort would hide a priority mix-up behind the timestamp key
+    got, want = ev.run_cycle(snap), oracle.run_cycle(snap)
+    assert_cycle_equal(got, want)
+    # and with lone ClusterQueues holding several entries each
+    snap = synth.make_snapshot(2, W=5000, Q=50)
+    snap.arrays["wl_priority"][:] = rng.choice(np.array([-5, 0, 7, -2**31, 2**31 - 1], np.int64), snap.n_wl).astype(np.int32)
+    assert_cycle_equal(ev.run_cycle(snap), oracle.run_cycle(snap))
+
+
+@pytest.fixture(scope="module")
+def cfg4_full():
+    """BASELINE cfg4 at full size (Q=10 000, C=1 310, A=200 000, 10 roots x 1 131 nodes) and the oracle's cycle."""
+    snap = synth.make_snapshot(4, heads="one_per_cq")
+    cap = 40 * snap.n_adm
+    return snap, cap, oracle.run_cycle(snap, cap)
+
+
+def test_full_size_config4_single_cycle(ev, cfg4_full):
+    snap, cap, want = cfg4_full
+    assert want.n_targets > 0
+    got = ev.run_cycle(snap, abi.CycleOut(snap, cap))
+    assert_cycle_equal(got, want)
+
+
+@pytest.mark.parametrize("world", [2, 8])
+def test_full_size_config4_sharded_device(ev, cfg4_full, world):
+    """shard.shard -> device cycle per shard -> shard.merge == the unsharded oracle (the N>1 path of bench.py with
+    the CUDA evaluator in the loop)."""
+    from kueue_b200 import shard
+    snap, cap, want = cfg4_full
+    node_rank = shard.partition_roots(snap, world)
+    parts = []
+    for r in range(world):
+        sub, m = shard.shard(snap, r, world, node_rank)
+        parts.append((ev.run_cycle(sub, abi.CycleOut(sub, cap)), m))
+    assert_cycle_equal(shard.merge(snap, parts), want)
+
+
+@pytest.mark.parametrize("world", [2, 8])
+def test_config3_sharded_device(ev, world):
+    from kueue_b200 import shard
+    snap = synth.make_snapshot(3, W=200_000, Q=2000, heads="one_per_cq")
+    want = oracle.run_cycle(snap)
+    node_rank = shard.partition_roots(snap, world)
+    parts = []
+    for r in range(world):
+        sub, m = shard.shard(snap, r, world, node_rank)
+        parts.append((ev.run_cycle(sub), m))
+    assert_cycle_equal(shard.merge(snap, parts), want)
