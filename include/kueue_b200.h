@@ -182,6 +182,14 @@ typedef struct kb_snapshot {
                                   Reference mode: one per CQ (manager.go:770-794);
                                   batched mode: any subset, e.g. all of them.            */
 
+  /* ---- optional per-workload tables: NULL = absent ---- */
+  const uint8_t *wl_has_quota_reservation; /* [n_wl] workload.HasQuotaReservation(Obj): entries that already hold a quota
+                                  reservation (second pass) come first in the classical order (scheduler.go:781-789) */
+  const int64_t *wl_sched_hash; /* [n_wl] 64-bit digest of Info.SchedulingHash, 0 = SchedulingHashUnknown
+                                  (workload.go:311-343).  Read by kb_run_drain only: a NoFit head of a BestEffortFIFO
+                                  queue moves every queued workload of the same class to the inadmissible set
+                                  (handleInadmissibleHash, cluster_queue.go:408-425). */
+
   /* ---- upload hint ---- */
   int64_t static_generation;   /* 0 = none.  When non-zero and equal to the value of the previous call on
                                   this handle (with unchanged n_cq/n_cohort/n_flavor/n_resource/n_rg), the
@@ -239,6 +247,10 @@ typedef struct kb_stats {
   /* per-kernel device time of the last kb_cycle_resident when kb_set_profile(h, 1):
    * CUDA events recorded on the launching stream around each kernel. */
   float   kernel_ms[KB_N_KERNELS];
+  /* target-search counters of the last cycle: [0] searches run, [1] candidate records classified (32 B each),
+   * [2] candidates visited by the greedy loops, [3] workloads removed (incl. fill-back), [4] GetTargets calls,
+   * [5..7] SM clock cycles summed over warps: column load / classification / greedy (diagnostics) */
+  int64_t search_stat[8];
 } kb_stats;
 
 /* indices into kb_stats.kernel_ms */

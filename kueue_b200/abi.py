@@ -69,6 +69,7 @@ class kb_snapshot(C.Structure):
         ("adm_qr_ts", _P(C.c_int64)), ("adm_uid", _P(C.c_int64)), ("adm_evicted", _P(C.c_uint8)),
         ("adm_use_start", _P(C.c_int32)), ("adm_use_fr", _P(C.c_int32)), ("adm_use_qty", _P(C.c_int64)),
         ("heads", _P(C.c_int32)),
+        ("wl_has_quota_reservation", _P(C.c_uint8)), ("wl_sched_hash", _P(C.c_int64)),
         ("static_generation", C.c_int64),
     ]
 
@@ -96,7 +97,7 @@ class kb_stats(C.Structure):
     _fields_ = [
         ("last_cycle_gpu_ms", C.c_double), ("last_h2d_ms", C.c_double), ("last_d2h_ms", C.c_double),
         ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64), ("kernel_launches", C.c_int32), ("sm_count", C.c_int32),
-        ("kernel_ms", C.c_float * 16),
+        ("kernel_ms", C.c_float * 16), ("search_stat", C.c_int64 * 8),
     ]
 
 
@@ -121,7 +122,9 @@ _DT = {
     "adm_cq": np.int32, "adm_priority": np.int32, "adm_ts": np.int64, "adm_qr_ts": np.int64, "adm_uid": np.int64,
     "adm_evicted": np.uint8, "adm_use_start": np.int32, "adm_use_fr": np.int32, "adm_use_qty": np.int64,
     "heads": np.int32,
+    "wl_has_quota_reservation": np.uint8, "wl_sched_hash": np.int64,
 }
+OPTIONAL_FIELDS = ("wl_has_quota_reservation", "wl_sched_hash")  # NULL in kb_snapshot when absent
 ARRAY_FIELDS = list(_DT.keys())
 # tables the library keeps resident while kb_snapshot.static_generation is unchanged (include/kueue_b200.h)
 STATIC_FIELDS = ("parent", "fair_weight", "nominal", "borrow_limit", "lend_limit", "cq_within_cq", "cq_reclaim_within",
@@ -250,6 +253,8 @@ class FlatSnapshot:
         s.pods_resource, s.flags, s.now_ns = self.pods_resource, self.flags, self.now_ns
         s.static_generation = self.static_generation
         for name in ARRAY_FIELDS:
+            if name in OPTIONAL_FIELDS and name not in self.arrays:
+                continue  # stays NULL
             arr = self.arrays[name]
             setattr(s, name, _ptr(arr, _CT[_DT[name]]))
         s._keepalive = self  # noqa: keep numpy buffers alive with the struct

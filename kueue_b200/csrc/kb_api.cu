@@ -74,6 +74,7 @@ struct kb_handle {
   int sa_wpb = 1, sa_grid = 1, sa_col_elems = 0, sa_codes = 0; size_t sa_smem = 0;
   int sb_wpb = 1, sb_grid = 1, sb_col_elems = 0; size_t sb_smem = 0;
   int sa_list_cap = 32, sb_list_cap = 32;
+  bool sg_on = false; int sg_wpb = 1, sg_grid = 1, sg_ncap = 1; size_t sg_smem = 0;  // grouped form of k_search_cells
   // device ranking of the admitted workloads (kb_rank.cuh)
   u64 *rk_keys[2] = {nullptr, nullptr}; int32_t *rk_vals[2] = {nullptr, nullptr}; void *rk_temp = nullptr; size_t rk_temp_bytes = 0;
   int search_grid = 1;
@@ -140,7 +141,7 @@ int32_t kb_create(const kb_config *cfg, kb_handle **out) {
   if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return fail(nullptr, KB_ERR_CUDA, "stream"); }
   cudaEventCreate(&h->ev0); cudaEventCreate(&h->ev1); cudaEventCreate(&h->ev2); cudaEventCreate(&h->ev3); cudaEventCreate(&h->ev4); cudaEventCreate(&h->ev5);
   for (int i = 0; i <= KB_N_KERNELS; i++) cudaEventCreate(&h->kev[i]);
-  cudaHostAlloc((void **)&h->host_words, 64, cudaHostAllocDefault);
+  cudaHostAlloc((void **)&h->host_words, 256, cudaHostAllocDefault);
   h->stats.sm_count = h->sm_count;
   *out = h;
   return KB_OK;
@@ -432,7 +433,7 @@ static int32_t upload_impl(kb_handle *h, const kb_snapshot *s, bool sync) {
   need(W, 4); need(W, 4); need(W, 8); need(W, 8); need(W, 8); need(W + 1, 4);
   need(P * R, 8); need(P, 4); need(P, 4); need(P, 4); need(P, 8); need(P * R, 1);
   need(A, 4); need(A, 4); need(A, 8); need(A, 8); need(A, 8); need(A, 1); need(A + 1, 4); need(s->n_adm_use, 4); need(s->n_adm_use, 8);
-  need(H, 4);
+  need(H, 4); need(W, 1); need(W, 8);
   need(Q + 1, 4); need(A, 4); need(A, 4); need(Q, 4); need(nroots, 4);
   need(nroots + 2, 4); need(Q + 2, 4); need(A, 8); need(A, 8); need(A, 4); need(A, 4);
   size_t rk_temp_bytes = 0;
@@ -480,14 +481,26 @@ static int32_t upload_impl(kb_handle *h, const kb_snapshot *s, bool sync) {
     int bpsA = (int)std::max<size_t>(1, std::min<size_t>(32 / wpbA, (220 * 1024) / (perA * wpbA + 1024)));
     h->sa_wpb = wpbA; h->sa_col_elems = (int)colA; h->sa_codes = (int)codesA; h->sa_smem = perA * wpbA;
     h->sa_grid = std::max(1, std::min(h->sm_count * bpsA, (int)((H * (size_t)FR + 31) / 32)));
+    // grouped form: one column's statics + base usage shared by the CTA, private column + codes per warp
+    {
+      size_t shared_b = ((ncap_s * (sizeof(ColStat) + 8)) + 15) & ~(size_t)15;
+      size_t perG = ctxA + ((ncap_s * 8 + 15) & ~(size_t)15) + ((codesA + 15) & ~(size_t)15);
+      size_t budget = 220 * 1024;
+      int wpbG = shared_b + perG <= budget ? (int)std::min<size_t>(16, (budget - shared_b) / perG) : 0;
+      h->sg_on = wpbG >= 4;
+      h->sg_wpb = std::max(1, wpbG); h->sg_ncap = (int)ncap_s; h->sg_smem = shared_b + perG * h->sg_wpb;
+      h->sg_grid = h->sm_count;
+      if (h->sg_on) { wpbA = std::max(wpbA, wpbG); h->sa_grid = std::max(h->sa_grid, h->sg_grid); }
+    }
     // k_nominate_walk: up to Kcap columns (cells of one workload's assignment)
     size_t kcap = std::min<size_t>(std::min<size_t>((size_t)FR, KB_MAX_CELLS), (size_t)h->max_head_podsets * R);
     size_t ctxB = (sizeof(WCtx<KB_MAX_CELLS>) + 15) & ~(size_t)15;
-    size_t colB = std::min<size_t>(kcap * ncap_s, 5120);
-    if (colB < ncap_s) colB = 0;  // not even one column fits: global columns
-    size_t perB = ctxB + ((colB * 8 + 15) & ~(size_t)15);
-    int wpbB = (int)std::max<size_t>(1, std::min<size_t>(8, kSmemBudget / perB));
-    int bpsB = (int)std::max<size_t>(1, std::min<size_t>(16 / wpbB, (220 * 1024) / (perB * wpbB + 1024)));
+    // The walk is a chain of dependent loads per entry: occupancy (16 warps per SM at 128 registers) hides more
+    // latency than shared-memory columns would save, so the private columns of its searches live in global scratch.
+    size_t colB = 0;
+    size_t perB = ctxB;
+    int wpbB = 8;
+    int bpsB = 2;
     h->sb_wpb = wpbB; h->sb_col_elems = (int)colB; h->sb_smem = perB * wpbB;
     h->sb_grid = std::max(1, std::min(h->sm_count * bpsB, (int)((H + wpbB - 1) / wpbB)));
     ws_warps = std::max((size_t)h->sa_grid * wpbA, (size_t)h->sb_grid * wpbB);
@@ -508,9 +521,10 @@ static int32_t upload_impl(kb_handle *h, const kb_snapshot *s, bool sync) {
   // classical search tables + per-warp scratch
   const size_t nbuckets = (size_t)nroots * FR;
   const size_t sNF = A ? NF : 1, sAU = A ? (size_t)s->n_adm_use : 1;
-  need(A, 4); need(sNF, 8); need(sNF, sizeof(ColStat)); need(sNF, 4); need(A ? nbuckets + 1 : 1, 4); need(A ? nbuckets + 2 : 1, 4); need(sAU, sizeof(FrRec));
-  need(memo_items * FR, sizeof(SimMemo)); need(1, 4);
-  need(ws_warps * ws_col_stride, 8); need(ws_list_total, 1); need(ws_list_total, 4); need(ws_list_total, 1);
+  need(A, 4); need(sNF, 8); need(sNF, sizeof(ColStat)); need(sNF, 4); need(A ? nbuckets + 1 : 1, 4); need(A ? nbuckets + 2 : 1, 4); need(sAU, sizeof(FrRec)); need(A, sizeof(FrRec));
+  need(memo_items * FR, sizeof(SimMemo)); need(1, 4); need(8, 8);
+  need(A ? nbuckets + 2 : 1, 4); need(A ? nbuckets + 2 : 1, 4); need(A ? nbuckets + 2 : 1, 4); need(memo_items * FR, 4); need(memo_items * FR, 4);
+  need(ws_warps * ws_col_stride, 8); need(ws_list_total, 1); need(ws_list_total, 4); need(ws_list_total, 1); need(ws_warps * (size_t)h->sa_list_cap, 8);
   if (fair) { need(H * FR, 8); need(H * (48 + 16 * KB_MAX_DEPTH), 1); need(N, 4); need(N, 4); }
   const size_t span_cap = tot;  // the input tables are part of tot: a span of up to that size is covered by the slack below
   if (!h->arena.reserve(tot + tot / 2 + (1u << 20))) return fail(h, KB_ERR_CUDA, "cudaMalloc failed");
@@ -531,6 +545,9 @@ static int32_t upload_impl(kb_handle *h, const kb_snapshot *s, bool sync) {
   UP(adm_qr_ts, (const i64 *)s->adm_qr_ts, A); UP(adm_uid, (const i64 *)s->adm_uid, A); UP(adm_evicted, s->adm_evicted, A);
   UP(adm_use_start, s->adm_use_start, A + 1); UP(adm_use_fr, s->adm_use_fr, s->n_adm_use); UP(adm_use_qty, (const i64 *)s->adm_use_qty, s->n_adm_use);
   UP(heads, s->heads, H);
+  D.wl_has_qr = nullptr; D.wl_sched_hash = nullptr;
+  if (s->wl_has_quota_reservation) UP(wl_has_qr, s->wl_has_quota_reservation, W);
+  if (s->wl_sched_hash) UP(wl_sched_hash, (const i64 *)s->wl_sched_hash, W);
   size_t caller_tabs = tabs.size();
 #undef UP
   {
@@ -592,12 +609,16 @@ static int32_t upload_impl(kb_handle *h, const kb_snapshot *s, bool sync) {
   D.sc_adm_cap = (int)acap; D.sc_node_cap = (int)ncap;
   D.colU = h->arena.take<i64>(sNF); D.colS = h->arena.take<ColStat>(sNF); D.ovm = h->arena.take<uint32_t>(sNF);
   D.frl_count = h->arena.take<int32_t>(A ? nbuckets + 1 : 1); D.frl_start = h->arena.take<int32_t>(A ? nbuckets + 2 : 1);
-  D.frl = h->arena.take<FrRec>(sAU);
+  D.frl = h->arena.take<FrRec>(sAU); D.rrec = h->arena.take<FrRec>(A);
   D.memo = h->arena.take<SimMemo>(memo_items * FR); D.memo_items = (int)memo_items;
-  D.cell_cursor = h->arena.take<int32_t>(1);
+  D.cell_cursor = h->arena.take<int32_t>(1); D.sstat = h->arena.take<u64>(8);
+  D.cell_count = h->arena.take<int32_t>(A ? nbuckets + 2 : 1); D.cell_start = h->arena.take<int32_t>(A ? nbuckets + 2 : 1);
+  D.cell_fill = h->arena.take<int32_t>(A ? nbuckets + 2 : 1);
+  D.cell_list = h->arena.take<int32_t>(memo_items * FR); D.cell_bucket = h->arena.take<int32_t>(memo_items * FR);
   D.ws_col = h->arena.take<i64>(ws_warps * ws_col_stride); D.ws_col_stride = ws_col_stride;
   D.ws_codes = h->arena.take<uint8_t>(ws_list_total); D.ws_tgt = h->arena.take<int32_t>(ws_list_total);
   D.ws_tgt_reason = h->arena.take<uint8_t>(ws_list_total);
+  D.ws_tgtq = h->arena.take<i64>(ws_warps * (size_t)h->sa_list_cap); D.ws_tgtq_cap = h->sa_list_cap;
   if (fair) {
     D.q_scratch = h->arena.take<i64>(H * FR); D.fs_state = h->arena.take<unsigned char>(H * (48 + 16 * KB_MAX_DEPTH));
     D.fs_cq_entry = h->arena.take<int32_t>(N); D.fs_winner = h->arena.take<int32_t>(N);
@@ -704,6 +725,7 @@ static int32_t cycle_enqueue(kb_handle *h) {
   int launches = 0;
   CUDA_TRY(h, cudaEventRecord(h->ev2, h->stream));
   CUDA_TRY(h, cudaMemsetAsync(D.status, 0, 4, h->stream));
+  CUDA_TRY(h, cudaMemsetAsync(D.sstat, 0, 64, h->stream));
   CUDA_TRY(h, cudaMemsetAsync(D.root_count, 0, sizeof(int32_t) * (size_t)std::max(1, D.nRoots), h->stream));
   CUDA_TRY(h, cudaMemsetAsync(D.ps_n, 0, 8, h->stream));
   CUDA_TRY(h, cudaMemsetAsync(D.tgt_pool_used, 0, 4, h->stream));
@@ -766,11 +788,23 @@ static int32_t cycle_enqueue(kb_handle *h) {
         CUDA_TRY(h, cudaMemsetAsync(D.cell_cursor, 0, 4, h->stream));
         if (D.AU) { k_frl_count<<<(D.AU + 255) / 256, 256, 0, h->stream>>>(D); launches++; }
         k_scan_i32<<<1, 1024, 0, h->stream>>>(D.frl_count, D.frl_start, nb); launches++;
+        k_root_recs<<<(D.A + 255) / 256, 256, 0, h->stream>>>(D); launches++;
         if (D.AU) { k_frl_fill<<<(unsigned)(((size_t)nb * 32 + 127) / 128), 128, 0, h->stream>>>(D); launches++; }
         CUDA_TRY(h, cudaFuncSetAttribute(k_search_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
         CUDA_TRY(h, cudaFuncSetAttribute(k_nominate_walk, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
         kmark(h, KB_K_SEARCH_CELLS);
-        k_search_cells<<<h->sa_grid, h->sa_wpb * 32, h->sa_smem, h->stream>>>(D, h->sa_col_elems, h->sa_codes, h->sa_list_cap); launches++;
+        if (h->sg_on && D.memo_items) {
+          long long ncell = (long long)D.memo_items * D.FR;
+          CUDA_TRY(h, cudaMemsetAsync(D.cell_count, 0, sizeof(int32_t) * (size_t)(nb + 1), h->stream));
+          CUDA_TRY(h, cudaMemsetAsync(D.cell_fill, 0, sizeof(int32_t) * (size_t)(nb + 1), h->stream));
+          k_cells_mark<<<(unsigned)((ncell + 255) / 256), 256, 0, h->stream>>>(D); launches++;
+          k_scan_i32<<<1, 1024, 0, h->stream>>>(D.cell_count, D.cell_start, nb); launches++;
+          k_cells_scatter<<<(unsigned)((ncell + 255) / 256), 256, 0, h->stream>>>(D); launches++;
+          CUDA_TRY(h, cudaFuncSetAttribute(k_search_cells_grouped, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+          k_search_cells_grouped<<<h->sg_grid, h->sg_wpb * 32, h->sg_smem, h->stream>>>(D, h->sg_ncap, h->sa_codes, h->sa_list_cap); launches++;
+        } else {
+          k_search_cells<<<h->sa_grid, h->sa_wpb * 32, h->sa_smem, h->stream>>>(D, h->sa_col_elems, h->sa_codes, h->sa_list_cap); launches++;
+        }
         kmark(h, KB_K_WALK);
         k_nominate_walk<<<h->sb_grid, h->sb_wpb * 32, h->sb_smem, h->stream>>>(D, h->sb_col_elems, h->sb_list_cap); launches++;
       }
@@ -789,6 +823,7 @@ static int32_t cycle_enqueue(kb_handle *h) {
   h->last_launches = launches;
   CUDA_TRY(h, cudaMemcpyAsync(&h->host_words[0], D.status, 4, cudaMemcpyDeviceToHost, h->stream));
   CUDA_TRY(h, cudaMemcpyAsync(&h->host_words[1], D.tgt_pool_used, 4, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaMemcpyAsync(&h->host_words[16], D.sstat, 64, cudaMemcpyDeviceToHost, h->stream));
   return KB_OK;
 }
 
@@ -802,6 +837,7 @@ static int32_t cycle_finish(kb_handle *h) {
     float kms = 0; cudaEventElapsedTime(&kms, h->kev[i], h->kev[i + 1]);
     if (h->kev_id[i] >= 0) h->stats.kernel_ms[h->kev_id[i]] += kms;
   }
+  memcpy(h->stats.search_stat, &h->host_words[16], 64);
   uint32_t st = h->host_words[0];
   if (st & KBS_UNSUPPORTED_PREEMPTION) return fail(h, KB_ERR_UNSUPPORTED, "unsupported preemption configuration");
   if (st & KBS_TARGET_OVERFLOW) return fail(h, KB_ERR_CAPACITY, "per-entry usage cell / target pool capacity exceeded");

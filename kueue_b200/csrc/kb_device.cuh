@@ -67,6 +67,8 @@ struct DevSnap {
   const int32_t *adm_use_start, *adm_use_fr;
   const i64 *adm_use_qty;
   const int32_t *heads;
+  const uint8_t *wl_has_qr;    // optional (nullptr = absent): workload.HasQuotaReservation
+  const i64 *wl_sched_hash;    // optional: scheduling equivalence class, 0 = unknown (drain only)
   // ---- derived, static per topology (host-built at upload) ----
   const int32_t *root_slot;   // [N] dense index of the node's root among all roots
   const int32_t *depth;       // [N] distance to the root
@@ -135,10 +137,15 @@ struct DevSnap {
   i64 *colU; ColStat *colS; uint32_t *ovm;  // [N*FR] transposed per root: index = slot_base*FR + fr*nn + h
   int32_t *frl_count, *frl_start;  // [nRoots*FR (+1)] buckets of the fr-lists
   FrRec *frl;                 // [AU]
+  FrRec *rrec;                // [A] the roots' ranked lists as packed records (qty field = used flavor-resource bit set)
   SimMemo *memo; int memo_items;  // [memo_items][FR] results of the speculative single-cell searches (item = position in ps_list)
   int32_t *cell_cursor;       // work counter of k_search_cells
+  int32_t *cell_count, *cell_start, *cell_fill;  // [nRoots*FR (+1)] oracle cells per (root, flavor-resource) bucket
+  int32_t *cell_list, *cell_bucket;              // [memo_items*FR] memo index / bucket of every oracle cell, grouped by bucket
+  u64 *sstat;                 // [8] search counters (kb_stats.search_stat)
   i64 *ws_col; size_t ws_col_stride;  // per-warp global column storage when shared memory is too small (stride in i64)
   uint8_t *ws_codes; int32_t *ws_tgt; uint8_t *ws_tgt_reason;  // per-warp [list_cap of the kernel]
+  i64 *ws_tgtq; int ws_tgtq_cap;  // per-warp [ws_tgtq_cap] target quantities of single-column searches
   // ---- fair-sharing scratch ----
   i64 *q_scratch;        // [H][FR] dense Assignment.Usage.Quota per entry (absent = -1)
   unsigned char *fs_state; // [H] x (48 + 16*KB_MAX_DEPTH) B: per-entry tournament state when it does not fit shared memory

@@ -664,6 +664,27 @@ __global__ void k_over(DevSnap D) {
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
 
+// Would the flavor walk of the first podset of entry `item` call the preemption oracle on flavor-resource fr?
+// (fitsResourceQuota flavorassigner.go:1017-1047 reaches SimulatePreemption.)  *req = the quantity it would pass.
+__device__ inline bool oracle_cell_needed(const DevSnap &D, int item, int fr, int *wl_out, int *cq_out, i64 *req) {
+  const int R = D.R;
+  int wl = D.heads[D.ps_list[item]], cq = D.wl_cq[wl];
+  *wl_out = wl; *cq_out = cq;
+  int row = D.wl_ps_start[wl];
+  if (!(D.wl_ps_start[wl + 1] > row) || !candidates_possible(D, cq)) return false;
+  int f = fr / R, r = fr % R;
+  bool covers_pods = D.pods_res >= 0 && rg_by_resource(D, cq, D.pods_res) >= 0;
+  uint32_t mask = D.ps_req_mask[row] | (covers_pods ? 1u << D.pods_res : 0u);
+  int g = ((mask >> r) & 1) && ((D.ps_flavor_ok[row] >> f) & 1) ? rg_by_resource(D, cq, r) : -1;
+  bool in_rg = false;
+  if (g >= 0) for (int k = D.rg_flavor_start[g]; k < D.rg_flavor_start[g + 1]; k++) in_rg |= D.rg_flavors[k] == f;
+  if (!in_rg) return false;
+  *req = ps_request(D, row, r, D.ps_count[row], covers_pods);
+  int b0;
+  return cell_eval(D, cq, fr, 0, *req, &b0) == PM_NEED;
+}
+
+// Ungrouped form (trees too large to share a column per CTA): warps pull (entry, flavor-resource) cells in order.
 __global__ void __launch_bounds__(512) k_search_cells(DevSnap D, int col_smem_elems, int codes_smem, int list_cap) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
@@ -675,7 +696,8 @@ __global__ void __launch_bounds__(512) k_search_cells(DevSnap D, int col_smem_el
   S.col = col_smem_elems ? reinterpret_cast<i64 *>(base + ctx_b) : D.ws_col + gw * D.ws_col_stride;
   S.codes = codes_smem ? base + ctx_b + col_b : D.ws_codes + gw * list_cap;
   S.tgt = D.ws_tgt + gw * list_cap; S.tgt_reason = D.ws_tgt_reason + gw * list_cap;
-  const int FR = D.FR, R = D.R;
+  S.tgtq = D.ws_tgtq + gw * D.ws_tgtq_cap;
+  const int FR = D.FR;
   const int n_items = min(*D.ps_n, D.memo_items);
   const long long total = (long long)n_items * FR;
   while (true) {
@@ -684,26 +706,8 @@ __global__ void __launch_bounds__(512) k_search_cells(DevSnap D, int col_smem_el
     chunk = __shfl_sync(0xffffffffu, chunk, 0);
     long long idx = (long long)chunk * 32 + lane;
     if ((long long)chunk * 32 >= total) break;
-    // ---- one (entry, flavor-resource) cell per lane: would the flavor walk of the first podset call the oracle here?
     bool need = false; int item = 0, fr = 0, wl = 0, cq = 0; i64 req = 0;
-    if (idx < total) {
-      item = (int)(idx / FR); fr = (int)(idx % FR);
-      wl = D.heads[D.ps_list[item]]; cq = D.wl_cq[wl];
-      int row = D.wl_ps_start[wl];
-      if (D.wl_ps_start[wl + 1] > row && candidates_possible(D, cq)) {
-        int f = fr / R, r = fr % R;
-        bool covers_pods = D.pods_res >= 0 && rg_by_resource(D, cq, D.pods_res) >= 0;
-        uint32_t mask = D.ps_req_mask[row] | (covers_pods ? 1u << D.pods_res : 0u);
-        int g = ((mask >> r) & 1) && ((D.ps_flavor_ok[row] >> f) & 1) ? rg_by_resource(D, cq, r) : -1;
-        bool in_rg = false;
-        if (g >= 0) for (int k = D.rg_flavor_start[g]; k < D.rg_flavor_start[g + 1]; k++) in_rg |= D.rg_flavors[k] == f;
-        if (in_rg) {
-          req = ps_request(D, row, r, D.ps_count[row], covers_pods);
-          int b0;
-          need = cell_eval(D, cq, fr, 0, req, &b0) == PM_NEED;
-        }
-      }
-    }
+    if (idx < total) { item = (int)(idx / FR); fr = (int)(idx % FR); need = oracle_cell_needed(D, item, fr, &wl, &cq, &req); }
     if (idx < total && !need) D.memo[idx].val = -1;  // memo row index = item * FR + fr: no oracle call expected here
     unsigned m = __ballot_sync(0xffffffffu, need);
     while (m) {
@@ -715,6 +719,91 @@ __global__ void __launch_bounds__(512) k_search_cells(DevSnap D, int col_smem_el
       int pm = ws_simulate<1>(D, w, S, s_wl, s_cq, s_fr, s_req, &borrow);
       if (lane == 0) { SimMemo mm; mm.val = s_req; mm.pm = pm; mm.borrow = borrow; D.memo[(size_t)s_item * FR + s_fr] = mm; }
       __syncwarp();
+    }
+  }
+}
+
+// Grouped form: the oracle cells are bucketed by (root, flavor-resource) first (k_cells_mark -> scan -> k_cells_scatter),
+// so that a CTA works on ONE column at a time: the column's static cell records (32 B per node) and cycle-start usage
+// are staged in shared memory once per task and every dependent step of its warps' greedy loops (removeUsage /
+// available walks, above-nominal checks) is a shared-memory access.
+__global__ void k_cells_mark(DevSnap D) {
+  const int FR = D.FR;
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int n_items = min(*D.ps_n, D.memo_items);
+  if (idx >= (long long)n_items * FR) return;
+  int item = (int)(idx / FR), fr = (int)(idx % FR), wl, cq; i64 req = 0;
+  bool need = oracle_cell_needed(D, item, fr, &wl, &cq, &req);
+  SimMemo mm; mm.val = need ? req : -1; mm.pm = -1; mm.borrow = 0;  // pm -1: search pending
+  D.memo[idx] = mm;
+  if (need) atomicAdd(&D.cell_count[(size_t)D.root_slot[cq] * FR + fr], 1);
+}
+__global__ void k_cells_scatter(DevSnap D) {
+  const int FR = D.FR;
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int n_items = min(*D.ps_n, D.memo_items);
+  if (idx >= (long long)n_items * FR) return;
+  if (D.memo[idx].val < 0) return;
+  int item = (int)(idx / FR), fr = (int)(idx % FR);
+  int cq = D.wl_cq[D.heads[D.ps_list[item]]];
+  int b = D.root_slot[cq] * FR + fr;
+  int pos = D.cell_start[b] + atomicAdd(&D.cell_fill[b], 1);
+  D.cell_list[pos] = (int)idx; D.cell_bucket[pos] = b;
+}
+#define KB_CELL_TASK 64  // oracle cells per CTA task
+__global__ void __launch_bounds__(512) k_search_cells_grouped(DevSnap D, int ncap, int codes_smem, int list_cap) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ int s_task;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  const size_t gw = (size_t)blockIdx.x * wpb + warp;
+  const int FR = D.FR;
+  ColStat *sh_stat = reinterpret_cast<ColStat *>(smem_raw);
+  i64 *sh_base = reinterpret_cast<i64 *>(smem_raw + (size_t)ncap * sizeof(ColStat));
+  const size_t shared_b = align16((size_t)ncap * (sizeof(ColStat) + 8));
+  const size_t ctx_b = align16(sizeof(WCtx<1>)), col_b = align16((size_t)ncap * 8), codes_b = align16((size_t)codes_smem);
+  unsigned char *base = smem_raw + shared_b + (size_t)warp * (ctx_b + col_b + codes_b);
+  WCtx<1> *w = reinterpret_cast<WCtx<1> *>(base);
+  WScratch S;
+  S.col = reinterpret_cast<i64 *>(base + ctx_b);
+  S.codes = codes_smem ? base + ctx_b + col_b : D.ws_codes + gw * list_cap;
+  S.tgt = D.ws_tgt + gw * list_cap; S.tgt_reason = D.ws_tgt_reason + gw * list_cap;
+  S.tgtq = D.ws_tgtq + gw * D.ws_tgtq_cap;
+  S.stat0 = sh_stat; S.base0 = sh_base;
+  const int n_cells = D.cell_start[D.nRoots * FR];
+  int staged = -1;
+  while (true) {
+    __syncthreads();
+    if (threadIdx.x == 0) s_task = atomicAdd(D.cell_cursor, 1);
+    __syncthreads();
+    const int lo = s_task * KB_CELL_TASK, hi = min(lo + KB_CELL_TASK, n_cells);
+    if (lo >= n_cells) break;
+    for (int p = lo; p < hi;) {
+      const int b = D.cell_bucket[p];
+      int q = p + 1;
+      while (q < hi && D.cell_bucket[q] == b) q++;  // run of cells in the same bucket (the list is grouped by bucket)
+      if (b != staged) {
+        __syncthreads();  // every warp is done with the previous column
+        const int slot = b / FR, fr = b % FR;
+        const int nbase = D.slot_base[slot], nn = D.slot_base[slot + 1] - nbase;
+        const size_t o = (size_t)nbase * FR + (size_t)fr * nn;
+        const int4 *src = reinterpret_cast<const int4 *>(D.colS + o);
+        int4 *dst = reinterpret_cast<int4 *>(sh_stat);
+        for (int i = threadIdx.x; i < nn * 2; i += blockDim.x) dst[i] = __ldg(src + i);
+        for (int i = threadIdx.x; i < nn; i += blockDim.x) sh_base[i] = D.colU[o + i];
+        staged = b;
+        __syncthreads();
+      }
+      for (int c = p + warp; c < q; c += wpb) {
+        const int idx = D.cell_list[c];
+        const int item = idx / FR, fr = idx % FR;
+        const int wl = D.heads[D.ps_list[item]], cq = D.wl_cq[wl];
+        const i64 req = D.memo[idx].val;
+        int borrow;
+        int pm = ws_simulate<1>(D, w, S, wl, cq, fr, req, &borrow);
+        if (lane == 0) { SimMemo mm; mm.val = req; mm.pm = pm; mm.borrow = borrow; D.memo[idx] = mm; }
+        __syncwarp();
+      }
+      p = q;
     }
   }
 }
@@ -799,6 +888,7 @@ __global__ void __launch_bounds__(256) k_nominate_walk(DevSnap D, int col_smem_e
   orc.S.col = orc.col_glob;
   orc.S.codes = D.ws_codes + gw * list_cap;
   orc.S.tgt = D.ws_tgt + gw * list_cap; orc.S.tgt_reason = D.ws_tgt_reason + gw * list_cap;
+  orc.S.tgtq = D.ws_tgtq + gw * D.ws_tgtq_cap;
   const int n_items = *D.ps_n;
   while (true) {
     int item = 0;
@@ -976,7 +1066,9 @@ __device__ inline void compute_entry_key(const DevSnap &D, int e, u64 *k) {
   int P = D.parent[cq];
   bool fair_flat = (D.flags & KB_F_FAIR_SHARING) && P >= 0 && D.tree_flat[D.root_slot[cq] - D.nLone];
   if (!fair_flat) {
-    k[0] = ((u64)(unsigned)D.borrow[e] << 32) | prio; k[1] = ts; k[2] = (u64)(unsigned)e; k[3] = 0;
+    // workloads that already hold a quota reservation (second pass) first: scheduler.go:781-789
+    u64 no_qr = (D.wl_has_qr && D.wl_has_qr[wl]) ? 0ull : 1ull;
+    k[0] = (no_qr << 63) | ((u64)(unsigned)D.borrow[e] << 32) | prio; k[1] = ts; k[2] = (u64)(unsigned)e; k[3] = 0;
     return;
   }
   // dominantResourceShare(cq) with the entry's usage added (computeDRS fair_sharing_iterator.go:206-229).

@@ -30,6 +30,8 @@
 // runs GetTargets for the chosen assignment.
 #pragma once
 
+#include <climits>
+
 #include "kb_device.cuh"
 
 enum { PV_NEVER = 0, PV_WITHIN_CQ = 1, PV_HIER_RECLAIM = 2, PV_RECLAIM_NO_BORROW = 3, PV_RECLAIM_WHILE_BORROW = 4 };
@@ -155,13 +157,32 @@ __global__ void __launch_bounds__(128) k_frl_fill(DevSnap D) {
     written += __popc(m);
   }
 }
+// The root's ranked list as packed records (multi-cell GetTargets searches stream these instead of gathering):
+// same 32 B layout as FrRec with the quantity replaced by the set of flavor-resources the workload uses (bit fr,
+// exact when F*R <= 64, all ones otherwise -> the CSR cells are consulted).
+__global__ void k_root_recs(DevSnap D) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= D.A) return;
+  int a = D.adm_sorted[i];
+  int cq = D.adm_cq[a];
+  int slot = D.root_slot[cq];
+  int h = D.local_idx[cq];
+  u64 mask = 0;
+  if (D.FR <= 64) { for (int k = D.adm_use_start[a]; k < D.adm_use_start[a + 1]; k++) mask |= 1ull << D.adm_use_fr[k]; }
+  else mask = ~0ull;
+  FrRec r;
+  r.adm = a; r.hcq = h; r.prio = D.adm_priority[a];
+  r.info = (D.adm_evicted[a] ? 1u : 0u) | ((uint32_t)D.depth[cq] << 1);
+  r.qty = (i64)mask; r.tin = D.nd_tin[D.slot_base[slot] + h]; r.cq = cq;
+  D.rrec[i] = r;
+}
 
 // ---------------------------------------------------------------------------
 // Column arithmetic on a private copy of one flavor-resource column (resource_node.go).
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ ColStat ld_stat(const ColStat *s, int h) {
-  const int4 *p = reinterpret_cast<const int4 *>(s + h);
-  int4 a = __ldg(p), b = __ldg(p + 1);
+  const int4 *p = reinterpret_cast<const int4 *>(s + h);  // generic loads: the column may sit in shared memory
+  int4 a = p[0], b = p[1];
   ColStat st;
   st.sub = ((i64)(unsigned)a.y << 32) | (unsigned)a.x; st.lq = ((i64)(unsigned)a.w << 32) | (unsigned)a.z;
   st.bl = ((i64)(unsigned)b.y << 32) | (unsigned)b.x; st.parent = b.z;
@@ -243,6 +264,11 @@ struct WScratch {
   uint8_t *codes;      // [>= list length] (segment, variant) code per candidate
   int32_t *tgt;        // [>= list length] targets of the current search
   uint8_t *tgt_reason;
+  i64 *tgtq = nullptr; // [>= bucket length] quantity of every target in the searched cell (single-column searches)
+  // single-column searches of a CTA bound to one (root, flavor-resource) bucket: that column's static cell records
+  // and cycle-start usage staged once in shared memory (nullptr: read the global tables)
+  const ColStat *stat0 = nullptr;
+  const i64 *base0 = nullptr;
 };
 
 __device__ __forceinline__ bool ws_satisfies_policy(const DevSnap &D, int pre_prio, i64 pre_ts, int a, int cp, int policy) {  // preemption_policy.go:30-48
@@ -286,11 +312,11 @@ __device__ inline int ws_classical(const DevSnap &D, WCtx<KMAX> *w, const WScrat
     bool on = j < K;
     myfr[s] = on ? w->tfr[j] : 0; myflag[s] = on ? w->tflag[j] : 0;
     mycol[s] = S.col + (size_t)(on ? j : 0) * nn;
-    mys[s] = D.colS + cbase + (size_t)myfr[s] * nn;
+    mys[s] = (S.stat0 && K == 1) ? S.stat0 : D.colS + cbase + (size_t)myfr[s] * nn;
   }
   // ---- 1. preemptor path (lane 0), Euler intervals of the path nodes
   if (lane == 0) {
-    const ColStat *s0 = D.colS + cbase + (size_t)w->tfr[0] * nn;
+    const ColStat *s0 = (S.stat0 && K == 1) ? S.stat0 : D.colS + cbase + (size_t)w->tfr[0] * nn;
     int pl = 0;
     for (int t = hcq; t >= 0; t = ld_stat(s0, t).parent) {
       w->path[pl] = t; w->ptin[pl] = D.nd_tin[nbase + t]; w->ptout[pl] = D.nd_tout[nbase + t]; pl++;
@@ -300,14 +326,16 @@ __device__ inline int ws_classical(const DevSnap &D, WCtx<KMAX> *w, const WScrat
   // ---- 2. private columns <- cycle-start usage
   auto load_columns = [&]() {
     for (int j = 0; j < K; j++) {
-      const i64 *src = D.colU + cbase + (size_t)w->tfr[j] * nn;
+      const i64 *src = (S.base0 && K == 1) ? S.base0 : D.colU + cbase + (size_t)w->tfr[j] * nn;
       i64 *dst = S.col + (size_t)j * nn;
       for (int h = lane; h < nn; h += 32) dst[h] = src[h];
     }
     __syncwarp();
   };
   __syncwarp();
+  long long t0 = clock64();
   load_columns();
+  long long t1 = clock64();
   const int plen = w->plen;
   const int *path = w->path;
   // ---- 3. hierarchical advantage per path level (collectCandidatesForHierarchicalReclaim :151-177,
@@ -348,62 +376,88 @@ __device__ inline int ws_classical(const DevSnap &D, WCtx<KMAX> *w, const WScrat
   const bool forbidden = D.cq_borrow_within[cq] == KB_POLICY_NEVER;  // IsBorrowingWithinCohortForbidden :72-78
   const bool has_thr = D.cq_has_bwc_threshold[cq]; const int thr = D.cq_bwc_threshold[cq];
   unsigned present = 0;  // bit seg: the segment has a candidate
-  for (int i0 = 0; i0 < list_len; i0 += 32) {
-    int i = i0 + lane;
-    uint8_t code = 0xff;
-    if (i < list_len) {
-      int a, h, cp, depth, tin; uint32_t ovmask; bool evicted, uses;
-      if (single) {
-        const int4 *rp = reinterpret_cast<const int4 *>(D.frl + list_off + i);
-        int4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
-        a = r0.x; h = r0.y; cp = r0.z; uint32_t info = (uint32_t)r0.w;
-        evicted = info & 1; depth = (info >> 1) & 31; ovmask = info >> 8; tin = r1.z; uses = true;
-      } else {
-        a = D.adm_sorted[list_off + i];
-        int acq = D.adm_cq[a];
-        h = D.local_idx[acq]; cp = D.adm_priority[a]; evicted = D.adm_evicted[a];
-        depth = D.depth[acq]; tin = D.nd_tin[nbase + h];
-        uses = false;  // WorkloadUsesResources candidate_generator.go:52-61
-        for (int k = D.adm_use_start[a]; k < D.adm_use_start[a + 1]; k++) { int fr = D.adm_use_fr[k]; if ((w->need_bits[fr >> 5] >> (fr & 31)) & 1) uses = true; }
-        ovmask = 0;
-        if (uses && h != hcq)
-          for (int j = 0; j < K; j++) if (w->tflag[j] & TC_NEED) ovmask |= D.ovm[cbase + (size_t)w->tfr[j] * nn + h];
-      }
-      if (uses) {
-        bool same = h == hcq;
-        if (same ? own_cands : cohort_cands) {
-          if (ws_satisfies_policy(D, prio, ts, a, cp, same ? pol_within : pol_reclaim)) {  // classifyPreemptionVariant :82-114
-            int variant = PV_NEVER, cls = 0;
-            if (same) { variant = PV_WITHIN_CQ; cls = 2; }
-            else if ((ovmask >> depth) & 1) {  // the ClusterQueue is above nominal in a cell needing preemption
-              int lvl = plen - 1;              // lowest common ancestor with the preemptor's path
-              for (int k = 1; k < plen; k++) if (tin >= w->ptin[k] && tin < w->ptout[k]) { lvl = k; break; }
-              int dt = plen - 1 - lvl;         // depth of that ancestor; cohorts strictly between must be above nominal too
-              uint32_t chain = ((1u << depth) - 1u) & ~((1u << (dt + 1)) - 1u);
-              if ((ovmask & chain) == chain) {
-                bool hier = w->adv[lvl];
-                cls = hier ? 0 : 1;
-                if (hier) variant = PV_HIER_RECLAIM;
-                else if (forbidden) variant = PV_RECLAIM_NO_BORROW;
-                else {
-                  bool above;  // isAboveBorrowingThreshold :116-124
-                  if (cp >= prio) above = true;
-                  else if (!has_thr) above = false;
-                  else above = cp > thr;
-                  variant = above ? PV_RECLAIM_NO_BORROW : PV_RECLAIM_WHILE_BORROW;
-                }
-              }
-            }
-            if (variant != PV_NEVER) { int seg = (evicted ? 0 : 3) + cls; code = (uint8_t)(seg * 8 + variant); present |= 1u << seg; }
-          }
-        }
-      }
-      S.codes[i] = code;
-    }
+  // Candidates are streamed as 32 B records in rank order (evicted first, then priority ascending): two batches of
+  // 32 in flight per step.  No candidate above `pmax` can satisfy either preemption policy
+  // (preemption_policy.go:30-48), so the stream ends at the first non-evicted batch that starts above it.
+  long long pmax = LLONG_MIN;
+  {
+    auto cap = [&](int pol) -> long long {
+      return pol == KB_POLICY_LOWER_PRIORITY ? (long long)prio - 1 : pol == KB_POLICY_LOWER_OR_NEWER_EQUAL_PRIORITY ? (long long)prio
+             : pol == KB_POLICY_ANY ? LLONG_MAX : LLONG_MIN;
+    };
+    if (own_cands) pmax = cap(pol_within);
+    if (cohort_cands) { long long c2 = cap(pol_reclaim); if (c2 > pmax) pmax = c2; }
   }
+  const FrRec *recs = single ? D.frl + list_off : D.rrec + list_off;
+  const bool mask_exact = FR <= 64;
+  u64 need64 = 0;
+  if (!single) need64 = (u64)w->need_bits[0] | ((u64)w->need_bits[1] << 32);
+  auto classify = [&](int4 r0, int4 r1) -> int {
+    int a = r0.x, h = r0.y, cp = r0.z; uint32_t info = (uint32_t)r0.w;
+    bool evicted = info & 1; int depth = (info >> 1) & 31; int tin = r1.z;
+    uint32_t ovmask = info >> 8;
+    bool same = h == hcq;
+    if (!single) {
+      bool uses;  // WorkloadUsesResources candidate_generator.go:52-61
+      u64 um = ((u64)(unsigned)r1.y << 32) | (unsigned)r1.x;
+      if (mask_exact) uses = (um & need64) != 0;
+      else {
+        uses = false;
+        for (int k = D.adm_use_start[a]; k < D.adm_use_start[a + 1]; k++) { int fr = D.adm_use_fr[k]; if ((w->need_bits[fr >> 5] >> (fr & 31)) & 1) uses = true; }
+      }
+      if (!uses) return 0xff;
+    }
+    if (!(same ? own_cands : cohort_cands)) return 0xff;
+    if (!ws_satisfies_policy(D, prio, ts, a, cp, same ? pol_within : pol_reclaim)) return 0xff;  // classifyPreemptionVariant :82-114
+    int variant, cls;
+    if (same) { variant = PV_WITHIN_CQ; cls = 2; }
+    else {
+      if (!single) { ovmask = 0; for (int j = 0; j < K; j++) if (w->tflag[j] & TC_NEED) ovmask |= D.ovm[cbase + (size_t)w->tfr[j] * nn + h]; }
+      if (!((ovmask >> depth) & 1)) return 0xff;  // the ClusterQueue is within nominal in every cell needing preemption
+      int lvl = plen - 1;                         // lowest common ancestor with the preemptor's path
+      for (int k = 1; k < plen; k++) if (tin >= w->ptin[k] && tin < w->ptout[k]) { lvl = k; break; }
+      int dt = plen - 1 - lvl;                    // its depth; the cohorts strictly between must be above nominal too
+      uint32_t chain = ((1u << depth) - 1u) & ~((1u << (dt + 1)) - 1u);
+      if ((ovmask & chain) != chain) return 0xff;
+      bool hier = w->adv[lvl];
+      cls = hier ? 0 : 1;
+      if (hier) variant = PV_HIER_RECLAIM;
+      else if (forbidden) variant = PV_RECLAIM_NO_BORROW;
+      else {
+        bool above;  // isAboveBorrowingThreshold :116-124
+        if (cp >= prio) above = true;
+        else if (!has_thr) above = false;
+        else above = cp > thr;
+        variant = above ? PV_RECLAIM_NO_BORROW : PV_RECLAIM_WHILE_BORROW;
+      }
+    }
+    int seg = (evicted ? 0 : 3) + cls;
+    present |= 1u << seg;
+    return seg * 8 + variant;
+  };
+  int scan_len = list_len;
+  for (int i0 = 0; i0 < list_len; i0 += 64) {
+    const int ia = i0 + lane, ib = i0 + 32 + lane;
+    int4 a0 = make_int4(0, 0, 0, 0), a1 = a0, b0 = a0, b1 = a0;
+    if (ia < list_len) { const int4 *rp = reinterpret_cast<const int4 *>(recs + ia); a0 = __ldg(rp); a1 = __ldg(rp + 1); }
+    if (ib < list_len) { const int4 *rp = reinterpret_cast<const int4 *>(recs + ib); b0 = __ldg(rp); b1 = __ldg(rp + 1); }
+    // first record of the step: not evicted and already above every admissible priority -> nothing further qualifies
+    int first_prio = __shfl_sync(FULL, a0.z, 0); unsigned first_info = (unsigned)__shfl_sync(FULL, a0.w, 0);
+    if (!(first_info & 1) && (long long)first_prio > pmax) { scan_len = i0; break; }
+    if (ia < list_len) S.codes[ia] = (uint8_t)classify(a0, a1);
+    if (ib < list_len) S.codes[ib] = (uint8_t)classify(b0, b1);
+  }
+  list_len = scan_len;
   present = __reduce_or_sync(FULL, present);
   __syncwarp();
+  long long t2 = clock64();
+  if (lane == 0) {
+    atomicAdd(&D.sstat[0], 1ull); atomicAdd(&D.sstat[1], (u64)list_len);
+    atomicAdd(&D.sstat[5], (u64)(t1 - t0)); atomicAdd(&D.sstat[6], (u64)(t2 - t1));
+    if (K > 1) atomicAdd(&D.sstat[4], 1ull);
+  }
   if (present == 0) return 0;
+  int n_visit = 0, n_removed = 0;
   // ---- 5. greedy remove / fill back (preemption.go:265-293)
   const bool no_hier = !(present & 0x09), no_other = !(present & 0x1b);
   bool under_nominal = true;  // queueUnderNominalInResourcesNeedingPreemption :577-584
@@ -431,16 +485,18 @@ __device__ inline int ws_classical(const DevSnap &D, WCtx<KMAX> *w, const WScrat
     }
     return (bool)__all_sync(FULL, ok);
   };
-  auto apply_adm = [&](int a, int h, bool remove) {  // Snapshot.RemoveWorkload / AddWorkload on the tracked columns
+  // Snapshot.RemoveWorkload / AddWorkload on the tracked columns; q0 >= 0: the quantity in column 0 is already known
+  // (single-column searches carry it in the bucket record)
+  auto apply_adm = [&](int a, int h, bool remove, i64 q0 = -1) {
 #pragma unroll
     for (int s = 0; s < KPL; s++) {
       if (!myflag[s]) continue;
-      i64 q = adm_qty(D, a, myfr[s]);
+      i64 q = (q0 >= 0 && s == 0 && K == 1) ? q0 : adm_qty(D, a, myfr[s]);
       if (q == 0) continue;
       if (remove) col_remove(mycol[s], mys[s], h, q); else col_add(mycol[s], mys[s], h, q);
     }
   };
-  const ColStat *s0 = D.colS + cbase + (size_t)w->tfr[0] * nn;  // parent / depth of any node (identical in every column)
+  const ColStat *s0 = (S.stat0 && K == 1) ? S.stat0 : D.colS + cbase + (size_t)w->tfr[0] * nn;  // parent / depth of any node (identical in every column)
   int nt = 0; bool found = false;
   for (int oi = 0; oi < nopts && !found; oi++) {
     const bool borrow = opts[oi];
@@ -452,14 +508,22 @@ __device__ inline int ws_classical(const DevSnap &D, WCtx<KMAX> *w, const WScrat
       for (int i0 = 0; i0 < list_len && !found; i0 += 32) {
         int cur = nxt;
         nxt = (i0 + 32 + lane < list_len) ? S.codes[i0 + 32 + lane] : 0xff;
-        unsigned m = __ballot_sync(FULL, cur != 0xff && (cur >> 3) == seg);
+        const bool mine = cur != 0xff && (cur >> 3) == seg;
+        unsigned m = __ballot_sync(FULL, mine);
+        if (!m) continue;
+        // the records of every candidate of this step in one coalesced load; the ordered walk below reads them by shuffle
+        int my_a = 0, my_h = 0; i64 my_q = -1;
+        if (mine) {
+          const int4 *rp = reinterpret_cast<const int4 *>(recs + i0 + lane);
+          int4 r0 = __ldg(rp); my_a = r0.x; my_h = r0.y;
+          if (single && K == 1) { int4 r1 = __ldg(rp + 1); my_q = ((i64)(unsigned)r1.y << 32) | (unsigned)r1.x; }
+        }
         while (m) {
           int src = __ffs(m) - 1; m &= m - 1;
           int v = __shfl_sync(FULL, cur, src) & 7;
-          int i = i0 + src;
-          int a, h;
-          if (single) { const int4 *rp = reinterpret_cast<const int4 *>(D.frl + list_off + i); int4 r0 = __ldg(rp); a = r0.x; h = r0.y; }
-          else { a = D.adm_sorted[list_off + i]; h = D.local_idx[D.adm_cq[a]]; }
+          n_visit++;
+          const int a = __shfl_sync(FULL, my_a, src), h = __shfl_sync(FULL, my_h, src);
+          const i64 q0 = __shfl_sync(FULL, my_q, src);
           if (h != hcq) {  // candidateIsValid candidate_generator.go:140-162
             if (borrow && v == PV_RECLAIM_NO_BORROW) continue;
             if (within_nominal(h)) continue;
@@ -473,20 +537,23 @@ __device__ inline int ws_classical(const DevSnap &D, WCtx<KMAX> *w, const WScrat
             }
             if (!valid) continue;
           }
-          apply_adm(a, h, true);
-          if (lane == 0) { S.tgt[nt] = a; S.tgt_reason[nt] = (uint8_t)variant_reason(v); }
+          apply_adm(a, h, true, q0);
+          n_removed++;
+          if (lane == 0) { S.tgt[nt] = a; S.tgt_reason[nt] = (uint8_t)variant_reason(v); if (S.tgtq && K == 1) S.tgtq[nt] = q0; }
           nt++;
           if (fits(borrow)) {
             __syncwarp();
             for (int k = nt - 2; k >= 0; k--) {  // fillBackWorkloads :295-308
               int b = S.tgt[k];
+              i64 qb = (S.tgtq && K == 1) ? S.tgtq[k] : -1;
               int hb = D.local_idx[D.adm_cq[b]];
-              apply_adm(b, hb, false);
+              apply_adm(b, hb, false, qb);
+              n_removed++;
               if (fits(borrow)) {
-                if (lane == 0) { S.tgt[k] = S.tgt[nt - 1]; S.tgt_reason[k] = S.tgt_reason[nt - 1]; }
+                if (lane == 0) { S.tgt[k] = S.tgt[nt - 1]; S.tgt_reason[k] = S.tgt_reason[nt - 1]; if (S.tgtq && K == 1) S.tgtq[k] = S.tgtq[nt - 1]; }
                 nt--;
                 __syncwarp();
-              } else apply_adm(b, hb, true);
+              } else apply_adm(b, hb, true, qb);
             }
             found = true;
             break;
@@ -496,6 +563,10 @@ __device__ inline int ws_classical(const DevSnap &D, WCtx<KMAX> *w, const WScrat
     }
   }
   __syncwarp();
+  if (lane == 0) {
+    atomicAdd(&D.sstat[2], (u64)n_visit); atomicAdd(&D.sstat[3], (u64)n_removed);
+    atomicAdd(&D.sstat[7], (u64)(clock64() - t2));
+  }
   return found ? nt : 0;
 }
 
@@ -517,7 +588,7 @@ __device__ inline int ws_simulate(const DevSnap &D, WCtx<KMAX> *w, const WScratc
   // borrow height with the targets removed (:57-63); the column is private and reloaded by the next search
   int slot = D.root_slot[cq];
   int nbase = D.slot_base[slot], nn = D.slot_base[slot + 1] - nbase;
-  const ColStat *s0 = D.colS + (size_t)nbase * D.FR + (size_t)fr * nn;
+  const ColStat *s0 = S.stat0 ? S.stat0 : D.colS + (size_t)nbase * D.FR + (size_t)fr * nn;
   int hcq = D.local_idx[cq];
   int b = 0; bool own = false;
   if (lane == 0) {

@@ -1,21 +1,27 @@
 """Drain mode: iterate scheduling cycles over a snapshot whose pending tables hold whole queues.
 
-Host-side loop around the unchanged single-cycle evaluator — the queue layer stays on the host this round
-(SURVEY §8 f1 is the device version):
+This module is the HOST DEFINITION of the drain (numpy bookkeeping around any single-cycle evaluator); the product
+path is kb_run_drain (include/kueue_b200.h), which keeps the queue layer on the device.  tests/test_drain.py runs this
+loop on the oracle and compares kb_run_drain with it cycle by cycle.
 
   * per ClusterQueue the pending workloads are ordered once by queueOrderingFunc
     (pkg/cache/queue/cluster_queue.go:636-685: priority desc, queue-order timestamp, UID);
-  * every cycle takes the current head of every ClusterQueue (queues.Heads, manager.go:770-794), runs ONE cycle
-    (`run_cycle`: the device library or, in tests, the oracle) and applies its decisions:
+  * every cycle takes the current head of every ClusterQueue (queues.Heads, manager.go:770-794), runs ONE cycle and
+    applies its decisions the way schedule() + requeueAndUpdate (scheduler.go:405-418,823-850) do:
       - Assumed: the workload leaves the queue, its Assignment.Usage is added to the ClusterQueue usage and it joins
         the admitted tables (a preemption candidate of later cycles);
-      - not admitted, StrictFIFO: it stays the head (RequeueIfNotPresent is immediate, cluster_queue.go:622-624);
-      - not admitted, BestEffortFIFO: NoFit / Preempt-without-targets go to the inadmissible set and the next workload
-        becomes the head; skipped entries (FailedAfterNomination) and pending preemptions stay (:625-629);
-  * the drain ends with the first cycle that admits nothing (evictions are asynchronous in the reference and are not
-    replayed here: a Preempting entry keeps its place and its targets stay admitted).
-
-The result is defined by this loop; parity between the device and the oracle follows cycle by cycle.
+      - every other entry keeps `LastAssignment = &assignment.LastState` (scheduler.go:494): the next attempt starts
+        after the flavors already tried (ps_tried_idx -> ps_last_tried, ClusterQueueGeneration -> wl_last_gen);
+        a Preempting entry gets LastAssignment = nil (scheduler.go:345);
+      - StrictFIFO: the entry stays the head (requeue is immediate, cluster_queue.go:622-624);
+      - BestEffortFIFO: skipped entries (FailedAfterNomination) and pending preemptions stay (immediate requeue);
+        NoFit / Preempt-without-targets entries stay when LastAssignment.PendingFlavors() (cluster_queue.go:372,
+        workload.go:163-176) and otherwise go to the inadmissible set: the next workload becomes the head;
+      - BestEffortFIFO, mode NoFit, known SchedulingHash: every queued workload of the same equivalence class moves to
+        the inadmissible set as well (handleInadmissibleHash, cluster_queue.go:408-425; scheduler.go:292-300);
+  * the drain ends with the first cycle that admits nothing (no cluster event can change the outcome after that;
+    evictions are asynchronous in the reference and are not replayed: a Preempting entry keeps its place and its
+    targets stay admitted).
 """
 from __future__ import annotations
 
@@ -67,6 +73,11 @@ def drain(snap: abi.FlatSnapshot, run_cycle: Callable[[abi.FlatSnapshot], abi.Cy
     ps_start = a["wl_ps_start"].astype(np.int64)
     ps_req = a["ps_req"].reshape(-1, R)
     res = DrainResult()
+    last_gen = a["wl_last_gen"].astype(np.int64).copy()          # LastAssignment.ClusterQueueGeneration, -1 = nil
+    last_tried = a["ps_last_tried"].reshape(-1, R).copy()         # LastAssignment.LastTriedFlavorIdx
+    shash = a.get("wl_sched_hash")
+    has_qr = a.get("wl_has_quota_reservation")
+    gone = np.zeros(snap.n_wl, bool)                              # moved to the inadmissible set by its scheduling hash
     static = {k: v for k, v in a.items() if not (k.startswith(("wl_", "ps_", "adm_")) or k in ("heads", "cq_usage"))}
     covers_pods = np.zeros(Q, bool)
     if snap.pods_resource >= 0:
@@ -84,11 +95,14 @@ def drain(snap: abi.FlatSnapshot, run_cycle: Callable[[abi.FlatSnapshot], abi.Cy
         cs.set("cq_usage", usage)
         for k, v in adm.items():
             cs.set(k, v)
-        for nm in ("wl_cq", "wl_priority", "wl_ts", "wl_uid", "wl_last_gen"):
+        for nm in ("wl_cq", "wl_priority", "wl_ts", "wl_uid"):
             cs.set(nm, a[nm][heads])
+        cs.set("wl_last_gen", last_gen[heads])
+        if has_qr is not None:
+            cs.set("wl_has_quota_reservation", has_qr[heads])
         st, rows = _csr_take(ps_start, heads)
         cs.set("wl_ps_start", st)
-        cs.set("ps_req", ps_req[rows]); cs.set("ps_last_tried", a["ps_last_tried"].reshape(-1, R)[rows])
+        cs.set("ps_req", ps_req[rows]); cs.set("ps_last_tried", last_tried[rows])
         for nm in ("ps_req_mask", "ps_count", "ps_min_count", "ps_flavor_ok"):
             cs.set(nm, a[nm][rows])
         cs.set("heads", np.arange(len(heads)))
@@ -133,11 +147,36 @@ def drain(snap: abi.FlatSnapshot, run_cycle: Callable[[abi.FlatSnapshot], abi.Cy
             adm["adm_use_start"] = np.concatenate([adm["adm_use_start"], np.asarray(new_start[1:], np.int32)])
             adm["adm_use_fr"] = np.concatenate([adm["adm_use_fr"], np.asarray(new_fr, np.int32)])
             adm["adm_use_qty"] = np.concatenate([adm["adm_use_qty"], np.asarray(new_qty, np.int64)])
-        # ---- queue movement (cluster_queue.go:609-633)
+        # ---- LastAssignment of the entries that stay pending (scheduler.go:345,494)
+        tried = np.asarray(out.ps_tried_idx).reshape(-1, R)
+        pending_flavors = np.zeros(len(heads), bool)
+        for e in range(len(heads)):
+            if ok[e]:
+                continue
+            w = int(heads[e])
+            r0, r1 = int(st[e]), int(st[e + 1])
+            if dec[e] == abi.DEC_PREEMPTING:
+                last_gen[w] = -1
+            else:
+                last_gen[w] = int(a["cq_generation"][int(a["wl_cq"][w])])
+                last_tried[int(ps_start[w]):int(ps_start[w + 1])] = tried[r0:r1]
+                pending_flavors[e] = bool((tried[r0:r1] != -1).any())
+        # ---- queue movement (cluster_queue.go:362-425,609-633)
         cqs = live
-        inadmissible = (dec == abi.DEC_NOFIT) | (dec == abi.DEC_PREEMPT_NO_TARGETS)
+        inadmissible = ((dec == abi.DEC_NOFIT) | (dec == abi.DEC_PREEMPT_NO_TARGETS)) & ~pending_flavors
         advance = ok | (inadmissible & ~strict[cqs])
+        if shash is not None:
+            for e in np.flatnonzero((dec == abi.DEC_NOFIT) & ~strict[cqs]):
+                hsh = int(shash[heads[e]])
+                if hsh == 0:
+                    continue
+                q = int(cqs[e])
+                rest = order[qstart[q] + cursor[q] + 1:qstart[q + 1]]
+                gone[rest[shash[rest] == hsh]] = True
         cursor[cqs[advance]] += 1
+        for q in cqs:  # the next head is the first queued workload that was not set aside
+            while cursor[q] < qlen[q] and gone[order[qstart[q] + cursor[q]]]:
+                cursor[q] += 1
         if n_new == 0:
             break
     res.cq_usage = usage

@@ -967,6 +967,9 @@ class Oracle {
       bool prio = s.flags & KB_F_PRIORITY_SORTING_WITHIN_COHORT;
       std::sort(order.begin(), order.end(), [&](int x, int y) {
         const Entry &a = entries[x], &b = entries[y];
+        bool aq = s.wl_has_quota_reservation && s.wl_has_quota_reservation[a.wl];  // scheduler.go:781-789
+        bool bq = s.wl_has_quota_reservation && s.wl_has_quota_reservation[b.wl];
+        if (aq != bq) return aq;
         if (a.a.borrowing != b.a.borrowing) return a.a.borrowing < b.a.borrowing;
         if (prio && s.wl_priority[a.wl] != s.wl_priority[b.wl]) return s.wl_priority[a.wl] > s.wl_priority[b.wl];
         if (s.wl_ts[a.wl] != s.wl_ts[b.wl]) return s.wl_ts[a.wl] < s.wl_ts[b.wl];
