@@ -292,6 +292,45 @@ int32_t kb_upload(kb_handle *h, const kb_snapshot *s);
 int32_t kb_cycle_resident(kb_handle *h);
 int32_t kb_download(kb_handle *h, kb_cycle_out *out);
 
+/* Drain mode: iterate scheduling cycles over a snapshot whose pending tables hold WHOLE QUEUES
+ * (s->heads / s->n_heads are ignored) until a cycle admits nothing or max_cycles is reached.  The queue layer of
+ * pkg/cache/queue runs on the device: per-ClusterQueue order by queueOrderingFunc (cluster_queue.go:636-685), one
+ * head per ClusterQueue per cycle (manager.go:770-794), and after every cycle what schedule() + requeueAndUpdate do
+ * (scheduler.go:405-418,823-850):
+ *   assumed                 -> leaves the queue; Assignment.Usage joins the ClusterQueue usage, the workload joins
+ *                              the admitted tables (QuotaReserved time = now_ns + cycle);
+ *   every other entry       -> keeps LastAssignment (tried flavor indexes + ClusterQueue generation), nil after
+ *                              issuing preemptions (scheduler.go:345);
+ *   StrictFIFO              -> stays the head (cluster_queue.go:622-624);
+ *   BestEffortFIFO          -> skipped / preempting entries stay; NoFit and Preempt-without-targets entries stay only
+ *                              while LastAssignment.PendingFlavors() (workload.go:163-176), else the next workload
+ *                              becomes the head; a NoFit head with a known wl_sched_hash also sets aside every queued
+ *                              workload of its class (handleInadmissibleHash, cluster_queue.go:408-425).
+ * Evictions are asynchronous in the reference and are not replayed: the targets of a Preempting entry stay admitted.
+ * Cycle c runs with now_ns + c.  Bit-exact with iterating kb_run_cycle under the same rules (kueue_b200/drain.py). */
+typedef struct kb_drain_out {
+  int32_t max_cycles;        /* in */
+  int32_t n_cycles;          /* out: cycles run */
+  int64_t n_decisions;       /* out: entries evaluated over all cycles */
+  int64_t n_admitted;        /* out */
+  int32_t *cycle_heads;      /* [max_cycles] entries per cycle (may be NULL) */
+  int32_t *cycle_admitted;   /* [max_cycles] admissions per cycle (may be NULL) */
+  /* per pending workload [n_wl] (each may be NULL) */
+  int32_t *wl_admit_cycle;   /* cycle that admitted it, -1 = still pending */
+  uint8_t *wl_last_decision; /* KB_DEC_* of its last evaluation, 0xff = never a head */
+  int32_t *wl_evals;         /* cycles that evaluated it */
+  /* assignment of the last evaluation, indexed like the input podset tables (may be NULL) */
+  int8_t  *ps_flavor;        /* [n_podset][R] */
+  int32_t *ps_count;         /* [n_podset] */
+  int64_t *cq_usage;         /* [n_cq][F*R] ClusterQueue usage after the drain (may be NULL) */
+  /* optional trace for parity checks: entries of every cycle in order, concatenated */
+  int32_t *trace_wl;         /* [trace_capacity] pending workload index */
+  uint8_t *trace_decision;   /* [trace_capacity] KB_DEC_* */
+  int64_t trace_capacity;
+  double gpu_ms;             /* out: device time of all cycles (kernels of the cycles + queue layer) */
+} kb_drain_out;
+int32_t kb_run_drain(kb_handle *h, const kb_snapshot *s, kb_drain_out *out);
+
 int32_t kb_get_stats(const kb_handle *h, kb_stats *out);
 int32_t kb_set_profile(kb_handle *h, int32_t on);  /* per-kernel event timing on/off */
 

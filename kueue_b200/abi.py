@@ -105,6 +105,17 @@ KERNEL_NAMES = ["k_tree", "k_lone", "k_nominate", "k_scan_roots", "k_scatter", "
                 "k_rank_admitted", "k_search_tables", "k_search_cells", "k_nominate_walk", "k_fair_prep", "k_drain", "k_tas", "-"]
 
 
+class kb_drain_out(C.Structure):
+    _fields_ = [
+        ("max_cycles", C.c_int32), ("n_cycles", C.c_int32), ("n_decisions", C.c_int64), ("n_admitted", C.c_int64),
+        ("cycle_heads", _P(C.c_int32)), ("cycle_admitted", _P(C.c_int32)),
+        ("wl_admit_cycle", _P(C.c_int32)), ("wl_last_decision", _P(C.c_uint8)), ("wl_evals", _P(C.c_int32)),
+        ("ps_flavor", _P(C.c_int8)), ("ps_count", _P(C.c_int32)), ("cq_usage", _P(C.c_int64)),
+        ("trace_wl", _P(C.c_int32)), ("trace_decision", _P(C.c_uint8)), ("trace_capacity", C.c_int64),
+        ("gpu_ms", C.c_double),
+    ]
+
+
 class kb_config(C.Structure):
     _fields_ = [("device", C.c_int32), ("reserved", C.c_int32)]
 
@@ -313,3 +324,51 @@ class TreeOut:
         s.drs_rounded = _ptr(self.drs_rounded, C.c_int64); s.drs_resource = _ptr(self.drs_resource, C.c_int32)
         s.drs_borrowing = _ptr(self.drs_borrowing, C.c_uint8)
         self.struct = s
+
+
+class DrainOut:
+    """Caller-allocated output buffers of kb_run_drain."""
+
+    def __init__(self, snap: FlatSnapshot, max_cycles: int = 10_000, trace: bool = True):
+        W, Q, R = snap.n_wl, snap.n_cq, snap.n_resource
+        self.max_cycles = max_cycles
+        self.cycle_heads = np.zeros(max_cycles, np.int32)
+        self.cycle_admitted = np.zeros(max_cycles, np.int32)
+        self.wl_admit_cycle = np.full(W, -1, np.int32)
+        self.wl_last_decision = np.full(W, 0xff, np.uint8)
+        self.wl_evals = np.zeros(W, np.int32)
+        self.ps_flavor = np.full((snap.n_podset, R), -1, np.int8)
+        self.ps_count = np.zeros(snap.n_podset, np.int32)
+        self.cq_usage = np.zeros((Q, snap.n_fr), np.int64)
+        cap = min(W * 4 + Q, min(Q, W) * max_cycles) if trace else 0
+        self.trace_wl = np.zeros(max(1, cap), np.int32)
+        self.trace_decision = np.zeros(max(1, cap), np.uint8)
+        s = kb_drain_out()
+        s.max_cycles = max_cycles
+        s.cycle_heads = _ptr(self.cycle_heads, C.c_int32); s.cycle_admitted = _ptr(self.cycle_admitted, C.c_int32)
+        s.wl_admit_cycle = _ptr(self.wl_admit_cycle, C.c_int32); s.wl_last_decision = _ptr(self.wl_last_decision, C.c_uint8)
+        s.wl_evals = _ptr(self.wl_evals, C.c_int32)
+        s.ps_flavor = _ptr(self.ps_flavor, C.c_int8); s.ps_count = _ptr(self.ps_count, C.c_int32)
+        s.cq_usage = _ptr(self.cq_usage, C.c_int64)
+        if trace:
+            s.trace_wl = _ptr(self.trace_wl, C.c_int32); s.trace_decision = _ptr(self.trace_decision, C.c_uint8)
+        s.trace_capacity = cap
+        self.struct = s
+
+    @property
+    def n_cycles(self): return int(self.struct.n_cycles)
+    @property
+    def n_decisions(self): return int(self.struct.n_decisions)
+    @property
+    def n_admitted(self): return int(self.struct.n_admitted)
+    @property
+    def gpu_ms(self): return float(self.struct.gpu_ms)
+
+    def cycles(self):
+        """[(heads, decisions)] per cycle from the trace."""
+        out, off = [], 0
+        for c in range(self.n_cycles):
+            n = int(self.cycle_heads[c])
+            out.append((self.trace_wl[off:off + n].copy(), self.trace_decision[off:off + n].copy()))
+            off += n
+        return out

@@ -66,6 +66,9 @@ struct kb_handle {
   // host-side derived topology
   std::vector<int32_t> root_slot, depth, height, tree_start, tree_nodes, tree_level, lone, cq_adm_start, cq_adm, local_idx, child_start, child_list, adm_sorted, root_adm_start, adm_rank, root_cq_start;
   std::vector<uint8_t> tree_flat;
+  // host copies of the static tables build_dynamic consults every cycle (the caller's static pointers are not read
+  // again while static_generation is unchanged)
+  std::vector<int32_t> s_parent; std::vector<uint8_t> s_within_cq, s_reclaim_within;
   std::vector<int32_t> sn_node, slot_base, nd_tin, nd_tout;
   int max_root_adm = 1;
   int max_frl_len = 1;      // longest (root, flavor-resource) candidate bucket of this cycle
@@ -74,6 +77,9 @@ struct kb_handle {
   int sa_wpb = 1, sa_grid = 1, sa_col_elems = 0, sa_codes = 0; size_t sa_smem = 0;
   int sb_wpb = 1, sb_grid = 1, sb_col_elems = 0; size_t sb_smem = 0;
   int sa_list_cap = 32, sb_list_cap = 32;
+  // kb_run_drain: capacity reserved beyond the snapshot's admitted tables, heads chosen on the device
+  size_t drain_extra_adm = 0, drain_extra_au = 0; bool drain_mode = false; bool preempt_possible = true;
+  char *drain_buf = nullptr; size_t drain_buf_cap = 0; cudaEvent_t ev_d = nullptr;
   bool sg_on = false; int sg_wpb = 1, sg_grid = 1, sg_ncap = 1; size_t sg_smem = 0;  // grouped form of k_search_cells
   // device ranking of the admitted workloads (kb_rank.cuh)
   u64 *rk_keys[2] = {nullptr, nullptr}; int32_t *rk_vals[2] = {nullptr, nullptr}; void *rk_temp = nullptr; size_t rk_temp_bytes = 0;
@@ -152,6 +158,8 @@ void kb_destroy(kb_handle *h) {
   cudaSetDevice(h->device);
   if (h->arena.base) cudaFree(h->arena.base);
   if (h->sarena.base) cudaFree(h->sarena.base);
+  if (h->drain_buf) cudaFree(h->drain_buf);
+  if (h->ev_d) cudaEventDestroy(h->ev_d);
   if (h->host_words) cudaFreeHost(h->host_words);
   if (h->stream) cudaStreamDestroy(h->stream);
   if (h->ev0) cudaEventDestroy(h->ev0);
@@ -266,6 +274,9 @@ static int32_t build_static(kb_handle *h, const kb_snapshot *s) {
   h->D.nTrees = ntrees;
   h->D.nLone = (int)h->lone.size();
   h->D.nRoots = nroots;
+  h->s_parent.assign(s->parent, s->parent + N);
+  h->s_within_cq.assign(s->cq_within_cq, s->cq_within_cq + Q);
+  h->s_reclaim_within.assign(s->cq_reclaim_within, s->cq_reclaim_within + Q);
   {  // slot-node numbering (cohort-less ClusterQueues, then the trees) and Euler-tour intervals inside every tree
     int nl = (int)h->lone.size();
     h->sn_node.assign(std::max(1, N), 0); h->nd_tin.assign(std::max(1, N), 0); h->nd_tout.assign(std::max(1, N), 1);
@@ -316,6 +327,7 @@ static int32_t build_dynamic(kb_handle *h, const kb_snapshot *s) {
   for (int a = 0; a < s->n_adm; a++) h->root_adm_start[h->root_slot[s->adm_cq[a]] + 1]++;
   h->max_root_adm = 1;
   for (int r = 0; r < nroots; r++) { h->max_root_adm = std::max(h->max_root_adm, h->root_adm_start[r + 1]); h->root_adm_start[r + 1] += h->root_adm_start[r]; }
+  h->max_root_adm += (int)h->drain_extra_adm;  // a drain may admit everything into one root
   if (h->max_root_adm >= (1 << 28)) return fail(h, KB_ERR_INVALID, "more than 2^28 admitted workloads under one root");
   {  // longest (root, flavor-resource) bucket: sizes the per-warp candidate-code scratch of the single-cell searches
     int FRn = s->n_flavor * s->n_resource;
@@ -331,20 +343,22 @@ static int32_t build_dynamic(kb_handle *h, const kb_snapshot *s) {
     }
     h->max_frl_len = 1;
     for (int32_t c : cnt) h->max_frl_len = std::max(h->max_frl_len, c);
+    h->max_frl_len += (int)h->drain_extra_adm;
     h->max_head_podsets = 1;
-    for (int i = 0; i < s->n_heads; i++) {
+    if (h->drain_mode) for (int w = 0; w < s->n_wl; w++) h->max_head_podsets = std::max(h->max_head_podsets, s->wl_ps_start[w + 1] - s->wl_ps_start[w]);
+    for (int i = 0; i < s->n_heads && !h->drain_mode; i++) {
       int w = s->heads[i];
       if (w >= 0 && w < s->n_wl) h->max_head_podsets = std::max(h->max_head_podsets, s->wl_ps_start[w + 1] - s->wl_ps_start[w]);
     }
   }
   // light bounds checks on the hot tables
-  for (int i = 0; i < s->n_heads; i++) if (s->heads[i] < 0 || s->heads[i] >= s->n_wl) return fail(h, KB_ERR_INVALID, "heads out of range");
+  for (int i = 0; i < s->n_heads && !h->drain_mode; i++) if (s->heads[i] < 0 || s->heads[i] >= s->n_wl) return fail(h, KB_ERR_INVALID, "heads out of range");
   for (int w = 0; w < s->n_wl; w++) {
     if (s->wl_cq[w] < 0 || s->wl_cq[w] >= Q) return fail(h, KB_ERR_INVALID, "wl_cq out of range");
     if (s->wl_ps_start[w + 1] < s->wl_ps_start[w]) return fail(h, KB_ERR_INVALID, "wl_ps_start not monotone");
   }
   if (s->n_wl && s->wl_ps_start[s->n_wl] != s->n_podset) return fail(h, KB_ERR_INVALID, "wl_ps_start[n_wl] != n_podset");
-  if (s->flags & KB_F_FAIR_SHARING) {  // fairSharingIterator keeps one entry per CQ (fair_sharing_iterator.go:52-54)
+  if ((s->flags & KB_F_FAIR_SHARING) && !h->drain_mode) {  // fairSharingIterator keeps one entry per CQ (fair_sharing_iterator.go:52-54)
     std::vector<char> seen(Q, 0);
     for (int i = 0; i < s->n_heads; i++) {
       int c = s->wl_cq[s->heads[i]];
@@ -356,8 +370,14 @@ static int32_t build_dynamic(kb_handle *h, const kb_snapshot *s) {
   {
     bool any = false;
     for (int q = 0; q < Q && !any; q++)
-      if (s->parent[q] < 0 && s->cq_within_cq[q] != KB_POLICY_NEVER && h->cq_adm_start[q + 1] > h->cq_adm_start[q]) any = true;
+      if (h->s_parent[q] < 0 && h->s_within_cq[q] != KB_POLICY_NEVER && h->cq_adm_start[q + 1] > h->cq_adm_start[q]) any = true;
+    if (h->drain_mode)  // admitted workloads appear during the drain
+      for (int q = 0; q < Q && !any; q++) if (h->s_parent[q] < 0 && h->s_within_cq[q] != KB_POLICY_NEVER) any = true;
     h->D.lone_fast = !any && s->n_flavor * s->n_resource <= 64;
+    // can any ClusterQueue ever have preemption candidates?  (candidates_possible, kb_kernels.cuh)
+    h->preempt_possible = false;
+    for (int q = 0; q < Q && !h->preempt_possible; q++)
+      if (h->s_within_cq[q] != KB_POLICY_NEVER || (h->s_parent[q] >= 0 && h->s_reclaim_within[q] != KB_POLICY_NEVER)) h->preempt_possible = true;
   }
   return KB_OK;
 }
@@ -377,7 +397,10 @@ static int32_t upload_impl(kb_handle *h, const kb_snapshot *s, bool sync) {
   h->uploaded = false;
   DevSnap &D = h->D;
   int Q = s->n_cq, C = s->n_cohort, N = Q + C, F = s->n_flavor, R = s->n_resource, FR = F * R;
-  size_t NF = (size_t)N * FR, P = (size_t)s->n_podset, W = (size_t)s->n_wl, A = (size_t)s->n_adm, H = (size_t)s->n_heads;
+  // A / AU are CAPACITIES (kb_run_drain grows the admitted tables on the device); A_in / AU_in what the caller passed
+  const size_t A_in = (size_t)s->n_adm, AU_in = (size_t)s->n_adm_use;
+  size_t NF = (size_t)N * FR, P = (size_t)s->n_podset, W = (size_t)s->n_wl, A = A_in + h->drain_extra_adm, H = (size_t)s->n_heads;
+  const size_t AUc = AU_in + h->drain_extra_au;
   int n_rg_fl = (s->n_rg > 0 && s->rg_flavor_start) ? s->rg_flavor_start[s->n_rg] : 0;
   int dims[6] = {Q, C, F, R, s->n_rg, n_rg_fl};
   bool reuse = s->static_generation != 0 && s->static_generation == h->static_gen && memcmp(dims, h->s_dims, sizeof(dims)) == 0;
@@ -432,7 +455,7 @@ static int32_t upload_impl(kb_handle *h, const kb_snapshot *s, bool sync) {
   need((size_t)Q * FR, 8);
   need(W, 4); need(W, 4); need(W, 8); need(W, 8); need(W, 8); need(W + 1, 4);
   need(P * R, 8); need(P, 4); need(P, 4); need(P, 4); need(P, 8); need(P * R, 1);
-  need(A, 4); need(A, 4); need(A, 8); need(A, 8); need(A, 8); need(A, 1); need(A + 1, 4); need(s->n_adm_use, 4); need(s->n_adm_use, 8);
+  need(A, 4); need(A, 4); need(A, 8); need(A, 8); need(A, 8); need(A, 1); need(A + 1, 4); need(AUc, 4); need(AUc, 8);
   need(H, 4); need(W, 1); need(W, 8);
   need(Q + 1, 4); need(A, 4); need(A, 4); need(Q, 4); need(nroots, 4);
   need(nroots + 2, 4); need(Q + 2, 4); need(A, 8); need(A, 8); need(A, 4); need(A, 4);
@@ -520,7 +543,7 @@ static int32_t upload_impl(kb_handle *h, const kb_snapshot *s, bool sync) {
   if (fair && A && !h->search_smem) need(G * ncap * FR, 8);
   // classical search tables + per-warp scratch
   const size_t nbuckets = (size_t)nroots * FR;
-  const size_t sNF = A ? NF : 1, sAU = A ? (size_t)s->n_adm_use : 1;
+  const size_t sNF = A ? NF : 1, sAU = A ? AUc : 1;
   need(A, 4); need(sNF, 8); need(sNF, sizeof(ColStat)); need(sNF, 4); need(A ? nbuckets + 1 : 1, 4); need(A ? nbuckets + 2 : 1, 4); need(sAU, sizeof(FrRec)); need(A, sizeof(FrRec));
   need(memo_items * FR, sizeof(SimMemo)); need(1, 4); need(8, 8);
   need(A ? nbuckets + 2 : 1, 4); need(A ? nbuckets + 2 : 1, 4); need(A ? nbuckets + 2 : 1, 4); need(memo_items * FR, 4); need(memo_items * FR, 4);
@@ -533,28 +556,31 @@ static int32_t upload_impl(kb_handle *h, const kb_snapshot *s, bool sync) {
   // one pinned block (kb_alloc_pinned carved by the shim): when their host span is not much larger than their
   // total size the whole span goes to the device with ONE DMA and the device tables alias into it at the same
   // offsets; otherwise every table is copied on its own.
-  struct Tab { const void *src; size_t bytes; const void **dst; };
+  struct Tab { const void *src; size_t bytes; const void **dst; size_t cap; };
   std::vector<Tab> tabs;
-#define UP(field, src, n) tabs.push_back(Tab{(const void *)(src), (size_t)(n) * sizeof(*D.field), (const void **)&D.field})
+#define UPC(field, src, n, capn) tabs.push_back(Tab{(const void *)(src), (size_t)(n) * sizeof(*D.field), (const void **)&D.field, (size_t)(capn) * sizeof(*D.field)})
+#define UP(field, src, n) UPC(field, src, n, n)
   UP(cq_usage, (const i64 *)s->cq_usage, (size_t)Q * FR);
   UP(wl_cq, s->wl_cq, W); UP(wl_priority, s->wl_priority, W); UP(wl_ts, (const i64 *)s->wl_ts, W); UP(wl_uid, (const i64 *)s->wl_uid, W);
   UP(wl_last_gen, (const i64 *)s->wl_last_gen, W); UP(wl_ps_start, s->wl_ps_start, W + 1);
   UP(ps_req, (const i64 *)s->ps_req, P * R); UP(ps_req_mask, s->ps_req_mask, P); UP(ps_count, s->ps_count, P);
   UP(ps_min_count, s->ps_min_count, P); UP(ps_flavor_ok, (const u64 *)s->ps_flavor_ok, P); UP(ps_last_tried, s->ps_last_tried, P * R);
-  UP(adm_cq, s->adm_cq, A); UP(adm_priority, s->adm_priority, A); UP(adm_ts, (const i64 *)s->adm_ts, A);
-  UP(adm_qr_ts, (const i64 *)s->adm_qr_ts, A); UP(adm_uid, (const i64 *)s->adm_uid, A); UP(adm_evicted, s->adm_evicted, A);
-  UP(adm_use_start, s->adm_use_start, A + 1); UP(adm_use_fr, s->adm_use_fr, s->n_adm_use); UP(adm_use_qty, (const i64 *)s->adm_use_qty, s->n_adm_use);
-  UP(heads, s->heads, H);
+  UPC(adm_cq, s->adm_cq, A_in, A); UPC(adm_priority, s->adm_priority, A_in, A); UPC(adm_ts, (const i64 *)s->adm_ts, A_in, A);
+  UPC(adm_qr_ts, (const i64 *)s->adm_qr_ts, A_in, A); UPC(adm_uid, (const i64 *)s->adm_uid, A_in, A); UPC(adm_evicted, s->adm_evicted, A_in, A);
+  UPC(adm_use_start, s->adm_use_start, A_in + 1, A + 1); UPC(adm_use_fr, s->adm_use_fr, AU_in, AUc); UPC(adm_use_qty, (const i64 *)s->adm_use_qty, AU_in, AUc);
+  if (!h->drain_mode) UP(heads, s->heads, H);
   D.wl_has_qr = nullptr; D.wl_sched_hash = nullptr;
   if (s->wl_has_quota_reservation) UP(wl_has_qr, s->wl_has_quota_reservation, W);
   if (s->wl_sched_hash) UP(wl_sched_hash, (const i64 *)s->wl_sched_hash, W);
   size_t caller_tabs = tabs.size();
 #undef UP
+#undef UPC
   {
     uintptr_t lo = UINTPTR_MAX, hi = 0; size_t sum = 0;
     for (size_t i = 0; i < caller_tabs; i++) {
       if (!tabs[i].bytes) continue;
       if (!tabs[i].src) return fail(h, KB_ERR_INVALID, "null table with non-zero length");
+      if (tabs[i].cap != tabs[i].bytes) continue;  // growable table: its own allocation
       lo = std::min(lo, (uintptr_t)tabs[i].src); hi = std::max(hi, (uintptr_t)tabs[i].src + tabs[i].bytes); sum += tabs[i].bytes;
     }
     uintptr_t lo_al = lo & ~(uintptr_t)255;
@@ -566,12 +592,13 @@ static int32_t upload_impl(kb_handle *h, const kb_snapshot *s, bool sync) {
     }
     for (size_t i = 0; i < tabs.size(); i++) {
       const Tab &t = tabs[i];
-      if (span && i < caller_tabs && t.bytes) { *t.dst = dspan + ((uintptr_t)t.src - lo_al); continue; }
-      char *d = h->arena.take<char>(t.bytes);
+      if (span && i < caller_tabs && t.bytes && t.cap == t.bytes) { *t.dst = dspan + ((uintptr_t)t.src - lo_al); continue; }
+      char *d = h->arena.take<char>(std::max(t.bytes, t.cap));
       *t.dst = d;
       if (t.bytes) { CUDA_TRY(h, cudaMemcpyAsync(d, t.src, t.bytes, cudaMemcpyHostToDevice, h->stream)); bytes += (int64_t)t.bytes; }
     }
   }
+  if (h->drain_mode) D.heads = h->arena.take<int32_t>(H);
   D.over_list = h->arena.take<int32_t>(Q); D.over_count = h->arena.take<int32_t>(nroots);
   D.root_adm_start = h->arena.take<int32_t>(nroots + 1); D.cq_adm_start = h->arena.take<int32_t>(Q + 1);
   D.cq_adm = h->arena.take<int32_t>(A); D.adm_rank = h->arena.take<int32_t>(A);
@@ -925,6 +952,151 @@ extern "C" int32_t kb_run_cycle(kb_handle *h, const kb_snapshot *s, kb_cycle_out
   rc = cycle_finish(h);
   if (rc != KB_OK) return rc;
   return download_finish(h, out);
+}
+
+// ---------------------------------------------------------------------------
+// kb_run_drain: iterated cycles with the queue layer on the device (kb_drain.cuh)
+// ---------------------------------------------------------------------------
+static int32_t drain_impl(kb_handle *h, const kb_snapshot *s, kb_drain_out *out) {
+  const int Q = s->n_cq, W = s->n_wl, R = s->n_resource, FR = s->n_flavor * s->n_resource;
+  const int Hcap = std::min(Q, W);
+  const int max_cycles = std::max(0, out->max_cycles);
+  out->n_cycles = 0; out->n_decisions = 0; out->n_admitted = 0; out->gpu_ms = 0;
+  if (Hcap == 0 || max_cycles == 0) return KB_OK;
+  size_t extra = (size_t)std::min<long long>((long long)W, (long long)Hcap * max_cycles);
+  h->drain_extra_adm = extra;
+  h->drain_extra_au = std::min<size_t>((size_t)s->n_podset * R, extra * (size_t)FR);
+  h->drain_mode = true;
+  kb_snapshot s2 = *s;
+  s2.n_heads = Hcap; s2.heads = nullptr;
+  int32_t rc = upload_impl(h, &s2, false);
+  if (rc != KB_OK) return rc;
+  DevSnap &D = h->D;
+  if (!h->ev_d) cudaEventCreate(&h->ev_d);
+  // ---- drain-only device buffers
+  const size_t Wz = (size_t)W, Hz = (size_t)Hcap;
+  size_t sort_bytes = 0;
+  {
+    cub::DoubleBuffer<u64> dk(nullptr, nullptr); cub::DoubleBuffer<int32_t> dv(nullptr, nullptr);
+    cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, dk, dv, W, 0, 64, h->stream);
+    sort_bytes += 256;
+  }
+  const size_t trace_cap = out->trace_wl && out->trace_decision ? (size_t)std::max<int64_t>(0, out->trace_capacity) : 0;
+  size_t tot = 0;
+  auto need = [&](size_t n, size_t sz) { tot += pad256(n * sz); };
+  need(Wz, 8); need(Wz, 8); need(Wz, 4); need(Wz, 4); need(sort_bytes, 1);
+  need((size_t)Q + 2, 4); need((size_t)Q + 2, 4); need(Q, 4); need(Wz, 1); need((size_t)Q + 2, 4); need((size_t)Q + 2, 4);
+  for (int k = 0; k < 4; k++) need(Hz + 2, 4);
+  need(16, 4); need(Wz, 4); need(Wz, 4); need(Wz, 1); need(trace_cap, 4); need(trace_cap, 1);
+  if (tot > h->drain_buf_cap) {
+    if (h->drain_buf) cudaFree(h->drain_buf);
+    h->drain_buf = nullptr; h->drain_buf_cap = 0;
+    CUDA_TRY(h, cudaMalloc(&h->drain_buf, tot + (1 << 20)));
+    h->drain_buf_cap = tot + (1 << 20);
+  }
+  size_t used = 0;
+  auto take = [&](size_t n, size_t sz) { char *p = h->drain_buf + used; used += pad256(n * sz); return p; };
+  u64 *keys[2] = {(u64 *)take(Wz, 8), (u64 *)take(Wz, 8)};
+  int32_t *vals[2] = {(int32_t *)take(Wz, 4), (int32_t *)take(Wz, 4)};
+  void *sort_tmp = take(sort_bytes, 1);
+  DrainDev X{};
+  int32_t *q_count = (int32_t *)take((size_t)Q + 2, 4);
+  X.q_start = (int32_t *)take((size_t)Q + 2, 4); X.cursor = (int32_t *)take(Q, 4); X.gone = (uint8_t *)take(Wz, 1);
+  X.flag = (int32_t *)take((size_t)Q + 2, 4); X.pos = (int32_t *)take((size_t)Q + 2, 4);
+  X.e_assumed = (int32_t *)take(Hz + 2, 4); X.e_ncells = (int32_t *)take(Hz + 2, 4);
+  X.e_adm_off = (int32_t *)take(Hz + 2, 4); X.e_cell_off = (int32_t *)take(Hz + 2, 4);
+  X.counters = (int32_t *)take(16, 4);
+  X.wl_admit_cycle = (int32_t *)take(Wz, 4); X.wl_evals = (int32_t *)take(Wz, 4); X.wl_last_decision = (uint8_t *)take(Wz, 1);
+  X.trace_wl = trace_cap ? (int32_t *)take(trace_cap, 4) : nullptr; X.trace_dec = trace_cap ? (uint8_t *)take(trace_cap, 1) : nullptr;
+  X.trace_cap = (long long)trace_cap;
+  X.cq_usage = const_cast<i64 *>(D.cq_usage); X.wl_last_gen = const_cast<i64 *>(D.wl_last_gen); X.ps_last_tried = const_cast<int8_t *>(D.ps_last_tried);
+  X.adm_cq = const_cast<int32_t *>(D.adm_cq); X.adm_priority = const_cast<int32_t *>(D.adm_priority);
+  X.adm_ts = const_cast<i64 *>(D.adm_ts); X.adm_qr_ts = const_cast<i64 *>(D.adm_qr_ts); X.adm_uid = const_cast<i64 *>(D.adm_uid);
+  X.adm_evicted = const_cast<uint8_t *>(D.adm_evicted); X.adm_use_start = const_cast<int32_t *>(D.adm_use_start);
+  X.adm_use_fr = const_cast<int32_t *>(D.adm_use_fr); X.adm_use_qty = const_cast<i64 *>(D.adm_use_qty);
+  // ---- per-ClusterQueue order (queueOrderingFunc): stable LSD passes uid -> timestamp -> (ClusterQueue | priority desc)
+  const int tb = 256, nbW = (W + tb - 1) / tb, nbQ = (Q + tb - 1) / tb;
+  CUDA_TRY(h, cudaMemsetAsync(q_count, 0, sizeof(int32_t) * ((size_t)Q + 2), h->stream));
+  {
+    cub::DoubleBuffer<u64> dk(keys[0], keys[1]); cub::DoubleBuffer<int32_t> dv(vals[0], vals[1]);
+    size_t bytes = sort_bytes;
+    k_drain_keys_uid<<<nbW, tb, 0, h->stream>>>(D, dk.Current(), dv.Current());
+    CUDA_TRY(h, cub::DeviceRadixSort::SortPairs(sort_tmp, bytes, dk, dv, W, 0, 64, h->stream));
+    k_drain_keys_ts<<<nbW, tb, 0, h->stream>>>(D, dv.Current(), dk.Current());
+    CUDA_TRY(h, cub::DeviceRadixSort::SortPairs(sort_tmp, bytes, dk, dv, W, 0, 64, h->stream));
+    k_drain_keys_cq<<<nbW, tb, 0, h->stream>>>(D, dv.Current(), dk.Current(), q_count);
+    int cq_bits = 1; while ((1ll << cq_bits) < (long long)Q) cq_bits++;
+    CUDA_TRY(h, cub::DeviceRadixSort::SortPairs(sort_tmp, bytes, dk, dv, W, 0, 32 + cq_bits, h->stream));
+    X.q_order = dv.Current();
+  }
+  k_scan_i32<<<1, 1024, 0, h->stream>>>(q_count, X.q_start, Q);
+  k_drain_init<<<std::max(nbW, nbQ), tb, 0, h->stream>>>(D, X);
+  int32_t *d_heads = const_cast<int32_t *>(D.heads);
+  auto enqueue_heads = [&]() {
+    k_drain_flag<<<nbQ, tb, 0, h->stream>>>(D, X);
+    k_scan_i32<<<1, 1024, 0, h->stream>>>(X.flag, X.pos, Q);
+    k_drain_heads<<<nbQ, tb, 0, h->stream>>>(D, X, d_heads);
+  };
+  enqueue_heads();
+  CUDA_TRY(h, cudaMemcpyAsync(&h->host_words[8], X.counters, 4, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  int n_live = (int)h->host_words[8];
+  int A_cur = s->n_adm, AU_cur = s->n_adm_use;
+  const bool pre = h->preempt_possible;
+  double gpu_ms = 0;
+  for (int cyc = 0; cyc < max_cycles && n_live > 0; cyc++) {
+    D.H = n_live; D.now_ns = s->now_ns + cyc;
+    D.A = pre ? A_cur : 0; D.AU = pre ? AU_cur : 0;  // without preemption policies the cycle never looks at the admitted tables
+    rc = cycle_enqueue(h);
+    if (rc != KB_OK) return rc;
+    X.A = A_cur; X.AU = AU_cur; X.cycle = cyc; X.trace_off = (long long)out->n_decisions;
+    const int nbH = (n_live + tb - 1) / tb;
+    k_drain_apply<<<nbH, tb, 0, h->stream>>>(D, X);
+    k_scan_i32<<<1, 1024, 0, h->stream>>>(X.e_assumed, X.e_adm_off, n_live);
+    k_scan_i32<<<1, 1024, 0, h->stream>>>(X.e_ncells, X.e_cell_off, n_live);
+    k_drain_admit<<<nbH, tb, 0, h->stream>>>(D, X, s->now_ns + cyc);
+    enqueue_heads();
+    CUDA_TRY(h, cudaEventRecord(h->ev_d, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(&h->host_words[8], X.counters, 4, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(&h->host_words[9], X.e_adm_off + n_live, 4, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(&h->host_words[10], X.e_cell_off + n_live, 4, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    rc = cycle_finish(h);
+    if (rc != KB_OK) return rc;
+    { float ms = 0; cudaEventElapsedTime(&ms, h->ev2, h->ev_d); gpu_ms += ms; }
+    int n_new = (int)h->host_words[9], n_cells = (int)h->host_words[10];
+    if (out->cycle_heads) out->cycle_heads[cyc] = n_live;
+    if (out->cycle_admitted) out->cycle_admitted[cyc] = n_new;
+    out->n_cycles = cyc + 1; out->n_decisions += n_live; out->n_admitted += n_new;
+    A_cur += n_new; AU_cur += n_cells;
+    n_live = (int)h->host_words[8];
+    if (n_new == 0) break;  // nothing admitted: the next cycle would see the same snapshot
+  }
+  out->gpu_ms = gpu_ms;
+  h->stats.last_cycle_gpu_ms = gpu_ms;
+  // ---- results
+  size_t PR = (size_t)D.P * D.R;
+  if (out->wl_admit_cycle) CUDA_TRY(h, cudaMemcpyAsync(out->wl_admit_cycle, X.wl_admit_cycle, Wz * 4, cudaMemcpyDeviceToHost, h->stream));
+  if (out->wl_last_decision) CUDA_TRY(h, cudaMemcpyAsync(out->wl_last_decision, X.wl_last_decision, Wz, cudaMemcpyDeviceToHost, h->stream));
+  if (out->wl_evals) CUDA_TRY(h, cudaMemcpyAsync(out->wl_evals, X.wl_evals, Wz * 4, cudaMemcpyDeviceToHost, h->stream));
+  if (out->ps_flavor && PR) CUDA_TRY(h, cudaMemcpyAsync(out->ps_flavor, D.ps_flavor, PR, cudaMemcpyDeviceToHost, h->stream));
+  if (out->ps_count && D.P) CUDA_TRY(h, cudaMemcpyAsync(out->ps_count, D.ps_count_out, (size_t)D.P * 4, cudaMemcpyDeviceToHost, h->stream));
+  if (out->cq_usage) CUDA_TRY(h, cudaMemcpyAsync(out->cq_usage, D.cq_usage, (size_t)Q * FR * 8, cudaMemcpyDeviceToHost, h->stream));
+  size_t nt = std::min<size_t>(trace_cap, (size_t)out->n_decisions);
+  if (nt) {
+    CUDA_TRY(h, cudaMemcpyAsync(out->trace_wl, X.trace_wl, nt * 4, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(out->trace_decision, X.trace_dec, nt, cudaMemcpyDeviceToHost, h->stream));
+  }
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  return KB_OK;
+}
+
+extern "C" int32_t kb_run_drain(kb_handle *h, const kb_snapshot *s, kb_drain_out *out) {
+  if (!h || !s || !out) return KB_ERR_INVALID;
+  int32_t rc = drain_impl(h, s, out);
+  h->drain_mode = false; h->drain_extra_adm = 0; h->drain_extra_au = 0;
+  h->uploaded = false;  // the resident snapshot was consumed (queues advanced, admitted tables grown)
+  return rc;
 }
 
 extern "C" int32_t kb_tree_eval(kb_handle *h, const kb_snapshot *s, kb_tree_out *out) {

@@ -20,6 +20,7 @@
 #include "kb_preempt.cuh"
 #include "kb_search.cuh"
 #include "kb_rank.cuh"
+#include "kb_drain.cuh"
 
 #define KB_RANK_CAP 2048  // roots up to this many entries are ordered by the all-pairs k_rank kernel
 

@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, "libkueue_b200.so")
 _LIB = None
 
 EXPORTS = ["kb_create", "kb_destroy", "kb_last_error", "kb_alloc_pinned", "kb_free_pinned", "kb_version",
-           "kb_tree_eval", "kb_run_cycle", "kb_upload", "kb_cycle_resident", "kb_download", "kb_get_stats", "kb_set_profile"]
+           "kb_tree_eval", "kb_run_cycle", "kb_run_drain", "kb_upload", "kb_cycle_resident", "kb_download", "kb_get_stats", "kb_set_profile"]
 
 
 class KueueB200Error(RuntimeError):
@@ -132,6 +132,13 @@ class Evaluator:
         s = snap.as_struct(cached=True)
         self._check(lib().kb_run_cycle(self._h, C.byref(s), C.byref(out.struct)))
         out.n_targets = out.struct.n_targets
+        return out
+
+    def run_drain(self, snap: abi.FlatSnapshot, out: "abi.DrainOut | None" = None, max_cycles: int = 10_000) -> "abi.DrainOut":
+        """kb_run_drain: iterated cycles over whole queues with the queue layer on the device."""
+        out = out or abi.DrainOut(snap, max_cycles)
+        s = snap.as_struct()
+        self._check(lib().kb_run_drain(self._h, C.byref(s), C.byref(out.struct)))
         return out
 
     def upload(self, snap: abi.FlatSnapshot):

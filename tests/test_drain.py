@@ -72,3 +72,57 @@ def test_drain_device_equals_oracle(make):
         assert np.array_equal(got.cq_usage, want.cq_usage)
     finally:
         ev.close()
+
+
+DRAIN_DEVICE_CASES = CASES + [
+    lambda: synth.make_snapshot(2, W=3000, Q=30, preemption=True, tight=1.2),                  # within-ClusterQueue preemption: admitted tables grow and are re-ranked on the device
+    lambda: synth.make_snapshot(4, W=2000, Q=100, tight=1.06),                                  # hierarchical cohorts, reclaim
+    lambda: _with_hashes(synth.make_snapshot(3, W=4000, Q=40)),                                 # scheduling-hash bulk move (BestEffortFIFO)
+]
+
+
+def _with_hashes(snap):
+    rng = np.random.default_rng(3)
+    snap.set("wl_sched_hash", rng.integers(0, 6, snap.n_wl))  # few classes, 0 = unknown
+    return snap
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("make", DRAIN_DEVICE_CASES)
+def test_kb_run_drain_equals_host_definition(make):
+    """kb_run_drain (queue layer on the device) == kueue_b200/drain.py iterating the oracle, cycle by cycle."""
+    from kueue_b200 import native
+    ev = native.Evaluator(0)
+    try:
+        snap = make()
+        cap = 40 * (snap.n_adm + snap.n_wl) + 10000
+        want = drain(snap, lambda s: oracle.run_cycle(s, cap))
+        got = ev.run_drain(snap)
+        assert got.n_cycles == want.cycles
+        cyc = got.cycles()
+        for k in range(want.cycles):
+            assert np.array_equal(cyc[k][0], want.heads[k]), k
+            assert np.array_equal(cyc[k][1], want.decisions[k]), k
+        assert np.array_equal(got.cq_usage, want.cq_usage)
+        adm = np.concatenate(want.admitted) if want.admitted else np.zeros(0, np.int64)
+        assert got.n_admitted == len(adm) and np.array_equal(np.flatnonzero(got.wl_admit_cycle >= 0), np.sort(adm))
+    finally:
+        ev.close()
+
+
+@pytest.mark.gpu
+def test_kb_run_drain_full_size_config3():
+    """cfg3 at full size: 1M pending workloads reach the device; the drain equals the iterated oracle."""
+    from kueue_b200 import native
+    ev = native.Evaluator(0)
+    try:
+        snap = synth.make_snapshot(3)
+        want = drain(snap, oracle.run_cycle, max_cycles=6)
+        got = ev.run_drain(snap, max_cycles=6)
+        assert got.n_cycles == want.cycles
+        cyc = got.cycles()
+        for k in range(want.cycles):
+            assert np.array_equal(cyc[k][0], want.heads[k]) and np.array_equal(cyc[k][1], want.decisions[k]), k
+        assert np.array_equal(got.cq_usage, want.cq_usage)
+    finally:
+        ev.close()
