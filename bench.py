@@ -75,7 +75,9 @@ def algorithmic_bytes(snap) -> dict:
             # target searches stream 32 B candidate records; the count is data dependent and reported by the library
             # (kb_stats.search_records); this entry is the per-entry floor used when the counter is absent
             "k_search_cells": wl_in + nodes, "k_nominate_walk": wl_in + wl_out + nodes,
-            "k_fair_prep": N * FR * 16 + N * R * 16, "k_drain": W * 64, "k_tas": 0, "-": 0,
+            "k_fair_prep": N * FR * 16 + N * R * 16, "k_drain": W * 64, "k_tas": 0,
+            # fused per-root cycle: nominal / limits / ClusterQueue usage in, usage out, entries in, assignments + decisions out
+            "k_cycle_root": N * FR * 40 + N * 16 + wl_in + wl_out + W * 5,
             "k_tree": N * FR * 64 + N * 16, "k_lone": N * FR * 64,
             "k_rank": W * 36, "k_scatter": W * 72, "k_scan_roots": N * 8,
             "k_admit": W * (P * R * 9 + 16) + N * FR * 40 + W * 5,
@@ -142,6 +144,32 @@ def cpu_baseline(snap, budget_s: float = 12.0):
                       f"(the reference cycle is single-goroutine, scheduler.go:468)"}
 
 
+def drain_line(ev, config: int, cpu: bool):
+    """Drain mode: kb_run_drain over the WHOLE pending set of the configuration (every pending
+    workload sits in its ClusterQueue's queue on the device), next to the host definition of the drain iterating the
+    oracle.  decisions = entries evaluated over all cycles until a cycle admits nothing."""
+    from kueue_b200 import abi, native, synth
+    snap = native.pin_snapshot(synth.make_snapshot(config))  # heads ignored: whole queues
+    out = abi.DrainOut(snap, max_cycles=1000, trace=False)
+    ev.run_drain(snap, out)  # warm (allocations, first-touch)
+    t0 = time.perf_counter()
+    ev.run_drain(snap, out)
+    wall = time.perf_counter() - t0
+    line = {"pending": snap.n_wl, "cycles": out.n_cycles, "decisions": out.n_decisions, "admitted": out.n_admitted,
+            "device_ms": out.gpu_ms, "decisions_per_s_device": out.n_decisions / (out.gpu_ms / 1e3) if out.gpu_ms else None,
+            "e2e_ms": wall * 1e3, "decisions_per_s_e2e": out.n_decisions / wall,
+            "e2e_includes": "upload of the whole snapshot from pinned host memory, per-ClusterQueue queue sort, all cycles, result download"}
+    if cpu:
+        import oracle
+        from kueue_b200.drain import drain
+        t0 = time.perf_counter()
+        ref = drain(snap, oracle.run_cycle, max_cycles=1000)
+        dt = time.perf_counter() - t0
+        line["cpu"] = {"decisions_per_s": ref.n_decisions / dt, "cycles": ref.cycles, "decisions": ref.n_decisions, "admitted": ref.n_admitted,
+                       "kind": "port", "cores": 1, "sample": f"kueue_b200/drain.py iterating the oracle: {ref.cycles} cycles in {dt:.1f} s"}
+    return line
+
+
 def run_reference(args, rank, world):
     from kueue_b200 import synth
     if rank != 0:
@@ -180,6 +208,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-drain", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -299,6 +328,8 @@ def main():
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(snap)
+        if world == 1 and args.config in (2, 3) and not args.no_drain:
+            line["drain"] = drain_line(ev, args.config, cpu=not args.no_cpu_baseline)
         print(json.dumps(line))
     ev.close()
     if world > 1:

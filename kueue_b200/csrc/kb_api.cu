@@ -80,6 +80,7 @@ struct kb_handle {
   // kb_run_drain: capacity reserved beyond the snapshot's admitted tables, heads chosen on the device
   size_t drain_extra_adm = 0, drain_extra_au = 0; bool drain_mode = false; bool preempt_possible = true;
   char *drain_buf = nullptr; size_t drain_buf_cap = 0; cudaEvent_t ev_d = nullptr;
+  bool fused_on = false; size_t fused_smem = 0; bool one_head_per_cq = false; int32_t *d_cq_entry = nullptr;
   bool sg_on = false; int sg_wpb = 1, sg_grid = 1, sg_ncap = 1; size_t sg_smem = 0;  // grouped form of k_search_cells
   // device ranking of the admitted workloads (kb_rank.cuh)
   u64 *rk_keys[2] = {nullptr, nullptr}; int32_t *rk_vals[2] = {nullptr, nullptr}; void *rk_temp = nullptr; size_t rk_temp_bytes = 0;
@@ -358,11 +359,16 @@ static int32_t build_dynamic(kb_handle *h, const kb_snapshot *s) {
     if (s->wl_ps_start[w + 1] < s->wl_ps_start[w]) return fail(h, KB_ERR_INVALID, "wl_ps_start not monotone");
   }
   if (s->n_wl && s->wl_ps_start[s->n_wl] != s->n_podset) return fail(h, KB_ERR_INVALID, "wl_ps_start[n_wl] != n_podset");
-  if ((s->flags & KB_F_FAIR_SHARING) && !h->drain_mode) {  // fairSharingIterator keeps one entry per CQ (fair_sharing_iterator.go:52-54)
+  h->one_head_per_cq = true;
+  if (!h->drain_mode) {  // fairSharingIterator keeps one entry per CQ (fair_sharing_iterator.go:52-54)
     std::vector<char> seen(Q, 0);
     for (int i = 0; i < s->n_heads; i++) {
       int c = s->wl_cq[s->heads[i]];
-      if (seen[c]) return fail(h, KB_ERR_INVALID, "fair sharing: more than one head for a ClusterQueue");
+      if (seen[c]) {
+        if (s->flags & KB_F_FAIR_SHARING) return fail(h, KB_ERR_INVALID, "fair sharing: more than one head for a ClusterQueue");
+        h->one_head_per_cq = false;
+        break;
+      }
       seen[c] = 1;
     }
   }
@@ -446,6 +452,7 @@ static int32_t upload_impl(kb_handle *h, const kb_snapshot *s, bool sync) {
   }
   rc = build_dynamic(h, s);
   if (rc != KB_OK) return rc;
+  D.tab_local = 0; D.gparent = D.parent; D.lq = nullptr; D.cq_entry = nullptr;
   D.Q = Q; D.C = C; D.N = N; D.F = F; D.R = R; D.FR = FR; D.W = s->n_wl; D.P = s->n_podset; D.A = s->n_adm;
   D.AU = s->n_adm_use; D.H = s->n_heads; D.NRG = s->n_rg; D.pods_res = s->pods_resource; D.flags = s->flags; D.now_ns = s->now_ns;
   int nroots = D.nRoots;
@@ -456,7 +463,7 @@ static int32_t upload_impl(kb_handle *h, const kb_snapshot *s, bool sync) {
   need(W, 4); need(W, 4); need(W, 8); need(W, 8); need(W, 8); need(W + 1, 4);
   need(P * R, 8); need(P, 4); need(P, 4); need(P, 4); need(P, 8); need(P * R, 1);
   need(A, 4); need(A, 4); need(A, 8); need(A, 8); need(A, 8); need(A, 1); need(A + 1, 4); need(AUc, 4); need(AUc, 8);
-  need(H, 4); need(W, 1); need(W, 8);
+  need(H, 4); need(W, 1); need(W, 8); need(Q, 4);
   need(Q + 1, 4); need(A, 4); need(A, 4); need(Q, 4); need(nroots, 4);
   need(nroots + 2, 4); need(Q + 2, 4); need(A, 8); need(A, 8); need(A, 4); need(A, 4);
   size_t rk_temp_bytes = 0;
@@ -599,6 +606,20 @@ static int32_t upload_impl(kb_handle *h, const kb_snapshot *s, bool sync) {
     }
   }
   if (h->drain_mode) D.heads = h->arena.take<int32_t>(H);
+  h->d_cq_entry = h->arena.take<int32_t>(Q); D.cq_entry = h->d_cq_entry;
+  {  // fused per-root cycle (k_cycle_root): see the kernel's header for the conditions
+    bool all_flat = true;
+    for (uint8_t f : h->tree_flat) if (!f) all_flat = false;
+    size_t nnm = (size_t)h->max_tree_nodes, tbm = nnm * FR;
+    size_t sm = 6 * tbm * 8 + 2 * nnm * R * 8 + 4 * nnm * 4 + 7 * KB_TILE * 4 + (KB_MAX_DEPTH + 2 + 4) * 4 + 32 + nnm * 32;
+    h->fused_smem = sm;
+    h->fused_on = D.nLone == 0 && D.nTrees > 0 && h->one_head_per_cq && sm <= 220 * 1024 && (A_in == 0 || !h->preempt_possible) &&
+                  (!(s->flags & KB_F_FAIR_SHARING) || all_flat) && getenv("KB_NO_FUSED") == nullptr;
+    if (h->fused_on && !h->drain_mode) {
+      CUDA_TRY(h, cudaMemsetAsync(h->d_cq_entry, 0xff, sizeof(int32_t) * (size_t)Q, h->stream));
+      if (H) k_cq_entry<<<(unsigned)((H + 255) / 256), 256, 0, h->stream>>>(D, h->d_cq_entry);
+    }
+  }
   D.over_list = h->arena.take<int32_t>(Q); D.over_count = h->arena.take<int32_t>(nroots);
   D.root_adm_start = h->arena.take<int32_t>(nroots + 1); D.cq_adm_start = h->arena.take<int32_t>(Q + 1);
   D.cq_adm = h->arena.take<int32_t>(A); D.adm_rank = h->arena.take<int32_t>(A);
@@ -621,11 +642,14 @@ static int32_t upload_impl(kb_handle *h, const kb_snapshot *s, bool sync) {
   D.borrow = h->arena.take<int32_t>(H); D.rank = h->arena.take<int32_t>(H);
   D.ps_flavor = h->arena.take<int8_t>(P * R); D.ps_res_mode = h->arena.take<int8_t>(P * R); D.ps_tried = h->arena.take<int8_t>(P * R);
   D.ps_count_out = h->arena.take<int32_t>(P);
-  D.status = h->arena.take<uint32_t>(1);
-  D.ps_list = h->arena.take<int32_t>(H); D.ps_n = h->arena.take<int32_t>(2); D.ps_cursor = D.ps_n + 1;
+  {  // cycle header block, cleared by one memset per cycle: [0] status, [2..3] ps_n / ps_cursor, [4] target pool cursor, [8..23] search counters
+    uint32_t *hdr = h->arena.take<uint32_t>(32);
+    D.status = hdr; D.ps_n = (int32_t *)(hdr + 2); D.ps_cursor = D.ps_n + 1; D.tgt_pool_used = (int32_t *)(hdr + 4); D.sstat = (u64 *)(hdr + 8);
+  }
+  D.ps_list = h->arena.take<int32_t>(H);
   D.tgt_off = h->arena.take<int32_t>(H); D.tgt_cnt = h->arena.take<int32_t>(H);
   D.tgt_pool_adm = h->arena.take<int32_t>(pool_cap); D.tgt_pool_reason = h->arena.take<uint8_t>(pool_cap);
-  D.tgt_pool_used = h->arena.take<int32_t>(1); D.tgt_pool_cap = (int)pool_cap;
+  D.tgt_pool_cap = (int)pool_cap;
   D.preempted = h->arena.take<uint8_t>(A);
   D.usage_shadow = h->arena.take<i64>(A ? NF : 1);
   D.sc_cand = h->arena.take<int32_t>(G * acap); D.sc_tgt = h->arena.take<int32_t>(G * acap); D.sc_cq_lca = h->arena.take<int32_t>(G * ncap);
@@ -638,7 +662,7 @@ static int32_t upload_impl(kb_handle *h, const kb_snapshot *s, bool sync) {
   D.frl_count = h->arena.take<int32_t>(A ? nbuckets + 1 : 1); D.frl_start = h->arena.take<int32_t>(A ? nbuckets + 2 : 1);
   D.frl = h->arena.take<FrRec>(sAU); D.rrec = h->arena.take<FrRec>(A);
   D.memo = h->arena.take<SimMemo>(memo_items * FR); D.memo_items = (int)memo_items;
-  D.cell_cursor = h->arena.take<int32_t>(1); D.sstat = h->arena.take<u64>(8);
+  D.cell_cursor = h->arena.take<int32_t>(1);
   D.cell_count = h->arena.take<int32_t>(A ? nbuckets + 2 : 1); D.cell_start = h->arena.take<int32_t>(A ? nbuckets + 2 : 1);
   D.cell_fill = h->arena.take<int32_t>(A ? nbuckets + 2 : 1);
   D.cell_list = h->arena.take<int32_t>(memo_items * FR); D.cell_bucket = h->arena.take<int32_t>(memo_items * FR);
@@ -751,14 +775,13 @@ static int32_t cycle_enqueue(kb_handle *h) {
   DevSnap &D = h->D;
   int launches = 0;
   CUDA_TRY(h, cudaEventRecord(h->ev2, h->stream));
-  CUDA_TRY(h, cudaMemsetAsync(D.status, 0, 4, h->stream));
-  CUDA_TRY(h, cudaMemsetAsync(D.sstat, 0, 64, h->stream));
-  CUDA_TRY(h, cudaMemsetAsync(D.root_count, 0, sizeof(int32_t) * (size_t)std::max(1, D.nRoots), h->stream));
-  CUDA_TRY(h, cudaMemsetAsync(D.ps_n, 0, 8, h->stream));
-  CUDA_TRY(h, cudaMemsetAsync(D.tgt_pool_used, 0, 4, h->stream));
+  // cycle header (status word, deferred-entry counters, target pool cursor, search counters): one contiguous block
+  CUDA_TRY(h, cudaMemsetAsync(D.status, 0, 128, h->stream));
+  if (!(h->fused_on && D.H)) CUDA_TRY(h, cudaMemsetAsync(D.root_count, 0, sizeof(int32_t) * (size_t)std::max(1, D.nRoots), h->stream));
   if (D.A) CUDA_TRY(h, cudaMemsetAsync(D.preempted, 0, (size_t)D.A, h->stream));
   h->kev_n = 0;
   int32_t rc_admit = KB_OK;
+  if (D.A && !h->preempt_possible) { D.A = 0; D.AU = 0; }  // no ClusterQueue can ever preempt: the cycle never looks at the admitted tables
   if (D.A) {  // rank the admitted workloads (kb_rank.cuh): stable LSD passes UID -> reservation time -> (root | evicted | priority)
     kmark(h, KB_K_RANKADM);
     const int A = D.A, tb = 256, nb = (A + tb - 1) / tb;
@@ -786,6 +809,15 @@ static int32_t cycle_enqueue(kb_handle *h) {
     k_scan_i32<<<1, 1024, 0, h->stream>>>(D.cq_adm_count, D.cq_adm_start, D.Q); launches++;
     launches += 8;  // radix-sort passes (cub): histogram + onesweep kernels, counted coarsely
   }
+  if (h->fused_on && D.H) {
+    if (h->drain_mode) {
+      CUDA_TRY(h, cudaMemsetAsync(h->d_cq_entry, 0xff, sizeof(int32_t) * (size_t)D.Q, h->stream));
+      k_cq_entry<<<(D.H + 255) / 256, 256, 0, h->stream>>>(D, h->d_cq_entry); launches++;
+    }
+    kmark(h, KB_K_CYCLE_ROOT);
+    CUDA_TRY(h, cudaFuncSetAttribute(k_cycle_root, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+    k_cycle_root<<<D.nTrees, KB_ROOT_THREADS, h->fused_smem, h->stream>>>(D); launches++;
+  } else {
   launch_tree(h, &launches);
   if (D.H) {
     kmark(h, KB_K_NOMINATE);
@@ -842,6 +874,7 @@ static int32_t cycle_enqueue(kb_handle *h) {
     kmark(h, KB_K_RANK); k_rank<<<(D.H + 255) / 256, 256, 0, h->stream>>>(D); launches++;
     kmark(h, KB_K_ADMIT);
     rc_admit = launch_admit(h, &launches);
+  }
   }
   kmark(h, -1);
   CUDA_TRY(h, cudaEventRecord(h->ev3, h->stream));

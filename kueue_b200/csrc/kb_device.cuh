@@ -67,6 +67,14 @@ struct DevSnap {
   const int32_t *adm_use_start, *adm_use_fr;
   const i64 *adm_use_qty;
   const int32_t *heads;
+  // Node-table index space.  Normally the node tables (nominal .. potential, parent, height, fs_*) are indexed by
+  // the global node id.  The fused per-root kernel (k_cycle_root) passes a copy of this struct whose node tables
+  // live in shared memory and are indexed by the LOCAL handle inside the root's tree: tab_local = 1, and every
+  // function that takes a global node id maps it with nix().  gparent is always the global parent table.
+  int tab_local;
+  const int32_t *gparent;
+  const i64 *lq;              // localQuota per cell when precomputed (tab_local), else nullptr
+  const int32_t *cq_entry;    // [Q] entry (position in heads) of the ClusterQueue's single head, or -1 (k_cycle_root)
   const uint8_t *wl_has_qr;    // optional (nullptr = absent): workload.HasQuotaReservation
   const i64 *wl_sched_hash;    // optional: scheduling equivalence class, 0 = unknown (drain only)
   // ---- derived, static per topology (host-built at upload) ----
@@ -163,19 +171,22 @@ __device__ __forceinline__ i64 local_quota(i64 subtree, i64 lend_limit) {
 
 // FindHeightOfLowestSubtreeThatFits hierarchical_preemption.go:214-227, on the
 // cycle-start usage.  Returns the borrow height; *may_reclaim = second result.
+__device__ __forceinline__ int nix(const DevSnap &D, int node) { return D.tab_local ? D.local_idx[node] : node; }
+__device__ __forceinline__ i64 lq_of(const DevSnap &D, size_t c) { return D.lq ? D.lq[c] : local_quota(D.subtree[c], D.llimit[c]); }
 __device__ inline int find_height(const DevSnap &D, const i64 *usage, int cq, int fr, i64 val, bool *may_reclaim) {
   int FR = D.FR;
-  int p = D.parent[cq];
-  size_t c = (size_t)cq * FR + fr;
+  int hq = nix(D, cq);
+  int p = D.parent[hq];
+  size_t c = (size_t)hq * FR + fr;
   i64 ucq = usage[c];
   if (!(ucq + val > D.nominal[c]) || p < 0) { *may_reclaim = p >= 0; return 0; }
-  i64 remaining = val - imax(0, local_quota(D.subtree[c], D.llimit[c]) - ucq);
+  i64 remaining = val - imax(0, lq_of(D, c) - ucq);
   int t = p, last = p;
   while (t >= 0) {
     size_t i = (size_t)t * FR + fr;
     i64 u = usage[i], sub = D.subtree[i];
     if (!(u + remaining > sub)) { *may_reclaim = D.parent[t] >= 0; return D.height[t]; }
-    remaining -= imax(0, local_quota(sub, D.llimit[i]) - u);
+    remaining -= imax(0, lq_of(D, i) - u);
     last = t;
     t = D.parent[t];
   }

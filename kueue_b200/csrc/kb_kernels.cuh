@@ -181,7 +181,7 @@ __device__ __forceinline__ i64 ps_request(const DevSnap &D, int row, int r, int 
 __device__ __forceinline__ bool candidates_possible(const DevSnap &D, int cq) {
   int own_n = D.cq_adm_start[cq + 1] - D.cq_adm_start[cq];
   if (D.cq_within_cq[cq] != KB_POLICY_NEVER && own_n > 0) return true;
-  if (D.parent[cq] >= 0 && D.cq_reclaim_within[cq] != KB_POLICY_NEVER) {
+  if (D.gparent[cq] >= 0 && D.cq_reclaim_within[cq] != KB_POLICY_NEVER) {
     int slot = D.root_slot[cq];
     if (D.root_adm_start[slot + 1] - D.root_adm_start[slot] - own_n > 0) return true;
   }
@@ -207,7 +207,7 @@ struct NomThread {
 // fitsResourceQuota :1017-1047
 template <typename Oracle>
 __device__ inline int fits_resource_quota(const DevSnap &D, Oracle &orc, int wl, int cq, int fr, i64 assumed, i64 request, int *borrow) {
-  size_t c = (size_t)cq * D.FR + fr;
+  size_t c = (size_t)nix(D, cq) * D.FR + fr;
   i64 avail = imax(0, D.avail[c]);
   i64 val = assumed + request;
   if (val > D.potential[c]) { *borrow = 0; return PM_NOFIT; }
@@ -400,7 +400,7 @@ enum { PM_NEED = 5 };
 
 // fitsResourceQuota :1017-1047 without the oracle call: PM_NEED where SimulatePreemption would run.
 __device__ __forceinline__ int cell_eval(const DevSnap &D, int cq, int fr, i64 assumed, i64 request, int *borrow) {
-  size_t c = (size_t)cq * D.FR + fr;
+  size_t c = (size_t)nix(D, cq) * D.FR + fr;
   i64 avail = imax(0, D.avail[c]);
   i64 val = assumed + request;
   if (val > D.potential[c]) { *borrow = 0; return PM_NOFIT; }
@@ -1064,7 +1064,8 @@ __device__ inline void compute_entry_key(const DevSnap &D, int e, u64 *k) {
   unsigned prio = 0;
   if (D.flags & KB_F_PRIORITY_SORTING_WITHIN_COHORT) prio = ~((unsigned)D.wl_priority[wl] ^ 0x80000000u);  // signed priority, descending
   u64 ts = (u64)D.wl_ts[wl] ^ 0x8000000000000000ull;
-  int P = D.parent[cq];
+  const int hq = nix(D, cq);
+  int P = D.parent[hq];
   bool fair_flat = (D.flags & KB_F_FAIR_SHARING) && P >= 0 && D.tree_flat[D.root_slot[cq] - D.nLone];
   if (!fair_flat) {
     // workloads that already hold a quota reservation (second pass) first: scheduler.go:781-789
@@ -1079,7 +1080,7 @@ __device__ inline void compute_entry_key(const DevSnap &D, int e, u64 *k) {
   bool covers_pods = D.pods_res >= 0 && rg_by_resource(D, cq, D.pods_res) >= 0;
   double best = 0.0;
   for (int r = 0; r < R; r++) {
-    i64 b = D.fs_over[(size_t)cq * R + r];
+    i64 b = D.fs_over[(size_t)hq * R + r];
     // flavors this entry uses for resource r (aggregated over its podsets)
     int ps0 = D.wl_ps_start[wl], ps1 = D.wl_ps_start[wl + 1];
     for (int row = ps0; row < ps1; row++) {
@@ -1091,7 +1092,7 @@ __device__ inline void compute_entry_key(const DevSnap &D, int e, u64 *k) {
       i64 q = 0;
       for (int prow = row; prow < ps1; prow++)
         if (D.ps_flavor[(size_t)prow * R + r] == f) q += ps_request(D, prow, r, D.ps_count_out[prow], covers_pods);
-      size_t c = (size_t)cq * FR + (size_t)f * R + r;
+      size_t c = (size_t)hq * FR + (size_t)f * R + r;
       i64 base = D.usage[c] - D.subtree[c];
       b += imax(0, base + (q > 0 ? q : 0)) - imax(0, base);
     }
@@ -1647,6 +1648,336 @@ __global__ void __launch_bounds__(KB_ADMIT_THREADS) k_admit(DevSnap D, int slot_
     }
   }
   publish_usage<kSmemTables>(D, T, nodes, nn);
+}
+
+// ---------------------------------------------------------------------------
+// Fused cycle, one CTA per root cohort (k_cycle_root): tree pass -> nominate -> iterator order -> admit loop with
+// the root's quota tables in shared memory from the first load to the last store.  Root cohorts are independent
+// coupling domains (resource_node.go:106-108), so the whole cycle of one root needs no other CTA: the node tables
+// leave HBM once (nominal / limits / ClusterQueue usage in, final usage out) instead of once per kernel of the chain
+// k_tree -> k_nominate -> k_fair_prep -> k_scan_roots -> k_scatter -> k_rank -> k_admit.
+// Used when no entry can need a target search (no admitted workloads), every ClusterQueue has a cohort and at most
+// one head, the tables of the largest tree fit shared memory, and fair sharing only meets flat cohorts.
+// All node tables are indexed by the local handle (DevSnap::tab_local).
+// ---------------------------------------------------------------------------
+#define KB_ROOT_THREADS 1024
+__global__ void __launch_bounds__(KB_ROOT_THREADS) k_cycle_root(DevSnap D) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int FR = D.FR, R = D.R, Fn = D.F;
+  const int t = blockIdx.x;
+  long long tk0 = clock64();
+#define KB_PHASE(k) do { if (blockIdx.x == 0 && threadIdx.x == 0) { long long now = clock64(); D.sstat[k] = (u64)(now - tk0); tk0 = now; } } while (0)
+  const int32_t *nodes = D.tree_nodes + D.tree_start[t];
+  const int nn = D.tree_start[t + 1] - D.tree_start[t];
+  const int32_t *lvl = D.tree_level + (size_t)t * KB_LEVELS;
+  int nlev = 0;
+  while (nlev + 1 < KB_LEVELS && lvl[nlev + 1] > lvl[nlev]) nlev++;
+  const size_t tb = (size_t)nn * FR;
+  // ---- shared memory: [usage][sub][lq][bl][avail | request tile][potential][fs_over][fs_lend][parent][height][entries...]
+  i64 *s_u = (i64 *)smem_raw, *s_sub = s_u + tb, *s_lq = s_sub + tb, *s_bl = s_lq + tb, *s_av = s_bl + tb, *s_pot = s_av + tb;
+  i64 *s_over = s_pot + tb, *s_lend = s_over + (size_t)nn * R;
+  int *s_par = (int *)(s_lend + (size_t)nn * R), *s_hgt = s_par + nn;
+  int *s_ent = s_hgt + nn;           // [nn] entries of the root in ClusterQueue order
+  int *s_sorted = s_ent + nn;        // [nn] entries in iterator order
+  int *t_e = s_sorted + nn, *t_node = t_e + KB_TILE, *t_mode = t_node + KB_TILE, *t_borrow = t_mode + KB_TILE;
+  int *t_cq = t_borrow + KB_TILE, *t_ntg = t_cq + KB_TILE, *t_toff = t_ntg + KB_TILE;
+  int *s_path = t_toff + KB_TILE;
+  int *s_misc = s_path + KB_MAX_DEPTH + 2;  // [0] shadow_on, [1] n entries
+  u64 *s_key = (u64 *)(((uintptr_t)(s_misc + 4) + 15) & ~(uintptr_t)15);  // [nn][4]
+  // ---- 1. stage: SubtreeQuota = Nominal, Usage = ClusterQueue usage | 0 (updateCohortResourceNode :184-190)
+  for (int i = threadIdx.x; i < (int)tb; i += blockDim.x) {
+    int nd = nodes[i / FR], fr = i % FR;
+    size_t c = (size_t)nd * FR + fr;
+    s_sub[i] = D.nominal[c];
+    s_u[i] = nd < D.Q ? D.cq_usage[c] : 0;
+    s_bl[i] = D.blimit[c];
+    s_lq[i] = D.llimit[c];  // lending limit for now; turned into localQuota once SubtreeQuota is final
+  }
+  for (int i = threadIdx.x; i < nn; i += blockDim.x) {
+    int nd = nodes[i], pn = D.parent[nd];
+    s_par[i] = pn < 0 ? -1 : D.local_idx[pn]; s_hgt[i] = D.height[nd];
+  }
+  if (threadIdx.x == 0) { s_misc[0] = 0; s_misc[1] = 0; }
+  __syncthreads();
+  KB_PHASE(0);
+  // ---- 2. bottom-up accumulateFromChild :210-217 (deepest level first), then localQuota, then available top-down
+  if (nlev == 2) {
+    // flat cohort: every other node is a child of the root -> one warp per column sums its children (no atomics
+    // on the ~100-way contended root cells)
+    const int lane_ = threadIdx.x & 31, warp_ = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int fr = warp_; fr < FR; fr += nw) {
+      i64 dsub = 0, dus = 0;
+      for (int h = 1 + lane_; h < nn; h += 32) {
+        int c = h * FR + fr;
+        i64 sub = s_sub[c];
+        i64 lq = local_quota(sub, s_lq[c]);
+        dsub += sub - lq;
+        dus += imax(0, s_u[c] - lq);
+      }
+      for (int o = 16; o > 0; o >>= 1) { dsub += __shfl_xor_sync(0xffffffffu, dsub, o); dus += __shfl_xor_sync(0xffffffffu, dus, o); }
+      if (lane_ == 0) { s_sub[fr] += dsub; s_u[fr] += dus; }
+    }
+    __syncthreads();
+  } else
+  for (int L = nlev - 1; L >= 1; L--) {
+    int a = lvl[L], b = lvl[L + 1];
+    for (int i = threadIdx.x; i < (b - a) * FR; i += blockDim.x) {
+      int h = a + i / FR, fr = i % FR;
+      int c = h * FR + fr, pc = s_par[h] * FR + fr;
+      i64 sub = s_sub[c];
+      i64 lq = local_quota(sub, s_lq[c]);
+      atomicAdd((u64 *)&s_sub[pc], (u64)(sub - lq));
+      i64 spill = imax(0, s_u[c] - lq);
+      if (spill) atomicAdd((u64 *)&s_u[pc], (u64)spill);
+    }
+    __syncthreads();
+  }
+  for (int i = threadIdx.x; i < (int)tb; i += blockDim.x) s_lq[i] = local_quota(s_sub[i], s_lq[i]);
+  __syncthreads();
+  for (int L = 0; L < nlev; L++) {
+    int a = lvl[L], b = lvl[L + 1];
+    for (int i = threadIdx.x; i < (b - a) * FR; i += blockDim.x) {
+      int h = a + i / FR, fr = i % FR;
+      int c = h * FR + fr;
+      i64 sub = s_sub[c], u = s_u[c];
+      if (L == 0) { s_av[c] = sub - u; s_pot[c] = sub; }
+      else {
+        int pc = s_par[h] * FR + fr;
+        i64 lq = s_lq[c], bl = s_bl[c];
+        i64 pa = s_av[pc], pot = lq + s_pot[pc];
+        if (bl != KB_NO_LIMIT) { pa = imin((sub - lq) - imax(0, u - lq) + bl, pa); pot = imin(sub + bl, pot); }
+        s_av[c] = imax(0, lq - u) + pa;
+        s_pot[c] = pot;
+      }
+    }
+    __syncthreads();
+  }
+  KB_PHASE(1);
+  // ---- 3. fair sharing inputs (k_fair_prep): over-usage per (ClusterQueue, resource), lendable per (node, resource)
+  const bool fair = D.flags & KB_F_FAIR_SHARING;
+  if (fair) {
+    for (int i = threadIdx.x; i < nn * R; i += blockDim.x) {
+      int h = i / R, r = i % R;
+      i64 over = 0, lend = 0;
+      for (int f = 0; f < Fn; f++) {
+        int c = h * FR + f * R + r;
+        lend += s_pot[c];
+        i64 o = s_u[c] - s_sub[c];
+        if (o > 0) over += o;
+      }
+      s_lend[i] = lend; s_over[i] = over;
+    }
+  }
+  // ---- 4. the root's entries, in ClusterQueue (= local handle) order
+  if (threadIdx.x < 32) {
+    int cnt = 0;
+    for (int h0 = 0; h0 < nn; h0 += 32) {
+      int h = h0 + threadIdx.x;
+      int e = -1;
+      if (h < nn && nodes[h] < D.Q) e = D.cq_entry[nodes[h]];
+      unsigned m = __ballot_sync(0xffffffffu, e >= 0);
+      if (e >= 0) s_ent[cnt + __popc(m & ((1u << threadIdx.x) - 1))] = e;
+      cnt += __popc(m);
+    }
+    if (threadIdx.x == 0) s_misc[1] = cnt;
+  }
+  __syncthreads();
+  const int n = s_misc[1];
+  if (n == 0) { for (int i = threadIdx.x; i < (int)tb; i += blockDim.x) D.usage[(size_t)nodes[i / FR] * FR + i % FR] = s_u[i]; return; }
+  KB_PHASE(2);
+  // local view of the snapshot: node tables in shared memory, indexed by the local handle
+  DevSnap L = D;
+  L.tab_local = 1; L.parent = s_par; L.height = s_hgt; L.lq = s_lq;
+  L.nominal = s_sub;  // only ever read for ClusterQueues: SubtreeQuota == Nominal there (resource_node.go:160-166)
+  L.subtree = s_sub; L.usage = s_u; L.avail = s_av; L.potential = s_pot; L.blimit = s_bl;
+  L.fs_over = s_over; L.fs_lend = s_lend;
+  // ---- 5. nominate: KB_NG lanes per entry (get_assignments_coop), rows written straight to the output tables
+  {
+    const int lane = threadIdx.x & 31, glane = lane % KB_NG, gbase = lane - glane;
+    const unsigned gmask = ((1u << KB_NG) - 1u) << gbase;
+    const int groups = blockDim.x / KB_NG;
+    for (int i0 = 0; i0 < n; i0 += groups) {
+      int i = i0 + threadIdx.x / KB_NG;
+      if (i < n) {  // whole KB_NG-lane groups take the branch together
+        int e = s_ent[i];
+        int wl = D.heads[e];
+        bool need_search = false;
+        int borrowing;
+        int mode = get_assignments_coop(L, &need_search, wl, &borrowing, gmask, gbase, glane);
+        if (glane == 0) { D.mode[e] = (uint8_t)mode; D.borrow[e] = borrowing; D.decision[e] = KB_DEC_NOFIT; D.rank[e] = -1; D.tgt_cnt[e] = 0; D.tgt_off[e] = 0; }
+      }
+    }
+  }
+  __syncthreads();
+  KB_PHASE(3);  // output rows and mode/borrow are read back below by other threads (same CTA: visible after the barrier)
+  Tab<true> T;
+  T.D = &D; T.FR = FR; T.usage = s_u; T.sub = s_sub; T.lq = s_lq; T.bl = s_bl; T.lparent = s_par;
+  T.shadow = D.usage_shadow; T.tnodes = nodes; T.tnn = nn; T.shadow_on = &s_misc[0];
+  i64 *s_q = s_av;  // [entries][FR] requests: avail + potential are contiguous and dead after nomination
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const bool flat = FR <= 64 && D.tree_flat[t];
+  if (flat && n <= KB_TILE) {
+    // ---- 6a. Flat cohort, one entry per ClusterQueue, no preemption targets.  The only state one entry passes to
+    // the next is the ROOT's usage per column: everything else of available() (resource_node.go:104-118 on the
+    // two-node path) depends on the entry's own ClusterQueue row, which no other entry touches.  So the iterator keys
+    // and, per (entry, column), one threshold are computed for all entries in parallel:
+    //   fits  <=>  cap >= x  and  usage_root <= SubtreeQuota_root - x,   x = request - LocalAvailable(cq)
+    //   admitted: usage_root += max(0, x)            (addUsage :137-145: what exceeds the local availability)
+    // and the ordered loop (scheduler.go:269-401) is compare / vote / add on registers.  Entries in Preempt mode
+    // without targets reserve unconditionally (:303-318, quotaResourcesToReserve :530-548).
+    i64 *s_lim = s_pot;
+    const int half = blockDim.x / 2;
+    if ((int)threadIdx.x < n) compute_entry_key(L, s_ent[threadIdx.x], s_key + (size_t)threadIdx.x * 4);
+    else if ((int)threadIdx.x >= half && (int)threadIdx.x - half < n) {  // tile metadata + dense request row, in entry order
+      int i = threadIdx.x - half;
+      int e = s_ent[i];
+      int cqn = D.wl_cq[D.heads[e]];
+      t_e[i] = e; t_node[i] = D.local_idx[cqn]; t_cq[i] = cqn; t_mode[i] = D.mode[e]; t_borrow[i] = D.borrow[e];
+      i64 *qrow = s_q + (size_t)i * FR;
+      for (int c = 0; c < FR; c++) qrow[c] = -1;
+      expand_entry(D, e, qrow);
+    }
+    __syncthreads();
+    KB_PHASE(4);
+    if ((int)threadIdx.x < n) {  // position in the iterator order
+      const u64 *mine = s_key + (size_t)threadIdx.x * 4;
+      int rank = 0;
+      for (int j = 0; j < n; j++) rank += key4_less(s_key + (size_t)j * 4, mine) ? 1 : 0;
+      s_sorted[rank] = threadIdx.x;  // entry index (position in s_ent) at iterator position `rank`
+      t_toff[threadIdx.x] = rank;
+    } else if ((int)threadIdx.x >= half) {
+      for (int c = threadIdx.x - half; c < n * FR; c += half) {
+        int i = c / FR, fr = c % FR;
+        i64 q = s_q[c];
+        int r = t_node[i] * FR + fr;
+        i64 u = s_u[r], l = s_lq[r], bl = s_bl[r], sub = s_sub[r];
+        i64 A = imax(0, l - u);
+        i64 v = INT64_MAX;  // Fit: threshold on the root usage; Preempt: amount added to the root
+        int mode = t_mode[i];
+        if (mode == KB_MODE_FIT) {
+          if (q > 0) {
+            i64 x = q - A;
+            bool cap_ok = bl == KB_NO_LIMIT || (sub - l) - imax(0, u - l) + bl >= x;
+            v = cap_ok ? s_sub[fr] - x : INT64_MIN;
+          }
+        } else if (mode == KB_MODE_PREEMPT) {
+          v = 0;
+          if (q >= 0 && D.cq_reclaim_within[t_cq[i]] != KB_POLICY_ANY) {
+            i64 rsv = t_borrow[i] > 0 ? (bl == KB_NO_LIMIT ? q : imin(q, sub + bl - u)) : imax(0, imin(q, sub - u));
+            v = rsv > A ? rsv - A : 0;
+          }
+        }
+        s_lim[c] = v;
+      }
+    }
+    __syncthreads();
+    KB_PHASE(5);
+    if (warp == 0) {
+      const int fr0 = lane, fr1 = lane + 32;
+      const bool c0 = fr0 < FR, c1 = fr1 < FR;
+      i64 urt0 = c0 ? s_u[fr0] : 0, urt1 = c1 ? s_u[fr1] : 0;
+      const i64 srt0 = c0 ? s_sub[fr0] : 0, srt1 = c1 ? s_sub[fr1] : 0;
+      for (int p0 = 0; p0 < n; p0 += 4) {
+        i64 v0[4], v1[4]; int md[4], ix[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          bool in = p0 + k < n;
+          int i = in ? s_sorted[p0 + k] : 0;
+          ix[k] = i;
+          md[k] = in ? t_mode[i] : -1;
+          v0[k] = (in && c0) ? s_lim[(size_t)i * FR + fr0] : INT64_MAX;
+          v1[k] = (in && c1) ? s_lim[(size_t)i * FR + fr1] : INT64_MAX;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          if (md[k] < 0) break;
+          int dec = KB_DEC_NOFIT;
+          if (md[k] == KB_MODE_FIT) {
+            bool ok = __all_sync(0xffffffffu, urt0 <= v0[k] && urt1 <= v1[k]);
+            if (ok) {
+              if (c0 && v0[k] != INT64_MAX && srt0 > v0[k]) urt0 += srt0 - v0[k];
+              if (c1 && v1[k] != INT64_MAX && srt1 > v1[k]) urt1 += srt1 - v1[k];
+            }
+            dec = ok ? KB_DEC_ASSUMED : KB_DEC_SKIPPED_NO_FIT;
+          } else if (md[k] == KB_MODE_PREEMPT) {
+            if (c0) urt0 += v0[k];
+            if (c1) urt1 += v1[k];
+            dec = KB_DEC_PREEMPT_NO_TARGETS;
+          }
+          if (lane == 0) t_ntg[ix[k]] = dec;
+        }
+      }
+      if (c0) s_u[fr0] = urt0;
+      if (c1) s_u[fr1] = urt1;
+    }
+    __syncthreads();
+    KB_PHASE(6);
+    // ClusterQueue rows of the admitted / reserving entries (cq.AddUsage), decisions and ranks
+    for (int c = threadIdx.x; c < n * FR; c += blockDim.x) {
+      int i = c / FR, fr = c % FR;
+      int dec = t_ntg[i];
+      i64 q = s_q[c];
+      int r = t_node[i] * FR + fr;
+      if (dec == KB_DEC_ASSUMED) { if (q > 0) s_u[r] += q; }
+      else if (dec == KB_DEC_PREEMPT_NO_TARGETS && q >= 0 && D.cq_reclaim_within[t_cq[i]] != KB_POLICY_ANY) {
+        i64 u = s_u[r], bl = s_bl[r], sub = s_sub[r];
+        s_u[r] = u + (t_borrow[i] > 0 ? (bl == KB_NO_LIMIT ? q : imin(q, sub + bl - u)) : imax(0, imin(q, sub - u)));
+      }
+      if (fr == 0) { D.decision[t_e[i]] = (uint8_t)dec; D.rank[t_e[i]] = t_toff[i]; }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < (int)tb; i += blockDim.x) D.usage[(size_t)nodes[i / FR] * FR + i % FR] = s_u[i];
+    KB_PHASE(7);
+    return;
+  }
+  // ---- 6b. general form: iterator order (4 x u64 key per entry, all-pairs rank in shared memory) ...
+  for (int i = threadIdx.x; i < n; i += blockDim.x) compute_entry_key(L, s_ent[i], s_key + (size_t)i * 4);
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const u64 *mine = s_key + (size_t)i * 4;
+    int rank = 0;
+    for (int j = 0; j < n; j++) rank += key4_less(s_key + (size_t)j * 4, mine) ? 1 : 0;
+    s_sorted[rank] = s_ent[i];
+  }
+  __syncthreads();
+  KB_PHASE(4);
+  // ---- 7. ... and the admit loop (scheduler.go:269-401) in tiles of KB_TILE entries
+  for (int base = 0; base < n; base += KB_TILE) {
+    int tn = min(KB_TILE, n - base);
+    for (int i = threadIdx.x; i < tn; i += blockDim.x) {
+      int e = s_sorted[base + i];
+      int cqn = D.wl_cq[D.heads[e]];
+      t_e[i] = e; t_node[i] = D.local_idx[cqn]; t_cq[i] = cqn;
+      t_mode[i] = D.mode[e]; t_borrow[i] = D.borrow[e]; t_ntg[i] = 0; t_toff[i] = 0;
+    }
+    for (int c = threadIdx.x; c < tn * FR; c += blockDim.x) s_q[c] = -1;
+    __syncthreads();
+    for (int i = threadIdx.x; i < tn; i += blockDim.x) expand_entry(D, t_e[i], s_q + (size_t)i * FR);
+    __syncthreads();
+    if (warp == 0) {
+      if (flat) {
+        if (FR > 32) commit_tile_flat<true>(D, T, s_path, lane, tn, base, s_q, t_e, t_node, t_mode, t_borrow, t_cq, t_ntg, t_toff);
+        else commit_tile_flat<false>(D, T, s_path, lane, tn, base, s_q, t_e, t_node, t_mode, t_borrow, t_cq, t_ntg, t_toff);
+      } else {
+        for (int i = 0; i < tn; i++)
+          commit_entry<true>(D, T, s_path, lane, t_e[i], t_node[i], t_mode[i], t_borrow[i], s_q + (size_t)i * FR, base + i, t_cq[i], 0, 0);
+      }
+    }
+    __syncthreads();
+    if (flat)
+      for (int i = threadIdx.x; i < tn; i += blockDim.x) {
+        int m = t_mode[i];
+        if (m >= 0x100) { D.decision[t_e[i]] = (uint8_t)(m & 0xff); D.rank[t_e[i]] = base + i; }
+      }
+    __syncthreads();
+  }
+  KB_PHASE(5);
+  for (int i = threadIdx.x; i < (int)tb; i += blockDim.x) D.usage[(size_t)nodes[i / FR] * FR + i % FR] = s_u[i];
+  KB_PHASE(6);
+}
+__global__ void k_cq_entry(DevSnap D, int32_t *cq_entry) {  // ClusterQueue -> its single head of this cycle
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < D.H) cq_entry[D.wl_cq[D.heads[e]]] = e;
 }
 
 // ---------------------------------------------------------------------------
