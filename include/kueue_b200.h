@@ -331,6 +331,69 @@ typedef struct kb_drain_out {
 } kb_drain_out;
 int32_t kb_run_drain(kb_handle *h, const kb_snapshot *s, kb_drain_out *out);
 
+/* ------------------------------------------------------------------------
+ * Topology-aware scheduling: TASFlavorSnapshot.FindTopologyAssignmentsForFlavor
+ * (pkg/cache/scheduler/tas_flavor_snapshot.go:485-560) for the podsets that reach
+ * findTopologyAssignment (:765-970) with BestFit / LeastFreeCapacity placement: no leader/worker podset groups,
+ * no balanced placement (TASBalancedPlacement, off by default), no multi-layer slices, no node replacement,
+ * no elastic slices — the shim keeps those on the Go path.
+ *
+ * One TAS ResourceFlavor = one topology: a forest of domains, `n_levels` levels, every level-(l) domain has one
+ * level-(l-1) parent; the leaves are the lowest level.  Domains are numbered level-major (level 0 first); inside a
+ * level in ASCENDING lexicographic order of their levelValues (the reference's final tie-break, sortedDomains
+ * :1495-1515, and the order of the returned assignment, buildAssignment :1455-1466).
+ * ---------------------------------------------------------------------- */
+typedef struct kb_tas_topology {
+  int32_t n_levels;             /* len(levelKeys)                                                      */
+  int32_t n_domains;            /* all domains of all levels                                           */
+  int32_t n_resource;           /* resources tracked per leaf, INCLUDING corev1.ResourcePods           */
+  int32_t pods_resource;        /* index of corev1.ResourcePods among them                            */
+  const int32_t *level_start;   /* [n_levels+1] first domain of every level                            */
+  const int32_t *parent;        /* [n_domains] parent domain (previous level) or -1 at level 0         */
+  /* leaves = domains [level_start[n_levels-1], n_domains), tables indexed by leaf = domain - first leaf */
+  const int64_t *free_capacity; /* [n_leaves][n_resource] leafDomain.freeCapacity (allocatable - non-TAS usage) */
+  const uint32_t *cap_mask;     /* [n_leaves] bit r: resource r is a key of freeCapacity (CountIn returns 0 for a
+                                   requested resource the node does not expose, requests.go:187-190)  */
+  const int64_t *tas_usage;     /* [n_leaves][n_resource] leafDomain.tasUsage (incl. pods)              */
+  const uint32_t *usage_mask;   /* [n_leaves] keys of tasUsage                                         */
+} kb_tas_topology;
+
+enum { KB_TAS_REQUIRED = 1u << 0,       /* TopologyRequest.Required != nil (isRequired :1107)             */
+       KB_TAS_UNCONSTRAINED = 1u << 1,  /* isUnconstrained :1111 (explicit, implied, or slice-only request) */
+       KB_TAS_SIMULATE_EMPTY = 1u << 2, /* WithSimulateEmpty: ignore tasUsage (:1583-1585)                 */
+       KB_TAS_PROFILE_MIXED = 1u << 3   /* features.TASProfileMixed (default on): LeastFreeCapacity for
+                                           unconstrained requests (useLeastFreeCapacityAlgorithm :1291)  */ };
+enum { KB_TAS_OK = 0, KB_TAS_NO_FIT = 1, KB_TAS_BAD_REQUEST = 2 };
+
+/* A batch of podset requests against one topology.  Requests with the same chain id are the podsets of one
+ * workload: they are placed in input order and every placed podset's usage (SinglePodRequests x count per leaf,
+ * addAssumedUsage :619-627) is assumed by the following ones; a failure stops the chain (:551-553).  Different
+ * chains are independent (each sees the snapshot's tasUsage only). */
+typedef struct kb_tas_requests {
+  int32_t n_req;
+  const int32_t *chain;          /* [n_req] non-decreasing chain id                                      */
+  const int64_t *pod_request;    /* [n_req][n_resource] TASPodSetRequests.SinglePodRequests (WITHOUT pods)  */
+  const uint32_t *request_mask;  /* [n_req] keys of SinglePodRequests                                     */
+  const int32_t *count;          /* [n_req] TASPodSetRequests.Count                                       */
+  const int32_t *slice_size;     /* [n_req] getSliceSizeWithSinglePodAsDefault (:1129-1147), >= 1          */
+  const int32_t *level;          /* [n_req] resolved index of the requested topology level (:813-820)     */
+  const int32_t *slice_level;    /* [n_req] resolved index of the slice level (>= level, :822-829)        */
+  const uint32_t *flags;         /* [n_req] KB_TAS_*                                                      */
+  const uint32_t *leaf_ok;       /* [n_req][ceil(n_leaves/32)] or NULL: bit = the leaf passes taints/tolerations,
+                                    nodeSelector and required node affinity (fillInCounts :1541-1571, host-evaluated) */
+} kb_tas_requests;
+
+typedef struct kb_tas_out {
+  int32_t *status;               /* [n_req] KB_TAS_* (requests after a failed one in the same chain: KB_TAS_NO_FIT with no attempt = -1) */
+  int32_t *asg_start;            /* [n_req+1] CSR into the assignment arrays                              */
+  int32_t *asg_leaf;             /* [capacity] leaf index (ascending = lexicographic levelValues order)    */
+  int32_t *asg_count;            /* [capacity] pods on that leaf (TopologyDomainAssignment.Count)          */
+  int32_t capacity;
+  int32_t n_assigned;            /* out */
+} kb_tas_out;
+
+int32_t kb_tas_find(kb_handle *h, const kb_tas_topology *t, const kb_tas_requests *r, kb_tas_out *out);
+
 int32_t kb_get_stats(const kb_handle *h, kb_stats *out);
 int32_t kb_set_profile(kb_handle *h, int32_t on);  /* per-kernel event timing on/off */
 

@@ -116,6 +116,33 @@ class kb_drain_out(C.Structure):
     ]
 
 
+class kb_tas_topology(C.Structure):
+    _fields_ = [
+        ("n_levels", C.c_int32), ("n_domains", C.c_int32), ("n_resource", C.c_int32), ("pods_resource", C.c_int32),
+        ("level_start", _P(C.c_int32)), ("parent", _P(C.c_int32)),
+        ("free_capacity", _P(C.c_int64)), ("cap_mask", _P(C.c_uint32)), ("tas_usage", _P(C.c_int64)), ("usage_mask", _P(C.c_uint32)),
+    ]
+
+
+class kb_tas_requests(C.Structure):
+    _fields_ = [
+        ("n_req", C.c_int32), ("chain", _P(C.c_int32)), ("pod_request", _P(C.c_int64)), ("request_mask", _P(C.c_uint32)),
+        ("count", _P(C.c_int32)), ("slice_size", _P(C.c_int32)), ("level", _P(C.c_int32)), ("slice_level", _P(C.c_int32)),
+        ("flags", _P(C.c_uint32)), ("leaf_ok", _P(C.c_uint32)),
+    ]
+
+
+class kb_tas_out(C.Structure):
+    _fields_ = [
+        ("status", _P(C.c_int32)), ("asg_start", _P(C.c_int32)), ("asg_leaf", _P(C.c_int32)), ("asg_count", _P(C.c_int32)),
+        ("capacity", C.c_int32), ("n_assigned", C.c_int32),
+    ]
+
+
+TAS_REQUIRED, TAS_UNCONSTRAINED, TAS_SIMULATE_EMPTY, TAS_PROFILE_MIXED = 1, 2, 4, 8
+TAS_OK, TAS_NO_FIT, TAS_BAD_REQUEST = 0, 1, 2
+
+
 class kb_config(C.Structure):
     _fields_ = [("device", C.c_int32), ("reserved", C.c_int32)]
 

@@ -16,8 +16,9 @@ _LIB = None
 def build(force: bool = False) -> str:
     so = os.path.join(_HERE, "libkueue_oracle.so")
     src = os.path.join(_HERE, "kueue_oracle.cpp")
+    src2 = os.path.join(_HERE, "kueue_oracle_tas.cpp")
     hdr = os.path.join(_HERE, "..", "include", "kueue_b200.h")
-    stale = (not os.path.exists(so)) or any(os.path.getmtime(so) < os.path.getmtime(p) for p in (src, hdr))
+    stale = (not os.path.exists(so)) or any(os.path.getmtime(so) < os.path.getmtime(p) for p in (src, src2, hdr))
     if force or stale:
         subprocess.check_call(["make", "-s", "-C", _HERE, "-B", "libkueue_oracle.so"])
     return so
@@ -124,3 +125,14 @@ def sort_candidates(snap, cq):
 def is_preferred(a, b, pref):
     """isPreferred (flavorassigner.go:410-441); a, b = (preemption mode 0..4, borrowing level)."""
     return bool(lib().ko_is_preferred(C.c_int32(a[0]), C.c_int32(a[1]), C.c_int32(b[0]), C.c_int32(b[1]), C.c_int32(pref)))
+
+
+def tas_find(topo, reqs, capacity=None):
+    """FindTopologyAssignmentsForFlavor restated (oracle/kueue_oracle_tas.cpp): topo / reqs are kueue_b200.tas objects."""
+    from kueue_b200 import tas
+    out = tas.TasOut(reqs, capacity if capacity is not None else max(16, int(reqs.count.sum()) + 16))
+    f = lib().ko_tas_find
+    f.restype = C.c_int32
+    rc = f(C.byref(topo.struct), C.byref(reqs.struct), C.byref(out.struct))
+    assert rc == 0, rc
+    return out

@@ -9,7 +9,7 @@ NOW = 1_700_000_000_000_000_000  # `now := time.Now().Truncate(time.Second)` in 
 DUR = {"Nanosecond": 1, "Microsecond": 10**3, "Millisecond": 10**6, "Second": 10**9, "Minute": 60 * 10**9, "Hour": 3600 * 10**9}
 CONST = {
     "corev1.ResourceCPU": "cpu", "corev1.ResourceMemory": "memory", "corev1.ResourcePods": "pods",
-    "corev1.ResourceEphemeralStorage": "ephemeral-storage",
+    "corev1.ResourceEphemeralStorage": "ephemeral-storage", "corev1.LabelHostname": "kubernetes.io/hostname",
     "kueue.DefaultPodSetName": "main",
     "utiltesting.Ki": 2**10, "utiltesting.Mi": 2**20, "utiltesting.Gi": 2**30, "utiltesting.Ti": 2**40,
     "metav1.ConditionTrue": "True", "metav1.ConditionFalse": "False",
@@ -157,7 +157,7 @@ class Interp:
                 return NOW
             if short in self.helpers and fn[0] == "id":
                 return self.helpers[short](self, [self.ev(a) for a in args])
-            if q.startswith(("utiltestingapi.", "utiltesting.", "testingapi.")) and short.startswith("Make"):
+            if q.startswith(("utiltestingapi.", "utiltesting.", "testingapi.", "testingnode.", "testingpod.")) and short.startswith("Make"):
                 return self.make(short, [self.ev(a) for a in args])
             if q in ("resource.MustParse", "metav1.NewTime", "ptr.To", "kueue.ResourceFlavorReference", "kueue.ClusterQueueReference",
                      "kueue.CohortReference", "kueue.PodSetReference", "kueue.LocalQueueName", "corev1.ResourceName", "int32", "int64",
@@ -230,6 +230,9 @@ class Interp:
             return o
         if m == "Clone":
             return copy.deepcopy(o)
+        if k in ("MakeNode", "MakePod"):  # testingnode / testingpod wrappers: keep the call chain, tools/transcribe_tas.py reads it
+            o.setdefault("calls", []).append([m, [strip(x) for x in a]])
+            return o
         if k == "FlavorQuotas":
             if m == "Resource":
                 o["resources"].append({"name": a[0], "nominal": a[1] if len(a) > 1 else "0",
