@@ -80,6 +80,7 @@ struct kb_handle {
   // kb_run_drain: capacity reserved beyond the snapshot's admitted tables, heads chosen on the device
   size_t drain_extra_adm = 0, drain_extra_au = 0; bool drain_mode = false; bool preempt_possible = true;
   char *drain_buf = nullptr; size_t drain_buf_cap = 0; cudaEvent_t ev_d = nullptr;
+  char *tas_buf = nullptr; size_t tas_buf_cap = 0;
   bool fused_on = false; size_t fused_smem = 0; bool one_head_per_cq = false; int32_t *d_cq_entry = nullptr;
   bool sg_on = false; int sg_wpb = 1, sg_grid = 1, sg_ncap = 1; size_t sg_smem = 0;  // grouped form of k_search_cells
   // device ranking of the admitted workloads (kb_rank.cuh)
@@ -160,6 +161,7 @@ void kb_destroy(kb_handle *h) {
   if (h->arena.base) cudaFree(h->arena.base);
   if (h->sarena.base) cudaFree(h->sarena.base);
   if (h->drain_buf) cudaFree(h->drain_buf);
+  if (h->tas_buf) cudaFree(h->tas_buf);
   if (h->ev_d) cudaEventDestroy(h->ev_d);
   if (h->host_words) cudaFreeHost(h->host_words);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -1023,6 +1025,7 @@ static int32_t drain_impl(kb_handle *h, const kb_snapshot *s, kb_drain_out *out)
   need(16, 4); need(Wz, 4); need(Wz, 4); need(Wz, 1); need(trace_cap, 4); need(trace_cap, 1);
   if (tot > h->drain_buf_cap) {
     if (h->drain_buf) cudaFree(h->drain_buf);
+  if (h->tas_buf) cudaFree(h->tas_buf);
     h->drain_buf = nullptr; h->drain_buf_cap = 0;
     CUDA_TRY(h, cudaMalloc(&h->drain_buf, tot + (1 << 20)));
     h->drain_buf_cap = tot + (1 << 20);
@@ -1130,6 +1133,158 @@ extern "C" int32_t kb_run_drain(kb_handle *h, const kb_snapshot *s, kb_drain_out
   h->drain_mode = false; h->drain_extra_adm = 0; h->drain_extra_au = 0;
   h->uploaded = false;  // the resident snapshot was consumed (queues advanced, admitted tables grown)
   return rc;
+}
+
+// ---------------------------------------------------------------------------
+// kb_tas_find: topology-aware placement (kb_tas.cuh)
+// ---------------------------------------------------------------------------
+extern "C" int32_t kb_tas_find(kb_handle *h, const kb_tas_topology *t, const kb_tas_requests *r, kb_tas_out *out) {
+  if (!h || !t || !r || !out) return KB_ERR_INVALID;
+  cudaSetDevice(h->device);
+  const int L = t->n_levels, ND = t->n_domains, R = t->n_resource, NQ = r->n_req;
+  if (L < 1 || ND < 0 || R < 1 || R > 32 || t->pods_resource < 0 || t->pods_resource >= R || NQ < 0) return fail(h, KB_ERR_INVALID, "tas: bad dimensions");
+  if (ND == 0) {  // no node of the flavor is schedulable: "no topology domains at level" (:1203-1205) for the first podset of every chain
+    for (int q = 0; q < NQ; q++) {
+      bool first = q == 0 || r->chain[q] != r->chain[q - 1];
+      bool bad = r->level[q] < 0 || r->level[q] >= L || r->slice_level[q] < 0 || r->slice_level[q] >= L || r->level[q] > r->slice_level[q] || r->slice_size[q] < 1;
+      out->status[q] = first ? (bad ? KB_TAS_BAD_REQUEST : KB_TAS_NO_FIT) : -1;
+      out->asg_start[q] = 0;
+    }
+    out->asg_start[NQ] = 0; out->n_assigned = 0;
+    return KB_OK;
+  }
+  if (t->level_start[0] != 0 || t->level_start[L] != ND) return fail(h, KB_ERR_INVALID, "tas: level_start must cover [0, n_domains)");
+  const int leaf0 = t->level_start[L - 1], NL = ND - leaf0;
+  // Children of a domain are contiguous in the next level (lexicographic numbering) and the child ranges of level l
+  // tile level l+1 in order, so one [ND+1] table serves as child_start[d] .. child_start[d+1]: the end of the last
+  // domain of level l is level_start[l+2], which is also where the children of the first domain of level l+1 start.
+  std::vector<int32_t> cstart(ND + 1, ND);
+  for (int l = 0; l < L; l++) {
+    int a = t->level_start[l], b = t->level_start[l + 1];
+    if (b < a) return fail(h, KB_ERR_INVALID, "tas: level_start not monotone");
+    for (int d = a; d < b; d++) {
+      int p = t->parent[d];
+      if (l == 0) { if (p != -1) return fail(h, KB_ERR_INVALID, "tas: level-0 domains have no parent"); continue; }
+      if (p < t->level_start[l - 1] || p >= a) return fail(h, KB_ERR_INVALID, "tas: parent must be a domain of the previous level");
+      if (d > a && p < t->parent[d - 1]) return fail(h, KB_ERR_INVALID, "tas: domains of a level must be numbered in lexicographic levelValues order (children of one parent contiguous)");
+    }
+    if (l + 1 < L) {
+      int c = t->level_start[l + 1], ce = t->level_start[l + 2];
+      for (int d = a; d < b; d++) { cstart[d] = c; while (c < ce && t->parent[c] == d) c++; }
+      if (c != ce) return fail(h, KB_ERR_INVALID, "tas: a domain of the next level has no parent in this level");
+    }
+  }
+  // chains, rounds, shape slots
+  std::vector<int32_t> pred(std::max(1, NQ), -1), chain_slot(std::max(1, NQ), -1), pos(std::max(1, NQ), 0), slot(std::max(1, NQ), 0);
+  int n_chain_slots = 0, n_rounds = 0, max_count = 1;
+  for (int q = 0; q < NQ;) {
+    int e = q;
+    while (e + 1 < NQ && r->chain[e + 1] == r->chain[q]) e++;
+    if (e + 1 < NQ && r->chain[e + 1] < r->chain[q]) return fail(h, KB_ERR_INVALID, "tas: chain ids must be non-decreasing");
+    int len = e - q + 1;
+    int cs = len > 1 ? n_chain_slots++ : -1;
+    for (int i = q; i <= e; i++) { pos[i] = i - q; pred[i] = i > q ? i - 1 : -1; chain_slot[i] = cs; }
+    n_rounds = std::max(n_rounds, len);
+    q = e + 1;
+  }
+  for (int q = 0; q < NQ; q++) max_count = std::max(max_count, r->count[q]);
+  const int ok_words = (NL + 31) / 32;
+  std::vector<std::vector<int32_t>> round_req(n_rounds), round_slot_req(n_rounds);
+  {
+    std::map<std::string, int> shapes;  // round 0: requests with the same shape share the counts
+    for (int q = 0; q < NQ; q++) {
+      int rd = pos[q];
+      round_req[rd].push_back(q);
+      if (rd == 0) {
+        std::string key((const char *)(r->pod_request + (size_t)q * R), (size_t)R * 8);
+        key.append((const char *)&r->request_mask[q], 4);
+        uint32_t fl = r->flags[q] & KB_TAS_SIMULATE_EMPTY; key.append((const char *)&fl, 4);
+        key.append((const char *)&r->slice_size[q], 4); key.append((const char *)&r->slice_level[q], 4);
+        if (r->leaf_ok) key.append((const char *)(r->leaf_ok + (size_t)q * ok_words), (size_t)ok_words * 4);
+        auto it = shapes.find(key);
+        if (it == shapes.end()) { it = shapes.emplace(key, (int)round_slot_req[0].size()).first; round_slot_req[0].push_back(q); }
+        slot[q] = it->second;
+      } else { slot[q] = (int)round_slot_req[rd].size(); round_slot_req[rd].push_back(q); }
+    }
+  }
+  size_t max_slots = 1, max_round = 1;
+  for (int rd = 0; rd < n_rounds; rd++) { max_slots = std::max(max_slots, round_slot_req[rd].size()); max_round = std::max(max_round, round_req[rd].size()); }
+  std::vector<int32_t> tmp_start(NQ + 1, 0);
+  for (int q = 0; q < NQ; q++) tmp_start[q + 1] = tmp_start[q] + std::max(0, std::min(r->count[q], NL));
+  const int list_cap = max_count + 8;
+  const int sel_grid = (int)std::min<size_t>(max_round, (size_t)h->sm_count * 8);
+  // ---- device buffer (grow-only)
+  size_t tot = 0;
+  auto need = [&](size_t n, size_t sz) { tot += pad256(n * sz); };
+  need(L + 1, 4); need(ND, 4); need(ND + 1, 4); need((size_t)NL * R, 8); need(NL, 4); need((size_t)NL * R, 8); need(NL, 4);
+  need((size_t)NQ * R, 8); for (int k = 0; k < 10; k++) need(NQ, 4); need(r->leaf_ok ? (size_t)NQ * ok_words : 1, 4);
+  need(max_slots * ND, 4); need(max_slots * ND, 4); need((size_t)n_chain_slots * NL * R, 8); need((size_t)n_chain_slots * NL, 4);
+  need(NQ + 1, 4); need(NQ + 1, 4); need(NQ + 2, 4); need(tmp_start[NQ] + 1, 4); need(tmp_start[NQ] + 1, 4);
+  need((size_t)sel_grid * 6 * list_cap, 4); need(max_round, 4); need(max_slots, 4); need(std::max(1, out->capacity), 4); need(std::max(1, out->capacity), 4);
+  if (tot > h->tas_buf_cap) {
+    if (h->tas_buf) cudaFree(h->tas_buf);
+    h->tas_buf = nullptr; h->tas_buf_cap = 0;
+    CUDA_TRY(h, cudaMalloc(&h->tas_buf, tot + (1 << 20)));
+    h->tas_buf_cap = tot + (1 << 20);
+  }
+  size_t used = 0;
+  auto take = [&](size_t n, size_t sz) { char *p = h->tas_buf + used; used += pad256(n * sz); return p; };
+  auto upl = [&](const void *src, size_t n, size_t sz) -> char * { char *d = take(n, sz); if (n) cudaMemcpyAsync(d, src, n * sz, cudaMemcpyHostToDevice, h->stream); return d; };
+  TasDev T{};
+  T.L = L; T.n_domains = ND; T.n_leaves = NL; T.leaf0 = leaf0; T.R = R; T.pods_res = t->pods_resource; T.n_req = NQ;
+  T.level_start = (const int32_t *)upl(t->level_start, L + 1, 4); T.parent = (const int32_t *)upl(t->parent, ND, 4);
+  T.child_start = (const int32_t *)upl(cstart.data(), ND + 1, 4);
+  T.free_cap = (const i64 *)upl(t->free_capacity, (size_t)NL * R, 8); T.cap_mask = (const uint32_t *)upl(t->cap_mask, NL, 4);
+  T.tas_usage = (const i64 *)upl(t->tas_usage, (size_t)NL * R, 8); T.usage_mask = (const uint32_t *)upl(t->usage_mask, NL, 4);
+  T.pod_request = (const i64 *)upl(r->pod_request, (size_t)NQ * R, 8); T.request_mask = (const uint32_t *)upl(r->request_mask, NQ, 4);
+  T.flags = (const uint32_t *)upl(r->flags, NQ, 4); T.count = (const int32_t *)upl(r->count, NQ, 4);
+  T.slice_size = (const int32_t *)upl(r->slice_size, NQ, 4); T.level = (const int32_t *)upl(r->level, NQ, 4);
+  T.slice_level = (const int32_t *)upl(r->slice_level, NQ, 4);
+  T.slot = (const int32_t *)upl(slot.data(), NQ, 4); T.chain_slot = (const int32_t *)upl(chain_slot.data(), NQ, 4); T.pred = (const int32_t *)upl(pred.data(), NQ, 4);
+  T.leaf_ok = r->leaf_ok ? (const uint32_t *)upl(r->leaf_ok, (size_t)NQ * ok_words, 4) : nullptr; T.ok_words = ok_words;
+  T.state = (int32_t *)take(max_slots * ND, 4); T.slice = (int32_t *)take(max_slots * ND, 4);
+  T.assumed = (i64 *)take((size_t)n_chain_slots * NL * R, 8); T.assumed_mask = (uint32_t *)take((size_t)n_chain_slots * NL, 4);
+  if (n_chain_slots) { cudaMemsetAsync(T.assumed, 0, (size_t)n_chain_slots * NL * R * 8, h->stream); cudaMemsetAsync(T.assumed_mask, 0, (size_t)n_chain_slots * NL * 4, h->stream); }
+  T.status = (int32_t *)take(NQ + 1, 4); T.n_out = (int32_t *)take(NQ + 1, 4);
+  int32_t *d_asg_start = (int32_t *)take(NQ + 2, 4);
+  T.tmp_start = (int32_t *)upl(tmp_start.data(), NQ + 1, 4);
+  T.tmp_leaf = (int32_t *)take(tmp_start[NQ] + 1, 4); T.tmp_count = (int32_t *)take(tmp_start[NQ] + 1, 4);
+  T.lists = (int32_t *)take((size_t)sel_grid * 6 * list_cap, 4); T.list_cap = list_cap;
+  int32_t *d_round = (int32_t *)take(max_round, 4), *d_slotreq = (int32_t *)take(max_slots, 4);
+  int32_t *d_leaf = (int32_t *)take(std::max(1, out->capacity), 4), *d_cnt = (int32_t *)take(std::max(1, out->capacity), 4);
+  if (NQ) cudaMemsetAsync(T.n_out, 0, (size_t)(NQ + 1) * 4, h->stream);
+  CUDA_TRY(h, cudaEventRecord(h->ev2, h->stream));
+  for (int rd = 0; rd < n_rounds; rd++) {
+    int ns = (int)round_slot_req[rd].size(), nr = (int)round_req[rd].size();
+    CUDA_TRY(h, cudaMemcpyAsync(d_slotreq, round_slot_req[rd].data(), (size_t)ns * 4, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(d_round, round_req[rd].data(), (size_t)nr * 4, cudaMemcpyHostToDevice, h->stream));
+    k_tas_leaf<<<dim3((NL + 255) / 256, ns), 256, 0, h->stream>>>(T, d_slotreq, ns);
+    for (int l = L - 2; l >= 0; l--) {
+      int n = t->level_start[l + 1] - t->level_start[l];
+      k_tas_reduce<<<dim3((n + 127) / 128, ns), 128, 0, h->stream>>>(T, d_slotreq, ns, l);
+    }
+    k_tas_select<<<std::min(nr, sel_grid), KB_TAS_THREADS, 0, h->stream>>>(T, d_round, nr);
+  }
+  if (NQ) {
+    k_scan_i32<<<1, 1024, 0, h->stream>>>(T.n_out, d_asg_start, NQ);
+    k_tas_compact<<<NQ, 64, 0, h->stream>>>(T, d_asg_start, d_leaf, d_cnt, out->capacity);
+  }
+  CUDA_TRY(h, cudaEventRecord(h->ev3, h->stream));
+  CUDA_TRY(h, cudaGetLastError());
+  if (NQ) {
+    CUDA_TRY(h, cudaMemcpyAsync(out->status, T.status, (size_t)NQ * 4, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(out->asg_start, d_asg_start, (size_t)(NQ + 1) * 4, cudaMemcpyDeviceToHost, h->stream));
+  } else out->asg_start[0] = 0;
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  out->n_assigned = out->asg_start[NQ];
+  int ncopy = std::min(out->n_assigned, out->capacity);
+  if (ncopy > 0) {
+    CUDA_TRY(h, cudaMemcpy(out->asg_leaf, d_leaf, (size_t)ncopy * 4, cudaMemcpyDeviceToHost));
+    CUDA_TRY(h, cudaMemcpy(out->asg_count, d_cnt, (size_t)ncopy * 4, cudaMemcpyDeviceToHost));
+  }
+  { float ms = 0; cudaEventElapsedTime(&ms, h->ev2, h->ev3); h->stats.last_cycle_gpu_ms = ms; }
+  if (out->n_assigned > out->capacity) return fail(h, KB_ERR_CAPACITY, "tas: assignment buffer too small");
+  return KB_OK;
 }
 
 extern "C" int32_t kb_tree_eval(kb_handle *h, const kb_snapshot *s, kb_tree_out *out) {

@@ -21,6 +21,7 @@
 #include "kb_search.cuh"
 #include "kb_rank.cuh"
 #include "kb_drain.cuh"
+#include "kb_tas.cuh"
 
 #define KB_RANK_CAP 2048  // roots up to this many entries are ordered by the all-pairs k_rank kernel
 

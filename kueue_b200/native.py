@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, "libkueue_b200.so")
 _LIB = None
 
 EXPORTS = ["kb_create", "kb_destroy", "kb_last_error", "kb_alloc_pinned", "kb_free_pinned", "kb_version",
-           "kb_tree_eval", "kb_run_cycle", "kb_run_drain", "kb_upload", "kb_cycle_resident", "kb_download", "kb_get_stats", "kb_set_profile"]
+           "kb_tree_eval", "kb_run_cycle", "kb_run_drain", "kb_tas_find", "kb_upload", "kb_cycle_resident", "kb_download", "kb_get_stats", "kb_set_profile"]
 
 
 class KueueB200Error(RuntimeError):
@@ -139,6 +139,13 @@ class Evaluator:
         out = out or abi.DrainOut(snap, max_cycles)
         s = snap.as_struct()
         self._check(lib().kb_run_drain(self._h, C.byref(s), C.byref(out.struct)))
+        return out
+
+    def tas_find(self, topo, reqs, capacity: int | None = None):
+        """kb_tas_find: topology-aware placement of a batch of podset requests (kueue_b200.tas objects)."""
+        from . import tas
+        out = tas.TasOut(reqs, capacity if capacity is not None else max(16, int(reqs.count.sum()) + 16))
+        self._check(lib().kb_tas_find(self._h, C.byref(topo.struct), C.byref(reqs.struct), C.byref(out.struct)))
         return out
 
     def upload(self, snap: abi.FlatSnapshot):

@@ -203,3 +203,58 @@ class TasOut:
     def assignment(self, q: int):
         a, b = int(self.asg_start[q]), int(self.asg_start[q + 1])
         return [(int(self.asg_leaf[k]), int(self.asg_count[k])) for k in range(a, b)]
+
+
+def synth_topology(blocks: int = 10, racks: int = 100, hosts: int = 100, seed: int = 5, used: float = 0.5):
+    """cfg5-style synthetic topology (BASELINE.json configs[4]): blocks x racks x hosts, node capacity like
+    test/performance/scheduler/configs/tas/generator.yaml:12-24 (96 cpu, 256 Gi, 8 gpu, 110 pods); a fraction of every
+    node already used by TAS workloads.  Built directly in flat form (no per-node dicts)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    t = object.__new__(TasTopology)
+    t.levels = ["cloud.com/topology-block", "cloud.com/topology-rack", HOSTNAME]
+    t.resources = ["cpu", "gpu", "memory", "pods"]
+    t.pods_resource = 3
+    nb, nr, nh = blocks, blocks * racks, blocks * racks * hosts
+    t.level_start = np.array([0, nb, nb + nr, nb + nr + nh], np.int32)
+    t.parent = np.concatenate([np.full(nb, -1), np.repeat(np.arange(nb), racks), nb + np.repeat(np.arange(nr), hosts)]).astype(np.int32)
+    t.n_leaves = nh
+    t.leaf_values = None
+    cap = np.array([96_000, 8, 256 << 30, 110], np.int64)
+    t.free = np.tile(cap, (nh, 1))
+    t.cap_mask = np.full(nh, 0xf, np.uint32)
+    frac = rng.uniform(0, 2 * used, (nh, 1)).clip(0, 1)
+    t.usage = (t.free * frac * rng.uniform(0.7, 1.0, (nh, 4))).astype(np.int64)
+    t.usage_mask = np.full(nh, 0xf, np.uint32)
+    t.leaf_nodes = []
+    t.lowest_is_node = True
+    s = abi.kb_tas_topology()
+    s.n_levels, s.n_domains, s.n_resource, s.pods_resource = 3, int(t.level_start[3]), 4, 3
+    P = C.POINTER
+    s.level_start = t.level_start.ctypes.data_as(P(C.c_int32)); s.parent = t.parent.ctypes.data_as(P(C.c_int32))
+    s.free_capacity = t.free.ctypes.data_as(P(C.c_int64)); s.cap_mask = t.cap_mask.ctypes.data_as(P(C.c_uint32))
+    s.tas_usage = t.usage.ctypes.data_as(P(C.c_int64)); s.usage_mask = t.usage_mask.ctypes.data_as(P(C.c_uint32))
+    t.struct = s
+    return t
+
+
+def synth_requests(topo: TasTopology, n: int, seed: int = 7, shapes: int = 16, chains: bool = False, max_pods: int = 64) -> TasRequests:
+    """n podset requests: `shapes` distinct pod templates, 1..max_pods pods, required / preferred at rack or block level or
+    unconstrained; with chains=True some workloads carry two or three podsets."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    tmpl = [{"cpu": int(rng.integers(1, 33)) * 1000, "memory": int(rng.integers(1, 65)) << 30, **({"gpu": int(rng.integers(1, 5))} if rng.random() < 0.5 else {})}
+            for _ in range(shapes)]
+    reqs = TasRequests(topo)
+    chain, left = 0, 0
+    for i in range(n):
+        if left == 0:
+            chain += 1
+            left = int(rng.integers(1, 4)) if chains and rng.random() < 0.3 else 1
+        left -= 1
+        mode = rng.integers(0, 5)
+        lvl = topo.levels[int(rng.integers(0, len(topo.levels)))]
+        tr = ({"required": lvl}, {"preferred": lvl}, {"unconstrained": True}, None, {"required": topo.levels[1], "sliceRequiredTopology": topo.levels[-1], "sliceSize": 2})[mode]
+        count = int(rng.integers(1, max_pods + 1))
+        if mode == 4:
+            count += count % 2
+        reqs.add(chain, tmpl[int(rng.integers(0, shapes))], count, None if tr is None else {"required": None, "preferred": None, "unconstrained": False, "sliceRequiredTopology": None, "sliceSize": None, **tr})
+    return reqs.finalize()
