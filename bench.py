@@ -40,12 +40,13 @@ WORKLOADS = {
     2: "cfg2: 100k pending x 1k ClusterQueues x 8 flavors x 4 resources, StrictFIFO, no borrowing",
     3: "cfg3: 1M pending x 10k ClusterQueues, BestEffortFIFO + flat cohorts + DRF fair sharing",
     4: "cfg4: 1M pending x 10k ClusterQueues, depth-4 hierarchical cohorts + within-cohort/reclaim preemption, 200k admitted",
+    5: "cfg5: topology-aware placement, 100k nodes (10 blocks x 100 racks x 100 hosts), 10k podset requests per cycle (one head per ClusterQueue)",
 }
 
 
 # cfg3 runs the fair-sharing iterator, which holds one entry per ClusterQueue
 # (fair_sharing_iterator.go:52-54): its step is one reference cycle over the Q heads.
-HEADS = {1: "all", 2: "all", 3: "one_per_cq", 4: "one_per_cq"}
+HEADS = {1: "all", 2: "all", 3: "one_per_cq", 4: "one_per_cq", 5: "one_per_cq"}
 
 
 def algorithmic_bytes(snap) -> dict:
@@ -170,11 +171,123 @@ def drain_line(ev, config: int, cpu: bool):
     return line
 
 
+def run_tas(args, rank, world, local_rank):
+    """cfg5: one step = kb_tas_find over the cycle's podset requests (FindTopologyAssignmentsForFlavor per head)."""
+    import torch
+    import torch.distributed as dist
+    from kueue_b200 import abi, native, tas
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    # N > 1: every rank places the requests of its own cohorts' ClusterQueues on its own replica of the topology
+    # tables (cfg5 "sharded by cohort"): weak scaling, no data-path collective
+    topo = tas.synth_topology(10, 100, 100)
+    nreq = 10_000
+    reqs = tas.synth_requests(topo, nreq, seed=7 + rank, shapes=16)
+    cap = int(reqs.count.sum()) + 16
+    ev = native.Evaluator(local_rank)
+    ev.set_profile(True)
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    for _ in range(max(3, args.warmup)):
+        ev.tas_find(topo, reqs, cap)
+    sampler = ClockSampler(local_rank); sampler.start()
+    barrier()
+    dev_ms, kms, launches = 0.0, np.zeros(20), 0
+    for _ in range(args.steps):
+        flush.zero_(); torch.cuda.synchronize()
+        ev.tas_find(topo, reqs, cap)
+        st = ev.stats()
+        dev_ms += st.last_cycle_gpu_ms; kms += np.array(list(st.kernel_ms)); launches += st.kernel_launches
+    barrier()
+    clocks = sampler.stop()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        out = ev.tas_find(topo, reqs, cap)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([dev_ms, e2e_s, float(nreq)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        dev_ms, e2e_s, total = tmax[0].item(), tmax[1].item(), tsum[2].item()
+    else:
+        total = float(nreq)
+    if rank == 0:
+        NL, R = topo.n_leaves, len(topo.resources)
+        ms = dev_ms / args.steps
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        names = abi.KERNEL_NAMES
+        per = {names[i]: kms[i] / args.steps for i in range(20) if kms[i] > 0 and i != 14}
+        kname = max(per, key=per.get)
+        # algorithmic bytes: leaf pass = per distinct shape every leaf's capacity + usage rows (R x 16 B), masks (8 B) in, state + sliceState (8 B) out;
+        # select = per request the (state, sliceState) of the domains of its level and of the children it descends into, 8 B each (lower bound: its level once)
+        level_sizes = np.diff(topo.level_start)
+        ab = {"k_tas_leaf": 16 * NL * (R * 16 + 16), "k_tas_reduce": 16 * int(level_sizes.sum()) * 16,
+              "k_tas_select": float(sum(int(level_sizes[l]) for l in reqs.level) * 8 + nreq * 64)}
+        kbytes = ab.get(kname, 0.0)
+        top_ms = per[kname]
+        achieved = kbytes / (top_ms / 1e3) / 1e9 if top_ms else 0.0
+        h2d = int(topo.free.nbytes + topo.usage.nbytes + topo.cap_mask.nbytes * 2 + topo.parent.nbytes + reqs.pod_request.nbytes + reqs.count.nbytes * 8)
+        d2h = int(nreq * 8 + out.asg_start[-1] * 8)
+        line = {"metric": METRIC, "value": total / (ms / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+                "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
+                "config": {"workload": WORKLOADS[5], "decisions_per_step_per_gpu": nreq, "request_shapes": 16,
+                           "l2": "512 MiB flush buffer written between timed steps",
+                           "timing": "CUDA events on the library stream around the kernels of kb_tas_find, summed over steps, max over ranks",
+                           "placed": int((out.status == 0).sum()), "no_fit": int((out.status == 1).sum())},
+                "clocks": clocks, "e2e": {"value": total * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+                "gpu_launches": launches, "kernel_ms_per_step": per,
+                "roofline": {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None,
+                             "traffic": measured_traffic(5, kname), "algorithmic_bytes_per_launch": kbytes, "kernel_ms": top_ms,
+                             "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)"}}
+        if world == 1 and not args.no_cpu_baseline:
+            import oracle
+            sample = tas.synth_requests(topo, 400, seed=7, shapes=16)
+            oracle.tas_find(topo, sample)
+            t0 = time.perf_counter(); n = 0
+            while time.perf_counter() - t0 < 10:
+                oracle.tas_find(topo, sample); n += 1
+            dt = time.perf_counter() - t0
+            line["cpu_baseline"] = {"value": n * 400 / dt, "unit": UNIT, "cores": 1, "kind": "port",
+                                    "sample": f"{n} passes over the first 400 requests of the same distribution on the same topology in {dt:.1f} s, 1 thread"}
+        print(json.dumps(line))
+    ev.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def run_reference(args, rank, world):
     from kueue_b200 import synth
     if rank != 0:
         return
     import oracle
+    if args.config == 5:
+        from kueue_b200 import tas
+        topo = tas.synth_topology(10, 100, 100)
+        sample = tas.synth_requests(topo, 400, seed=7, shapes=16)
+        for _ in range(args.warmup):
+            oracle.tas_find(topo, sample)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            oracle.tas_find(topo, sample)
+        dt = time.perf_counter() - t0
+        val = args.steps * 400 / dt
+        print(json.dumps({"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                          "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
+                          "config": {"workload": WORKLOADS[5], "sample": "every step places the first 400 requests of the cycle's distribution on the same 100k-node topology"},
+                          "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "kind": "port", "sample": f"{args.steps} passes of 400 requests"},
+                          "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
+        return
     snap = synth.make_snapshot(args.config, heads=HEADS[args.config])
     if HEADS[args.config] == "one_per_cq":
         snap = synth.compact_to_heads(snap)
@@ -214,6 +327,8 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         return run_reference(args, rank, world)
+    if args.config == 5:
+        return run_tas(args, rank, world, local_rank)
 
     import torch
     import torch.distributed as dist
@@ -255,7 +370,7 @@ def main():
     barrier()
     t_wall0 = time.perf_counter()
     dev_ms = 0.0
-    kms = np.zeros(16)
+    kms = np.zeros(20)
     launches = 0
     for _ in range(args.steps):
         flush.zero_(); torch.cuda.synchronize()  # L2 flush between timed iterations
@@ -320,7 +435,7 @@ def main():
             "clocks": clocks,
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches,
-            "kernel_ms_per_step": {abi.KERNEL_NAMES[i]: kms[i] / args.steps for i in range(16) if kms[i] > 0},
+            "kernel_ms_per_step": {abi.KERNEL_NAMES[i]: kms[i] / args.steps for i in range(20) if kms[i] > 0},
             "roofline": {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak if peak else None, "traffic": measured_traffic(args.config, kname),
                          "algorithmic_bytes_per_launch": kbytes, "kernel_ms": top_ms,

@@ -37,7 +37,7 @@ extern "C" {
 #define KB_MAX_RESOURCES 16   /* n_resource <= 16  */
 #define KB_MAX_FLAVORS   64   /* n_flavor   <= 64 (eligibility bitmask is u64) */
 #define KB_MAX_DEPTH     16   /* CQ -> root path length <= 16 */
-#define KB_N_KERNELS     16
+#define KB_N_KERNELS     20
 
 typedef enum kb_status {
   KB_OK = 0,
@@ -258,7 +258,8 @@ enum { KB_K_TREE = 0, KB_K_LONE = 1, KB_K_NOMINATE = 2, KB_K_SCAN = 3, KB_K_SCAT
        KB_K_ADMIT = 5, KB_K_RANK = 6, KB_K_PREEMPT = 7 /* fair-sharing target search (+ k_over) */,
        KB_K_RANKADM = 8 /* ranking of the admitted workloads */, KB_K_SEARCH_TABLES = 9 /* k_columns + candidate buckets */,
        KB_K_SEARCH_CELLS = 10, KB_K_WALK = 11, KB_K_FAIR_PREP = 12, KB_K_DRAIN = 13 /* queue layer of kb_run_drain */,
-       KB_K_TAS = 14, KB_K_CYCLE_ROOT = 15 /* fused per-root cycle */ };
+       KB_K_TAS = 14 /* kb_tas_find, all kernels */, KB_K_CYCLE_ROOT = 15 /* fused per-root cycle */,
+       KB_K_TAS_LEAF = 16, KB_K_TAS_REDUCE = 17, KB_K_TAS_SELECT = 18 };
 
 typedef struct kb_handle kb_handle;
 

@@ -41,6 +41,12 @@ import (
 type kbEvaluator struct {
 	h         *C.kb_handle
 	staticGen int64 // bumped by the cache whenever a ClusterQueue / Cohort spec changes
+	// ONE page-locked block per evaluator, carved per cycle (bump allocator, reset at the top of every cycle): no
+	// cudaHostAlloc on the cycle's path, nothing leaks, and the per-cycle tables sit in one span the library moves
+	// with a single DMA (INTEGRATION.md §3).  It grows (free + allocate twice the size) when a cycle does not fit.
+	arena    unsafe.Pointer
+	arenaCap uintptr
+	arenaOff uintptr
 }
 
 func newKBEvaluator(device int) (*kbEvaluator, error) {
@@ -52,14 +58,31 @@ func newKBEvaluator(device int) (*kbEvaluator, error) {
 	return &kbEvaluator{h: h}, nil
 }
 
-// pinned returns a slice over page-locked memory owned by the library: the Go GC never moves it and C keeps no Go
-// pointer after the call returns (cgo pointer rules).  In production all tables are carved out of ONE block so
-// the library moves the per-cycle tables with a single DMA (INTEGRATION.md §3).
-func pinned[T any](n int) []T {
-	var p unsafe.Pointer
+// resetArena starts a new cycle: every slice handed out by pinned() in the previous cycle is dead after this call.
+func (k *kbEvaluator) resetArena(need uintptr) {
+	if need > k.arenaCap {
+		if k.arena != nil {
+			C.kb_free_pinned(k.arena)
+		}
+		k.arenaCap = 2 * need
+		C.kb_alloc_pinned(&k.arena, C.uint64_t(k.arenaCap))
+	}
+	k.arenaOff = 0
+}
+
+// pinned carves a zeroed slice out of the evaluator's page-locked block (256-byte aligned like the library's device
+// arena): the Go GC never moves it and C keeps no Go pointer after the call returns (cgo pointer rules).
+func pinned[T any](k *kbEvaluator, n int) []T {
 	var zero T
-	C.kb_alloc_pinned(&p, C.uint64_t(uintptr(max(n, 1))*unsafe.Sizeof(zero)))
-	return unsafe.Slice((*T)(p), n)
+	bytes := (uintptr(max(n, 1))*unsafe.Sizeof(zero) + 255) &^ 255
+	if k.arenaOff+bytes > k.arenaCap {
+		panic("kueue_b200: per-cycle arena estimate too small") // resetArena sizes it from the snapshot's dimensions
+	}
+	p := unsafe.Add(k.arena, k.arenaOff)
+	k.arenaOff += bytes
+	s := unsafe.Slice((*T)(p), n)
+	clear(s)
+	return s
 }
 
 // flatSnapshot is kb_snapshot plus the name tables needed to read the outputs back.
@@ -89,6 +112,12 @@ func (s *Scheduler) flatten(snap *schdcache.Snapshot, heads []workload.Info, gen
 	}
 	slices.Sort(cohortNames)
 	resSet := map[corev1.ResourceName]struct{}{}
+	addFR := func(fr resources.FlavorResource) { // every flavor-resource that can index a table must be in the universe
+		if !slices.Contains(f.flavors, fr.Flavor) {
+			f.flavors = append(f.flavors, fr.Flavor)
+		}
+		resSet[fr.Resource] = struct{}{}
+	}
 	for _, n := range cqNames {
 		cq := snap.ClusterQueue(n)
 		f.cqs = append(f.cqs, cq)
@@ -101,6 +130,19 @@ func (s *Scheduler) flatten(snap *schdcache.Snapshot, heads []workload.Info, gen
 			for r := range rg.CoveredResources {
 				resSet[r] = struct{}{}
 			}
+		}
+		for fr := range cq.ResourceNode.Usage { // usage on a flavor the ClusterQueue no longer defines
+			addFR(fr)
+		}
+		for _, wi := range cq.Workloads { // admitted usage (preemption candidates)
+			for fr := range wi.FlavorResourceUsage() {
+				addFR(fr)
+			}
+		}
+	}
+	for _, name := range cohortNames { // quotas defined at cohort level only
+		for fr := range snap.Cohort(name).ResourceNode.Quotas {
+			addFR(fr)
 		}
 	}
 	for i := range heads {
@@ -116,11 +158,22 @@ func (s *Scheduler) flatten(snap *schdcache.Snapshot, heads []workload.Info, gen
 	sort.Slice(f.resources, func(i, j int) bool { return f.resources[i] < f.resources[j] }) // DRS tie-break compares names
 	Q, C_, F, R := len(cqNames), len(cohortNames), len(f.flavors), len(f.resources)
 	N, FR := Q+C_, F*R
+	k := s.kb
+	{ // size the page-locked block for this cycle: node tables + entries + admitted workloads + outputs, with slack
+		nAdm, nPs := 0, 0
+		for _, cq := range f.cqs {
+			nAdm += len(cq.Workloads)
+		}
+		for i := range heads {
+			nPs += len(heads[i].TotalRequests)
+		}
+		k.resetArena(uintptr(N*FR*32+N*64+Q*64+nAdm*(64+16*R)+len(heads)*128+nPs*(R*12+64)) + 1<<20)
+	}
 
-	parent := pinned[int32](N)
-	weight := pinned[float64](N)
-	nominal, blimit, llimit := pinned[int64](N*FR), pinned[int64](N*FR), pinned[int64](N*FR)
-	usage := pinned[int64](Q * FR)
+	parent := pinned[int32](k, N)
+	weight := pinned[float64](k, N)
+	nominal, blimit, llimit := pinned[int64](k, N*FR), pinned[int64](k, N*FR), pinned[int64](k, N*FR)
+	usage := pinned[int64](k, Q*FR)
 	for i := range blimit {
 		blimit[i], llimit[i] = noLimit, noLimit
 	}
@@ -138,9 +191,9 @@ func (s *Scheduler) flatten(snap *schdcache.Snapshot, heads []workload.Info, gen
 	}
 	cohortIdx := func(name kueue.CohortReference) int32 { return int32(Q + slices.Index(cohortNames, name)) }
 	// ---- ClusterQueue tables
-	within, reclaim, bwc := pinned[uint8](Q), pinned[uint8](Q), pinned[uint8](Q)
-	hasThr, thr := pinned[uint8](Q), pinned[int32](Q)
-	wcb, wcp, pref, strat, cqGen := pinned[uint8](Q), pinned[uint8](Q), pinned[uint8](Q), pinned[uint8](Q), pinned[int64](Q)
+	within, reclaim, bwc := pinned[uint8](k, Q), pinned[uint8](k, Q), pinned[uint8](k, Q)
+	hasThr, thr := pinned[uint8](k, Q), pinned[int32](k, Q)
+	wcb, wcp, pref, strat, cqGen := pinned[uint8](k, Q), pinned[uint8](k, Q), pinned[uint8](k, Q), pinned[uint8](k, Q), pinned[int64](k, Q)
 	var rgStart, rgMask, rgFlStart, rgFl []int32
 	rgStart, rgFlStart = append(rgStart, 0), append(rgFlStart, 0)
 	for i, cq := range f.cqs {
@@ -161,6 +214,9 @@ func (s *Scheduler) flatten(snap *schdcache.Snapshot, heads []workload.Info, gen
 			}
 		}
 		wcb[i], wcp[i], pref[i] = fungibilityCodes(cq.FlavorFungibility)
+		if s.queues.QueueingStrategy(cq.Name) == kueue.StrictFIFO { // read by kb_run_drain's requeue rules
+			strat[i] = C.KB_QUEUE_STRICT_FIFO
+		}
 		cqGen[i] = cq.AllocatableResourceGeneration
 		for _, rg := range cq.ResourceGroups {
 			var mask int32
@@ -256,7 +312,7 @@ func (s *Scheduler) flatten(snap *schdcache.Snapshot, heads []workload.Info, gen
 	for i := range headsIdx {
 		headsIdx[i] = int32(i)
 	}
-	// ---- struct (every table copied into pinned memory; copyPinned omitted for brevity: pinned[T](len) + copy)
+	// ---- struct (cp32 / cp64 / ... copy a Go slice into the evaluator's pinned block: pinned[T](k, len) + copy)
 	c := &f.c
 	c.n_cq, c.n_cohort, c.n_flavor, c.n_resource = C.int32_t(Q), C.int32_t(C_), C.int32_t(F), C.int32_t(R)
 	c.n_rg, c.n_wl, c.n_podset = C.int32_t(len(rgMask)), C.int32_t(len(heads)), C.int32_t(len(psCount))
@@ -286,12 +342,13 @@ func (s *Scheduler) flatten(snap *schdcache.Snapshot, heads []workload.Info, gen
 func (s *Scheduler) scheduleKB(heads []workload.Info, snap *schdcache.Snapshot) ([]entry, error) {
 	f := s.flatten(snap, heads, s.kb.staticGen)
 	H, P, R := len(heads), int(f.c.n_podset), len(f.resources)
-	decision, mode := pinned[uint8](H), pinned[uint8](H)
-	borrow, rank := pinned[int32](H), pinned[int32](H)
-	psFlavor, psMode, psTried := pinned[int8](P*R), pinned[int8](P*R), pinned[int8](P*R)
-	psCount, tgtStart := pinned[int32](P), pinned[int32](H+1)
+	k := s.kb // outputs come from the same per-cycle block as the inputs (flatten reset it)
+	decision, mode := pinned[uint8](k, H), pinned[uint8](k, H)
+	borrow, rank := pinned[int32](k, H), pinned[int32](k, H)
+	psFlavor, psMode, psTried := pinned[int8](k, P*R), pinned[int8](k, P*R), pinned[int8](k, P*R)
+	psCount, tgtStart := pinned[int32](k, P), pinned[int32](k, H+1)
 	capT := 4*int(f.c.n_adm) + 1024
-	tgtAdm, tgtReason := pinned[int32](capT), pinned[uint8](capT)
+	tgtAdm, tgtReason := pinned[int32](k, capT), pinned[uint8](k, capT)
 	out := C.kb_cycle_out{decision: (*C.uint8_t)(&decision[0]), mode: (*C.uint8_t)(&mode[0]), borrow: (*C.int32_t)(&borrow[0]),
 		commit_rank: (*C.int32_t)(&rank[0]), ps_flavor: (*C.int8_t)(&psFlavor[0]), ps_res_mode: (*C.int8_t)(&psMode[0]),
 		ps_tried_idx: (*C.int8_t)(&psTried[0]), ps_count: (*C.int32_t)(&psCount[0]), tgt_start: (*C.int32_t)(&tgtStart[0]),
@@ -302,10 +359,15 @@ func (s *Scheduler) scheduleKB(heads []workload.Info, snap *schdcache.Snapshot) 
 	if rc != 0 { // any error: the caller runs the stock Go cycle, outputs are not consumed
 		return nil, fmt.Errorf("kb_run_cycle: %d %s", int(rc), C.GoString(C.kb_last_error(s.kb.h)))
 	}
-	entries := make([]entry, H)
+	type ranked struct {
+		entry
+		root, rank int32
+	}
+	entries := make([]ranked, H)
 	row := 0
 	for e := range heads {
 		en := &entries[e]
+		en.rank = rank[e]
 		en.Info = heads[e]
 		en.clusterQueueSnapshot = f.cqs[slices.IndexFunc(f.cqs, func(c *schdcache.ClusterQueueSnapshot) bool { return c.Name == heads[e].ClusterQueue })]
 		en.assignment = s.assignmentFromRows(f, &heads[e], row, psFlavor, psMode, psTried, psCount, int(borrow[e])) // Flavors/Mode/TriedFlavorIdx/Count/Usage
@@ -322,9 +384,15 @@ func (s *Scheduler) scheduleKB(heads []workload.Info, snap *schdcache.Snapshot) 
 			en.status = skipped
 		}
 	}
-	// replay order: per root cohort by commit_rank (the iterator's pop order, scheduler.go:269)
-	sort.SliceStable(entries, func(i, j int) bool { return rank[i] < rank[j] })
-	return entries, nil
+	// replay order: the iterator's pop order inside every root cohort (commit_rank, scheduler.go:269).  The rank
+	// travels WITH the entry so the comparator stays consistent while the slice is permuted; root cohorts are
+	// independent, so interleaving them by rank is as good as any other order.
+	sort.SliceStable(entries, func(i, j int) bool { return entries[i].rank < entries[j].rank })
+	ordered := make([]entry, H)
+	for i := range entries {
+		ordered[i] = entries[i].entry
+	}
+	return ordered, nil
 }
 
 func policyCode(p kueue.PreemptionPolicy) uint8 {

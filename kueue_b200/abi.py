@@ -97,12 +97,12 @@ class kb_stats(C.Structure):
     _fields_ = [
         ("last_cycle_gpu_ms", C.c_double), ("last_h2d_ms", C.c_double), ("last_d2h_ms", C.c_double),
         ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64), ("kernel_launches", C.c_int32), ("sm_count", C.c_int32),
-        ("kernel_ms", C.c_float * 16), ("search_stat", C.c_int64 * 8),
+        ("kernel_ms", C.c_float * 20), ("search_stat", C.c_int64 * 8),
     ]
 
 
 KERNEL_NAMES = ["k_tree", "k_lone", "k_nominate", "k_scan_roots", "k_scatter", "k_admit", "k_rank", "k_nominate_search_fair",
-                "k_rank_admitted", "k_search_tables", "k_search_cells", "k_nominate_walk", "k_fair_prep", "k_drain", "k_tas", "k_cycle_root"]
+                "k_rank_admitted", "k_search_tables", "k_search_cells", "k_nominate_walk", "k_fair_prep", "k_drain", "k_tas", "k_cycle_root", "k_tas_leaf", "k_tas_reduce", "k_tas_select", "-"]
 
 
 class kb_drain_out(C.Structure):

@@ -187,6 +187,18 @@ static int32_t build_static(kb_handle *h, const kb_snapshot *s) {
       s->n_resource > KB_MAX_RESOURCES || s->n_wl < 0 || s->n_podset < 0 || s->n_adm < 0 || s->n_heads < 0)
     return fail(h, KB_ERR_INVALID, "bad dimensions");
   if (s->n_flavor > 127) return fail(h, KB_ERR_INVALID, "flavor index must fit int8");
+  if (s->n_rg < 0 || s->pods_resource < -1 || s->pods_resource >= s->n_resource) return fail(h, KB_ERR_INVALID, "bad n_rg / pods_resource");
+  // resource-group CSR tables (resource.go:31-38): monotone, in range, flavor indexes < F
+  if (Q > 0) {
+    if (s->cq_rg_start[0] != 0 || s->cq_rg_start[Q] != s->n_rg) return fail(h, KB_ERR_INVALID, "cq_rg_start must run from 0 to n_rg");
+    for (int q = 0; q < Q; q++) if (s->cq_rg_start[q + 1] < s->cq_rg_start[q]) return fail(h, KB_ERR_INVALID, "cq_rg_start not monotone");
+  }
+  if (s->n_rg > 0) {
+    if (s->rg_flavor_start[0] != 0) return fail(h, KB_ERR_INVALID, "rg_flavor_start[0] != 0");
+    for (int g = 0; g < s->n_rg; g++) if (s->rg_flavor_start[g + 1] < s->rg_flavor_start[g]) return fail(h, KB_ERR_INVALID, "rg_flavor_start not monotone");
+    for (int k = 0; k < s->rg_flavor_start[s->n_rg]; k++)
+      if (s->rg_flavors[k] < 0 || s->rg_flavors[k] >= s->n_flavor) return fail(h, KB_ERR_INVALID, "rg_flavors out of range");
+  }
   for (int n = 0; n < N; n++) {
     int p = s->parent[n];
     if (p != -1 && (p < Q || p >= N)) return fail(h, KB_ERR_INVALID, "parent must be a cohort node or -1");
@@ -360,7 +372,11 @@ static int32_t build_dynamic(kb_handle *h, const kb_snapshot *s) {
     if (s->wl_cq[w] < 0 || s->wl_cq[w] >= Q) return fail(h, KB_ERR_INVALID, "wl_cq out of range");
     if (s->wl_ps_start[w + 1] < s->wl_ps_start[w]) return fail(h, KB_ERR_INVALID, "wl_ps_start not monotone");
   }
-  if (s->n_wl && s->wl_ps_start[s->n_wl] != s->n_podset) return fail(h, KB_ERR_INVALID, "wl_ps_start[n_wl] != n_podset");
+  if (s->n_wl && (s->wl_ps_start[0] != 0 || s->wl_ps_start[s->n_wl] != s->n_podset)) return fail(h, KB_ERR_INVALID, "wl_ps_start must run from 0 to n_podset");
+  if (s->n_adm_use < 0 || (s->n_adm && (s->adm_use_start[0] != 0 || s->adm_use_start[s->n_adm] != s->n_adm_use)))
+    return fail(h, KB_ERR_INVALID, "adm_use_start must run from 0 to n_adm_use");
+  for (size_t i = 0; i < (size_t)s->n_podset * s->n_resource; i++)
+    if (s->ps_last_tried[i] < -1) return fail(h, KB_ERR_INVALID, "ps_last_tried below -1");
   h->one_head_per_cq = true;
   if (!h->drain_mode) {  // fairSharingIterator keeps one entry per CQ (fair_sharing_iterator.go:52-54)
     std::vector<char> seen(Q, 0);
@@ -1254,21 +1270,28 @@ extern "C" int32_t kb_tas_find(kb_handle *h, const kb_tas_topology *t, const kb_
   int32_t *d_leaf = (int32_t *)take(std::max(1, out->capacity), 4), *d_cnt = (int32_t *)take(std::max(1, out->capacity), 4);
   if (NQ) cudaMemsetAsync(T.n_out, 0, (size_t)(NQ + 1) * 4, h->stream);
   CUDA_TRY(h, cudaEventRecord(h->ev2, h->stream));
+  h->kev_n = 0;
+  int launches = 0;
   for (int rd = 0; rd < n_rounds; rd++) {
     int ns = (int)round_slot_req[rd].size(), nr = (int)round_req[rd].size();
     CUDA_TRY(h, cudaMemcpyAsync(d_slotreq, round_slot_req[rd].data(), (size_t)ns * 4, cudaMemcpyHostToDevice, h->stream));
     CUDA_TRY(h, cudaMemcpyAsync(d_round, round_req[rd].data(), (size_t)nr * 4, cudaMemcpyHostToDevice, h->stream));
-    k_tas_leaf<<<dim3((NL + 255) / 256, ns), 256, 0, h->stream>>>(T, d_slotreq, ns);
+    if (rd == 0) kmark(h, KB_K_TAS_LEAF);
+    k_tas_leaf<<<dim3((NL + 255) / 256, ns), 256, 0, h->stream>>>(T, d_slotreq, ns); launches++;
+    if (rd == 0) kmark(h, KB_K_TAS_REDUCE);
     for (int l = L - 2; l >= 0; l--) {
       int n = t->level_start[l + 1] - t->level_start[l];
-      k_tas_reduce<<<dim3((n + 127) / 128, ns), 128, 0, h->stream>>>(T, d_slotreq, ns, l);
+      k_tas_reduce<<<dim3((n + 127) / 128, ns), 128, 0, h->stream>>>(T, d_slotreq, ns, l); launches++;
     }
-    k_tas_select<<<std::min(nr, sel_grid), KB_TAS_THREADS, 0, h->stream>>>(T, d_round, nr);
+    if (rd == 0) kmark(h, KB_K_TAS_SELECT);
+    k_tas_select<<<std::min(nr, sel_grid), KB_TAS_THREADS, 0, h->stream>>>(T, d_round, nr); launches++;
+    if (rd == 0) kmark(h, KB_K_TAS);
   }
   if (NQ) {
-    k_scan_i32<<<1, 1024, 0, h->stream>>>(T.n_out, d_asg_start, NQ);
-    k_tas_compact<<<NQ, 64, 0, h->stream>>>(T, d_asg_start, d_leaf, d_cnt, out->capacity);
+    k_scan_i32<<<1, 1024, 0, h->stream>>>(T.n_out, d_asg_start, NQ); launches++;
+    k_tas_compact<<<NQ, 64, 0, h->stream>>>(T, d_asg_start, d_leaf, d_cnt, out->capacity); launches++;
   }
+  kmark(h, -1);
   CUDA_TRY(h, cudaEventRecord(h->ev3, h->stream));
   CUDA_TRY(h, cudaGetLastError());
   if (NQ) {
@@ -1283,6 +1306,12 @@ extern "C" int32_t kb_tas_find(kb_handle *h, const kb_tas_topology *t, const kb_
     CUDA_TRY(h, cudaMemcpy(out->asg_count, d_cnt, (size_t)ncopy * 4, cudaMemcpyDeviceToHost));
   }
   { float ms = 0; cudaEventElapsedTime(&ms, h->ev2, h->ev3); h->stats.last_cycle_gpu_ms = ms; }
+  h->stats.kernel_launches = launches;
+  for (int i = 0; i < KB_N_KERNELS; i++) h->stats.kernel_ms[i] = 0.f;
+  for (int i = 0; i + 1 < h->kev_n; i++) {
+    float kms = 0; cudaEventElapsedTime(&kms, h->kev[i], h->kev[i + 1]);
+    if (h->kev_id[i] >= 0) h->stats.kernel_ms[h->kev_id[i]] += kms;
+  }
   if (out->n_assigned > out->capacity) return fail(h, KB_ERR_CAPACITY, "tas: assignment buffer too small");
   return KB_OK;
 }

@@ -25,4 +25,5 @@ def test_algorithmic_bytes_table_covers_every_timed_kernel():
     from kueue_b200 import abi, synth
     ab = bench.algorithmic_bytes(synth.make_snapshot(1))
     for name in abi.KERNEL_NAMES:
-        assert name in ab or name in ("k_lone",), name
+        # the kb_tas_find kernels are accounted in bench.run_tas (cfg5), "-" is an unused timing slot
+        assert name in ab or name in ("k_lone", "k_tas_leaf", "k_tas_reduce", "k_tas_select", "-"), name

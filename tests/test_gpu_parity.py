@@ -378,3 +378,18 @@ def test_config3_sharded_device(ev, world):
         sub, m = shard.shard(snap, r, world, node_rank)
         parts.append((ev.run_cycle(sub), m))
     assert_cycle_equal(shard.merge(snap, parts), want)
+
+
+def _last_context_cases():
+    from tests.last_context_golden import DOC
+    return [pytest.param(n, id=f"lastctx:{n[:60]}") for n in DOC["cases"]]
+
+
+@pytest.mark.parametrize("name", _last_context_cases())
+def test_reference_last_scheduling_context_two_cycles(ev, name):
+    """TestLastSchedulingContext (scheduler_test.go:8569) on the device: two cycles with ps_tried_idx fed back as
+    ps_last_tried; the reference's admissions after the second cycle, and device == oracle in both cycles."""
+    from tests.last_context_golden import DOC, check
+    outs = check(DOC["cases"][name], ev.run_cycle)
+    for snap, got in outs:
+        assert_cycle_equal(got, oracle.run_cycle(snap))

@@ -12,7 +12,7 @@ CONST = {
     "corev1.ResourceEphemeralStorage": "ephemeral-storage", "corev1.LabelHostname": "kubernetes.io/hostname",
     "kueue.DefaultPodSetName": "main",
     "utiltesting.Ki": 2**10, "utiltesting.Mi": 2**20, "utiltesting.Gi": 2**30, "utiltesting.Ti": 2**40,
-    "metav1.ConditionTrue": "True", "metav1.ConditionFalse": "False",
+    "metav1.ConditionTrue": "True", "metav1.ConditionFalse": "False", "metav1.NamespaceDefault": "default",
 }
 IGNORED = set()
 
