@@ -145,6 +145,28 @@ def cpu_baseline(snap, budget_s: float = 12.0):
                       f"(the reference cycle is single-goroutine, scheduler.go:468)"}
 
 
+def pin_to_gpu_numa(local_rank: int):
+    """Bind this rank to the CPUs local to its GPU (sysfs local_cpulist of the PCI function) BEFORE any pinned host
+    memory is allocated: first-touch then places the page-locked snapshot on the GPU's NUMA node, so the per-cycle
+    DMA does not cross the inter-socket link.  Returns what was done for the bench line."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(local_rank)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        base = f"/sys/bus/pci/devices/{bdf}"
+        cpus = set()
+        for part in open(base + "/local_cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        node = open(base + "/numa_node").read().strip()
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return {"numa_node": int(node), "cpus": len(cpus)}
+    except Exception as e:  # noqa: BLE001 — sysfs layout differs between boxes; running unpinned is only slower
+        return {"numa_node": None, "error": type(e).__name__}
+    return {"numa_node": None}
+
+
 def drain_line(ev, config: int, cpu: bool):
     """Drain mode: kb_run_drain over the WHOLE pending set of the configuration (every pending
     workload sits in its ClusterQueue's queue on the device), next to the host definition of the drain iterating the
@@ -322,6 +344,7 @@ def main():
     ap.add_argument("--config", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-drain", action="store_true")
+    ap.add_argument("--scaling", default=None, choices=["weak", "strong"])
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -334,17 +357,26 @@ def main():
     import torch.distributed as dist
     from kueue_b200 import abi, native, synth
     torch.cuda.set_device(local_rank)
+    numa = pin_to_gpu_numa(local_rank) if world > 1 else {"numa_node": None}
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    # weak scaling: the cluster grows with the number of GPUs (world x the config's ClusterQueues and pending
-    # workloads); every rank keeps the root cohorts kueue_b200.shard assigns to it — root cohorts are independent
-    # coupling domains, so there is no collective on the data path and the host concatenates the decisions.
+    # Root cohorts are independent coupling domains (resource_node.go:106-108), so ranks take disjoint sets of roots
+    # (kueue_b200.shard) and there is no collective on the data path; the decisions are gathered and merged on rank 0.
+    #   weak scaling (default): the cluster grows with the number of GPUs (world x the config's ClusterQueues and
+    #     pending workloads);
+    #   strong scaling (--scaling strong, the default of cfg4): the configuration's own snapshot is split by root —
+    #     cfg4 has 10 root cohorts, so 8 GPUs hold at most 2 roots each (5x is the ceiling of this partition).
+    scaling = args.scaling or ("strong" if args.config == 4 else "weak")
+    shard_map, glob_heads = None, None
     if world > 1:
         from kueue_b200 import shard as kshard
-        base = synth.make_snapshot(args.config, W=1, Q=1) if False else None
         dflt = {1: (100, 10), 2: (100_000, 1_000), 3: (1_000_000, 10_000), 4: (1_000_000, 10_000)}[args.config]
-        glob = synth.make_snapshot(args.config, W=dflt[0] * world, Q=dflt[1] * world, heads=HEADS[args.config])
-        snap, _ = kshard.shard(glob, rank, world)
+        mult = 1 if scaling == "strong" else world
+        glob = synth.make_snapshot(args.config, W=dflt[0] * mult, Q=dflt[1] * mult, heads=HEADS[args.config])
+        if HEADS[args.config] == "one_per_cq":
+            glob = synth.compact_to_heads(glob)
+        glob_heads = glob.n_heads
+        snap, shard_map = kshard.shard(glob, rank, world)
         del glob
     else:
         snap = synth.make_snapshot(args.config, heads=HEADS[args.config])
@@ -388,12 +420,34 @@ def main():
     # steady state of the controller: ClusterQueue / Cohort specs do not change between cycles, so the shim keeps
     # static_generation constant and only usage + entries + admitted workloads cross PCIe every cycle.
     snap.static_generation = 1
+    def gather_and_merge():
+        """N > 1: the shards' decisions travel to every rank (one NCCL all-gather of H bytes per rank, padded to the
+        largest shard) and rank 0 scatters them to their global entry positions (shard.merge for the decision table)."""
+        if world == 1:
+            return None
+        mine = torch.zeros(hmax, dtype=torch.uint8, device="cuda")
+        mine[:snap.n_heads] = torch.from_numpy(out.decision).cuda()
+        allv = torch.empty(world * hmax, dtype=torch.uint8, device="cuda")
+        dist.all_gather_into_tensor(allv, mine)
+        if rank != 0:
+            return None
+        host = allv.cpu().numpy()
+        full = np.zeros(glob_heads, np.uint8)
+        for r in range(world):
+            full[all_maps[r]] = host[r * hmax:r * hmax + len(all_maps[r])]
+        return full
+    if world > 1:
+        sizes = [None] * world
+        dist.all_gather_object(sizes, shard_map.heads)
+        all_maps = sizes
+        hmax = max(len(m) for m in all_maps)
     for _ in range(2):
-        ev.run_cycle(snap, out)
+        ev.run_cycle(snap, out); gather_and_merge()
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         ev.run_cycle(snap, out)
+        gather_and_merge()
     barrier()
     e2e_s = time.perf_counter() - t0
     st = ev.stats()
@@ -424,14 +478,17 @@ def main():
         achieved = kbytes / (top_ms / 1e3) / 1e9 if top_ms > 0 else 0.0
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
             "dtype": "int64", "data": "synthetic",
             "config": {"workload": WORKLOADS[args.config], "heads": "all pending workloads (batched evaluator)" if HEADS[args.config] == "all" else "one head per ClusterQueue (reference cycle)",
                        "decisions_per_step_per_gpu": snap.n_heads, "l2": "512 MiB flush buffer written between timed steps",
                        "timing": "CUDA events on the library stream around the cycle's kernels, summed over steps, max over ranks",
                        "wall_ms_per_step_incl_flush": wall_ms / args.steps,
                        "e2e_static_tables": "quota / policy / topology tables uploaded once (static_generation constant), "
-                                            "usage + entries + admitted workloads copied every step"},
+                                            "usage + entries + admitted workloads copied every step",
+                       "multi_gpu": None if world == 1 else {"partition": "root cohorts (kueue_b200.shard), no data-path collective",
+                                                             "e2e_includes": "NCCL all-gather of the shards' decisions + merge on rank 0",
+                                                             "host_affinity": numa}},
             "clocks": clocks,
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches,

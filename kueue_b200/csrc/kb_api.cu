@@ -69,7 +69,7 @@ struct kb_handle {
   // host copies of the static tables build_dynamic consults every cycle (the caller's static pointers are not read
   // again while static_generation is unchanged)
   std::vector<int32_t> s_parent; std::vector<uint8_t> s_within_cq, s_reclaim_within;
-  std::vector<int32_t> sn_node, slot_base, nd_tin, nd_tout;
+  std::vector<int32_t> sn_node, slot_base, nd_tin, nd_tout, cq_path, cq_plen; int path_stride = 1;
   int max_root_adm = 1;
   int max_frl_len = 1;      // longest (root, flavor-resource) candidate bucket of this cycle
   int max_head_podsets = 1; // most podsets of one entry (bounds the columns a GetTargets search tracks)
@@ -289,6 +289,13 @@ static int32_t build_static(kb_handle *h, const kb_snapshot *s) {
   h->D.nTrees = ntrees;
   h->D.nLone = (int)h->lone.size();
   h->D.nRoots = nroots;
+  {  // static ClusterQueue -> root paths (global-table admit loop)
+    int maxd = 0;
+    for (int q = 0; q < Q; q++) maxd = std::max(maxd, h->depth[q]);
+    h->path_stride = maxd + 1;
+    h->cq_path.assign((size_t)std::max(1, Q) * h->path_stride, -1); h->cq_plen.assign(std::max(1, Q), 1);
+    for (int q = 0; q < Q; q++) { int k = 0; for (int t = q; t >= 0; t = s->parent[t]) h->cq_path[(size_t)q * h->path_stride + k++] = t; h->cq_plen[q] = k; }
+  }
   h->s_parent.assign(s->parent, s->parent + N);
   h->s_within_cq.assign(s->cq_within_cq, s->cq_within_cq + Q);
   h->s_reclaim_within.assign(s->cq_reclaim_within, s->cq_reclaim_within + Q);
@@ -444,6 +451,7 @@ static int32_t upload_impl(kb_handle *h, const kb_snapshot *s, bool sync) {
     sneed(N, 4); sneed(N, 4); sneed(N, 4); sneed(D.nTrees + 1, 4); sneed(h->tree_nodes.size(), 4); sneed(h->tree_level.size(), 4);
     sneed(h->lone.size(), 4); sneed(N, 4); sneed(h->tree_flat.size(), 1); sneed(N + 1, 4); sneed(h->child_list.size(), 4); sneed(h->root_cq_start.size(), 4);
     sneed(h->sn_node.size(), 4); sneed(h->slot_base.size(), 4); sneed(h->nd_tin.size(), 4); sneed(h->nd_tout.size(), 4);
+    sneed(h->cq_path.size(), 4); sneed(h->cq_plen.size(), 4);
     if (!h->sarena.reserve(stot + 4096)) return fail(h, KB_ERR_CUDA, "cudaMalloc failed");
     h->sarena.reset();
 #define SUP(field, src, n) CUDA_TRY(h, up(h, h->sarena, D.field, src, (size_t)(n), &bytes))
@@ -464,6 +472,8 @@ static int32_t upload_impl(kb_handle *h, const kb_snapshot *s, bool sync) {
     SUP(root_cq_start, h->root_cq_start.data(), h->root_cq_start.size());
     SUP(sn_node, h->sn_node.data(), h->sn_node.size()); SUP(slot_base, h->slot_base.data(), h->slot_base.size());
     SUP(nd_tin, h->nd_tin.data(), h->nd_tin.size()); SUP(nd_tout, h->nd_tout.data(), h->nd_tout.size());
+    SUP(cq_path, h->cq_path.data(), h->cq_path.size()); SUP(cq_plen, h->cq_plen.data(), h->cq_plen.size());
+    D.path_stride = h->path_stride;
 #undef SUP
     memcpy(h->s_dims, dims, sizeof(dims));
     h->static_gen = s->static_generation;

@@ -86,6 +86,9 @@ struct DevSnap {
   const int32_t *tree_level;  // [nTrees][KB_LEVELS] start (relative) of each depth level
   const int32_t *local_idx;   // [N] position of the node inside its tree (0 for lone CQs)
   const int32_t *lone_cqs;    // CQs without a cohort
+  const int32_t *cq_path;     // [Q][path_stride] node ids from the ClusterQueue up to its root (-1 padded)
+  const int32_t *cq_plen;     // [Q] path length
+  int path_stride;
   const int32_t *child_start; // [N+1] children CSR: child cohorts ascending, then child CQs ascending
   const int32_t *child_list;
   int32_t *cq_adm_start;      // [Q+1] admitted workloads grouped by CQ (device-built, kb_rank.cuh)

@@ -1290,8 +1290,42 @@ struct Tab {
   __device__ __forceinline__ int parent(int nd) const { return kSmem ? lparent[nd] : D->parent[nd]; }
   __device__ __forceinline__ int handle(int node) const { return kSmem ? D->local_idx[node] : node; }
   // available() resource_node.go:104-118 along a staged path (path[0] = CQ ... path[plen-1] = root)
+  // Global-table mode (trees too large for shared memory): every level of a walk costs an L2 round trip, so the
+  // operands of ALL levels of the path (<= KB_PF) are requested first and the level-by-level arithmetic of
+  // available() / addUsage / removeUsage then runs on registers — one memory latency per walk instead of one per level.
+#define KB_PF 6
+  template <bool S>
+  __device__ __forceinline__ void prefetch(const int *path, int plen, int fr, i64 (&u)[KB_PF], i64 (&sb)[KB_PF], i64 (&ll)[KB_PF], i64 (&b)[KB_PF], bool want_bl) const {
+#pragma unroll
+    for (int k = 0; k < KB_PF; k++) {
+      u[k] = sb[k] = 0; ll[k] = b[k] = KB_NO_LIMIT;
+      if (k < plen) {
+        size_t c = (size_t)path[k] * FR + fr;
+        u[k] = S ? shadow[c] : __ldcg(&D->usage[c]);
+        sb[k] = D->subtree[c]; ll[k] = D->llimit[c];
+        if (want_bl) b[k] = D->blimit[c];
+      }
+    }
+  }
   template <bool S = false>
   __device__ inline i64 avail(const int *path, int plen, int fr) const {
+    if constexpr (!kSmem) {
+      if (plen <= KB_PF) {
+        i64 u[KB_PF], sb[KB_PF], ll[KB_PF], b[KB_PF];
+        prefetch<S>(path, plen, fr, u, sb, ll, b, true);
+        i64 a = 0;
+#pragma unroll
+        for (int k = KB_PF - 1; k >= 0; k--) {
+          if (k >= plen) continue;
+          if (k == plen - 1) { a = sb[k] - u[k]; continue; }
+          i64 l = local_quota(sb[k], ll[k]);
+          i64 pa = a;
+          if (b[k] != KB_NO_LIMIT) pa = imin((sb[k] - l) - imax(0, u[k] - l) + b[k], pa);
+          a = imax(0, l - u[k]) + pa;
+        }
+        return a;
+      }
+    }
     int rt = path[plen - 1];
     i64 a = Sub(rt, fr) - Ux<S>(rt, fr);
     for (int k = plen - 2; k >= 0; k--) {
@@ -1303,28 +1337,25 @@ struct Tab {
     }
     return a;
   }
+  // addUsage :137-145 / removeUsage :149-158 along an explicit path (path[0] = the ClusterQueue)
   template <bool S = false>
-  __device__ inline void add_node(int nd, int fr, i64 val) const {  // addUsage :137-145 walking parents
-    while (true) {
-      i64 u = Ux<S>(nd, fr), la = imax(0, LQ(nd, fr) - u);
-      setUx<S>(nd, fr, u + val);
-      int p = parent(nd);
-      if (p < 0 || !(val > la)) break;
-      val -= la; nd = p;
+  __device__ inline void add(const int *path, int plen, int fr, i64 val) const {
+    if constexpr (!kSmem) {
+      if (plen <= KB_PF) {
+        i64 u[KB_PF], sb[KB_PF], ll[KB_PF], b[KB_PF];
+        prefetch<S>(path, plen, fr, u, sb, ll, b, false);
+        bool go = true;
+#pragma unroll
+        for (int k = 0; k < KB_PF; k++) {
+          if (k >= plen || !go) continue;
+          i64 la = imax(0, local_quota(sb[k], ll[k]) - u[k]);
+          setUx<S>(path[k], fr, u[k] + val);
+          if (!(k + 1 < plen && val > la)) go = false;
+          val -= la;
+        }
+        return;
+      }
     }
-  }
-  template <bool S = false>
-  __device__ inline void remove_node(int nd, int fr, i64 val) const {  // removeUsage :149-158
-    while (true) {
-      i64 u = Ux<S>(nd, fr), stored = u - LQ(nd, fr);
-      setUx<S>(nd, fr, u - val);
-      int p = parent(nd);
-      if (stored <= 0 || p < 0) break;
-      val = imin(val, stored); nd = p;
-    }
-  }
-  template <bool S = false>
-  __device__ inline void add(const int *path, int plen, int fr, i64 val) const {  // addUsage :137-145
     for (int k = 0; k < plen; k++) {
       int nd = path[k];
       i64 u = Ux<S>(nd, fr);
@@ -1333,6 +1364,58 @@ struct Tab {
       if (!(k + 1 < plen && val > la)) break;
       val -= la;
     }
+  }
+  template <bool S = false>
+  __device__ inline void remove(const int *path, int plen, int fr, i64 val) const {
+    if constexpr (!kSmem) {
+      if (plen <= KB_PF) {
+        i64 u[KB_PF], sb[KB_PF], ll[KB_PF], b[KB_PF];
+        prefetch<S>(path, plen, fr, u, sb, ll, b, false);
+        bool go = true;
+#pragma unroll
+        for (int k = 0; k < KB_PF; k++) {
+          if (k >= plen || !go) continue;
+          i64 stored = u[k] - local_quota(sb[k], ll[k]);
+          setUx<S>(path[k], fr, u[k] - val);
+          if (stored <= 0 || k + 1 >= plen) go = false;
+          val = imin(val, stored);
+        }
+        return;
+      }
+    }
+    for (int k = 0; k < plen; k++) {
+      int nd = path[k];
+      i64 u = Ux<S>(nd, fr), stored = u - LQ(nd, fr);
+      setUx<S>(nd, fr, u - val);
+      if (stored <= 0 || k + 1 >= plen) break;
+      val = imin(val, stored);
+    }
+  }
+  // the same starting from a node (an admitted workload's ClusterQueue): global-table mode reads the node's static
+  // path (DevSnap::cq_path), shared-memory mode chases the staged parent handles
+  template <bool S = false>
+  __device__ inline void add_node(int nd, int fr, i64 val) const {
+    if constexpr (!kSmem) add<S>(D->cq_path + (size_t)nd * D->path_stride, D->cq_plen[nd], fr, val);
+    else
+      while (true) {
+        i64 u = Ux<S>(nd, fr), la = imax(0, LQ(nd, fr) - u);
+        setUx<S>(nd, fr, u + val);
+        int p = parent(nd);
+        if (p < 0 || !(val > la)) break;
+        val -= la; nd = p;
+      }
+  }
+  template <bool S = false>
+  __device__ inline void remove_node(int nd, int fr, i64 val) const {
+    if constexpr (!kSmem) remove<S>(D->cq_path + (size_t)nd * D->path_stride, D->cq_plen[nd], fr, val);
+    else
+      while (true) {
+        i64 u = Ux<S>(nd, fr), stored = u - LQ(nd, fr);
+        setUx<S>(nd, fr, u - val);
+        int p = parent(nd);
+        if (stored <= 0 || p < 0) break;
+        val = imin(val, stored); nd = p;
+      }
   }
 };
 
@@ -1377,7 +1460,13 @@ __device__ inline void commit_entry(const DevSnap &D, const Tab<kSmem> &T, int *
   const int FR = D.FR;
   if (lane == 0) D.rank[e] = rank;
   if (mode == KB_MODE_NOFIT) { if (lane == 0) D.decision[e] = KB_DEC_NOFIT; return; }
-  if (lane == 0) { int pl = 0; for (int t = nd; t >= 0; t = T.parent(t)) s_path[pl++] = t; s_path[KB_MAX_DEPTH + 1] = pl; }
+  if constexpr (!kSmem) {  // static path table: one coalesced row instead of a chain of dependent parent loads
+    int pl = D.cq_plen[nd];
+    if (lane < pl) s_path[lane] = D.cq_path[(size_t)nd * D.path_stride + lane];
+    if (lane == 0) s_path[KB_MAX_DEPTH + 1] = pl;
+  } else {
+    if (lane == 0) { int pl = 0; for (int t = nd; t >= 0; t = T.parent(t)) s_path[pl++] = t; s_path[KB_MAX_DEPTH + 1] = pl; }
+  }
   __syncwarp();
   int plen = s_path[KB_MAX_DEPTH + 1];
   bool shadow = *T.shadow_on != 0;

@@ -88,6 +88,8 @@ __global__ void k_tas_reduce(TasDev T, const int32_t *slot_req, int n_slots, int
 // Phase 2: one CTA per podset request.
 // ---------------------------------------------------------------------------
 #define KB_TAS_THREADS 128
+#define KB_TAS_LOCAL 4        // cached candidates per thread
+#define KB_TAS_CACHE_MIN 2048 // level sets larger than this are walked through the sorted cache
 struct TasKey { int v, k0, k1, d; };  // lexicographic; d < 0 = none
 __device__ __forceinline__ bool tk_less(const TasKey &a, const TasKey &b) {
   if (b.d < 0) return a.d >= 0;
@@ -121,6 +123,7 @@ struct TasSel {
   const int32_t *st, *sl;  // counts of the request's shape (read-only)
   bool lfc;                // LeastFreeCapacity order (:1291-1294)
   TasKey *s_red;
+  TasKey *s_cache; int *s_cmeta;  // sorted candidate cache of a large level set + {a, b, filter, arg, n valid, complete}
   // sort key of sortedDomains :1495-1515: sliceState (desc, or asc under LeastFreeCapacity), state asc, levelValues asc
   __device__ __forceinline__ TasKey key(int d) const { TasKey k; k.v = 0; k.k0 = lfc ? sl[d] : -sl[d]; k.k1 = st[d]; k.d = d; return k; }
   template <typename F> __device__ inline void for_each(const TasSet &S, F f) const {
@@ -134,7 +137,82 @@ struct TasSel {
   // sliceState >= arg; filter 2 / 3: skip domains whose sliceState / state is 0 — the reference appends them with zero
   // pods (they sort first under LeastFreeCapacity), which changes nothing downstream: their descendants get zero
   // pods and buildTopologyAssignmentForLevels drops zero counts (:1443-1446)
+  // Large level sets (tens of thousands of hosts) are walked through a sorted CACHE of their smallest keys: one pass
+  // keeps every thread's KB_TAS_LOCAL best candidates, the block sorts their union in shared memory, and all keys up
+  // to T = the smallest "worst kept key" among the threads that had to drop something are provably complete (every
+  // dropped key is larger than its thread's worst kept key >= T).  Successive next() calls are served from the cache;
+  // a new pass starts behind the last served key only when the walk runs past T.
   __device__ inline TasKey next(const TasSet &S, TasKey after, int filter, int arg) const {
+    if (!S.parents && S.b - S.a > KB_TAS_CACHE_MIN) return next_cached(S, after, filter, arg);
+    return next_pass(S, after, filter, arg);
+  }
+  __device__ inline TasKey next_cached(const TasSet &S, TasKey after, int filter, int arg) const {
+    const TasKey none{0, 0, 0, -1};
+    for (int attempt = 0; attempt < 2; attempt++) {
+      __syncthreads();
+      // the cache answers walks that are at or behind the key it was filled from
+      const TasKey from = s_cache[KB_TAS_THREADS * KB_TAS_LOCAL];
+      const bool valid = s_cmeta[0] == S.a && s_cmeta[1] == S.b && s_cmeta[2] == filter && s_cmeta[3] == arg && s_cmeta[4] >= 0 &&
+                         (from.d < 0 || (after.d >= 0 && !tk_less(after, from)));
+      if (valid) {
+        const int n = s_cmeta[4];
+        // first cached key after `after` (the cache is sorted ascending); lanes search disjoint strides, block-min picks the first
+        TasKey best = none;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) { TasKey k = s_cache[i]; if (after.d < 0 || tk_less(after, k)) { best = k; break; } }
+        best = tk_block_min(best, s_red);
+        if (best.d >= 0) return best;
+        if (s_cmeta[5]) return none;  // the cache held every qualifying domain
+        // past the complete part: is `after` at or beyond the cache's first key?  then refill behind it, else (walk restarted
+        // before the cached window) refill from `after` as well
+      }
+      // ---- fill: one pass, KB_TAS_LOCAL best per thread
+      TasKey loc[KB_TAS_LOCAL];
+#pragma unroll
+      for (int j = 0; j < KB_TAS_LOCAL; j++) loc[j] = none;
+      bool dropped = false;
+      for (int d = S.a + threadIdx.x; d < S.b; d += blockDim.x) {
+        TasKey k = key(d);
+        if (after.d >= 0 && !tk_less(after, k)) continue;
+        if (filter == 1 && sl[d] < arg) continue;
+        if (filter == 2 && sl[d] == 0) continue;
+        if (filter == 3 && st[d] == 0) continue;
+        if (loc[KB_TAS_LOCAL - 1].d >= 0 && !tk_less(k, loc[KB_TAS_LOCAL - 1])) { dropped = true; continue; }
+        if (loc[KB_TAS_LOCAL - 1].d >= 0) dropped = true;
+        loc[KB_TAS_LOCAL - 1] = k;
+#pragma unroll
+        for (int j = KB_TAS_LOCAL - 1; j > 0; j--) if (tk_less(loc[j], loc[j - 1])) { TasKey t = loc[j]; loc[j] = loc[j - 1]; loc[j - 1] = t; }
+      }
+      __syncthreads();
+#pragma unroll
+      for (int j = 0; j < KB_TAS_LOCAL; j++) s_cache[threadIdx.x * KB_TAS_LOCAL + j] = loc[j];
+      // T: smallest worst-kept key among the threads that dropped something
+      TasKey tmin = dropped ? loc[KB_TAS_LOCAL - 1] : none;
+      tmin = tk_block_min(tmin, s_red);
+      // bitonic sort of the KB_TAS_THREADS * KB_TAS_LOCAL cached keys (`none` sorts last)
+      const int NC = KB_TAS_THREADS * KB_TAS_LOCAL;
+      for (int k2 = 2; k2 <= NC; k2 <<= 1)
+        for (int j = k2 >> 1; j > 0; j >>= 1) {
+          __syncthreads();
+          for (int i = threadIdx.x; i < NC; i += blockDim.x) {
+            int l = i ^ j;
+            if (l > i) {
+              TasKey a = s_cache[i], b = s_cache[l];
+              bool up = (i & k2) == 0;
+              if (up ? tk_less(b, a) : tk_less(a, b)) { s_cache[i] = b; s_cache[l] = a; }
+            }
+          }
+        }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        int n = 0;
+        while (n < NC && s_cache[n].d >= 0 && (tmin.d < 0 || !tk_less(tmin, s_cache[n]))) n++;  // keys <= T are complete
+        s_cmeta[0] = S.a; s_cmeta[1] = S.b; s_cmeta[2] = filter; s_cmeta[3] = arg; s_cmeta[4] = n; s_cmeta[5] = tmin.d < 0;
+        s_cache[NC] = after;
+      }
+    }
+    return next_pass(S, after, filter, arg);  // not reached in practice: a fresh cache always holds the successor when one exists
+  }
+  __device__ inline TasKey next_pass(const TasSet &S, TasKey after, int filter, int arg) const {
     TasKey best; best.d = -1; best.v = best.k0 = best.k1 = 0;
     for_each(S, [&](int d) {
       TasKey k = key(d);
@@ -167,7 +245,7 @@ struct TasSel {
 };
 
 // result lists of one CTA: [domain][assigned state][assigned sliceState], two buffers (current / next level)
-__device__ inline void tas_select_one(const TasDev &T, const int q, TasKey *s_red, int &s_n) {
+__device__ inline void tas_select_one(const TasDev &T, const int q, TasKey *s_red, int &s_n, TasKey *s_cache, int *s_cmeta) {
   const int cap = T.list_cap;
   int32_t *base = T.lists + (size_t)blockIdx.x * 6 * cap;
   int32_t *c_d = base, *c_st = base + cap, *c_sl = base + 2 * cap, *n_d = base + 3 * cap, *n_st = base + 4 * cap, *n_sl = base + 5 * cap;
@@ -179,7 +257,9 @@ __device__ inline void tas_select_one(const TasDev &T, const int q, TasKey *s_re
   if (T.pred[q] >= 0 && T.status[T.pred[q]] != KB_TAS_OK) { finish(-1, 0); return; }  // the chain stopped at an earlier podset (:551-553)
   if (levelIdx < 0 || levelIdx >= L || sliceLevel < 0 || sliceLevel >= L || levelIdx > sliceLevel || sliceSize < 1) { finish(KB_TAS_BAD_REQUEST, 0); return; }
   const int slot = T.slot[q];
-  TasSel X{T, T.state + (size_t)slot * T.n_domains, T.slice + (size_t)slot * T.n_domains, unconstrained && (flags & KB_TAS_PROFILE_MIXED), s_red};
+  TasSel X{T, T.state + (size_t)slot * T.n_domains, T.slice + (size_t)slot * T.n_domains, unconstrained && (flags & KB_TAS_PROFILE_MIXED), s_red, s_cache, s_cmeta};
+  if (threadIdx.x == 0) s_cmeta[4] = -1;  // the cache belongs to one request (its shape's counts)
+  __syncthreads();
   const bool lfc = X.lfc;
   const TasKey none{0, 0, 0, -1};
   // ---- findLevelWithFitDomains :1200-1282 (no leaders)
@@ -312,10 +392,12 @@ __device__ inline void tas_select_one(const TasDev &T, const int q, TasKey *s_re
 
 __global__ void __launch_bounds__(KB_TAS_THREADS) k_tas_select(TasDev T, const int32_t *round_req, int n_round) {
   __shared__ TasKey s_red[KB_TAS_THREADS / 32];
+  __shared__ TasKey s_cache[KB_TAS_THREADS * KB_TAS_LOCAL + 1];  // + the key the cache was filled from
+  __shared__ int s_cmeta[8];
   __shared__ int s_n;
   for (int i = blockIdx.x; i < n_round; i += gridDim.x) {
     __syncthreads();
-    tas_select_one(T, round_req[i], s_red, s_n);
+    tas_select_one(T, round_req[i], s_red, s_n, s_cache, s_cmeta);
   }
 }
 
