@@ -475,6 +475,13 @@ def main():
         peak = float(peaks.get("hbm_gbs", 6650.0))
         kname = abi.KERNEL_NAMES[top]
         kbytes = ab.get(kname, ab["total"])
+        ss = list(st.search_stat)
+        if ss[0] and kname in ("k_search_cells", "k_nominate_walk"):
+            # streamed 32 B candidate records of the last cycle (kb_stats.search_stat: [1] all records, [4] those of the
+            # multi-column GetTargets searches of k_nominate_walk) on top of the per-entry floor; the quota columns a
+            # search stages are shared by the searches of one bucket and are part of the floor's node tables
+            multi = ss[4]
+            kbytes = float((ss[1] - multi) * 32 + ab[kname]) if kname == "k_search_cells" else float(multi * 32 + ab[kname])
         achieved = kbytes / (top_ms / 1e3) / 1e9 if top_ms > 0 else 0.0
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),

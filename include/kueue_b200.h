@@ -189,6 +189,10 @@ typedef struct kb_snapshot {
                                   (workload.go:311-343).  Read by kb_run_drain only: a NoFit head of a BestEffortFIFO
                                   queue moves every queued workload of the same class to the inadmissible set
                                   (handleInadmissibleHash, cluster_queue.go:408-425). */
+  const int32_t *ps_group;     /* [n_podset] PodSetGroupName of the podset's TopologyRequest as a small id, -1 = none.
+                                  Consecutive podsets of one workload with the same id get their flavors together: the
+                                  requests are summed and one search serves the group (flavorassigner.go:613-675;
+                                  LeaderWorkerSet leader + workers).  The podsets of a group must be adjacent. */
 
   /* ---- upload hint ---- */
   int64_t static_generation;   /* 0 = none.  When non-zero and equal to the value of the previous call on
@@ -248,7 +252,8 @@ typedef struct kb_stats {
    * CUDA events recorded on the launching stream around each kernel. */
   float   kernel_ms[KB_N_KERNELS];
   /* target-search counters of the last cycle: [0] searches run, [1] candidate records classified (32 B each),
-   * [2] candidates visited by the greedy loops, [3] workloads removed (incl. fill-back), [4] GetTargets calls,
+   * [2] candidates visited by the greedy loops, [3] workloads removed (incl. fill-back), [4] the part of [1] classified by
+   * multi-column searches (GetTargets of k_nominate_walk),
    * [5..7] SM clock cycles summed over warps: column load / classification / greedy (diagnostics) */
   int64_t search_stat[8];
 } kb_stats;

@@ -69,7 +69,7 @@ class kb_snapshot(C.Structure):
         ("adm_qr_ts", _P(C.c_int64)), ("adm_uid", _P(C.c_int64)), ("adm_evicted", _P(C.c_uint8)),
         ("adm_use_start", _P(C.c_int32)), ("adm_use_fr", _P(C.c_int32)), ("adm_use_qty", _P(C.c_int64)),
         ("heads", _P(C.c_int32)),
-        ("wl_has_quota_reservation", _P(C.c_uint8)), ("wl_sched_hash", _P(C.c_int64)),
+        ("wl_has_quota_reservation", _P(C.c_uint8)), ("wl_sched_hash", _P(C.c_int64)), ("ps_group", _P(C.c_int32)),
         ("static_generation", C.c_int64),
     ]
 
@@ -160,9 +160,9 @@ _DT = {
     "adm_cq": np.int32, "adm_priority": np.int32, "adm_ts": np.int64, "adm_qr_ts": np.int64, "adm_uid": np.int64,
     "adm_evicted": np.uint8, "adm_use_start": np.int32, "adm_use_fr": np.int32, "adm_use_qty": np.int64,
     "heads": np.int32,
-    "wl_has_quota_reservation": np.uint8, "wl_sched_hash": np.int64,
+    "wl_has_quota_reservation": np.uint8, "wl_sched_hash": np.int64, "ps_group": np.int32,
 }
-OPTIONAL_FIELDS = ("wl_has_quota_reservation", "wl_sched_hash")  # NULL in kb_snapshot when absent
+OPTIONAL_FIELDS = ("wl_has_quota_reservation", "wl_sched_hash", "ps_group")  # NULL in kb_snapshot when absent
 ARRAY_FIELDS = list(_DT.keys())
 # tables the library keeps resident while kb_snapshot.static_generation is unchanged (include/kueue_b200.h)
 STATIC_FIELDS = ("parent", "fair_weight", "nominal", "borrow_limit", "lend_limit", "cq_within_cq", "cq_reclaim_within",

@@ -210,6 +210,7 @@ class MakeWorkload:
         self.admission: Optional[MakeAdmission] = None
         self.quota_reserved_ns: Optional[int] = None
         self.evicted = False
+        self.reclaimable: Dict[str, int] = {}
         self.conditions: Dict[str, tuple] = {}  # type -> (status, reason, lastTransitionTime ns); SetStatusCondition keeps one per type
         self.last_tried: Optional[List[Dict[str, int]]] = None
         self.last_gen = 0
@@ -224,6 +225,7 @@ class MakeWorkload:
     def Request(self, res: str, q): self.podsets[0].Request(res, q); return self
     def PodSets(self, *ps: MakePodSet): self.podsets = list(ps); return self
     def Evicted(self): self.evicted = True; return self
+    def ReclaimablePods(self, counts: Dict[str, int]): self.reclaimable = dict(counts); return self  # Status.ReclaimablePods
 
     def Condition(self, type: str, status: bool, reason: str = "", last_transition_ns: int = 0):
         self.conditions[type] = (bool(status), reason, int(last_transition_ns))
@@ -307,7 +309,7 @@ def flatten(cqs: Sequence[MakeClusterQueue], cohorts: Sequence[MakeCohort] = (),
             heads: Optional[Sequence[str]] = None, now_ns: int = 0,
             flavors: Optional[Sequence[str]] = None, extra_resources: Sequence[str] = (),
             resource_flavors: Optional[Sequence["MakeResourceFlavor"]] = None,
-            pods_ready_requeuing: str = "Eviction"):
+            pods_ready_requeuing: str = "Eviction", reclaimable_pods: bool = True):
     """Build (FlatSnapshot, Index).
 
     `usage` optionally overrides ClusterQueue usage as {cq: {(flavor, resource): int64}}
@@ -428,11 +430,14 @@ def flatten(cqs: Sequence[MakeClusterQueue], cohorts: Sequence[MakeCohort] = (),
         w_lg.append(w.last_gen if w.last_tried is not None else -1)
         for pi, ps in enumerate(w.podsets):
             row = np.zeros(R, np.int64); mask = 0
+            count = ps.count
+            if reclaimable_pods:  # podSetsCountsAfterReclaim workload.go:547-559 (feature gate ReclaimablePods, on by default)
+                count -= getattr(w, "reclaimable", {}).get(ps.name, 0)
             for rname, q in ps.requests.items():
                 r = resources.index(rname)
-                row[r] = resource_value(rname, q) * ps.count  # totalRequestsFromPodSets workload.go:567-598
+                row[r] = resource_value(rname, q) * count  # totalRequestsFromPodSets workload.go:567-598
                 mask |= 1 << r
-            p_req.append(row); p_mask.append(mask); p_cnt.append(ps.count)
+            p_req.append(row); p_mask.append(mask); p_cnt.append(count)
             p_min.append(-1 if ps.min_count is None else ps.min_count)
             ok = (1 << 64) - 1
             if ps.flavor_ok is not None:

@@ -384,6 +384,16 @@ static int32_t build_dynamic(kb_handle *h, const kb_snapshot *s) {
     return fail(h, KB_ERR_INVALID, "adm_use_start must run from 0 to n_adm_use");
   for (size_t i = 0; i < (size_t)s->n_podset * s->n_resource; i++)
     if (s->ps_last_tried[i] < -1) return fail(h, KB_ERR_INVALID, "ps_last_tried below -1");
+  if (s->ps_group)  // the podsets of one PodSetGroup are adjacent rows of their workload
+    for (int w = 0; w < s->n_wl; w++)
+      for (int a = s->wl_ps_start[w]; a < s->wl_ps_start[w + 1]; a++) {
+        int g = s->ps_group[a];
+        if (g < 0 || (a > s->wl_ps_start[w] && s->ps_group[a - 1] == g)) continue;
+        int b = a + 1;
+        while (b < s->wl_ps_start[w + 1] && s->ps_group[b] == g) b++;
+        for (int c = b; c < s->wl_ps_start[w + 1]; c++)
+          if (s->ps_group[c] == g) return fail(h, KB_ERR_INVALID, "ps_group: podsets of one group must be adjacent");
+      }
   h->one_head_per_cq = true;
   if (!h->drain_mode) {  // fairSharingIterator keeps one entry per CQ (fair_sharing_iterator.go:52-54)
     std::vector<char> seen(Q, 0);
@@ -491,7 +501,7 @@ static int32_t upload_impl(kb_handle *h, const kb_snapshot *s, bool sync) {
   need(W, 4); need(W, 4); need(W, 8); need(W, 8); need(W, 8); need(W + 1, 4);
   need(P * R, 8); need(P, 4); need(P, 4); need(P, 4); need(P, 8); need(P * R, 1);
   need(A, 4); need(A, 4); need(A, 8); need(A, 8); need(A, 8); need(A, 1); need(A + 1, 4); need(AUc, 4); need(AUc, 8);
-  need(H, 4); need(W, 1); need(W, 8); need(Q, 4);
+  need(H, 4); need(W, 1); need(W, 8); need(P, 4); need(Q, 4);
   need(Q + 1, 4); need(A, 4); need(A, 4); need(Q, 4); need(nroots, 4);
   need(nroots + 2, 4); need(Q + 2, 4); need(A, 8); need(A, 8); need(A, 4); need(A, 4);
   size_t rk_temp_bytes = 0;
@@ -574,7 +584,7 @@ static int32_t upload_impl(kb_handle *h, const kb_snapshot *s, bool sync) {
   size_t pool_cap = A * 4 + 1024;
   need(A, 4); need(nroots + 1, 4); need(H, 4); need(2, 4); need(H, 4); need(H, 4); need(pool_cap, 4); need(pool_cap, 1); need(1, 4);
   need(A, 1); need(A, 4); need(nroots, 4); need(A ? NF : 1, 8);
-  need(G * acap, 4); need(G * acap, 4); need(G * acap, 4); need(G * acap, 4); need(G * ncap, 4); need(G * acap, 1); need(G * acap, 1); need(G * ncap, 1); need(G * ncap, 1);
+  need(G * acap, 4); need(G * acap, 4); need(G * acap, 4); need(G * acap, 4); need(G * ncap, 4); need(G * acap, 1); need(G * acap, 1); need(G * ncap, 1); need(G * ncap, 1); need(G * ncap, 1); need(G * ncap, 8); need(G * ncap, 1);
   if (fair && A && !h->search_smem) need(G * ncap * FR, 8);
   // classical search tables + per-warp scratch
   const size_t nbuckets = (size_t)nroots * FR;
@@ -604,7 +614,8 @@ static int32_t upload_impl(kb_handle *h, const kb_snapshot *s, bool sync) {
   UPC(adm_qr_ts, (const i64 *)s->adm_qr_ts, A_in, A); UPC(adm_uid, (const i64 *)s->adm_uid, A_in, A); UPC(adm_evicted, s->adm_evicted, A_in, A);
   UPC(adm_use_start, s->adm_use_start, A_in + 1, A + 1); UPC(adm_use_fr, s->adm_use_fr, AU_in, AUc); UPC(adm_use_qty, (const i64 *)s->adm_use_qty, AU_in, AUc);
   if (!h->drain_mode) UP(heads, s->heads, H);
-  D.wl_has_qr = nullptr; D.wl_sched_hash = nullptr;
+  D.wl_has_qr = nullptr; D.wl_sched_hash = nullptr; D.ps_group = nullptr;
+  if (s->ps_group) UP(ps_group, s->ps_group, P);
   if (s->wl_has_quota_reservation) UP(wl_has_qr, s->wl_has_quota_reservation, W);
   if (s->wl_sched_hash) UP(wl_sched_hash, (const i64 *)s->wl_sched_hash, W);
   size_t caller_tabs = tabs.size();
@@ -684,6 +695,7 @@ static int32_t upload_impl(kb_handle *h, const kb_snapshot *s, bool sync) {
   D.sc_aux1 = h->arena.take<int32_t>(G * acap); D.sc_aux2 = h->arena.take<int32_t>(G * acap);
   D.sc_variant = h->arena.take<uint8_t>(G * acap); D.sc_tgt_reason = h->arena.take<uint8_t>(G * acap);
   D.sc_cq_class = h->arena.take<int8_t>(G * ncap); D.sc_on_path = h->arena.take<int8_t>(G * ncap);
+  D.sc_dirty = h->arena.take<uint8_t>(G * ncap); D.sc_drs_ratio = h->arena.take<double>(G * ncap); D.sc_drs_meta = h->arena.take<int8_t>(G * ncap);
   D.sc_usage = (fair && A && !h->search_smem) ? h->arena.take<i64>(G * ncap * FR) : nullptr;
   D.sc_adm_cap = (int)acap; D.sc_node_cap = (int)ncap;
   D.colU = h->arena.take<i64>(sNF); D.colS = h->arena.take<ColStat>(sNF); D.ovm = h->arena.take<uint32_t>(sNF);

@@ -77,6 +77,7 @@ struct DevSnap {
   const int32_t *cq_entry;    // [Q] entry (position in heads) of the ClusterQueue's single head, or -1 (k_cycle_root)
   const uint8_t *wl_has_qr;    // optional (nullptr = absent): workload.HasQuotaReservation
   const i64 *wl_sched_hash;    // optional: scheduling equivalence class, 0 = unknown (drain only)
+  const int32_t *ps_group;     // optional: PodSetGroup id per podset, -1 = none (members adjacent)
   // ---- derived, static per topology (host-built at upload) ----
   const int32_t *root_slot;   // [N] dense index of the node's root among all roots
   const int32_t *depth;       // [N] distance to the root
@@ -134,6 +135,7 @@ struct DevSnap {
   // per-CTA scratch of k_nominate_search
   int32_t *sc_cand, *sc_tgt, *sc_cq_lca, *sc_aux1, *sc_aux2; uint8_t *sc_variant, *sc_tgt_reason; int8_t *sc_cq_class, *sc_on_path;
   i64 *sc_usage;
+  uint8_t *sc_dirty; double *sc_drs_ratio; int8_t *sc_drs_meta;  // [G][node cap] DRS cache of the fair search
   int sc_adm_cap, sc_node_cap;
   // per-LANE scratch of the speculative single-cell searches (k_nominate_search phase A)
   int32_t *sl_cand, *sl_tgt, *sl_cq_lca, *sl_aux1; uint8_t *sl_variant, *sl_tgt_reason; int8_t *sl_cq_class, *sl_on_path;

@@ -239,27 +239,40 @@ __device__ inline int assign_workload(const DevSnap &D, Oracle &orc, int wl, con
   int borrowing = 0, rep = KB_MODE_FIT;
   if (ps1 == ps0) rep = KB_MODE_NOFIT;  // RepresentativeMode :148-151
   bool stop = false;
-  for (int row = ps0; row < ps1; row++) {
-    int8_t *oflv = D.ps_flavor + (size_t)row * R;
-    int8_t *omode = D.ps_res_mode + (size_t)row * R;
-    int8_t *otried = D.ps_tried + (size_t)row * R;
-    for (int r = 0; r < R; r++) { oflv[r] = -1; omode[r] = -1; otried[r] = -1; }
-    int full = D.ps_count[row];
-    int count = (counts && full != 0) ? counts[row - ps0] : full;
-    D.ps_count_out[row] = count;
-    if (stop) { D.ps_count_out[row] = full; continue; }
-    uint32_t mask = D.ps_req_mask[row];
+  // A unit is one podset, or the run of consecutive podsets that share a PodSetGroupName (groupedRequests :613-623):
+  // the group's requests are summed, one flavor search serves all of them, each member keeps the flavors of the
+  // resources it requests.
+  int row_end;
+  for (int row = ps0; row < ps1; row = row_end) {
+    row_end = row + 1;
+    if (D.ps_group && D.ps_group[row] >= 0) while (row_end < ps1 && D.ps_group[row_end] == D.ps_group[row]) row_end++;
+    auto cnt_of = [&](int m) { int full = D.ps_count[m]; return (counts && full != 0) ? counts[m - ps0] : full; };
+    uint32_t mask = 0;
+    u64 ok = ~0ull;
+    for (int m = row; m < row_end; m++) {
+      int8_t *fl = D.ps_flavor + (size_t)m * R, *md = D.ps_res_mode + (size_t)m * R, *tr = D.ps_tried + (size_t)m * R;
+      for (int r = 0; r < R; r++) { fl[r] = -1; md[r] = -1; tr[r] = -1; }
+      D.ps_count_out[m] = stop ? D.ps_count[m] : cnt_of(m);
+      mask |= D.ps_req_mask[m];
+      ok &= D.ps_flavor_ok[m];  // checkFlavorForPodSets walks every podset of the group :915-941
+    }
+    if (stop) continue;
     if (covers_pods) mask |= 1u << D.pods_res;
-    u64 ok = D.ps_flavor_ok[row];
+    auto unit_request = [&](int r) {  // requests.Add(podset.podSet.Requests) :627-631
+      i64 q = 0;
+      for (int m = row; m < row_end; m++) q += ps_request(D, m, r, cnt_of(m), covers_pods);
+      return q;
+    };
     bool has_reasons = false, failed = false;
     int ps_borrow = 0;
+    uint32_t assigned = 0;
     for (int r0 = 0; r0 < R; r0++) {  // :639-661
       if (!(mask & (1u << r0))) continue;
-      if (oflv[r0] >= 0) continue;  // got the flavor of its resource group already
+      if (assigned & (1u << r0)) continue;  // got the flavor of its resource group already
       int g = rg_by_resource(D, cq, r0);
       if (g < 0) {
-        if (ps_request(D, row, r0, count, covers_pods) == 0) continue;  // zero request for an undefined resource
-        has_reasons = true; failed = true; break;                      // :770-772
+        if (unit_request(r0) == 0) continue;  // zero request for an undefined resource
+        has_reasons = true; failed = true; break;  // :770-772
       }
       // findFlavorForPodSets :762-897
       uint32_t rgm = D.rg_res_mask[g] & mask;
@@ -269,7 +282,7 @@ __device__ inline int assign_workload(const DevSnap &D, Oracle &orc, int wl, con
       bool any_reason = false;
       int attempted = -1;
       int idx = 0;
-      if (fung && use_last) idx = D.ps_last_tried[(size_t)row * R + r0] + 1;  // NextFlavorToTryForPodSetResource
+      if (fung && use_last) idx = D.ps_last_tried[(size_t)row * R + r0] + 1;  // NextFlavorToTryForPodSetResource(psIDs[0], ...)
       for (; idx < nfl; idx++) {
         attempted = idx;
         int f = D.rg_flavors[fl0 + idx];
@@ -283,7 +296,7 @@ __device__ inline int assign_workload(const DevSnap &D, Oracle &orc, int wl, con
           for (int prow = ps0; prow < row; prow++)
             if (D.ps_flavor[(size_t)prow * R + r] == f) assumed += ps_request(D, prow, r, D.ps_count_out[prow], covers_pods);
           int b;
-          int pm = fits_resource_quota(D, orc, wl, cq, f * R + r, assumed, ps_request(D, row, r, count, covers_pods), &b);
+          int pm = fits_resource_quota(D, orc, wl, cq, f * R + r, assumed, unit_request(r), &b);
           if (pm != PM_FIT) any_reason = true;
           if (gm_preferred(rpm, rb, pm, b, pref)) { rpm = pm; rb = b; }  // :846-848 keep the worst
           if (rpm == PM_NOFIT) break;                                    // :849-852
@@ -306,30 +319,37 @@ __device__ inline int assign_workload(const DevSnap &D, Oracle &orc, int wl, con
       }
       if (best_f < 0) { has_reasons = true; failed = true; break; }  // :652-656
       int tried = fung ? (attempted == nfl - 1 ? -1 : attempted) : 0;  // :883-891
-      for (int r = 0; r < R; r++) {
-        if (!(rgm & (1u << r))) continue;
-        oflv[r] = (int8_t)best_f;
-        omode[r] = (best_pmask >> r) & 1 ? KB_MODE_PREEMPT : KB_MODE_FIT;
-        otried[r] = (int8_t)tried;
+      for (int m = row; m < row_end; m++) {  // FilterKeys(groupFlavors, keys(podSet.Requests)) :666
+        uint32_t mm = (D.ps_req_mask[m] | (covers_pods ? 1u << D.pods_res : 0u)) & rgm;
+        for (int r = 0; r < R; r++) {
+          if (!(mm & (1u << r))) continue;
+          D.ps_flavor[(size_t)m * R + r] = (int8_t)best_f;
+          D.ps_res_mode[(size_t)m * R + r] = (best_pmask >> r) & 1 ? KB_MODE_PREEMPT : KB_MODE_FIT;
+          D.ps_tried[(size_t)m * R + r] = (int8_t)tried;
+        }
       }
+      assigned |= rgm;
       if (best_maxb > ps_borrow) ps_borrow = best_maxb;
       if (best_pm != PM_FIT && any_reason) has_reasons = true;  // status is nil when the best mode is fit :892-894
     }
-    int psmode;
     if (failed) {
-      for (int r = 0; r < R; r++) { oflv[r] = -1; omode[r] = -1; otried[r] = -1; }
-      psmode = KB_MODE_NOFIT;
+      for (int m = row; m < row_end; m++)
+        for (int r = 0; r < R; r++) { D.ps_flavor[(size_t)m * R + r] = -1; D.ps_res_mode[(size_t)m * R + r] = -1; D.ps_tried[(size_t)m * R + r] = -1; }
+      rep = KB_MODE_NOFIT;
       stop = true;  // :677-679 return assignment
     } else {
       if (ps_borrow > borrowing) borrowing = ps_borrow;  // Assignment.append :721-723
-      psmode = KB_MODE_FIT;  // PodSetAssignment.RepresentativeMode :277-295
-      if (has_reasons) {
-        int nfl_assigned = 0;
-        for (int r = 0; r < R; r++) if (oflv[r] >= 0) { nfl_assigned++; if (omode[r] < psmode) psmode = omode[r]; }
-        if (nfl_assigned == 0) psmode = KB_MODE_NOFIT;
+      for (int m = row; m < row_end; m++) {
+        int psmode = KB_MODE_FIT;  // PodSetAssignment.RepresentativeMode :277-295
+        if (has_reasons) {
+          const int8_t *fl = D.ps_flavor + (size_t)m * R, *md = D.ps_res_mode + (size_t)m * R;
+          int nfl_assigned = 0;
+          for (int r = 0; r < R; r++) if (fl[r] >= 0) { nfl_assigned++; if (md[r] < psmode) psmode = md[r]; }
+          if (nfl_assigned == 0) psmode = KB_MODE_NOFIT;
+        }
+        if (psmode < rep) rep = psmode;
       }
     }
-    if (psmode < rep) rep = psmode;
   }
   *borrowing_out = borrowing;
   return rep;
@@ -430,29 +450,38 @@ __device__ inline int assign_workload_coop(const DevSnap &D, bool *need_search, 
   int borrowing = 0, rep = KB_MODE_FIT;
   if (ps1 == ps0) rep = KB_MODE_NOFIT;
   bool stop = false;
-  for (int row = ps0; row < ps1; row++) {
-    int8_t *oflv = D.ps_flavor + (size_t)row * R;
-    int8_t *omode = D.ps_res_mode + (size_t)row * R;
-    int8_t *otried = D.ps_tried + (size_t)row * R;
-    int full = D.ps_count[row];
-    int count = (counts && full != 0) ? counts[row - ps0] : full;
-    if (glane == 0) {
-      for (int r = 0; r < R; r++) { oflv[r] = -1; omode[r] = -1; otried[r] = -1; }
-      D.ps_count_out[row] = stop ? full : count;
+  int row_end;
+  for (int row = ps0; row < ps1; row = row_end) {  // units as in assign_workload: a podset or a run of one PodSetGroup
+    row_end = row + 1;
+    if (D.ps_group && D.ps_group[row] >= 0) while (row_end < ps1 && D.ps_group[row_end] == D.ps_group[row]) row_end++;
+    auto cnt_of = [&](int m) { int full = D.ps_count[m]; return (counts && full != 0) ? counts[m - ps0] : full; };
+    uint32_t mask = 0;
+    u64 ok = ~0ull;
+    for (int m = row; m < row_end; m++) {
+      if (glane == 0) {
+        int8_t *fl = D.ps_flavor + (size_t)m * R, *md = D.ps_res_mode + (size_t)m * R, *tr = D.ps_tried + (size_t)m * R;
+        for (int r = 0; r < R; r++) { fl[r] = -1; md[r] = -1; tr[r] = -1; }
+        D.ps_count_out[m] = stop ? D.ps_count[m] : cnt_of(m);
+      }
+      mask |= D.ps_req_mask[m];
+      ok &= D.ps_flavor_ok[m];
     }
     if (stop) continue;
-    uint32_t mask = D.ps_req_mask[row];
     if (covers_pods) mask |= 1u << D.pods_res;
-    u64 ok = D.ps_flavor_ok[row];
+    auto unit_request = [&](int r) {
+      i64 q = 0;
+      for (int m = row; m < row_end; m++) q += ps_request(D, m, r, cnt_of(m), covers_pods);
+      return q;
+    };
     bool has_reasons = false, failed = false;
     int ps_borrow = 0;
-    uint32_t assigned = 0, ps_pmask = 0;  // resources with a flavor / with Mode == Preempt in this podset
+    uint32_t assigned = 0, ps_pmask = 0;  // resources with a flavor / with Mode == Preempt in this unit
     for (int r0 = 0; r0 < R; r0++) {
       if (!(mask & (1u << r0))) continue;
       if (assigned & (1u << r0)) continue;
       int g = rg_by_resource(D, cq, r0);
       if (g < 0) {
-        if (ps_request(D, row, r0, count, covers_pods) == 0) continue;
+        if (unit_request(r0) == 0) continue;
         has_reasons = true; failed = true; break;
       }
       uint32_t rgm = D.rg_res_mask[g] & mask;
@@ -480,7 +509,7 @@ __device__ inline int assign_workload_coop(const DevSnap &D, bool *need_search, 
               for (int prow = ps0; prow < row; prow++)
                 if (D.ps_flavor[(size_t)prow * R + r] == f) assumed += ps_request(D, prow, r, D.ps_count_out[prow], covers_pods);
               int b;
-              int pm = cell_eval(D, cq, f * R + r, assumed, ps_request(D, row, r, count, covers_pods), &b);
+              int pm = cell_eval(D, cq, f * R + r, assumed, unit_request(r), &b);
               if (pm == PM_NEED) { pm = PM_NOCAND; need = need || cand_possible; }  // what the deferring oracle returns (b = height on the untouched snapshot)
               if (pm != PM_FIT) reason = true;
               if (gm_preferred(rpm, rb, pm, b, pref)) { rpm = pm; rb = b; }
@@ -520,31 +549,38 @@ __device__ inline int assign_workload_coop(const DevSnap &D, bool *need_search, 
       if (best_f < 0) { has_reasons = true; failed = true; break; }
       int tried = fung ? (attempted == nfl - 1 ? -1 : attempted) : 0;
       if (glane == 0)
-        for (int r = 0; r < R; r++) {
-          if (!(rgm & (1u << r))) continue;
-          oflv[r] = (int8_t)best_f;
-          omode[r] = (best_pmask >> r) & 1 ? KB_MODE_PREEMPT : KB_MODE_FIT;
-          otried[r] = (int8_t)tried;
+        for (int m = row; m < row_end; m++) {
+          uint32_t mm = (D.ps_req_mask[m] | (covers_pods ? 1u << D.pods_res : 0u)) & rgm;
+          for (int r = 0; r < R; r++) {
+            if (!(mm & (1u << r))) continue;
+            D.ps_flavor[(size_t)m * R + r] = (int8_t)best_f;
+            D.ps_res_mode[(size_t)m * R + r] = (best_pmask >> r) & 1 ? KB_MODE_PREEMPT : KB_MODE_FIT;
+            D.ps_tried[(size_t)m * R + r] = (int8_t)tried;
+          }
         }
       assigned |= rgm;
       ps_pmask |= best_pmask & rgm;
       if (best_maxb > ps_borrow) ps_borrow = best_maxb;
       if (best_pm != PM_FIT && any_reason) has_reasons = true;
     }
-    int psmode;
     if (failed) {
-      if (glane == 0) for (int r = 0; r < R; r++) { oflv[r] = -1; omode[r] = -1; otried[r] = -1; }
-      psmode = KB_MODE_NOFIT;
+      if (glane == 0)
+        for (int m = row; m < row_end; m++)
+          for (int r = 0; r < R; r++) { D.ps_flavor[(size_t)m * R + r] = -1; D.ps_res_mode[(size_t)m * R + r] = -1; D.ps_tried[(size_t)m * R + r] = -1; }
+      rep = KB_MODE_NOFIT;
       stop = true;
     } else {
       if (ps_borrow > borrowing) borrowing = ps_borrow;
-      psmode = KB_MODE_FIT;
-      if (has_reasons) {
-        if (assigned == 0) psmode = KB_MODE_NOFIT;
-        else if (ps_pmask) psmode = KB_MODE_PREEMPT;
+      for (int m = row; m < row_end; m++) {
+        int psmode = KB_MODE_FIT;
+        if (has_reasons) {
+          uint32_t mm = D.ps_req_mask[m] | (covers_pods ? 1u << D.pods_res : 0u);
+          if ((assigned & mm) == 0) psmode = KB_MODE_NOFIT;
+          else if (ps_pmask & mm) psmode = KB_MODE_PREEMPT;
+        }
+        if (psmode < rep) rep = psmode;
       }
     }
-    if (psmode < rep) rep = psmode;
     __syncwarp(gmask);  // rows written by lane 0 are read by every lane for the next podset's assumed usage
   }
   *borrowing_out = borrowing;
@@ -988,6 +1024,8 @@ __global__ void __launch_bounds__(32, 16) k_nominate_search_fair(DevSnap D) {  /
   }
   PTab<kSmem> T;
   T.D = &D; T.FR = FR;
+  T.dirty = D.sc_dirty + (size_t)blockIdx.x * D.sc_node_cap; T.drs_ratio = D.sc_drs_ratio + (size_t)blockIdx.x * D.sc_node_cap;
+  T.drs_meta = D.sc_drs_meta + (size_t)blockIdx.x * D.sc_node_cap;
   int cur_slot = -1;
   while (true) {
     __syncthreads();

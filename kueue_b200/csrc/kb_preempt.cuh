@@ -29,6 +29,8 @@ struct PTab {
                          // preemption oracle only ever read and write that column: columns are independent)
   const i64 *sub, *lq, *bl;  // smem copies (kSmem) — unused otherwise
   const int *lparent;        // smem (kSmem) — unused otherwise
+  uint8_t *dirty = nullptr;  // fair search: per node, "usage changed since its DominantResourceShare was cached"
+  double *drs_ratio = nullptr; int8_t *drs_meta = nullptr;  // cached DRS per node: unweighted ratio; bit 7 borrowing, low bits dominant resource + 1
   __device__ __forceinline__ i64 U(int h, int fr) const { return usage[col_fr >= 0 ? h : h * FR + fr]; }
   __device__ __forceinline__ void setU(int h, int fr, i64 v) const { usage[col_fr >= 0 ? h : h * FR + fr] = v; }
   __device__ __forceinline__ i64 Sub(int h, int fr) const { return kSmem ? sub[h * FR + fr] : D->subtree[(size_t)nodes[h] * FR + fr]; }
@@ -63,6 +65,7 @@ struct PTab {
     while (true) {
       i64 u = U(h, fr), la = imax(0, LQ(h, fr) - u);
       setU(h, fr, u + val);
+      if (dirty) dirty[h] = 1;
       int p = parent(h);
       if (p < 0 || !(val > la)) break;
       val -= la; h = p;
@@ -72,6 +75,7 @@ struct PTab {
     while (true) {
       i64 u = U(h, fr), stored = u - LQ(h, fr);
       setU(h, fr, u - val);
+      if (dirty) dirty[h] = 1;
       int p = parent(h);
       if (stored <= 0 || p < 0) break;
       val = imin(val, stored); h = p;
@@ -213,11 +217,28 @@ __device__ inline int cand_ordering(const DevSnap &D, int a, int b, int cq) {
   return 0;
 }
 template <bool kSmem>
-__device__ inline DevDRS fair_drs(const DevSnap &D, const PTab<kSmem> &T, int h) {  // dominantResourceShare fair_sharing.go:126-156
+__device__ inline DevDRS fair_drs_compute(const DevSnap &D, const PTab<kSmem> &T, int h, DevDRS d, int p);
+// dominantResourceShare fair_sharing.go:126-156 on the private tree.  The share of a node only changes when the usage
+// of the node changes (addUsage / removeUsage mark every node they touch), so it is cached per node: the tournament of
+// nextTarget (ordering.go:141-208) re-reads the shares of ALL children of a cohort after every popped candidate, but
+// only the nodes on that candidate's path were modified.
+template <bool kSmem>
+__device__ inline DevDRS fair_drs(const DevSnap &D, const PTab<kSmem> &T, int h) {
   int node = T.nodes[h];
   DevDRS d{D.fair_weight[node], 0.0, -1, false};
   int p = D.parent[node];
   if (p < 0) return d;
+  if (T.dirty && !T.dirty[h]) {
+    int8_t m = T.drs_meta[h];
+    d.ratio = T.drs_ratio[h]; d.borrowing = m & 0x40; d.res = (m & 0x3f) - 1;
+    return d;
+  }
+  d = fair_drs_compute(D, T, h, d, p);
+  if (T.dirty) { T.dirty[h] = 0; T.drs_ratio[h] = d.ratio; T.drs_meta[h] = (int8_t)((d.borrowing ? 0x40 : 0) | ((d.res + 1) & 0x3f)); }
+  return d;
+}
+template <bool kSmem>
+__device__ inline DevDRS fair_drs_compute(const DevSnap &D, const PTab<kSmem> &T, int h, DevDRS d, int p) {
   const int R = D.R, F = D.F, FR = D.FR;
   for (int r = 0; r < R; r++) {
     i64 b = 0, lend = 0;
@@ -253,7 +274,7 @@ __device__ inline void fair_search(const DevSnap &D, const PTab<kSmem> &T, PreCt
     c->n_targets = 0;
     c->overflow = 0;
   }
-  for (int h = 0; h < T.nn; h++) { S.on_path[h] = -1; S.cq_class[h] = 0; S.cq_lca[h] = -1; }
+  for (int h = 0; h < T.nn; h++) { S.on_path[h] = -1; S.cq_class[h] = 0; S.cq_lca[h] = -1; if (T.dirty) T.dirty[h] = 1; }
   for (int k = 1; k < c->plen; k++) S.on_path[c->path[k]] = (int8_t)k;  // preemptorAncestors
   // ---- findCandidates :514-533, sorted by CandidatesOrdering: evicted first, other CQs before the preemptor's.
   //         Other ClusterQueues qualify only while borrowing (cqIsBorrowing :535-545) -> subset of k_over's list.

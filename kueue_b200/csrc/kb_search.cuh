@@ -454,7 +454,7 @@ __device__ inline int ws_classical(const DevSnap &D, WCtx<KMAX> *w, const WScrat
   if (lane == 0) {
     atomicAdd(&D.sstat[0], 1ull); atomicAdd(&D.sstat[1], (u64)list_len);
     atomicAdd(&D.sstat[5], (u64)(t1 - t0)); atomicAdd(&D.sstat[6], (u64)(t2 - t1));
-    if (K > 1) atomicAdd(&D.sstat[4], 1ull);
+    if (K > 1) atomicAdd(&D.sstat[4], (u64)list_len);
   }
   if (present == 0) return 0;
   int n_visit = 0, n_removed = 0;

@@ -1,7 +1,7 @@
 """Pins the oracle's flavor assignment to the reference's TestAssignFlavors table
 (pkg/scheduler/flavorassigner/flavorassigner_test.go:165) with the reference's own stub
 preemption oracle (testOracle :145-158).  Fixture: tests/golden/assign_flavors_cases.json
-(tools/transcribe_tables.py); workload-slice / reclaimable-pod / TAS cases are out of scope."""
+(tools/transcribe_tables.py); workload-slice / TAS cases are out of scope."""
 import json
 import os
 
@@ -50,7 +50,7 @@ def build(tc):
         if ps["affinityTerms"]:
             p.RequiredDuringSchedulingIgnoredDuringExecution(ps["affinityTerms"])
         pss.append(p)
-    wl = MakeWorkload("wl", "").PodSets(*pss).ClusterQueue(tc["clusterQueue"]["name"])
+    wl = MakeWorkload("wl", "").PodSets(*pss).ClusterQueue(tc["clusterQueue"]["name"]).ReclaimablePods(tc.get("reclaimablePods") or {})
     usage = {tc["clusterQueue"]["name"]: {(f, r): v for f, r, v in tc["clusterQueueUsage"]}}
     if tc["secondaryClusterQueue"]:
         usage[tc["secondaryClusterQueue"]["name"]] = {(f, r): v for f, r, v in tc["secondaryClusterQueueUsage"]}
@@ -65,7 +65,8 @@ def build(tc):
         if f not in known:
             known.append(f)
     snap, idx = flatten(cqs, [], pending=[wl], usage=usage, flags=flags, extra_resources=extra, resource_flavors=rfs,
-                        flavors=[f for rg in cqs[0].resource_groups for f in [q.name for q in rg]] + known)
+                        flavors=[f for rg in cqs[0].resource_groups for f in [q.name for q in rg]] + known,
+                        reclaimable_pods=tc.get("reclaimablePodsGate", True))
     return snap, idx
 
 

@@ -21,6 +21,6 @@ for i, nm in enumerate(abi.KERNEL_NAMES):
     if st.kernel_ms[i] > 0:
         print(f"  {nm:26s} {st.kernel_ms[i]:9.3f} ms")
 ss = list(st.search_stat)
-print("searches", ss[0], "records", ss[1], "visited", ss[2], "removed", ss[3], "GetTargets", ss[4])
+print("searches", ss[0], "records", ss[1], "visited", ss[2], "removed", ss[3], "records of multi-column searches", ss[4])
 if ss[0]:
     print("per search: records %.0f, cycles load %.0f classify %.0f greedy %.0f" % (ss[1] / ss[0], ss[5] / ss[0], ss[6] / ss[0], ss[7] / ss[0]))

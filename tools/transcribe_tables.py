@@ -217,10 +217,11 @@ def assign_cases():
         lit_text[k] = "\n".join(src_lines[ln - 1:end - 1])
     for key, v in cases:
         tc = interp.ev(v)
-        if tc.get("elasticJobsViaWorkloadSlicesEnabled") or tc.get("preemptWorkloadSlice") or tc.get("wlReclaimablePods"):
-            skipped[key] = "workload slices / reclaimable pods (out of scope)"
+        if tc.get("elasticJobsViaWorkloadSlicesEnabled") or tc.get("preemptWorkloadSlice"):
+            skipped[key] = "workload slices (alpha gate ElasticJobsViaWorkloadSlices, out of scope)"
             continue
-        if tc.get("featureGates"):
+        gates = {str(sym(k)).split(".")[-1]: bool(v) for k, v in (tc.get("featureGates") or {}).items() if not str(k).startswith("_")}
+        if set(gates) - {"ReclaimablePods"}:
             skipped[key] = "non-default feature gates"
             continue
         wa = tc.get("wantAssignment") or {}
@@ -260,6 +261,8 @@ def assign_cases():
             "secondaryClusterQueue": norm_cq(tc["secondaryClusterQueue"]) if tc.get("secondaryClusterQueue") else None,
             "secondaryClusterQueueUsage": _frq(tc.get("secondaryClusterQueueUsage")),
             "enableFairSharing": bool(tc.get("enableFairSharing")),
+            "reclaimablePods": {p["Name"]: p["Count"] for p in gointerp.strip(tc.get("wlReclaimablePods") or [])},
+            "reclaimablePodsGate": gates.get("ReclaimablePods", True),
             "simulationResult": sim,
             "wantRepMode": AMODE[sym(tc.get("wantRepMode"))] if tc.get("wantRepMode") is not None else 0,
             "wantPodSets": want_ps,
