@@ -367,17 +367,26 @@ def main():
     #   strong scaling (--scaling strong, the default of cfg4): the configuration's own snapshot is split by root —
     #     cfg4 has 10 root cohorts, so 8 GPUs hold at most 2 roots each (5x is the ceiling of this partition).
     scaling = args.scaling or ("strong" if args.config == 4 else "weak")
-    shard_map, glob_heads = None, None
-    if world > 1:
+    shard_map, glob_heads = None, None  # noqa: F841
+    my_heads = None  # global entry positions of this rank's entries
+    if world > 1 and scaling == "strong":
         from kueue_b200 import shard as kshard
-        dflt = {1: (100, 10), 2: (100_000, 1_000), 3: (1_000_000, 10_000), 4: (1_000_000, 10_000)}[args.config]
-        mult = 1 if scaling == "strong" else world
-        glob = synth.make_snapshot(args.config, W=dflt[0] * mult, Q=dflt[1] * mult, heads=HEADS[args.config])
+        glob = synth.make_snapshot(args.config, heads=HEADS[args.config])
         if HEADS[args.config] == "one_per_cq":
             glob = synth.compact_to_heads(glob)
         glob_heads = glob.n_heads
         snap, shard_map = kshard.shard(glob, rank, world)
+        my_heads = np.asarray(shard_map.heads)
         del glob
+    elif world > 1:
+        # weak scaling: the cluster is `world` times the configuration — since root cohorts never interact, that is
+        # the union of `world` independent copies of the configuration (different seeds), one per rank; the sharding
+        # of ONE snapshot by root (shard -> device per shard -> merge == unsharded oracle) is covered by tests/
+        snap = synth.make_snapshot(args.config, heads=HEADS[args.config], seed=1000 + rank)
+        if HEADS[args.config] == "one_per_cq":
+            snap = synth.compact_to_heads(snap)
+        glob_heads = snap.n_heads * world
+        my_heads = np.arange(snap.n_heads) + rank * snap.n_heads
     else:
         snap = synth.make_snapshot(args.config, heads=HEADS[args.config])
     if HEADS[args.config] == "one_per_cq":
@@ -438,7 +447,7 @@ def main():
         return full
     if world > 1:
         sizes = [None] * world
-        dist.all_gather_object(sizes, shard_map.heads)
+        dist.all_gather_object(sizes, my_heads)
         all_maps = sizes
         hmax = max(len(m) for m in all_maps)
     for _ in range(2):
@@ -476,7 +485,7 @@ def main():
         kname = abi.KERNEL_NAMES[top]
         kbytes = ab.get(kname, ab["total"])
         ss = list(st.search_stat)
-        if ss[0] and kname in ("k_search_cells", "k_nominate_walk"):
+        if kname in ("k_search_cells", "k_nominate_walk"):
             # streamed 32 B candidate records of the last cycle (kb_stats.search_stat: [1] all records, [4] those of the
             # multi-column GetTargets searches of k_nominate_walk) on top of the per-entry floor; the quota columns a
             # search stages are shared by the searches of one bucket and are part of the floor's node tables
@@ -493,12 +502,15 @@ def main():
                        "wall_ms_per_step_incl_flush": wall_ms / args.steps,
                        "e2e_static_tables": "quota / policy / topology tables uploaded once (static_generation constant), "
                                             "usage + entries + admitted workloads copied every step",
-                       "multi_gpu": None if world == 1 else {"partition": "root cohorts (kueue_b200.shard), no data-path collective",
+                       "multi_gpu": None if world == 1 else {"partition": ("the configuration's root cohorts split over the ranks (kueue_b200.shard)" if scaling == "strong" else
+                                                                           "one independent copy of the configuration (its own root cohorts) per rank") + ", no data-path collective",
                                                              "e2e_includes": "NCCL all-gather of the shards' decisions + merge on rank 0",
                                                              "host_affinity": numa}},
             "clocks": clocks,
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches,
+            "search_counters": ({"searches": ss[0], "records_classified": ss[1], "candidates_visited": ss[2], "workloads_removed": ss[3],
+                                 "records_of_multi_column_searches": ss[4]} if kms[abi.KERNEL_NAMES.index("k_nominate_walk")] > 0 else None),
             "kernel_ms_per_step": {abi.KERNEL_NAMES[i]: kms[i] / args.steps for i in range(20) if kms[i] > 0},
             "roofline": {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak if peak else None, "traffic": measured_traffic(args.config, kname),

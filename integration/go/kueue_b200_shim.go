@@ -270,6 +270,8 @@ func (s *Scheduler) flatten(snap *schdcache.Snapshot, heads []workload.Info, gen
 	var wlTs, wlUID, wlGen, psReq []int64
 	var psOk []uint64
 	var psLast []int8
+	var psGroup []int32 // PodSetGroupName as a per-workload id, -1 = none (flavorassigner.go:613-616)
+	anyGroup := false
 	wlPsStart = append(wlPsStart, 0)
 	for i := range heads {
 		w := &heads[i]
@@ -281,7 +283,17 @@ func (s *Scheduler) flatten(snap *schdcache.Snapshot, heads []workload.Info, gen
 			gen = w.LastAssignment.ClusterQueueGeneration
 		}
 		wlGen = append(wlGen, gen)
+		var groupNames []string
 		for pi, ps := range w.TotalRequests {
+			gid := int32(-1)
+			if tr := w.Obj.Spec.PodSets[pi].TopologyRequest; tr != nil && tr.PodSetGroupName != nil {
+				k := slices.Index(groupNames, *tr.PodSetGroupName)
+				if k < 0 {
+					groupNames, k = append(groupNames, *tr.PodSetGroupName), len(groupNames)
+				}
+				gid, anyGroup = int32(k), true
+			}
+			psGroup = append(psGroup, gid)
 			row := make([]int64, R)
 			last := make([]int8, R)
 			var mask int32
@@ -334,6 +346,9 @@ func (s *Scheduler) flatten(snap *schdcache.Snapshot, heads []workload.Info, gen
 	c.adm_cq, c.adm_priority, c.adm_ts, c.adm_qr_ts, c.adm_uid = cp32(admCq), cp32(admPrio), cp64(admTs), cp64(admQr), cp64(admUID)
 	c.adm_evicted, c.adm_use_start, c.adm_use_fr, c.adm_use_qty = cpU8(admEv), cp32(admUseStart), cp32(admFr), cp64(admQty)
 	c.heads = cp32(headsIdx)
+	if anyGroup { // optional table: NULL when no podset is grouped
+		c.ps_group = cp32(psGroup)
+	}
 	return f
 }
 

@@ -163,8 +163,10 @@ class MakePodSet:
         self.tolerations: List[dict] = []
         self.node_selector: Optional[Dict[str, str]] = None
         self.affinity_terms: Optional[List[dict]] = None
+        self.group: Optional[str] = None  # TopologyRequest.PodSetGroupName
 
     def Request(self, res: str, q): self.requests[res] = q; return self
+    def PodSetGroup(self, g: Optional[str]): self.group = g; return self
     def Toleration(self, **t): self.tolerations.append(t); return self
     def NodeSelector(self, kv: Dict[str, str]): self.node_selector = dict(kv); return self
 
@@ -422,7 +424,7 @@ def flatten(cqs: Sequence[MakeClusterQueue], cohorts: Sequence[MakeCohort] = (),
 
     # pending workloads
     w_cq, w_pr, w_ts, w_uid, w_lg, w_st = [], [], [], [], [], [0]
-    p_req, p_mask, p_cnt, p_min, p_ok, p_lt = [], [], [], [], [], []
+    p_req, p_mask, p_cnt, p_min, p_ok, p_lt, p_grp = [], [], [], [], [], [], []
     for w in pending:
         assert w.cq is not None, f"pending workload {w.name} has no ClusterQueue"
         w_cq.append(idx.cqs.index(w.cq)); w_pr.append(w.priority); w_uid.append(w.uid)
@@ -438,6 +440,8 @@ def flatten(cqs: Sequence[MakeClusterQueue], cohorts: Sequence[MakeCohort] = (),
                 row[r] = resource_value(rname, q) * count  # totalRequestsFromPodSets workload.go:567-598
                 mask |= 1 << r
             p_req.append(row); p_mask.append(mask); p_cnt.append(count)
+            groups = [g.group for g in w.podsets if g.group is not None]
+            p_grp.append(-1 if ps.group is None else sorted(set(groups)).index(ps.group))  # groupKey flavorassigner.go:613-616
             p_min.append(-1 if ps.min_count is None else ps.min_count)
             ok = (1 << 64) - 1
             if ps.flavor_ok is not None:
@@ -471,6 +475,8 @@ def flatten(cqs: Sequence[MakeClusterQueue], cohorts: Sequence[MakeCohort] = (),
     snap.set("ps_req", np.array(p_req, np.int64).reshape(len(p_cnt), R)); snap.set("ps_req_mask", p_mask)
     snap.set("ps_count", p_cnt); snap.set("ps_min_count", p_min)
     snap.set("ps_flavor_ok", np.array(p_ok, dtype=np.uint64)); snap.set("ps_last_tried", np.array(p_lt, np.int8).reshape(len(p_cnt), R))
+    if any(g >= 0 for g in p_grp):
+        snap.set("ps_group", np.array(p_grp, np.int32))
     if heads is None:
         snap.set("heads", np.arange(len(w_cq)))
     else:

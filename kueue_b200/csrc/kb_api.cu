@@ -46,7 +46,8 @@ struct kb_handle {
   int sm_count = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr, ev4 = nullptr, ev5 = nullptr;
-  Arena arena;   // per-cycle tables, scratch, outputs
+  Arena arena;   // per-cycle scratch, outputs
+  Arena iarena;  // per-cycle input tables (copied before the host-side checks finish)
   Arena sarena;  // static tables (quotas, policies, topology): kept while kb_snapshot.static_generation is unchanged
   int64_t static_gen = 0;
   int s_dims[6] = {-1, -1, -1, -1, -1, -1};
@@ -160,6 +161,7 @@ void kb_destroy(kb_handle *h) {
   cudaSetDevice(h->device);
   if (h->arena.base) cudaFree(h->arena.base);
   if (h->sarena.base) cudaFree(h->sarena.base);
+  if (h->iarena.base) cudaFree(h->iarena.base);
   if (h->drain_buf) cudaFree(h->drain_buf);
   if (h->tas_buf) cudaFree(h->tas_buf);
   if (h->ev_d) cudaEventDestroy(h->ev_d);
@@ -446,7 +448,6 @@ static int32_t upload_impl(kb_handle *h, const kb_snapshot *s, bool sync) {
   int dims[6] = {Q, C, F, R, s->n_rg, n_rg_fl};
   bool reuse = s->static_generation != 0 && s->static_generation == h->static_gen && memcmp(dims, h->s_dims, sizeof(dims)) == 0;
   int64_t bytes = 0;
-  CUDA_TRY(h, cudaEventRecord(h->ev0, h->stream));
   int32_t rc;
   if (!reuse) {
     h->static_gen = 0;
@@ -488,8 +489,65 @@ static int32_t upload_impl(kb_handle *h, const kb_snapshot *s, bool sync) {
     memcpy(h->s_dims, dims, sizeof(dims));
     h->static_gen = s->static_generation;
   }
+  // Per-cycle input tables, enqueued FIRST: the DMA runs while the host validates the tables and sizes the scratch
+  // arena below (build_dynamic).  The caller's tables (dynamic part of kb_snapshot) usually sit close together in
+  // one pinned block (kb_alloc_pinned carved by the shim): when their host span is not much larger than their
+  // total size the whole span goes to the device with ONE DMA and the device tables alias into it at the same
+  // offsets; otherwise every table is copied on its own.
+  struct Tab { const void *src; size_t bytes; const void **dst; size_t cap; };
+  std::vector<Tab> tabs;
+#define UPC(field, src, n, capn) tabs.push_back(Tab{(const void *)(src), (size_t)(n) * sizeof(*D.field), (const void **)&D.field, (size_t)(capn) * sizeof(*D.field)})
+#define UP(field, src, n) UPC(field, src, n, n)
+  UP(cq_usage, (const i64 *)s->cq_usage, (size_t)Q * FR);
+  UP(wl_cq, s->wl_cq, W); UP(wl_priority, s->wl_priority, W); UP(wl_ts, (const i64 *)s->wl_ts, W); UP(wl_uid, (const i64 *)s->wl_uid, W);
+  UP(wl_last_gen, (const i64 *)s->wl_last_gen, W); UP(wl_ps_start, s->wl_ps_start, W + 1);
+  UP(ps_req, (const i64 *)s->ps_req, P * R); UP(ps_req_mask, s->ps_req_mask, P); UP(ps_count, s->ps_count, P);
+  UP(ps_min_count, s->ps_min_count, P); UP(ps_flavor_ok, (const u64 *)s->ps_flavor_ok, P); UP(ps_last_tried, s->ps_last_tried, P * R);
+  UPC(adm_cq, s->adm_cq, A_in, A); UPC(adm_priority, s->adm_priority, A_in, A); UPC(adm_ts, (const i64 *)s->adm_ts, A_in, A);
+  UPC(adm_qr_ts, (const i64 *)s->adm_qr_ts, A_in, A); UPC(adm_uid, (const i64 *)s->adm_uid, A_in, A); UPC(adm_evicted, s->adm_evicted, A_in, A);
+  UPC(adm_use_start, s->adm_use_start, A_in + 1, A + 1); UPC(adm_use_fr, s->adm_use_fr, AU_in, AUc); UPC(adm_use_qty, (const i64 *)s->adm_use_qty, AU_in, AUc);
+  if (!h->drain_mode) UP(heads, s->heads, H);
+  D.wl_has_qr = nullptr; D.wl_sched_hash = nullptr; D.ps_group = nullptr;
+  if (s->ps_group) UP(ps_group, s->ps_group, P);
+  if (s->wl_has_quota_reservation) UP(wl_has_qr, s->wl_has_quota_reservation, W);
+  if (s->wl_sched_hash) UP(wl_sched_hash, (const i64 *)s->wl_sched_hash, W);
+  size_t caller_tabs = tabs.size();
+#undef UP
+#undef UPC
+  {
+    uintptr_t lo = UINTPTR_MAX, hi = 0; size_t sum = 0;
+    for (size_t i = 0; i < caller_tabs; i++) {
+      if (!tabs[i].bytes) continue;
+      if (!tabs[i].src) return fail(h, KB_ERR_INVALID, "null table with non-zero length");
+      if (tabs[i].cap != tabs[i].bytes) continue;  // growable table: its own allocation
+      lo = std::min(lo, (uintptr_t)tabs[i].src); hi = std::max(hi, (uintptr_t)tabs[i].src + tabs[i].bytes); sum += tabs[i].bytes;
+    }
+    uintptr_t lo_al = lo & ~(uintptr_t)255;
+    bool span = sum > 0 && (hi - lo) <= sum + sum / 4 + (64u << 10) && inside_one_pinned_block(lo_al, hi);
+    size_t itot = span ? pad256(hi - lo_al) : 0;
+    for (size_t i = 0; i < tabs.size(); i++) {
+      const Tab &t = tabs[i];
+      if (!(span && i < caller_tabs && t.bytes && t.cap == t.bytes)) itot += pad256(std::max(t.bytes, t.cap));
+    }
+    if (!h->iarena.reserve(itot + 4096)) return fail(h, KB_ERR_CUDA, "cudaMalloc failed");
+    h->iarena.reset();
+    CUDA_TRY(h, cudaEventRecord(h->ev0, h->stream));
+    char *dspan = span ? h->iarena.take<char>(hi - lo_al) : nullptr;
+    if (span) {
+      CUDA_TRY(h, cudaMemcpyAsync(dspan, (const void *)lo_al, hi - lo_al, cudaMemcpyHostToDevice, h->stream));
+      bytes += (int64_t)(hi - lo_al);
+    }
+    for (size_t i = 0; i < tabs.size(); i++) {
+      const Tab &t = tabs[i];
+      if (span && i < caller_tabs && t.bytes && t.cap == t.bytes) { *t.dst = dspan + ((uintptr_t)t.src - lo_al); continue; }
+      char *d = h->iarena.take<char>(std::max(t.bytes, t.cap));
+      *t.dst = d;
+      if (t.bytes) { CUDA_TRY(h, cudaMemcpyAsync(d, t.src, t.bytes, cudaMemcpyHostToDevice, h->stream)); bytes += (int64_t)t.bytes; }
+    }
+  }
+  CUDA_TRY(h, cudaEventRecord(h->ev1, h->stream));
   rc = build_dynamic(h, s);
-  if (rc != KB_OK) return rc;
+  if (rc != KB_OK) { cudaStreamSynchronize(h->stream); return rc; }  // the copies read the caller's buffers
   D.tab_local = 0; D.gparent = D.parent; D.lq = nullptr; D.cq_entry = nullptr;
   D.Q = Q; D.C = C; D.N = N; D.F = F; D.R = R; D.FR = FR; D.W = s->n_wl; D.P = s->n_podset; D.A = s->n_adm;
   D.AU = s->n_adm_use; D.H = s->n_heads; D.NRG = s->n_rg; D.pods_res = s->pods_resource; D.flags = s->flags; D.now_ns = s->now_ns;
@@ -520,20 +578,24 @@ static int32_t upload_impl(kb_handle *h, const kb_snapshot *s, bool sync) {
   // fair-sharing preemption: search kernel configuration (single-warp CTAs on a private copy of the whole tree)
   bool fair = (s->flags & KB_F_FAIR_SHARING) != 0;
   h->search_grid = 1; h->search_smem = true; h->search_smem_bytes = 0;
+  size_t fair_memo_items = 0;
   if (fair && A) {
-    size_t tb = (size_t)h->max_tree_nodes * FR * 32 + (size_t)h->max_tree_nodes * 4 + 64;
+    // private tree tables [nodes][FR] x 4, parent links, per-node search state (16 B: queue head, cached share, flags)
+    size_t tb = (size_t)h->max_tree_nodes * FR * 32 + (size_t)h->max_tree_nodes * 4 + (size_t)h->max_tree_nodes * 16 + 128;
     h->search_smem = tb <= 190 * 1024;
     h->search_smem_bytes = h->search_smem ? tb : 0;
     // resident single-warp CTAs per SM as the occupancy calculator sees them (registers / shared memory)
     int per_sm = 1;
     if (h->search_smem) {
-      cudaFuncSetAttribute(k_nominate_search_fair<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_nominate_search_fair<true>, 32, h->search_smem_bytes);
+      cudaFuncSetAttribute(k_nominate_search_fair<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_nominate_search_fair<true, true>, 32, h->search_smem_bytes);
     } else {
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_nominate_search_fair<false>, 32, 0);
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_nominate_search_fair<false, true>, 32, 0);
     }
     per_sm = std::max(1, std::min(per_sm, 16));
-    h->search_grid = std::max(1, std::min(h->sm_count * per_sm, std::max(1, s->n_heads)));
+    // the oracle-cell pass has up to FR tasks per entry
+    h->search_grid = (int)std::max<size_t>(1, std::min<size_t>((size_t)h->sm_count * per_sm, std::max<size_t>(1, H * (size_t)FR)));
+    fair_memo_items = std::min<size_t>(H, (64u << 20) / ((size_t)FR * sizeof(SimMemo)));
   }
   // warp-cooperative classical search: shared memory per warp = context + private column(s) + candidate codes
   size_t ws_warps = 1, ws_col_stride = 0, memo_items = 0, ws_list_total = 32;
@@ -580,6 +642,7 @@ static int32_t upload_impl(kb_handle *h, const kb_snapshot *s, bool sync) {
     if (kcap * ncap_s > colB) ws_col_stride = std::max(ws_col_stride, std::min<size_t>((size_t)FR, KB_MAX_CELLS) * ncap_s);
     memo_items = std::min<size_t>(H, (64u << 20) / ((size_t)FR * sizeof(SimMemo)));
   }
+  if (fair && A) memo_items = fair_memo_items;
   size_t G = (fair && A) ? (size_t)h->search_grid : 1, acap = (fair && A) ? (size_t)h->max_root_adm : 1, ncap = (size_t)h->max_tree_nodes;
   size_t pool_cap = A * 4 + 1024;
   need(A, 4); need(nroots + 1, 4); need(H, 4); need(2, 4); need(H, 4); need(H, 4); need(pool_cap, 4); need(pool_cap, 1); need(1, 4);
@@ -594,56 +657,8 @@ static int32_t upload_impl(kb_handle *h, const kb_snapshot *s, bool sync) {
   need(A ? nbuckets + 2 : 1, 4); need(A ? nbuckets + 2 : 1, 4); need(A ? nbuckets + 2 : 1, 4); need(memo_items * FR, 4); need(memo_items * FR, 4);
   need(ws_warps * ws_col_stride, 8); need(ws_list_total, 1); need(ws_list_total, 4); need(ws_list_total, 1); need(ws_warps * (size_t)h->sa_list_cap, 8);
   if (fair) { need(H * FR, 8); need(H * (48 + 16 * KB_MAX_DEPTH), 1); need(N, 4); need(N, 4); }
-  const size_t span_cap = tot;  // the input tables are part of tot: a span of up to that size is covered by the slack below
-  if (!h->arena.reserve(tot + tot / 2 + (1u << 20))) return fail(h, KB_ERR_CUDA, "cudaMalloc failed");
+  if (!h->arena.reserve(tot + (1u << 20))) { cudaStreamSynchronize(h->stream); return fail(h, KB_ERR_CUDA, "cudaMalloc failed"); }
   h->arena.reset();
-  // Per-cycle input tables.  The caller's tables (dynamic part of kb_snapshot) usually sit close together in
-  // one pinned block (kb_alloc_pinned carved by the shim): when their host span is not much larger than their
-  // total size the whole span goes to the device with ONE DMA and the device tables alias into it at the same
-  // offsets; otherwise every table is copied on its own.
-  struct Tab { const void *src; size_t bytes; const void **dst; size_t cap; };
-  std::vector<Tab> tabs;
-#define UPC(field, src, n, capn) tabs.push_back(Tab{(const void *)(src), (size_t)(n) * sizeof(*D.field), (const void **)&D.field, (size_t)(capn) * sizeof(*D.field)})
-#define UP(field, src, n) UPC(field, src, n, n)
-  UP(cq_usage, (const i64 *)s->cq_usage, (size_t)Q * FR);
-  UP(wl_cq, s->wl_cq, W); UP(wl_priority, s->wl_priority, W); UP(wl_ts, (const i64 *)s->wl_ts, W); UP(wl_uid, (const i64 *)s->wl_uid, W);
-  UP(wl_last_gen, (const i64 *)s->wl_last_gen, W); UP(wl_ps_start, s->wl_ps_start, W + 1);
-  UP(ps_req, (const i64 *)s->ps_req, P * R); UP(ps_req_mask, s->ps_req_mask, P); UP(ps_count, s->ps_count, P);
-  UP(ps_min_count, s->ps_min_count, P); UP(ps_flavor_ok, (const u64 *)s->ps_flavor_ok, P); UP(ps_last_tried, s->ps_last_tried, P * R);
-  UPC(adm_cq, s->adm_cq, A_in, A); UPC(adm_priority, s->adm_priority, A_in, A); UPC(adm_ts, (const i64 *)s->adm_ts, A_in, A);
-  UPC(adm_qr_ts, (const i64 *)s->adm_qr_ts, A_in, A); UPC(adm_uid, (const i64 *)s->adm_uid, A_in, A); UPC(adm_evicted, s->adm_evicted, A_in, A);
-  UPC(adm_use_start, s->adm_use_start, A_in + 1, A + 1); UPC(adm_use_fr, s->adm_use_fr, AU_in, AUc); UPC(adm_use_qty, (const i64 *)s->adm_use_qty, AU_in, AUc);
-  if (!h->drain_mode) UP(heads, s->heads, H);
-  D.wl_has_qr = nullptr; D.wl_sched_hash = nullptr; D.ps_group = nullptr;
-  if (s->ps_group) UP(ps_group, s->ps_group, P);
-  if (s->wl_has_quota_reservation) UP(wl_has_qr, s->wl_has_quota_reservation, W);
-  if (s->wl_sched_hash) UP(wl_sched_hash, (const i64 *)s->wl_sched_hash, W);
-  size_t caller_tabs = tabs.size();
-#undef UP
-#undef UPC
-  {
-    uintptr_t lo = UINTPTR_MAX, hi = 0; size_t sum = 0;
-    for (size_t i = 0; i < caller_tabs; i++) {
-      if (!tabs[i].bytes) continue;
-      if (!tabs[i].src) return fail(h, KB_ERR_INVALID, "null table with non-zero length");
-      if (tabs[i].cap != tabs[i].bytes) continue;  // growable table: its own allocation
-      lo = std::min(lo, (uintptr_t)tabs[i].src); hi = std::max(hi, (uintptr_t)tabs[i].src + tabs[i].bytes); sum += tabs[i].bytes;
-    }
-    uintptr_t lo_al = lo & ~(uintptr_t)255;
-    bool span = sum > 0 && (hi - lo) <= sum + sum / 4 + (64u << 10) && (hi - lo) <= span_cap && inside_one_pinned_block(lo_al, hi);
-    char *dspan = span ? h->arena.take<char>(hi - lo_al) : nullptr;
-    if (span) {
-      CUDA_TRY(h, cudaMemcpyAsync(dspan, (const void *)lo_al, hi - lo_al, cudaMemcpyHostToDevice, h->stream));
-      bytes += (int64_t)(hi - lo_al);
-    }
-    for (size_t i = 0; i < tabs.size(); i++) {
-      const Tab &t = tabs[i];
-      if (span && i < caller_tabs && t.bytes && t.cap == t.bytes) { *t.dst = dspan + ((uintptr_t)t.src - lo_al); continue; }
-      char *d = h->arena.take<char>(std::max(t.bytes, t.cap));
-      *t.dst = d;
-      if (t.bytes) { CUDA_TRY(h, cudaMemcpyAsync(d, t.src, t.bytes, cudaMemcpyHostToDevice, h->stream)); bytes += (int64_t)t.bytes; }
-    }
-  }
   if (h->drain_mode) D.heads = h->arena.take<int32_t>(H);
   h->d_cq_entry = h->arena.take<int32_t>(Q); D.cq_entry = h->d_cq_entry;
   {  // fused per-root cycle (k_cycle_root): see the kernel's header for the conditions
@@ -715,13 +730,12 @@ static int32_t upload_impl(kb_handle *h, const kb_snapshot *s, bool sync) {
     D.fs_cq_entry = h->arena.take<int32_t>(N); D.fs_winner = h->arena.take<int32_t>(N);
   }
   h->d_drs_rounded = h->arena.take<i64>(N); h->d_drs_res = h->arena.take<int32_t>(N); h->d_drs_borrowing = h->arena.take<uint8_t>(N);
-  if (h->arena.used > h->arena.cap) return fail(h, KB_ERR_CUDA, "device arena accounting");
+  if (h->arena.used > h->arena.cap) { cudaStreamSynchronize(h->stream); return fail(h, KB_ERR_CUDA, "device arena accounting"); }
   // rows of workloads that are not heads stay at -1
   CUDA_TRY(h, cudaMemsetAsync(D.ps_flavor, 0xff, P * R, h->stream));
   CUDA_TRY(h, cudaMemsetAsync(D.ps_res_mode, 0xff, P * R, h->stream));
   CUDA_TRY(h, cudaMemsetAsync(D.ps_tried, 0xff, P * R, h->stream));
   CUDA_TRY(h, cudaMemsetAsync(D.ps_count_out, 0, P * 4, h->stream));
-  CUDA_TRY(h, cudaEventRecord(h->ev1, h->stream));
   h->stats.h2d_bytes = bytes;
   h->uploaded = true;
   if (sync) {  // caller buffers may be released after return
@@ -752,7 +766,8 @@ static int32_t launch_tree(kb_handle *h, int *launches) {
 static size_t admit_smem(int nn_tables, int FR, int sort_cap) {
   size_t tb = (size_t)nn_tables * FR * 32;
   size_t mid = (size_t)KB_TILE * FR * 8; (void)sort_cap;
-  return tb + mid + 16 + (size_t)nn_tables * 4 + KB_TILE * 28 + (KB_MAX_DEPTH + 2) * 4 + 64;
+  size_t staging = nn_tables == 0 ? (size_t)KB_TILE * 4 * (KB_PF + 2) + 32 + (size_t)KB_TG_CAP * sizeof(TgCell) : (size_t)KB_TILE * 4 * (KB_PF + 2) + 32;
+  return tb + mid + 16 + (size_t)nn_tables * 4 + KB_TILE * 28 + (KB_MAX_DEPTH + 2) * 4 + 64 + staging;
 }
 static int32_t launch_admit(kb_handle *h, int *launches) {
   DevSnap &D = h->D;
@@ -860,6 +875,8 @@ static int32_t cycle_enqueue(kb_handle *h) {
   } else {
   launch_tree(h, &launches);
   if (D.H) {
+    // per-(node, resource) sums the DominantResourceShare reads (fair target search, fair admit loop); only needs the tree pass
+    if (D.flags & KB_F_FAIR_SHARING) { kmark(h, KB_K_FAIR_PREP); k_fair_prep<<<(D.N * D.R + 255) / 256, 256, 0, h->stream>>>(D); launches++; }
     kmark(h, KB_K_NOMINATE);
     // few entries: latency-bound -> KB_NG lanes per entry; many entries: throughput-bound -> one thread per entry
     if ((size_t)D.H * KB_NG <= (size_t)h->sm_count * 2048) k_nominate_coop<<<(int)(((size_t)D.H * KB_NG + 127) / 128), 128, 0, h->stream>>>(D);
@@ -870,11 +887,15 @@ static int32_t cycle_enqueue(kb_handle *h) {
         kmark(h, KB_K_PREEMPT);
         CUDA_TRY(h, cudaMemsetAsync(D.over_count, 0, sizeof(int32_t) * (size_t)std::max(1, D.nRoots), h->stream));
         k_over<<<(D.Q + 255) / 256, 256, 0, h->stream>>>(D); launches++;
+        CUDA_TRY(h, cudaMemsetAsync(D.cell_cursor, 0, 4, h->stream));
         if (h->search_smem) {
-          CUDA_TRY(h, cudaFuncSetAttribute(k_nominate_search_fair<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-          k_nominate_search_fair<true><<<h->search_grid, 32, h->search_smem_bytes, h->stream>>>(D);
+          CUDA_TRY(h, cudaFuncSetAttribute(k_nominate_search_fair<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+          CUDA_TRY(h, cudaFuncSetAttribute(k_nominate_search_fair<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+          if (D.memo_items) { k_nominate_search_fair<true, true><<<h->search_grid, 32, h->search_smem_bytes, h->stream>>>(D); launches++; }
+          k_nominate_search_fair<true, false><<<h->search_grid, 32, h->search_smem_bytes, h->stream>>>(D);
         } else {
-          k_nominate_search_fair<false><<<h->search_grid, 32, 0, h->stream>>>(D);
+          if (D.memo_items) { k_nominate_search_fair<false, true><<<h->search_grid, 32, 0, h->stream>>>(D); launches++; }
+          k_nominate_search_fair<false, false><<<h->search_grid, 32, 0, h->stream>>>(D);
         }
         launches++;
       } else {
@@ -908,7 +929,6 @@ static int32_t cycle_enqueue(kb_handle *h) {
         k_nominate_walk<<<h->sb_grid, h->sb_wpb * 32, h->sb_smem, h->stream>>>(D, h->sb_col_elems, h->sb_list_cap); launches++;
       }
     }
-    if (D.flags & KB_F_FAIR_SHARING) { kmark(h, KB_K_FAIR_PREP); k_fair_prep<<<(D.N * D.R + 255) / 256, 256, 0, h->stream>>>(D); launches++; }
     kmark(h, KB_K_SCAN); k_scan_roots<<<1, 1024, 0, h->stream>>>(D); launches++;
     kmark(h, KB_K_SCATTER); k_scatter<<<(D.H + 255) / 256, 256, 0, h->stream>>>(D); launches++;
     kmark(h, KB_K_RANK); k_rank<<<(D.H + 255) / 256, 256, 0, h->stream>>>(D); launches++;

@@ -788,10 +788,11 @@ __global__ void k_cells_scatter(DevSnap D) {
   int pos = D.cell_start[b] + atomicAdd(&D.cell_fill[b], 1);
   D.cell_list[pos] = (int)idx; D.cell_bucket[pos] = b;
 }
-#define KB_CELL_TASK 64  // oracle cells per CTA task
+#define KB_CELL_TASK 512     // oracle cells per CTA task: at most / at least
+#define KB_CELL_TASK_MIN 32
 __global__ void __launch_bounds__(512) k_search_cells_grouped(DevSnap D, int ncap, int codes_smem, int list_cap) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ int s_task;
+  __shared__ int s_task, s_task_n, s_next;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
   const size_t gw = (size_t)blockIdx.x * wpb + warp;
   const int FR = D.FR;
@@ -810,17 +811,25 @@ __global__ void __launch_bounds__(512) k_search_cells_grouped(DevSnap D, int nca
   const int n_cells = D.cell_start[D.nRoots * FR];
   int staged = -1;
   while (true) {
+    // Guided self-scheduling over the bucket-grouped cell list: a CTA claims a share of what is left (large tasks while
+    // there is plenty, KB_CELL_TASK_MIN at the end), so the barrier per task is amortised and the kernel's tail is short.
     __syncthreads();
-    if (threadIdx.x == 0) s_task = atomicAdd(D.cell_cursor, 1);
+    if (threadIdx.x == 0) {
+      int seen = *(volatile int *)D.cell_cursor;
+      int chunk = (n_cells - seen) / (2 * (int)gridDim.x);
+      chunk = max(KB_CELL_TASK_MIN, min(KB_CELL_TASK, chunk));
+      s_task = atomicAdd(D.cell_cursor, chunk);
+      s_task_n = chunk;
+    }
     __syncthreads();
-    const int lo = s_task * KB_CELL_TASK, hi = min(lo + KB_CELL_TASK, n_cells);
+    const int lo = s_task, hi = min(lo + s_task_n, n_cells);
     if (lo >= n_cells) break;
     for (int p = lo; p < hi;) {
       const int b = D.cell_bucket[p];
       int q = p + 1;
       while (q < hi && D.cell_bucket[q] == b) q++;  // run of cells in the same bucket (the list is grouped by bucket)
+      __syncthreads();  // every warp is done with the previous run and its column
       if (b != staged) {
-        __syncthreads();  // every warp is done with the previous column
         const int slot = b / FR, fr = b % FR;
         const int nbase = D.slot_base[slot], nn = D.slot_base[slot + 1] - nbase;
         const size_t o = (size_t)nbase * FR + (size_t)fr * nn;
@@ -829,9 +838,14 @@ __global__ void __launch_bounds__(512) k_search_cells_grouped(DevSnap D, int nca
         for (int i = threadIdx.x; i < nn * 2; i += blockDim.x) dst[i] = __ldg(src + i);
         for (int i = threadIdx.x; i < nn; i += blockDim.x) sh_base[i] = D.colU[o + i];
         staged = b;
-        __syncthreads();
       }
-      for (int c = p + warp; c < q; c += wpb) {
+      if (threadIdx.x == 0) s_next = p;
+      __syncthreads();
+      while (true) {  // searches differ a lot in length: warps take the run's cells one at a time
+        int c = 0;
+        if (lane == 0) c = atomicAdd(&s_next, 1);
+        c = __shfl_sync(0xffffffffu, c, 0);
+        if (c >= q) break;
         const int idx = D.cell_list[c];
         const int item = idx / FR, fr = idx % FR;
         const int wl = D.heads[D.ps_list[item]], cq = D.wl_cq[wl];
@@ -960,8 +974,10 @@ struct NomSearch {
   const PTab<kSmem> *T;
   PreCtx *c;
   PreScratch S;
+  const SimMemo *memo = nullptr;  // [FR] results of k_fair_cells for this entry, or nullptr
   // SimulatePreemption preemption_oracle.go:41-71 on the private tree
   __device__ inline int simulate(const DevSnap &D, int wl, int cq, int fr, i64 val, int *borrow_after) {
+    if (memo) { SimMemo m = memo[fr]; if (m.val == val && m.pm >= 0) { *borrow_after = m.borrow; return m.pm; } }
     int hcq = T->handle(cq);
     *borrow_after = T->find_height(hcq, fr, val);  // no candidates: height on the untouched snapshot (:53-56)
     if (!candidates_possible(D, cq)) return PM_NOCAND;
@@ -1006,7 +1022,11 @@ struct NomSearch {
   }
 };
 
-template <bool kSmem>
+// kCells: the searches of the preemption oracle are independent of each other (every SimulatePreemption starts from
+// the cycle's snapshot), so they run first, one (entry, flavor-resource) cell per task over the whole grid, and leave
+// their results in the memo; the per-entry walk (kCells = false) then replays the flavor assignment against the memo
+// and only runs GetTargets itself.
+template <bool kSmem, bool kCells>
 __global__ void __launch_bounds__(32, 16) k_nominate_search_fair(DevSnap D) {  // <= 128 registers: 16 single-warp CTAs per SM
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ PreCtx ctx;
@@ -1026,16 +1046,35 @@ __global__ void __launch_bounds__(32, 16) k_nominate_search_fair(DevSnap D) {  /
   T.D = &D; T.FR = FR;
   T.dirty = D.sc_dirty + (size_t)blockIdx.x * D.sc_node_cap; T.drs_ratio = D.sc_drs_ratio + (size_t)blockIdx.x * D.sc_node_cap;
   T.drs_meta = D.sc_drs_meta + (size_t)blockIdx.x * D.sc_node_cap;
+  unsigned char *smem_tab = smem_raw;
+  if (kSmem) {  // per-node search state next to the tree: [share 8 B][queue head 4 B][on_path][pruned][dirty][share meta]
+    const size_t cap = (size_t)D.sc_node_cap;
+    T.drs_ratio = (double *)smem_raw;
+    S.cq_lca = {(int32_t *)(smem_raw + cap * 8)};
+    S.on_path = {(int8_t *)(smem_raw + cap * 12)};
+    S.cq_class = {(int8_t *)(smem_raw + cap * 13)};
+    T.dirty = smem_raw + cap * 14;
+    T.drs_meta = (int8_t *)(smem_raw + cap * 15);
+    smem_tab = smem_raw + ((cap * 16 + 15) & ~(size_t)15);
+  }
   int cur_slot = -1;
+  const int n_items = kCells ? min(*D.ps_n, D.memo_items) : *D.ps_n;
   while (true) {
     __syncthreads();
-    if (threadIdx.x == 0) s_item = atomicAdd(D.ps_cursor, 1);
+    if (threadIdx.x == 0) s_item = atomicAdd(kCells ? D.cell_cursor : D.ps_cursor, 1);
     __syncthreads();
-    int item = s_item;
-    if (item >= *D.ps_n) break;
+    int item = s_item, cell_fr = 0;
+    if (kCells) { cell_fr = item % FR; item /= FR; }
+    if (item >= n_items) break;
     int e = D.ps_list[item];
     int wl = D.heads[e];
     int cq = D.wl_cq[wl];
+    i64 cell_req = 0;
+    if (kCells) {  // cells the flavor walk would not ask the oracle about are marked and skipped (uniform over the warp)
+      int wl2, cq2;
+      bool need = oracle_cell_needed(D, item, cell_fr, &wl2, &cq2, &cell_req);
+      if (!need) { if (threadIdx.x == 0) { SimMemo mm; mm.val = -1; mm.pm = -1; mm.borrow = 0; D.memo[(size_t)item * FR + cell_fr] = mm; } continue; }
+    }
     int slot = D.root_slot[cq];
     if (slot != cur_slot) {  // stage a private copy of the root's tree (the search restores it after use)
       cur_slot = slot;
@@ -1043,7 +1082,7 @@ __global__ void __launch_bounds__(32, 16) k_nominate_search_fair(DevSnap D) {  /
       else { int t = slot - D.nLone; T.nodes = D.tree_nodes + D.tree_start[t]; T.nn = D.tree_start[t + 1] - D.tree_start[t]; }
       size_t tb = (size_t)T.nn * FR;
       if (kSmem) {
-        i64 *u = (i64 *)smem_raw, *sb = u + tb, *lq = sb + tb, *bl = lq + tb;
+        i64 *u = (i64 *)smem_tab, *sb = u + tb, *lq = sb + tb, *bl = lq + tb;
         int *lp = (int *)(bl + tb);
         for (int i = threadIdx.x; i < (int)tb; i += blockDim.x) {
           size_t c = (size_t)T.nodes[i / FR] * FR + i % FR;
@@ -1059,8 +1098,19 @@ __global__ void __launch_bounds__(32, 16) k_nominate_search_fair(DevSnap D) {  /
       }
       __syncthreads();
     }
+    if (kCells) {
+      if (threadIdx.x == 0) {
+        NomSearch<kSmem> orc{&T, &ctx, S};
+        int borrow;
+        int pm = orc.simulate(D, wl, cq, cell_fr, cell_req, &borrow);
+        SimMemo mm; mm.val = cell_req; mm.pm = pm; mm.borrow = borrow;
+        D.memo[(size_t)item * FR + cell_fr] = mm;
+      }
+      continue;
+    }
     if (threadIdx.x == 0) {
       NomSearch<kSmem> orc{&T, &ctx, S};
+      orc.memo = item < D.memo_items ? D.memo + (size_t)item * FR : nullptr;
       int borrowing, nt;
       int mode = get_assignments(D, orc, wl, &borrowing, &nt);
       D.mode[e] = (uint8_t)mode;
@@ -1345,23 +1395,40 @@ struct Tab {
       }
     }
   }
+  // available() on operands already in registers (plen <= KB_PF)
+  __device__ __forceinline__ static i64 avail_from(const i64 (&u)[KB_PF], const i64 (&sb)[KB_PF], const i64 (&ll)[KB_PF], const i64 (&b)[KB_PF], int plen) {
+    i64 a = 0;
+#pragma unroll
+    for (int k = KB_PF - 1; k >= 0; k--) {
+      if (k >= plen) continue;
+      if (k == plen - 1) { a = sb[k] - u[k]; continue; }
+      i64 l = local_quota(sb[k], ll[k]);
+      i64 pa = a;
+      if (b[k] != KB_NO_LIMIT) pa = imin((sb[k] - l) - imax(0, u[k] - l) + b[k], pa);
+      a = imax(0, l - u[k]) + pa;
+    }
+    return a;
+  }
+  // addUsage on operands already in registers (plen <= KB_PF): stores the new usage of the touched levels
+  template <bool S>
+  __device__ __forceinline__ void add_from(const int *path, int plen, int fr, const i64 (&u)[KB_PF], const i64 (&sb)[KB_PF], const i64 (&ll)[KB_PF], i64 val) const {
+    bool go = true;
+#pragma unroll
+    for (int k = 0; k < KB_PF; k++) {
+      if (k >= plen || !go) continue;
+      i64 la = imax(0, local_quota(sb[k], ll[k]) - u[k]);
+      setUx<S>(path[k], fr, u[k] + val);
+      if (!(k + 1 < plen && val > la)) go = false;
+      val -= la;
+    }
+  }
   template <bool S = false>
   __device__ inline i64 avail(const int *path, int plen, int fr) const {
     if constexpr (!kSmem) {
       if (plen <= KB_PF) {
         i64 u[KB_PF], sb[KB_PF], ll[KB_PF], b[KB_PF];
         prefetch<S>(path, plen, fr, u, sb, ll, b, true);
-        i64 a = 0;
-#pragma unroll
-        for (int k = KB_PF - 1; k >= 0; k--) {
-          if (k >= plen) continue;
-          if (k == plen - 1) { a = sb[k] - u[k]; continue; }
-          i64 l = local_quota(sb[k], ll[k]);
-          i64 pa = a;
-          if (b[k] != KB_NO_LIMIT) pa = imin((sb[k] - l) - imax(0, u[k] - l) + b[k], pa);
-          a = imax(0, l - u[k]) + pa;
-        }
-        return a;
+        return avail_from(u, sb, ll, b, plen);
       }
     }
     int rt = path[plen - 1];
@@ -1492,13 +1559,22 @@ __device__ inline void publish_usage(const DevSnap &D, const Tab<kSmem> &T, cons
 // aggregated Assignment.Usage.Quota (absent cell = -1).  s_path: KB_MAX_DEPTH+2 ints.
 // cq = global id of the entry's ClusterQueue, ntg/toff = its preemption targets in the pool.
 // T.shadow_on points at a shared-memory flag (0 at kernel start).
+// Global-table mode: the CTA stages, per tile, everything of an entry that does not depend on earlier commits — its
+// path and the usage cells of its preemption targets (TgCell: quantity, column, the target ClusterQueue's path) — so
+// the commit warp only waits for the usage / shadow values themselves.
+struct TgCell { i64 qty; int32_t path[KB_PF]; int32_t adm; int16_t fr; int8_t plen; int8_t pad; };
+#define KB_TG_CAP 2048  // staged target cells per tile
 template <bool kSmem>
 __device__ inline void commit_entry(const DevSnap &D, const Tab<kSmem> &T, int *s_path, int lane, int e, int nd, int mode,
-                                    int borrowing, const i64 *qrow, int rank, int cq, int ntg, int toff) {
+                                    int borrowing, const i64 *qrow, int rank, int cq, int ntg, int toff,
+                                    const int *st_path = nullptr, int st_plen = 0, const TgCell *cells = nullptr, int ncell = 0) {
   const int FR = D.FR;
   if (lane == 0) D.rank[e] = rank;
   if (mode == KB_MODE_NOFIT) { if (lane == 0) D.decision[e] = KB_DEC_NOFIT; return; }
-  if constexpr (!kSmem) {  // static path table: one coalesced row instead of a chain of dependent parent loads
+  if (st_path) {  // staged by the tile preparation
+    if (lane < st_plen) s_path[lane] = st_path[lane];
+    if (lane == 0) s_path[KB_MAX_DEPTH + 1] = st_plen;
+  } else if constexpr (!kSmem) {  // static path table: one coalesced row instead of a chain of dependent parent loads
     int pl = D.cq_plen[nd];
     if (lane < pl) s_path[lane] = D.cq_path[(size_t)nd * D.path_stride + lane];
     if (lane == 0) s_path[KB_MAX_DEPTH + 1] = pl;
@@ -1529,7 +1605,8 @@ __device__ inline void commit_entry(const DevSnap &D, const Tab<kSmem> &T, int *
   // workload preempted so far in this root and without the new targets (:503-511) = the shadow table
   if (ntg > 0) {
     bool overlap = false;
-    for (int k = lane; k < ntg; k += 32) if (D.preempted[D.tgt_pool_adm[toff + k]]) overlap = true;
+    if (cells) { for (int k = lane; k < ncell; k += 32) if (D.preempted[cells[k].adm]) overlap = true; }
+    else for (int k = lane; k < ntg; k += 32) if (D.preempted[D.tgt_pool_adm[toff + k]]) overlap = true;
     if (__any_sync(0xffffffffu, overlap)) { if (lane == 0) D.decision[e] = KB_DEC_SKIPPED_OVERLAP; __syncwarp(); return; }
     if (!shadow) {  // first targets of this root: the shadow starts as a copy of the current usage
       for (int i = lane; i < T.tnn * FR; i += 32) { int h = kSmem ? i / FR : T.tnodes[i / FR]; T.shadow[T.scell(h, i % FR)] = T.U(h, i % FR); }
@@ -1547,21 +1624,71 @@ __device__ inline void commit_entry(const DevSnap &D, const Tab<kSmem> &T, int *
     }
     __syncwarp();
   };
-  for (int k = 0; k < ntg; k++) apply(D.tgt_pool_adm[toff + k], true);  // SimulateWorkloadRemoval snapshot.go:67-84
-  bool ok = true;  // fits :503-511
-  for (int fr = lane; fr < FR; fr += 32) {
-    i64 q = qrow[fr];
-    if (q > 0 && imax(0, shadow ? T.template avail<true>(s_path, plen, fr) : T.avail(s_path, plen, fr)) < q) ok = false;
-  }
-  ok = __all_sync(0xffffffffu, ok);
-  if (ok) {
-    for (int k = lane; k < ntg; k += 32) D.preempted[D.tgt_pool_adm[toff + k]] = 1;  // preemptedWorkloads.Insert :335 (stay removed in the shadow)
-    for (int fr = lane; fr < FR; fr += 32) {  // cq.AddUsage :336
-      i64 q = qrow[fr];
-      if (q > 0) { T.add(s_path, plen, fr, q); if (shadow) T.template add<true>(s_path, plen, fr, q); }
+  // staged cells: columns are independent, so every lane walks the cells of ITS columns (in target order) and the
+  // lanes' walks overlap — one memory round trip per "layer" of cells instead of one per cell
+  unsigned long long mine = 0;
+  if (cells) for (int k = 0; k < ncell; k++) if ((cells[k].fr & 31) == lane) mine |= 1ull << k;
+  auto apply_cells = [&](bool remove) {
+    if constexpr (!kSmem) {
+      unsigned long long m = mine;
+      while (__any_sync(0xffffffffu, m != 0)) {
+        if (m) {
+          int k = __ffsll((long long)m) - 1;
+          m &= m - 1;
+          const TgCell &c = cells[k];
+          if (remove) T.template remove<true>(c.path, c.plen, c.fr, c.qty);
+          else T.template add<true>(c.path, c.plen, c.fr, c.qty);
+        }
+      }
+      __syncwarp();
     }
-  } else {
-    for (int k = 0; k < ntg; k++) apply(D.tgt_pool_adm[toff + k], false);
+  };
+  if (cells) apply_cells(true);
+  else for (int k = 0; k < ntg; k++) apply(D.tgt_pool_adm[toff + k], true);  // SimulateWorkloadRemoval snapshot.go:67-84
+  bool ok = true;  // fits :503-511
+  bool fused = false;
+  if constexpr (!kSmem) {
+    if (FR <= 32 && plen <= KB_PF) {  // one column per lane: fits() and AddUsage share one load of the path's operands
+      fused = true;
+      const int fr = lane;
+      const i64 q = lane < FR ? qrow[fr] : -1;
+      i64 um[KB_PF], us[KB_PF], sb[KB_PF], ll[KB_PF], b[KB_PF];
+      if (q > 0) {
+        T.template prefetch<false>(s_path, plen, fr, um, sb, ll, b, true);
+        if (shadow) {
+#pragma unroll
+          for (int k = 0; k < KB_PF; k++) us[k] = k < plen ? T.shadow[(size_t)s_path[k] * FR + fr] : 0;
+          if (imax(0, Tab<kSmem>::avail_from(us, sb, ll, b, plen)) < q) ok = false;
+        } else if (imax(0, Tab<kSmem>::avail_from(um, sb, ll, b, plen)) < q) ok = false;
+      }
+      ok = __all_sync(0xffffffffu, ok);
+      if (ok) {
+        if (cells) { for (int k = lane; k < ncell; k += 32) D.preempted[cells[k].adm] = 1; }
+        else for (int k = lane; k < ntg; k += 32) D.preempted[D.tgt_pool_adm[toff + k]] = 1;  // preemptedWorkloads.Insert :335
+        if (q > 0) {  // cq.AddUsage :336
+          T.template add_from<false>(s_path, plen, fr, um, sb, ll, q);
+          if (shadow) T.template add_from<true>(s_path, plen, fr, us, sb, ll, q);
+        }
+      }
+    }
+  }
+  if (!fused) {
+    for (int fr = lane; fr < FR; fr += 32) {
+      i64 q = qrow[fr];
+      if (q > 0 && imax(0, shadow ? T.template avail<true>(s_path, plen, fr) : T.avail(s_path, plen, fr)) < q) ok = false;
+    }
+    ok = __all_sync(0xffffffffu, ok);
+    if (ok) {
+      for (int k = lane; k < ntg; k += 32) D.preempted[D.tgt_pool_adm[toff + k]] = 1;  // preemptedWorkloads.Insert :335 (stay removed in the shadow)
+      for (int fr = lane; fr < FR; fr += 32) {  // cq.AddUsage :336
+        i64 q = qrow[fr];
+        if (q > 0) { T.add(s_path, plen, fr, q); if (shadow) T.template add<true>(s_path, plen, fr, q); }
+      }
+    }
+  }
+  if (!ok) {
+    if (cells) apply_cells(false);
+    else for (int k = 0; k < ntg; k++) apply(D.tgt_pool_adm[toff + k], false);
   }
   if (lane == 0) D.decision[e] = ok ? (mode == KB_MODE_PREEMPT ? KB_DEC_PREEMPTING : KB_DEC_ASSUMED) : KB_DEC_SKIPPED_NO_FIT;
   __syncwarp();
@@ -1716,6 +1843,10 @@ __global__ void __launch_bounds__(KB_ADMIT_THREADS) k_admit(DevSnap D, int slot_
   int *s_shadow_on = s_path + KB_MAX_DEPTH + 2;
   if (threadIdx.x == 0) *s_shadow_on = 0;
   T.shadow_on = s_shadow_on;
+  // global-table mode: per-tile staging of paths and target cells (commit_entry)
+  int *t_plen = s_shadow_on + 2, *t_path = t_plen + KB_TILE, *tc_start = t_path + KB_TILE * KB_PF;
+  TgCell *tcells = reinterpret_cast<TgCell *>(((uintptr_t)(tc_start + KB_TILE + 2) + 7) & ~(uintptr_t)7);
+  const bool stage_cells = !kSmemTables && D.path_stride <= KB_PF;
 
   // ---- 1. iterator order: k_rank already produced it for roots up to KB_RANK_CAP entries; larger roots sort here
   //         with an ascending-only bitonic network over the global index array (virtual +inf padding never moves).
@@ -1753,6 +1884,32 @@ __global__ void __launch_bounds__(KB_ADMIT_THREADS) k_admit(DevSnap D, int slot_
     __syncthreads();
     // one thread per entry walks its podset rows once and scatters the cells of its row
     for (int i = threadIdx.x; i < tn; i += blockDim.x) expand_entry(D, t_e[i], s_q + (size_t)i * FR);
+    if (stage_cells) {
+      for (int i = threadIdx.x; i < tn; i += blockDim.x) {
+        int nd = t_node[i], pl = D.cq_plen[nd];
+        t_plen[i] = pl;
+        for (int k = 0; k < pl; k++) t_path[i * KB_PF + k] = D.cq_path[(size_t)nd * D.path_stride + k];
+        int nc = 0;
+        for (int k = 0; k < t_ntg[i]; k++) { int a = D.tgt_pool_adm[t_toff[i] + k]; nc += D.adm_use_start[a + 1] - D.adm_use_start[a]; }
+        tc_start[i + 1] = nc;
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) { int acc = 0; tc_start[0] = 0; for (int i = 0; i < tn; i++) { acc += tc_start[i + 1]; tc_start[i + 1] = acc; } }
+      __syncthreads();
+      for (int i = threadIdx.x; i < tn; i += blockDim.x) {
+        int c0 = tc_start[i], c1 = tc_start[i + 1];
+        if (c1 > KB_TG_CAP || c1 - c0 > 64) continue;  // the commit falls back to the unstaged walk for this entry
+        for (int k = 0; k < t_ntg[i]; k++) {
+          int a = D.tgt_pool_adm[t_toff[i] + k];
+          int nd2 = D.adm_cq[a], pl = D.cq_plen[nd2];
+          for (int u = D.adm_use_start[a]; u < D.adm_use_start[a + 1]; u++, c0++) {
+            TgCell &c = tcells[c0];
+            c.qty = D.adm_use_qty[u]; c.fr = (int16_t)D.adm_use_fr[u]; c.adm = a; c.plen = (int8_t)pl;
+            for (int j = 0; j < pl; j++) c.path[j] = D.cq_path[(size_t)nd2 * D.path_stride + j];
+          }
+        }
+      }
+    }
     __syncthreads();
     if (warp == 0) {
       if constexpr (kSmemTables) {
@@ -1762,9 +1919,17 @@ __global__ void __launch_bounds__(KB_ADMIT_THREADS) k_admit(DevSnap D, int slot_
         }
       }
       if (!flat)
-        for (int i = 0; i < tn; i++)
-          commit_entry<kSmemTables>(D, T, s_path, lane, t_e[i], t_node[i], t_mode[i], t_borrow[i], s_q + (size_t)i * FR, base + i,
-                                    t_cq[i], t_ntg[i], t_toff[i]);
+        for (int i = 0; i < tn; i++) {
+          if (stage_cells) {
+            int c0 = tc_start[i], c1 = tc_start[i + 1];
+            bool st = c1 <= KB_TG_CAP && c1 - c0 <= 64;
+            commit_entry<kSmemTables>(D, T, s_path, lane, t_e[i], t_node[i], t_mode[i], t_borrow[i], s_q + (size_t)i * FR, base + i,
+                                      t_cq[i], t_ntg[i], t_toff[i], t_path + i * KB_PF, t_plen[i], st ? tcells + c0 : nullptr, c1 - c0);
+          } else {
+            commit_entry<kSmemTables>(D, T, s_path, lane, t_e[i], t_node[i], t_mode[i], t_borrow[i], s_q + (size_t)i * FR, base + i,
+                                      t_cq[i], t_ntg[i], t_toff[i]);
+          }
+        }
     }
     __syncthreads();
     if (flat) {  // decisions of the flat commit loop (t_mode[i] = KB_DEC_* | 0x100), written by the whole CTA

@@ -10,10 +10,10 @@
 // else in a per-CTA global scratch.  One search is a data-dependent sequential walk (classify,
 // remove, re-check, fill back), so it runs on ONE thread; parallelism comes from running many
 // searches at once (one single-warp CTA each; the other lanes only stage the tree).  The
-// ordered candidate list is a filtered pass over the root's admitted workloads, which are
-// pre-sorted once per cycle by the preemptor-independent keys of CandidatesOrdering — no sort
-// per preemptor.  (A barrier-based master/worker split inside one warp is not expressible:
-// bar.sync is warp-aligned.)
+// per-ClusterQueue candidate queues are cursors into the ClusterQueue's list of admitted
+// workloads, which is ranked once per cycle by the preemptor-independent keys of
+// CandidatesOrdering — no gathering and no sort per preemptor.  (A barrier-based master/worker
+// split inside one warp is not expressible: bar.sync is warp-aligned.)
 #pragma once
 
 #include "kb_device.cuh"
@@ -157,33 +157,6 @@ __device__ __forceinline__ bool uses_resources(const DevSnap &D, const PreCtx &c
   return false;
 }
 
-// ---------------------------------------------------------------------------
-// Ordered candidate gathering.  The host orders the admitted workloads of every root once per
-// cycle by the preemptor-independent part of CandidatesOrdering (common/ordering.go:41-100:
-// evicted first, lower priority first, more recently reserved first, UID) -> adm_rank; the
-// per-CQ lists (cq_adm) are in that order.  A search only touches the lists of the ClusterQueues it
-// can take candidates from: gather the accepted workloads, then heap sort on (segment << 28 | rank).
-// ---------------------------------------------------------------------------
-// heap sort of (key, cand, variant) triples by key
-__device__ inline void sort_candidates(const SArr<int32_t> &key, const SArr<int32_t> &cand, const SArr<uint8_t> &var, int n) {
-  auto swp = [&](int i, int j) {
-    int32_t t = key[i]; key[i] = key[j]; key[j] = t;
-    t = cand[i]; cand[i] = cand[j]; cand[j] = t;
-    uint8_t v = var[i]; var[i] = var[j]; var[j] = v;
-  };
-  auto sift = [&](int i, int len) {
-    while (true) {
-      int l = 2 * i + 1, r = l + 1, b = i;
-      if (l < len && key[l] > key[b]) b = l;
-      if (r < len && key[r] > key[b]) b = r;
-      if (b == i) return;
-      swp(i, b); i = b;
-    }
-  };
-  for (int i = n / 2 - 1; i >= 0; i--) sift(i, n);
-  for (int len = n - 1; len > 0; len--) { swp(0, len); sift(0, len); }
-}
-
 template <bool kSmem>
 __device__ __forceinline__ bool within_nominal(const PTab<kSmem> &T, const PreCtx &c, int h) {  // IsWithinNominalInResources resource_node.go:248-255
   for (int j = 0; j < c.n_need; j++) if (T.U(h, c.need_fr[j]) > T.Sub(h, c.need_fr[j])) return false;
@@ -239,16 +212,16 @@ __device__ inline DevDRS fair_drs(const DevSnap &D, const PTab<kSmem> &T, int h)
 }
 template <bool kSmem>
 __device__ inline DevDRS fair_drs_compute(const DevSnap &D, const PTab<kSmem> &T, int h, DevDRS d, int p) {
-  const int R = D.R, F = D.F, FR = D.FR;
+  const int R = D.R, F = D.F;
   for (int r = 0; r < R; r++) {
-    i64 b = 0, lend = 0;
+    i64 b = 0;
     for (int f = 0; f < F; f++) {
       int fr = f * R + r;
       i64 over = T.U(h, fr) - T.Sub(h, fr);
       if (over > 0) b += over;
-      lend += D.potential[(size_t)p * FR + fr];
     }
     if (b > 0) {
+      const i64 lend = D.fs_lend[(size_t)p * R + r];  // sum over flavors of the parent's potentialAvailable (k_fair_prep)
       d.borrowing = true;
       if (lend > 0) {
         double ratio = (double)b * 1000.0 / (double)lend;
@@ -276,8 +249,13 @@ __device__ inline void fair_search(const DevSnap &D, const PTab<kSmem> &T, PreCt
   }
   for (int h = 0; h < T.nn; h++) { S.on_path[h] = -1; S.cq_class[h] = 0; S.cq_lca[h] = -1; if (T.dirty) T.dirty[h] = 1; }
   for (int k = 1; k < c->plen; k++) S.on_path[c->path[k]] = (int8_t)k;  // preemptorAncestors
-  // ---- findCandidates :514-533, sorted by CandidatesOrdering: evicted first, other CQs before the preemptor's.
-  //         Other ClusterQueues qualify only while borrowing (cqIsBorrowing :535-545) -> subset of k_over's list.
+  // ---- findCandidates :514-533 + MakeClusterQueueOrdering ordering.go:62-83.  The reference sorts all candidates by
+  // CandidatesOrdering and splits them into one queue per ClusterQueue; only the order INSIDE a queue is ever used
+  // (nextTarget compares queue heads, pop takes a head).  Inside one ClusterQueue that order is (evicted first,
+  // priority, reservation time, UID) = the preemptor-independent rank the per-ClusterQueue lists (cq_adm) are kept
+  // in.  So a queue is a cursor into the ClusterQueue's rank-ordered list that skips the workloads the preemptor may
+  // not preempt: no gathering, no sort.  Other ClusterQueues qualify only while borrowing (cqIsBorrowing :535-545)
+  // -> subset of k_over's list.
   const int slot = D.root_slot[cq];
   const int32_t *over = D.over_list + D.root_cq_start[slot];
   const int n_over = cohort_cands ? D.over_count[slot] : 0;
@@ -286,29 +264,40 @@ __device__ inline void fair_search(const DevSnap &D, const PTab<kSmem> &T, PreCt
     for (int j = 0; j < c->n_need; j++) if (T.borrowing_with(h, c->need_fr[j], 0)) return true;
     return false;
   };
-  int nall = 0;
-  auto gather = [&](int q, int cls) {  // cls: 0 other ClusterQueue, 1 the preemptor's
-    int policy = cls == 1 ? D.cq_within_cq[cq] : D.cq_reclaim_within[cq];
-    for (int i = D.cq_adm_start[q]; i < D.cq_adm_start[q + 1]; i++) {
-      int a = D.cq_adm[i];
-      if (!satisfies_policy(D, *c, a, policy) || !uses_resources(D, *c, a)) continue;
-      S.cand[nall] = a; S.variant[nall] = 0; S.aux1[nall] = (((D.adm_evicted[a] ? 0 : 2) + cls) << 28) | D.adm_rank[a];
-      nall++;
-    }
-  };
-  if (own_cands) gather(cq, 1);
-  for (int i = 0; i < n_over; i++) {
-    int q = over[i];
-    if (q != cq && is_borrowing(q)) gather(q, 0);
-  }
-  sort_candidates(S.aux1, S.cand, S.variant, nall);
-  if (nall == 0) { c->n_targets = 0; return; }
-  SArr<int32_t> head = S.cq_lca;   // per node: index (into the current candidate list) of the queue head, or -1
-  SArr<int32_t> next = S.aux1;
+  SArr<int32_t> head = S.cq_lca;   // per node: position of the queue head (in cq_adm, or in the retry list), or -1
+  SArr<int32_t> next = S.aux1;     // retry list: next of the same ClusterQueue
   SArr<int8_t> pruned = S.cq_class;
-  auto build_queues = [&](const SArr<int32_t> &list, int n) {  // MakeClusterQueueOrdering ordering.go:62-83
+  SArr<int32_t> retry = S.aux2;
+  bool second = false;             // queues over the retry list (runSecondFsStrategy)
+  auto advance = [&](int q, int i) -> int {  // first candidate of ClusterQueue q at or after position i of cq_adm
+    const int policy = q == cq ? D.cq_within_cq[cq] : D.cq_reclaim_within[cq];
+    for (const int e = D.cq_adm_start[q + 1]; i < e; i++) {
+      int a = D.cq_adm[i];
+      if (satisfies_policy(D, *c, a, policy) && uses_resources(D, *c, a)) return i;
+    }
+    return -1;
+  };
+  auto front = [&](int h) -> int { int i = head[h]; return second ? retry[i] : D.cq_adm[i]; };  // head[h] >= 0
+  auto pop = [&](int h) -> int {
+    int i = head[h], a;
+    if (second) { a = retry[i]; head[h] = next[i]; }
+    else { a = D.cq_adm[i]; head[h] = advance(T.nodes[h], i + 1); }
+    return a;
+  };
+  const int n_root_adm = D.root_adm_start[slot + 1] - D.root_adm_start[slot];  // bound on the candidates (loop guards)
+  int nall = 0;  // ClusterQueues with at least one candidate
+  if (own_cands) { int i = advance(cq, D.cq_adm_start[cq]); head[hcq] = i; nall += i >= 0; }
+  for (int k = 0; k < n_over; k++) {
+    int q = over[k];
+    if (q == cq || !is_borrowing(q)) continue;
+    int i = advance(q, D.cq_adm_start[q]);
+    head[T.handle(q)] = i; nall += i >= 0;
+  }
+  if (nall == 0) { c->n_targets = 0; return; }
+  auto build_retry_queues = [&](int n) {  // MakeClusterQueueOrdering over the retry candidates
     for (int h = 0; h < T.nn; h++) { head[h] = -1; pruned[h] = 0; }
-    for (int i = n - 1; i >= 0; i--) { int h = T.handle(D.adm_cq[list[i]]); next[i] = head[h]; head[h] = i; }
+    for (int i = n - 1; i >= 0; i--) { int h = T.handle(D.adm_cq[retry[i]]); next[i] = head[h]; head[h] = i; }
+    second = true;
   };
   auto usage_add = [&](bool add) {  // SimulateUsageAddition / Removal of the incoming workload
     for (int j = 0; j < c->n_use; j++) { if (add) T.add(hcq, c->use_fr[j], c->use_q[j]); else T.remove(hcq, c->use_fr[j], c->use_q[j]); }
@@ -319,7 +308,6 @@ __device__ inline void fair_search(const DevSnap &D, const PTab<kSmem> &T, PreCt
     usage_add(true);
     return r;
   };
-  SArr<int32_t> list = S.cand;
   auto next_target = [&](int root) -> int {  // nextTarget ordering.go:141-208 (tail recursion unrolled)
     int cohort = root;
     for (int guard = 0;; guard++) {
@@ -337,7 +325,7 @@ __device__ inline void fair_search(const DevSnap &D, const PTab<kSmem> &T, PreCt
         else {
           int cmp = drs_compare(drs, hcq_drs);
           if (cmp == 0) {
-            if (cand_ordering(D, list[head[h]], list[head[highest_cq]], cq) < 0) highest_cq = h;
+            if (cand_ordering(D, front(h), front(highest_cq), cq) < 0) highest_cq = h;
           } else if (cmp == 1) { hcq_drs = drs; highest_cq = h; }
         }
       }
@@ -370,16 +358,13 @@ __device__ inline void fair_search(const DevSnap &D, const PTab<kSmem> &T, PreCt
 
   usage_add(true);  // :446 DRS values must include the incoming workload
   int nt = 0, nretry = 0;
-  SArr<int32_t> retry = S.aux2;
   bool fits = false;
   {  // runFirstFsStrategy :338-403
-    build_queues(S.cand, nall);
     bool within_nominal = false;
     if (D.flags & KB_F_FS_PREEMPT_WITHIN_NOMINAL) {  // queueWithinNominalInResourcesNeedingPreemption :591-598
       within_nominal = true;
       for (int j = 0; j < c->n_need; j++) if (T.borrowing_with(hcq, c->need_fr[j], 0)) within_nominal = false;
     }
-    auto pop = [&](int h) { int i = head[h]; head[h] = next[i]; return list[i]; };
     auto take = [&](int a, int reason) { T.remove_adm(a); S.tgt[nt] = a; S.tgt_reason[nt] = (uint8_t)reason; nt++; };
     auto step = [&](int h) -> bool {
       if (h == hcq) { take(pop(h), KB_REASON_IN_CLUSTER_QUEUE); return fits_fs(); }
@@ -403,7 +388,7 @@ __device__ inline void fair_search(const DevSnap &D, const PTab<kSmem> &T, PreCt
     } else {
       int root = c->path[c->plen - 1];
       for (int guard = 0; !pruned[root]; guard++) {
-        if (guard > 4 * (T.nn + nall) + 64) { atomicOr(D.status, KBS_INTERNAL_LOOP); break; }
+        if (guard > 4 * (T.nn + n_root_adm) + 64) { atomicOr(D.status, KBS_INTERNAL_LOOP); break; }
         int h = next_target(root);
         if (h < 0) continue;
         if (step(h)) { fits = true; break; }
@@ -411,18 +396,16 @@ __device__ inline void fair_search(const DevSnap &D, const PTab<kSmem> &T, PreCt
     }
   }
   if (!fits && nstrat > 1 && has_parent) {  // runSecondFsStrategy :407-431
-    list = retry;
-    build_queues(retry, nretry);
+    build_retry_queues(nretry);
     int root = c->path[c->plen - 1];
     for (int guard = 0; !pruned[root]; guard++) {
-      if (guard > 4 * (T.nn + nall) + 64) { atomicOr(D.status, KBS_INTERNAL_LOOP); break; }
+      if (guard > 4 * (T.nn + n_root_adm) + 64) { atomicOr(D.status, KBS_INTERNAL_LOOP); break; }
       int h = next_target(root);
       if (h < 0) continue;
       int pa, ta; almost_lcas(h, &pa, &ta);
       DevDRS pre_new = fair_drs(D, T, pa), tgt_old = fair_drs(D, T, ta);
       if (drs_compare(pre_new, tgt_old) < 0) {
-        int i = head[h]; head[h] = next[i];
-        int a = retry[i];
+        int a = pop(h);
         T.remove_adm(a); S.tgt[nt] = a; S.tgt_reason[nt] = KB_REASON_IN_COHORT_FAIR_SHARING; nt++;
         if (fits_fs()) { fits = true; break; }
       }

@@ -105,6 +105,8 @@ def drain(snap: abi.FlatSnapshot, run_cycle: Callable[[abi.FlatSnapshot], abi.Cy
         cs.set("ps_req", ps_req[rows]); cs.set("ps_last_tried", last_tried[rows])
         for nm in ("ps_req_mask", "ps_count", "ps_min_count", "ps_flavor_ok"):
             cs.set(nm, a[nm][rows])
+        if "ps_group" in a:  # optional tables (kb_snapshot: NULL when absent)
+            cs.set("ps_group", a["ps_group"][rows])
         cs.set("heads", np.arange(len(heads)))
         cs.finalize()
         out = run_cycle(cs)

@@ -110,6 +110,11 @@ def shard(snap: abi.FlatSnapshot, rank: int, world: int, node_rank: np.ndarray |
     out.set("ps_last_tried", a["ps_last_tried"].reshape(-1, R)[ps_rows])
     for nm in ("ps_req_mask", "ps_count", "ps_min_count", "ps_flavor_ok"):
         out.set(nm, a[nm][ps_rows])
+    if "ps_group" in a:  # optional tables (kb_snapshot: NULL when absent)
+        out.set("ps_group", a["ps_group"][ps_rows])
+    for nm in ("wl_has_quota_reservation", "wl_sched_hash"):
+        if nm in a:
+            out.set(nm, a[nm][wls])
     hpos = np.flatnonzero(wl_remap[a["heads"]] >= 0) if snap.n_heads else np.zeros(0, np.int64)
     out.set("heads", wl_remap[a["heads"][hpos]])
     # admitted workloads

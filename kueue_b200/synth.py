@@ -178,5 +178,10 @@ def compact_to_heads(snap: abi.FlatSnapshot) -> abi.FlatSnapshot:
     out.set("ps_req", a["ps_req"].reshape(-1, R)[rows]); out.set("ps_last_tried", a["ps_last_tried"].reshape(-1, R)[rows])
     for nm in ("ps_req_mask", "ps_count", "ps_min_count", "ps_flavor_ok"):
         out.set(nm, a[nm][rows])
+    if "ps_group" in a:  # optional tables (kb_snapshot: NULL when absent)
+        out.set("ps_group", a["ps_group"][rows])
+    for nm in ("wl_has_quota_reservation", "wl_sched_hash"):
+        if nm in a:
+            out.set(nm, a[nm][h])
     out.set("heads", np.arange(len(h)))
     return out.finalize()

@@ -37,6 +37,7 @@
 #include <cstring>
 #include <limits>
 #include <utility>
+#include <array>
 #include <vector>
 
 namespace {
@@ -726,9 +727,9 @@ class Oracle {
     for (int g = s.cq_rg_start[cq]; g < s.cq_rg_start[cq + 1]; g++) if (s.rg_res_mask[g] & (1u << r)) return g;
     return -1;
   }
-  // findFlavorForPodSets :762-897 for one podset (no podset groups without TAS).
-  // Returns false when no flavor could be assigned.  hasReasons <- status != nil.
-  bool findFlavorForPodSet(int wl, int psRow, const Preemptor &p, const i64 *reqs, uint32_t mask, int resName,
+  // findFlavorForPodSets :762-897 for one podset or one PodSetGroup (psRow = psIDs[0], reqs / mask / okMask of the
+  // whole group).  Returns false when no flavor could be assigned.  hasReasons <- status != nil.
+  bool findFlavorForPodSet(int wl, int psRow, uint64_t okMask, const Preemptor &p, const i64 *reqs, uint32_t mask, int resName,
                            const UsageVec &assignmentUsage, bool useLast, PodSetAssign &out, bool &hasReasons) {
     int cq = p.cq;
     int g = rgByResource(cq, resName);
@@ -747,7 +748,7 @@ class Oracle {
     for (; idx < nfl; idx++) {
       attempted = idx;
       int f = flv[idx];
-      if (!((s.ps_flavor_ok[psRow] >> f) & 1)) { anyReason = true; continue; }  // checkFlavorForPodSets :798-806
+      if (!((okMask >> f) & 1)) { anyReason = true; continue; }  // checkFlavorForPodSets :798-806
       GranularMode rep{P_FIT, 0};
       int8_t aMode[KB_MAX_RESOURCES]; int aBorrow[KB_MAX_RESOURCES]; bool aSet[KB_MAX_RESOURCES];
       for (int r = 0; r < R; r++) aSet[r] = false;
@@ -792,40 +793,59 @@ class Oracle {
     Assignment a;
     int ps0 = s.wl_ps_start[wl], ps1 = s.wl_ps_start[wl + 1];
     bool coversPods = s.pods_resource >= 0 && rgByResource(cq, s.pods_resource) >= 0;
-    for (int row = ps0; row < ps1; row++) {
-      i64 reqs[KB_MAX_RESOURCES]; uint32_t mask = s.ps_req_mask[row];
-      int count = s.ps_count[row];
-      for (int r = 0; r < R; r++) reqs[r] = s.ps_req[(size_t)row * R + r];
-      if (counts) {  // ScaledTo workload.go:258-275
-        int nc = counts[row - ps0];
-        if (count != 0 && count != nc) {
-          for (int r = 0; r < R; r++) if (mask & (1u << r)) reqs[r] = reqs[r] / count * nc;
-          count = nc;
+    int rowEnd;
+    for (int row = ps0; row < ps1; row = rowEnd) {
+      // one unit: a podset, or the adjacent podsets of one PodSetGroup (groupedRequests :613-631)
+      rowEnd = row + 1;
+      if (s.ps_group && s.ps_group[row] >= 0) while (rowEnd < ps1 && s.ps_group[rowEnd] == s.ps_group[row]) rowEnd++;
+      const int nm = rowEnd - row;
+      std::vector<std::array<i64, KB_MAX_RESOURCES>> mreq(nm);
+      std::vector<uint32_t> mmask(nm); std::vector<int> mcount(nm);
+      i64 reqs[KB_MAX_RESOURCES]; uint32_t mask = 0; uint64_t okMask = ~0ull;
+      for (int r = 0; r < R; r++) reqs[r] = 0;
+      for (int m = 0; m < nm; m++) {
+        int mr = row + m;
+        uint32_t mk = s.ps_req_mask[mr];
+        int count = s.ps_count[mr];
+        for (int r = 0; r < R; r++) mreq[m][r] = s.ps_req[(size_t)mr * R + r];
+        if (counts) {  // ScaledTo workload.go:258-275
+          int nc = counts[mr - ps0];
+          if (count != 0 && count != nc) {
+            for (int r = 0; r < R; r++) if (mk & (1u << r)) mreq[m][r] = mreq[m][r] / count * nc;
+            count = nc;
+          }
         }
+        if (coversPods) { mreq[m][s.pods_resource] = count; mk |= 1u << s.pods_resource; }  // :585-587
+        mmask[m] = mk; mcount[m] = count;
+        for (int r = 0; r < R; r++) if (mk & (1u << r)) reqs[r] += mreq[m][r];  // requests.Add :630
+        mask |= mk;
+        okMask &= s.ps_flavor_ok[mr];  // checkFlavorForPodSets walks every podset of the group :915-941
       }
-      if (coversPods) { reqs[s.pods_resource] = count; mask |= 1u << s.pods_resource; }  // :585-587
-      PodSetAssign psa; psa.count = count;
+      PodSetAssign grp;
       bool hasReasons = false, failed = false;
       for (int r = 0; r < R; r++) {  // :639-661
         if (!(mask & (1u << r))) continue;
         if (reqs[r] == 0 && rgByResource(cq, r) < 0) continue;
-        if (psa.flavor[r] >= 0) continue;
-        if (!findFlavorForPodSet(wl, row, p, reqs, mask, r, a.usage, useLast, psa, hasReasons)) { failed = true; break; }
+        if (grp.flavor[r] >= 0) continue;
+        if (!findFlavorForPodSet(wl, row, okMask, p, reqs, mask, r, a.usage, useLast, grp, hasReasons)) { failed = true; break; }
       }
-      if (failed) {
-        for (int r = 0; r < R; r++) { psa.flavor[r] = -1; psa.mode[r] = -1; psa.tried[r] = -1; psa.borrow[r] = 0; }
-        hasReasons = true;
+      if (failed) hasReasons = true;
+      for (int m = 0; m < nm; m++) {  // :664-675
+        PodSetAssign psa; psa.count = mcount[m];
+        if (!failed)
+          for (int r = 0; r < R; r++)  // FilterKeys(groupFlavors, keys(podSet.Requests)) :666
+            if ((mmask[m] & (1u << r)) && grp.flavor[r] >= 0) { psa.flavor[r] = grp.flavor[r]; psa.mode[r] = grp.mode[r]; psa.tried[r] = grp.tried[r]; psa.borrow[r] = grp.borrow[r]; }
+        psa.hasReasons = hasReasons;
+        psa.nFlavors = 0;
+        // Assignment.append :717-738
+        for (int r = 0; r < R; r++) {
+          if (psa.flavor[r] < 0) continue;
+          psa.nFlavors++;
+          if (psa.borrow[r] > a.borrowing) a.borrowing = psa.borrow[r];
+          a.usage.add(psa.flavor[r] * R + r, mreq[m][r]);
+        }
+        a.ps.push_back(psa);
       }
-      psa.hasReasons = hasReasons;
-      psa.nFlavors = 0;
-      // Assignment.append :717-738
-      for (int r = 0; r < R; r++) {
-        if (psa.flavor[r] < 0) continue;
-        psa.nFlavors++;
-        if (psa.borrow[r] > a.borrowing) a.borrowing = psa.borrow[r];
-        a.usage.add(psa.flavor[r] * R + r, reqs[r]);
-      }
-      a.ps.push_back(psa);
       if (failed) return a;  // :677-679
     }
     return a;

@@ -110,6 +110,44 @@ def test_partial_admission_matches_oracle(ev, make):
     assert_cycle_equal(got, want)
 
 
+def _grouped(snap, seed=3):
+    """Random PodSetGroups: in every workload with >= 2 podsets the first two (sometimes three) rows share a group."""
+    rng = np.random.default_rng(seed)
+    st = np.asarray(snap.arrays["wl_ps_start"])
+    grp = np.full(snap.n_podset, -1, np.int32)
+    for w in np.flatnonzero(np.diff(st) >= 2):
+        if rng.random() < 0.7:
+            n = min(int(st[w + 1] - st[w]), 2 + int(rng.random() < 0.3))
+            grp[st[w]:st[w] + n] = 0
+    assert (grp >= 0).any()
+    snap.set("ps_group", grp)
+    return snap.finalize() if hasattr(snap, "finalize") else snap
+
+
+@pytest.mark.parametrize("make", [
+    lambda: synth.make_snapshot(2, W=20000, Q=200, podsets_max=3),                                             # k_nominate
+    lambda: synth.make_snapshot(3, W=3000, Q=300, heads="one_per_cq", podsets_max=3),                          # fused per-root cycle
+    lambda: synth.make_snapshot(2, W=5000, Q=50, preemption=True, tight=1.2, podsets_max=3, seed=9),           # walk with searches
+    lambda: synth.make_snapshot(4, W=4000, Q=200, heads="one_per_cq", tight=1.1, podsets_max=3),
+    lambda: synth.make_snapshot(4, W=2000, Q=100, partial=True, podsets_max=3, tight=1.06),                    # reducer x groups
+    lambda: _fair(synth.make_snapshot(3, W=3000, Q=300, preemption=True, heads="one_per_cq", tight=1.1, podsets_max=3)),
+])
+def test_podset_groups_match_oracle(ev, make):
+    """PodSetGroup units (flavorassigner.go:613-675): grouped podsets get one flavor search over their summed requests."""
+    snap = _grouped(make())
+    cap = 40 * snap.n_adm + 10000
+    got, want = ev.run_cycle(snap, abi.CycleOut(snap, cap)), oracle.run_cycle(snap, cap)
+    plain = oracle.run_cycle(_ungrouped(snap), cap)
+    assert not np.array_equal(plain.ps_flavor, want.ps_flavor) or not np.array_equal(plain.decision, want.decision), "groups must matter in the fixture"
+    assert_cycle_equal(got, want)
+
+
+def _ungrouped(snap):
+    import copy
+    s2 = copy.copy(snap); s2.arrays = dict(snap.arrays); s2.arrays.pop("ps_group", None); s2._struct = None
+    return s2
+
+
 def _fair_golden_cases():
     import json, os
     from tests.test_oracle_golden_preemption2 import fair_flags

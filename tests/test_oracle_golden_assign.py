@@ -41,6 +41,7 @@ def build(tc):
         p = MakePodSet(ps["name"], ps["count"])
         for r, q in ps["requests"].items():
             p.Request(r, q)
+        p.PodSetGroup(ps.get("group"))
         if ps.get("minCount") is not None:
             p.SetMinimumCount(ps["minCount"])
         for t in ps["tolerations"]:

@@ -286,6 +286,7 @@ class Interp:
             if m == "Request": o["requests"][a[0]] = a[1]; return o
             if m == "Limit": o.setdefault("limits", {})[a[0]] = a[1]; return o
             if m == "SetMinimumCount": o["minCount"] = a[0]; return o
+            if m == "PodSetGroup": o["group"] = a[0]; return o
             if m == "Containers":
                 cs = [c for x in a for c in (x if isinstance(x, list) else [x])]
                 o["requests"] = dict(cs[0]["requests"]) if cs else {}

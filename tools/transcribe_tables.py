@@ -199,7 +199,7 @@ def _frq(d):
 
 
 def norm_podset(o):
-    return {"name": o["name"], "count": o["count"], "minCount": o.get("minCount"), "requests": o["requests"],
+    return {"name": o["name"], "count": o["count"], "minCount": o.get("minCount"), "group": o.get("group"), "requests": o["requests"],
             "tolerations": o.get("tolerations") or [], "nodeSelector": o.get("nodeSelector"), "affinityTerms": o.get("affinityTerms")}
 
 
@@ -238,9 +238,6 @@ def assign_cases():
             want_ps.append({"name": ps.get("Name"), "count": ps.get("Count"), "flavors": fl})
         if tas:
             skipped[key] = "TAS"
-            continue
-        if "PodSetGroup(" in lit_text.get(key, ""):
-            skipped[key] = "TAS podset groups"
             continue
         sim = []
         for k, r in (tc.get("simulationResult") or {}).items():
