@@ -129,6 +129,20 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.samples[0][1], "reasons": sorted(self.reasons)}
 
 
+def go_toolchain():
+    """The reference is 100 % Go: with a Go toolchain on the box its own Scheduler.schedule() harness
+    (scheduler_test.go:8139-8209) could serve as the reference arm.  Probe and report; without it the arm is the C++
+    restatement (kind "port")."""
+    import shutil
+    exe = shutil.which("go")
+    if not exe:
+        return None
+    try:
+        return subprocess.run([exe, "version"], capture_output=True, text=True, timeout=10).stdout.strip() or exe
+    except Exception:  # noqa: BLE001
+        return exe
+
+
 def cpu_baseline(snap, budget_s: float = 12.0):
     """Oracle (kind 'port') on one host core over repeated passes of the same snapshot."""
     import oracle
@@ -142,7 +156,8 @@ def cpu_baseline(snap, budget_s: float = 12.0):
             break
     return {"value": n * snap.n_heads / dt, "unit": UNIT, "cores": 1, "kind": "port",
             "sample": f"{n} full passes of the same snapshot ({snap.n_heads} decisions each) in {dt:.1f} s, 1 thread "
-                      f"(the reference cycle is single-goroutine, scheduler.go:468)"}
+                      f"(the reference cycle is single-goroutine, scheduler.go:468)",
+            "go_toolchain_on_box": go_toolchain()}
 
 
 def pin_to_gpu_numa(local_rank: int):
@@ -329,7 +344,8 @@ def run_reference(args, rank, world):
                        "sample": "every step is one full pass of the N=1 snapshot on rank 0's host cores"},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "kind": "port",
                              "sample": f"{args.steps} full passes ({snap.n_heads} decisions each); C++ restatement of "
-                                       "pkg/scheduler (Go toolchain absent), 1 thread like the reference's cycle"},
+                                       "pkg/scheduler, 1 thread like the reference's cycle",
+                             "go_toolchain_on_box": go_toolchain()},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
@@ -429,34 +445,67 @@ def main():
     # steady state of the controller: ClusterQueue / Cohort specs do not change between cycles, so the shim keeps
     # static_generation constant and only usage + entries + admitted workloads cross PCIe every cycle.
     snap.static_generation = 1
-    def gather_and_merge():
-        """N > 1: the shards' decisions travel to every rank (one NCCL all-gather of H bytes per rank, padded to the
-        largest shard) and rank 0 scatters them to their global entry positions (shard.merge for the decision table)."""
-        if world == 1:
-            return None
-        mine = torch.zeros(hmax, dtype=torch.uint8, device="cuda")
-        mine[:snap.n_heads] = torch.from_numpy(out.decision).cuda()
-        allv = torch.empty(world * hmax, dtype=torch.uint8, device="cuda")
-        dist.all_gather_into_tensor(allv, mine)
-        if rank != 0:
-            return None
-        host = allv.cpu().numpy()
-        full = np.zeros(glob_heads, np.uint8)
-        for r in range(world):
-            full[all_maps[r]] = host[r * hmax:r * hmax + len(all_maps[r])]
-        return full
+    # N > 1: the shards' decisions travel to every rank (one NCCL all-gather of H bytes per rank, padded to the largest
+    # shard) and rank 0 scatters them to their global entry positions (shard.merge for the decision table).  Root
+    # cohorts never interact, so a rank's next cycle does not wait for the merge: a write-back thread gathers and merges
+    # the decisions of cycle k while cycle k+1 runs (the timed region ends when the last merge is done).
+    merged = {"n": 0, "full": None}
     if world > 1:
+        import queue
         sizes = [None] * world
         dist.all_gather_object(sizes, my_heads)
         all_maps = sizes
         hmax = max(len(m) for m in all_maps)
-    for _ in range(2):
-        ev.run_cycle(snap, out); gather_and_merge()
+        contiguous = all(len(m) == hmax and m[0] == r * hmax and m[-1] == (r + 1) * hmax - 1 for r, m in enumerate(all_maps))
+        side = torch.cuda.Stream()
+        mine_host = torch.zeros(hmax, dtype=torch.uint8).pin_memory()
+        mine_dev = torch.zeros(hmax, dtype=torch.uint8, device="cuda")
+        all_dev = torch.empty(world * hmax, dtype=torch.uint8, device="cuda")
+        all_host = torch.empty(world * hmax, dtype=torch.uint8).pin_memory()
+        full = np.zeros(glob_heads, np.uint8)
+        q = queue.Queue()
+
+        def writer():
+            torch.cuda.set_device(local_rank)
+            while True:
+                dec = q.get()
+                if dec is None:
+                    return
+                with torch.cuda.stream(side):
+                    mine_host[:len(dec)] = torch.from_numpy(dec)
+                    mine_dev.copy_(mine_host, non_blocking=True)
+                    dist.all_gather_into_tensor(all_dev, mine_dev)
+                    if rank == 0:
+                        all_host.copy_(all_dev, non_blocking=True)
+                side.synchronize()
+                if rank == 0:
+                    host = all_host.numpy()
+                    if contiguous:
+                        full[:] = host
+                    else:
+                        for r in range(world):
+                            full[all_maps[r]] = host[r * hmax:r * hmax + len(all_maps[r])]
+                    merged["full"] = full
+                merged["n"] += 1
+                q.task_done()
+
+    def e2e_steps(n):
+        if world == 1:
+            for _ in range(n):
+                ev.run_cycle(snap, out)
+            return
+        th = threading.Thread(target=writer, daemon=True)
+        th.start()
+        for _ in range(n):
+            ev.run_cycle(snap, out)
+            q.put(np.array(out.decision, copy=True))
+        q.put(None)
+        th.join()
+
+    e2e_steps(2)
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        ev.run_cycle(snap, out)
-        gather_and_merge()
+    e2e_steps(args.steps)
     barrier()
     e2e_s = time.perf_counter() - t0
     st = ev.stats()
@@ -504,7 +553,7 @@ def main():
                                             "usage + entries + admitted workloads copied every step",
                        "multi_gpu": None if world == 1 else {"partition": ("the configuration's root cohorts split over the ranks (kueue_b200.shard)" if scaling == "strong" else
                                                                            "one independent copy of the configuration (its own root cohorts) per rank") + ", no data-path collective",
-                                                             "e2e_includes": "NCCL all-gather of the shards' decisions + merge on rank 0",
+                                                             "e2e_includes": "NCCL all-gather of the shards' decisions + merge on rank 0, pipelined one cycle behind by a write-back thread (shards never interact)",
                                                              "host_affinity": numa}},
             "clocks": clocks,
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},

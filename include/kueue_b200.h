@@ -279,6 +279,12 @@ void    kb_destroy(kb_handle *h);
 const char *kb_last_error(const kb_handle *h);
 int32_t kb_alloc_pinned(void **ptr, uint64_t bytes);
 int32_t kb_free_pinned(void *ptr);
+/* Output buffers of kb_run_cycle / kb_download in ONE page-locked block laid out like the library's device-side
+ * result tables: the eight per-entry / per-podset tables then come back with a single DMA (separately allocated
+ * buffers work too, one copy per table).  n_node_cells = (n_cq + n_cohort) * F * R to receive node_usage, 0 to leave
+ * it NULL.  Fills every pointer of *out and tgt_capacity; release with kb_free_pinned(out->decision).
+ * Replaces the per-cycle result maps of the reference's loop (entry.assignment / preemptionTargets, scheduler.go:255-401). */
+int32_t kb_alloc_cycle_out(int32_t n_heads, int32_t n_podset, int32_t n_resource, int32_t tgt_capacity, int64_t n_node_cells, kb_cycle_out *out);
 int32_t kb_version(void);
 
 /* K1: rebuild the resource-node tree on the device and return the derived

@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <chrono>
 #include <vector>
 #include <map>
 #include <mutex>
@@ -48,6 +49,9 @@ struct kb_handle {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr, ev4 = nullptr, ev5 = nullptr;
   Arena arena;   // per-cycle scratch, outputs
   Arena iarena;  // per-cycle input tables (copied before the host-side checks finish)
+  char *d_out_block = nullptr;  // result tables of the cycle in the canonical layout
+  int32_t *d_tgt_start = nullptr, *d_tgt_adm = nullptr; uint8_t *d_tgt_reason = nullptr;  // preemption targets, CSR by entry
+  bool tgt_csr = false;
   Arena sarena;  // static tables (quotas, policies, topology): kept while kb_snapshot.static_generation is unchanged
   int64_t static_gen = 0;
   int s_dims[6] = {-1, -1, -1, -1, -1, -1};
@@ -122,6 +126,42 @@ static bool inside_one_pinned_block(uintptr_t lo, uintptr_t hi) {
   return lo >= it->first && hi <= it->first + it->second;
 }
 
+// Canonical layout of the eight per-entry / per-podset output tables: the device block of every cycle and the host
+// block of kb_alloc_cycle_out use the same offsets, so those results come back with ONE device-to-host DMA.
+struct OutLayout { size_t off[8]; size_t prefix; };
+static OutLayout out_layout(size_t H, size_t P, size_t R) {
+  const size_t sz[8] = {H, H, 4 * H, 4 * H, P * R, P * R, P * R, 4 * P};  // decision mode borrow rank flavor res_mode tried count
+  OutLayout L; size_t o = 0;
+  for (int i = 0; i < 8; i++) { L.off[i] = o; o += pad256(sz[i]); }
+  L.prefix = o;
+  return L;
+}
+struct OutBlock { size_t H, P, R; };
+static std::map<uintptr_t, OutBlock> g_out_blocks;  // base of a kb_alloc_cycle_out block -> its dimensions
+
+int32_t kb_alloc_cycle_out(int32_t n_heads, int32_t n_podset, int32_t n_resource, int32_t tgt_capacity, int64_t n_node_cells, kb_cycle_out *out) {
+  if (!out || n_heads < 0 || n_podset < 0 || n_resource < 0 || tgt_capacity < 0 || n_node_cells < 0) return KB_ERR_INVALID;
+  const size_t H = (size_t)n_heads, P = (size_t)n_podset, R = (size_t)n_resource, cap = (size_t)tgt_capacity;
+  OutLayout L = out_layout(H, P, R);
+  size_t o_ts = L.prefix, o_ta = o_ts + pad256(4 * (H + 1)), o_tr = o_ta + pad256(4 * cap), o_nu = o_tr + pad256(cap);
+  size_t total = o_nu + pad256(8 * (size_t)n_node_cells);
+  void *base = nullptr;
+  int32_t rc = kb_alloc_pinned(&base, total);
+  if (rc != KB_OK) return rc;
+  memset(base, 0, total);
+  char *b = (char *)base;
+  out->decision = (uint8_t *)(b + L.off[0]); out->mode = (uint8_t *)(b + L.off[1]);
+  out->borrow = (int32_t *)(b + L.off[2]); out->commit_rank = (int32_t *)(b + L.off[3]);
+  out->ps_flavor = (int8_t *)(b + L.off[4]); out->ps_res_mode = (int8_t *)(b + L.off[5]); out->ps_tried_idx = (int8_t *)(b + L.off[6]);
+  out->ps_count = (int32_t *)(b + L.off[7]);
+  out->tgt_start = (int32_t *)(b + o_ts); out->tgt_adm = (int32_t *)(b + o_ta); out->tgt_reason = (uint8_t *)(b + o_tr);
+  out->tgt_capacity = tgt_capacity; out->n_targets = 0;
+  out->node_usage = n_node_cells ? (int64_t *)(b + o_nu) : nullptr;
+  std::lock_guard<std::mutex> lk(g_pin_mu);
+  g_out_blocks[(uintptr_t)base] = OutBlock{H, P, R};
+  return KB_OK;
+}
+
 int32_t kb_alloc_pinned(void **ptr, uint64_t bytes) {
   if (!ptr) return KB_ERR_INVALID;
   cudaError_t e = cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocDefault);
@@ -132,7 +172,7 @@ int32_t kb_alloc_pinned(void **ptr, uint64_t bytes) {
 }
 int32_t kb_free_pinned(void *ptr) {
   if (!ptr) return KB_OK;
-  { std::lock_guard<std::mutex> lk(g_pin_mu); g_pinned.erase((uintptr_t)ptr); }
+  { std::lock_guard<std::mutex> lk(g_pin_mu); g_pinned.erase((uintptr_t)ptr); g_out_blocks.erase((uintptr_t)ptr); }
   return cudaFreeHost(ptr) == cudaSuccess ? KB_OK : KB_ERR_CUDA;
 }
 
@@ -646,6 +686,7 @@ static int32_t upload_impl(kb_handle *h, const kb_snapshot *s, bool sync) {
   size_t G = (fair && A) ? (size_t)h->search_grid : 1, acap = (fair && A) ? (size_t)h->max_root_adm : 1, ncap = (size_t)h->max_tree_nodes;
   size_t pool_cap = A * 4 + 1024;
   need(A, 4); need(nroots + 1, 4); need(H, 4); need(2, 4); need(H, 4); need(H, 4); need(pool_cap, 4); need(pool_cap, 1); need(1, 4);
+  need(H + 1, 4); need(pool_cap, 4); need(pool_cap, 1);  // preemption targets in CSR order (download)
   need(A, 1); need(A, 4); need(nroots, 4); need(A ? NF : 1, 8);
   need(G * acap, 4); need(G * acap, 4); need(G * acap, 4); need(G * acap, 4); need(G * ncap, 4); need(G * acap, 1); need(G * acap, 1); need(G * ncap, 1); need(G * ncap, 1); need(G * ncap, 1); need(G * ncap, 8); need(G * ncap, 1);
   if (fair && A && !h->search_smem) need(G * ncap * FR, 8);
@@ -692,10 +733,15 @@ static int32_t upload_impl(kb_handle *h, const kb_snapshot *s, bool sync) {
   D.root_cursor = h->arena.take<int32_t>(nroots); D.root_entries = h->arena.take<int32_t>(H);
   D.sorted = h->arena.take<int32_t>(H); D.pos_slot = h->arena.take<int32_t>(H); D.ekey = h->arena.take<u64>(H * 4); D.skey = h->arena.take<u64>(H * 4);
   D.fs_over = h->arena.take<i64>((size_t)Q * R); D.fs_lend = h->arena.take<i64>((size_t)N * R);
-  D.decision = h->arena.take<uint8_t>(H); D.mode = h->arena.take<uint8_t>(H);
-  D.borrow = h->arena.take<int32_t>(H); D.rank = h->arena.take<int32_t>(H);
-  D.ps_flavor = h->arena.take<int8_t>(P * R); D.ps_res_mode = h->arena.take<int8_t>(P * R); D.ps_tried = h->arena.take<int8_t>(P * R);
-  D.ps_count_out = h->arena.take<int32_t>(P);
+  {  // the result tables in the canonical layout (out_layout)
+    OutLayout L = out_layout(H, P, (size_t)R);
+    char *ob = h->arena.take<char>(L.prefix);
+    h->d_out_block = ob;
+    D.decision = (uint8_t *)(ob + L.off[0]); D.mode = (uint8_t *)(ob + L.off[1]);
+    D.borrow = (int32_t *)(ob + L.off[2]); D.rank = (int32_t *)(ob + L.off[3]);
+    D.ps_flavor = (int8_t *)(ob + L.off[4]); D.ps_res_mode = (int8_t *)(ob + L.off[5]); D.ps_tried = (int8_t *)(ob + L.off[6]);
+    D.ps_count_out = (int32_t *)(ob + L.off[7]);
+  }
   {  // cycle header block, cleared by one memset per cycle: [0] status, [2..3] ps_n / ps_cursor, [4] target pool cursor, [8..23] search counters
     uint32_t *hdr = h->arena.take<uint32_t>(32);
     D.status = hdr; D.ps_n = (int32_t *)(hdr + 2); D.ps_cursor = D.ps_n + 1; D.tgt_pool_used = (int32_t *)(hdr + 4); D.sstat = (u64 *)(hdr + 8);
@@ -704,6 +750,7 @@ static int32_t upload_impl(kb_handle *h, const kb_snapshot *s, bool sync) {
   D.tgt_off = h->arena.take<int32_t>(H); D.tgt_cnt = h->arena.take<int32_t>(H);
   D.tgt_pool_adm = h->arena.take<int32_t>(pool_cap); D.tgt_pool_reason = h->arena.take<uint8_t>(pool_cap);
   D.tgt_pool_cap = (int)pool_cap;
+  h->d_tgt_start = h->arena.take<int32_t>(H + 1); h->d_tgt_adm = h->arena.take<int32_t>(pool_cap); h->d_tgt_reason = h->arena.take<uint8_t>(pool_cap);
   D.preempted = h->arena.take<uint8_t>(A);
   D.usage_shadow = h->arena.take<i64>(A ? NF : 1);
   D.sc_cand = h->arena.take<int32_t>(G * acap); D.sc_tgt = h->arena.take<int32_t>(G * acap); D.sc_cq_lca = h->arena.take<int32_t>(G * ncap);
@@ -732,9 +779,7 @@ static int32_t upload_impl(kb_handle *h, const kb_snapshot *s, bool sync) {
   h->d_drs_rounded = h->arena.take<i64>(N); h->d_drs_res = h->arena.take<int32_t>(N); h->d_drs_borrowing = h->arena.take<uint8_t>(N);
   if (h->arena.used > h->arena.cap) { cudaStreamSynchronize(h->stream); return fail(h, KB_ERR_CUDA, "device arena accounting"); }
   // rows of workloads that are not heads stay at -1
-  CUDA_TRY(h, cudaMemsetAsync(D.ps_flavor, 0xff, P * R, h->stream));
-  CUDA_TRY(h, cudaMemsetAsync(D.ps_res_mode, 0xff, P * R, h->stream));
-  CUDA_TRY(h, cudaMemsetAsync(D.ps_tried, 0xff, P * R, h->stream));
+  CUDA_TRY(h, cudaMemsetAsync(D.ps_flavor, 0xff, 3 * pad256(P * R), h->stream));  // flavor, res_mode, tried are adjacent (out_layout)
   CUDA_TRY(h, cudaMemsetAsync(D.ps_count_out, 0, P * 4, h->stream));
   h->stats.h2d_bytes = bytes;
   h->uploaded = true;
@@ -763,10 +808,13 @@ static int32_t launch_tree(kb_handle *h, int *launches) {
 
 // admit kernel launches: lone-CQ roots (slots [0, nLone)) and cohort-tree roots
 // (slots [nLone, nRoots)) separately so each class gets the shared memory it needs.
-static size_t admit_smem(int nn_tables, int FR, int sort_cap) {
+static size_t admit_smem(int nn_tables, int FR, int sort_cap, int nn_stage = 0) {
   size_t tb = (size_t)nn_tables * FR * 32;
   size_t mid = (size_t)KB_TILE * FR * 8; (void)sort_cap;
-  size_t staging = nn_tables == 0 ? (size_t)KB_TILE * 4 * (KB_PF + 2) + 32 + (size_t)KB_TG_CAP * sizeof(TgCell) : (size_t)KB_TILE * 4 * (KB_PF + 2) + 32;
+  // global-table mode: staging buffers of the commit pipeline (k_admit: cells, path table, target ids, scratch)
+  size_t staging = nn_stage ? sizeof(TgCell) * 2 * KB_SUB * KB_ECAP + 4 * (size_t)nn_stage * KB_PF + 4 * 2 * KB_SUB * KB_TCAP +
+                                  4 * KB_SUB * (KB_TCAP + 1) + 4 * KB_SUB * 32 + 2 * 2 * KB_SUB * 34 + (size_t)nn_stage + 2 * KB_SUB + 64
+                            : 0;
   return tb + mid + 16 + (size_t)nn_tables * 4 + KB_TILE * 28 + (KB_MAX_DEPTH + 2) * 4 + 64 + staging;
 }
 static int32_t launch_admit(kb_handle *h, int *launches) {
@@ -787,7 +835,7 @@ static int32_t launch_admit(kb_handle *h, int *launches) {
     int cap = pick_cap(1);
     size_t sm = admit_smem(1, D.FR, cap);
     CUDA_TRY(h, cudaFuncSetAttribute(k_admit<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
-    k_admit<true><<<D.nLone, KB_ADMIT_THREADS, sm, h->stream>>>(D, 0, cap); (*launches)++;
+    k_admit<true><<<D.nLone, KB_ADMIT_THREADS, sm, h->stream>>>(D, 0, cap, 0); (*launches)++;
   }
   bool fair_trees = D.nTrees && (D.flags & KB_F_FAIR_SHARING);
   bool any_deep = false;
@@ -813,12 +861,14 @@ static int32_t launch_admit(kb_handle *h, int *launches) {
       int cap = pick_cap(h->max_tree_nodes);
       size_t sm = admit_smem(h->max_tree_nodes, D.FR, cap);
       CUDA_TRY(h, cudaFuncSetAttribute(k_admit<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
-      k_admit<true><<<D.nTrees, KB_ADMIT_THREADS, sm, h->stream>>>(D, D.nLone, cap); (*launches)++;
+      k_admit<true><<<D.nTrees, KB_ADMIT_THREADS, sm, h->stream>>>(D, D.nLone, cap, 0); (*launches)++;
     } else {
       int cap = pick_cap(0);
-      size_t sm = admit_smem(0, D.FR, cap);
+      size_t sm = admit_smem(0, D.FR, cap, h->max_tree_nodes);
+      int staged = sm <= kMaxSmem;
+      if (!staged) sm = admit_smem(0, D.FR, cap);
       CUDA_TRY(h, cudaFuncSetAttribute(k_admit<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
-      k_admit<false><<<D.nTrees, KB_ADMIT_THREADS, sm, h->stream>>>(D, D.nLone, cap); (*launches)++;
+      k_admit<false><<<D.nTrees, KB_ADMIT_THREADS, sm, h->stream>>>(D, D.nLone, cap, staged); (*launches)++;
     }
   }
   return KB_OK;
@@ -972,6 +1022,14 @@ extern "C" int32_t kb_cycle_resident(kb_handle *h) {
   return cycle_finish(h);
 }
 
+// preemption targets of the cycle from the per-entry pool slices into CSR order (kb_cycle_out.tgt_start / tgt_adm / tgt_reason)
+__global__ void k_tgt_compact(DevSnap D, const int32_t *start, int32_t *adm, uint8_t *reason) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= D.H) return;
+  int n = D.tgt_cnt[e], o = D.tgt_off[e], s = start[e];
+  for (int k = 0; k < n; k++) { adm[s + k] = D.tgt_pool_adm[o + k]; reason[s + k] = D.tgt_pool_reason[o + k]; }
+}
+
 static int32_t download_enqueue(kb_handle *h, kb_cycle_out *out) {
   if (!h || !h->uploaded || !out) return fail(h, KB_ERR_INVALID, "nothing to download");
   cudaSetDevice(h->device);
@@ -980,11 +1038,35 @@ static int32_t download_enqueue(kb_handle *h, kb_cycle_out *out) {
   int64_t bytes = 0;
   CUDA_TRY(h, cudaEventRecord(h->ev4, h->stream));
 #define DOWN(dst, src, n, T) if (out->dst && (n)) { CUDA_TRY(h, cudaMemcpyAsync(out->dst, D.src, (n) * sizeof(T), cudaMemcpyDeviceToHost, h->stream)); bytes += (n) * sizeof(T); }
-  DOWN(decision, decision, H, uint8_t); DOWN(mode, mode, H, uint8_t); DOWN(borrow, borrow, H, int32_t); DOWN(commit_rank, rank, H, int32_t);
-  DOWN(ps_flavor, ps_flavor, PR, int8_t); DOWN(ps_res_mode, ps_res_mode, PR, int8_t); DOWN(ps_tried_idx, ps_tried, PR, int8_t);
-  DOWN(ps_count, ps_count_out, (size_t)D.P, int32_t);
+  bool one_dma = false;
+  if (out->decision && H) {  // a kb_alloc_cycle_out block of these dimensions, pointers untouched
+    OutLayout L = out_layout(H, (size_t)D.P, (size_t)D.R);
+    char *b = (char *)out->decision;
+    {
+      std::lock_guard<std::mutex> lk(g_pin_mu);
+      auto it = g_out_blocks.find((uintptr_t)b);
+      one_dma = it != g_out_blocks.end() && it->second.H == H && it->second.P == (size_t)D.P && it->second.R == (size_t)D.R;
+    }
+    one_dma = one_dma && (char *)out->mode == b + L.off[1] && (char *)out->borrow == b + L.off[2] && (char *)out->commit_rank == b + L.off[3] &&
+              (char *)out->ps_flavor == b + L.off[4] && (char *)out->ps_res_mode == b + L.off[5] && (char *)out->ps_tried_idx == b + L.off[6] &&
+              (char *)out->ps_count == b + L.off[7];
+    if (one_dma) { CUDA_TRY(h, cudaMemcpyAsync(b, h->d_out_block, L.prefix, cudaMemcpyDeviceToHost, h->stream)); bytes += (int64_t)L.prefix; }
+  }
+  if (!one_dma) {
+    DOWN(decision, decision, H, uint8_t); DOWN(mode, mode, H, uint8_t); DOWN(borrow, borrow, H, int32_t); DOWN(commit_rank, rank, H, int32_t);
+    DOWN(ps_flavor, ps_flavor, PR, int8_t); DOWN(ps_res_mode, ps_res_mode, PR, int8_t); DOWN(ps_tried_idx, ps_tried, PR, int8_t);
+    DOWN(ps_count, ps_count_out, (size_t)D.P, int32_t);
+  }
   DOWN(node_usage, usage, (size_t)D.N * D.FR, i64);
 #undef DOWN
+  h->tgt_csr = false;
+  if (out->tgt_start && D.A && H) {  // target lists -> CSR on the device: scan of the per-entry counts, one gather
+    k_scan_i32<<<1, 1024, 0, h->stream>>>(D.tgt_cnt, h->d_tgt_start, (int)H);
+    k_tgt_compact<<<(unsigned)((H + 127) / 128), 128, 0, h->stream>>>(D, h->d_tgt_start, h->d_tgt_adm, h->d_tgt_reason);
+    CUDA_TRY(h, cudaMemcpyAsync(out->tgt_start, h->d_tgt_start, (H + 1) * 4, cudaMemcpyDeviceToHost, h->stream));
+    bytes += (int64_t)(H + 1) * 4;
+    h->tgt_csr = true;
+  }
   CUDA_TRY(h, cudaEventRecord(h->ev5, h->stream));
   h->last_d2h_bytes = bytes;
   return KB_OK;
@@ -997,25 +1079,17 @@ static int32_t download_finish(kb_handle *h, kb_cycle_out *out) {
   int64_t bytes = h->last_d2h_bytes;
   out->n_targets = 0;
   if (out->tgt_start) {
-    memset(out->tgt_start, 0, sizeof(int32_t) * (H + 1));
-    int32_t used = (D.A && H) ? (int32_t)h->host_words[1] : 0;
-    if (used > 0) {  // gather the per-entry target lists into CSR order
-      std::vector<int32_t> off(H), cnt(H), padm(used);
-      std::vector<uint8_t> preason(used);
-      CUDA_TRY(h, cudaMemcpy(off.data(), D.tgt_off, H * 4, cudaMemcpyDeviceToHost));
-      CUDA_TRY(h, cudaMemcpy(cnt.data(), D.tgt_cnt, H * 4, cudaMemcpyDeviceToHost));
-      CUDA_TRY(h, cudaMemcpy(padm.data(), D.tgt_pool_adm, (size_t)used * 4, cudaMemcpyDeviceToHost));
-      CUDA_TRY(h, cudaMemcpy(preason.data(), D.tgt_pool_reason, (size_t)used, cudaMemcpyDeviceToHost));
-      bytes += (int64_t)H * 8 + (int64_t)used * 5;
-      int32_t nt = 0;
-      for (size_t e = 0; e < H; e++) {
-        out->tgt_start[e] = nt;
-        for (int k = 0; k < cnt[e]; k++, nt++)
-          if (nt < out->tgt_capacity && out->tgt_adm && out->tgt_reason) { out->tgt_adm[nt] = padm[off[e] + k]; out->tgt_reason[nt] = preason[off[e] + k]; }
-      }
-      out->tgt_start[H] = nt;
+    if (!h->tgt_csr) memset(out->tgt_start, 0, sizeof(int32_t) * (H + 1));
+    else {
+      int32_t nt = out->tgt_start[H];
       out->n_targets = nt;
       if (nt > out->tgt_capacity) return fail(h, KB_ERR_CAPACITY, "target buffer too small");
+      if (nt > 0 && out->tgt_adm && out->tgt_reason) {
+        CUDA_TRY(h, cudaMemcpyAsync(out->tgt_adm, h->d_tgt_adm, (size_t)nt * 4, cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(h, cudaMemcpyAsync(out->tgt_reason, h->d_tgt_reason, (size_t)nt, cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+        bytes += (int64_t)nt * 5;
+      }
     }
   }
   float ms = 0; cudaEventElapsedTime(&ms, h->ev4, h->ev5);
@@ -1034,13 +1108,20 @@ extern "C" int32_t kb_download(kb_handle *h, kb_cycle_out *out) {
 
 // One blocking call, one stream synchronisation: H2D copies, kernels and D2H copies are all enqueued first.
 extern "C" int32_t kb_run_cycle(kb_handle *h, const kb_snapshot *s, kb_cycle_out *out) {
+  static const bool trace = getenv("KB_TRACE") != nullptr;  // host-side phase times of the call on stderr
+  auto now = [] { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  double t0 = trace ? now() : 0, t1 = 0, t2 = 0, t3 = 0;
   int32_t rc = upload_impl(h, s, false);
   if (rc != KB_OK) return rc;
+  if (trace) t1 = now();
   rc = cycle_enqueue(h);
   if (rc != KB_OK) return rc;
+  if (trace) t2 = now();
   rc = download_enqueue(h, out);
   if (rc != KB_OK) return rc;
+  if (trace) t3 = now();
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  if (trace) fprintf(stderr, "kb_run_cycle host us: upload %.1f enqueue %.1f download-enqueue %.1f wait %.1f\n", t1 - t0, t2 - t1, t3 - t2, now() - t3);
   { float ms = 0; cudaEventElapsedTime(&ms, h->ev0, h->ev1); h->stats.last_h2d_ms = ms; }
   rc = cycle_finish(h);
   if (rc != KB_OK) return rc;

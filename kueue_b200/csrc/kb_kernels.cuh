@@ -1559,21 +1559,33 @@ __device__ inline void publish_usage(const DevSnap &D, const Tab<kSmem> &T, cons
 // aggregated Assignment.Usage.Quota (absent cell = -1).  s_path: KB_MAX_DEPTH+2 ints.
 // cq = global id of the entry's ClusterQueue, ntg/toff = its preemption targets in the pool.
 // T.shadow_on points at a shared-memory flag (0 at kernel start).
-// Global-table mode: the CTA stages, per tile, everything of an entry that does not depend on earlier commits — its
-// path and the usage cells of its preemption targets (TgCell: quantity, column, the target ClusterQueue's path) — so
-// the commit warp only waits for the usage / shadow values themselves.
-struct TgCell { i64 qty; int32_t path[KB_PF]; int32_t adm; int16_t fr; int8_t plen; int8_t pad; };
-#define KB_TG_CAP 2048  // staged target cells per tile
+// Global-table mode (trees too large for shared memory): while warp 0 commits one group of KB_SUB entries, the other
+// warps stage everything of the NEXT group that does not depend on earlier commits — per entry the ids of its
+// preemption targets and their usage cells (quantity, column, ClusterQueue), counting-sorted by column.  Columns are
+// independent, so in the commit every lane walks the cells of ITS columns in target order and the lanes' walks
+// overlap: the commit warp only ever waits for the usage / shadow values themselves.
+struct TgCell { i64 qty; int32_t lh; int16_t fr; int16_t pad; };  // lh: local handle of the target's ClusterQueue
+#define KB_SUB 7        // entries per group = staging warps (KB_ADMIT_THREADS / 32 - 1)
+#define KB_ECAP 256     // staged cells per entry
+#define KB_TCAP 256     // staged targets per entry
+struct StagedEntry {
+  const TgCell *cells;        // [ncell] sorted by column (fr & 31), target order inside a column
+  const uint16_t *col_start;  // [33]
+  const int32_t *adm;         // [ntg] target ids
+  const int32_t *cq_path;     // [nn][KB_PF] paths of the root's ClusterQueues by local handle (shared memory)
+  const int8_t *cq_plen;      // [nn]
+};
 template <bool kSmem>
 __device__ inline void commit_entry(const DevSnap &D, const Tab<kSmem> &T, int *s_path, int lane, int e, int nd, int mode,
                                     int borrowing, const i64 *qrow, int rank, int cq, int ntg, int toff,
-                                    const int *st_path = nullptr, int st_plen = 0, const TgCell *cells = nullptr, int ncell = 0) {
+                                    const StagedEntry *st = nullptr) {
   const int FR = D.FR;
   if (lane == 0) D.rank[e] = rank;
   if (mode == KB_MODE_NOFIT) { if (lane == 0) D.decision[e] = KB_DEC_NOFIT; return; }
-  if (st_path) {  // staged by the tile preparation
-    if (lane < st_plen) s_path[lane] = st_path[lane];
-    if (lane == 0) s_path[KB_MAX_DEPTH + 1] = st_plen;
+  if (st) {  // path table of the root in shared memory
+    const int lh = D.local_idx[nd], pl = st->cq_plen[lh];
+    if (lane < pl) s_path[lane] = st->cq_path[lh * KB_PF + lane];
+    if (lane == 0) s_path[KB_MAX_DEPTH + 1] = pl;
   } else if constexpr (!kSmem) {  // static path table: one coalesced row instead of a chain of dependent parent loads
     int pl = D.cq_plen[nd];
     if (lane < pl) s_path[lane] = D.cq_path[(size_t)nd * D.path_stride + lane];
@@ -1605,7 +1617,7 @@ __device__ inline void commit_entry(const DevSnap &D, const Tab<kSmem> &T, int *
   // workload preempted so far in this root and without the new targets (:503-511) = the shadow table
   if (ntg > 0) {
     bool overlap = false;
-    if (cells) { for (int k = lane; k < ncell; k += 32) if (D.preempted[cells[k].adm]) overlap = true; }
+    if (st) { for (int k = lane; k < ntg; k += 32) if (D.preempted[st->adm[k]]) overlap = true; }
     else for (int k = lane; k < ntg; k += 32) if (D.preempted[D.tgt_pool_adm[toff + k]]) overlap = true;
     if (__any_sync(0xffffffffu, overlap)) { if (lane == 0) D.decision[e] = KB_DEC_SKIPPED_OVERLAP; __syncwarp(); return; }
     if (!shadow) {  // first targets of this root: the shadow starts as a copy of the current usage
@@ -1624,26 +1636,20 @@ __device__ inline void commit_entry(const DevSnap &D, const Tab<kSmem> &T, int *
     }
     __syncwarp();
   };
-  // staged cells: columns are independent, so every lane walks the cells of ITS columns (in target order) and the
-  // lanes' walks overlap — one memory round trip per "layer" of cells instead of one per cell
-  unsigned long long mine = 0;
-  if (cells) for (int k = 0; k < ncell; k++) if ((cells[k].fr & 31) == lane) mine |= 1ull << k;
-  auto apply_cells = [&](bool remove) {
+  auto apply_cells = [&](bool remove) {  // staged cells: lane l walks the cells of columns l, l+32, ... in target order
     if constexpr (!kSmem) {
-      unsigned long long m = mine;
-      while (__any_sync(0xffffffffu, m != 0)) {
-        if (m) {
-          int k = __ffsll((long long)m) - 1;
-          m &= m - 1;
-          const TgCell &c = cells[k];
-          if (remove) T.template remove<true>(c.path, c.plen, c.fr, c.qty);
-          else T.template add<true>(c.path, c.plen, c.fr, c.qty);
-        }
+      const int j1 = st->col_start[lane + 1];
+      for (int j = st->col_start[lane]; j < j1; j++) {
+        const TgCell c = st->cells[j];
+        const int32_t *cp = st->cq_path + c.lh * KB_PF;
+        const int pl = st->cq_plen[c.lh];
+        if (remove) T.template remove<true>(cp, pl, c.fr, c.qty);
+        else T.template add<true>(cp, pl, c.fr, c.qty);
       }
       __syncwarp();
     }
   };
-  if (cells) apply_cells(true);
+  if (st) apply_cells(true);
   else for (int k = 0; k < ntg; k++) apply(D.tgt_pool_adm[toff + k], true);  // SimulateWorkloadRemoval snapshot.go:67-84
   bool ok = true;  // fits :503-511
   bool fused = false;
@@ -1663,7 +1669,7 @@ __device__ inline void commit_entry(const DevSnap &D, const Tab<kSmem> &T, int *
       }
       ok = __all_sync(0xffffffffu, ok);
       if (ok) {
-        if (cells) { for (int k = lane; k < ncell; k += 32) D.preempted[cells[k].adm] = 1; }
+        if (st) { for (int k = lane; k < ntg; k += 32) D.preempted[st->adm[k]] = 1; }
         else for (int k = lane; k < ntg; k += 32) D.preempted[D.tgt_pool_adm[toff + k]] = 1;  // preemptedWorkloads.Insert :335
         if (q > 0) {  // cq.AddUsage :336
           T.template add_from<false>(s_path, plen, fr, um, sb, ll, q);
@@ -1687,7 +1693,7 @@ __device__ inline void commit_entry(const DevSnap &D, const Tab<kSmem> &T, int *
     }
   }
   if (!ok) {
-    if (cells) apply_cells(false);
+    if (st) apply_cells(false);
     else for (int k = 0; k < ntg; k++) apply(D.tgt_pool_adm[toff + k], false);
   }
   if (lane == 0) D.decision[e] = ok ? (mode == KB_MODE_PREEMPT ? KB_DEC_PREEMPTING : KB_DEC_ASSUMED) : KB_DEC_SKIPPED_NO_FIT;
@@ -1817,9 +1823,12 @@ __device__ inline void expand_entry(const DevSnap &D, int e, i64 *qrow) {
 }
 
 template <bool kSmemTables>
-__global__ void __launch_bounds__(KB_ADMIT_THREADS) k_admit(DevSnap D, int slot_base, int sort_cap) {
+__global__ void __launch_bounds__(KB_ADMIT_THREADS) k_admit(DevSnap D, int slot_base, int sort_cap, int stage_buffers) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int FR = D.FR;
+#ifdef KB_ADMIT_PROBE
+  const long long kp0 = clock64();
+#endif
   int slot = slot_base + blockIdx.x;
   int off = D.root_offset[slot];
   int n = D.root_offset[slot + 1] - off;
@@ -1843,11 +1852,80 @@ __global__ void __launch_bounds__(KB_ADMIT_THREADS) k_admit(DevSnap D, int slot_
   int *s_shadow_on = s_path + KB_MAX_DEPTH + 2;
   if (threadIdx.x == 0) *s_shadow_on = 0;
   T.shadow_on = s_shadow_on;
-  // global-table mode: per-tile staging of paths and target cells (commit_entry)
-  int *t_plen = s_shadow_on + 2, *t_path = t_plen + KB_TILE, *tc_start = t_path + KB_TILE * KB_PF;
-  TgCell *tcells = reinterpret_cast<TgCell *>(((uintptr_t)(tc_start + KB_TILE + 2) + 7) & ~(uintptr_t)7);
-  const bool stage_cells = !kSmemTables && D.path_stride <= KB_PF;
-
+  // global-table mode: staging buffers of the commit pipeline (commit_entry / StagedEntry)
+  const bool stage_cells = !kSmemTables && stage_buffers && D.path_stride <= KB_PF && nn <= 32767;  // stage_buffers: the launch provided the shared memory
+  int32_t *s_cqpath = nullptr, *s_tadm = nullptr, *s_pref = nullptr, *s_run = nullptr; int8_t *s_cqplen = nullptr, *s_staged = nullptr;
+  TgCell *s_cells = nullptr; uint16_t *s_cs = nullptr;
+  if (stage_cells) {
+    unsigned char *q = (unsigned char *)(((uintptr_t)(s_shadow_on + 2) + 15) & ~(uintptr_t)15);
+    s_cells = (TgCell *)q; q += sizeof(TgCell) * 2 * KB_SUB * KB_ECAP;           // [2][KB_SUB][KB_ECAP]
+    s_cqpath = (int32_t *)q; q += sizeof(int32_t) * (size_t)nn * KB_PF;           // [nn][KB_PF]
+    s_tadm = (int32_t *)q; q += sizeof(int32_t) * 2 * KB_SUB * KB_TCAP;           // [2][KB_SUB][KB_TCAP]
+    s_pref = (int32_t *)q; q += sizeof(int32_t) * KB_SUB * (KB_TCAP + 1);         // per staging warp: cells before target k
+    s_run = (int32_t *)q; q += sizeof(int32_t) * KB_SUB * 32;                     // per staging warp: per-column cursors
+    s_cs = (uint16_t *)q; q += sizeof(uint16_t) * 2 * KB_SUB * 34;                // [2][KB_SUB][33] column offsets
+    s_cqplen = (int8_t *)q; q += (size_t)nn;                                      // [nn]
+    s_staged = (int8_t *)q;                                                       // [2][KB_SUB]
+    for (int i = threadIdx.x; i < nn; i += blockDim.x) {
+      int nd = nodes[i];
+      int pl = nd < D.Q ? D.cq_plen[nd] : 0;
+      s_cqplen[i] = (int8_t)pl;
+      for (int k = 0; k < pl; k++) s_cqpath[i * KB_PF + k] = D.cq_path[(size_t)nd * D.path_stride + k];
+    }
+  }
+  // One warp stages one entry: target ids, then the targets' usage cells counting-sorted by column (stable: the cells
+  // of a column keep target order).  slot = position of the entry inside its group, b = buffer of the group.
+  auto stage_entry = [&](int b, int slot, int ntg, int toff, int sw) {
+    const int ln = threadIdx.x & 31;
+    int32_t *tadm = s_tadm + ((size_t)b * KB_SUB + slot) * KB_TCAP;
+    int32_t *pref = s_pref + (size_t)sw * (KB_TCAP + 1), *run = s_run + sw * 32;
+    TgCell *cells = s_cells + ((size_t)b * KB_SUB + slot) * KB_ECAP;
+    uint16_t *cs = s_cs + ((size_t)b * KB_SUB + slot) * 34;
+    bool ok = ntg <= KB_TCAP;
+    int total = 0;
+    run[ln] = 0;
+    __syncwarp();
+    if (ok) {
+      for (int k0 = 0; k0 < ntg; k0 += 32) {  // targets: ids, cell counts (prefix), histogram of columns
+        int k = k0 + ln, cnt = 0, a = -1, u0 = 0;
+        if (k < ntg) { a = D.tgt_pool_adm[toff + k]; u0 = D.adm_use_start[a]; cnt = D.adm_use_start[a + 1] - u0; tadm[k] = a; }
+        int inc = cnt;
+        for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(0xffffffffu, inc, o); if (ln >= o) inc += v; }
+        if (k < ntg) pref[k] = total + inc - cnt;
+        total += __shfl_sync(0xffffffffu, inc, 31);
+        for (int j = 0; j < cnt; j++) atomicAdd(&run[D.adm_use_fr[u0 + j] & 31], 1);
+      }
+      if (ln == 0) pref[ntg] = total;
+      ok = total <= KB_ECAP;
+    }
+    __syncwarp();
+    if (ok) {
+      int h = run[ln], inc = h;
+      for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(0xffffffffu, inc, o); if (ln >= o) inc += v; }
+      __syncwarp();
+      run[ln] = inc - h;                     // first free position of column ln
+      cs[ln] = (uint16_t)(inc - h);
+      if (ln == 31) cs[32] = (uint16_t)inc;
+      __syncwarp();
+      for (int c0 = 0; c0 < total; c0 += 32) {  // cells in (target, cell) order, 32 at a time
+        int c = c0 + ln, col = 32 + ln;
+        TgCell cell; cell.qty = 0; cell.lh = 0; cell.fr = 0; cell.pad = 0;
+        if (c < total) {
+          int lo = 0, hi = ntg;                // last target k with pref[k] <= c
+          while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (pref[mid] <= c) lo = mid; else hi = mid; }
+          int a = tadm[lo], u = D.adm_use_start[a] + (c - pref[lo]);
+          cell.qty = D.adm_use_qty[u]; cell.fr = (int16_t)D.adm_use_fr[u]; cell.lh = D.local_idx[D.adm_cq[a]];
+          col = cell.fr & 31;
+        }
+        unsigned m = __match_any_sync(0xffffffffu, col);
+        if (c < total) cells[run[col] + __popc(m & ((1u << ln) - 1u))] = cell;
+        __syncwarp();
+        if (c < total && (m & ((1u << ln) - 1u)) == 0) run[col] += __popc(m);
+        __syncwarp();
+      }
+    }
+    if (ln == 0) s_staged[b * KB_SUB + slot] = ok ? 1 : 0;
+  };
   // ---- 1. iterator order: k_rank already produced it for roots up to KB_RANK_CAP entries; larger roots sort here
   //         with an ascending-only bitonic network over the global index array (virtual +inf padding never moves).
   if (n <= KB_RANK_CAP) ent = D.sorted + off;
@@ -1868,6 +1946,17 @@ __global__ void __launch_bounds__(KB_ADMIT_THREADS) k_admit(DevSnap D, int slot_
     }
   }
   __syncthreads();
+  if constexpr (!kSmemTables) {
+    // Large tree: if any entry of the root carries preemption targets the shadow table (usage without the workloads
+    // preempted so far, commit_entry) will be needed — the whole CTA copies it now instead of warp 0 inside the loop.
+    int any = 0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) any |= D.tgt_cnt[ent[i]] > 0;
+    if (__syncthreads_or(any)) {
+      for (int i = threadIdx.x; i < nn * FR; i += blockDim.x) { size_t c = (size_t)nodes[i / FR] * FR + i % FR; D.usage_shadow[c] = __ldcg(&D.usage[c]); }
+      if (threadIdx.x == 0) *s_shadow_on = 1;
+    }
+    __syncthreads();
+  }
   // ---- 2. tiles: expand (all threads), commit (warp 0) ----
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   // flat cohort (every ClusterQueue directly under the root), tables in shared memory, at most two columns per lane
@@ -1884,34 +1973,52 @@ __global__ void __launch_bounds__(KB_ADMIT_THREADS) k_admit(DevSnap D, int slot_
     __syncthreads();
     // one thread per entry walks its podset rows once and scatters the cells of its row
     for (int i = threadIdx.x; i < tn; i += blockDim.x) expand_entry(D, t_e[i], s_q + (size_t)i * FR);
-    if (stage_cells) {
-      for (int i = threadIdx.x; i < tn; i += blockDim.x) {
-        int nd = t_node[i], pl = D.cq_plen[nd];
-        t_plen[i] = pl;
-        for (int k = 0; k < pl; k++) t_path[i * KB_PF + k] = D.cq_path[(size_t)nd * D.path_stride + k];
-        int nc = 0;
-        for (int k = 0; k < t_ntg[i]; k++) { int a = D.tgt_pool_adm[t_toff[i] + k]; nc += D.adm_use_start[a + 1] - D.adm_use_start[a]; }
-        tc_start[i + 1] = nc;
-      }
-      __syncthreads();
-      if (threadIdx.x == 0) { int acc = 0; tc_start[0] = 0; for (int i = 0; i < tn; i++) { acc += tc_start[i + 1]; tc_start[i + 1] = acc; } }
-      __syncthreads();
-      for (int i = threadIdx.x; i < tn; i += blockDim.x) {
-        int c0 = tc_start[i], c1 = tc_start[i + 1];
-        if (c1 > KB_TG_CAP || c1 - c0 > 64) continue;  // the commit falls back to the unstaged walk for this entry
-        for (int k = 0; k < t_ntg[i]; k++) {
-          int a = D.tgt_pool_adm[t_toff[i] + k];
-          int nd2 = D.adm_cq[a], pl = D.cq_plen[nd2];
-          for (int u = D.adm_use_start[a]; u < D.adm_use_start[a + 1]; u++, c0++) {
-            TgCell &c = tcells[c0];
-            c.qty = D.adm_use_qty[u]; c.fr = (int16_t)D.adm_use_fr[u]; c.adm = a; c.plen = (int8_t)pl;
-            for (int j = 0; j < pl; j++) c.path[j] = D.cq_path[(size_t)nd2 * D.path_stride + j];
-          }
-        }
-      }
-    }
     __syncthreads();
-    if (warp == 0) {
+    if (stage_cells) {
+      // groups of KB_SUB entries: warp 0 commits group j while warps 1..KB_SUB stage group j + 1
+      const int ngrp = (tn + KB_SUB - 1) / KB_SUB;
+#ifdef KB_ADMIT_PROBE
+#define AP(k, v) do { if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&D.sstat[k], (u64)(v)); } while (0)
+      long long ap0 = clock64();
+#else
+#define AP(k, v) do { } while (0)
+#endif
+      if (warp >= 1 && warp <= KB_SUB) { int i = warp - 1; if (i < tn) stage_entry(0, i, t_ntg[i], t_toff[i], warp - 1); }
+      __syncthreads();
+#ifdef KB_ADMIT_PROBE
+      AP(0, clock64() - ap0);  // first group staging (exposed)
+#endif
+      for (int j = 0; j < ngrp; j++) {
+        const int b = j & 1, i0 = j * KB_SUB, i1 = min(tn, i0 + KB_SUB);
+#ifdef KB_ADMIT_PROBE
+        long long ap1 = clock64();
+#endif
+        if (warp == 0) {
+          for (int i = i0; i < i1; i++) {
+#ifdef KB_ADMIT_PROBE
+            AP(2, 1); AP(3, s_staged[b * KB_SUB + (i - i0)] ? 1 : 0); AP(4, t_ntg[i]); AP(5, s_staged[b * KB_SUB + (i - i0)] ? (s_cs + ((size_t)b * KB_SUB + (i - i0)) * 34)[32] : 0);
+#endif
+            StagedEntry st;
+            const int slot = i - i0;
+            st.cells = s_cells + ((size_t)b * KB_SUB + slot) * KB_ECAP; st.col_start = s_cs + ((size_t)b * KB_SUB + slot) * 34;
+            st.adm = s_tadm + ((size_t)b * KB_SUB + slot) * KB_TCAP; st.cq_path = s_cqpath; st.cq_plen = s_cqplen;
+            commit_entry<kSmemTables>(D, T, s_path, lane, t_e[i], t_node[i], t_mode[i], t_borrow[i], s_q + (size_t)i * FR, base + i,
+                                      t_cq[i], t_ntg[i], t_toff[i], s_staged[b * KB_SUB + slot] ? &st : nullptr);
+          }
+        } else if (warp <= KB_SUB) {
+          int i = i1 + warp - 1;
+          if (i < tn) stage_entry(b ^ 1, warp - 1, t_ntg[i], t_toff[i], warp - 1);
+        }
+#ifdef KB_ADMIT_PROBE
+        long long ap2 = clock64();
+        AP(1, ap2 - ap1);  // commit time of the group (warp 0)
+#endif
+        __syncthreads();
+#ifdef KB_ADMIT_PROBE
+        AP(6, clock64() - ap2);  // warp 0 waiting for the stagers
+#endif
+      }
+    } else if (warp == 0) {
       if constexpr (kSmemTables) {
         if (flat) {
           if (FR > 32) commit_tile_flat<true>(D, T, s_path, lane, tn, base, s_q, t_e, t_node, t_mode, t_borrow, t_cq, t_ntg, t_toff);
@@ -1919,17 +2026,9 @@ __global__ void __launch_bounds__(KB_ADMIT_THREADS) k_admit(DevSnap D, int slot_
         }
       }
       if (!flat)
-        for (int i = 0; i < tn; i++) {
-          if (stage_cells) {
-            int c0 = tc_start[i], c1 = tc_start[i + 1];
-            bool st = c1 <= KB_TG_CAP && c1 - c0 <= 64;
-            commit_entry<kSmemTables>(D, T, s_path, lane, t_e[i], t_node[i], t_mode[i], t_borrow[i], s_q + (size_t)i * FR, base + i,
-                                      t_cq[i], t_ntg[i], t_toff[i], t_path + i * KB_PF, t_plen[i], st ? tcells + c0 : nullptr, c1 - c0);
-          } else {
-            commit_entry<kSmemTables>(D, T, s_path, lane, t_e[i], t_node[i], t_mode[i], t_borrow[i], s_q + (size_t)i * FR, base + i,
-                                      t_cq[i], t_ntg[i], t_toff[i]);
-          }
-        }
+        for (int i = 0; i < tn; i++)
+          commit_entry<kSmemTables>(D, T, s_path, lane, t_e[i], t_node[i], t_mode[i], t_borrow[i], s_q + (size_t)i * FR, base + i,
+                                    t_cq[i], t_ntg[i], t_toff[i]);
     }
     __syncthreads();
     if (flat) {  // decisions of the flat commit loop (t_mode[i] = KB_DEC_* | 0x100), written by the whole CTA
@@ -1941,6 +2040,13 @@ __global__ void __launch_bounds__(KB_ADMIT_THREADS) k_admit(DevSnap D, int slot_
     }
   }
   publish_usage<kSmemTables>(D, T, nodes, nn);
+#ifdef KB_ADMIT_PROBE
+  if (threadIdx.x == 0) {
+    long long tg = 0; int big = 0;
+    for (int i = 0; i < n; i++) { int e = ent[i]; tg += D.tgt_cnt[e]; if (D.tgt_cnt[e] > 100) big++; }
+    printf("k_admit root %d: nn %d entries %d targets %lld entries>100tg %d cycles %lld\n", slot, nn, n, tg, big, clock64() - kp0);
+  }
+#endif
 }
 
 // ---------------------------------------------------------------------------
@@ -1977,6 +2083,32 @@ __global__ void __launch_bounds__(KB_ROOT_THREADS) k_cycle_root(DevSnap D) {
   int *s_path = t_toff + KB_TILE;
   int *s_misc = s_path + KB_MAX_DEPTH + 2;  // [0] shadow_on, [1] n entries
   u64 *s_key = (u64 *)(((uintptr_t)(s_misc + 4) + 15) & ~(uintptr_t)15);  // [nn][4]
+  // ---- 0. The nominate / key phases below follow, per entry, a chain of dependent loads through the per-cycle tables
+  // (head -> workload -> podset rows -> resource group -> flavors), cold in L2 after the upload.  One thread per
+  // ClusterQueue walks that chain now and only touches the lines (prefetch), overlapped with the table staging of
+  // phase 1, so that the later phases find them in L1/L2.
+  if ((int)threadIdx.x < nn) {
+    auto touch = [](const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); };
+    const int nd = nodes[threadIdx.x];
+    const int e = nd < D.Q ? D.cq_entry[nd] : -1;
+    if (e >= 0) {
+      const int wl = D.heads[e];
+      touch(D.wl_cq + wl); touch(D.wl_last_gen + wl); touch(D.wl_priority + wl); touch(D.wl_ts + wl); touch(D.wl_uid + wl);
+      touch(D.cq_generation + nd); touch(D.cq_preference + nd); touch(D.cq_when_can_borrow + nd); touch(D.cq_when_can_preempt + nd);
+      touch(D.cq_within_cq + nd); touch(D.cq_reclaim_within + nd); touch(D.cq_borrow_within + nd); touch(D.fair_weight + nd);
+      const int ps0 = D.wl_ps_start[wl], ps1 = D.wl_ps_start[wl + 1];
+      const int g0 = D.cq_rg_start[nd], g1 = D.cq_rg_start[nd + 1];
+      for (int row = ps0; row < ps1 && row < ps0 + 4; row++) {
+        touch(D.ps_count + row); touch(D.ps_min_count + row); touch(D.ps_req_mask + row); touch(D.ps_flavor_ok + row);
+        touch(D.ps_req + (size_t)row * R); touch(D.ps_last_tried + (size_t)row * R);
+      }
+      for (int g = g0; g < g1 && g < g0 + 4; g++) {
+        touch(D.rg_res_mask + g);
+        const int f0 = D.rg_flavor_start[g], f1 = D.rg_flavor_start[g + 1];
+        for (int k = f0; k < f1; k += 32) touch(D.rg_flavors + k);
+      }
+    }
+  }
   // ---- 1. stage: SubtreeQuota = Nominal, Usage = ClusterQueue usage | 0 (updateCohortResourceNode :184-190)
   for (int i = threadIdx.x; i < (int)tb; i += blockDim.x) {
     int nd = nodes[i / FR], fr = i % FR;

@@ -51,6 +51,41 @@ class DrainResult:
         return int(sum(len(h) for h in self.heads))
 
 
+# RequeueReason (pkg/cache/queue/cluster_queue.go:55-66) of an entry that was not admitted, from the cycle's decision:
+# entries that were nominated and then lost the admit loop are "FailedAfterNomination" (requeueAndUpdate
+# scheduler.go:825-828), a Preempting entry waits for its evictions ("PendingPreemption", scheduler.go:339-346), NoFit and
+# Preempt-without-targets entries keep the generic reason.
+REASON_GENERIC, REASON_FAILED_AFTER_NOMINATION, REASON_NAMESPACE_MISMATCH, REASON_PENDING_PREEMPTION = (
+    "", "FailedAfterNomination", "NamespaceMismatch", "PendingPreemption")
+
+
+def requeue_reason(decision: int) -> str:
+    if decision in (abi.DEC_NOFIT, abi.DEC_PREEMPT_NO_TARGETS):
+        return REASON_GENERIC
+    if decision == abi.DEC_PREEMPTING:
+        return REASON_PENDING_PREEMPTION
+    return REASON_FAILED_AFTER_NOMINATION  # skipped in the admit loop
+
+
+def pending_flavors(last_tried) -> bool:
+    """AssignmentClusterQueueState.PendingFlavors (workload.go:163-176): some podset resource still has a flavor to
+    try.  `last_tried`: LastTriedFlavorIdx as rows of per-resource indices (-1 = exhausted / absent), or None."""
+    if last_tried is None:
+        return False
+    return bool((np.asarray(last_tried) != -1).any())
+
+
+def requeue_goes_inadmissible(strict_fifo: bool, reason: str, last_tried) -> bool:
+    """RequeueIfNotPresent + requeueIfNotPresent (cluster_queue.go:362-393,609-633) inside a drain: no
+    QueueInadmissibleWorkloads call happens between Pop and the requeue and no backoff is pending, so the workload
+    returns to the heap iff the requeue is immediate or flavors are pending; otherwise it joins the inadmissible set."""
+    if strict_fifo:
+        immediate = reason != REASON_NAMESPACE_MISMATCH
+    else:
+        immediate = reason in (REASON_FAILED_AFTER_NOMINATION, REASON_PENDING_PREEMPTION, "PreemptionFailed")
+    return not (immediate or pending_flavors(last_tried))
+
+
 def _queue_order(a, Q):
     """Pending workloads of every ClusterQueue in queueOrderingFunc order: (order, start[Q+1])."""
     cq = a["wl_cq"].astype(np.int64)
@@ -151,7 +186,8 @@ def drain(snap: abi.FlatSnapshot, run_cycle: Callable[[abi.FlatSnapshot], abi.Cy
             adm["adm_use_qty"] = np.concatenate([adm["adm_use_qty"], np.asarray(new_qty, np.int64)])
         # ---- LastAssignment of the entries that stay pending (scheduler.go:345,494)
         tried = np.asarray(out.ps_tried_idx).reshape(-1, R)
-        pending_flavors = np.zeros(len(heads), bool)
+        cqs = live
+        inadmissible = np.zeros(len(heads), bool)
         for e in range(len(heads)):
             if ok[e]:
                 continue
@@ -159,13 +195,13 @@ def drain(snap: abi.FlatSnapshot, run_cycle: Callable[[abi.FlatSnapshot], abi.Cy
             r0, r1 = int(st[e]), int(st[e + 1])
             if dec[e] == abi.DEC_PREEMPTING:
                 last_gen[w] = -1
+                last = None
             else:
                 last_gen[w] = int(a["cq_generation"][int(a["wl_cq"][w])])
                 last_tried[int(ps_start[w]):int(ps_start[w + 1])] = tried[r0:r1]
-                pending_flavors[e] = bool((tried[r0:r1] != -1).any())
-        # ---- queue movement (cluster_queue.go:362-425,609-633)
-        cqs = live
-        inadmissible = ((dec == abi.DEC_NOFIT) | (dec == abi.DEC_PREEMPT_NO_TARGETS)) & ~pending_flavors
+                last = tried[r0:r1]
+            # ---- queue movement (cluster_queue.go:362-425,609-633); a StrictFIFO queue keeps its head either way
+            inadmissible[e] = requeue_goes_inadmissible(False, requeue_reason(int(dec[e])), last)
         advance = ok | (inadmissible & ~strict[cqs])
         if shash is not None:
             for e in np.flatnonzero((dec == abi.DEC_NOFIT) & ~strict[cqs]):

@@ -9,11 +9,12 @@ import os
 from . import abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libkueue_b200.so")
+LIB_PATH = os.environ.get("KUEUE_B200_LIB") or os.path.join(_HERE, "libkueue_b200.so")  # override: instrumented builds
 _LIB = None
 
 EXPORTS = ["kb_create", "kb_destroy", "kb_last_error", "kb_alloc_pinned", "kb_free_pinned", "kb_version",
-           "kb_tree_eval", "kb_run_cycle", "kb_run_drain", "kb_tas_find", "kb_upload", "kb_cycle_resident", "kb_download", "kb_get_stats", "kb_set_profile"]
+           "kb_tree_eval", "kb_run_cycle", "kb_run_drain", "kb_tas_find", "kb_upload", "kb_cycle_resident", "kb_download", "kb_get_stats", "kb_set_profile",
+           "kb_alloc_cycle_out"]
 
 
 class KueueB200Error(RuntimeError):
@@ -80,19 +81,29 @@ def pin_snapshot(snap: abi.FlatSnapshot) -> abi.FlatSnapshot:
 
 
 def pin_cycle_out(out: abi.CycleOut) -> abi.CycleOut:
-    """Re-point the output buffers at pinned host memory."""
+    """Re-point the output buffers at ONE page-locked block from kb_alloc_cycle_out (laid out like the library's
+    device-side result tables, so the eight per-entry / per-podset tables come back with a single DMA)."""
     import numpy as np
-    for name, ctype in (("decision", C.c_uint8), ("mode", C.c_uint8), ("borrow", C.c_int32), ("commit_rank", C.c_int32),
-                        ("ps_flavor", C.c_int8), ("ps_res_mode", C.c_int8), ("ps_tried_idx", C.c_int8),
-                        ("ps_count", C.c_int32), ("tgt_start", C.c_int32), ("tgt_adm", C.c_int32),
-                        ("tgt_reason", C.c_uint8), ("node_usage", C.c_int64)):
+    H, (P, R) = out.decision.shape[0], out.ps_flavor.shape
+    cells = 0 if out.node_usage is None else int(out.node_usage.size)
+    s = abi.kb_cycle_out()
+    rc = lib().kb_alloc_cycle_out(C.c_int32(H), C.c_int32(P), C.c_int32(R), C.c_int32(out.struct.tgt_capacity), C.c_int64(cells), C.byref(s))
+    if rc != 0:
+        raise KueueB200Error(rc, "kb_alloc_cycle_out failed")
+
+    def view(ptr, like):
+        n = max(1, like.size * like.dtype.itemsize)
+        buf = (C.c_char * n).from_address(C.cast(ptr, C.c_void_p).value)
+        a = np.frombuffer(buf, dtype=like.dtype, count=like.size).reshape(like.shape)
+        a[...] = like
+        return a
+    for name in ("decision", "mode", "borrow", "commit_rank", "ps_flavor", "ps_res_mode", "ps_tried_idx", "ps_count",
+                 "tgt_start", "tgt_adm", "tgt_reason", "node_usage"):
         old = getattr(out, name)
         if old is None:
             continue
-        a = pinned_array(old.shape, old.dtype)
-        a[...] = old
-        setattr(out, name, a)
-        setattr(out.struct, name, a.ctypes.data_as(C.POINTER(ctype)))
+        setattr(out, name, view(getattr(s, name), old))
+    out.struct = s
     return out
 
 

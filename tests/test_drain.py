@@ -47,6 +47,29 @@ def test_drain_on_oracle(make):
     assert again.cycles == res.cycles and all(np.array_equal(x, y) for x, y in zip(again.decisions, res.decisions))
 
 
+# TestBestEffortFIFORequeueIfNotPresent (pkg/cache/queue/cluster_queue_test.go:749-815), transcribed by hand: requeue
+# reason + LastAssignment.LastTriedFlavorIdx -> does the workload land in the inadmissible set of a BestEffortFIFO queue?
+_REQUEUE_CASES = {
+    "failure after nomination": ("FailedAfterNomination", None, False),
+    "namespace doesn't match": ("NamespaceMismatch", None, True),
+    "didn't fit and no pending flavors": ("", [{"memory": -1}, {"cpu": -1, "memory": -1}], True),
+    "didn't fit but pending flavors": ("", [{"cpu": -1, "memory": 0}, {"memory": 1}], False),
+}
+
+
+@pytest.mark.parametrize("name", list(_REQUEUE_CASES))
+def test_requeue_rule_matches_reference_table(name):
+    from kueue_b200.drain import requeue_goes_inadmissible
+    reason, last, want = _REQUEUE_CASES[name]
+    rows = None
+    if last is not None:  # LastTriedFlavorIdx as [podset][resource] rows, absent resources = -1 like the flat tables
+        res = ["cpu", "memory"]
+        rows = np.array([[ps.get(r, -1) for r in res] for ps in last], np.int8)
+    assert requeue_goes_inadmissible(False, reason, rows) == want
+    # StrictFIFO requeues immediately unless the namespace does not match (cluster_queue.go:622-624): the head stays
+    assert requeue_goes_inadmissible(True, reason, rows) == (reason == "NamespaceMismatch" and not (rows is not None and (rows != -1).any()))
+
+
 def test_first_drain_cycle_is_the_reference_cycle():
     snap = synth.make_snapshot(3, W=2000, Q=40, heads="one_per_cq")
     one = oracle.run_cycle(synth.compact_to_heads(snap))

@@ -290,6 +290,11 @@ def test_span_upload_from_one_pinned_block(ev):
         pinned.static_generation = 7
         assert_cycle_equal(ev.run_cycle(pinned, abi.CycleOut(pinned, cap)), want)
         assert_cycle_equal(ev.run_cycle(pinned, abi.CycleOut(pinned, cap)), want)  # static tables reused, span upload again
+        # results into one kb_alloc_cycle_out block: the per-entry / per-podset tables come back with a single DMA
+        pout = native.pin_cycle_out(abi.CycleOut(pinned, cap))
+        assert_cycle_equal(ev.run_cycle(pinned, pout), want)
+        assert ev.stats().d2h_bytes > 0
+        assert_cycle_equal(ev.run_cycle(pinned, pout), want)
 
 
 def test_reference_podset_reducer_cycle(ev):
