@@ -2063,6 +2063,11 @@ __global__ void __launch_bounds__(KB_ADMIT_THREADS) k_admit(DevSnap D, int slot_
 __global__ void __launch_bounds__(KB_ROOT_THREADS) k_cycle_root(DevSnap D) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int FR = D.FR, R = D.R, Fn = D.F;
+  // index -> (row, column): FR is a power of two in every configuration at hand; the shift form saves a ~20-instruction
+  // integer division per cell in the phases below (uniform branch)
+  const int fr_sh = 31 - __clz(FR); const bool fr_p2 = (1 << fr_sh) == FR;
+  auto row_of = [&](int i) { return fr_p2 ? i >> fr_sh : i / FR; };
+  auto col_of = [&](int i) { return fr_p2 ? i & (FR - 1) : i % FR; };
   const int t = blockIdx.x;
   long long tk0 = clock64();
 #define KB_PHASE(k) do { if (blockIdx.x == 0 && threadIdx.x == 0) { long long now = clock64(); D.sstat[k] = (u64)(now - tk0); tk0 = now; } } while (0)
@@ -2111,7 +2116,7 @@ __global__ void __launch_bounds__(KB_ROOT_THREADS) k_cycle_root(DevSnap D) {
   }
   // ---- 1. stage: SubtreeQuota = Nominal, Usage = ClusterQueue usage | 0 (updateCohortResourceNode :184-190)
   for (int i = threadIdx.x; i < (int)tb; i += blockDim.x) {
-    int nd = nodes[i / FR], fr = i % FR;
+    int nd = nodes[row_of(i)], fr = col_of(i);
     size_t c = (size_t)nd * FR + fr;
     s_sub[i] = D.nominal[c];
     s_u[i] = nd < D.Q ? D.cq_usage[c] : 0;
@@ -2140,14 +2145,31 @@ __global__ void __launch_bounds__(KB_ROOT_THREADS) k_cycle_root(DevSnap D) {
         dus += imax(0, s_u[c] - lq);
       }
       for (int o = 16; o > 0; o >>= 1) { dsub += __shfl_xor_sync(0xffffffffu, dsub, o); dus += __shfl_xor_sync(0xffffffffu, dus, o); }
-      if (lane_ == 0) { s_sub[fr] += dsub; s_u[fr] += dus; }
+      if (lane_ == 0) {  // the root's cell is final: localQuota, available, potentialAvailable of the root (:104-133)
+        i64 sub = s_sub[fr] + dsub, u = s_u[fr] + dus;
+        s_sub[fr] = sub; s_u[fr] = u;
+        s_lq[fr] = local_quota(sub, s_lq[fr]);
+        s_av[fr] = sub - u; s_pot[fr] = sub;
+      }
     }
     __syncthreads();
-  } else
+    // children in one pass: localQuota, then available / potentialAvailable below the root
+    for (int i = FR + threadIdx.x; i < (int)tb; i += blockDim.x) {
+      const int fr = col_of(i);
+      i64 sub = s_sub[i], u = s_u[i], bl = s_bl[i];
+      i64 lq = local_quota(sub, s_lq[i]);
+      s_lq[i] = lq;
+      i64 pa = s_av[fr], pot = lq + s_pot[fr];
+      if (bl != KB_NO_LIMIT) { pa = imin((sub - lq) - imax(0, u - lq) + bl, pa); pot = imin(sub + bl, pot); }
+      s_av[i] = imax(0, lq - u) + pa;
+      s_pot[i] = pot;
+    }
+    __syncthreads();
+  } else {
   for (int L = nlev - 1; L >= 1; L--) {
     int a = lvl[L], b = lvl[L + 1];
     for (int i = threadIdx.x; i < (b - a) * FR; i += blockDim.x) {
-      int h = a + i / FR, fr = i % FR;
+      int h = a + row_of(i), fr = col_of(i);
       int c = h * FR + fr, pc = s_par[h] * FR + fr;
       i64 sub = s_sub[c];
       i64 lq = local_quota(sub, s_lq[c]);
@@ -2162,7 +2184,7 @@ __global__ void __launch_bounds__(KB_ROOT_THREADS) k_cycle_root(DevSnap D) {
   for (int L = 0; L < nlev; L++) {
     int a = lvl[L], b = lvl[L + 1];
     for (int i = threadIdx.x; i < (b - a) * FR; i += blockDim.x) {
-      int h = a + i / FR, fr = i % FR;
+      int h = a + row_of(i), fr = col_of(i);
       int c = h * FR + fr;
       i64 sub = s_sub[c], u = s_u[c];
       if (L == 0) { s_av[c] = sub - u; s_pot[c] = sub; }
@@ -2176,6 +2198,7 @@ __global__ void __launch_bounds__(KB_ROOT_THREADS) k_cycle_root(DevSnap D) {
       }
     }
     __syncthreads();
+  }
   }
   KB_PHASE(1);
   // ---- 3. fair sharing inputs (k_fair_prep): over-usage per (ClusterQueue, resource), lendable per (node, resource)
@@ -2208,7 +2231,7 @@ __global__ void __launch_bounds__(KB_ROOT_THREADS) k_cycle_root(DevSnap D) {
   }
   __syncthreads();
   const int n = s_misc[1];
-  if (n == 0) { for (int i = threadIdx.x; i < (int)tb; i += blockDim.x) D.usage[(size_t)nodes[i / FR] * FR + i % FR] = s_u[i]; return; }
+  if (n == 0) { for (int i = threadIdx.x; i < (int)tb; i += blockDim.x) D.usage[(size_t)nodes[row_of(i)] * FR + col_of(i)] = s_u[i]; return; }
   KB_PHASE(2);
   // local view of the snapshot: node tables in shared memory, indexed by the local handle
   DevSnap L = D;
@@ -2272,7 +2295,7 @@ __global__ void __launch_bounds__(KB_ROOT_THREADS) k_cycle_root(DevSnap D) {
       t_toff[threadIdx.x] = rank;
     } else if ((int)threadIdx.x >= half) {
       for (int c = threadIdx.x - half; c < n * FR; c += half) {
-        int i = c / FR, fr = c % FR;
+        int i = row_of(c), fr = col_of(c);
         i64 q = s_q[c];
         int r = t_node[i] * FR + fr;
         i64 u = s_u[r], l = s_lq[r], bl = s_bl[r], sub = s_sub[r];
@@ -2339,7 +2362,7 @@ __global__ void __launch_bounds__(KB_ROOT_THREADS) k_cycle_root(DevSnap D) {
     KB_PHASE(6);
     // ClusterQueue rows of the admitted / reserving entries (cq.AddUsage), decisions and ranks
     for (int c = threadIdx.x; c < n * FR; c += blockDim.x) {
-      int i = c / FR, fr = c % FR;
+      int i = row_of(c), fr = col_of(c);
       int dec = t_ntg[i];
       i64 q = s_q[c];
       int r = t_node[i] * FR + fr;
@@ -2351,7 +2374,7 @@ __global__ void __launch_bounds__(KB_ROOT_THREADS) k_cycle_root(DevSnap D) {
       if (fr == 0) { D.decision[t_e[i]] = (uint8_t)dec; D.rank[t_e[i]] = t_toff[i]; }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < (int)tb; i += blockDim.x) D.usage[(size_t)nodes[i / FR] * FR + i % FR] = s_u[i];
+    for (int i = threadIdx.x; i < (int)tb; i += blockDim.x) D.usage[(size_t)nodes[row_of(i)] * FR + col_of(i)] = s_u[i];
     KB_PHASE(7);
     return;
   }
@@ -2397,7 +2420,7 @@ __global__ void __launch_bounds__(KB_ROOT_THREADS) k_cycle_root(DevSnap D) {
     __syncthreads();
   }
   KB_PHASE(5);
-  for (int i = threadIdx.x; i < (int)tb; i += blockDim.x) D.usage[(size_t)nodes[i / FR] * FR + i % FR] = s_u[i];
+  for (int i = threadIdx.x; i < (int)tb; i += blockDim.x) D.usage[(size_t)nodes[row_of(i)] * FR + col_of(i)] = s_u[i];
   KB_PHASE(6);
 }
 __global__ void k_cq_entry(DevSnap D, int32_t *cq_entry) {  // ClusterQueue -> its single head of this cycle

@@ -5,6 +5,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import weakref
 
 from . import abi
 
@@ -51,8 +52,16 @@ def pinned_array(shape, dtype) -> "np.ndarray":
     if rc != 0:
         raise KueueB200Error(rc, "kb_alloc_pinned failed")
     buf = (C.c_char * max(1, n * dtype.itemsize)).from_address(ptr.value)
+    weakref.finalize(buf, _free_pinned, ptr.value)  # released when the last numpy view of the block is gone
     arr = np.frombuffer(buf, dtype=dtype, count=n).reshape(shape)
     return arr
+
+
+def _free_pinned(address: int) -> None:
+    try:
+        lib().kb_free_pinned(C.c_void_p(address))
+    except Exception:  # noqa: BLE001 — interpreter shutdown
+        pass
 
 
 def pin_snapshot(snap: abi.FlatSnapshot) -> abi.FlatSnapshot:
@@ -104,6 +113,8 @@ def pin_cycle_out(out: abi.CycleOut) -> abi.CycleOut:
             continue
         setattr(out, name, view(getattr(s, name), old))
     out.struct = s
+    # the block lives as long as the CycleOut object (its arrays are views into it)
+    weakref.finalize(out, _free_pinned, C.cast(s.decision, C.c_void_p).value)
     return out
 
 
