@@ -63,7 +63,8 @@ struct kb_handle {
   int kev_n = 0;
   std::string err;
   kb_stats stats{};
-  uint32_t *host_words = nullptr;  // pinned: [0] status bits, [1] targets used
+  uint32_t *host_words = nullptr;  // pinned scratch words; [32..63] = copy of the cycle header
+  const uint32_t *hdr_host = nullptr;  // where the last cycle's header landed (host_words or the caller's result block)
   int last_launches = 0;
   int64_t last_d2h_bytes = 0;
   // tree_eval scratch
@@ -74,6 +75,8 @@ struct kb_handle {
   // host copies of the static tables build_dynamic consults every cycle (the caller's static pointers are not read
   // again while static_generation is unchanged)
   std::vector<int32_t> s_parent; std::vector<uint8_t> s_within_cq, s_reclaim_within;
+  std::vector<uint32_t> seen; uint32_t seen_stamp = 0;  // one-head-per-ClusterQueue check without clearing a table per cycle
+  bool s_any_lone_within = false, s_preempt_policy = false;  // static: some cohort-less CQ has WithinClusterQueue != Never / some CQ has a preemption policy
   std::vector<int32_t> sn_node, slot_base, nd_tin, nd_tout, cq_path, cq_plen; int path_stride = 1;
   int max_root_adm = 1;
   int max_frl_len = 1;      // longest (root, flavor-resource) candidate bucket of this cycle
@@ -87,6 +90,9 @@ struct kb_handle {
   char *drain_buf = nullptr; size_t drain_buf_cap = 0; cudaEvent_t ev_d = nullptr;
   char *tas_buf = nullptr; size_t tas_buf_cap = 0;
   bool fused_on = false; size_t fused_smem = 0; bool one_head_per_cq = false; int32_t *d_cq_entry = nullptr;
+  // k_cycle_flat (kb_flat.cuh): static per-tree blocks in local numbering, head records per tree node
+  std::vector<unsigned char> tree_blob; std::vector<int32_t> tree_blob_off; int max_blob_bytes = 16;
+  bool flat_on = false, flat_attr_set = false, hdr_clean = false; unsigned rec_stamp = 0; const void *rec_seen = nullptr; size_t rec_seen_n = 0; size_t flat_smem = 0; int flat_rcap = 1; int4 *d_cq_rec = nullptr;
   bool sg_on = false; int sg_wpb = 1, sg_grid = 1, sg_ncap = 1; size_t sg_smem = 0;  // grouped form of k_search_cells
   // device ranking of the admitted workloads (kb_rank.cuh)
   u64 *rk_keys[2] = {nullptr, nullptr}; int32_t *rk_vals[2] = {nullptr, nullptr}; void *rk_temp = nullptr; size_t rk_temp_bytes = 0;
@@ -128,11 +134,13 @@ static bool inside_one_pinned_block(uintptr_t lo, uintptr_t hi) {
 
 // Canonical layout of the eight per-entry / per-podset output tables: the device block of every cycle and the host
 // block of kb_alloc_cycle_out use the same offsets, so those results come back with ONE device-to-host DMA.
-struct OutLayout { size_t off[8]; size_t prefix; };
+// The block ends with the 128-byte cycle header (status word, counters), so that it too needs no copy of its own.
+struct OutLayout { size_t off[8]; size_t hdr; size_t prefix; };
 static OutLayout out_layout(size_t H, size_t P, size_t R) {
   const size_t sz[8] = {H, H, 4 * H, 4 * H, P * R, P * R, P * R, 4 * P};  // decision mode borrow rank flavor res_mode tried count
   OutLayout L; size_t o = 0;
   for (int i = 0; i < 8; i++) { L.off[i] = o; o += pad256(sz[i]); }
+  L.hdr = o; o += 256;
   L.prefix = o;
   return L;
 }
@@ -341,6 +349,11 @@ static int32_t build_static(kb_handle *h, const kb_snapshot *s) {
   h->s_parent.assign(s->parent, s->parent + N);
   h->s_within_cq.assign(s->cq_within_cq, s->cq_within_cq + Q);
   h->s_reclaim_within.assign(s->cq_reclaim_within, s->cq_reclaim_within + Q);
+  h->s_any_lone_within = false; h->s_preempt_policy = false;
+  for (int q = 0; q < Q; q++) {
+    if (s->parent[q] < 0 && s->cq_within_cq[q] != KB_POLICY_NEVER) h->s_any_lone_within = true;
+    if (s->cq_within_cq[q] != KB_POLICY_NEVER || (s->parent[q] >= 0 && s->cq_reclaim_within[q] != KB_POLICY_NEVER)) h->s_preempt_policy = true;
+  }
   {  // slot-node numbering (cohort-less ClusterQueues, then the trees) and Euler-tour intervals inside every tree
     int nl = (int)h->lone.size();
     h->sn_node.assign(std::max(1, N), 0); h->nd_tin.assign(std::max(1, N), 0); h->nd_tout.assign(std::max(1, N), 1);
@@ -368,6 +381,52 @@ static int32_t build_static(kb_handle *h, const kb_snapshot *s) {
         }
       }
     }
+  }
+  {  // static per-tree blocks in local numbering (TreeBlobHdr, kb_flat.cuh)
+    h->tree_blob.clear(); h->tree_blob_off.assign(ntrees + 1, 0); h->max_blob_bytes = 16;
+    for (int t = 0; t < ntrees; t++) {
+      const int nn = h->tree_start[t + 1] - h->tree_start[t];
+      const int32_t *nodes = h->tree_nodes.data() + h->tree_start[t];
+      int nrg = 0, nfl = 0;
+      for (int i = 0; i < nn; i++) if (nodes[i] < Q) for (int g = s->cq_rg_start[nodes[i]]; g < s->cq_rg_start[nodes[i] + 1]; g++) { nrg++; nfl += s->rg_flavor_start[g + 1] - s->rg_flavor_start[g]; }
+      TreeBlobHdr H{};
+      size_t o = sizeof(TreeBlobHdr);
+      auto take = [&](size_t bytes) { o = (o + 15) & ~(size_t)15; size_t at = o; o += bytes; return (int32_t)at; };
+      H.nn = nn; H.nrg = nrg; H.nfl = nfl;
+      H.gid = take((size_t)nn * 4); H.par = take((size_t)nn * 4); H.hgt = take((size_t)nn * 4); H.rgs = take((size_t)(nn + 1) * 4);
+      H.gen = take((size_t)nn * 8); H.wgt = take((size_t)nn * 8);
+      H.within = take(nn); H.reclaim = take(nn); H.borrow_w = take(nn); H.wcb = take(nn); H.wcp = take(nn); H.pref = take(nn);
+      H.rgmask = take((size_t)nrg * 4); H.rgfl = take((size_t)(nrg + 1) * 4); H.fl = take((size_t)nfl * 4);
+      o = (o + 15) & ~(size_t)15;
+      H.bytes = (int32_t)o;
+      size_t base = h->tree_blob.size();
+      if (base + o >= (size_t)INT32_MAX) return fail(h, KB_ERR_INVALID, "static tree tables exceed 2 GiB");
+      h->tree_blob.resize(base + o, 0);
+      unsigned char *b = h->tree_blob.data() + base;
+      memcpy(b, &H, sizeof(H));
+      int32_t *gid = (int32_t *)(b + H.gid), *par = (int32_t *)(b + H.par), *hgt = (int32_t *)(b + H.hgt), *rgs = (int32_t *)(b + H.rgs);
+      i64 *gen = (i64 *)(b + H.gen); double *wgt = (double *)(b + H.wgt);
+      uint32_t *rgmask = (uint32_t *)(b + H.rgmask); int32_t *rgfl = (int32_t *)(b + H.rgfl), *fl = (int32_t *)(b + H.fl);
+      int lg = 0, lf = 0;
+      for (int i = 0; i < nn; i++) {
+        const int nd = nodes[i];
+        gid[i] = nd; par[i] = s->parent[nd] < 0 ? -1 : h->local_idx[s->parent[nd]]; hgt[i] = h->height[nd]; rgs[i] = lg;
+        wgt[i] = s->fair_weight[nd];
+        if (nd >= Q) continue;
+        gen[i] = s->cq_generation[nd];
+        b[H.within + i] = s->cq_within_cq[nd]; b[H.reclaim + i] = s->cq_reclaim_within[nd]; b[H.borrow_w + i] = s->cq_borrow_within[nd];
+        b[H.wcb + i] = s->cq_when_can_borrow[nd]; b[H.wcp + i] = s->cq_when_can_preempt[nd]; b[H.pref + i] = s->cq_preference[nd];
+        for (int g = s->cq_rg_start[nd]; g < s->cq_rg_start[nd + 1]; g++) {
+          rgmask[lg] = s->rg_res_mask[g]; rgfl[lg] = lf;
+          for (int k = s->rg_flavor_start[g]; k < s->rg_flavor_start[g + 1]; k++) fl[lf++] = s->rg_flavors[k];
+          lg++;
+        }
+      }
+      rgs[nn] = lg; rgfl[lg] = lf;
+      h->tree_blob_off[t + 1] = (int32_t)(base + o);
+      h->max_blob_bytes = std::max(h->max_blob_bytes, (int)o);
+    }
+    if (h->tree_blob.empty()) h->tree_blob.resize(16, 0);
   }
   return KB_OK;
 }
@@ -410,22 +469,50 @@ static int32_t build_dynamic(kb_handle *h, const kb_snapshot *s) {
     h->max_frl_len += (int)h->drain_extra_adm;
     h->max_head_podsets = 1;
     if (h->drain_mode) for (int w = 0; w < s->n_wl; w++) h->max_head_podsets = std::max(h->max_head_podsets, s->wl_ps_start[w + 1] - s->wl_ps_start[w]);
-    for (int i = 0; i < s->n_heads && !h->drain_mode; i++) {
-      int w = s->heads[i];
-      if (w >= 0 && w < s->n_wl) h->max_head_podsets = std::max(h->max_head_podsets, s->wl_ps_start[w + 1] - s->wl_ps_start[w]);
-    }
   }
   // light bounds checks on the hot tables
-  for (int i = 0; i < s->n_heads && !h->drain_mode; i++) if (s->heads[i] < 0 || s->heads[i] >= s->n_wl) return fail(h, KB_ERR_INVALID, "heads out of range");
   for (int w = 0; w < s->n_wl; w++) {
     if (s->wl_cq[w] < 0 || s->wl_cq[w] >= Q) return fail(h, KB_ERR_INVALID, "wl_cq out of range");
     if (s->wl_ps_start[w + 1] < s->wl_ps_start[w]) return fail(h, KB_ERR_INVALID, "wl_ps_start not monotone");
   }
   if (s->n_wl && (s->wl_ps_start[0] != 0 || s->wl_ps_start[s->n_wl] != s->n_podset)) return fail(h, KB_ERR_INVALID, "wl_ps_start must run from 0 to n_podset");
+  // heads: range, most podsets of one entry, one head per ClusterQueue? (fairSharingIterator keeps one entry per CQ,
+  // fair_sharing_iterator.go:52-54) — one pass
+  h->one_head_per_cq = true;
+  if (!h->drain_mode) {
+    h->seen_stamp++;
+    if ((int)h->seen.size() < Q || h->seen_stamp == 0) { h->seen.assign((size_t)std::max(1, Q), 0); h->seen_stamp = 1; }
+    const uint32_t stamp = h->seen_stamp;
+    int maxps = 1; bool dup = false;
+    for (int i = 0; i < s->n_heads; i++) {
+      const int w = s->heads[i];
+      if (w < 0 || w >= s->n_wl) return fail(h, KB_ERR_INVALID, "heads out of range");
+      maxps = std::max(maxps, s->wl_ps_start[w + 1] - s->wl_ps_start[w]);
+      const int c = s->wl_cq[w];
+      if (h->seen[c] == stamp) dup = true;
+      h->seen[c] = stamp;
+    }
+    h->max_head_podsets = std::max(h->max_head_podsets, maxps);
+    if (dup) {
+      if (s->flags & KB_F_FAIR_SHARING) return fail(h, KB_ERR_INVALID, "fair sharing: more than one head for a ClusterQueue");
+      h->one_head_per_cq = false;
+    }
+  }
   if (s->n_adm_use < 0 || (s->n_adm && (s->adm_use_start[0] != 0 || s->adm_use_start[s->n_adm] != s->n_adm_use)))
     return fail(h, KB_ERR_INVALID, "adm_use_start must run from 0 to n_adm_use");
-  for (size_t i = 0; i < (size_t)s->n_podset * s->n_resource; i++)
-    if (s->ps_last_tried[i] < -1) return fail(h, KB_ERR_INVALID, "ps_last_tried below -1");
+  {  // ps_last_tried >= -1 (int8): eight at a time — a byte below -1 has its top bit set and is not 0xff
+    const size_t nb = (size_t)s->n_podset * s->n_resource;
+    const int8_t *lt = s->ps_last_tried;
+    size_t i = 0;
+    bool bad = false;
+    for (; i + 8 <= nb; i += 8) {
+      uint64_t v; memcpy(&v, lt + i, 8);
+      const uint64_t top = v & 0x8080808080808080ull;         // bytes that are negative
+      if (top) { for (int k = 0; k < 8; k++) if (lt[i + k] < -1) bad = true; }
+    }
+    for (; i < nb; i++) if (lt[i] < -1) bad = true;
+    if (bad) return fail(h, KB_ERR_INVALID, "ps_last_tried below -1");
+  }
   if (s->ps_group)  // the podsets of one PodSetGroup are adjacent rows of their workload
     for (int w = 0; w < s->n_wl; w++)
       for (int a = s->wl_ps_start[w]; a < s->wl_ps_start[w + 1]; a++) {
@@ -436,32 +523,29 @@ static int32_t build_dynamic(kb_handle *h, const kb_snapshot *s) {
         for (int c = b; c < s->wl_ps_start[w + 1]; c++)
           if (s->ps_group[c] == g) return fail(h, KB_ERR_INVALID, "ps_group: podsets of one group must be adjacent");
       }
-  h->one_head_per_cq = true;
-  if (!h->drain_mode) {  // fairSharingIterator keeps one entry per CQ (fair_sharing_iterator.go:52-54)
-    std::vector<char> seen(Q, 0);
-    for (int i = 0; i < s->n_heads; i++) {
-      int c = s->wl_cq[s->heads[i]];
-      if (seen[c]) {
-        if (s->flags & KB_F_FAIR_SHARING) return fail(h, KB_ERR_INVALID, "fair sharing: more than one head for a ClusterQueue");
-        h->one_head_per_cq = false;
-        break;
-      }
-      seen[c] = 1;
-    }
-  }
   // warp-per-root admit for cohort-less CQs: only when none of them can ever get preemption targets
   {
     bool any = false;
-    for (int q = 0; q < Q && !any; q++)
-      if (h->s_parent[q] < 0 && h->s_within_cq[q] != KB_POLICY_NEVER && h->cq_adm_start[q + 1] > h->cq_adm_start[q]) any = true;
-    if (h->drain_mode)  // admitted workloads appear during the drain
-      for (int q = 0; q < Q && !any; q++) if (h->s_parent[q] < 0 && h->s_within_cq[q] != KB_POLICY_NEVER) any = true;
+    if (h->s_any_lone_within) {
+      for (int q = 0; q < Q && !any; q++)
+        if (h->s_parent[q] < 0 && h->s_within_cq[q] != KB_POLICY_NEVER && h->cq_adm_start[q + 1] > h->cq_adm_start[q]) any = true;
+      if (h->drain_mode) any = true;  // admitted workloads appear during the drain
+    }
     h->D.lone_fast = !any && s->n_flavor * s->n_resource <= 64;
     // can any ClusterQueue ever have preemption candidates?  (candidates_possible, kb_kernels.cuh)
-    h->preempt_possible = false;
-    for (int q = 0; q < Q && !h->preempt_possible; q++)
-      if (h->s_within_cq[q] != KB_POLICY_NEVER || (h->s_parent[q] >= 0 && h->s_reclaim_within[q] != KB_POLICY_NEVER)) h->preempt_possible = true;
+    h->preempt_possible = h->s_preempt_policy;
   }
+  return KB_OK;
+}
+
+// next stamp of the head records (kb_flat.cuh); the table is cleared when it moved, grew or the 16-bit stamp wrapped
+static int32_t flat_rec_stamp(kb_handle *h) {
+  const size_t n = h->tree_nodes.size() + 1;
+  if (h->rec_seen != (const void *)h->d_cq_rec || h->rec_seen_n != n || h->rec_stamp >= 0xffffu) {
+    CUDA_TRY(h, cudaMemsetAsync(h->d_cq_rec, 0, sizeof(int4) * n, h->stream));
+    h->rec_seen = h->d_cq_rec; h->rec_seen_n = n; h->rec_stamp = 0;
+  }
+  h->D.rec_stamp = ++h->rec_stamp;
   return KB_OK;
 }
 
@@ -503,6 +587,7 @@ static int32_t upload_impl(kb_handle *h, const kb_snapshot *s, bool sync) {
     sneed(h->lone.size(), 4); sneed(N, 4); sneed(h->tree_flat.size(), 1); sneed(N + 1, 4); sneed(h->child_list.size(), 4); sneed(h->root_cq_start.size(), 4);
     sneed(h->sn_node.size(), 4); sneed(h->slot_base.size(), 4); sneed(h->nd_tin.size(), 4); sneed(h->nd_tout.size(), 4);
     sneed(h->cq_path.size(), 4); sneed(h->cq_plen.size(), 4);
+    sneed(h->tree_blob.size(), 1); sneed(h->tree_blob_off.size(), 4);
     if (!h->sarena.reserve(stot + 4096)) return fail(h, KB_ERR_CUDA, "cudaMalloc failed");
     h->sarena.reset();
 #define SUP(field, src, n) CUDA_TRY(h, up(h, h->sarena, D.field, src, (size_t)(n), &bytes))
@@ -524,6 +609,7 @@ static int32_t upload_impl(kb_handle *h, const kb_snapshot *s, bool sync) {
     SUP(sn_node, h->sn_node.data(), h->sn_node.size()); SUP(slot_base, h->slot_base.data(), h->slot_base.size());
     SUP(nd_tin, h->nd_tin.data(), h->nd_tin.size()); SUP(nd_tout, h->nd_tout.data(), h->nd_tout.size());
     SUP(cq_path, h->cq_path.data(), h->cq_path.size()); SUP(cq_plen, h->cq_plen.data(), h->cq_plen.size());
+    SUP(tree_blob, h->tree_blob.data(), h->tree_blob.size()); SUP(tree_blob_off, h->tree_blob_off.data(), h->tree_blob_off.size());
     D.path_stride = h->path_stride;
 #undef SUP
     memcpy(h->s_dims, dims, sizeof(dims));
@@ -588,7 +674,7 @@ static int32_t upload_impl(kb_handle *h, const kb_snapshot *s, bool sync) {
   CUDA_TRY(h, cudaEventRecord(h->ev1, h->stream));
   rc = build_dynamic(h, s);
   if (rc != KB_OK) { cudaStreamSynchronize(h->stream); return rc; }  // the copies read the caller's buffers
-  D.tab_local = 0; D.gparent = D.parent; D.lq = nullptr; D.cq_entry = nullptr;
+  D.tab_local = 0; D.gparent = D.parent; D.lq = nullptr; D.cq_entry = nullptr; D.ent_gid = nullptr; D.node_gid = nullptr; D.local_flat = 0; D.cq_rec = nullptr;
   D.Q = Q; D.C = C; D.N = N; D.F = F; D.R = R; D.FR = FR; D.W = s->n_wl; D.P = s->n_podset; D.A = s->n_adm;
   D.AU = s->n_adm_use; D.H = s->n_heads; D.NRG = s->n_rg; D.pods_res = s->pods_resource; D.flags = s->flags; D.now_ns = s->now_ns;
   int nroots = D.nRoots;
@@ -599,7 +685,7 @@ static int32_t upload_impl(kb_handle *h, const kb_snapshot *s, bool sync) {
   need(W, 4); need(W, 4); need(W, 8); need(W, 8); need(W, 8); need(W + 1, 4);
   need(P * R, 8); need(P, 4); need(P, 4); need(P, 4); need(P, 8); need(P * R, 1);
   need(A, 4); need(A, 4); need(A, 8); need(A, 8); need(A, 8); need(A, 1); need(A + 1, 4); need(AUc, 4); need(AUc, 8);
-  need(H, 4); need(W, 1); need(W, 8); need(P, 4); need(Q, 4);
+  need(H, 4); need(W, 1); need(W, 8); need(P, 4); need(Q, 4); need(h->tree_nodes.size() + 1, 16); need(256, 1);
   need(Q + 1, 4); need(A, 4); need(A, 4); need(Q, 4); need(nroots, 4);
   need(nroots + 2, 4); need(Q + 2, 4); need(A, 8); need(A, 8); need(A, 4); need(A, 4);
   size_t rk_temp_bytes = 0;
@@ -710,7 +796,13 @@ static int32_t upload_impl(kb_handle *h, const kb_snapshot *s, bool sync) {
     h->fused_smem = sm;
     h->fused_on = D.nLone == 0 && D.nTrees > 0 && h->one_head_per_cq && sm <= 220 * 1024 && (A_in == 0 || !h->preempt_possible) &&
                   (!(s->flags & KB_F_FAIR_SHARING) || all_flat) && getenv("KB_NO_FUSED") == nullptr;
-    if (h->fused_on && !h->drain_mode) {
+    // k_cycle_flat: every tree flat, FR <= 64, the relocated copy of the largest root fits shared memory
+    h->d_cq_rec = h->arena.take<int4>(h->tree_nodes.size() + 1); D.cq_rec = h->d_cq_rec;
+    h->flat_rcap = (int)std::min<size_t>((size_t)1 << 20, nnm * (size_t)std::max(1, h->max_head_podsets));
+    h->flat_smem = flat_layout((int)nnm, FR, R, h->flat_rcap, h->max_blob_bytes).total;
+    h->flat_on = h->fused_on && all_flat && FR <= 64 && h->flat_smem <= 227 * 1024 && getenv("KB_FUSED_V1") == nullptr;
+    h->flat_on = h->flat_on && h->max_head_podsets < 65536;
+    if (h->fused_on && !h->flat_on && !h->drain_mode) {
       CUDA_TRY(h, cudaMemsetAsync(h->d_cq_entry, 0xff, sizeof(int32_t) * (size_t)Q, h->stream));
       if (H) k_cq_entry<<<(unsigned)((H + 255) / 256), 256, 0, h->stream>>>(D, h->d_cq_entry);
     }
@@ -742,8 +834,8 @@ static int32_t upload_impl(kb_handle *h, const kb_snapshot *s, bool sync) {
     D.ps_flavor = (int8_t *)(ob + L.off[4]); D.ps_res_mode = (int8_t *)(ob + L.off[5]); D.ps_tried = (int8_t *)(ob + L.off[6]);
     D.ps_count_out = (int32_t *)(ob + L.off[7]);
   }
-  {  // cycle header block, cleared by one memset per cycle: [0] status, [2..3] ps_n / ps_cursor, [4] target pool cursor, [8..23] search counters
-    uint32_t *hdr = h->arena.take<uint32_t>(32);
+  {  // cycle header block, cleared once per cycle: [0] status, [2..3] ps_n / ps_cursor, [4] target pool cursor, [8..23] search counters
+    uint32_t *hdr = (uint32_t *)(h->d_out_block + out_layout(H, P, (size_t)R).hdr);
     D.status = hdr; D.ps_n = (int32_t *)(hdr + 2); D.ps_cursor = D.ps_n + 1; D.tgt_pool_used = (int32_t *)(hdr + 4); D.sstat = (u64 *)(hdr + 8);
   }
   D.ps_list = h->arena.take<int32_t>(H);
@@ -778,9 +870,19 @@ static int32_t upload_impl(kb_handle *h, const kb_snapshot *s, bool sync) {
   }
   h->d_drs_rounded = h->arena.take<i64>(N); h->d_drs_res = h->arena.take<int32_t>(N); h->d_drs_borrowing = h->arena.take<uint8_t>(N);
   if (h->arena.used > h->arena.cap) { cudaStreamSynchronize(h->stream); return fail(h, KB_ERR_CUDA, "device arena accounting"); }
-  // rows of workloads that are not heads stay at -1
-  CUDA_TRY(h, cudaMemsetAsync(D.ps_flavor, 0xff, 3 * pad256(P * R), h->stream));  // flavor, res_mode, tried are adjacent (out_layout)
-  CUDA_TRY(h, cudaMemsetAsync(D.ps_count_out, 0, P * 4, h->stream));
+  h->hdr_clean = false;
+  if (h->flat_on && !h->drain_mode) {  // head records + result-row fills + cleared header: one launch (k_flat_prep)
+    int32_t rc2 = flat_rec_stamp(h);
+    if (rc2 != KB_OK) return rc2;
+    const size_t fill_words = 3 * pad256(P * R) / 4;
+    const size_t nthr = std::max(std::max(H, fill_words), std::max(P, (size_t)32));
+    k_flat_prep<<<(unsigned)((nthr + 255) / 256), 256, 0, h->stream>>>(D, h->d_cq_rec, (int)fill_words, (int)P);
+    h->hdr_clean = true;
+  } else {
+    // rows of workloads that are not heads stay at -1
+    CUDA_TRY(h, cudaMemsetAsync(D.ps_flavor, 0xff, 3 * pad256(P * R), h->stream));  // flavor, res_mode, tried are adjacent (out_layout)
+    CUDA_TRY(h, cudaMemsetAsync(D.ps_count_out, 0, P * 4, h->stream));
+  }
   h->stats.h2d_bytes = bytes;
   h->uploaded = true;
   if (sync) {  // caller buffers may be released after return
@@ -874,14 +976,15 @@ static int32_t launch_admit(kb_handle *h, int *launches) {
   return KB_OK;
 }
 
-static int32_t cycle_enqueue(kb_handle *h) {
+static int32_t cycle_enqueue(kb_handle *h, bool hdr_copy = true) {
   if (!h || !h->uploaded) return fail(h, KB_ERR_INVALID, "kb_upload first");
   cudaSetDevice(h->device);
   DevSnap &D = h->D;
   int launches = 0;
   CUDA_TRY(h, cudaEventRecord(h->ev2, h->stream));
   // cycle header (status word, deferred-entry counters, target pool cursor, search counters): one contiguous block
-  CUDA_TRY(h, cudaMemsetAsync(D.status, 0, 128, h->stream));
+  if (!h->hdr_clean) CUDA_TRY(h, cudaMemsetAsync(D.status, 0, 128, h->stream));  // (k_flat_prep cleared it with the upload)
+  h->hdr_clean = false;
   if (!(h->fused_on && D.H)) CUDA_TRY(h, cudaMemsetAsync(D.root_count, 0, sizeof(int32_t) * (size_t)std::max(1, D.nRoots), h->stream));
   if (D.A) CUDA_TRY(h, cudaMemsetAsync(D.preempted, 0, (size_t)D.A, h->stream));
   h->kev_n = 0;
@@ -916,12 +1019,23 @@ static int32_t cycle_enqueue(kb_handle *h) {
   }
   if (h->fused_on && D.H) {
     if (h->drain_mode) {
-      CUDA_TRY(h, cudaMemsetAsync(h->d_cq_entry, 0xff, sizeof(int32_t) * (size_t)D.Q, h->stream));
-      k_cq_entry<<<(D.H + 255) / 256, 256, 0, h->stream>>>(D, h->d_cq_entry); launches++;
+      if (h->flat_on) {
+        int32_t rc2 = flat_rec_stamp(h);
+        if (rc2 != KB_OK) return rc2;
+        k_cq_rec<<<(D.H + 255) / 256, 256, 0, h->stream>>>(D, h->d_cq_rec); launches++;
+      } else {
+        CUDA_TRY(h, cudaMemsetAsync(h->d_cq_entry, 0xff, sizeof(int32_t) * (size_t)D.Q, h->stream));
+        k_cq_entry<<<(D.H + 255) / 256, 256, 0, h->stream>>>(D, h->d_cq_entry); launches++;
+      }
     }
     kmark(h, KB_K_CYCLE_ROOT);
-    CUDA_TRY(h, cudaFuncSetAttribute(k_cycle_root, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
-    k_cycle_root<<<D.nTrees, KB_ROOT_THREADS, h->fused_smem, h->stream>>>(D); launches++;
+    if (h->flat_on) {
+      if (!h->flat_attr_set) { CUDA_TRY(h, cudaFuncSetAttribute(k_cycle_flat, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); h->flat_attr_set = true; }
+      k_cycle_flat<<<D.nTrees, KB_FLAT_THREADS, h->flat_smem, h->stream>>>(D, flat_layout(h->max_tree_nodes, D.FR, D.R, h->flat_rcap, h->max_blob_bytes)); launches++;
+    } else {
+      CUDA_TRY(h, cudaFuncSetAttribute(k_cycle_root, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+      k_cycle_root<<<D.nTrees, KB_ROOT_THREADS, h->fused_smem, h->stream>>>(D); launches++;
+    }
   } else {
   launch_tree(h, &launches);
   if (D.H) {
@@ -991,9 +1105,10 @@ static int32_t cycle_enqueue(kb_handle *h) {
   if (rc_admit != KB_OK) return rc_admit;
   CUDA_TRY(h, cudaGetLastError());
   h->last_launches = launches;
-  CUDA_TRY(h, cudaMemcpyAsync(&h->host_words[0], D.status, 4, cudaMemcpyDeviceToHost, h->stream));
-  CUDA_TRY(h, cudaMemcpyAsync(&h->host_words[1], D.tgt_pool_used, 4, cudaMemcpyDeviceToHost, h->stream));
-  CUDA_TRY(h, cudaMemcpyAsync(&h->host_words[16], D.sstat, 64, cudaMemcpyDeviceToHost, h->stream));
+  // the cycle header (status word, counters, search / phase statistics: 128 contiguous bytes) comes back with one copy —
+  // or, when the caller's result block has the canonical layout, inside the block's own copy (download_enqueue)
+  h->hdr_host = &h->host_words[32];
+  if (hdr_copy) CUDA_TRY(h, cudaMemcpyAsync(&h->host_words[32], D.status, 128, cudaMemcpyDeviceToHost, h->stream));
   return KB_OK;
 }
 
@@ -1007,8 +1122,8 @@ static int32_t cycle_finish(kb_handle *h) {
     float kms = 0; cudaEventElapsedTime(&kms, h->kev[i], h->kev[i + 1]);
     if (h->kev_id[i] >= 0) h->stats.kernel_ms[h->kev_id[i]] += kms;
   }
-  memcpy(h->stats.search_stat, &h->host_words[16], 64);
-  uint32_t st = h->host_words[0];
+  memcpy(h->stats.search_stat, h->hdr_host + 8, 64);
+  uint32_t st = h->hdr_host[0];
   if (st & KBS_UNSUPPORTED_PREEMPTION) return fail(h, KB_ERR_UNSUPPORTED, "unsupported preemption configuration");
   if (st & KBS_TARGET_OVERFLOW) return fail(h, KB_ERR_CAPACITY, "per-entry usage cell / target pool capacity exceeded");
   if (st & KBS_INTERNAL_LOOP) return fail(h, KB_ERR_CUDA, "internal: iteration guard tripped in the target search");
@@ -1030,6 +1145,24 @@ __global__ void k_tgt_compact(DevSnap D, const int32_t *start, int32_t *adm, uin
   for (int k = 0; k < n; k++) { adm[s + k] = D.tgt_pool_adm[o + k]; reason[s + k] = D.tgt_pool_reason[o + k]; }
 }
 
+// a kb_alloc_cycle_out block of this cycle's dimensions, pointers untouched: its tables have the device block's layout
+static bool out_is_canonical_block(kb_handle *h, const kb_cycle_out *out) {
+  const DevSnap &D = h->D;
+  const size_t H = D.H;
+  if (!out || !out->decision || !H) return false;
+  OutLayout L = out_layout(H, (size_t)D.P, (size_t)D.R);
+  const char *b = (const char *)out->decision;
+  bool ok;
+  {
+    std::lock_guard<std::mutex> lk(g_pin_mu);
+    auto it = g_out_blocks.find((uintptr_t)b);
+    ok = it != g_out_blocks.end() && it->second.H == H && it->second.P == (size_t)D.P && it->second.R == (size_t)D.R;
+  }
+  return ok && (const char *)out->mode == b + L.off[1] && (const char *)out->borrow == b + L.off[2] && (const char *)out->commit_rank == b + L.off[3] &&
+         (const char *)out->ps_flavor == b + L.off[4] && (const char *)out->ps_res_mode == b + L.off[5] && (const char *)out->ps_tried_idx == b + L.off[6] &&
+         (const char *)out->ps_count == b + L.off[7];
+}
+
 static int32_t download_enqueue(kb_handle *h, kb_cycle_out *out) {
   if (!h || !h->uploaded || !out) return fail(h, KB_ERR_INVALID, "nothing to download");
   cudaSetDevice(h->device);
@@ -1038,19 +1171,11 @@ static int32_t download_enqueue(kb_handle *h, kb_cycle_out *out) {
   int64_t bytes = 0;
   CUDA_TRY(h, cudaEventRecord(h->ev4, h->stream));
 #define DOWN(dst, src, n, T) if (out->dst && (n)) { CUDA_TRY(h, cudaMemcpyAsync(out->dst, D.src, (n) * sizeof(T), cudaMemcpyDeviceToHost, h->stream)); bytes += (n) * sizeof(T); }
-  bool one_dma = false;
-  if (out->decision && H) {  // a kb_alloc_cycle_out block of these dimensions, pointers untouched
+  const bool one_dma = out_is_canonical_block(h, out);
+  if (one_dma) {  // the eight result tables and the cycle header: one copy
     OutLayout L = out_layout(H, (size_t)D.P, (size_t)D.R);
-    char *b = (char *)out->decision;
-    {
-      std::lock_guard<std::mutex> lk(g_pin_mu);
-      auto it = g_out_blocks.find((uintptr_t)b);
-      one_dma = it != g_out_blocks.end() && it->second.H == H && it->second.P == (size_t)D.P && it->second.R == (size_t)D.R;
-    }
-    one_dma = one_dma && (char *)out->mode == b + L.off[1] && (char *)out->borrow == b + L.off[2] && (char *)out->commit_rank == b + L.off[3] &&
-              (char *)out->ps_flavor == b + L.off[4] && (char *)out->ps_res_mode == b + L.off[5] && (char *)out->ps_tried_idx == b + L.off[6] &&
-              (char *)out->ps_count == b + L.off[7];
-    if (one_dma) { CUDA_TRY(h, cudaMemcpyAsync(b, h->d_out_block, L.prefix, cudaMemcpyDeviceToHost, h->stream)); bytes += (int64_t)L.prefix; }
+    CUDA_TRY(h, cudaMemcpyAsync(out->decision, h->d_out_block, L.prefix, cudaMemcpyDeviceToHost, h->stream)); bytes += (int64_t)L.prefix;
+    h->hdr_host = (const uint32_t *)((const char *)out->decision + L.hdr);
   }
   if (!one_dma) {
     DOWN(decision, decision, H, uint8_t); DOWN(mode, mode, H, uint8_t); DOWN(borrow, borrow, H, int32_t); DOWN(commit_rank, rank, H, int32_t);
@@ -1101,7 +1226,6 @@ extern "C" int32_t kb_download(kb_handle *h, kb_cycle_out *out) {
   int32_t rc = download_enqueue(h, out);
   if (rc != KB_OK) return rc;
   // the target count of the last cycle is re-read here in case kb_cycle_resident ran several times
-  CUDA_TRY(h, cudaMemcpyAsync(&h->host_words[1], h->D.tgt_pool_used, 4, cudaMemcpyDeviceToHost, h->stream));
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
   return download_finish(h, out);
 }
@@ -1114,7 +1238,7 @@ extern "C" int32_t kb_run_cycle(kb_handle *h, const kb_snapshot *s, kb_cycle_out
   int32_t rc = upload_impl(h, s, false);
   if (rc != KB_OK) return rc;
   if (trace) t1 = now();
-  rc = cycle_enqueue(h);
+  rc = cycle_enqueue(h, !out_is_canonical_block(h, out));
   if (rc != KB_OK) return rc;
   if (trace) t2 = now();
   rc = download_enqueue(h, out);

@@ -78,6 +78,15 @@ struct DevSnap {
   const uint8_t *wl_has_qr;    // optional (nullptr = absent): workload.HasQuotaReservation
   const i64 *wl_sched_hash;    // optional: scheduling equivalence class, 0 = unknown (drain only)
   const int32_t *ps_group;     // optional: PodSetGroup id per podset, -1 = none (members adjacent)
+  // ---- relocated per-root view (k_cycle_flat, tab_local == 2): every id (workload, entry, podset row, ClusterQueue,
+  // resource group) is LOCAL to one root cohort and all tables above point into shared memory.  These map back.
+  const int32_t *ent_gid;      // [entries of the root] global entry index (iterator tie-break), nullptr otherwise
+  const int32_t *node_gid;     // [nodes of the root] global node id, nullptr otherwise
+  int local_flat;              // tree_flat of the root the local view belongs to
+  // static per-tree tables in local numbering (one contiguous block per tree, built by the host at static upload)
+  const unsigned char *tree_blob; const int32_t *tree_blob_off;  // [nTrees+1] byte offsets
+  const int4 *cq_rec;          // [tree_start[nTrees]] head record per tree node (kb_flat.cuh: cq_rec_write), valid when stamped rec_stamp
+  unsigned rec_stamp;
   // ---- derived, static per topology (host-built at upload) ----
   const int32_t *root_slot;   // [N] dense index of the node's root among all roots
   const int32_t *depth;       // [N] distance to the root
@@ -176,7 +185,7 @@ __device__ __forceinline__ i64 local_quota(i64 subtree, i64 lend_limit) {
 
 // FindHeightOfLowestSubtreeThatFits hierarchical_preemption.go:214-227, on the
 // cycle-start usage.  Returns the borrow height; *may_reclaim = second result.
-__device__ __forceinline__ int nix(const DevSnap &D, int node) { return D.tab_local ? D.local_idx[node] : node; }
+__device__ __forceinline__ int nix(const DevSnap &D, int node) { return D.tab_local == 1 ? D.local_idx[node] : node; }
 __device__ __forceinline__ i64 lq_of(const DevSnap &D, size_t c) { return D.lq ? D.lq[c] : local_quota(D.subtree[c], D.llimit[c]); }
 __device__ inline int find_height(const DevSnap &D, const i64 *usage, int cq, int fr, i64 val, bool *may_reclaim) {
   int FR = D.FR;

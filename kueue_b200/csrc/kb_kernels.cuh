@@ -180,6 +180,7 @@ __device__ __forceinline__ i64 ps_request(const DevSnap &D, int row, int r, int 
 // != Never and another CQ of the root has admitted workloads.)  When not, getTargets returns
 // nil and SimulatePreemption returns NoCandidates without any search.
 __device__ __forceinline__ bool candidates_possible(const DevSnap &D, int cq) {
+  if (D.tab_local == 2) return false;  // the relocated view only exists for cycles in which no ClusterQueue can have candidates
   int own_n = D.cq_adm_start[cq + 1] - D.cq_adm_start[cq];
   if (D.cq_within_cq[cq] != KB_POLICY_NEVER && own_n > 0) return true;
   if (D.gparent[cq] >= 0 && D.cq_reclaim_within[cq] != KB_POLICY_NEVER) {
@@ -1147,53 +1148,68 @@ __device__ __forceinline__ i64 entry_request_early(const DevSnap &D, int e, int 
 //   ClusterQueue would have with its entry admitted depends only on its own usage, which no other pop changes,
 //   so the tournament's pop sequence (fair_sharing_iterator.go:120-199) is the order of
 //   [requiresBorrowing, zeroWeightBorrows | share hi] [share lo | priority desc] [timestamp] [cq index].
-__device__ inline void compute_entry_key(const DevSnap &D, int e, u64 *k) {
-  int wl = D.heads[e];
-  int cq = D.wl_cq[wl];
+// One term of dominantResourceShare(cq) with the entry's usage added (computeDRS fair_sharing_iterator.go:206-229):
+// borrowed[r] * 1000 / lendable[r] (fair_sharing.go:126-156), 0 when nothing is borrowed or lendable.
+// borrowed[r] = sum_f max(0, usage + q - SubtreeQuota); only the cells the entry is assigned to differ from the
+// ClusterQueue's own over-usage, which k_fair_prep precomputed per (cq, resource) together with lendable[r].
+__device__ inline double entry_share_ratio(const DevSnap &D, int e, int r) {
+  const int wl = D.heads[e];
+  const int cq = D.wl_cq[wl];
+  const int hq = nix(D, cq);
+  const int P = D.parent[hq];
+  const int R = D.R, FR = D.FR;
+  const bool covers_pods = D.pods_res >= 0 && rg_by_resource(D, cq, D.pods_res) >= 0;
+  i64 b = D.fs_over[(size_t)hq * R + r];
+  // flavors this entry uses for resource r (aggregated over its podsets)
+  const int ps0 = D.wl_ps_start[wl], ps1 = D.wl_ps_start[wl + 1];
+  for (int row = ps0; row < ps1; row++) {
+    const int f = D.ps_flavor[(size_t)row * R + r];
+    if (f < 0) continue;
+    bool first = true;  // count each (f, r) cell once, with the summed request of all podsets on it
+    for (int prow = ps0; prow < row; prow++) if (D.ps_flavor[(size_t)prow * R + r] == f) first = false;
+    if (!first) continue;
+    i64 q = 0;
+    for (int prow = row; prow < ps1; prow++)
+      if (D.ps_flavor[(size_t)prow * R + r] == f) q += ps_request(D, prow, r, D.ps_count_out[prow], covers_pods);
+    const size_t c = (size_t)hq * FR + (size_t)f * R + r;
+    const i64 base = D.usage[c] - D.subtree[c];
+    b += imax(0, base + (q > 0 ? q : 0)) - imax(0, base);
+  }
+  const i64 lend = D.fs_lend[(size_t)P * R + r];
+  return (b > 0 && lend > 0) ? (double)b * 1000.0 / (double)lend : 0.0;
+}
+// Is the entry ordered by the flat-cohort fair-sharing key (else: the classical key)?
+__device__ __forceinline__ bool entry_key_is_fair_flat(const DevSnap &D, int e) {
+  const int cq = D.wl_cq[D.heads[e]];
+  const int P = D.parent[nix(D, cq)];
+  return (D.flags & KB_F_FAIR_SHARING) && P >= 0 && (D.tab_local == 2 ? D.local_flat != 0 : D.tree_flat[D.root_slot[cq] - D.nLone] != 0);
+}
+// The 4 x u64 key; `best` = max over the resources of entry_share_ratio (only read on the fair flat path).
+__device__ inline void entry_key_finish(const DevSnap &D, int e, bool fair_flat, double best, u64 *k) {
+  const int wl = D.heads[e];
+  const int cq = D.wl_cq[wl];
   unsigned prio = 0;
   if (D.flags & KB_F_PRIORITY_SORTING_WITHIN_COHORT) prio = ~((unsigned)D.wl_priority[wl] ^ 0x80000000u);  // signed priority, descending
-  u64 ts = (u64)D.wl_ts[wl] ^ 0x8000000000000000ull;
-  const int hq = nix(D, cq);
-  int P = D.parent[hq];
-  bool fair_flat = (D.flags & KB_F_FAIR_SHARING) && P >= 0 && D.tree_flat[D.root_slot[cq] - D.nLone];
+  const u64 ts = (u64)D.wl_ts[wl] ^ 0x8000000000000000ull;
   if (!fair_flat) {
     // workloads that already hold a quota reservation (second pass) first: scheduler.go:781-789
-    u64 no_qr = (D.wl_has_qr && D.wl_has_qr[wl]) ? 0ull : 1ull;
-    k[0] = (no_qr << 63) | ((u64)(unsigned)D.borrow[e] << 32) | prio; k[1] = ts; k[2] = (u64)(unsigned)e; k[3] = 0;
+    const u64 no_qr = (D.wl_has_qr && D.wl_has_qr[wl]) ? 0ull : 1ull;
+    k[0] = (no_qr << 63) | ((u64)(unsigned)D.borrow[e] << 32) | prio; k[1] = ts; k[2] = (u64)(unsigned)(D.ent_gid ? D.ent_gid[e] : e); k[3] = 0;
     return;
   }
-  // dominantResourceShare(cq) with the entry's usage added (computeDRS fair_sharing_iterator.go:206-229).
-  // borrowed[r] = sum_f max(0, usage + q - SubtreeQuota); only the cells the entry is assigned to differ from the
-  // ClusterQueue's own over-usage, which k_fair_prep precomputed per (cq, resource) together with lendable[r].
-  const int R = D.R, FR = D.FR;
-  bool covers_pods = D.pods_res >= 0 && rg_by_resource(D, cq, D.pods_res) >= 0;
+  const double w = D.fair_weight[cq];
+  const bool zwb = w == 0 && best != 0;
+  const double value = zwb ? best : (best == 0 ? 0.0 : best / w);
+  const u64 vb = (u64)__double_as_longlong(value);  // value >= 0: the bit pattern is monotone
+  const u64 flags = ((D.flags & KB_F_FS_PRIORITIZE_NON_BORROWING) && D.borrow[e] > 0 ? 2 : 0) | (zwb ? 1 : 0);
+  k[0] = (flags << 32) | (vb >> 32); k[1] = (vb << 32) | prio; k[2] = ts; k[3] = (u64)(unsigned)(D.node_gid ? D.node_gid[cq] : cq);
+}
+__device__ inline void compute_entry_key(const DevSnap &D, int e, u64 *k) {
+  const bool fair_flat = entry_key_is_fair_flat(D, e);
   double best = 0.0;
-  for (int r = 0; r < R; r++) {
-    i64 b = D.fs_over[(size_t)hq * R + r];
-    // flavors this entry uses for resource r (aggregated over its podsets)
-    int ps0 = D.wl_ps_start[wl], ps1 = D.wl_ps_start[wl + 1];
-    for (int row = ps0; row < ps1; row++) {
-      int f = D.ps_flavor[(size_t)row * R + r];
-      if (f < 0) continue;
-      bool first = true;  // count each (f, r) cell once, with the summed request of all podsets on it
-      for (int prow = ps0; prow < row; prow++) if (D.ps_flavor[(size_t)prow * R + r] == f) first = false;
-      if (!first) continue;
-      i64 q = 0;
-      for (int prow = row; prow < ps1; prow++)
-        if (D.ps_flavor[(size_t)prow * R + r] == f) q += ps_request(D, prow, r, D.ps_count_out[prow], covers_pods);
-      size_t c = (size_t)hq * FR + (size_t)f * R + r;
-      i64 base = D.usage[c] - D.subtree[c];
-      b += imax(0, base + (q > 0 ? q : 0)) - imax(0, base);
-    }
-    i64 lend = D.fs_lend[(size_t)P * R + r];
-    if (b > 0 && lend > 0) { double ratio = (double)b * 1000.0 / (double)lend; if (ratio > best) best = ratio; }
-  }
-  double w = D.fair_weight[cq];
-  bool zwb = w == 0 && best != 0;
-  double value = zwb ? best : (best == 0 ? 0.0 : best / w);
-  u64 vb = (u64)__double_as_longlong(value);  // value >= 0: the bit pattern is monotone
-  u64 flags = ((D.flags & KB_F_FS_PRIORITIZE_NON_BORROWING) && D.borrow[e] > 0 ? 2 : 0) | (zwb ? 1 : 0);
-  k[0] = (flags << 32) | (vb >> 32); k[1] = (vb << 32) | prio; k[2] = ts; k[3] = (u64)(unsigned)cq;
+  if (fair_flat)
+    for (int r = 0; r < D.R; r++) { const double ratio = entry_share_ratio(D, e, r); if (ratio > best) best = ratio; }
+  entry_key_finish(D, e, fair_flat, best, k);
 }
 __device__ __forceinline__ bool key4_less(const u64 *a, const u64 *b) {
   if (a[0] != b[0]) return a[0] < b[0];
@@ -2059,7 +2075,9 @@ __global__ void __launch_bounds__(KB_ADMIT_THREADS) k_admit(DevSnap D, int slot_
 // one head, the tables of the largest tree fit shared memory, and fair sharing only meets flat cohorts.
 // All node tables are indexed by the local handle (DevSnap::tab_local).
 // ---------------------------------------------------------------------------
+#ifndef KB_ROOT_THREADS
 #define KB_ROOT_THREADS 1024
+#endif
 __global__ void __launch_bounds__(KB_ROOT_THREADS) k_cycle_root(DevSnap D) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int FR = D.FR, R = D.R, Fn = D.F;
@@ -2718,3 +2736,5 @@ __global__ void __launch_bounds__(128) k_admit_fair(DevSnap D, int slot_base, in
   }
   publish_usage<kSmemTables>(D, T, nodes, nn);
 }
+
+#include "kb_flat.cuh"

@@ -436,3 +436,28 @@ def test_reference_last_scheduling_context_two_cycles(ev, name):
     outs = check(DOC["cases"][name], ev.run_cycle)
     for snap, got in outs:
         assert_cycle_equal(got, oracle.run_cycle(snap))
+
+
+def _with_qr(snap, seed=11):
+    rng = np.random.default_rng(seed)
+    snap.set("wl_has_quota_reservation", (rng.random(snap.n_wl) < 0.3).astype(np.uint8))
+    return snap.finalize() if hasattr(snap, "finalize") else snap
+
+
+@pytest.mark.parametrize("v1", [False, True], ids=["k_cycle_flat", "k_cycle_root"])
+@pytest.mark.parametrize("make", [
+    lambda: synth.make_snapshot(3, W=900, Q=90, F=3, R=3, heads="one_per_cq"),                             # FR = 9: odd rows, columns not aligned to the CTA
+    lambda: synth.make_snapshot(3, W=3000, Q=300, heads="one_per_cq", podsets_max=3, partial=True),        # PodSetReducer on the relocated tables
+    lambda: _grouped(synth.make_snapshot(3, W=3000, Q=300, heads="one_per_cq", podsets_max=3)),            # PodSetGroup units
+    lambda: synth.make_snapshot(3, W=1200, Q=120, F=16, R=4, heads="one_per_cq"),                          # FR = 64
+    lambda: _classical(_with_qr(synth.make_snapshot(3, W=3000, Q=300, heads="one_per_cq"))),               # HasQuotaReservation key
+    lambda: _classical(synth.make_snapshot(3, W=2000, Q=200, F=2, R=2, heads="one_per_cq")),               # FR = 4: rows shorter than a warp
+    lambda: synth.make_snapshot(3, W=30, Q=3, heads="one_per_cq"),                                         # one tiny root
+])
+def test_fused_flat_kernels(ev, monkeypatch, make, v1):
+    """Both fused per-root kernels on flat cohorts: k_cycle_flat (kb_flat.cuh, the relocated per-root snapshot in shared
+    memory) and k_cycle_root (KB_FUSED_V1: the kernel it falls back to when the relocated copy does not fit)."""
+    if v1:
+        monkeypatch.setenv("KB_FUSED_V1", "1")
+    snap = make()
+    assert_cycle_equal(ev.run_cycle(snap), oracle.run_cycle(snap))
