@@ -511,6 +511,36 @@ def main():
     st = ev.stats()
     h2d, d2h = int(st.h2d_bytes), int(st.d2h_bytes)
 
+    # ---- the same with incremental usage (kb_snapshot.usage_delta_*): the usage table stays on the device and
+    # every step carries only the rows of the ClusterQueues that admitted a workload in this cycle (the rows the cache
+    # would have touched); their values are unchanged, so every step still evaluates the same snapshot.  Reported next to
+    # `e2e` (which keeps moving the whole table), never instead of it.
+    inc_line = None
+    if world == 1 and args.config == 3:
+        import copy
+        admitted = np.flatnonzero(np.asarray(out.decision) == 5)  # KB_DEC_ASSUMED
+        dirty = np.unique(np.asarray(snap.wl_cq)[np.asarray(snap.heads)[admitted]]).astype(np.int32)
+        usage = np.asarray(snap.cq_usage).reshape(snap.n_cq, snap.n_fr)
+        seed = copy.copy(snap); seed.arrays = dict(snap.arrays); seed._struct = None
+        seed.flags = snap.flags | abi.F_USAGE_RESIDENT
+        ev.run_cycle(seed, out)  # leaves the table resident (same static_generation)
+        inc = abi.FlatSnapshot(n_cq=snap.n_cq, n_cohort=snap.n_cohort, n_flavor=snap.n_flavor, n_resource=snap.n_resource,
+                               pods_resource=snap.pods_resource, flags=snap.flags, now_ns=snap.now_ns)
+        inc.arrays = {k: v for k, v in snap.arrays.items() if k != "cq_usage"}
+        inc.arrays["cq_usage"] = np.zeros(0, np.int64)
+        inc.set("usage_delta_cq", dirty); inc.set("usage_delta_rows", usage[dirty])
+        inc = native.pin_snapshot(inc); inc.static_generation = snap.static_generation
+        for _ in range(2):
+            ev.run_cycle(inc, out)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            ev.run_cycle(inc, out)
+        inc_s = time.perf_counter() - t0
+        sti = ev.stats()
+        inc_line = {"value": snap.n_heads * args.steps / inc_s, "unit": UNIT, "h2d_bytes_per_step": int(sti.h2d_bytes), "d2h_bytes_per_step": int(sti.d2h_bytes),
+                    "usage_rows_per_step": int(len(dirty)), "of_rows": int(snap.n_cq),
+                    "what": "kb_snapshot.usage_delta_*: rows of the ClusterQueues that admitted in this cycle; the rest of the usage table stays on the device"}
+
     t = torch.tensor([dev_ms, e2e_s, float(snap.n_heads)], dtype=torch.float64, device="cuda")
     if world > 1:
         tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -566,6 +596,8 @@ def main():
                          "algorithmic_bytes_per_launch": kbytes, "kernel_ms": top_ms,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)"},
         }
+        if inc_line:
+            line["e2e_incremental"] = inc_line
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(snap)
         if world == 1 and args.config in (2, 3) and not args.no_drain:

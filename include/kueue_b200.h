@@ -91,9 +91,12 @@ enum {
   KB_F_FS_STRATEGY_S2A = 1u << 6,              /* LessThanOrEqualToFinalShare configured (strategy.go) */
   KB_F_FS_STRATEGY_S2B = 1u << 7,              /* LessThanInitialShare configured                      */
   KB_F_FS_STRATEGY_S2B_FIRST = 1u << 8,        /* strategies = [S2-b, ...] instead of [S2-a, S2-b]     */
-  KB_F_TS_PREEMPTION_BUFFER = 1u << 9          /* features.SchedulerTimestampPreemptionBuffer (alpha, default off):
+  KB_F_TS_PREEMPTION_BUFFER = 1u << 9,         /* features.SchedulerTimestampPreemptionBuffer (alpha, default off):
                                                   LowerOrNewerEqualPriority needs the candidate > 5 min newer
                                                   (preemption_policy.go:28,44-46)                       */
+  KB_F_USAGE_RESIDENT = 1u << 16               /* upload hint, not a scheduler setting: keep this call's cq_usage table on
+                                                  the device so that following calls may pass only the rows that changed
+                                                  (kb_snapshot.usage_delta_*)                            */
 };
 #define KB_FLAGS_DEFAULT (KB_F_PARTIAL_ADMISSION | KB_F_FLAVOR_FUNGIBILITY | \
   KB_F_PRIORITY_SORTING_WITHIN_COHORT | KB_F_FS_PRIORITIZE_NON_BORROWING |   \
@@ -202,6 +205,17 @@ typedef struct kb_snapshot {
                                   device copies and the cohort topology derived from them are reused.  The Go
                                   shim bumps it whenever a ClusterQueue / Cohort spec changes (the event that
                                   increments AllocatableResourceGeneration, clusterqueue_snapshot.go:51-53). */
+
+  /* ---- incremental usage (optional).  The scheduler cache knows which ClusterQueues' usage changed
+     since the previous cycle (admissions it issued: cache.go:619-711 AddOrUpdateWorkload / DeleteWorkload; finished
+     workloads).  When usage_delta_cq != NULL the library takes the usage table it kept from the previous call on this
+     handle (that call, or an earlier one in an unbroken sequence of delta calls, carried KB_F_USAGE_RESIDENT and the
+     full cq_usage), replaces the listed rows and evaluates the cycle on the result; cq_usage is not read and may be
+     NULL.  Requires the static tables of that call (same non-zero static_generation and dimensions); otherwise
+     KB_ERR_INVALID.  Not available for kb_run_drain. ---- */
+  int32_t n_usage_delta;            /* rows in the two tables below                                   */
+  const int32_t *usage_delta_cq;    /* [n_usage_delta] ClusterQueue index, each at most once; NULL = cq_usage is the full table */
+  const int64_t *usage_delta_rows;  /* [n_usage_delta][F*R] the rows' new values (same layout as a cq_usage row) */
 } kb_snapshot;
 
 /* ------------------------------------------------------------------------

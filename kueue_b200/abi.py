@@ -38,6 +38,7 @@ F_FS_PREEMPT_WITHIN_NOMINAL = 1 << 5
 F_FS_STRATEGY_S2A = 1 << 6
 F_FS_STRATEGY_S2B = 1 << 7
 F_FS_STRATEGY_S2B_FIRST = 1 << 8
+F_USAGE_RESIDENT = 1 << 16  # upload hint: keep cq_usage on the device, usage_delta_* may follow (include/kueue_b200.h)
 FLAGS_DEFAULT = (F_PARTIAL_ADMISSION | F_FLAVOR_FUNGIBILITY | F_PRIORITY_SORTING_WITHIN_COHORT |
                  F_FS_PRIORITIZE_NON_BORROWING | F_FS_PREEMPT_WITHIN_NOMINAL | F_FS_STRATEGY_S2A | F_FS_STRATEGY_S2B)
 
@@ -71,6 +72,7 @@ class kb_snapshot(C.Structure):
         ("heads", _P(C.c_int32)),
         ("wl_has_quota_reservation", _P(C.c_uint8)), ("wl_sched_hash", _P(C.c_int64)), ("ps_group", _P(C.c_int32)),
         ("static_generation", C.c_int64),
+        ("n_usage_delta", C.c_int32), ("usage_delta_cq", _P(C.c_int32)), ("usage_delta_rows", _P(C.c_int64)),
     ]
 
 
@@ -161,8 +163,9 @@ _DT = {
     "adm_evicted": np.uint8, "adm_use_start": np.int32, "adm_use_fr": np.int32, "adm_use_qty": np.int64,
     "heads": np.int32,
     "wl_has_quota_reservation": np.uint8, "wl_sched_hash": np.int64, "ps_group": np.int32,
+    "usage_delta_cq": np.int32, "usage_delta_rows": np.int64,
 }
-OPTIONAL_FIELDS = ("wl_has_quota_reservation", "wl_sched_hash", "ps_group")  # NULL in kb_snapshot when absent
+OPTIONAL_FIELDS = ("wl_has_quota_reservation", "wl_sched_hash", "ps_group", "usage_delta_cq", "usage_delta_rows")  # NULL in kb_snapshot when absent
 ARRAY_FIELDS = list(_DT.keys())
 # tables the library keeps resident while kb_snapshot.static_generation is unchanged (include/kueue_b200.h)
 STATIC_FIELDS = ("parent", "fair_weight", "nominal", "borrow_limit", "lend_limit", "cq_within_cq", "cq_reclaim_within",
@@ -287,6 +290,7 @@ class FlatSnapshot:
         s.n_cq, s.n_cohort, s.n_flavor, s.n_resource = self.n_cq, self.n_cohort, self.n_flavor, self.n_resource
         s.n_rg, s.n_wl, s.n_podset, s.n_adm = self.n_rg, self.n_wl, self.n_podset, self.n_adm
         s.n_adm_use = len(self.arrays["adm_use_fr"])
+        s.n_usage_delta = len(self.arrays["usage_delta_cq"]) if "usage_delta_cq" in self.arrays else 0
         s.n_heads = self.n_heads
         s.pods_resource, s.flags, s.now_ns = self.pods_resource, self.flags, self.now_ns
         s.static_generation = self.static_generation

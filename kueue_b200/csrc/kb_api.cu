@@ -92,6 +92,9 @@ struct kb_handle {
   bool fused_on = false; size_t fused_smem = 0; bool one_head_per_cq = false; int32_t *d_cq_entry = nullptr;
   // k_cycle_flat (kb_flat.cuh): static per-tree blocks in local numbering, head records per tree node
   std::vector<unsigned char> tree_blob; std::vector<int32_t> tree_blob_off; int max_blob_bytes = 16;
+  // incremental usage (kb_snapshot.usage_delta_*): the ClusterQueue usage table kept between calls
+  i64 *d_usage_res = nullptr; size_t usage_res_cells = 0; bool usage_res_valid = false; int64_t usage_res_gen = 0;
+  std::vector<uint32_t> delta_seen; uint32_t delta_stamp = 0;
   bool flat_on = false, flat_attr_set = false, hdr_clean = false; unsigned rec_stamp = 0; const void *rec_seen = nullptr; size_t rec_seen_n = 0; size_t flat_smem = 0; int flat_rcap = 1; int4 *d_cq_rec = nullptr;
   bool sg_on = false; int sg_wpb = 1, sg_grid = 1, sg_ncap = 1; size_t sg_smem = 0;  // grouped form of k_search_cells
   // device ranking of the admitted workloads (kb_rank.cuh)
@@ -211,6 +214,7 @@ void kb_destroy(kb_handle *h) {
   if (h->sarena.base) cudaFree(h->sarena.base);
   if (h->iarena.base) cudaFree(h->iarena.base);
   if (h->drain_buf) cudaFree(h->drain_buf);
+  if (h->d_usage_res) cudaFree(h->d_usage_res);
   if (h->tas_buf) cudaFree(h->tas_buf);
   if (h->ev_d) cudaEventDestroy(h->ev_d);
   if (h->host_words) cudaFreeHost(h->host_words);
@@ -549,6 +553,13 @@ static int32_t flat_rec_stamp(kb_handle *h) {
   return KB_OK;
 }
 
+// rows of the resident usage table replaced by the caller's deltas (kb_snapshot.usage_delta_*)
+__global__ void k_usage_patch(i64 *usage, const int32_t *cq, const i64 *rows, int n, int FR) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * FR) return;
+  usage[(size_t)cq[i / FR] * FR + i % FR] = rows[i];
+}
+
 template <typename T>
 static cudaError_t up(kb_handle *h, Arena &arena, const T *&dst, const T *src, size_t n, int64_t *bytes) {
   T *d = arena.take<T>(n);
@@ -624,7 +635,37 @@ static int32_t upload_impl(kb_handle *h, const kb_snapshot *s, bool sync) {
   std::vector<Tab> tabs;
 #define UPC(field, src, n, capn) tabs.push_back(Tab{(const void *)(src), (size_t)(n) * sizeof(*D.field), (const void **)&D.field, (size_t)(capn) * sizeof(*D.field)})
 #define UP(field, src, n) UPC(field, src, n, n)
-  UP(cq_usage, (const i64 *)s->cq_usage, (size_t)Q * FR);
+  // ClusterQueue usage: the full table with the other per-cycle tables | into the resident buffer (KB_F_USAGE_RESIDENT)
+  // | the resident buffer patched with the caller's rows (usage_delta_*)
+  const bool delta = s->usage_delta_cq != nullptr;
+  const bool keep_usage = (s->flags & KB_F_USAGE_RESIDENT) != 0 && !h->drain_mode;
+  const int32_t *d_delta_cq = nullptr; const i64 *d_delta_rows = nullptr;
+  if (delta) {
+    if (h->drain_mode) return fail(h, KB_ERR_INVALID, "usage deltas are not available for kb_run_drain");
+    if (!reuse || !h->usage_res_valid || h->usage_res_gen != s->static_generation || h->usage_res_cells != (size_t)Q * FR)
+      return fail(h, KB_ERR_INVALID, "usage_delta_*: no resident usage table of this static_generation (pass cq_usage with KB_F_USAGE_RESIDENT first)");
+    if (s->n_usage_delta < 0 || (s->n_usage_delta > 0 && !s->usage_delta_rows)) return fail(h, KB_ERR_INVALID, "usage_delta_*: bad count / null rows");
+    h->delta_stamp++;
+    if ((int)h->delta_seen.size() < Q || h->delta_stamp == 0) { h->delta_seen.assign((size_t)std::max(1, Q), 0); h->delta_stamp = 1; }
+    for (int i = 0; i < s->n_usage_delta; i++) {
+      const int c = s->usage_delta_cq[i];
+      if (c < 0 || c >= Q) return fail(h, KB_ERR_INVALID, "usage_delta_cq out of range");
+      if (h->delta_seen[c] == h->delta_stamp) return fail(h, KB_ERR_INVALID, "usage_delta_cq lists a ClusterQueue twice");
+      h->delta_seen[c] = h->delta_stamp;
+    }
+    tabs.push_back(Tab{(const void *)s->usage_delta_cq, (size_t)s->n_usage_delta * 4, (const void **)&d_delta_cq, (size_t)s->n_usage_delta * 4});
+    tabs.push_back(Tab{(const void *)s->usage_delta_rows, (size_t)s->n_usage_delta * FR * 8, (const void **)&d_delta_rows, (size_t)s->n_usage_delta * FR * 8});
+  } else if (keep_usage) {
+    if (h->usage_res_cells != (size_t)Q * FR || !h->d_usage_res) {
+      if (h->d_usage_res) cudaFree(h->d_usage_res);
+      h->d_usage_res = nullptr; h->usage_res_cells = 0;
+      if (cudaMalloc((void **)&h->d_usage_res, std::max<size_t>(8, (size_t)Q * FR * 8)) != cudaSuccess) { cudaStreamSynchronize(h->stream); return fail(h, KB_ERR_CUDA, "cudaMalloc failed"); }
+      h->usage_res_cells = (size_t)Q * FR;
+    }
+  } else {
+    UP(cq_usage, (const i64 *)s->cq_usage, (size_t)Q * FR);
+  }
+  if (!delta) h->usage_res_valid = false;  // a full table supersedes whatever was resident
   UP(wl_cq, s->wl_cq, W); UP(wl_priority, s->wl_priority, W); UP(wl_ts, (const i64 *)s->wl_ts, W); UP(wl_uid, (const i64 *)s->wl_uid, W);
   UP(wl_last_gen, (const i64 *)s->wl_last_gen, W); UP(wl_ps_start, s->wl_ps_start, W + 1);
   UP(ps_req, (const i64 *)s->ps_req, P * R); UP(ps_req_mask, s->ps_req_mask, P); UP(ps_count, s->ps_count, P);
@@ -670,6 +711,19 @@ static int32_t upload_impl(kb_handle *h, const kb_snapshot *s, bool sync) {
       *t.dst = d;
       if (t.bytes) { CUDA_TRY(h, cudaMemcpyAsync(d, t.src, t.bytes, cudaMemcpyHostToDevice, h->stream)); bytes += (int64_t)t.bytes; }
     }
+  }
+  if (delta) {
+    D.cq_usage = h->d_usage_res;
+    const int nd = s->n_usage_delta;
+    if (nd > 0) k_usage_patch<<<(unsigned)(((size_t)nd * FR + 255) / 256), 256, 0, h->stream>>>(h->d_usage_res, d_delta_cq, d_delta_rows, nd, FR);
+  } else if (keep_usage) {
+    if ((size_t)Q * FR) {
+      if (!s->cq_usage) { cudaStreamSynchronize(h->stream); return fail(h, KB_ERR_INVALID, "null table with non-zero length"); }
+      CUDA_TRY(h, cudaMemcpyAsync(h->d_usage_res, s->cq_usage, (size_t)Q * FR * 8, cudaMemcpyHostToDevice, h->stream));
+      bytes += (int64_t)Q * FR * 8;
+    }
+    D.cq_usage = h->d_usage_res;
+    h->usage_res_valid = s->static_generation != 0; h->usage_res_gen = s->static_generation;
   }
   CUDA_TRY(h, cudaEventRecord(h->ev1, h->stream));
   rc = build_dynamic(h, s);

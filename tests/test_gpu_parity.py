@@ -461,3 +461,45 @@ def test_fused_flat_kernels(ev, monkeypatch, make, v1):
         monkeypatch.setenv("KB_FUSED_V1", "1")
     snap = make()
     assert_cycle_equal(ev.run_cycle(snap), oracle.run_cycle(snap))
+
+
+def test_incremental_usage_rows(ev):
+    """kb_snapshot.usage_delta_* (SURVEY f2): after one call that leaves the usage table resident (KB_F_USAGE_RESIDENT),
+    cycles that pass only the changed ClusterQueue rows decide exactly like cycles that pass the full table."""
+    from kueue_b200 import native
+    rng = np.random.default_rng(17)
+    base = synth.make_snapshot(3, W=3000, Q=300, heads="one_per_cq")
+    base.static_generation = 41
+    base.flags |= abi.F_USAGE_RESIDENT
+    assert_cycle_equal(ev.run_cycle(base), oracle.run_cycle(base))
+    usage = np.array(base.arrays["cq_usage"]).reshape(base.n_cq, base.n_fr).copy()
+    for step in range(3):
+        dirty = np.sort(rng.choice(base.n_cq, size=[40, 1, 300][step], replace=False)).astype(np.int32)
+        usage[dirty] = (usage[dirty] * rng.uniform(0.3, 1.4, (len(dirty), base.n_fr))).astype(np.int64)
+        full = synth.make_snapshot(3, W=3000, Q=300, heads="one_per_cq")   # what the oracle sees: the whole patched table
+        full.set("cq_usage", usage)
+        inc = synth.make_snapshot(3, W=3000, Q=300, heads="one_per_cq")    # what the library gets: only the rows
+        inc.static_generation = 41
+        inc.set("usage_delta_cq", dirty); inc.set("usage_delta_rows", usage[dirty])
+        inc.arrays["cq_usage"] = np.zeros(0, np.int64)                     # not read
+        got = ev.run_cycle(inc, abi.CycleOut(full))
+        assert_cycle_equal(got, oracle.run_cycle(full))
+    # an empty delta list re-evaluates the resident table
+    inc = synth.make_snapshot(3, W=3000, Q=300, heads="one_per_cq"); inc.static_generation = 41
+    inc.set("usage_delta_cq", np.zeros(0, np.int32)); inc.set("usage_delta_rows", np.zeros(0, np.int64))
+    inc.arrays["cq_usage"] = np.zeros(0, np.int64)
+    assert_cycle_equal(ev.run_cycle(inc, abi.CycleOut(full)), oracle.run_cycle(full))
+    # errors: a duplicate row, a stale generation, no resident table
+    bad = synth.make_snapshot(3, W=3000, Q=300, heads="one_per_cq"); bad.static_generation = 41
+    bad.set("usage_delta_cq", np.array([5, 5], np.int32)); bad.set("usage_delta_rows", usage[[5, 5]])
+    with pytest.raises(native.KueueB200Error):
+        ev.run_cycle(bad)
+    bad.static_generation = 42
+    bad.set("usage_delta_cq", np.array([5], np.int32)); bad.set("usage_delta_rows", usage[[5]])
+    with pytest.raises(native.KueueB200Error):
+        ev.run_cycle(bad)
+    plain = synth.make_snapshot(3, W=3000, Q=300, heads="one_per_cq"); plain.static_generation = 41
+    ev.run_cycle(plain)                                 # a full table without the hint drops the resident one
+    bad.static_generation = 41
+    with pytest.raises(native.KueueB200Error):
+        ev.run_cycle(bad)
