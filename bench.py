@@ -78,7 +78,7 @@ def algorithmic_bytes(snap) -> dict:
             "k_search_cells": wl_in + nodes, "k_nominate_walk": wl_in + wl_out + nodes,
             "k_fair_prep": N * FR * 16 + N * R * 16, "k_drain": W * 64, "k_tas": 0,
             # fused per-root cycle: nominal / limits / ClusterQueue usage in, usage out, entries in, assignments + decisions out
-            "k_cycle_root": N * FR * 40 + N * 16 + wl_in + wl_out + W * 5,
+            "k_cycle_flat": N * FR * 40 + N * 16 + wl_in + wl_out + W * 5,
             "k_tree": N * FR * 64 + N * 16, "k_lone": N * FR * 64,
             "k_rank": W * 36, "k_scatter": W * 72, "k_scan_roots": N * 8,
             "k_admit": W * (P * R * 9 + 16) + N * FR * 40 + W * 5,
@@ -361,6 +361,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-drain", action="store_true")
     ap.add_argument("--scaling", default=None, choices=["weak", "strong"])
+    ap.add_argument("--l2", default="rotate", choices=["rotate", "flush"],
+                    help="how inputs are kept out of L2 between timed steps: rotate = device-resident copies of the snapshot "
+                         "whose total exceeds L2, used round-robin; flush = a 512 MiB buffer is written before every step")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -418,28 +421,55 @@ def main():
         torch.cuda.synchronize()
 
     # ---- resident-input throughput (value) ----
+    # Inputs must not be L2-resident when a timed step starts.  Default (--l2 rotate): the snapshot is uploaded into
+    # several evaluators (own device tables each, static ones included) whose total size exceeds L2 (126 MB), and the
+    # steps walk them round-robin, so a step's tables were last touched more than an L2 ago; the kernels' code stays
+    # where a scheduler that runs cycle after cycle has it.  --l2 flush: one copy, a 512 MiB buffer written before every
+    # step (this also evicts the code; reported as value_l2_flush next to the headline).
+    L2_BYTES = 126 << 20
     ev.upload(snap)
-    ev.set_profile(True)
-    for _ in range(max(3, args.warmup)):
-        flush.zero_(); torch.cuda.synchronize()
-        ev.cycle_resident()
+    copy_bytes = max(1, int(ev.stats().h2d_bytes))
+    n_copies = 1 if args.l2 == "flush" else min(64, int(np.ceil(1.35 * L2_BYTES / copy_bytes)) + 1)
+    evs = [ev]
+    for _ in range(n_copies - 1):
+        e2 = native.Evaluator(local_rank)
+        e2.upload(snap)
+        evs.append(e2)
+
+    def timed_pass(steps, use_flush, profile):
+        dev, lau, km = 0.0, 0, np.zeros(20)
+        for k in range(steps):
+            e = evs[k % len(evs)]
+            if use_flush:
+                flush.zero_(); torch.cuda.synchronize()
+            e.set_profile(profile)
+            e.cycle_resident()
+            st_ = e.stats()
+            dev += st_.last_cycle_gpu_ms; lau += st_.kernel_launches; km += np.array(list(st_.kernel_ms))
+            if profile:
+                e.set_profile(False)
+        return dev, lau, km
+
+    use_flush = args.l2 == "flush"
+    timed_pass(max(3, args.warmup) * len(evs) if not use_flush else max(3, args.warmup), use_flush, False)
     sampler = ClockSampler(local_rank); sampler.start()
     barrier()
     t_wall0 = time.perf_counter()
-    dev_ms = 0.0
-    kms = np.zeros(20)
-    launches = 0
-    for _ in range(args.steps):
-        flush.zero_(); torch.cuda.synchronize()  # L2 flush between timed iterations
-        ev.cycle_resident()
-        st = ev.stats()
-        dev_ms += st.last_cycle_gpu_ms
-        kms += np.array(list(st.kernel_ms))
-        launches += st.kernel_launches
+    dev_ms, launches, _ = timed_pass(args.steps, use_flush, False)
     barrier()
     wall_ms = (time.perf_counter() - t_wall0) * 1e3
     clocks = sampler.stop()
-    ev.set_profile(False)
+    # per-kernel split (roofline.kernel_ms): the same K steps once more with an event before every kernel; not part of
+    # `value` (the extra event records sit between the kernels of the timed stream)
+    _, _, kms = timed_pass(args.steps, use_flush, True)
+    # the other methodology, for comparison
+    alt_ms = None
+    if not use_flush and world == 1:
+        timed_pass(3, True, False)
+        alt_ms = timed_pass(args.steps, True, False)[0] / args.steps
+    for e2 in evs[1:]:
+        e2.close()
+    evs = [ev]
 
     # ---- end-to-end through the C-ABI with host buffers (e2e) ----
     # steady state of the controller: ClusterQueue / Cohort specs do not change between cycles, so the shim keeps
@@ -576,8 +606,12 @@ def main():
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
             "dtype": "int64", "data": "synthetic",
             "config": {"workload": WORKLOADS[args.config], "heads": "all pending workloads (batched evaluator)" if HEADS[args.config] == "all" else "one head per ClusterQueue (reference cycle)",
-                       "decisions_per_step_per_gpu": snap.n_heads, "l2": "512 MiB flush buffer written between timed steps",
-                       "timing": "CUDA events on the library stream around the cycle's kernels, summed over steps, max over ranks",
+                       "decisions_per_step_per_gpu": snap.n_heads,
+                       "l2": ("512 MiB flush buffer written between timed steps" if use_flush else
+                              f"inputs larger than L2: {n_copies} device-resident copies of the snapshot ({copy_bytes / 1e6:.1f} MB each, static tables included), "
+                              f"timed steps walk them round-robin; with a 512 MiB flush before every step instead (evicts the kernel code as well): "
+                              + (f"{alt_ms:.4f} ms/step" if alt_ms else "n/a")),
+                       "timing": "CUDA events on the library stream around the cycle's kernels, summed over steps, max over ranks; kernel_ms_per_step from a second pass of the same steps with an event before every kernel",
                        "wall_ms_per_step_incl_flush": wall_ms / args.steps,
                        "e2e_static_tables": "quota / policy / topology tables uploaded once (static_generation constant), "
                                             "usage + entries + admitted workloads copied every step",

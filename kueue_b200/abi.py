@@ -104,7 +104,7 @@ class kb_stats(C.Structure):
 
 
 KERNEL_NAMES = ["k_tree", "k_lone", "k_nominate", "k_scan_roots", "k_scatter", "k_admit", "k_rank", "k_nominate_search_fair",
-                "k_rank_admitted", "k_search_tables", "k_search_cells", "k_nominate_walk", "k_fair_prep", "k_drain", "k_tas", "k_cycle_root", "k_tas_leaf", "k_tas_reduce", "k_tas_select", "-"]
+                "k_rank_admitted", "k_search_tables", "k_search_cells", "k_nominate_walk", "k_fair_prep", "k_drain", "k_tas", "k_cycle_flat", "k_tas_leaf", "k_tas_reduce", "k_tas_select", "-"]
 
 
 class kb_drain_out(C.Structure):

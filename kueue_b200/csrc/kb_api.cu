@@ -599,6 +599,8 @@ static int32_t upload_impl(kb_handle *h, const kb_snapshot *s, bool sync) {
     sneed(h->sn_node.size(), 4); sneed(h->slot_base.size(), 4); sneed(h->nd_tin.size(), 4); sneed(h->nd_tout.size(), 4);
     sneed(h->cq_path.size(), 4); sneed(h->cq_plen.size(), 4);
     sneed(h->tree_blob.size(), 1); sneed(h->tree_blob_off.size(), 4);
+    const size_t tl_cells = h->tree_nodes.size() * (size_t)FR;
+    sneed(tl_cells, 8); sneed(tl_cells, 8); sneed(tl_cells, 8);
     if (!h->sarena.reserve(stot + 4096)) return fail(h, KB_ERR_CUDA, "cudaMalloc failed");
     h->sarena.reset();
 #define SUP(field, src, n) CUDA_TRY(h, up(h, h->sarena, D.field, src, (size_t)(n), &bytes))
@@ -621,6 +623,13 @@ static int32_t upload_impl(kb_handle *h, const kb_snapshot *s, bool sync) {
     SUP(nd_tin, h->nd_tin.data(), h->nd_tin.size()); SUP(nd_tout, h->nd_tout.data(), h->nd_tout.size());
     SUP(cq_path, h->cq_path.data(), h->cq_path.size()); SUP(cq_plen, h->cq_plen.data(), h->cq_plen.size());
     SUP(tree_blob, h->tree_blob.data(), h->tree_blob.size()); SUP(tree_blob_off, h->tree_blob_off.data(), h->tree_blob_off.size());
+    D.tl_nominal = D.tl_blimit = D.tl_llimit = nullptr; D.tl_usage = nullptr;
+    if (tl_cells && tl_cells < (size_t)INT32_MAX) {  // quota tables in tree-local row order (k_cycle_flat's bulk staging)
+      i64 *tn = h->sarena.take<i64>(tl_cells), *tb_ = h->sarena.take<i64>(tl_cells), *tl_ = h->sarena.take<i64>(tl_cells);
+      D.FR = FR; D.Q = Q;
+      k_tl_static<<<(unsigned)((tl_cells + 255) / 256), 256, 0, h->stream>>>(D, tn, tb_, tl_, (int)tl_cells);
+      D.tl_nominal = tn; D.tl_blimit = tb_; D.tl_llimit = tl_;
+    }
     D.path_stride = h->path_stride;
 #undef SUP
     memcpy(h->s_dims, dims, sizeof(dims));
@@ -739,7 +748,7 @@ static int32_t upload_impl(kb_handle *h, const kb_snapshot *s, bool sync) {
   need(W, 4); need(W, 4); need(W, 8); need(W, 8); need(W, 8); need(W + 1, 4);
   need(P * R, 8); need(P, 4); need(P, 4); need(P, 4); need(P, 8); need(P * R, 1);
   need(A, 4); need(A, 4); need(A, 8); need(A, 8); need(A, 8); need(A, 1); need(A + 1, 4); need(AUc, 4); need(AUc, 8);
-  need(H, 4); need(W, 1); need(W, 8); need(P, 4); need(Q, 4); need(h->tree_nodes.size() + 1, 16); need(256, 1);
+  need(H, 4); need(W, 1); need(W, 8); need(P, 4); need(Q, 4); need(h->tree_nodes.size() + 1, 16); need(256, 1); need(h->tree_nodes.size() * (size_t)FR, 8);
   need(Q + 1, 4); need(A, 4); need(A, 4); need(Q, 4); need(nroots, 4);
   need(nroots + 2, 4); need(Q + 2, 4); need(A, 8); need(A, 8); need(A, 4); need(A, 4);
   size_t rk_temp_bytes = 0;
@@ -852,9 +861,10 @@ static int32_t upload_impl(kb_handle *h, const kb_snapshot *s, bool sync) {
                   (!(s->flags & KB_F_FAIR_SHARING) || all_flat) && getenv("KB_NO_FUSED") == nullptr;
     // k_cycle_flat: every tree flat, FR <= 64, the relocated copy of the largest root fits shared memory
     h->d_cq_rec = h->arena.take<int4>(h->tree_nodes.size() + 1); D.cq_rec = h->d_cq_rec;
+    D.tl_usage = D.tl_nominal ? h->arena.take<i64>(h->tree_nodes.size() * (size_t)FR) : nullptr;
     h->flat_rcap = (int)std::min<size_t>((size_t)1 << 20, nnm * (size_t)std::max(1, h->max_head_podsets));
     h->flat_smem = flat_layout((int)nnm, FR, R, h->flat_rcap, h->max_blob_bytes).total;
-    h->flat_on = h->fused_on && all_flat && FR <= 64 && h->flat_smem <= 227 * 1024 && getenv("KB_FUSED_V1") == nullptr;
+    h->flat_on = h->fused_on && all_flat && FR <= 64 && h->flat_smem + 2048 <= 227 * 1024 && getenv("KB_FUSED_V1") == nullptr;
     h->flat_on = h->flat_on && h->max_head_podsets < 65536;
     if (h->fused_on && !h->flat_on && !h->drain_mode) {
       CUDA_TRY(h, cudaMemsetAsync(h->d_cq_entry, 0xff, sizeof(int32_t) * (size_t)Q, h->stream));
@@ -929,8 +939,9 @@ static int32_t upload_impl(kb_handle *h, const kb_snapshot *s, bool sync) {
     int32_t rc2 = flat_rec_stamp(h);
     if (rc2 != KB_OK) return rc2;
     const size_t fill_words = 3 * pad256(P * R) / 4;
-    const size_t nthr = std::max(std::max(H, fill_words), std::max(P, (size_t)32));
-    k_flat_prep<<<(unsigned)((nthr + 255) / 256), 256, 0, h->stream>>>(D, h->d_cq_rec, (int)fill_words, (int)P);
+    const size_t tlc = D.tl_usage ? h->tree_nodes.size() * (size_t)FR : 0;
+    const size_t nthr = std::max(std::max(std::max(H, fill_words), std::max(P, (size_t)32)), tlc);
+    k_flat_prep<<<(unsigned)((nthr + 255) / 256), 256, 0, h->stream>>>(D, h->d_cq_rec, (int)fill_words, (int)P, (int)tlc);
     h->hdr_clean = true;
   } else {
     // rows of workloads that are not heads stay at -1
@@ -1076,7 +1087,8 @@ static int32_t cycle_enqueue(kb_handle *h, bool hdr_copy = true) {
       if (h->flat_on) {
         int32_t rc2 = flat_rec_stamp(h);
         if (rc2 != KB_OK) return rc2;
-        k_cq_rec<<<(D.H + 255) / 256, 256, 0, h->stream>>>(D, h->d_cq_rec); launches++;
+        const size_t tlc = D.tl_usage ? h->tree_nodes.size() * (size_t)D.FR : 0;
+        k_cq_rec<<<(unsigned)((std::max<size_t>((size_t)D.H, tlc) + 255) / 256), 256, 0, h->stream>>>(D, h->d_cq_rec, (int)tlc); launches++;
       } else {
         CUDA_TRY(h, cudaMemsetAsync(h->d_cq_entry, 0xff, sizeof(int32_t) * (size_t)D.Q, h->stream));
         k_cq_entry<<<(D.H + 255) / 256, 256, 0, h->stream>>>(D, h->d_cq_entry); launches++;

@@ -19,7 +19,7 @@
 
 struct FlatLay {  // byte offsets into the dynamic shared memory of k_cycle_flat (computed on the host, passed by value)
   uint32_t u, sub, lq, bl, av, pot, over, lend, blob, n_e, n_wl, n_ps0, n_psn, e_gid, e_cq, e_prio, e_ident, e_psn, e_wl, e_ps0, e_ts, e_lg, e_qr,
-      e_mode, e_borrow, e_rank, sorted, m_sorted, d_sorted, r_gid, r_count, r_min, r_mask, r_group, r_ok, r_req, r_last, o_fl, o_md, o_tr, o_cnt, key, misc, snap, total;
+      e_mode, e_borrow, e_rank, sorted, m_sorted, d_sorted, r_gid, r_count, r_min, r_mask, r_group, r_ok, r_req, r_last, o_fl, o_md, o_tr, o_cnt, key, misc, snap, rec, total;
 };
 __host__ __device__ inline FlatLay flat_layout(int ncap, int FR, int R, int rcap, int bcap) {
   FlatLay L;
@@ -39,8 +39,9 @@ __host__ __device__ inline FlatLay flat_layout(int ncap, int FR, int R, int rcap
   L.r_group = take((size_t)rcap * 4); L.r_ok = take((size_t)rcap * 8); L.r_req = take((size_t)rcap * R * 8); L.r_last = take((size_t)rcap * R);
   L.o_fl = take((size_t)rcap * R); L.o_md = take((size_t)rcap * R); L.o_tr = take((size_t)rcap * R); L.o_cnt = take((size_t)rcap * 4);
   L.key = take((size_t)ncap * 32);
-  L.misc = take(64);
+  L.misc = take(64 + 256);
   L.snap = take(sizeof(DevSnap));
+  L.rec = take((size_t)ncap * 16);
   L.total = (uint32_t)(o < 0xffffffffu ? o : 0xffffffffu);
   return L;
 }
@@ -69,15 +70,29 @@ __device__ __forceinline__ void cq_rec_write(const DevSnap &D, int4 *rec, int e)
   const int ps0 = D.wl_ps_start[wl];
   rec[D.tree_start[slot] + D.local_idx[cq]] = make_int4(e, wl, ps0, (D.wl_ps_start[wl + 1] - ps0) | (int)(D.rec_stamp << 16));
 }
-__global__ void k_cq_rec(DevSnap D, int4 *rec) {
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e < D.H) cq_rec_write(D, rec, e);
+// usage rows into tree-local order (cohort rows zero): cell i of [tree nodes][FR]
+__device__ __forceinline__ void tl_usage_write(const DevSnap &D, int i) {
+  const int nd = D.tree_nodes[i / D.FR];
+  D.tl_usage[i] = nd < D.Q ? D.cq_usage[(size_t)nd * D.FR + i % D.FR] : 0;
+}
+__global__ void k_cq_rec(DevSnap D, int4 *rec, int tl_cells) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < D.H) cq_rec_write(D, rec, i);
+  if (i < tl_cells) tl_usage_write(D, i);
+}
+// static quota tables into tree-local row order (once per static upload)
+__global__ void k_tl_static(DevSnap D, i64 *nominal, i64 *blimit, i64 *llimit, int tl_cells) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= tl_cells) return;
+  const size_t g = (size_t)D.tree_nodes[i / D.FR] * D.FR + i % D.FR;
+  nominal[i] = D.nominal[g]; blimit[i] = D.blimit[g]; llimit[i] = D.llimit[g];
 }
 // Everything the cycle needs prepared on the device, in one launch: head records, result rows of workloads that are
 // not heads (-1 / 0), cleared cycle header.
-__global__ void k_flat_prep(DevSnap D, int4 *rec, int fill_words, int P) {
+__global__ void k_flat_prep(DevSnap D, int4 *rec, int fill_words, int P, int tl_cells) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < D.H) cq_rec_write(D, rec, i);
+  if (i < tl_cells) tl_usage_write(D, i);
   if (i < fill_words) ((uint32_t *)D.ps_flavor)[i] = 0xffffffffu;  // flavor, res_mode, tried are adjacent (out_layout)
   if (i < P) D.ps_count_out[i] = 0;
   if (i < 32) D.status[i] = 0;
@@ -86,6 +101,23 @@ __global__ void k_flat_prep(DevSnap D, int4 *rec, int fill_words, int P) {
 __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
   unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+// 1-D bulk copies (the TMA engine, no tensor map) completing on an mbarrier
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n\tfence.mbarrier_init.release.cluster;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gsrc, unsigned bytes, unsigned long long *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long *bar, unsigned parity) {
+  unsigned ok;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+               : "=r"(ok) : "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+  return ok != 0;
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory"); }
 
@@ -186,6 +218,32 @@ __global__ void __launch_bounds__(KB_FLAT_THREADS) k_cycle_flat(const __grid_con
   const int nn = D.tree_start[t + 1] - ts0;
   const int32_t *nodes = D.tree_nodes + ts0;
   const int tb = nn * FR;
+  int4 *s_rec = (int4 *)(smem_raw + Y.rec);
+  __shared__ __align__(8) unsigned long long s_mbar;
+  // Tree-local tables (DevSnap::tl_*): a root's rows are contiguous -> one bulk copy per table, issued by one thread,
+  // completion counted in bytes on an mbarrier.  Otherwise (odd rows: 16 B alignment) per-thread cp.async gathers.
+  const bool bulk = D.tl_nominal != nullptr && (FR & 1) == 0;
+  if (bulk) {
+    if (tid == 0) mbar_init(&s_mbar, 1);
+    __syncthreads();
+    if (tid == 0) {
+      const int b0 = D.tree_blob_off[t], bn = D.tree_blob_off[t + 1] - b0;  // static block of the tree (multiple of 16 B)
+      const unsigned tbytes = (unsigned)tb * 8u;
+      mbar_expect_tx(&s_mbar, 4u * tbytes + (unsigned)bn + (unsigned)nn * 16u);
+      const size_t r0 = (size_t)ts0 * FR;
+      bulk_g2s(s_sub, D.tl_nominal + r0, tbytes, &s_mbar);  // SubtreeQuota = Nominal (updateCohortResourceNode resource_node.go:184-190)
+      bulk_g2s(s_bl, D.tl_blimit + r0, tbytes, &s_mbar);
+      bulk_g2s(s_lq, D.tl_llimit + r0, tbytes, &s_mbar);    // lending limit for now; localQuota once SubtreeQuota is final
+      bulk_g2s(s_u, D.tl_usage + r0, tbytes, &s_mbar);      // ClusterQueue usage, zero rows for cohorts
+      bulk_g2s(s_blob, D.tree_blob + b0, (unsigned)bn, &s_mbar);
+      bulk_g2s(s_rec, D.cq_rec + ts0, (unsigned)nn * 16u, &s_mbar);
+    }
+    if (tid == nthreads - 1) *(DevSnap *)(smem_raw + Y.snap) = D;  // bulk of the relocated view (patched below), under the load latency
+    {
+      unsigned spins = 0;
+      while (!mbar_try_wait(&s_mbar, 0)) if (++spins > (1u << 24)) __trap();  // a lost copy must not hang the device
+    }
+  } else {
   {
     const int b0 = D.tree_blob_off[t], bn = D.tree_blob_off[t + 1] - b0;  // static block of the tree (multiple of 16 B)
     for (int c = tid * 16; c < bn; c += nthreads * 16) cp_async16(s_blob + c, D.tree_blob + b0 + c);
@@ -196,9 +254,9 @@ __global__ void __launch_bounds__(KB_FLAT_THREADS) k_cycle_flat(const __grid_con
       const int i = c << 1;
       const int nd = nodes[row_of(i)];
       const size_t g = (size_t)nd * FR + col_of(i);
-      cp_async16(s_sub + i, D.nominal + g);   // SubtreeQuota = Nominal (updateCohortResourceNode resource_node.go:184-190)
+      cp_async16(s_sub + i, D.nominal + g);
       cp_async16(s_bl + i, D.blimit + g);
-      cp_async16(s_lq + i, D.llimit + g);     // lending limit for now; localQuota once SubtreeQuota is final
+      cp_async16(s_lq + i, D.llimit + g);
       if (nd < D.Q) cp_async16(s_u + i, D.cq_usage + g);
       else { s_u[i] = 0; s_u[i + 1] = 0; }
     }
@@ -210,13 +268,27 @@ __global__ void __launch_bounds__(KB_FLAT_THREADS) k_cycle_flat(const __grid_con
       s_u[i] = nd < D.Q ? D.cq_usage[g] : 0;
     }
   }
-  for (int h = tid; h < nn; h += nthreads) {  // the head of every ClusterQueue of the tree (record written by k_cq_rec)
-    const int4 rc = D.cq_rec[ts0 + h];
+  for (int h = tid; h < nn; h += nthreads) s_rec[h] = D.cq_rec[ts0 + h];
+  if (tid == nthreads - 1) *(DevSnap *)(smem_raw + Y.snap) = D;
+  cp_async_wait_all();
+  __syncthreads();
+  }
+  for (int h = tid; h < nn; h += nthreads) {  // the head of every ClusterQueue of the tree (record written by k_flat_prep / k_cq_rec)
+    const int4 rc = s_rec[h];
     const bool live = ((unsigned)rc.w >> 16) == D.rec_stamp;  // written for this cycle
     n_e[h] = live ? rc.x : -1; n_wl[h] = rc.y; n_ps0[h] = rc.z; n_psn[h] = live ? (rc.w & 0xffff) : 0;
+    if (live) {  // the entry's per-cycle records are gathered in phase 2: request their lines now
+      auto touch = [](const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); };
+      const int wl = rc.y, row = rc.z;
+      touch(D.wl_priority + wl); touch(D.wl_ts + wl); touch(D.wl_last_gen + wl);
+      if (D.wl_has_qr) touch(D.wl_has_qr + wl);
+      if ((rc.w & 0xffff) > 0) {
+        touch(D.ps_count + row); touch(D.ps_min_count + row); touch(D.ps_req_mask + row); touch(D.ps_flavor_ok + row);
+        touch(D.ps_req + (size_t)row * R); touch(D.ps_last_tried + (size_t)row * R);
+        if (D.ps_group) touch(D.ps_group + row);
+      }
+    }
   }
-  if (tid == nthreads - 1) *(DevSnap *)(smem_raw + Y.snap) = D;  // bulk of the relocated view (patched below), under the load latency
-  cp_async_wait_all();
   __syncthreads();
   KB_FPHASE(0);
   KB_PP(1, 0);
@@ -226,23 +298,36 @@ __global__ void __launch_bounds__(KB_FLAT_THREADS) k_cycle_flat(const __grid_con
 
   // ---- 1. entries of the root in ClusterQueue (= local handle) order + local podset-row numbering (warp 0), and the
   // bottom-up pass of the flat tree for everyone: accumulateFromChild resource_node.go:210-217, children -> root
-  if (warp == 0) {
-    int cnt = 0, rows = 0;
-    for (int h0 = 0; h0 < nn; h0 += 32) {
-      const int h = h0 + lane;
+  // one warp per 32 nodes: ballot + warp scan, then the warps' totals are scanned (chunks of 32 warps, carried)
+  {
+    const int nw = nthreads >> 5;
+    int *w_cnt = s_misc + 4, *w_rows = s_misc + 4 + 32;  // [32] each (misc is 64 + 256 B)
+    int cnt_base = 0, rows_base = 0;
+    for (int c0 = 0; c0 < nn; c0 += nthreads) {
+      const int h = c0 + tid;
       const int e = h < nn ? n_e[h] : -1;
       const int pn = e >= 0 ? n_psn[h] : 0;
       const unsigned m = __ballot_sync(0xffffffffu, e >= 0);
       int incl = pn;  // inclusive scan of the row counts over the lanes
       for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
-      if (e >= 0) {
-        const int i = cnt + __popc(m & ((1u << lane) - 1));
-        e_gid[i] = e; e_cq[i] = h; e_ident[i] = i; e_wl[i] = n_wl[h]; e_ps0[i] = n_ps0[h]; e_psn[i] = rows + incl - pn;
+      if (lane == 31) { w_cnt[warp] = __popc(m); w_rows[warp] = incl; }
+      __syncthreads();
+      int pc = 0, pr = 0, tc = 0, tr = 0;  // totals of the warps before mine / of all warps of this chunk
+      {
+        const int wc = lane < nw ? w_cnt[lane] : 0, wr = lane < nw ? w_rows[lane] : 0;
+        int ic = wc, ir = wr;
+        for (int o = 1; o < 32; o <<= 1) { int a = __shfl_up_sync(0xffffffffu, ic, o), b = __shfl_up_sync(0xffffffffu, ir, o); if (lane >= o) { ic += a; ir += b; } }
+        pc = __shfl_sync(0xffffffffu, ic - wc, warp & 31); pr = __shfl_sync(0xffffffffu, ir - wr, warp & 31);
+        tc = __shfl_sync(0xffffffffu, ic, 31); tr = __shfl_sync(0xffffffffu, ir, 31);
       }
-      cnt += __popc(m);
-      rows += __shfl_sync(0xffffffffu, incl, 31);
+      if (e >= 0) {
+        const int i = cnt_base + pc + __popc(m & ((1u << lane) - 1));
+        e_gid[i] = e; e_cq[i] = h; e_ident[i] = i; e_wl[i] = n_wl[h]; e_ps0[i] = n_ps0[h]; e_psn[i] = rows_base + pr + incl - pn;
+      }
+      cnt_base += tc; rows_base += tr;
+      if (c0 + nthreads < nn) __syncthreads();  // w_cnt / w_rows are rewritten by the next chunk
     }
-    if (lane == 0) { e_psn[cnt] = rows; s_misc[0] = cnt; s_misc[1] = rows; }
+    if (tid == 0) { e_psn[cnt_base] = rows_base; s_misc[0] = cnt_base; s_misc[1] = rows_base; }
   }
   KB_PP(1, 1);
   // the relocated snapshot: every table the shared device functions read, in local numbering.  It lives in shared

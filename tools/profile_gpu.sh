@@ -4,7 +4,7 @@
 cfg=${1:-3}; tag=${2:-r02}
 mkdir -p gpurun_out
 case $cfg in
-  3) rx='k_cycle_root'; skip=4; cnt=2;;
+  3) rx='k_cycle_flat|k_cycle_root'; skip=6; cnt=2;;
   2) rx='k_lone|k_nominate|k_scan_roots|k_scatter|k_rank|k_admit_lone'; skip=24; cnt=6;;
   4) rx='k_rank_keys|k_columns|k_frl_fill|k_root_recs|k_cells_mark|k_search_cells_grouped|k_nominate_walk|k_admit|k_tree|k_rank'; skip=60; cnt=16;;
   5) rx='k_tas_leaf|k_tas_reduce|k_tas_select'; skip=12; cnt=4;;

@@ -61,5 +61,7 @@ tj = os.path.join(ROOT, "profiles", "traffic.json")
 t = json.load(open(tj)) if os.path.exists(tj) else {}
 t[cfg] = {k: sum(v) / len(v) for k, v in traffic.items()}
 t[cfg]["k_nominate"] = t[cfg].get("k_nominate_coop", t[cfg].get("k_nominate"))
+if "k_cycle_flat" not in t[cfg] and "k_cycle_root" in t[cfg]:
+    t[cfg]["k_cycle_flat"] = t[cfg]["k_cycle_root"]  # kb_stats slot of the fused per-root cycle: whichever of the two kernels ran
 json.dump(t, open(tj, "w"), indent=1, sort_keys=True)
 print(open(out).read())
