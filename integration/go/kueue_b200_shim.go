@@ -334,6 +334,10 @@ func (s *Scheduler) flatten(snap *schdcache.Snapshot, heads []workload.Info, gen
 	c.parent, c.fair_weight = (*C.int32_t)(&parent[0]), (*C.double)(&weight[0])
 	c.nominal, c.borrow_limit, c.lend_limit = (*C.int64_t)(&nominal[0]), (*C.int64_t)(&blimit[0]), (*C.int64_t)(&llimit[0])
 	c.cq_usage = (*C.int64_t)(&usage[0])
+	// Incremental form (kb_snapshot.usage_delta_*, INTEGRATION.md "Usage deltas"): once a call carried the full table with
+	// KB_F_USAGE_RESIDENT, a cache that tracks which ClusterQueues it touched since the previous cycle passes only those rows:
+	//   c.n_usage_delta, c.usage_delta_cq, c.usage_delta_rows = n, &dirtyCQ[0], &dirtyRows[0]   (c.cq_usage may stay nil)
+	// This shim always sends the full table.
 	c.cq_within_cq, c.cq_reclaim_within, c.cq_borrow_within = (*C.uint8_t)(&within[0]), (*C.uint8_t)(&reclaim[0]), (*C.uint8_t)(&bwc[0])
 	c.cq_has_bwc_threshold, c.cq_bwc_threshold = (*C.uint8_t)(&hasThr[0]), (*C.int32_t)(&thr[0])
 	c.cq_when_can_borrow, c.cq_when_can_preempt, c.cq_preference = (*C.uint8_t)(&wcb[0]), (*C.uint8_t)(&wcp[0]), (*C.uint8_t)(&pref[0])
