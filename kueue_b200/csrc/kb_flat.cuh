@@ -182,6 +182,9 @@ __device__ __forceinline__ int flat_decision(int mode, const uint32_t *ok_bits, 
 }
 
 #define KB_FLAT_THREADS 1024
+#ifndef KB_FLAT_NG
+#define KB_FLAT_NG 8  // lanes per entry in the nominate phase
+#endif
 __global__ void __launch_bounds__(KB_FLAT_THREADS) k_cycle_flat(const __grid_constant__ DevSnap D, const __grid_constant__ FlatLay Y) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int FR = D.FR, R = D.R;
@@ -467,17 +470,19 @@ __global__ void __launch_bounds__(KB_FLAT_THREADS) k_cycle_flat(const __grid_con
     }
   }
   KB_PP(2, 1);
-  // ---- 5. nominate: KB_NG lanes per entry (get_assignments_coop) on the relocated tables
+  // ---- 5. nominate: KB_FLAT_NG lanes per entry (get_assignments_coop) on the relocated tables.  A round evaluates
+  // KB_FLAT_NG flavors of a resource group at once; the walk usually stops in its first round, so fewer lanes per entry
+  // mean fewer warps competing for the SM's issue slots at the same chain length.
   {
-    const int glane = lane % KB_NG, gbase = lane - glane;
-    const unsigned gmask = ((1u << KB_NG) - 1u) << gbase;
-    const int groups = nthreads / KB_NG;
+    const int glane = lane % KB_FLAT_NG, gbase = lane - glane;
+    const unsigned gmask = (KB_FLAT_NG == 32 ? 0xffffffffu : ((1u << KB_FLAT_NG) - 1u)) << gbase;
+    const int groups = nthreads / KB_FLAT_NG;
     for (int i0 = 0; i0 < n; i0 += groups) {
-      const int i = i0 + tid / KB_NG;
-      if (i < n) {  // whole KB_NG-lane groups take the branch together
+      const int i = i0 + tid / KB_FLAT_NG;
+      if (i < n) {  // whole lane groups take the branch together
         bool need_search = false;
         int borrowing;
-        const int mode = get_assignments_coop(L, &need_search, i, &borrowing, gmask, gbase, glane);
+        const int mode = get_assignments_coop<KB_FLAT_NG>(L, &need_search, i, &borrowing, gmask, gbase, glane);
         if (glane == 0) { e_mode[i] = mode; e_borrow[i] = borrowing; }
       }
     }

@@ -436,6 +436,7 @@ __device__ __forceinline__ int cell_eval(const DevSnap &D, int cq, int fr, i64 a
   return PM_NOFIT;
 }
 
+template <int NG = KB_NG>  // lanes per entry (a power of two <= 32): NG flavors of a resource group are evaluated per round
 __device__ inline int assign_workload_coop(const DevSnap &D, bool *need_search, int wl, const int32_t *counts, int *borrowing_out,
                                            unsigned gmask, int gbase, int glane) {
   const int R = D.R;
@@ -494,7 +495,7 @@ __device__ inline int assign_workload_coop(const DevSnap &D, bool *need_search, 
       int idx0 = 0;
       if (fung && use_last) idx0 = D.ps_last_tried[(size_t)row * R + r0] + 1;
       bool done = false;
-      for (int base = idx0; base < nfl && !done; base += KB_NG) {
+      for (int base = idx0; base < nfl && !done; base += NG) {
         // ---- one flavor per lane ----
         int idx = base + glane;
         u64 res = 0;  // [0..2] rpm [3..9] rb [10..16] maxb [17] any_reason [18] need [19] eligible [32..47] pmask
@@ -523,7 +524,7 @@ __device__ inline int assign_workload_coop(const DevSnap &D, bool *need_search, 
           }
         }
         // ---- ordered scan over the KB_NG flavors of this round ----
-        for (int j = 0; j < KB_NG && base + j < nfl; j++) {
+        for (int j = 0; j < NG && base + j < nfl; j++) {
           u64 rj = __shfl_sync(gmask, res, gbase + j);
           int fj = __shfl_sync(gmask, myf, gbase + j);
           attempted = base + j;
@@ -589,8 +590,9 @@ __device__ inline int assign_workload_coop(const DevSnap &D, bool *need_search, 
 }
 
 // getInitialAssignments (scheduler.go:584-625) in cooperative form; targets are never produced here (deferred).
+template <int NG = KB_NG>
 __device__ inline int get_assignments_coop(const DevSnap &D, bool *need_search, int wl, int *borrowing_out, unsigned gmask, int gbase, int glane) {
-  int mode = assign_workload_coop(D, need_search, wl, nullptr, borrowing_out, gmask, gbase, glane);
+  int mode = assign_workload_coop<NG>(D, need_search, wl, nullptr, borrowing_out, gmask, gbase, glane);
   if (mode == KB_MODE_FIT) return mode;
   if (mode == KB_MODE_PREEMPT && candidates_possible(D, D.wl_cq[wl])) *need_search = true;  // GetTargets might find targets
   if (!(D.flags & KB_F_PARTIAL_ADMISSION)) return mode;
@@ -616,16 +618,16 @@ __device__ inline int get_assignments_coop(const DevSnap &D, bool *need_search, 
     fill(mid);
     int b;
     __syncwarp(gmask);
-    int m = assign_workload_coop(D, need_search, wl, counts, &b, gmask, gbase, glane);
+    int m = assign_workload_coop<NG>(D, need_search, wl, counts, &b, gmask, gbase, glane);
     bool good = m == KB_MODE_FIT;  // Preempt with targets is only decidable by the search kernel (entry already flagged)
     if (good) { last_good = mid; hi = mid; } else lo = mid + 1;
   }
   __syncwarp(gmask);
   if (last_good >= 0 && lo == last_good) {
     fill(last_good);
-    return assign_workload_coop(D, need_search, wl, counts, borrowing_out, gmask, gbase, glane);
+    return assign_workload_coop<NG>(D, need_search, wl, counts, borrowing_out, gmask, gbase, glane);
   }
-  return assign_workload_coop(D, need_search, wl, nullptr, borrowing_out, gmask, gbase, glane);
+  return assign_workload_coop<NG>(D, need_search, wl, nullptr, borrowing_out, gmask, gbase, glane);
 }
 
 __global__ void __launch_bounds__(128) k_nominate_coop(DevSnap D) {
