@@ -483,3 +483,53 @@ def flatten(cqs: Sequence[MakeClusterQueue], cohorts: Sequence[MakeCohort] = (),
         snap.set("heads", [idx.pending.index(h) for h in heads])
     snap.finalize()
     return snap, idx
+
+
+class UsageTracker:
+    """Host side of the incremental snapshot (`kb_snapshot.usage_delta_*`): what a scheduler cache that
+    maintains the flat usage table does between two cycles.  The reference cache changes a ClusterQueue's usage only in
+    `AddOrUpdateWorkload` / `DeleteWorkload` / `AssumeWorkload` / `ForgetWorkload` (pkg/cache/scheduler/cache.go:619-711
+    -> clusterqueue.go addOrUpdateWorkload / deleteWorkload -> updateWorkloadUsage); each of them calls `touch(cq)` here.
+    `prepare(snap)` then turns the next snapshot into its cheapest valid form: the full table (first call, or after the
+    static tables changed) tagged KB_F_USAGE_RESIDENT, or only the touched rows."""
+
+    def __init__(self):
+        self._gen = None       # static_generation the device-resident table belongs to
+        self._dims = None
+        self._dirty: set[int] = set()
+        self._last = None      # host copy of what the device holds (to make `touch` optional: rows are also diffed)
+
+    def touch(self, cq_index: int) -> None:
+        self._dirty.add(int(cq_index))
+
+    def reset(self) -> None:
+        """After any library error (the shim falls back to the stock cycle and the resident table is unknown)."""
+        self._gen = None; self._dirty.clear(); self._last = None
+
+    def prepare(self, snap: "abi.FlatSnapshot", diff: bool = True) -> "abi.FlatSnapshot":
+        import numpy as np
+        Q, FR = snap.n_cq, snap.n_fr
+        usage = np.asarray(snap.arrays["cq_usage"], dtype=np.int64).reshape(Q, FR)
+        dims = (Q, snap.n_cohort, snap.n_flavor, snap.n_resource)
+        fresh = snap.static_generation == 0 or self._gen != snap.static_generation or self._dims != dims or self._last is None
+        if fresh:
+            snap.arrays.pop("usage_delta_cq", None); snap.arrays.pop("usage_delta_rows", None)
+            snap.__dict__["_struct"] = None
+            if snap.static_generation != 0:  # the library keeps a usage table only next to resident static tables
+                snap.flags |= abi.F_USAGE_RESIDENT
+                self._gen, self._dims, self._last = snap.static_generation, dims, usage.copy()
+            else:
+                snap.flags &= ~abi.F_USAGE_RESIDENT
+                self._gen = None
+            self._dirty.clear()
+            return snap
+        rows = set(self._dirty)
+        if diff:  # rows the caller forgot to touch would silently go stale on the device: diff against the mirror
+            rows |= set(np.flatnonzero((usage != self._last).any(axis=1)).tolist())
+        idx = np.array(sorted(rows), dtype=np.int32)
+        snap.set("usage_delta_cq", idx)
+        snap.set("usage_delta_rows", usage[idx] if len(idx) else np.zeros((0, FR), np.int64))
+        snap.flags &= ~abi.F_USAGE_RESIDENT
+        self._last[idx] = usage[idx]
+        self._dirty.clear()
+        return snap

@@ -30,6 +30,7 @@ def test_struct_layout_matches_c():
 int main(void) {
   printf("%zu %zu %zu %zu %zu\n", sizeof(kb_snapshot), sizeof(kb_cycle_out), sizeof(kb_tree_out), sizeof(kb_stats), sizeof(kb_config));
   printf("%zu %zu %zu %zu\n", offsetof(kb_snapshot, now_ns), offsetof(kb_snapshot, parent), offsetof(kb_snapshot, heads), offsetof(kb_cycle_out, node_usage));
+  printf("%zu %zu %zu %zu\n", offsetof(kb_snapshot, static_generation), offsetof(kb_snapshot, n_usage_delta), offsetof(kb_snapshot, usage_delta_cq), offsetof(kb_snapshot, usage_delta_rows));
   return 0;
 }'''
     with tempfile.TemporaryDirectory() as d:
@@ -41,8 +42,10 @@ int main(void) {
     sizes = [int(x) for x in out]
     assert sizes[:5] == [C.sizeof(abi.kb_snapshot), C.sizeof(abi.kb_cycle_out), C.sizeof(abi.kb_tree_out),
                          C.sizeof(abi.kb_stats), C.sizeof(abi.kb_config)]
-    assert sizes[5:] == [abi.kb_snapshot.now_ns.offset, abi.kb_snapshot.parent.offset, abi.kb_snapshot.heads.offset,
-                         abi.kb_cycle_out.node_usage.offset]
+    assert sizes[5:9] == [abi.kb_snapshot.now_ns.offset, abi.kb_snapshot.parent.offset, abi.kb_snapshot.heads.offset,
+                          abi.kb_cycle_out.node_usage.offset]
+    assert sizes[9:] == [abi.kb_snapshot.static_generation.offset, abi.kb_snapshot.n_usage_delta.offset,
+                         abi.kb_snapshot.usage_delta_cq.offset, abi.kb_snapshot.usage_delta_rows.offset]
 
 
 def test_no_device_is_a_loud_error():
