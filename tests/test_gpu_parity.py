@@ -503,3 +503,32 @@ def test_incremental_usage_rows(ev):
     bad.static_generation = 41
     with pytest.raises(native.KueueB200Error):
         ev.run_cycle(bad)
+
+
+def test_usage_tracker_drives_incremental_cycles(ev):
+    """api.UsageTracker (cache-side bookkeeping) + usage_delta_*: a sequence of cycles in which admitted workloads'
+    usage is applied between cycles decides like the oracle on the full tables, including across a spec change."""
+    from kueue_b200.api import UsageTracker
+    t = UsageTracker()
+    rng = np.random.default_rng(23)
+    mk = lambda: synth.make_snapshot(3, W=2000, Q=200, heads="one_per_cq")  # noqa: E731
+    usage = np.array(mk().arrays["cq_usage"]).reshape(200, -1).copy()
+    gen = 5
+    for cycle in range(5):
+        if cycle == 3:
+            gen = 6  # a ClusterQueue spec changed: static tables and the usage table travel again
+        full = mk(); full.set("cq_usage", usage); full.static_generation = gen
+        want = oracle.run_cycle(full)
+        sent = mk(); sent.set("cq_usage", usage); sent.static_generation = gen
+        sent = t.prepare(sent)
+        if cycle not in (0, 3):
+            assert "usage_delta_cq" in sent.arrays and not (sent.flags & abi.F_USAGE_RESIDENT)
+        assert_cycle_equal(ev.run_cycle(sent, abi.CycleOut(full)), want)
+        # the cache applies the admissions (cache.AssumeWorkload) and some workloads finish
+        adm = np.flatnonzero(want.decision == 5)
+        cqs = np.asarray(full.wl_cq)[np.asarray(full.heads)[adm]]
+        usage = np.array(want.node_usage).reshape(-1, full.n_fr)[:200].copy()
+        for c in cqs:
+            t.touch(int(c))
+        done = rng.choice(200, 7, replace=False)
+        usage[done] = (usage[done] * 0.8).astype(np.int64)   # not touched: the tracker's diff must catch them
